@@ -1,0 +1,158 @@
+/* scoresde_b200 — C ABI of the B200 (sm_100a) score-SDE sampling engine.
+ *
+ * Drop-in boundary for the native surface of yang-song/score_sde_pytorch on the
+ * predictor–corrector sampling path.  Every entry point takes plain pointers and
+ * sizes (device pointers unless noted), an explicit CUDA stream (`void*` holding
+ * a cudaStream_t; NULL = default stream), never allocates device memory per call
+ * (workspaces are sized by a query and supplied by the caller, so calls are
+ * CUDA-graph capturable) and returns 0 on success.  On failure the return value
+ * is non-zero and b200_last_error() describes it (thread-local).
+ *
+ * The reference interface each group replaces is cited as file:line relative to
+ * the reference repository.
+ */
+#ifndef SCORESDE_B200_H_
+#define SCORESDE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+/* ---- library ---------------------------------------------------------------- */
+B200_API const char* b200_last_error(void);
+B200_API int b200_version(void);                  /* 10000*major + 100*minor + patch */
+B200_API int b200_device_sm_count(int* out);      /* multiProcessorCount of the current device */
+
+/* ---- FIR resampling ----------------------------------------------------------
+ * Replaces the pybind11 op `upfirdn2d(Tensor input[major,in_h,in_w,minor], Tensor
+ * kernel[kh,kw], up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)`
+ * (op/upfirdn2d.cpp:12-19 -> op/upfirdn2d_kernel.cu:209-369).  Same tensor
+ * convention and output size rule (op/upfirdn2d.py:106-107):
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1 (likewise out_w).
+ * `kernel` is a HOST pointer to kh*kw floats (<= 64 taps).  x/y are device fp32. */
+B200_API int b200_upfirdn2d_f32(const float* x, const float* kernel_host, float* y,
+                                int major, int in_h, int in_w, int minor, int kh, int kw,
+                                int up_x, int up_y, int down_x, int down_y,
+                                int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* ---- fused bias + activation -------------------------------------------------
+ * Replaces `fused_bias_act(Tensor input, Tensor bias, Tensor refer, int act, int grad,
+ * float alpha, float scale)` (op/fused_bias_act.cpp:11-17 -> fused_bias_act_kernel.cu:52-98).
+ * y[i] = act(x[i] + b[(i/step_b) % size_b]) * scale; act 1 = linear, 3 = leaky-relu;
+ * grad 0/1/2 as in the reference kernel (:36-46).  b / ref may be NULL. */
+B200_API int b200_fused_bias_act_f32(const float* x, const float* b, const float* ref, float* y,
+                                     long long n, int step_b, int size_b, int act, int grad,
+                                     float alpha, float scale, void* stream);
+
+/* ---- GroupNorm(+SiLU), softmax, Gaussian noise: building blocks exported for tests ---- */
+B200_API int b200_groupnorm_nhwc_f32(const float* x1, int c1, const float* x2, int c2,
+                                     const float* gamma, const float* beta, int batch, int hw, int groups,
+                                     float eps, int silu, int round_tf32, float* stats_ws /* [batch*groups*2] */,
+                                     float* y, float* raw_or_null, void* stream);
+B200_API int b200_softmax_rows_f32(const float* s, float* p, long long rows, int t, float scale,
+                                   int round_tf32, void* stream);
+/* torch.randn-compatible N(0,1) fill: the values torch.randn(numel, device='cuda') would
+ * produce for generator state (seed, offset); *offset_inc_out = offset consumed. */
+B200_API int b200_randn_like_torch_f32(float* out, long long numel, unsigned long long seed,
+                                       unsigned long long offset, unsigned long long* offset_inc_out,
+                                       unsigned long long* offset_ws_dev /* 8 B device scratch */, void* stream);
+
+/* ---- one contraction (3x3 / 1x1 convolution on NHWC, 'same' padding, stride 1) ----
+ * Exported so the tcgen05 path can be checked against the CUDA-core path and torch.
+ * w_packed is [taps][c_out][c_in] (see b200_pack_conv_weight_f32). impl: 0 = fp32 CUDA cores,
+ * 1 = tcgen05 TF32 (inputs must already be TF32-representable for exactness claims). */
+B200_API int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int batch, int h, int w,
+                                const float* w_packed, const float* bias, int c_out, int ksize,
+                                const float* rowvec, long long rowvec_ld, const float* residual, float scale,
+                                int round_tf32, float* out, int impl, void* stream);
+B200_API int b200_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int c_out, int c_in, int ksize,
+                                       int round_tf32, void* stream);
+/* batched C[b] = A[b] (M x K, pitch lda) * W[b]^T (N x K, pitch ldw), row-major out pitch ldo. */
+B200_API int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const float* w, long long ldw,
+                              int w_batch_rows, int nbatch, int m, int n, int k, const float* bias,
+                              int round_tf32, float* out, long long ldo, int impl, void* stream);
+
+/* ---- NCSN++ score network ----------------------------------------------------
+ * Replaces models/ncsnpp.py:38-381 (+ models/layerspp.py, models/layers.py:29-124,515-555,
+ * models/up_or_down_sampling.py, op/) for configurations with Fourier embedding,
+ * BigGAN residual blocks, FIR resampling, progressive='none' and
+ * progressive_input in {'none','residual'}.  forward(x[B,C,H,W], time_cond[B]) -> [B,C,H,W]
+ * like NCSNpp.forward (models/ncsnpp.py:232). */
+typedef struct b200_ncsnpp b200_ncsnpp_t;
+
+typedef struct {
+  int image_size, num_channels, nf, num_res_blocks;
+  int num_levels;  int ch_mult[8];
+  int num_attn_resolutions;  int attn_resolutions[8];
+  int centered, scale_by_sigma, skip_rescale, conditional;
+  int progressive_input;        /* 0 = none, 1 = residual */
+  int fir_taps;  float fir_kernel[8];   /* separable taps, e.g. {1,3,3,1} */
+  int precision;                /* 0 = TF32 tensor cores where shapes allow, 1 = strict fp32 CUDA cores */
+  int keep_activations;         /* debug: never recycle activation buffers so b200_ncsnpp_tap works */
+} b200_ncsnpp_config;
+
+B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);
+B200_API void b200_ncsnpp_destroy(b200_ncsnpp_t* h);
+/* Parameter table in the reference's state_dict order and naming (all_modules.{i}.…). */
+B200_API int b200_ncsnpp_num_params(const b200_ncsnpp_t* h);
+B200_API int b200_ncsnpp_param_info(const b200_ncsnpp_t* h, int index, char* name, int name_cap,
+                                    long long shape[4], int* ndim);
+B200_API long long b200_ncsnpp_weights_bytes(const b200_ncsnpp_t* h);
+B200_API int b200_ncsnpp_bind_weights(b200_ncsnpp_t* h, void* blob_dev);
+/* Repack one parameter (reference layout, fp32, device) into the bound blob. */
+B200_API int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src_dev, void* stream);
+B200_API long long b200_ncsnpp_workspace_bytes(b200_ncsnpp_t* h, int batch);
+B200_API int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws_dev, long long ws_bytes);
+/* labels_uniform != 0: every image has the label labels[0] (the sampler's case,
+ * sampling.py:404-405) — the time-embedding path is then evaluated for one row. */
+B200_API int b200_ncsnpp_forward(b200_ncsnpp_t* h, const float* x_nchw, const float* labels,
+                                 int labels_uniform, float* out_nchw, void* stream);
+/* debug (keep_activations=1): copy the output of all_modules[index] as NCHW into dst. */
+B200_API int b200_ncsnpp_tap(b200_ncsnpp_t* h, int module_index, float* dst_nchw, long long dst_cap_elems,
+                             int shape_out[4], void* stream);
+B200_API long long b200_ncsnpp_launches_per_forward(const b200_ncsnpp_t* h);
+
+/* ---- predictor–corrector loop --------------------------------------------------
+ * Replaces the body of pc_sampler (sampling.py:390-409) with
+ * shared_corrector_update_fn/LangevinCorrector (:344-352, :262-282) and
+ * shared_predictor_update_fn/ReverseDiffusion|EulerMaruyama (:333-341, :181-200)
+ * + get_score_fn (models/utils.py:129-178) for an engine-backed model.
+ * Per-step scalars are supplied as host tables of length n_steps (built by the host
+ * with the SDE's own torch ops so they are bit-equal to the reference's):
+ *   label[i]       network time label (VE: sigma(t_i), VP: 999 t_i)
+ *   score_scale[i] score = score_scale * net_out   (VE: 1, VP: -1/std(t_i))
+ *   alpha[i]       Langevin alpha (VE: 1)
+ *   pa,pb,pc[i]    predictor: x_mean = pa*x + pb*net_out ; x = x_mean + pc*z
+ */
+typedef struct b200_pc b200_pc_t;
+typedef struct {
+  int n_steps;                 /* sde.N */
+  int corrector;               /* 0 none, 1 langevin */
+  int predictor;               /* 0 none, 1 affine (reverse_diffusion / euler_maruyama) */
+  int n_corrector_steps;       /* config.sampling.n_steps_each */
+  float snr;
+  const float *label, *score_scale, *alpha, *pa, *pb, *pc;   /* HOST tables [n_steps] */
+} b200_pc_config;
+
+B200_API int b200_pc_create(b200_ncsnpp_t* model, const b200_pc_config* cfg, int batch, b200_pc_t** out);
+B200_API void b200_pc_destroy(b200_pc_t* pc);
+B200_API long long b200_pc_workspace_bytes(const b200_pc_t* pc);
+B200_API int b200_pc_bind_workspace(b200_pc_t* pc, void* ws_dev, long long ws_bytes, void* stream);
+/* Run iterations [first_step, first_step+num_steps) on x (NCHW, in place); x_mean receives the
+ * last predictor (or corrector) mean.  Noise comes from the in-kernel Philox stream equal to
+ * torch's CUDA generator at (seed, offset); *offset_out = offset after the run.
+ * use_graph != 0 replays one captured CUDA graph per iteration. */
+B200_API int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_steps,
+                         unsigned long long seed, unsigned long long offset, unsigned long long* offset_out,
+                         int use_graph, void* stream);
+/* One iteration with caller-supplied noise tensors (NCHW, may be NULL when unused). */
+B200_API int b200_pc_step_external(b200_pc_t* pc, float* x, float* x_mean, int step,
+                                   const float* noise_corrector, const float* noise_predictor, void* stream);
+B200_API long long b200_pc_launches_per_step(const b200_pc_t* pc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SCORESDE_B200_H_ */

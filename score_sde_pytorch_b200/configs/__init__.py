@@ -1,0 +1,103 @@
+"""Attribute-style config trees for the sampling engine.
+
+The reference describes experiments with ``ml_collections.ConfigDict`` objects
+(``configs/default_cifar10_configs.py:5-71``).  ``ml_collections`` is not a
+dependency here: any object with attribute access works (the engine only reads
+fields), and :class:`ConfigDict` below is the small stand-in we ship.
+"""
+import torch
+
+
+class ConfigDict(dict):
+  """dict with attribute access (duck-type of ``ml_collections.ConfigDict``)."""
+
+  def __getattr__(self, key):
+    try:
+      return self[key]
+    except KeyError as e:
+      raise AttributeError(key) from e
+
+  def __setattr__(self, key, value):
+    self[key] = value
+
+  def copy(self):
+    out = ConfigDict()
+    for k, v in self.items():
+      out[k] = v.copy() if isinstance(v, ConfigDict) else v
+    return out
+
+
+def _default_device():
+  return torch.device('cuda:0') if torch.cuda.is_available() else torch.device('cpu')
+
+
+def cifar10_defaults():
+  """Field-for-field equivalent of ``configs/default_cifar10_configs.py:5-71``
+  restricted to what the sampling path reads (training/optim bookkeeping that
+  the sampler never touches is kept only where the model constructor reads it)."""
+  c = ConfigDict()
+  c.training = ConfigDict(batch_size=128, continuous=True, reduce_mean=False,
+                          likelihood_weighting=False, sde='vesde')
+  c.sampling = ConfigDict(method='pc', predictor='reverse_diffusion', corrector='langevin',
+                          n_steps_each=1, noise_removal=True, probability_flow=False, snr=0.16)
+  c.eval = ConfigDict(batch_size=1024, num_samples=50000)
+  c.data = ConfigDict(dataset='CIFAR10', image_size=32, centered=False, num_channels=3,
+                      random_flip=True, uniform_dequantization=False)
+  c.model = ConfigDict(sigma_min=0.01, sigma_max=50, num_scales=1000, beta_min=0.1,
+                       beta_max=20., dropout=0.1, embedding_type='fourier')
+  c.seed = 42
+  c.device = _default_device()
+  return c
+
+
+def ve_cifar10_ncsnpp_continuous():
+  """``configs/ve/cifar10_ncsnpp_continuous.py:19-59`` — the headline workload."""
+  c = cifar10_defaults()
+  c.training.sde = 'vesde'
+  c.training.continuous = True
+  c.sampling.method = 'pc'
+  c.sampling.predictor = 'reverse_diffusion'
+  c.sampling.corrector = 'langevin'
+  m = c.model
+  m.name = 'ncsnpp'
+  m.scale_by_sigma = True
+  m.ema_rate = 0.999
+  m.normalization = 'GroupNorm'
+  m.nonlinearity = 'swish'
+  m.nf = 128
+  m.ch_mult = (1, 2, 2, 2)
+  m.num_res_blocks = 4
+  m.attn_resolutions = (16,)
+  m.resamp_with_conv = True
+  m.conditional = True
+  m.fir = True
+  m.fir_kernel = [1, 3, 3, 1]
+  m.skip_rescale = True
+  m.resblock_type = 'biggan'
+  m.progressive = 'none'
+  m.progressive_input = 'residual'
+  m.progressive_combine = 'sum'
+  m.attention_type = 'ddpm'
+  m.init_scale = 0.
+  m.fourier_scale = 16
+  m.conv_size = 3
+  return c
+
+
+def ve_cifar10_ncsnpp_deep_continuous():
+  """``configs/ve/cifar10_ncsnpp_deep_continuous.py`` — 8 blocks per level."""
+  c = ve_cifar10_ncsnpp_continuous()
+  c.model.num_res_blocks = 8
+  return c
+
+
+def tiny_ncsnpp(nf=32, image_size=16, num_res_blocks=1, ch_mult=(1, 2), attn_resolutions=(8,)):
+  """A small NCSN++ of the same family (test fixture sized; not a reference config)."""
+  c = ve_cifar10_ncsnpp_continuous()
+  c.model.nf = nf
+  c.model.ch_mult = tuple(ch_mult)
+  c.model.num_res_blocks = num_res_blocks
+  c.model.attn_resolutions = tuple(attn_resolutions)
+  c.model.init_scale = 1.0
+  c.data.image_size = image_size
+  return c

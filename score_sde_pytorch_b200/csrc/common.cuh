@@ -1,0 +1,91 @@
+// Shared helpers for the sm_100a kernels of the score-SDE sampling engine.
+// Error reporting follows the C-ABI contract in include/scoresde_b200.h:
+// every entry point returns 0 on success, non-zero on failure, and the text is
+// available from b200_last_error().
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+
+namespace b200 {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char* fmt, ...);           // defined in api.cu
+const char* last_error();
+
+#define B200_CHECK_CUDA(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::b200::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,           \
+                        cudaGetErrorString(_e));                                     \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+
+#define B200_CHECK_LAUNCH()  B200_CHECK_CUDA(cudaGetLastError())
+
+#define B200_REQUIRE(cond, ...)                                                      \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      ::b200::set_error(__VA_ARGS__);                                                \
+      return 2;                                                                      \
+    }                                                                                \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers --------------------------------------------------------
+__device__ __forceinline__ float round_tf32(float x) {
+  // round-to-nearest (ties away) to the 10-bit-mantissa TF32 grid, kept as fp32 bits.
+  // tcgen05 kind::tf32 ignores the low 13 mantissa bits of its operands; pre-rounding
+  // makes that truncation a no-op so the only error is one RN rounding per operand.
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- the one contraction descriptor both conv back-ends implement ----------
+// out[b][m, n] = epi( sum_{tap, c} A(b, m, tap, c) * W(b)[tap][n][c] )
+//   conv mode : m enumerates NHWC pixels of all images, A is the (zero padded,
+//               optionally two-source channel-concatenated) input neighbourhood;
+//   gemm mode : A is a row-major [rows, K] matrix (optionally batched).
+// epi(v) = (v + bias[n] + rowvec[img(m)][n] + residual[m][n]) * scale
+//          then / per_img_div[img(m)], then optional TF32 rounding.
+struct Epilogue {
+  const float* bias;        // [N] or null
+  const float* rowvec;      // per-image row vector (time-embedding bias) or null
+  long long rowvec_ld;      // stride between images in rowvec (0 = same row for every image)
+  const float* residual;    // [M, ld_res] or null
+  long long ld_res;
+  const float* per_img_div; // [images] divide (scale_by_sigma) or null
+  long long div_stride;     // 0 = same divisor for every image
+  float scale;              // multiplies after the adds (1/sqrt(2) for skip_rescale)
+  int round_tf32;           // round the stored value to TF32
+  int rows_per_img;         // H_out*W_out in conv mode, rows per batch item in gemm mode
+  float* out;
+  long long ld_out;         // elements between consecutive rows of out (NHWC: C_out_total)
+  int out_nchw;             // conv mode only: write [img][n][pix] instead of [m][n]
+};
+
+}  // namespace b200

@@ -1,0 +1,888 @@
+// NCSN++ execution engine: builds the layer graph from the model configuration in the
+// same order as the reference constructor (models/ncsnpp.py:68-230), owns the packed
+// weight blob layout, plans activation buffers inside a caller-provided workspace and
+// replays the forward pass (models/ncsnpp.py:232-381) as a fixed sequence of kernel
+// launches on the caller's stream.  Nothing here allocates device memory.
+#include "kernels.h"
+#include "../../include/scoresde_b200.h"
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace b200 {
+void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld);
+}
+using namespace b200;
+
+namespace {
+
+enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RESBLOCK, M_ATTN, M_PYR_DOWN, M_GN_OUT, M_CONV_OUT };
+enum PackKind { PK_COPY = 0, PK_CONV = 1, PK_NIN = 2 };
+
+struct Param {
+  std::string name;
+  int ndim; long long shape[4];
+  long long off, count;      // location in the packed blob (floats)
+  int pack, taps, O, I, round;
+};
+
+struct Mod {
+  ModKind kind; int index;
+  int cin1 = 0, cin2 = 0, cout = 0, up = 0, down = 0, res = 0, has_conv2 = 0;
+  int dense_row = 0;
+  bool tc0 = false, tc1 = false, tc2 = false, tcattn = false;
+  // parameter indices
+  int gn0w = -1, gn0b = -1, c0w = -1, c0b = -1, dw = -1, db = -1, gn1w = -1, gn1b = -1, c1w = -1, c1b = -1, c2w = -1, c2b = -1;
+  int nw[4] = {-1, -1, -1, -1}, nb[4] = {-1, -1, -1, -1};
+  int w = -1, b = -1;
+};
+
+struct Tensor { float* p = nullptr; int C = 0, H = 0, W = 0; long long bytes = 0; };
+
+class Arena {
+ public:
+  explicit Arena(bool keep) : keep_(keep) {}
+  long long alloc(long long bytes) {
+    bytes = (bytes + 1023) & ~1023LL;
+    if (!keep_) {
+      for (size_t i = 0; i < free_.size(); ++i) {
+        if (free_[i].second >= bytes) {
+          const long long off = free_[i].first;
+          if (free_[i].second == bytes) free_.erase(free_.begin() + i);
+          else { free_[i].first += bytes; free_[i].second -= bytes; }
+          return off;
+        }
+      }
+    }
+    const long long off = top_;
+    top_ += bytes;
+    return off;
+  }
+  void release(long long off, long long bytes) {
+    if (keep_ || bytes == 0) return;
+    bytes = (bytes + 1023) & ~1023LL;
+    size_t i = 0;
+    while (i < free_.size() && free_[i].first < off) ++i;
+    free_.insert(free_.begin() + i, {off, bytes});
+    if (i + 1 < free_.size() && free_[i].first + free_[i].second == free_[i + 1].first) {
+      free_[i].second += free_[i + 1].second; free_.erase(free_.begin() + i + 1);
+    }
+    if (i > 0 && free_[i - 1].first + free_[i - 1].second == free_[i].first) {
+      free_[i - 1].second += free_[i].second; free_.erase(free_.begin() + i);
+    }
+    // give the tail back to the bump pointer
+    if (!free_.empty() && free_.back().first + free_.back().second == top_) { top_ = free_.back().first; free_.pop_back(); }
+  }
+  long long high_water() const { return std::max(top_, hw_); }
+  void note() { hw_ = std::max(hw_, top_); }
+ private:
+  bool keep_;
+  long long top_ = 0, hw_ = 0;
+  std::vector<std::pair<long long, long long>> free_;
+};
+
+__global__ void affine_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float shift, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = (x[i] + shift) * scale;
+}
+
+}  // namespace
+
+struct b200_ncsnpp {
+  b200_ncsnpp_config cfg;
+  std::vector<Param> params;
+  std::vector<Mod> mods;
+  long long wcount = 0;
+  float* wblob = nullptr;
+  int sumC = 0; long long dense_w_off = 0, dense_b_off = 0;
+  float fir2d[64]; int firn = 0;
+  // plan
+  int B = 0; char* ws = nullptr; long long ws_bytes = 0;
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<TcGemmPlan*> tcplans;
+  std::map<int, Tensor> taps;
+  long long launches = 0;
+  // per-call arguments read by the closures
+  const float* in_x = nullptr; const float* in_labels = nullptr; float* out = nullptr; int uniform = 0;
+
+  const float* W(int pi) const { return wblob + params[pi].off; }
+  ~b200_ncsnpp() { for (auto* p : tcplans) tc_gemm_plan_destroy(p); }
+};
+
+namespace {
+
+int add_param(b200_ncsnpp* e, const std::string& name, std::vector<long long> shape, int pack, int taps, int O,
+              int I, int round, long long fixed_off = -1) {
+  Param p;
+  p.name = name; p.ndim = (int)shape.size();
+  p.count = 1;
+  for (int i = 0; i < 4; ++i) { p.shape[i] = i < p.ndim ? shape[i] : 1; p.count *= p.shape[i]; }
+  p.pack = pack; p.taps = taps; p.O = O; p.I = I; p.round = round;
+  if (fixed_off >= 0) p.off = fixed_off;
+  else { p.off = e->wcount; e->wcount += (p.count + 63) & ~63LL; }
+  e->params.push_back(p);
+  return (int)e->params.size() - 1;
+}
+
+bool tc_ok(const b200_ncsnpp* e, int C1, int C2, int Cout, int H, int W, int taps) {
+  if (e->cfg.precision != 0) return false;
+  TcGemmDesc d; memset(&d, 0, sizeof(d));
+  d.C1 = C1; d.C2 = C2; d.a2 = C2 ? (const float*)1 : nullptr; d.conv = 1; d.H = H; d.W = W; d.nimg = 1; d.taps = taps;
+  d.N_total = Cout; d.K_total = C1 + C2; d.nbatch = 1; d.epi.ld_out = Cout; d.epi.ld_res = Cout;
+  return tc_gemm_supported(d, nullptr);
+}
+
+int build_graph(b200_ncsnpp* e) {
+  const b200_ncsnpp_config& c = e->cfg;
+  B200_REQUIRE(c.num_levels >= 1 && c.num_levels <= 8, "ncsnpp: num_levels=%d out of range", c.num_levels);
+  B200_REQUIRE(c.nf % 4 == 0 && c.nf >= 8, "ncsnpp: nf=%d must be a multiple of 4", c.nf);
+  B200_REQUIRE(c.conditional, "ncsnpp: unconditional models are not supported by the engine");
+  B200_REQUIRE(c.fir_taps >= 1 && c.fir_taps <= 8, "ncsnpp: fir kernel length %d unsupported", c.fir_taps);
+  B200_REQUIRE((c.image_size >> (c.num_levels - 1)) >= 1 && c.image_size % (1 << (c.num_levels - 1)) == 0,
+               "ncsnpp: image_size=%d not divisible by 2^(levels-1)", c.image_size);
+  // 2-D FIR = outer(k,k)/sum  (up_or_down_sampling.py:181-188)
+  {
+    double s = 0; for (int i = 0; i < c.fir_taps; ++i) s += c.fir_kernel[i];
+    e->firn = c.fir_taps;
+    for (int i = 0; i < c.fir_taps; ++i)
+      for (int j = 0; j < c.fir_taps; ++j) {
+        float kk = c.fir_kernel[i] * c.fir_kernel[j];
+        e->fir2d[i * c.fir_taps + j] = kk / (float)(s * s);
+      }
+  }
+  const int nf = c.nf, L = c.num_levels, nrb = c.num_res_blocks, ch = c.num_channels;
+  std::vector<int> all_res(L);
+  for (int i = 0; i < L; ++i) all_res[i] = c.image_size >> i;
+  auto has_attn = [&](int r) { for (int i = 0; i < c.num_attn_resolutions; ++i) if (c.attn_resolutions[i] == r) return true; return false; };
+  auto nm = [&](const char* suffix) { return "all_modules." + std::to_string((int)e->mods.size()) + "." + suffix; };
+  auto nmi = [&](int idx, const std::string& suffix) { return "all_modules." + std::to_string(idx) + "." + suffix; };
+
+  // --- first pass: count Dense_0 rows so their packed rows are contiguous ---
+  // (done lazily: dense region is reserved after the walk; Dense params get fixed offsets then)
+  struct DenseFix { int pw, pb, row, cout; };
+  std::vector<DenseFix> dense;
+
+  {  // sigmas buffer is a state_dict key of the reference (ncsnpp.py:42) but unused on this path
+    // (it is fp64 there; the host skips it when loading)
+  }
+  // 0: Fourier projection
+  { Mod m; m.kind = M_FOURIER; m.index = (int)e->mods.size(); m.w = add_param(e, nm("W"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+  { Mod m; m.kind = M_LINEAR; m.index = (int)e->mods.size(); m.cin1 = 2 * nf; m.cout = 4 * nf;
+    m.w = add_param(e, nm("weight"), {4 * nf, 2 * nf}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {4 * nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+  { Mod m; m.kind = M_LINEAR; m.index = (int)e->mods.size(); m.cin1 = 4 * nf; m.cout = 4 * nf;
+    m.w = add_param(e, nm("weight"), {4 * nf, 4 * nf}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {4 * nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+
+  auto add_resblock = [&](int cin1, int cin2, int cout, int up, int down, int res_in) {
+    Mod m; m.kind = M_RESBLOCK; m.index = (int)e->mods.size();
+    const int cin = cin1 + cin2;
+    m.cin1 = cin1; m.cin2 = cin2; m.cout = cout; m.up = up; m.down = down; m.res = res_in;
+    m.has_conv2 = (cin != cout) || up || down;
+    const int ro = up ? res_in * 2 : down ? res_in / 2 : res_in;
+    m.tc0 = tc_ok(e, cin, 0, cout, ro, ro, 9);
+    m.tc1 = tc_ok(e, cout, 0, cout, ro, ro, 9);
+    m.tc2 = m.has_conv2 && tc_ok(e, cin, 0, cout, ro, ro, 1);
+    m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {cin}, PK_COPY, 0, 0, 0, 0);
+    m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {cin}, PK_COPY, 0, 0, 0, 0);
+    m.c0w = add_param(e, nm("Conv_0.weight"), {cout, cin, 3, 3}, PK_CONV, 9, cout, cin, m.tc0);
+    m.c0b = add_param(e, nm("Conv_0.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
+    m.dw = add_param(e, nm("Dense_0.weight"), {cout, 4 * nf}, PK_COPY, 0, 0, 0, 0, 0);   // offset fixed below
+    m.db = add_param(e, nm("Dense_0.bias"), {cout}, PK_COPY, 0, 0, 0, 0, 0);
+    m.dense_row = e->sumC;
+    dense.push_back({m.dw, m.db, e->sumC, cout});
+    e->sumC += cout;
+    m.gn1w = add_param(e, nm("GroupNorm_1.weight"), {cout}, PK_COPY, 0, 0, 0, 0);
+    m.gn1b = add_param(e, nm("GroupNorm_1.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
+    m.c1w = add_param(e, nm("Conv_1.weight"), {cout, cout, 3, 3}, PK_CONV, 9, cout, cout, m.tc1);
+    m.c1b = add_param(e, nm("Conv_1.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
+    if (m.has_conv2) {
+      m.c2w = add_param(e, nm("Conv_2.weight"), {cout, cin, 1, 1}, PK_CONV, 1, cout, cin, m.tc2);
+      m.c2b = add_param(e, nm("Conv_2.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
+    }
+    e->mods.push_back(m);
+  };
+  auto add_attn = [&](int C, int res) {
+    Mod m; m.kind = M_ATTN; m.index = (int)e->mods.size(); m.cin1 = C; m.cout = C; m.res = res;
+    const int T = res * res;
+    m.tcattn = (e->cfg.precision == 0) && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
+    m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {C}, PK_COPY, 0, 0, 0, 0);
+    m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {C}, PK_COPY, 0, 0, 0, 0);
+    // q,k,v projection weights packed as one [3C][C] block (rows: q, k, v), biases as one [3C] vector
+    const long long wbase = e->wcount; e->wcount += 3LL * C * C;
+    const long long bbase = e->wcount; e->wcount += (3LL * C + 63) & ~63LL;
+    const bool tcproj = m.tcattn;
+    for (int k = 0; k < 3; ++k) {
+      m.nw[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".W"), {C, C}, PK_NIN, 1, C, C, tcproj, wbase + (long long)k * C * C);
+      m.nb[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".b"), {C}, PK_COPY, 0, 0, 0, 0, bbase + (long long)k * C);
+    }
+    m.tc2 = tc_ok(e, C, 0, C, res, res, 1);   // output projection as a 1x1 conv over pixels
+    m.nw[3] = add_param(e, nmi(m.index, "NIN_3.W"), {C, C}, PK_NIN, 1, C, C, m.tc2);
+    m.nb[3] = add_param(e, nmi(m.index, "NIN_3.b"), {C}, PK_COPY, 0, 0, 0, 0);
+    e->mods.push_back(m);
+  };
+
+  // input conv
+  { Mod m; m.kind = M_CONV_IN; m.index = (int)e->mods.size(); m.cin1 = ch; m.cout = nf; m.res = c.image_size;
+    m.w = add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV, 9, nf, ch, 0); m.b = add_param(e, nm("bias"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+  std::vector<int> hs_c = {nf};
+  int in_ch = nf, pyr_ch = ch;
+  for (int lvl = 0; lvl < L; ++lvl) {
+    for (int b = 0; b < nrb; ++b) {
+      const int out_ch = nf * c.ch_mult[lvl];
+      add_resblock(in_ch, 0, out_ch, 0, 0, all_res[lvl]);
+      in_ch = out_ch;
+      if (has_attn(all_res[lvl])) add_attn(in_ch, all_res[lvl]);
+      hs_c.push_back(in_ch);
+    }
+    if (lvl != L - 1) {
+      add_resblock(in_ch, 0, in_ch, 0, 1, all_res[lvl]);
+      if (c.progressive_input == 1) {
+        Mod m; m.kind = M_PYR_DOWN; m.index = (int)e->mods.size(); m.cin1 = pyr_ch; m.cout = in_ch; m.res = all_res[lvl];
+        m.w = add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, 0);
+        m.b = add_param(e, nm("Conv2d_0.bias"), {in_ch}, PK_COPY, 0, 0, 0, 0);
+        e->mods.push_back(m);
+        pyr_ch = in_ch;
+      }
+      hs_c.push_back(in_ch);
+    }
+  }
+  in_ch = hs_c.back();
+  add_resblock(in_ch, 0, in_ch, 0, 0, all_res[L - 1]);
+  add_attn(in_ch, all_res[L - 1]);
+  add_resblock(in_ch, 0, in_ch, 0, 0, all_res[L - 1]);
+  for (int lvl = L - 1; lvl >= 0; --lvl) {
+    for (int b = 0; b < nrb + 1; ++b) {
+      const int out_ch = nf * c.ch_mult[lvl];
+      const int skip = hs_c.back(); hs_c.pop_back();
+      add_resblock(in_ch, skip, out_ch, 0, 0, all_res[lvl]);
+      in_ch = out_ch;
+    }
+    if (has_attn(all_res[lvl])) add_attn(in_ch, all_res[lvl]);
+    if (lvl != 0) add_resblock(in_ch, 0, in_ch, 1, 0, all_res[lvl]);
+  }
+  B200_REQUIRE(hs_c.empty(), "ncsnpp: internal skip-stack mismatch");
+  { Mod m; m.kind = M_GN_OUT; m.index = (int)e->mods.size(); m.cin1 = in_ch;
+    m.w = add_param(e, nm("weight"), {in_ch}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {in_ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+  { Mod m; m.kind = M_CONV_OUT; m.index = (int)e->mods.size(); m.cin1 = in_ch; m.cout = ch; m.res = c.image_size;
+    m.w = add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0); m.b = add_param(e, nm("bias"), {ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+
+  // contiguous Dense_0 block: one [sumC][4nf] matrix + [sumC] bias for a single batched linear
+  e->dense_w_off = e->wcount; e->wcount += ((long long)e->sumC * 4 * nf + 63) & ~63LL;
+  e->dense_b_off = e->wcount; e->wcount += (e->sumC + 63) & ~63LL;
+  for (auto& d : dense) {
+    e->params[d.pw].off = e->dense_w_off + (long long)d.row * 4 * nf;
+    e->params[d.pb].off = e->dense_b_off + d.row;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Plan builder
+// ---------------------------------------------------------------------------
+struct Builder {
+  b200_ncsnpp* e; int B; char* base; bool dry; Arena arena; int rc = 0;
+  Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0) {}
+
+  Tensor talloc(int C, int H, int W) {
+    Tensor t; t.C = C; t.H = H; t.W = W; t.bytes = (long long)B * H * W * C * 4;
+    const long long off = arena.alloc(t.bytes); arena.note();
+    t.p = reinterpret_cast<float*>(base + off);
+    return t;
+  }
+  float* falloc(long long floats, long long* bytes_out) {
+    *bytes_out = floats * 4;
+    const long long off = arena.alloc(*bytes_out); arena.note();
+    return reinterpret_cast<float*>(base + off);
+  }
+  void tfree(Tensor& t) { if (t.p) arena.release((char*)t.p - base, t.bytes); t.p = nullptr; }
+  void ffree(float* p, long long bytes) { arena.release((char*)p - base, bytes); }
+
+  void op(int launches, std::function<int(cudaStream_t)> f) {
+    if (dry) return;
+    e->launches += launches;
+    e->ops.push_back(std::move(f));
+  }
+
+  void gn(Tensor x1, Tensor x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
+    const int C = x1.C + x2.C, G = std::min(C / 4, 32), HW = x1.H * x1.W;
+    long long sb; float* stats = falloc((long long)B * G * 2, &sb);
+    const float *g = e->W(pgw), *bt = e->W(pgb);
+    const int Bc = B;
+    op(2, [=](cudaStream_t st) {
+      if (int r = launch_gn_stats(x1.p, x1.C, x2.p, x2.C, Bc, HW, G, 1e-6f, stats, st)) return r;
+      return launch_gn_apply(x1.p, x1.C, x2.p, x2.C, stats, g, bt, Bc, HW, G, act, round, y.p, raw, st);
+    });
+    ffree(stats, sb);
+  }
+
+  void fir(const float* x, int major, int H, int W, int minor, int up, int down, int pad0, int pad1, int round, float* y,
+           float gain) {
+    // kernel taps scaled by `gain` (x factor^2 when upsampling, up_or_down_sampling.py:220)
+    std::vector<float> k(e->firn * e->firn);
+    for (size_t i = 0; i < k.size(); ++i) k[i] = e->fir2d[i] * gain;
+    const int n = e->firn;
+    op(1, [=](cudaStream_t st) {
+      return launch_upfirdn2d(x, k.data(), y, major, H, W, minor, n, n, up, up, down, down, pad0, pad1, pad0, pad1, round, st);
+    });
+  }
+
+  // 3x3 / 1x1 'same' convolution on NHWC tensors, stride 1.
+  void conv(bool use_tc, Tensor a1, Tensor a2, int taps, int pw, int pb, int Cout, int dense_row /* -1 = none */,
+            const float* residual, float scale, int round, Tensor out) {
+    Epilogue ep; memset(&ep, 0, sizeof(ep));
+    ep.bias = e->W(pb);
+    ep.rowvec = nullptr;   // patched at launch (depends on the per-call buffers)
+    ep.residual = residual; ep.ld_res = Cout; ep.scale = scale; ep.round_tf32 = round;
+    ep.rows_per_img = a1.H * a1.W; ep.out = out.p; ep.ld_out = Cout;
+    b200_ncsnpp* eng = e;
+    const float* dense_all = dense_all_;
+    const int sumC = e->sumC;
+    if (use_tc) {
+      TcGemmDesc d; memset(&d, 0, sizeof(d));
+      d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = a1.H; d.W = a1.W; d.nimg = B; d.taps = taps;
+      d.w = e->W(pw); d.N_total = Cout; d.K_total = a1.C + a2.C; d.w_rows = (long long)taps * Cout; d.nbatch = 1;
+      if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
+      d.epi = ep;
+      if (dry) return;
+      TcGemmPlan* pl = nullptr;
+      if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
+      e->tcplans.push_back(pl);
+      op(1, [=](cudaStream_t st) {
+        if (dense_row >= 0) tc_gemm_set_rowvec_ld(pl, eng->uniform ? 0 : sumC);
+        return tc_gemm_launch(pl, st);
+      });
+    } else {
+      SimtConv s; memset(&s, 0, sizeof(s));
+      s.x1 = a1.p; s.C1 = a1.C; s.x2 = a2.p; s.C2 = a2.C; s.in_scale = 1.f; s.in_shift = 0.f;
+      s.H = a1.H; s.W = a1.W; s.R = s.S = (taps == 9 ? 3 : 1); s.stride = 1; s.pad = (taps == 9 ? 1 : 0);
+      s.OH = a1.H; s.OW = a1.W; s.nbatch = B; s.a_batched = 1; s.w = e->W(pw); s.N = Cout;
+      if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
+      s.epi = ep;
+      op(1, [=](cudaStream_t st) {
+        SimtConv c = s;
+        if (dense_row >= 0) c.epi.rowvec_ld = eng->uniform ? 0 : sumC;
+        return launch_conv_simt(c, st);
+      });
+    }
+  }
+
+  // batched C[b] = A[b] * W[b]^T
+  void gemm(bool use_tc, const float* A, long long lda, long long a_rows, int a_batch_rows, const float* Wm, long long ldw,
+            long long w_rows, int w_batch_rows, int nbatch, int M, int N, int K, const float* bias,
+            const float* residual, long long ld_res, float scale, int round, float* out, long long ldo) {
+    Epilogue ep; memset(&ep, 0, sizeof(ep));
+    ep.bias = bias; ep.residual = residual; ep.ld_res = ld_res; ep.scale = scale; ep.round_tf32 = round;
+    ep.rows_per_img = 1 << 30; ep.out = out; ep.ld_out = ldo;
+    if (use_tc) {
+      TcGemmDesc d; memset(&d, 0, sizeof(d));
+      d.a1 = A; d.C1 = K; d.conv = 0; d.taps = 1; d.a_rows = a_rows; d.a_ld = lda; d.a_batch_rows = a_batch_rows;
+      d.w = Wm; d.N_total = N; d.K_total = K; d.w_rows = w_rows; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
+      d.nbatch = nbatch; d.M_per_batch = M; d.epi = ep;
+      if (dry) return;
+      TcGemmPlan* pl = nullptr;
+      if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
+      e->tcplans.push_back(pl);
+      op(1, [=](cudaStream_t st) { return tc_gemm_launch(pl, st); });
+    } else {
+      SimtConv s; memset(&s, 0, sizeof(s));
+      s.x1 = A; s.C1 = K; s.ld1 = lda; s.in_scale = 1.f; s.H = M; s.W = 1; s.R = s.S = 1; s.stride = 1; s.pad = 0;
+      s.OH = M; s.OW = 1; s.nbatch = nbatch; s.a_batched = a_batch_rows != 0; s.w = Wm; s.N = N;
+      s.w_batch_stride = (long long)w_batch_rows * ldw; s.w_ld = ldw;
+      ep.rows_per_img = M; s.epi = ep;
+      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); });
+    }
+  }
+
+  const float* dense_all_ = nullptr;
+  void tap(int idx, const Tensor& t) { if (!dry) e->taps[idx] = t; }
+
+  Tensor resblock(const Mod& m, Tensor x1, Tensor x2) {
+    const int Cin = x1.C + x2.C, H = x1.H, Ho = m.up ? 2 * H : m.down ? H / 2 : H;
+    const bool resample = m.up || m.down;
+    const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
+    Tensor a0 = talloc(Cin, H, H);
+    Tensor raw; // TF32-rounded copy of the (concatenated) block input for the tensor-core skip conv
+    if (m.has_conv2 && m.tc2 && !resample) raw = talloc(Cin, H, H);
+    gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? 1 : 0, a0, raw.p);
+    Tensor xr;
+    if (resample) {
+      if (x2.p) { set_error("ncsnpp: resampling block with a two-source input"); rc = 2; return Tensor(); }
+      Tensor a0r = talloc(Cin, Ho, Ho);
+      xr = talloc(Cin, Ho, Ho);
+      if (m.up) {   // upsample_2d: up=2, pad=(2,1), gain*4 (up_or_down_sampling.py:218-224)
+        const int p = e->firn - 2;
+        fir(a0.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc0, a0r.p, 4.f);
+        fir(x1.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc2, xr.p, 4.f);
+      } else {      // downsample_2d: down=2, pad=(1,1) (up_or_down_sampling.py:252-257)
+        const int p = e->firn - 2;
+        fir(a0.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc0, a0r.p, 1.f);
+        fir(x1.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc2, xr.p, 1.f);
+      }
+      tfree(a0); a0 = a0r;
+    }
+    Tensor h1 = talloc(m.cout, Ho, Ho);
+    conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 0, h1);
+    tfree(a0);
+    Tensor a1 = talloc(m.cout, Ho, Ho);
+    gn(h1, Tensor(), m.gn1w, m.gn1b, 1, m.tc1 ? 1 : 0, a1, nullptr);
+    tfree(h1);
+    Tensor s;
+    const float* residual = x1.p;
+    if (m.has_conv2) {
+      s = talloc(m.cout, Ho, Ho);
+      if (resample) conv(m.tc2, xr, Tensor(), 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
+      else if (m.tc2) conv(true, raw, Tensor(), 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
+      else conv(false, x1, x2, 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
+      residual = s.p;
+      tfree(raw); tfree(xr);
+    } else if (x2.p) { set_error("ncsnpp: concat input without a skip convolution"); rc = 2; return Tensor(); }
+    Tensor out = talloc(m.cout, Ho, Ho);
+    conv(m.tc1, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, residual, inv_s2, 0, out);
+    tfree(a1); tfree(s);
+    return out;
+  }
+
+  Tensor attn(const Mod& m, Tensor x) {
+    const int C = x.C, T = x.H * x.W;
+    const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
+    const bool tc = m.tcattn;
+    const float* Wqkv = e->W(m.nw[0]);          // [3C][C]
+    const float* bqkv = e->W(m.nb[0]);          // [3C]
+    Tensor a = talloc(C, x.H, x.W);
+    gn(x, Tensor(), m.gn0w, m.gn0b, 0, tc ? 1 : 0, a, nullptr);
+    long long qkb, vtb, sb, ob;
+    float* qk = falloc((long long)B * T * 2 * C, &qkb);
+    float* vT = falloc((long long)B * C * T, &vtb);
+    const long long BT = (long long)B * T;
+    // q,k = a Wq^T + bq | a Wk^T + bk   (layerspp.py:78-79) in one N=2C contraction
+    gemm(tc, a.p, C, BT, 0 /* rows enumerated flat */, Wqkv, C, 2LL * C, 0, 1, (int)BT, 2 * C, C, bqkv, nullptr, 0, 1.f, tc, qk, 2 * C);
+    // v^T[b][c][t] = sum_i Wv[c][i] a[b][t][i]   (bias bv is added after the PV product: softmax rows sum to 1)
+    gemm(tc, Wqkv + 2LL * C * C, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc, vT, T);
+    tfree(a);
+    float* S = falloc(BT * T, &sb);
+    // logits[b][q][k] = q . k   (layerspp.py:82), scaled inside the softmax
+    gemm(tc, qk, 2 * C, BT, T, qk + C, 2 * C, BT, T, B, T, T, C, nullptr, nullptr, 0, 1.f, 0, S, T);
+    ffree(qk, qkb);
+    const float sc = 1.0f / std::sqrt((float)C);   // int(C) ** -0.5
+    const int Bc = B;
+    op(1, [=](cudaStream_t st) { return launch_softmax_rows(S, S, (long long)Bc * T, T, sc, tc ? 1 : 0, st); });
+    float* O = falloc(BT * C, &ob);
+    // h[b][q][c] = sum_k P[q][k] v[k][c] + bv[c]   (layerspp.py:86)
+    gemm(tc, S, T, BT, T, vT, T, (long long)B * C, C, B, T, C, T, bqkv + 2 * C, nullptr, 0, 1.f, m.tc2 ? 1 : 0, O, C);
+    ffree(S, sb); ffree(vT, vtb);
+    Tensor out = talloc(C, x.H, x.W);
+    Tensor Ot; Ot.p = O; Ot.C = C; Ot.H = x.H; Ot.W = x.W;
+    conv(m.tc2, Ot, Tensor(), 1, m.nw[3], m.nb[3], C, -1, x.p, inv_s2, 0, out);   // NIN_3 + (x+h)/sqrt2 (:87-91)
+    ffree(O, ob);
+    return out;
+  }
+
+  int build() {
+    const b200_ncsnpp_config& c = e->cfg;
+    const int nf = c.nf, R = c.image_size, ch = c.num_channels, sumC = e->sumC;
+    b200_ncsnpp* eng = e;
+    const int Bc = B;
+    // ---- time embedding (ncsnpp.py:236-255) + all Dense_0(act(temb)) rows (layerspp.py:263) ----
+    long long eb, t1b, t2b, db, xcb;
+    float* emb = falloc((long long)B * 2 * nf, &eb);
+    float* t1 = falloc((long long)B * 4 * nf, &t1b);
+    float* t2 = falloc((long long)B * 4 * nf, &t2b);
+    float* dense_all = falloc((long long)B * sumC, &db);
+    dense_all_ = dense_all;
+    {
+      const Mod &mf = e->mods[0], &l1 = e->mods[1], &l2 = e->mods[2];
+      const float *Wf = e->W(mf.w), *W1 = e->W(l1.w), *b1 = e->W(l1.b), *W2 = e->W(l2.w), *b2 = e->W(l2.b);
+      const float *Wd = e->wblob + e->dense_w_off, *bd = e->wblob + e->dense_b_off;
+      op(4, [=](cudaStream_t st) {
+        const int rows = eng->uniform ? 1 : Bc;
+        if (int r = launch_fourier_embed(eng->in_labels, 1, Wf, nf, rows, emb, st)) return r;
+        if (int r = launch_linear_rows(emb, 2 * nf, W1, b1, rows, 4 * nf, 2 * nf, 0, t1, 4 * nf, st)) return r;
+        if (int r = launch_linear_rows(t1, 4 * nf, W2, b2, rows, 4 * nf, 4 * nf, 1, t2, 4 * nf, st)) return r;
+        return launch_linear_rows(t2, 4 * nf, Wd, bd, rows, sumC, 4 * nf, 1, dense_all, sumC, st);
+      });
+    }
+    // ---- input (ncsnpp.py:259-268) ----
+    float* xc = falloc((long long)B * ch * R * R, &xcb);   // 2x-1 when data is not centred; NCHW
+    {
+      const long long n = (long long)B * ch * R * R;
+      const int centered = c.centered;
+      op(1, [=](cudaStream_t st) {
+        if (centered) return cudaMemcpyAsync(xc, eng->in_x, n * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : (set_error("memcpy failed"), 1);
+        affine_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, st>>>(eng->in_x, xc, n, -0.5f, 2.0f);
+        return cudaGetLastError() == cudaSuccess ? 0 : (set_error("affine launch failed"), 1);
+      });
+    }
+    size_t mi = 3;
+    std::vector<Tensor> hs;
+    {
+      const Mod& m = e->mods[mi++];
+      Tensor h0 = talloc(nf, R, R);
+      SimtConv s; memset(&s, 0, sizeof(s));
+      s.x1 = xc; s.C1 = ch; s.in_nchw = 1; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
+      s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = e->W(m.w); s.N = nf;
+      s.epi.bias = e->W(m.b); s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out = h0.p; s.epi.ld_out = nf;
+      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); });
+      hs.push_back(h0);
+      tap(m.index, h0);
+    }
+    // input pyramid (progressive_input='residual', ncsnpp.py:289-301): starts as the network input
+    Tensor pyr; pyr.p = xc; pyr.C = ch; pyr.H = R; pyr.W = R; bool pyr_nchw = true; bool pyr_owned = false;
+    const int L = c.num_levels;
+    for (int lvl = 0; lvl < L; ++lvl) {
+      for (int b = 0; b < c.num_res_blocks; ++b) {
+        const Mod& m = e->mods[mi++];
+        Tensor h = resblock(m, hs.back(), Tensor()); if (rc) return rc;
+        tap(m.index, h);
+        if (mi < e->mods.size() && e->mods[mi].kind == M_ATTN && e->mods[mi].res == h.H && lvl_has_attn(h.H)) {
+          const Mod& ma = e->mods[mi++];
+          Tensor h2 = attn(ma, h); if (rc) return rc;
+          tfree(h); h = h2; tap(ma.index, h);
+        }
+        hs.push_back(h);
+      }
+      if (lvl != L - 1) {
+        const Mod& m = e->mods[mi++];
+        Tensor h = resblock(m, hs.back(), Tensor()); if (rc) return rc;
+        tap(m.index, h);
+        if (c.progressive_input == 1) {
+          const Mod& mp = e->mods[mi++];
+          // Downsample(fir, with_conv): FIR with pad (2,2) then 3x3 stride-2 VALID conv + bias
+          // (up_or_down_sampling.py:170-178, Conv2d.forward :44-56), then (pyr + h)/sqrt2 (ncsnpp.py:297-301)
+          const int Hin = pyr.H, p = (e->firn - 2) + 2;
+          const int Hp = Hin + ((p + 1) / 2) + (p / 2) - e->firn + 1;
+          long long fb; float* fbuf = falloc((long long)B * pyr.C * Hp * Hp, &fb);
+          if (pyr_nchw) fir(pyr.p, B * pyr.C, Hin, Hin, 1, 1, 1, (p + 1) / 2, p / 2, 0, fbuf, 1.f);
+          else fir(pyr.p, B, Hin, Hin, pyr.C, 1, 1, (p + 1) / 2, p / 2, 0, fbuf, 1.f);
+          Tensor np = talloc(mp.cout, h.H, h.W);
+          SimtConv s; memset(&s, 0, sizeof(s));
+          s.x1 = fbuf; s.C1 = pyr.C; s.in_nchw = pyr_nchw ? 1 : 0; s.in_scale = 1.f; s.H = Hp; s.W = Hp; s.R = s.S = 3; s.stride = 2; s.pad = 0;
+          s.OH = h.H; s.OW = h.W; s.nbatch = B; s.a_batched = 1; s.w = e->W(mp.w); s.N = mp.cout;
+          s.epi.bias = e->W(mp.b); s.epi.residual = h.p; s.epi.ld_res = mp.cout;
+          s.epi.scale = c.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
+          s.epi.rows_per_img = h.H * h.W; s.epi.out = np.p; s.epi.ld_out = mp.cout;
+          if ((Hp - 3) / 2 + 1 != h.H) { set_error("ncsnpp: pyramid geometry mismatch (%d vs %d)", (Hp - 3) / 2 + 1, h.H); return 2; }
+          op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); });
+          ffree(fbuf, fb);
+          if (pyr_owned) tfree(pyr);
+          tfree(h);
+          h = np; pyr = np; pyr_nchw = false; pyr_owned = false;   // h aliases the pyramid from here on (it lives in hs)
+          tap(mp.index, np);
+        }
+        hs.push_back(h);
+      }
+    }
+    // ---- middle (ncsnpp.py:305-311) ----
+    Tensor h;
+    {
+      const Mod& m0 = e->mods[mi++]; h = resblock(m0, hs.back(), Tensor()); if (rc) return rc; tap(m0.index, h);
+      const Mod& ma = e->mods[mi++]; Tensor h2 = attn(ma, h); if (rc) return rc; tfree(h); h = h2; tap(ma.index, h);
+      const Mod& m1 = e->mods[mi++]; Tensor h3 = resblock(m1, h, Tensor()); if (rc) return rc; tfree(h); h = h3; tap(m1.index, h);
+    }
+    // ---- up path (ncsnpp.py:316-364) ----
+    for (int lvl = L - 1; lvl >= 0; --lvl) {
+      for (int b = 0; b < c.num_res_blocks + 1; ++b) {
+        const Mod& m = e->mods[mi++];
+        Tensor skip = hs.back(); hs.pop_back();
+        Tensor h2 = resblock(m, h, skip); if (rc) return rc;
+        tfree(h); tfree(skip);
+        h = h2; tap(m.index, h);
+      }
+      if (e->mods[mi].kind == M_ATTN) {
+        const Mod& ma = e->mods[mi++]; Tensor h2 = attn(ma, h); if (rc) return rc; tfree(h); h = h2; tap(ma.index, h);
+      }
+      if (lvl != 0) {
+        const Mod& m = e->mods[mi++]; Tensor h2 = resblock(m, h, Tensor()); if (rc) return rc; tfree(h); h = h2; tap(m.index, h);
+      }
+    }
+    // ---- output head (ncsnpp.py:371-379) ----
+    {
+      const Mod& mg = e->mods[mi++];
+      Tensor a = talloc(h.C, h.H, h.W);
+      gn(h, Tensor(), mg.w, mg.b, 1, 0, a, nullptr);
+      tfree(h);
+      const Mod& mo = e->mods[mi++];
+      SimtConv s; memset(&s, 0, sizeof(s));
+      s.x1 = a.p; s.C1 = a.C; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
+      s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = e->W(mo.w); s.N = ch;
+      s.epi.bias = e->W(mo.b); s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out_nchw = 1; s.epi.ld_out = ch;
+      const int sbs = c.scale_by_sigma;
+      op(1, [=](cudaStream_t st) {
+        SimtConv cc = s;
+        cc.epi.out = eng->out;
+        if (sbs) { cc.epi.per_img_div = eng->in_labels; cc.epi.div_stride = eng->uniform ? 0 : 1; }
+        return launch_conv_simt(cc, st);
+      });
+      tfree(a);
+    }
+    if (mi != e->mods.size()) { set_error("ncsnpp: plan walked %zu of %zu modules", mi, e->mods.size()); return 2; }
+    (void)eb; (void)t1b; (void)t2b; (void)db; (void)xcb;
+    return rc;
+  }
+
+  bool lvl_has_attn(int r) const {
+    for (int i = 0; i < e->cfg.num_attn_resolutions; ++i) if (e->cfg.attn_resolutions[i] == r) return true;
+    return false;
+  }
+};
+
+}  // namespace
+
+// ===========================================================================
+// C ABI: model
+// ===========================================================================
+extern "C" {
+
+int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out) {
+  B200_REQUIRE(cfg && out, "ncsnpp_create: null argument");
+  b200_ncsnpp* e = new b200_ncsnpp();
+  e->cfg = *cfg;
+  if (int r = build_graph(e)) { delete e; return r; }
+  *out = e;
+  return 0;
+}
+
+void b200_ncsnpp_destroy(b200_ncsnpp_t* h) { delete h; }
+
+int b200_ncsnpp_num_params(const b200_ncsnpp_t* h) { return h ? (int)h->params.size() : 0; }
+
+int b200_ncsnpp_param_info(const b200_ncsnpp_t* h, int index, char* name, int name_cap, long long shape[4], int* ndim) {
+  B200_REQUIRE(h && index >= 0 && index < (int)h->params.size(), "param_info: index %d out of range", index);
+  const Param& p = h->params[index];
+  if (name && name_cap > 0) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = p.shape[i];
+  if (ndim) *ndim = p.ndim;
+  return 0;
+}
+
+long long b200_ncsnpp_weights_bytes(const b200_ncsnpp_t* h) { return h ? h->wcount * 4 : 0; }
+
+int b200_ncsnpp_bind_weights(b200_ncsnpp_t* h, void* blob) {
+  B200_REQUIRE(h && blob, "bind_weights: null argument");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 255) == 0, "bind_weights: blob must be 256-byte aligned");
+  B200_REQUIRE(h->ops.empty(), "bind_weights: rebind after planning is not supported");
+  h->wblob = static_cast<float*>(blob);
+  return 0;
+}
+
+int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* stream) {
+  B200_REQUIRE(h && h->wblob, "load_param: weights not bound");
+  B200_REQUIRE(index >= 0 && index < (int)h->params.size(), "load_param: index %d out of range", index);
+  const Param& p = h->params[index];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dst = h->wblob + p.off;
+  if (p.pack == PK_COPY) {
+    B200_CHECK_CUDA(cudaMemcpyAsync(dst, src, p.count * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (p.pack == PK_CONV)   // OIHW -> [tap][O][I]
+    return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st);
+  // NIN W[in][out] -> [out][in]
+  return launch_pack_weight(src, dst, 1, p.O, p.I, 1, p.O, 0, p.round, st);
+}
+
+long long b200_ncsnpp_workspace_bytes(b200_ncsnpp_t* h, int batch) {
+  if (!h || batch <= 0) return -1;
+  Builder b(h, batch, nullptr, true);
+  if (b.build()) return -1;
+  return b.arena.high_water() + 1024;
+}
+
+int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long ws_bytes) {
+  B200_REQUIRE(h && ws && batch > 0, "bind_workspace: bad argument");
+  B200_REQUIRE(h->wblob, "bind_workspace: bind the weight blob first");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "bind_workspace: workspace must be 1024-byte aligned");
+  const long long need = b200_ncsnpp_workspace_bytes(h, batch);
+  B200_REQUIRE(need >= 0, "bind_workspace: planning failed: %s", last_error());
+  B200_REQUIRE(ws_bytes >= need, "bind_workspace: workspace too small (%lld < %lld bytes)", ws_bytes, need);
+  for (auto* p : h->tcplans) tc_gemm_plan_destroy(p);
+  h->tcplans.clear(); h->ops.clear(); h->taps.clear(); h->launches = 0;
+  h->B = batch; h->ws = static_cast<char*>(ws); h->ws_bytes = ws_bytes;
+  Builder b(h, batch, h->ws, false);
+  if (int r = b.build()) { h->ops.clear(); return r; }
+  return 0;
+}
+
+int b200_ncsnpp_forward(b200_ncsnpp_t* h, const float* x, const float* labels, int uniform, float* out, void* stream) {
+  B200_REQUIRE(h && x && labels && out, "forward: null argument");
+  B200_REQUIRE(!h->ops.empty(), "forward: no plan bound (call b200_ncsnpp_bind_workspace)");
+  h->in_x = x; h->in_labels = labels; h->out = out; h->uniform = uniform;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& f : h->ops) if (int r = f(st)) return r;
+  return 0;
+}
+
+int b200_ncsnpp_tap(b200_ncsnpp_t* h, int module_index, float* dst, long long cap, int shape_out[4], void* stream) {
+  B200_REQUIRE(h && h->cfg.keep_activations, "tap: engine was not created with keep_activations=1");
+  auto it = h->taps.find(module_index);
+  B200_REQUIRE(it != h->taps.end(), "tap: module %d has no recorded activation", module_index);
+  const Tensor& t = it->second;
+  const long long n = (long long)h->B * t.C * t.H * t.W;
+  if (shape_out) { shape_out[0] = h->B; shape_out[1] = t.C; shape_out[2] = t.H; shape_out[3] = t.W; }
+  B200_REQUIRE(cap >= n, "tap: destination too small (%lld < %lld)", cap, n);
+  return launch_nhwc_to_nchw(t.p, dst, h->B, t.H * t.W, t.C, static_cast<cudaStream_t>(stream));
+}
+
+long long b200_ncsnpp_launches_per_forward(const b200_ncsnpp_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// ===========================================================================
+// C ABI: predictor-corrector loop
+// ===========================================================================
+struct b200_pc {
+  b200_ncsnpp* model; b200_pc_config cfg; int B; long long numel, per_img;
+  std::vector<float> h_label, h_ss, h_alpha, h_pa, h_pb, h_pc;
+  // workspace carve-up
+  char* ws = nullptr; float *d_label, *d_ss, *d_alpha, *d_pa, *d_pb, *d_pc, *labels, *net_out, *norms, *means;
+  int* d_step; unsigned long long* d_offset;
+  PhiloxMap map;
+  cudaGraphExec_t gexec = nullptr; float* graph_x = nullptr; float* graph_xm = nullptr; cudaStream_t graph_stream = nullptr;
+  long long launches_per_step = 0;
+  ~b200_pc() { if (gexec) cudaGraphExecDestroy(gexec); }
+};
+
+namespace {
+
+long long pc_ws_layout(b200_pc* pc, char* base) {
+  long long off = 0;
+  auto take = [&](long long bytes) { long long o = off; off += (bytes + 255) & ~255LL; return base ? base + o : nullptr; };
+  const int N = pc->cfg.n_steps;
+  pc->d_label = (float*)take(N * 4LL); pc->d_ss = (float*)take(N * 4LL); pc->d_alpha = (float*)take(N * 4LL);
+  pc->d_pa = (float*)take(N * 4LL); pc->d_pb = (float*)take(N * 4LL); pc->d_pc = (float*)take(N * 4LL);
+  pc->labels = (float*)take(pc->B * 4LL); pc->net_out = (float*)take(pc->numel * 4LL);
+  pc->norms = (float*)take(2LL * pc->B * 4); pc->means = (float*)take(256);
+  pc->d_step = (int*)take(256); pc->d_offset = (unsigned long long*)take(256);
+  return off;
+}
+
+// one PC iteration at step *d_step; noise_c/noise_p non-null -> external noise
+int pc_iteration(b200_pc* pc, float* x, float* x_mean, const float* noise_c, const float* noise_p, cudaStream_t st) {
+  b200_ncsnpp* m = pc->model;
+  const b200_pc_config& c = pc->cfg;
+  PcStepScalars sc{pc->d_ss, pc->d_alpha, pc->d_pa, pc->d_pb, pc->d_pc};
+  const unsigned long long cps = (unsigned long long)((c.corrector ? c.n_corrector_steps : 0) + (c.predictor ? 1 : 0));
+  if (int r = launch_fill_from_table(pc->d_label, pc->d_step, pc->labels, pc->B, st)) return r;
+  unsigned long long call = 0;
+  if (c.corrector) {
+    for (int k = 0; k < c.n_corrector_steps; ++k) {
+      if (int r = b200_ncsnpp_forward(m, x, pc->labels, 1, pc->net_out, st)) return r;
+      if (int r = launch_pc_norms(pc->net_out, noise_c, pc->map, pc->d_offset, pc->d_step, cps, call, pc->B,
+                                  (int)pc->per_img, pc->norms, pc->means, st)) return r;
+      if (int r = launch_langevin_apply(x, x_mean, pc->net_out, noise_c, pc->map, pc->d_offset, pc->d_step, cps, call,
+                                        pc->means, c.snr, sc, st)) return r;
+      ++call;
+    }
+  }
+  if (c.predictor) {
+    if (int r = b200_ncsnpp_forward(m, x, pc->labels, 1, pc->net_out, st)) return r;
+    if (int r = launch_predictor_apply(x, x_mean, pc->net_out, noise_p, pc->map, pc->d_offset, pc->d_step, cps, call,
+                                       sc, 1, st)) return r;
+  }
+  return launch_step_increment(pc->d_step, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_pc_create(b200_ncsnpp_t* model, const b200_pc_config* cfg, int batch, b200_pc_t** out) {
+  B200_REQUIRE(model && cfg && out && batch > 0, "pc_create: bad argument");
+  B200_REQUIRE(model->B == batch && !model->ops.empty(), "pc_create: model is not planned for batch %d", batch);
+  B200_REQUIRE(cfg->n_steps > 0 && cfg->label && cfg->pb, "pc_create: missing schedule tables");
+  B200_REQUIRE(cfg->corrector == 0 || cfg->corrector == 1, "pc_create: corrector %d unsupported", cfg->corrector);
+  B200_REQUIRE(cfg->predictor == 0 || cfg->predictor == 1, "pc_create: predictor %d unsupported", cfg->predictor);
+  b200_pc* pc = new b200_pc();
+  pc->model = model; pc->cfg = *cfg; pc->B = batch;
+  const b200_ncsnpp_config& mc = model->cfg;
+  pc->per_img = (long long)mc.num_channels * mc.image_size * mc.image_size;
+  pc->numel = pc->per_img * batch;
+  const int N = cfg->n_steps;
+  auto cp = [&](std::vector<float>& dst, const float* src, float dflt) { dst.assign(N, dflt); if (src) memcpy(dst.data(), src, N * 4); };
+  cp(pc->h_label, cfg->label, 0.f); cp(pc->h_ss, cfg->score_scale, 1.f); cp(pc->h_alpha, cfg->alpha, 1.f);
+  cp(pc->h_pa, cfg->pa, 1.f); cp(pc->h_pb, cfg->pb, 0.f); cp(pc->h_pc, cfg->pc, 0.f);
+  pc->cfg.label = pc->cfg.score_scale = pc->cfg.alpha = pc->cfg.pa = pc->cfg.pb = pc->cfg.pc = nullptr;
+  const long long cps = (cfg->corrector ? cfg->n_corrector_steps : 0) + (cfg->predictor ? 1 : 0);
+  pc->launches_per_step = cps * model->launches + (cfg->corrector ? cfg->n_corrector_steps * 3 : 0) + (cfg->predictor ? 1 : 0) + 2;
+  *out = pc;
+  return 0;
+}
+
+void b200_pc_destroy(b200_pc_t* pc) { delete pc; }
+
+long long b200_pc_workspace_bytes(const b200_pc_t* pc) {
+  if (!pc) return -1;
+  b200_pc tmp = *pc; tmp.gexec = nullptr;
+  return pc_ws_layout(&tmp, nullptr) + 256;
+}
+
+int b200_pc_bind_workspace(b200_pc_t* pc, void* ws, long long bytes, void* stream) {
+  B200_REQUIRE(pc && ws, "pc_bind_workspace: null argument");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "pc_bind_workspace: workspace must be 256-byte aligned");
+  const long long need = pc_ws_layout(pc, static_cast<char*>(ws));
+  B200_REQUIRE(bytes >= need, "pc_bind_workspace: workspace too small (%lld < %lld)", bytes, need);
+  pc->ws = static_cast<char*>(ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = pc->cfg.n_steps;
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_label, pc->h_label.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_ss, pc->h_ss.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_alpha, pc->h_alpha.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_pa, pc->h_pa.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_pb, pc->h_pb.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_pc, pc->h_pc.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (pc->gexec) { cudaGraphExecDestroy(pc->gexec); pc->gexec = nullptr; }
+  return philox_map_init(&pc->map, pc->numel, 0);
+}
+
+int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_steps, unsigned long long seed,
+                unsigned long long offset, unsigned long long* offset_out, int use_graph, void* stream) {
+  B200_REQUIRE(pc && pc->ws && x, "pc_run: not bound");
+  B200_REQUIRE(first_step >= 0 && num_steps >= 0 && first_step + num_steps <= pc->cfg.n_steps,
+               "pc_run: steps [%d,%d) outside the %d-step schedule", first_step, first_step + num_steps, pc->cfg.n_steps);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pc->map.seed = seed;
+  // the noise offset of step s is *d_offset + (s*cps + call)*inc, so rebase for first_step
+  const unsigned long long cps = (unsigned long long)((pc->cfg.corrector ? pc->cfg.n_corrector_steps : 0) + (pc->cfg.predictor ? 1 : 0));
+  const unsigned long long base = offset - (unsigned long long)first_step * cps * pc->map.inc;
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_offset, &base, 8, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_step, &first_step, 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaStreamSynchronize(st));   // host sources above are stack variables
+  if (use_graph && num_steps > 0) {
+    if (!pc->gexec || pc->graph_x != x || pc->graph_xm != x_mean || pc->map.seed != seed || pc->graph_stream != st) {
+      if (pc->gexec) { cudaGraphExecDestroy(pc->gexec); pc->gexec = nullptr; }
+      cudaGraph_t g = nullptr;
+      B200_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int r = pc_iteration(pc, x, x_mean, nullptr, nullptr, st);
+      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (r) { if (g) cudaGraphDestroy(g); return r; }
+      B200_CHECK_CUDA(ce);
+      B200_CHECK_CUDA(cudaGraphInstantiate(&pc->gexec, g, 0));
+      cudaGraphDestroy(g);
+      pc->graph_x = x; pc->graph_xm = x_mean; pc->graph_stream = st;
+    }
+    for (int i = 0; i < num_steps; ++i) B200_CHECK_CUDA(cudaGraphLaunch(pc->gexec, st));
+  } else {
+    for (int i = 0; i < num_steps; ++i) if (int r = pc_iteration(pc, x, x_mean, nullptr, nullptr, st)) return r;
+  }
+  if (offset_out) *offset_out = offset + (unsigned long long)num_steps * cps * pc->map.inc;
+  return 0;
+}
+
+int b200_pc_step_external(b200_pc_t* pc, float* x, float* x_mean, int step, const float* noise_c,
+                          const float* noise_p, void* stream) {
+  B200_REQUIRE(pc && pc->ws && x, "pc_step_external: not bound");
+  B200_REQUIRE(step >= 0 && step < pc->cfg.n_steps, "pc_step_external: step %d out of range", step);
+  B200_REQUIRE(!pc->cfg.corrector || noise_c, "pc_step_external: corrector noise missing");
+  B200_REQUIRE(!pc->cfg.predictor || noise_p, "pc_step_external: predictor noise missing");
+  B200_REQUIRE(pc->cfg.n_corrector_steps <= 1 || !pc->cfg.corrector, "pc_step_external: supports n_steps_each <= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_step, &step, 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaStreamSynchronize(st));
+  return pc_iteration(pc, x, x_mean, noise_c, noise_p, st);
+}
+
+long long b200_pc_launches_per_step(const b200_pc_t* pc) { return pc ? pc->launches_per_step : 0; }
+
+}  // extern "C"

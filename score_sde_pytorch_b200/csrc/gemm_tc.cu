@@ -1,0 +1,443 @@
+// tcgen05 / TMEM / TMA implicit GEMM for the NCSN++ contractions (3x3 and 1x1
+// convolutions, NIN projections, the batched attention products) on sm_100a.
+//
+//   out[b][m, n] = epi( sum_{src, tap, c} A_src(b, m, tap, c) * W(b)[tap][n][koff_src + c] )
+//
+// Operands are fp32 bit patterns already rounded to the TF32 grid by their producers
+// (GroupNorm-apply / softmax / previous epilogue for A, the weight packer for W), so the
+// tensor core's operand truncation is exact and the only contraction error is the TF32
+// operand rounding itself; accumulation is fp32 in TMEM.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0 lane 0 : TMA producer.  Per K step it lands one 128-row x 32-channel A tile
+//                   (a 4-D box of the NHWC tensor shifted by the filter tap; the zero
+//                   halo of 'same' padding comes from TMA out-of-bounds fill) and one
+//                   BN-row x 32-channel W tile, both with the 128-byte swizzle, into a
+//                   STAGES-deep shared-memory ring guarded by full/empty mbarriers.
+//   warp 1 lane 0 : MMA issuer.  Four tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per
+//                   stage from shared-memory descriptors into one of two TMEM
+//                   accumulator stages; tcgen05.commit releases the smem slot and, after
+//                   the last K step, publishes the accumulator.
+//   warp 2        : allocates / frees the 2*BN TMEM columns.
+//   warps 4..7    : epilogue.  tcgen05.ld 32 lanes x 32 columns at a time, fused
+//                   bias + time-embedding row + residual + scale (+ TF32 rounding),
+//                   128-bit stores.  Runs concurrently with the next tile's main loop
+//                   thanks to the second accumulator stage.
+#include "kernels.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace b200 {
+
+namespace {
+
+constexpr int BM = 128;          // rows (pixels) per tile == UMMA M
+constexpr int BKE = 32;          // fp32 elements per K step == one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32
+constexpr int A_STAGE_BYTES = BM * BKE * 4;   // 16 KiB
+
+struct TcParams {
+  CUtensorMap tmA1, tmA2, tmW;
+  int conv, H, W, taps, pad, S;        // S = filter width (3 or 1)
+  int kchunks1, kchunks2, C1;
+  int N_total, tiles_n;
+  int nbatch, tiles_m_per_batch, M_per_batch;
+  int a_batch_rows, w_batch_rows;
+  long long total_tiles;
+  Epilogue epi;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
+      printf("gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows are 128 B, 8-row atoms are 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  const uint64_t lo = (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16);            // start address, LBO (unused for swizzled K-major)
+  const uint64_t hi = (uint64_t)(1024 >> 4) | (1ull << 14) | (2ull << 29);           // SBO = 1024 B, version 1 (sm_100), SWIZZLE_128B
+  return lo | (hi << 32);
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc() {
+  // D fp32 (1<<4), A tf32 (2<<7), B tf32 (2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24.
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BN * BKE * 4;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-B alignment
+};
+
+// ---------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kiters = (p.kchunks1 + p.kchunks2) * p.taps;
+  const int HW = p.H * p.W;
+
+  if (warp == 0 && lane == 0) {
+    // ======================= TMA producer =======================
+    uint32_t stage = 0, phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % p.tiles_n);
+      const long long mg = tile / p.tiles_n;
+      const int b = (int)(mg / p.tiles_m_per_batch);
+      const int mt = (int)(mg % p.tiles_m_per_batch);
+      int img0 = 0, h0 = 0, w0 = 0;
+      if (p.conv) {
+        const long long p0 = (long long)mt * BM;
+        img0 = (int)(p0 / HW);
+        const int rem = (int)(p0 % HW);
+        h0 = rem / p.W; w0 = rem % p.W;
+      }
+      const int arow0 = b * p.a_batch_rows + mt * BM;
+      const int wrow0 = b * p.w_batch_rows + nt * BN;
+      for (int src = 0; src < 2; ++src) {
+        const int nch = src ? p.kchunks2 : p.kchunks1;
+        if (nch == 0) continue;
+        const CUtensorMap* tmA = src ? &p.tmA2 : &p.tmA1;
+        const int wcol0 = src ? p.C1 : 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 + dw, h0 + dh, img0);
+            else tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, arow0, 0, 0);
+            tma_load_2d(&p.tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = make_idesc<BN>();
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa);
+        const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKE / UMMA_K; ++k) {
+          // advance 8 fp32 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+          umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int q = warp - 4;                    // TMEM lane quarter owned by this warp
+    const int r = q * 32 + lane;               // row of the tile held by this thread
+    const Epilogue& e = p.epi;
+    uint32_t acc = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % p.tiles_n);
+      const long long mg = tile / p.tiles_n;
+      const int b = (int)(mg / p.tiles_m_per_batch);
+      const int mt = (int)(mg % p.tiles_m_per_batch);
+      const int m = mt * BM + r;
+      const bool valid = m < p.M_per_batch;
+      const long long gm = (long long)b * p.M_per_batch + m;
+      const int img = valid ? (int)(gm / e.rows_per_img) : 0;
+      const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
+        if (valid) {
+          const int n0 = nt * BN + j * 32;
+          float* dst = e.out + gm * e.ld_out + n0;
+          const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
+          const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                   __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
+            if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
+            if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            *reinterpret_cast<float4*>(dst + c) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side: tensor maps, plan, launch
+// ---------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  auto fn = get_encode_fn();
+  B200_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm_tc: operand base %p not 16-byte aligned", (const void*)base);
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d "
+               "(rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r, rank,
+               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+               (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+}  // namespace
+
+struct TcGemmPlan {
+  TcParams prm;
+  int bn;
+};
+
+bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
+  static const char* w;
+  auto fail = [&](const char* m) { w = m; if (why) *why = w; return false; };
+  if (d.C1 % BKE || d.C2 % BKE || d.C1 <= 0) return fail("channel counts must be multiples of 32");
+  if (d.N_total % 128) return fail("N must be a multiple of 128");
+  if (d.taps != 1 && d.taps != 9) return fail("only 1x1 and 3x3 filters");
+  if (d.conv) {
+    if (d.nbatch != 1) return fail("conv mode is unbatched");
+    const int HW = d.H * d.W;
+    if (HW >= BM) {
+      if (d.W >= BM) { if (d.W % BM) return fail("image width does not tile 128 pixels"); }
+      else if ((BM % d.W) || (d.H % (BM / d.W))) return fail("image rows do not tile 128 pixels");
+    } else if (BM % HW) return fail("image size does not divide 128 pixels");
+  } else {
+    if (d.nbatch > 1 && (d.M_per_batch % BM)) return fail("batched gemm needs M_per_batch % 128 == 0");
+    if (d.a_ld % 4) return fail("A row pitch must be a multiple of 4 floats");
+  }
+  if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
+  if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 floats");
+  return true;
+}
+
+int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
+  const char* why = nullptr;
+  B200_REQUIRE(tc_gemm_supported(d, &why), "gemm_tc: unsupported shape: %s", why ? why : "?");
+  TcGemmPlan* pl = new TcGemmPlan();
+  TcParams& p = pl->prm;
+  memset(&p, 0, sizeof(p));
+  pl->bn = (d.N_total % 256 == 0) ? 256 : 128;
+  p.conv = d.conv; p.H = d.conv ? d.H : 1; p.W = d.conv ? d.W : 1; p.taps = d.taps;
+  p.S = d.taps == 9 ? 3 : 1; p.pad = d.taps == 9 ? 1 : 0;
+  p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
+  p.N_total = d.N_total; p.tiles_n = d.N_total / pl->bn;
+  p.a_batch_rows = d.a_batch_rows; p.w_batch_rows = d.w_batch_rows;
+  p.epi = d.epi;
+
+  int rc = 0;
+  if (d.conv) {
+    const int HW = d.H * d.W;
+    const long long M = (long long)d.nimg * HW;
+    p.nbatch = 1; p.M_per_batch = (int)M; p.tiles_m_per_batch = (int)((M + BM - 1) / BM);
+    uint32_t box[4];
+    if (HW >= BM) { box[1] = std::min(d.W, BM); box[2] = BM / box[1]; box[3] = 1; }
+    else { box[1] = d.W; box[2] = d.H; box[3] = BM / HW; }
+    box[0] = BKE;
+    for (int s = 0; s < 2; ++s) {
+      const float* base = s ? d.a2 : d.a1;
+      const int C = s ? d.C2 : d.C1;
+      if (!base) continue;
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.nimg};
+      uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)d.W * C * 4, (uint64_t)HW * C * 4};
+      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box);
+      if (rc) { delete pl; return rc; }
+    }
+  } else {
+    p.nbatch = d.nbatch; p.M_per_batch = d.M_per_batch; p.tiles_m_per_batch = (d.M_per_batch + BM - 1) / BM;
+    uint32_t box[4] = {BKE, BM, 1, 1};
+    for (int s = 0; s < 2; ++s) {
+      const float* base = s ? d.a2 : d.a1;
+      if (!base) continue;
+      uint64_t dims[4] = {(uint64_t)(s ? d.C2 : d.C1), (uint64_t)d.a_rows, 1, 1};
+      uint64_t str[3] = {(uint64_t)d.a_ld * 4, (uint64_t)d.a_ld * 4 * d.a_rows, (uint64_t)d.a_ld * 4 * d.a_rows};
+      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box);
+      if (rc) { delete pl; return rc; }
+    }
+  }
+  if (!d.a2) p.tmA2 = p.tmA1;
+  {
+    uint64_t dims[2] = {(uint64_t)d.K_total, (uint64_t)d.w_rows};
+    uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * 4};
+    uint32_t box[2] = {BKE, (uint32_t)pl->bn};
+    rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
+    if (rc) { delete pl; return rc; }
+  }
+  p.total_tiles = (long long)p.nbatch * p.tiles_m_per_batch * p.tiles_n;
+  *out = pl;
+  return 0;
+}
+
+void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
+void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
+
+template <int BN, int STAGES>
+static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int grid = (int)std::min<long long>(pl->prm.total_tiles, num_sms());
+  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL, st>>>(pl->prm);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
+  if (pl->prm.total_tiles == 0) return 0;
+  return pl->bn == 256 ? launch_impl<256, 4>(pl, st) : launch_impl<128, 6>(pl, st);
+}
+
+}  // namespace b200

@@ -1,0 +1,109 @@
+// Internal launch interface between the engine (engine.cu), the C-ABI (api.cu)
+// and the kernel translation units.  Every launcher returns 0 on success and has
+// already recorded the message for b200_last_error() otherwise.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <algorithm>
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- elementwise.cu --------------------------------------------------------
+int launch_gn_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int G,
+                    float eps, float* stats, cudaStream_t st);
+int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const float* stats,
+                    const float* gamma, const float* beta, int B, int HW, int G, int act,
+                    int round_out, float* y, float* raw, cudaStream_t st);
+int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
+                     int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                     int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_out, cudaStream_t st);
+int launch_fused_bias_act(const float* x, const float* b, const float* ref, float* y, long long n,
+                          int step_b, int size_b, int act, int grad, float alpha, float scale,
+                          cudaStream_t st);
+int launch_softmax_rows(const float* s, float* p, long long rows, int T, float scale, int round_out,
+                        cudaStream_t st);
+int launch_fourier_embed(const float* sigma, long long sigma_stride, const float* W, int nf, int rows,
+                         float* emb, cudaStream_t st);
+int launch_linear_rows(const float* x, long long ldx, const float* W, const float* bias, int rows, int N,
+                       int K, int act_in, float* y, long long ldy, cudaStream_t st);
+int launch_fill_from_table(const float* table, const int* step, float* dst, int n, cudaStream_t st);
+int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cudaStream_t st);
+int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, long long so, long long si,
+                       long long stp, int round_out, cudaStream_t st);
+
+// ---- conv_simt.cu : strict-fp32 CUDA-core implicit GEMM (any shape) ---------
+struct SimtConv {
+  // A operand
+  const float* x1; int C1;          // first source (NHWC, or NCHW when in_nchw)
+  const float* x2; int C2;          // optional second source, channel-concatenated after x1
+  long long ld1, ld2;               // pixel pitch of each source in elements (0 = C1 / C2)
+  int in_nchw;                      // x1 is [img][C1][H][W] (network input); x2 must be null
+  float in_scale, in_shift;         // a*x+b applied to in-bounds input samples (2x-1 centring)
+  int H, W;                         // input spatial size (gemm mode: H=rows per batch, W=1)
+  int R, S, stride, pad;            // filter geometry (gemm mode: 1,1,1,0)
+  int OH, OW;                       // output spatial size
+  int nbatch;                       // images (conv) or batch items (gemm)
+  long long a_batch_stride;         // elements between batch items of A (conv: H*W*C per source, implied)
+  int a_batched;                    // gemm mode: 0 = A shared by all batch items
+  // W operand: [tap][N][Cin] (Cin contiguous), optionally one per batch item
+  const float* w; int N; long long w_batch_stride;
+  long long w_ld;                   // row pitch of W in elements (0 = Cin)
+  Epilogue epi;
+};
+int launch_conv_simt(const SimtConv& p, cudaStream_t st);
+
+// ---- gemm_tc.cu : tcgen05 / TMEM / TMA implicit GEMM (TF32 operands) -------
+struct TcGemmPlan;   // opaque, owns the encoded tensor maps
+struct TcGemmDesc {
+  // A: NHWC activations, values already on the TF32 grid.
+  const float* a1; int C1; const float* a2; int C2;     // two-source channel concat (a2 may be null)
+  int conv;                 // 1: 4-D box gather with zero halo; 0: plain row-major [rows, K]
+  int H, W, nimg;           // conv geometry (stride 1, 'same' padding); gemm: unused
+  int taps;                 // 9 (3x3) or 1
+  long long a_rows;         // gemm: total rows of A; a_ld = row pitch in elements
+  long long a_ld;
+  int a_batch_rows;         // gemm: rows to advance per batch item (0 = shared)
+  // W: [tap][N_total][K_total] row-major (K contiguous), TF32 grid.
+  const float* w; int N_total; int K_total; long long w_rows;
+  long long w_ld;           // row pitch of W in elements (0 = K_total)
+  int w_batch_rows;         // rows to advance per batch item (0 = shared)
+  int nbatch; int M_per_batch;   // gemm: rows of output per batch item; conv: nbatch=1, M=nimg*H*W
+  Epilogue epi;
+};
+int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out);
+void tc_gemm_plan_destroy(TcGemmPlan* p);
+int tc_gemm_launch(const TcGemmPlan* p, cudaStream_t st);
+bool tc_gemm_supported(const TcGemmDesc& d, const char** why);
+
+// ---- pc_update.cu -----------------------------------------------------------
+struct PhiloxMap {          // torch.randn_like's launch geometry for `numel` elements
+  unsigned long long seed;
+  long long numel;
+  int grid, block;          // torch's grid/block => thread stride for element ownership
+  unsigned long long inc;   // Philox offset consumed per randn call
+};
+int philox_map_init(PhiloxMap* m, long long numel, unsigned long long seed);
+int launch_randn_torch(const PhiloxMap& m, const unsigned long long* offset_dev, unsigned long long offset_add,
+                       float* out, cudaStream_t st);
+struct PcStepScalars {       // device tables indexed by the step counter
+  const float* score_scale;  // multiplies the network output to give the score (VE: 1, VP: -1/std)
+  const float* alpha;        // Langevin alpha_i
+  const float* pa;           // predictor: x_mean = pa*x + pb*out
+  const float* pb;
+  const float* pc;           // x = x_mean + pc*z
+};
+int launch_pc_norms(const float* out, const float* noise, const PhiloxMap& m, const unsigned long long* offset_dev,
+                    const int* step, unsigned long long calls_per_step, unsigned long long call_idx,
+                    int B, int per_img, float* norms, float* means, cudaStream_t st);
+int launch_langevin_apply(float* x, float* x_mean, const float* out, const float* noise, const PhiloxMap& m,
+                          const unsigned long long* offset_dev, const int* step,
+                          unsigned long long calls_per_step, unsigned long long call_idx,
+                          const float* means, float snr, PcStepScalars sc, cudaStream_t st);
+int launch_predictor_apply(float* x, float* x_mean, const float* out, const float* noise, const PhiloxMap& m,
+                           const unsigned long long* offset_dev, const int* step,
+                           unsigned long long calls_per_step, unsigned long long call_idx,
+                           PcStepScalars sc, int add_noise, cudaStream_t st);
+int launch_step_increment(int* step, cudaStream_t st);
+
+}  // namespace b200

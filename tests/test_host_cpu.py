@@ -1,0 +1,176 @@
+"""CPU tests of the host-side mirror of the reference surface (sampling / sde_lib /
+models.utils), of the schedule tables handed to the native loop, and of the C-ABI library
+(loads, exports every declared symbol; no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, golden_config, seeded_model, rel_l2
+from oracle import ncsnpp_oracle as NO
+from score_sde_pytorch_b200 import _lib, configs, native, sampling, sde_lib
+from score_sde_pytorch_b200.models import utils as mutils
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class TorchModel(torch.nn.Module):
+  """A user-style nn.Module score model (oracle arithmetic) to drive the generic host loop."""
+
+  def __init__(self, cfg):
+    super().__init__()
+    self.cfg = cfg
+    self.sd = seeded_model(cfg).state_dict()
+
+  def forward(self, x, labels):
+    return NO.ncsnpp_forward(self.sd, self.cfg, x, labels)
+
+
+def test_generic_pc_loop_matches_reference_ve():
+  g = golden('pc_ve_tiny.npz')
+  cfg = golden_config('tiny')
+  cfg.device = torch.device('cpu')
+  model = TorchModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny.npz')['x'].shape)
+  sde = sde_lib.VESDE(0.01, 50, 12)
+  fn = sampling.get_pc_sampler(sde, shape, sampling.ReverseDiffusionPredictor, sampling.LangevinCorrector,
+                               lambda v: v, snr=0.16, n_steps=1, continuous=True, denoise=True, eps=1e-5, device='cpu')
+  torch.manual_seed(11)
+  s, nfe = fn(model)
+  assert nfe == int(g['nfe']) == 24
+  assert rel_l2(s, torch.from_numpy(g['rd_langevin'])) < 1e-5
+
+
+def test_get_sampling_fn_vp_em_plumbing():
+  """BASELINE.json configs[0]-style plumbing: VP SDE, Euler-Maruyama predictor only, 20 steps, B=2, CPU."""
+  g = golden('pc_vp_tiny.npz')
+  cfg = golden_config('tiny_vp')
+  cfg.device = torch.device('cpu')
+  cfg.sampling.predictor, cfg.sampling.corrector = 'euler_maruyama', 'none'
+  model = TorchModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny_vp.npz')['x'].shape)
+  sde = sde_lib.VPSDE(0.1, 20., 20)
+  fn = sampling.get_sampling_fn(cfg, sde, shape, lambda v: v, 1e-3)
+  torch.manual_seed(21)
+  s, nfe = fn(model)
+  assert nfe == 40          # N*(n_steps+1) even with the None corrector (sampling.py:409)
+  assert rel_l2(s, torch.from_numpy(g['em_none'])) < 1e-5
+  cfg.sampling.predictor, cfg.sampling.corrector = 'reverse_diffusion', 'langevin'
+  fn = sampling.get_sampling_fn(cfg, sde, shape, lambda v: v, 1e-3)
+  torch.manual_seed(22)
+  s, _ = fn(model)
+  assert rel_l2(s, torch.from_numpy(g['rd_langevin'])) < 1e-5
+
+
+def test_registries_and_errors():
+  assert sampling.get_predictor('reverse_diffusion') is sampling.ReverseDiffusionPredictor
+  assert sampling.get_corrector('langevin') is sampling.LangevinCorrector
+  assert set(sampling._PREDICTORS) >= {'euler_maruyama', 'reverse_diffusion', 'ancestral_sampling', 'none'}
+  assert set(sampling._CORRECTORS) >= {'langevin', 'ald', 'none'}
+  with pytest.raises(ValueError):
+    sampling.register_predictor(name='none')(sampling.NonePredictor)
+  with pytest.raises(ValueError):
+    mutils.register_model(name='ncsnpp')(object)
+
+  @sampling.register_corrector
+  class MyCorrector(sampling.Corrector):
+    def update_fn(self, x, t):
+      return x, x
+  assert sampling.get_corrector('MyCorrector') is MyCorrector
+  del sampling._CORRECTORS['MyCorrector']
+
+  cfg = configs.ve_cifar10_ncsnpp_continuous()
+  cfg.sampling.method = 'bogus'
+  with pytest.raises(ValueError):
+    sampling.get_sampling_fn(cfg, sde_lib.VESDE(), (1, 3, 32, 32), lambda v: v, 1e-5)
+
+  class OtherSDE(sde_lib.SDE):
+    T = 1
+    def sde(self, x, t): return x, t
+    def marginal_prob(self, x, t): return x, t
+    def prior_sampling(self, shape): return torch.zeros(*shape)
+    def prior_logp(self, z): return z
+  with pytest.raises(NotImplementedError):
+    mutils.get_score_fn(OtherSDE(10), lambda x, t: x)
+  with pytest.raises(NotImplementedError):
+    sampling.LangevinCorrector(OtherSDE(10), None, 0.1, 1)
+
+
+def test_schedule_tables_match_reference_scalars():
+  g = golden('sde_tables.npz')
+  tb = native.build_tables(sde_lib.VESDE(0.01, 50, 1000), 'reverse_diffusion', 'langevin', False, 1e-5)
+  assert np.array_equal(tb['label'], g['ve_sigma'])
+  assert np.array_equal(tb['pc'], g['ve_G'])
+  assert np.allclose(tb['pb'], g['ve_G'] ** 2, rtol=1e-6)
+  vp = native.build_tables(sde_lib.VPSDE(0.1, 20., 1000), 'reverse_diffusion', 'langevin', False, 1e-3)
+  assert np.array_equal(vp['pc'], g['vp_G'])
+  # x_mean = x - f - ... with x = 1: pa = 1 - f
+  assert np.allclose(vp['pa'], 1.0 - g['vp_f'], rtol=1e-6)
+  assert np.allclose(vp['score_scale'], -1.0 / g['vp_std'], rtol=1e-6)
+
+
+def test_affine_predictor_tables_reproduce_host_predictors():
+  """The (pa, pb, pc) tables must reproduce the class-based predictors for arbitrary network outputs."""
+  torch.manual_seed(0)
+  x = torch.randn(3, 2, 4, 4)
+  out = torch.randn(3, 2, 4, 4)
+  z = torch.randn(3, 2, 4, 4)
+  for sde, eps in ((sde_lib.VESDE(0.01, 50, 50), 1e-5), (sde_lib.VPSDE(0.1, 20., 50), 1e-3), (sde_lib.subVPSDE(0.1, 20., 50), 1e-3)):
+    for kind, cls in (('reverse_diffusion', sampling.ReverseDiffusionPredictor), ('euler_maruyama', sampling.EulerMaruyamaPredictor)):
+      for pf in (False, True):
+        if pf and kind == 'euler_maruyama':
+          continue   # the reference's EM predictor cannot run with probability_flow (float diffusion is indexed, sampling.py:186)
+        tb = native.build_tables(sde, kind, 'none', pf, eps)
+        ts = torch.linspace(sde.T, eps, sde.N)
+        for i in (0, 7, sde.N - 1):
+          t = torch.ones(3) * ts[i]
+          score_fn = mutils.get_score_fn(sde, torch.nn.Identity(), train=False, continuous=True)
+          score_fn._model_fn = lambda xx, labels: out      # fixed "network output"
+          pred = cls(sde, score_fn, pf)
+          torch.manual_seed(5)
+          xn, xm = pred.update_fn(x, t)
+          torch.manual_seed(5)
+          zz = torch.randn_like(x)
+          xm2 = float(tb['pa'][i]) * x + float(tb['pb'][i]) * out
+          xn2 = xm2 + float(tb['pc'][i]) * zz
+          assert torch.allclose(xm, xm2, rtol=2e-5, atol=2e-5), (type(sde).__name__, kind, pf, i)
+          assert torch.allclose(xn, xn2, rtol=2e-5, atol=2e-5), (type(sde).__name__, kind, pf, i)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+  lib = _lib.load()
+  assert lib.b200_version() >= 100
+  header = open(os.path.join(REPO, 'include', 'scoresde_b200.h')).read()
+  declared = set(re.findall(r'B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(', header))
+  assert declared, 'no declarations parsed'
+  for name in declared:
+    assert hasattr(lib, name), f'{name} declared in the header but not exported'
+  assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+  err = lib.b200_last_error()
+  assert isinstance(err, bytes)
+
+
+def test_engine_param_table_matches_module_and_reference_names():
+  for name in ('tiny', 'tiny_noattn', 'cifar10_ve'):
+    cfg = golden_config(name)
+    m = seeded_model(cfg)
+    table = m.native_param_table()
+    sd = dict(m.named_parameters())
+    assert [n for n, _ in table if n not in sd] == []
+    assert sorted(n for n, _ in table) == sorted(sd)
+    for n, shape in table:
+      assert tuple(sd[n].shape) == shape
+  assert sum(p.numel() for p in seeded_model(golden_config('cifar10_ve')).parameters()) == 62758915
+
+
+def test_product_model_has_no_cpu_path():
+  m = seeded_model(golden_config('tiny'))
+  with pytest.raises(RuntimeError, match='CUDA'):
+    m(torch.zeros(1, 3, 16, 16), torch.ones(1))
+  cfg = golden_config('tiny')
+  cfg.model.resblock_type = 'ddpm'
+  with pytest.raises(NotImplementedError):
+    seeded_model(cfg)

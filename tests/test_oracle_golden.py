@@ -1,0 +1,99 @@
+"""Pin the oracle (oracle/*.py) against fixtures produced by the real reference
+(tools/make_golden.py).  CPU only; these are the `-m "not gpu"` parity anchors."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, golden_config, seeded_model, rel_l2
+from oracle import ncsnpp_oracle as NO
+from oracle import sampling_oracle as SO
+
+
+@pytest.mark.parametrize('name', ['down2', 'up2', 'pad22', 'generic'])
+def test_upfirdn2d_oracle_matches_reference(name):
+  g = golden('upfirdn2d.npz')
+  up, down, p0, p1 = [int(v) for v in g[name + '_p']]
+  y = NO.upfirdn2d_native(torch.from_numpy(g[name + '_x']), torch.from_numpy(g[name + '_k']), up=up, down=down, pad=(p0, p1))
+  assert y.shape == g[name + '_y'].shape
+  assert torch.equal(y, torch.from_numpy(g[name + '_y']))
+
+
+@pytest.mark.parametrize('name', ['tiny', 'tiny_vp', 'tiny_noattn'])
+def test_ncsnpp_oracle_matches_reference(name):
+  g = golden(f'ncsnpp_{name}.npz')
+  cfg = golden_config(name)
+  sd = seeded_model(cfg).state_dict()
+  taps = {}
+  with torch.no_grad():
+    y = NO.ncsnpp_forward(sd, cfg, torch.from_numpy(g['x']), torch.from_numpy(g['sigma']), taps=taps)
+  for i, v in sorted(taps.items()):
+    key = f'tap{i}'
+    if key in g:
+      assert rel_l2(v, torch.from_numpy(g[key])) < 2e-6, f'module {i} diverges from the reference'
+  assert rel_l2(y, torch.from_numpy(g['y'])) < 2e-6
+
+
+def test_ncsnpp_oracle_matches_reference_cifar10():
+  g = golden('ncsnpp_cifar10_ve.npz')
+  cfg = golden_config('cifar10_ve')
+  sd = seeded_model(cfg).state_dict()
+  taps = {}
+  with torch.no_grad():
+    y = NO.ncsnpp_forward(sd, cfg, torch.from_numpy(g['x']), torch.from_numpy(g['sigma']), taps=taps)
+  assert rel_l2(y, torch.from_numpy(g['y'])) < 5e-6
+  for i, v in taps.items():
+    ref = g['tap_norms'][i]
+    if ref > 0:
+      assert abs(float(v.double().norm()) - ref) / ref < 5e-6, f'module {i}'
+
+
+class _OracleModel:
+  def __init__(self, cfg):
+    self.cfg = cfg
+    self.sd = seeded_model(cfg).state_dict()
+
+  def __call__(self, x, labels):
+    return NO.ncsnpp_forward(self.sd, self.cfg, x, labels)
+
+
+def test_pc_sampler_oracle_matches_reference_ve():
+  g = golden('pc_ve_tiny.npz')
+  cfg = golden_config('tiny')
+  model = _OracleModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny.npz')['x'].shape)
+  sde = SO.VE(0.01, 50, 12)
+  torch.manual_seed(11)
+  s, nfe = SO.pc_sample(sde, model, shape, 'reverse_diffusion', 'langevin', snr=0.16, n_steps=1, eps=1e-5)
+  assert nfe == int(g['nfe'])
+  assert rel_l2(s, torch.from_numpy(g['rd_langevin'])) < 1e-5
+  torch.manual_seed(12)
+  s2, nfe2 = SO.pc_sample(sde, model, shape, 'euler_maruyama', 'none', snr=0.16, n_steps=1, eps=1e-5, denoise=False)
+  assert nfe2 == int(g['nfe2'])
+  assert rel_l2(s2, torch.from_numpy(g['em_none'])) < 1e-5
+
+
+def test_pc_sampler_oracle_matches_reference_vp():
+  g = golden('pc_vp_tiny.npz')
+  cfg = golden_config('tiny_vp')
+  model = _OracleModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny_vp.npz')['x'].shape)
+  sde = SO.VP(0.1, 20., 20)
+  torch.manual_seed(21)
+  s, _ = SO.pc_sample(sde, model, shape, 'euler_maruyama', 'none', eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['em_none'])) < 1e-5
+  torch.manual_seed(22)
+  s, _ = SO.pc_sample(sde, model, shape, 'reverse_diffusion', 'langevin', eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['rd_langevin'])) < 1e-5
+
+
+def test_sde_tables_match_reference():
+  g = golden('sde_tables.npz')
+  ve = SO.VE(0.01, 50, 1000)
+  t = torch.linspace(1, 1e-5, 1000)
+  assert np.array_equal(ve.discretize(torch.zeros(1000, 1, 1, 1), t)[1].numpy(), g['ve_G'])
+  assert np.array_equal(ve.sigma(t).numpy(), g['ve_sigma'])
+  vp = SO.VP(0.1, 20., 1000)
+  t3 = torch.linspace(1, 1e-3, 1000)
+  f, G = vp.discretize(torch.ones(1000, 1, 1, 1), t3)
+  assert np.array_equal(f.reshape(-1).numpy(), g['vp_f']) and np.array_equal(G.numpy(), g['vp_G'])
+  assert np.array_equal(vp.std(t3).numpy(), g['vp_std'])
