@@ -113,6 +113,12 @@ B200_API int b200_ncsnpp_forward(b200_ncsnpp_t* h, const float* x_nchw, const fl
 B200_API int b200_ncsnpp_tap(b200_ncsnpp_t* h, int module_index, float* dst_nchw, long long dst_cap_elems,
                              int shape_out[4], void* stream);
 B200_API long long b200_ncsnpp_launches_per_forward(const b200_ncsnpp_t* h);
+/* One eager forward with a CUDA-event pair around every op; per-kind totals (kind 0 tcgen05
+ * contraction, 1 CUDA-core contraction, 2 GroupNorm, 3 FIR, 4 softmax, 5 time embedding, 6 misc):
+ * device milliseconds, algorithmic FLOPs (2*M*N*K of the contractions) and op counts. */
+B200_API int b200_ncsnpp_profile_forward(b200_ncsnpp_t* h, const float* x_nchw, const float* labels,
+                                         int labels_uniform, float* out_nchw, void* stream,
+                                         float ms_by_kind[8], double flops_by_kind[8], long long ops_by_kind[8]);
 
 /* ---- predictor–corrector loop --------------------------------------------------
  * Replaces the body of pc_sampler (sampling.py:390-409) with

@@ -69,6 +69,8 @@ SIGNATURES = {
   'b200_ncsnpp_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
   'b200_ncsnpp_tap': (c_int, [c_void_p, c_int, c_void_p, c_ll, P(c_int), c_void_p]),
   'b200_ncsnpp_launches_per_forward': (c_ll, [c_void_p]),
+  'b200_ncsnpp_profile_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                          P(c_float), P(ctypes.c_double), P(c_ll)]),
   'b200_pc_create': (c_int, [c_void_p, P(PcConfig), c_int, P(c_void_p)]),
   'b200_pc_destroy': (None, [c_void_p]),
   'b200_pc_workspace_bytes': (c_ll, [c_void_p]),
@@ -89,9 +91,9 @@ def load():
   with _LOCK:
     if _LIB is not None:
       return _LIB
-    path = _build.LIB
-    if not os.path.exists(path):
-      path = _build.build()
+    # build() is a no-op when the in-tree .so matches the source digest; a stale or missing
+    # library is rebuilt with nvcc (raises if that is impossible: there is no other code path)
+    path = _build.build()
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
       fn = getattr(lib, name)   # AttributeError here == header/library mismatch; let it surface

@@ -101,7 +101,8 @@ struct b200_ncsnpp {
   float fir2d[64]; int firn = 0;
   // plan
   int B = 0; char* ws = nullptr; long long ws_bytes = 0;
-  std::vector<std::function<int(cudaStream_t)>> ops;
+  struct Op { int kind; double flops; std::function<int(cudaStream_t)> fn; };
+  std::vector<Op> ops;
   std::vector<TcGemmPlan*> tcplans;
   std::map<int, Tensor> taps;
   long long launches = 0;
@@ -299,10 +300,11 @@ struct Builder {
   void tfree(Tensor& t) { if (t.p) arena.release((char*)t.p - base, t.bytes); t.p = nullptr; }
   void ffree(float* p, long long bytes) { arena.release((char*)p - base, bytes); }
 
-  void op(int launches, std::function<int(cudaStream_t)> f) {
+  // kind: 0 tcgen05 contraction, 1 CUDA-core contraction, 2 GroupNorm, 3 FIR, 4 softmax, 5 time embedding, 6 misc
+  void op(int launches, std::function<int(cudaStream_t)> f, int kind = 6, double flops = 0.0) {
     if (dry) return;
     e->launches += launches;
-    e->ops.push_back(std::move(f));
+    e->ops.push_back({kind, flops, std::move(f)});
   }
 
   void gn(Tensor x1, Tensor x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
@@ -313,7 +315,7 @@ struct Builder {
     op(2, [=](cudaStream_t st) {
       if (int r = launch_gn_stats(x1.p, x1.C, x2.p, x2.C, Bc, HW, G, 1e-6f, stats, st)) return r;
       return launch_gn_apply(x1.p, x1.C, x2.p, x2.C, stats, g, bt, Bc, HW, G, act, round, y.p, raw, st);
-    });
+    }, 2);
     ffree(stats, sb);
   }
 
@@ -325,7 +327,7 @@ struct Builder {
     const int n = e->firn;
     op(1, [=](cudaStream_t st) {
       return launch_upfirdn2d(x, k.data(), y, major, H, W, minor, n, n, up, up, down, down, pad0, pad1, pad0, pad1, round, st);
-    });
+    }, 3);
   }
 
   // 3x3 / 1x1 'same' convolution on NHWC tensors, stride 1.
@@ -339,6 +341,7 @@ struct Builder {
     b200_ncsnpp* eng = e;
     const float* dense_all = dense_all_;
     const int sumC = e->sumC;
+    const double cflops = 2.0 * B * a1.H * a1.W * (double)Cout * (a1.C + a2.C) * taps;
     if (use_tc) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = a1.H; d.W = a1.W; d.nimg = B; d.taps = taps;
@@ -352,7 +355,7 @@ struct Builder {
       op(1, [=](cudaStream_t st) {
         if (dense_row >= 0) tc_gemm_set_rowvec_ld(pl, eng->uniform ? 0 : sumC);
         return tc_gemm_launch(pl, st);
-      });
+      }, 0, cflops);
     } else {
       SimtConv s; memset(&s, 0, sizeof(s));
       s.x1 = a1.p; s.C1 = a1.C; s.x2 = a2.p; s.C2 = a2.C; s.in_scale = 1.f; s.in_shift = 0.f;
@@ -364,7 +367,7 @@ struct Builder {
         SimtConv c = s;
         if (dense_row >= 0) c.epi.rowvec_ld = eng->uniform ? 0 : sumC;
         return launch_conv_simt(c, st);
-      });
+      }, 1, cflops);
     }
   }
 
@@ -384,14 +387,14 @@ struct Builder {
       TcGemmPlan* pl = nullptr;
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
       e->tcplans.push_back(pl);
-      op(1, [=](cudaStream_t st) { return tc_gemm_launch(pl, st); });
+      op(1, [=](cudaStream_t st) { return tc_gemm_launch(pl, st); }, 0, 2.0 * nbatch * (double)M * N * K);
     } else {
       SimtConv s; memset(&s, 0, sizeof(s));
       s.x1 = A; s.C1 = K; s.ld1 = lda; s.in_scale = 1.f; s.H = M; s.W = 1; s.R = s.S = 1; s.stride = 1; s.pad = 0;
       s.OH = M; s.OW = 1; s.nbatch = nbatch; s.a_batched = a_batch_rows != 0; s.w = Wm; s.N = N;
       s.w_batch_stride = (long long)w_batch_rows * ldw; s.w_ld = ldw;
       ep.rows_per_img = M; s.epi = ep;
-      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); });
+      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * nbatch * (double)M * N * K);
     }
   }
 
@@ -467,7 +470,7 @@ struct Builder {
     ffree(qk, qkb);
     const float sc = 1.0f / std::sqrt((float)C);   // int(C) ** -0.5
     const int Bc = B;
-    op(1, [=](cudaStream_t st) { return launch_softmax_rows(S, S, (long long)Bc * T, T, sc, tc ? 1 : 0, st); });
+    op(1, [=](cudaStream_t st) { return launch_softmax_rows(S, S, (long long)Bc * T, T, sc, tc ? 1 : 0, st); }, 4);
     float* O = falloc(BT * C, &ob);
     // h[b][q][c] = sum_k P[q][k] v[k][c] + bv[c]   (layerspp.py:86)
     gemm(tc, S, T, BT, T, vT, T, (long long)B * C, C, B, T, C, T, bqkv + 2 * C, nullptr, 0, 1.f, m.tc2 ? 1 : 0, O, C);
@@ -501,7 +504,7 @@ struct Builder {
         if (int r = launch_linear_rows(emb, 2 * nf, W1, b1, rows, 4 * nf, 2 * nf, 0, t1, 4 * nf, st)) return r;
         if (int r = launch_linear_rows(t1, 4 * nf, W2, b2, rows, 4 * nf, 4 * nf, 1, t2, 4 * nf, st)) return r;
         return launch_linear_rows(t2, 4 * nf, Wd, bd, rows, sumC, 4 * nf, 1, dense_all, sumC, st);
-      });
+      }, 5);
     }
     // ---- input (ncsnpp.py:259-268) ----
     float* xc = falloc((long long)B * ch * R * R, &xcb);   // 2x-1 when data is not centred; NCHW
@@ -523,7 +526,7 @@ struct Builder {
       s.x1 = xc; s.C1 = ch; s.in_nchw = 1; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
       s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = e->W(m.w); s.N = nf;
       s.epi.bias = e->W(m.b); s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out = h0.p; s.epi.ld_out = nf;
-      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); });
+      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * B * R * R * (double)nf * ch * 9);
       hs.push_back(h0);
       tap(m.index, h0);
     }
@@ -563,12 +566,12 @@ struct Builder {
           s.epi.scale = c.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
           s.epi.rows_per_img = h.H * h.W; s.epi.out = np.p; s.epi.ld_out = mp.cout;
           if ((Hp - 3) / 2 + 1 != h.H) { set_error("ncsnpp: pyramid geometry mismatch (%d vs %d)", (Hp - 3) / 2 + 1, h.H); return 2; }
-          op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); });
+          op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * B * h.H * h.W * (double)mp.cout * pyr.C * 9);
           ffree(fbuf, fb);
           if (pyr_owned) tfree(pyr);
           tfree(h);
           h = np; pyr = np; pyr_nchw = false; pyr_owned = false;   // h aliases the pyramid from here on (it lives in hs)
-          tap(mp.index, np);
+          // (no debug tap: the reference module's own output is the pre-combine conv result, which is never materialised)
         }
         hs.push_back(h);
       }
@@ -613,7 +616,7 @@ struct Builder {
         cc.epi.out = eng->out;
         if (sbs) { cc.epi.per_img_div = eng->in_labels; cc.epi.div_stride = eng->uniform ? 0 : 1; }
         return launch_conv_simt(cc, st);
-      });
+      }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
       tfree(a);
     }
     if (mi != e->mods.size()) { set_error("ncsnpp: plan walked %zu of %zu modules", mi, e->mods.size()); return 2; }
@@ -709,8 +712,38 @@ int b200_ncsnpp_forward(b200_ncsnpp_t* h, const float* x, const float* labels, i
   B200_REQUIRE(!h->ops.empty(), "forward: no plan bound (call b200_ncsnpp_bind_workspace)");
   h->in_x = x; h->in_labels = labels; h->out = out; h->uniform = uniform;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (auto& f : h->ops) if (int r = f(st)) return r;
+  for (auto& o : h->ops) if (int r = o.fn(st)) return r;
   return 0;
+}
+
+int b200_ncsnpp_profile_forward(b200_ncsnpp_t* h, const float* x, const float* labels, int uniform, float* out,
+                                void* stream, float ms_by_kind[8], double flops_by_kind[8], long long ops_by_kind[8]) {
+  B200_REQUIRE(h && x && labels && out && ms_by_kind, "profile_forward: null argument");
+  B200_REQUIRE(!h->ops.empty(), "profile_forward: no plan bound");
+  h->in_x = x; h->in_labels = labels; h->out = out; h->uniform = uniform;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int k = 0; k < 8; ++k) { ms_by_kind[k] = 0.f; if (flops_by_kind) flops_by_kind[k] = 0.0; if (ops_by_kind) ops_by_kind[k] = 0; }
+  std::vector<cudaEvent_t> ev(h->ops.size() + 1);
+  for (auto& e : ev) B200_CHECK_CUDA(cudaEventCreate(&e));
+  int rc = 0;
+  B200_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  for (size_t i = 0; i < h->ops.size() && !rc; ++i) {
+    rc = h->ops[i].fn(st);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("profile_forward: stream sync failed"); rc = 1; }
+  if (!rc) {
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      const int k = h->ops[i].kind & 7;
+      ms_by_kind[k] += ms;
+      if (flops_by_kind) flops_by_kind[k] += h->ops[i].flops;
+      if (ops_by_kind) ops_by_kind[k] += 1;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int b200_ncsnpp_tap(b200_ncsnpp_t* h, int module_index, float* dst, long long cap, int shape_out[4], void* stream) {
@@ -739,6 +772,7 @@ struct b200_pc {
   int* d_step; unsigned long long* d_offset;
   PhiloxMap map;
   cudaGraphExec_t gexec = nullptr; float* graph_x = nullptr; float* graph_xm = nullptr; cudaStream_t graph_stream = nullptr;
+  unsigned long long graph_seed = 0;
   long long launches_per_step = 0;
   ~b200_pc() { if (gexec) cudaGraphExecDestroy(gexec); }
 };
@@ -850,7 +884,7 @@ int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_
   B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_step, &first_step, 4, cudaMemcpyHostToDevice, st));
   B200_CHECK_CUDA(cudaStreamSynchronize(st));   // host sources above are stack variables
   if (use_graph && num_steps > 0) {
-    if (!pc->gexec || pc->graph_x != x || pc->graph_xm != x_mean || pc->map.seed != seed || pc->graph_stream != st) {
+    if (!pc->gexec || pc->graph_x != x || pc->graph_xm != x_mean || pc->graph_seed != seed || pc->graph_stream != st) {
       if (pc->gexec) { cudaGraphExecDestroy(pc->gexec); pc->gexec = nullptr; }
       cudaGraph_t g = nullptr;
       B200_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -860,7 +894,7 @@ int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_
       B200_CHECK_CUDA(ce);
       B200_CHECK_CUDA(cudaGraphInstantiate(&pc->gexec, g, 0));
       cudaGraphDestroy(g);
-      pc->graph_x = x; pc->graph_xm = x_mean; pc->graph_stream = st;
+      pc->graph_x = x; pc->graph_xm = x_mean; pc->graph_stream = st; pc->graph_seed = seed;
     }
     for (int i = 0; i < num_steps; ++i) B200_CHECK_CUDA(cudaGraphLaunch(pc->gexec, st));
   } else {

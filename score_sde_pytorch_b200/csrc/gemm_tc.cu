@@ -339,6 +339,8 @@ struct TcGemmPlan {
   int bn;
 };
 
+static int tc_configure();
+
 bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
   static const char* w;
   auto fail = [&](const char* m) { w = m; if (why) *why = w; return false; };
@@ -364,6 +366,7 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
 int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   const char* why = nullptr;
   B200_REQUIRE(tc_gemm_supported(d, &why), "gemm_tc: unsupported shape: %s", why ? why : "?");
+  if (int r = tc_configure()) return r;
   TcGemmPlan* pl = new TcGemmPlan();
   TcParams& p = pl->prm;
   memset(&p, 0, sizeof(p));
@@ -421,14 +424,19 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
 
+// Opt in to the large dynamic shared-memory carve-out once, outside any stream capture.
+static int tc_configure() {
+  static bool configured = false;
+  if (configured) return 0;
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6>::TOTAL));
+  configured = true;
+  return 0;
+}
+
 template <int BN, int STAGES>
 static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
   const int grid = (int)std::min<long long>(pl->prm.total_tiles, num_sms());
   gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL, st>>>(pl->prm);
   B200_CHECK_LAUNCH();

@@ -96,6 +96,7 @@ class PcPlan:
     self._pc = None
     self._ws = None
     self._engine_id = None
+    self._x = self._xm = None      # persistent state buffers: stable addresses keep the captured graph valid
     self.use_graph = True
 
   def _release(self):
@@ -129,6 +130,9 @@ class PcPlan:
     self._pc = h
     need = _lib.load().b200_pc_workspace_bytes(h)
     self._ws = torch.zeros(need // 4 + 64, dtype=torch.float32, device=self.device)
+    if self._x is None:
+      self._x = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+      self._xm = torch.empty(self.shape, dtype=torch.float32, device=self.device)
     _lib.call('b200_pc_bind_workspace', h, _lib.ptr(self._ws), self._ws.numel() * 4, _lib.stream_ptr(self.device))
     self._engine_id = key
     return eng
@@ -137,15 +141,17 @@ class PcPlan:
     idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
     return torch.cuda.default_generators[idx]
 
-  def run(self, x, first_step=0, num_steps=None):
-    """Run iterations ``[first_step, first_step+num_steps)`` from state ``x`` (NCHW).
-    Consumes the CUDA generator exactly as the reference loop would (same seed/offset
-    bookkeeping), returns ``(x, x_mean)``."""
+  def run(self, x, first_step=0, num_steps=None, clone=True):
+    """Run iterations ``[first_step, first_step+num_steps)`` from state ``x`` (NCHW; a pinned host
+    tensor is uploaded asynchronously).  Consumes the CUDA generator exactly as the reference loop
+    would (same seed/offset bookkeeping).  Returns ``(x, x_mean)`` — fresh tensors, or with
+    ``clone=False`` the plan's persistent buffers (overwritten by the next call)."""
     with torch.cuda.device(self.device):
       self._ensure()
       num_steps = self.sde.N - first_step if num_steps is None else num_steps
-      x = x.detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
-      x_mean = x.clone()
+      self._x.copy_(x.detach().reshape(self.shape), non_blocking=True)
+      self._xm.copy_(self._x)
+      x, x_mean = self._x, self._xm
       gen = self._generator()
       seed, offset = gen.initial_seed(), gen.get_offset()
       off_out = ctypes.c_ulonglong(0)
@@ -153,6 +159,8 @@ class PcPlan:
                 ctypes.c_ulonglong(seed), ctypes.c_ulonglong(offset), ctypes.byref(off_out),
                 int(self.use_graph), _lib.stream_ptr(self.device))
       gen.set_offset(int(off_out.value))
+      if clone:
+        x, x_mean = x.clone(), x_mean.clone()
     return x, x_mean
 
   def step_external(self, x, x_mean, step, noise_c, noise_p):

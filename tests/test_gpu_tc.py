@@ -1,0 +1,145 @@
+"""`-m gpu`: the tcgen05/TMEM/TMA contraction kernel against the strict-fp32 CUDA-core kernel on
+TF32-representable operands (products are then exact in fp32, so only the summation order differs),
+then the TF32 execution mode of the whole network and sampler against the strict-fp32 oracle within
+the 1e-3 per-image relative-L2 tolerance BASELINE.json states."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, golden_config, seeded_model, rel_l2
+from oracle import ncsnpp_oracle as NO
+from oracle import sampling_oracle as SO
+
+pytestmark = pytest.mark.gpu
+TOL_PARITY = 1e-3      # BASELINE.json north_star: per-image relative L2 vs reference <= 1e-3
+
+
+@pytest.fixture(scope='module')
+def dev():
+  import gpu_util
+  gpu_util.strict_fp32()
+  return torch.device('cuda:0')
+
+
+CASES = [
+    dict(B=2, H=32, W=32, C1=128, C2=0, Cout=128, k=3),
+    dict(B=2, H=16, W=16, C1=256, C2=0, Cout=256, k=3),
+    dict(B=4, H=8, W=8, C1=256, C2=0, Cout=256, k=3),
+    dict(B=3, H=4, W=4, C1=256, C2=0, Cout=256, k=3),      # 48 rows: partial tile, TMA out-of-bounds images
+    dict(B=9, H=4, W=4, C1=256, C2=256, Cout=256, k=3),    # two tiles, two-source K loop
+    dict(B=2, H=16, W=16, C1=256, C2=128, Cout=256, k=3),  # 384-channel concat
+    dict(B=2, H=32, W=32, C1=256, C2=128, Cout=128, k=1),  # 1x1 skip conv
+    dict(B=1, H=32, W=32, C1=128, C2=0, Cout=128, k=1),
+    dict(B=1, H=64, W=64, C1=32, C2=0, Cout=128, k=3),     # box height 2
+    dict(B=1, H=8, W=256, C1=32, C2=0, Cout=128, k=3),     # width > 128: column tiles
+    dict(B=40, H=16, W=16, C1=128, C2=0, Cout=256, k=3),   # > 148 tiles? (80 tiles) multi-wave accum ping-pong
+    dict(B=160, H=16, W=16, C1=32, C2=0, Cout=128, k=3),   # 320 tiles on 148 CTAs: persistent loop, both TMEM stages reused
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: 'B{B}_{H}x{W}_{C1}+{C2}->{Cout}_k{k}'.format(**c))
+def test_tcgen05_conv_matches_cuda_core_conv(dev, case):
+  import gpu_util
+  B, H, W, C1, C2, Cout, k = (case[x] for x in ('B', 'H', 'W', 'C1', 'C2', 'Cout', 'k'))
+  torch.manual_seed(6)
+  rt = gpu_util.round_tf32
+  x1 = rt(torch.randn(B, H, W, C1, device=dev))
+  x2 = rt(torch.randn(B, H, W, C2, device=dev)) if C2 else None
+  w = rt(torch.randn(Cout, C1 + C2, k, k, device=dev) / np.sqrt((C1 + C2) * k * k))
+  bias = torch.randn(Cout, device=dev)
+  rowvec = torch.randn(B, Cout, device=dev)
+  res = torch.randn(B, H, W, Cout, device=dev)
+  wp = gpu_util.pack_conv_weight(w)
+  kw = dict(rowvec=rowvec, rowvec_ld=Cout, residual=res, scale=0.7071067690849304)
+  ref = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=0, **kw)
+  y = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=1, **kw)
+  torch.cuda.synchronize()
+  err = (y - ref).abs().max().item()
+  assert err < 2e-4 * max(1.0, ref.abs().max().item()), f'max abs err {err}'
+  # and against torch's own fp32 convolution
+  xc = x1 if x2 is None else torch.cat([x1, x2], 3)
+  tref = (F.conv2d(xc.permute(0, 3, 1, 2), w, bias, padding=k // 2).permute(0, 2, 3, 1) + rowvec[:, None, None, :] + res) * 0.7071067690849304
+  assert torch.allclose(y, tref, rtol=2e-4, atol=2e-4)
+  # TF32-rounded store is exactly the rounding of the plain store
+  y2 = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=1, round_out=True, **kw)
+  assert torch.equal(y2, rt(y))
+
+
+def test_tcgen05_batched_gemm_attention_shapes(dev):
+  import gpu_util
+  rt = gpu_util.round_tf32
+  torch.manual_seed(7)
+  nb, T, C = 3, 256, 256
+  qk = rt(torch.randn(nb * T, 2 * C, device=dev) * 0.3)
+  # S[b] = q[b] k[b]^T with q,k interleaved in one [B*T, 2C] buffer (pitch 2C)
+  S = gpu_util.gemm_nt(qk, qk[:, C:], nb, T, T, C, lda=2 * C, ldw=2 * C, impl=1)
+  ref = torch.bmm(qk[:, :C].reshape(nb, T, C), qk[:, C:].reshape(nb, T, C).transpose(1, 2)).reshape(nb * T, T)
+  assert torch.allclose(S, ref, rtol=2e-4, atol=2e-3)
+  # v^T[b] = Wv a[b]^T : shared row operand, batched column operand
+  Wv = rt(torch.randn(C, C, device=dev) / 16)
+  a = rt(torch.randn(nb * T, C, device=dev))
+  vT = gpu_util.gemm_nt(Wv, a, nb, C, T, C, a_batch_rows=0, w_batch_rows=T, impl=1)
+  refv = torch.einsum('ci,bti->bct', Wv, a.view(nb, T, C)).reshape(nb * C, T)
+  assert torch.allclose(vT, refv, rtol=2e-4, atol=2e-3)
+  # projection with N = 2C = 512 (two N tiles) and a bias
+  Wqk = rt(torch.randn(2 * C, C, device=dev) / 16)
+  b = torch.randn(2 * C, device=dev)
+  out = gpu_util.gemm_nt(a, Wqk, 1, nb * T, 2 * C, C, w_batch_rows=0, bias=b, impl=1)
+  assert torch.allclose(out, a @ Wqk.t() + b, rtol=2e-4, atol=2e-3)
+
+
+def test_forward_tf32_cifar10_matches_oracle_within_parity_bound(dev):
+  g = golden('ncsnpp_cifar10_ve.npz')
+  cfg = golden_config('cifar10_ve')
+  model = seeded_model(cfg, precision='tf32', keep_activations=True).to(dev)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  x, sigma = torch.from_numpy(g['x']).to(dev), torch.from_numpy(g['sigma']).to(dev)
+  taps = {}
+  with torch.no_grad():
+    ref = NO.ncsnpp_forward(sd, cfg, x, sigma, taps=taps)
+    y = model(x, sigma)
+  rows = []
+  for i in sorted(taps):
+    try:
+      rows.append((i, rel_l2(model.tap(i), taps[i])))
+    except RuntimeError:
+      pass
+  worst = sorted(rows, key=lambda r: -r[1])[:5]
+  assert all(r[1] < 5e-3 for r in rows), f'worst modules (index, rel-L2): {worst}'
+  e_or, e_gold = rel_l2(y, ref), rel_l2(y, torch.from_numpy(g['y']).to(dev))
+  print(f'cifar10 tf32 single-eval rel-L2 vs GPU oracle {e_or:.3e}, vs reference CPU golden {e_gold:.3e}; worst taps {worst}')
+  assert e_or < TOL_PARITY and e_gold < TOL_PARITY
+
+
+def test_forward_fp32_cifar10_matches_oracle(dev):
+  g = golden('ncsnpp_cifar10_ve.npz')
+  cfg = golden_config('cifar10_ve')
+  model = seeded_model(cfg, precision='fp32').to(dev)
+  x, sigma = torch.from_numpy(g['x']).to(dev), torch.from_numpy(g['sigma']).to(dev)
+  y = model(x, sigma)
+  assert rel_l2(y, torch.from_numpy(g['y']).to(dev)) < 1e-4
+
+
+def test_pc_sampler_tf32_cifar10_K_steps_within_parity_bound(dev):
+  """K PC iterations (2K network evaluations) of the headline sampler at B=8 vs the strict-fp32 oracle."""
+  from score_sde_pytorch_b200 import sampling, sde_lib, native
+  cfg = golden_config('cifar10_ve')
+  model = seeded_model(cfg, precision='tf32').to(dev)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  shape = (8, 3, 32, 32)
+  K = 10
+  sde, osde = sde_lib.VESDE(0.01, 50, 1000), SO.VE(0.01, 50, 1000)
+  torch.manual_seed(1)
+  x0 = osde.prior_sampling(shape).to(dev)
+  torch.cuda.manual_seed(1)
+  ref, _ = SO.pc_sample(osde, lambda x, l: NO.ncsnpp_forward(sd, cfg, x, l), shape, eps=1e-5, device=dev,
+                        x_init=x0, num_iters=K)
+  plan = native.match_pc_plan(sde=sde, model=model, predictor=sampling.ReverseDiffusionPredictor,
+                              corrector=sampling.LangevinCorrector, shape=shape, snr=0.16, n_steps=1,
+                              probability_flow=False, continuous=True, eps=1e-5, device=dev)
+  torch.cuda.manual_seed(1)
+  x, x_mean = plan.run(x0, first_step=0, num_steps=K)
+  e = rel_l2(x_mean, ref)
+  print(f'cifar10 tf32 {K}-step PC rel-L2 vs oracle: {e:.3e}')
+  assert e < TOL_PARITY
