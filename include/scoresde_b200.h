@@ -49,7 +49,8 @@ B200_API int b200_fused_bias_act_f32(const float* x, const float* b, const float
 /* ---- GroupNorm(+SiLU), softmax, Gaussian noise: building blocks exported for tests ---- */
 B200_API int b200_groupnorm_nhwc_f32(const float* x1, int c1, const float* x2, int c2,
                                      const float* gamma, const float* beta, int batch, int hw, int groups,
-                                     float eps, int silu, int round_tf32, float* stats_ws /* [batch*groups*2] */,
+                                     float eps, int silu, int round_tf32,
+                                     float* stats_ws /* 16*batch*(c1+c2)/4 bytes: fp64 quad sums */,
                                      float* y, float* raw_or_null, void* stream);
 B200_API int b200_softmax_rows_f32(const float* s, float* p, long long rows, int t, float scale,
                                    int round_tf32, void* stream);

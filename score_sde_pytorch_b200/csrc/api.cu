@@ -54,8 +54,12 @@ int b200_groupnorm_nhwc_f32(const float* x1, int c1, const float* x2, int c2, co
                             float* y, float* raw, void* stream) {
   B200_REQUIRE(x1 && gamma && beta && stats_ws && y, "groupnorm: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int r = launch_gn_stats(x1, c1, x2, x2 ? c2 : 0, batch, hw, groups, eps, stats_ws, st)) return r;
-  return launch_gn_apply(x1, c1, x2, x2 ? c2 : 0, stats_ws, gamma, beta, batch, hw, groups, silu, round_tf32, y, raw, st);
+  // stats_ws holds the fp64 quad sums of both sources: [batch][c1/4][2] then [batch][c2/4][2]
+  double* q1 = reinterpret_cast<double*>(stats_ws);
+  double* q2 = q1 + (long long)batch * (c1 / 4) * 2;
+  if (int r = launch_gn_quad_stats(x1, c1, batch, hw, q1, st)) return r;
+  if (x2) { if (int r = launch_gn_quad_stats(x2, c2, batch, hw, q2, st)) return r; }
+  return launch_gn_apply(x1, c1, x2, x2 ? c2 : 0, q1, q2, gamma, beta, batch, hw, groups, eps, silu, round_tf32, y, raw, st);
 }
 
 int b200_softmax_rows_f32(const float* s, float* p, long long rows, int t, float scale, int round_tf32, void* stream) {
@@ -98,7 +102,7 @@ int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int bat
     TcGemmDesc d; memset(&d, 0, sizeof(d));
     d.a1 = x1; d.C1 = c1; d.a2 = x2; d.C2 = c2; d.conv = 1; d.H = h; d.W = w; d.nimg = batch; d.taps = ksize * ksize;
     d.w = w_packed; d.N_total = c_out; d.K_total = c1 + c2; d.w_rows = (long long)ksize * ksize * c_out; d.nbatch = 1;
-    d.epi = ep;
+    d.epi_mode = -1; d.epi = ep;
     TcGemmPlan* pl = nullptr;
     if (int r = tc_gemm_plan_create(d, &pl)) return r;
     const int r = tc_gemm_launch(pl, st);
@@ -124,7 +128,7 @@ int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const floa
     d.a_rows = a_batch_rows ? (long long)a_batch_rows * (nbatch - 1) + m : m;
     d.w = w; d.N_total = n; d.K_total = k; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
     d.w_rows = w_batch_rows ? (long long)w_batch_rows * (nbatch - 1) + n : n;
-    d.nbatch = nbatch; d.M_per_batch = m; d.epi = ep;
+    d.nbatch = nbatch; d.M_per_batch = m; d.epi_mode = -1; d.epi = ep;
     TcGemmPlan* pl = nullptr;
     if (int r = tc_gemm_plan_create(d, &pl)) return r;
     const int r = tc_gemm_launch(pl, st);

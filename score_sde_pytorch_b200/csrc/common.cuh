@@ -19,6 +19,7 @@ const char* last_error();
   do {                                                                               \
     cudaError_t _e = (expr);                                                         \
     if (_e != cudaSuccess) {                                                         \
+      (void)cudaGetLastError(); /* clear the sticky last-error so later launches are not blamed */ \
       ::b200::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,           \
                         cudaGetErrorString(_e));                                     \
       return 1;                                                                      \

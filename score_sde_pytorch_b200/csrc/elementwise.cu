@@ -11,107 +11,182 @@
 namespace b200 {
 
 // ============================================================================
-// GroupNorm statistics.  Reference semantics: nn.GroupNorm(min(C/4,32), C, eps=1e-6)
+// GroupNorm.  Reference semantics: nn.GroupNorm(min(C/4,32), C, eps=1e-6)
 // (layerspp.py:67,219,231; ncsnpp.py:226) -> biased variance over (C/G)*H*W.
-// One CTA per image streams the whole [HW, C] slab once (coalesced float4),
-// accumulating per-thread sums in fp64 (robust to mean^2 >> var cancellation),
-// then folds threads that share a group through shared-memory fp64 atomics.
-// The input may be a virtual channel-concat of two tensors (U-Net skip joins,
-// ncsnpp.py:318) so torch.cat never materialises.
+//
+// Statistics are carried as fp64 "quad sums": for every image and every aligned group of 4
+// channels the pair (sum x, sum x^2).  Any GroupNorm group of this network (4/8/12/16 channels,
+// always quad aligned, possibly straddling the two sources of a U-Net channel concat,
+// ncsnpp.py:318) is a sum of 1-4 quads, so a tensor's quad sums serve every consumer.  They are
+// produced for free by the tcgen05 contraction's epilogue (gemm_tc.cu) for tensors it writes, or
+// by gn_quad_stats_kernel below for the rest; gn_apply_kernel turns them into mean / rstd once
+// per thread and streams the tensor exactly once (read + write, optional TF32-rounded raw copy).
 // ============================================================================
-__global__ void __launch_bounds__(384) gn_stats_kernel(
-    const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-    int HW, int G, float eps, float2* __restrict__ stats) {
-  extern __shared__ double sacc[];   // [2*G]
-  const int C = C1 + C2, Q = C >> 2, cpg = C / G;
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sacc[i] = 0.0;
-  __syncthreads();
-  const long long units = (long long)HW * Q;
-  const float* p1 = x1 + (long long)b * HW * C1;
-  const float* p2 = x2 ? x2 + (long long)b * HW * C2 : nullptr;
-  double s = 0.0, ss = 0.0;
-  int cur_g = -1;
-  for (long long u = threadIdx.x; u < units; u += blockDim.x) {
-    const int pix = (int)(u / Q), c0 = (int)(u % Q) << 2;
-    const int g = c0 / cpg;
-    if (g != cur_g) {
-      if (cur_g >= 0) { atomicAdd(&sacc[2 * cur_g], s); atomicAdd(&sacc[2 * cur_g + 1], ss); }
-      s = 0.0; ss = 0.0; cur_g = g;
+constexpr int GN_THREADS = 384;   // divisible by C/4 for every channel count of the network (32, 64, 96, 128)
+
+__global__ void __launch_bounds__(GN_THREADS) gn_quad_stats_kernel(
+    const float* __restrict__ x, int C, int HW, double* __restrict__ qsums /* [B][C/4][2] */) {
+  extern __shared__ double sred[];   // [lanes][Q][2]
+  const int Q = C >> 2, b = blockIdx.x;
+  const float* px = x + (long long)b * HW * C;
+  if (GN_THREADS % Q == 0) {
+    // deterministic: thread owns quad q for pixels lane, lane+L, ...; fixed-order fold over lanes
+    const int L = GN_THREADS / Q, q = threadIdx.x % Q, lane = threadIdx.x / Q;
+    double s = 0.0, ss = 0.0;
+    int pix = lane;
+    for (; pix + 3 * L < HW; pix += 4 * L) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(px + (long long)(pix + u * L) * C + 4 * q));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += ((double)v[u].x + (double)v[u].y) + ((double)v[u].z + (double)v[u].w);
+        ss += ((double)v[u].x * v[u].x + (double)v[u].y * v[u].y) + ((double)v[u].z * v[u].z + (double)v[u].w * v[u].w);
+      }
     }
-    float4 v = (c0 < C1) ? __ldg(reinterpret_cast<const float4*>(p1 + (long long)pix * C1 + c0))
-                         : __ldg(reinterpret_cast<const float4*>(p2 + (long long)pix * C2 + (c0 - C1)));
-    s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-    ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-  }
-  if (cur_g >= 0) { atomicAdd(&sacc[2 * cur_g], s); atomicAdd(&sacc[2 * cur_g + 1], ss); }
-  __syncthreads();
-  const double n = (double)HW * cpg;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    const double mean = sacc[2 * g] / n;
-    double var = sacc[2 * g + 1] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(long long)b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    for (; pix < HW; pix += L) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(px + (long long)pix * C + 4 * q));
+      s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      ss += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    }
+    sred[(lane * Q + q) * 2] = s; sred[(lane * Q + q) * 2 + 1] = ss;
+    __syncthreads();
+    if (threadIdx.x < Q) {
+      double a = 0.0, c = 0.0;
+      for (int l = 0; l < L; ++l) { a += sred[(l * Q + threadIdx.x) * 2]; c += sred[(l * Q + threadIdx.x) * 2 + 1]; }
+      qsums[((long long)b * Q + threadIdx.x) * 2] = a;
+      qsums[((long long)b * Q + threadIdx.x) * 2 + 1] = c;
+    }
+  } else {
+    // generic channel counts: shared-memory fp64 atomics
+    for (int i = threadIdx.x; i < 2 * Q; i += blockDim.x) sred[i] = 0.0;
+    __syncthreads();
+    for (long long u = threadIdx.x; u < (long long)HW * Q; u += blockDim.x) {
+      const int q = (int)(u % Q);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(px + (u / Q) * C + 4 * q));
+      atomicAdd(&sred[2 * q], ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w));
+      atomicAdd(&sred[2 * q + 1], ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Q; i += blockDim.x) qsums[(long long)b * 2 * Q + i] = sred[i];
   }
 }
 
-int launch_gn_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int G,
-                    float eps, float* stats, cudaStream_t st) {
-  const int C = C1 + C2;
-  B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0,
-               "gn_stats: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
-  gn_stats_kernel<<<B, 384, 2 * G * sizeof(double), st>>>(x1, C1, x2, C2, HW, G, eps,
-                                                          reinterpret_cast<float2*>(stats));
+int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st) {
+  B200_REQUIRE(C % 4 == 0, "gn_quad_stats: C=%d must be a multiple of 4", C);
+  const int Q = C / 4;
+  const size_t smem = (GN_THREADS % Q == 0) ? (size_t)GN_THREADS * 2 * sizeof(double) : (size_t)2 * Q * sizeof(double);
+  B200_REQUIRE(smem <= 48 * 1024, "gn_quad_stats: C=%d too large", C);
+  gn_quad_stats_kernel<<<B, GN_THREADS, smem, st>>>(x, C, HW, qsums);
   B200_CHECK_LAUNCH();
   return 0;
 }
 
-// ============================================================================
-// GroupNorm apply (+ optional SiLU, + optional TF32 rounding of the stored value
-// because the consumer is a tcgen05 kind::tf32 contraction).  Optionally also
-// emits `raw`: the TF32-rounded *un-normalised* (concatenated) input, which is the
-// A operand of the ResBlock's 1x1 skip convolution (layerspp.py:268-269).
-// ============================================================================
-__global__ void __launch_bounds__(256) gn_apply_kernel(
+// mean / rstd of the group containing concat-channel c0 from the quad sums of the two sources
+__device__ __forceinline__ float2 group_mean_rstd(const double* __restrict__ q1, int C1, const double* __restrict__ q2, int C2,
+                                                  int b, int c0, int cpg, double n, float eps) {
+  const int g0 = (c0 / cpg) * cpg;
+  double s = 0.0, ss = 0.0;
+  for (int c = g0; c < g0 + cpg; c += 4) {
+    const double* src = (c < C1) ? q1 + ((long long)b * (C1 >> 2) + (c >> 2)) * 2
+                                 : q2 + ((long long)b * (C2 >> 2) + ((c - C1) >> 2)) * 2;
+    s += src[0]; ss += src[1];
+  }
+  const double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+__device__ __forceinline__ float4 gn_norm4(float4 v, float2 mr, float4 ga, float4 be, int act, int round_out) {
+  float4 o;
+  o.x = (v.x - mr.x) * mr.y * ga.x + be.x;
+  o.y = (v.y - mr.x) * mr.y * ga.y + be.y;
+  o.z = (v.z - mr.x) * mr.y * ga.z + be.z;
+  o.w = (v.w - mr.x) * mr.y * ga.w + be.w;
+  if (act) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+  if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+  return o;
+}
+
+// grid = (pixel splits, images).  blockDim % (C/4) == 0: a thread keeps one channel quad (so its
+// group statistics, gamma and beta are loaded once) and walks pixels with 4 loads in flight.
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-    const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-    long long total_units, int HW, int G, int act, int round_out,
-    float* __restrict__ y, float* __restrict__ raw) {
-  const int C = C1 + C2, Q = C >> 2, cpg = C / G;
-  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < total_units;
-       u += (long long)gridDim.x * blockDim.x) {
-    const long long pixg = u / Q;               // global pixel index (b*HW + pix)
-    const int c0 = (int)(u % Q) << 2;
-    const int b = (int)(pixg / HW);
-    float4 v = (c0 < C1) ? __ldg(reinterpret_cast<const float4*>(x1 + pixg * C1 + c0))
-                         : __ldg(reinterpret_cast<const float4*>(x2 + pixg * C2 + (c0 - C1)));
-    const float2 mr = __ldg(&stats[(long long)b * G + c0 / cpg]);
+    const double* __restrict__ q1, const double* __restrict__ q2,
+    const float* __restrict__ gamma, const float* __restrict__ beta,
+    int HW, int G, float eps, int act, int round_out, float* __restrict__ y, float* __restrict__ raw) {
+  const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const double n = (double)HW * cpg;
+  const long long ib = (long long)b * HW;
+  if (blockDim.x % Q == 0) {
+    const int L = blockDim.x / Q, c0 = (threadIdx.x % Q) << 2, lane = threadIdx.x / Q;
+    const float2 mr = group_mean_rstd(q1, C1, q2, C2, b, c0, cpg, n, eps);
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
-    float4 o;
-    o.x = (v.x - mr.x) * mr.y * ga.x + be.x;
-    o.y = (v.y - mr.x) * mr.y * ga.y + be.y;
-    o.z = (v.z - mr.x) * mr.y * ga.z + be.z;
-    o.w = (v.w - mr.x) * mr.y * ga.w + be.w;
-    if (act) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    *reinterpret_cast<float4*>(y + pixg * C + c0) = o;
-    if (raw) {
-      float4 r = v;
-      if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-      *reinterpret_cast<float4*>(raw + pixg * C + c0) = r;
+    const bool first = c0 < C1;
+    const float* src = first ? x1 + ib * C1 + c0 : x2 + ib * C2 + (c0 - C1);
+    const int Cs = first ? C1 : C2;
+    int pix = p0 + lane;
+    for (; pix + 3 * L < p1; pix += 4 * L) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(pix + u * L) * Cs));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = (ib + pix + u * L) * C + c0;
+        *reinterpret_cast<float4*>(y + o) = gn_norm4(v[u], mr, ga, be, act, round_out);
+        if (raw) {
+          float4 r = v[u];
+          if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+          *reinterpret_cast<float4*>(raw + o) = r;
+        }
+      }
+    }
+    for (; pix < p1; pix += L) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)pix * Cs));
+      const long long o = (ib + pix) * C + c0;
+      *reinterpret_cast<float4*>(y + o) = gn_norm4(v, mr, ga, be, act, round_out);
+      if (raw) {
+        float4 r = v;
+        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        *reinterpret_cast<float4*>(raw + o) = r;
+      }
+    }
+  } else {
+    for (long long u = (long long)p0 * Q + threadIdx.x; u < (long long)p1 * Q; u += blockDim.x) {
+      const int pix = (int)(u / Q), c0 = (int)(u % Q) << 2;
+      const float4 v = (c0 < C1) ? __ldg(reinterpret_cast<const float4*>(x1 + (ib + pix) * C1 + c0))
+                                 : __ldg(reinterpret_cast<const float4*>(x2 + (ib + pix) * C2 + (c0 - C1)));
+      const float2 mr = group_mean_rstd(q1, C1, q2, C2, b, c0, cpg, n, eps);
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      const long long o = (ib + pix) * C + c0;
+      *reinterpret_cast<float4*>(y + o) = gn_norm4(v, mr, ga, be, act, round_out);
+      if (raw) {
+        float4 r = v;
+        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        *reinterpret_cast<float4*>(raw + o) = r;
+      }
     }
   }
 }
 
-int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const float* stats,
-                    const float* gamma, const float* beta, int B, int HW, int G, int act,
+int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
+                    const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
                     int round_out, float* y, float* raw, cudaStream_t st) {
   const int C = C1 + C2;
-  const long long units = (long long)B * HW * (C / 4);
-  const int grid = (int)std::min<long long>((units + 255) / 256, 148LL * 32);
-  gn_apply_kernel<<<grid, 256, 0, st>>>(x1, C1, x2, C2, reinterpret_cast<const float2*>(stats), gamma,
-                                        beta, units, HW, G, act, round_out, y, raw);
+  B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0,
+               "gn_apply: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
+  const int Q = C / 4;
+  // aim for ~16 float4 per thread, at least one block per image
+  const long long per_img_units = (long long)HW * Q;
+  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (GN_THREADS * 16LL), 64));
+  splits = std::min(splits, HW);
+  dim3 grid(splits, B);
+  gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -179,6 +254,44 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict_
   }
 }
 
+// Fast path for the three parameterisations NCSN++ uses (4x4 FIR, NHWC with minor % 4 == 0):
+//   UP=2 (pad 2,1): polyphase, 2x2 live taps per output;  DOWN=2 (pad 1,1): 4x4 taps, stride 2;
+//   UP=DOWN=1 (pad 2,2): 4x4 taps.  All index arithmetic is compile-time; one thread = one output float4.
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       const FirParams p) {
+  const int mv = p.minor >> 2;
+  const long long total = (long long)p.major * p.out_h * p.out_w * mv;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cm = (int)(i % mv) << 2;
+  long long t = i / mv;
+  const int ox = (int)(t % p.out_w); t /= p.out_w;
+  const int oy = (int)(t % p.out_h);
+  const int n = (int)(t / p.out_h);
+  const float* xin = x + (long long)n * p.in_h * p.in_w * p.minor + cm;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int Y = oy * DOWN + a - p.pad_y0;
+    if (UP == 2 && (Y & 1)) continue;
+    const int iy = UP == 2 ? (Y >> 1) : Y;
+    if (Y < 0 || iy >= p.in_h) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int X = ox * DOWN + b - p.pad_x0;
+      if (UP == 2 && (X & 1)) continue;
+      const int ix = UP == 2 ? (X >> 1) : X;
+      if (X < 0 || ix >= p.in_w) continue;
+      const float w = p.k[(3 - a) * 4 + (3 - b)];
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xin + ((long long)iy * p.in_w + ix) * p.minor));
+      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+  }
+  if (p.round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+  *reinterpret_cast<float4*>(y + (((long long)n * p.out_h + oy) * p.out_w + ox) * p.minor + cm) = acc;
+}
+
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
                      int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_out, cudaStream_t st) {
@@ -195,6 +308,12 @@ int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int maj
   const bool vec = (minor % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0);
   const long long total = (long long)major * p.out_h * p.out_w * (vec ? minor / 4 : minor);
   if (total == 0) return 0;
+  if (vec && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && pad_x0 >= 0 && total < (1LL << 31) * 256) {
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (up_x == 2 && down_x == 1) { fir4_nhwc_kernel<2, 1><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 1 && down_x == 2) { fir4_nhwc_kernel<1, 2><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 1 && down_x == 1) { fir4_nhwc_kernel<1, 1><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+  }
   const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
   if (vec) upfirdn2d_kernel<4><<<grid, 256, 0, st>>>(x, y, p);
   else upfirdn2d_kernel<1><<<grid, 256, 0, st>>>(x, y, p);
@@ -386,10 +505,11 @@ int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cuda
   return 0;
 }
 
-// dst[tap][o][i] = src[o*so + i*si + tap*st]  (OIHW conv weights: so=I*R*S, si=R*S, st=1;
-// NIN W[in][out]: taps=1, so=1, si=out).  Optional TF32 rounding for tensor-core layers.
+// dst[tap*dt + o*dO + i] = src[o*so + i*si + tap*st]  (OIHW conv weights: so=I*R*S, si=R*S, st=1;
+// NIN W[in][out]: taps=1, so=1, si=out).  Default destination [tap][o][i] (dt=O*I, dO=I); the
+// flat-K packing of the input convolution uses dt=I, dO=row pitch.  Optional TF32 rounding.
 __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int O, int I,
-                                   long long so, long long si, long long stp, int round_out) {
+                                   long long so, long long si, long long stp, int round_out, long long dt, long long dO) {
   const long long total = (long long)taps * O * I;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -398,14 +518,121 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restr
     const int o = (int)(t % O);
     const int tap = (int)(t / O);
     const float v = src[o * so + i * si + tap * stp];
-    dst[idx] = round_out ? round_tf32(v) : v;
+    dst[tap * dt + o * dO + i] = round_out ? round_tf32(v) : v;
   }
 }
 int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, long long so, long long si,
-                       long long stp, int round_out, cudaStream_t st) {
+                       long long stp, int round_out, cudaStream_t st, long long dt, long long dO) {
   const long long total = (long long)taps * O * I;
+  if (dt == 0) { dt = (long long)O * I; dO = I; }
   pack_weight_kernel<<<(int)std::min<long long>((total + 255) / 256, 148LL * 16), 256, 0, st>>>(
-      src, dst, taps, O, I, so, si, stp, round_out);
+      src, dst, taps, O, I, so, si, stp, round_out, dt, dO);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// ============================================================================
+// Input convolution as one K=32 contraction: patches[b*HW + pix][tap*C + c] = x[b][c][pix + tap offset]
+// (zero outside the image, zero for k >= 9*C), TF32-rounded, from the NCHW network input.
+// 9*C <= 32 (C = 3 for images).  The 3->nf 3x3 conv (ncsnpp.py:268) then runs on tcgen05 as a
+// [B*HW, 32] x [nf, 32]^T product instead of a 27-deep CUDA-core loop.
+// ============================================================================
+__global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __restrict__ x, float* __restrict__ patches,
+                                                            int B, int C, int H, int W) {
+  const long long total = (long long)B * H * W * 8;            // 8 float4 per 32-wide row
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k4 = (int)(i & 7) << 2;
+  const long long pg = i >> 3;
+  const int px = (int)(pg % W), py = (int)((pg / W) % H), b = (int)(pg / ((long long)W * H));
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = k4 + j;
+    float t = 0.f;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k % C;
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) t = __ldg(x + (((long long)b * C + c) * H + iy) * W + ix);
+    }
+    v[j] = round_tf32(t);
+  }
+  *reinterpret_cast<float4*>(patches + pg * 32 + k4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int H, int W, cudaStream_t st) {
+  B200_REQUIRE(9 * C <= 32, "im2col3x3: %d channels do not fit one 32-wide K step", C);
+  const long long total = (long long)B * H * W * 8;
+  im2col3x3_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, patches, B, C, H, W);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// ============================================================================
+// Output head: 3x3 'same' convolution to N <= 4 channels (ncsnpp.py:374) on NHWC input, written
+// straight to NCHW with bias and the 1/sigma scaling (ncsnpp.py:377-379) fused.  Memory-bound
+// (reads the activation once through L1, 9x tap reuse between neighbouring threads); the 9*N*C
+// weights sit in shared memory and are read as broadcast float4s.
+// ============================================================================
+template <int N>
+__global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w /* [9][N][C] */,
+                                                             const float* __restrict__ bias, const float* __restrict__ div,
+                                                             long long div_stride, float* __restrict__ out_nchw,
+                                                             int B, int H, int W, int C) {
+  extern __shared__ float sw[];   // [9][N][C]
+  for (int i = threadIdx.x; i < 9 * N * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long pg = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pg >= (long long)B * H * W) return;
+  const int px = (int)(pg % W), py = (int)((pg / W) % H), b = (int)(pg / ((long long)W * H));
+  float acc[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) acc[n] = 0.f;
+  const float* xb = x + (long long)b * H * W * C;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const float4* src = reinterpret_cast<const float4*>(xb + ((long long)iy * W + ix) * C);
+    const float4* wt = reinterpret_cast<const float4*>(sw + tap * N * C);
+    for (int c4 = 0; c4 < (C >> 2); ++c4) {
+      const float4 a = __ldg(src + c4);
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        const float4 ww = wt[n * (C >> 2) + c4];
+        acc[n] = fmaf(a.x, ww.x, fmaf(a.y, ww.y, fmaf(a.z, ww.z, fmaf(a.w, ww.w, acc[n]))));
+      }
+    }
+  }
+  const float dv = div ? __ldg(div + b * div_stride) : 1.f;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    float v = acc[n] + (bias ? __ldg(bias + n) : 0.f);
+    if (div) v = v / dv;
+    out_nchw[(((long long)b * N + n) * H + py) * W + px] = v;
+  }
+}
+
+int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
+                           float* out_nchw, int B, int H, int W, int C, int N, cudaStream_t st) {
+  B200_REQUIRE(N >= 1 && N <= 4 && C % 4 == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
+  const size_t smem = (size_t)9 * N * C * sizeof(float);
+  B200_REQUIRE(smem <= 96 * 1024, "conv3x3_small_n: weights (%zu B) exceed shared memory", smem);
+  const long long total = (long long)B * H * W;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+#define B200_LAUNCH_SMALLN(NN)                                                                                      \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_n_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv3x3_small_n_kernel<NN><<<blocks, 256, smem, st>>>(x, w, bias, div, div_stride, out_nchw, B, H, W, C);       \
+  } while (0)
+  switch (N) {
+    case 1: B200_LAUNCH_SMALLN(1); break;
+    case 2: B200_LAUNCH_SMALLN(2); break;
+    case 3: B200_LAUNCH_SMALLN(3); break;
+    default: B200_LAUNCH_SMALLN(4); break;
+  }
+#undef B200_LAUNCH_SMALLN
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -14,13 +14,14 @@
 
 namespace b200 {
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld);
+int tc_gemm_default_epi_mode();
 }
 using namespace b200;
 
 namespace {
 
 enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RESBLOCK, M_ATTN, M_PYR_DOWN, M_GN_OUT, M_CONV_OUT };
-enum PackKind { PK_COPY = 0, PK_CONV = 1, PK_NIN = 2 };
+enum PackKind { PK_COPY = 0, PK_CONV = 1, PK_NIN = 2, PK_CONV_FLAT32 = 3 };
 
 struct Param {
   std::string name;
@@ -40,7 +41,7 @@ struct Mod {
   int w = -1, b = -1;
 };
 
-struct Tensor { float* p = nullptr; int C = 0, H = 0, W = 0; long long bytes = 0; };
+struct Tensor { float* p = nullptr; int C = 0, H = 0, W = 0; long long bytes = 0; double* qs = nullptr; /* GroupNorm quad sums [B][C/4][2] */ };
 
 class Arena {
  public:
@@ -116,14 +117,14 @@ struct b200_ncsnpp {
 namespace {
 
 int add_param(b200_ncsnpp* e, const std::string& name, std::vector<long long> shape, int pack, int taps, int O,
-              int I, int round, long long fixed_off = -1) {
+              int I, int round, long long fixed_off = -1, long long reserve = 0) {
   Param p;
   p.name = name; p.ndim = (int)shape.size();
   p.count = 1;
   for (int i = 0; i < 4; ++i) { p.shape[i] = i < p.ndim ? shape[i] : 1; p.count *= p.shape[i]; }
   p.pack = pack; p.taps = taps; p.O = O; p.I = I; p.round = round;
   if (fixed_off >= 0) p.off = fixed_off;
-  else { p.off = e->wcount; e->wcount += (p.count + 63) & ~63LL; }
+  else { p.off = e->wcount; e->wcount += (std::max(p.count, reserve) + 63) & ~63LL; }
   e->params.push_back(p);
   return (int)e->params.size() - 1;
 }
@@ -226,7 +227,11 @@ int build_graph(b200_ncsnpp* e) {
 
   // input conv
   { Mod m; m.kind = M_CONV_IN; m.index = (int)e->mods.size(); m.cin1 = ch; m.cout = nf; m.res = c.image_size;
-    m.w = add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV, 9, nf, ch, 0); m.b = add_param(e, nm("bias"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+    // on tensor cores the 3x3 input conv is one K=32 contraction over im2col patches: weights packed [nf][32]
+    m.tc0 = (c.precision == 0) && (9 * ch <= 32) && (nf % 128 == 0);
+    m.w = m.tc0 ? add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV_FLAT32, 9, nf, ch, 1, -1, (long long)nf * 32)
+                : add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV, 9, nf, ch, 0);
+    m.b = add_param(e, nm("bias"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
   std::vector<int> hs_c = {nf};
   int in_ch = nf, pyr_ch = ch;
   for (int lvl = 0; lvl < L; ++lvl) {
@@ -241,7 +246,9 @@ int build_graph(b200_ncsnpp* e) {
       add_resblock(in_ch, 0, in_ch, 0, 1, all_res[lvl]);
       if (c.progressive_input == 1) {
         Mod m; m.kind = M_PYR_DOWN; m.index = (int)e->mods.size(); m.cin1 = pyr_ch; m.cout = in_ch; m.res = all_res[lvl];
-        m.w = add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, 0);
+        // FIR-padded stride-2 VALID conv: on tcgen05 via TMA element strides when the channel counts tile
+        m.tc0 = tc_ok(e, pyr_ch, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 9);
+        m.w = add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, m.tc0);
         m.b = add_param(e, nm("Conv2d_0.bias"), {in_ch}, PK_COPY, 0, 0, 0, 0);
         e->mods.push_back(m);
         pyr_ch = in_ch;
@@ -284,7 +291,19 @@ int build_graph(b200_ncsnpp* e) {
 // ---------------------------------------------------------------------------
 struct Builder {
   b200_ncsnpp* e; int B; char* base; bool dry; Arena arena; int rc = 0;
-  Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0) {}
+  char* stats_base = nullptr; long long stats_top = 0;   // bump region for GroupNorm quad sums, zeroed once per forward
+  bool fused_stats = false;
+  Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0) {
+    const char* v = getenv("B200_FUSED_GN_STATS");
+    fused_stats = (e_->cfg.precision == 0) && tc_gemm_default_epi_mode() == 1 && !(v && v[0] == '0');
+    if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
+  }
+  double* qalloc(int C) {
+    const long long bytes = ((long long)B * (C / 4) * 2 * 8 + 255) & ~255LL;
+    double* p = reinterpret_cast<double*>(stats_base + stats_top);
+    stats_top += bytes;
+    return p;
+  }
 
   Tensor talloc(int C, int H, int W) {
     Tensor t; t.C = C; t.H = H; t.W = W; t.bytes = (long long)B * H * W * C * 4;
@@ -307,16 +326,21 @@ struct Builder {
     e->ops.push_back({kind, flops, std::move(f)});
   }
 
-  void gn(Tensor x1, Tensor x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
+  // make sure tensor t has quad sums: produced by its tcgen05 epilogue, else by one streaming pass
+  void ensure_qs(Tensor& t) {
+    if (t.qs || !t.p) return;
+    t.qs = qalloc(t.C);
+    const Tensor tt = t; const int Bc = B;
+    op(1, [=](cudaStream_t st) { return launch_gn_quad_stats(tt.p, tt.C, Bc, tt.H * tt.W, tt.qs, st); }, 2);
+  }
+  void gn(Tensor& x1, Tensor& x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
     const int C = x1.C + x2.C, G = std::min(C / 4, 32), HW = x1.H * x1.W;
-    long long sb; float* stats = falloc((long long)B * G * 2, &sb);
+    ensure_qs(x1); ensure_qs(x2);
     const float *g = e->W(pgw), *bt = e->W(pgb);
-    const int Bc = B;
-    op(2, [=](cudaStream_t st) {
-      if (int r = launch_gn_stats(x1.p, x1.C, x2.p, x2.C, Bc, HW, G, 1e-6f, stats, st)) return r;
-      return launch_gn_apply(x1.p, x1.C, x2.p, x2.C, stats, g, bt, Bc, HW, G, act, round, y.p, raw, st);
+    const Tensor a = x1, b = x2; const int Bc = B;
+    op(1, [=](cudaStream_t st) {
+      return launch_gn_apply(a.p, a.C, b.p, b.C, a.qs, b.qs, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, st);
     }, 2);
-    ffree(stats, sb);
   }
 
   void fir(const float* x, int major, int H, int W, int minor, int up, int down, int pad0, int pad1, int round, float* y,
@@ -332,21 +356,25 @@ struct Builder {
 
   // 3x3 / 1x1 'same' convolution on NHWC tensors, stride 1.
   void conv(bool use_tc, Tensor a1, Tensor a2, int taps, int pw, int pb, int Cout, int dense_row /* -1 = none */,
-            const float* residual, float scale, int round, Tensor out) {
+            const float* residual, float scale, int round, Tensor& out, bool want_stats = false, int stride = 1,
+            int Hin = 0) {
     Epilogue ep; memset(&ep, 0, sizeof(ep));
     ep.bias = e->W(pb);
     ep.rowvec = nullptr;   // patched at launch (depends on the per-call buffers)
     ep.residual = residual; ep.ld_res = Cout; ep.scale = scale; ep.round_tf32 = round;
-    ep.rows_per_img = a1.H * a1.W; ep.out = out.p; ep.ld_out = Cout;
+    ep.rows_per_img = out.H * out.W; ep.out = out.p; ep.ld_out = Cout;
     b200_ncsnpp* eng = e;
     const float* dense_all = dense_all_;
     const int sumC = e->sumC;
-    const double cflops = 2.0 * B * a1.H * a1.W * (double)Cout * (a1.C + a2.C) * taps;
+    const double cflops = 2.0 * B * out.H * out.W * (double)Cout * (a1.C + a2.C) * taps;
     if (use_tc) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
-      d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = a1.H; d.W = a1.W; d.nimg = B; d.taps = taps;
+      d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = out.H; d.W = out.W; d.nimg = B; d.taps = taps;
+      d.stride = stride; d.valid_pad = stride == 2 ? 1 : 0; d.Hin = Hin ? Hin : out.H; d.Win = Hin ? Hin : out.W;
       d.w = e->W(pw); d.N_total = Cout; d.K_total = a1.C + a2.C; d.w_rows = (long long)taps * Cout; d.nbatch = 1;
+      d.epi_mode = -1;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
+      if (want_stats && fused_stats && (ep.rows_per_img % 32 == 0 || ep.rows_per_img == 16)) { out.qs = qalloc(Cout); d.qstats = out.qs; }
       d.epi = ep;
       if (dry) return;
       TcGemmPlan* pl = nullptr;
@@ -374,15 +402,16 @@ struct Builder {
   // batched C[b] = A[b] * W[b]^T
   void gemm(bool use_tc, const float* A, long long lda, long long a_rows, int a_batch_rows, const float* Wm, long long ldw,
             long long w_rows, int w_batch_rows, int nbatch, int M, int N, int K, const float* bias,
-            const float* residual, long long ld_res, float scale, int round, float* out, long long ldo) {
+            const float* residual, long long ld_res, float scale, int round, float* out, long long ldo,
+            double* qstats = nullptr, int rows_per_img = 1 << 30) {
     Epilogue ep; memset(&ep, 0, sizeof(ep));
     ep.bias = bias; ep.residual = residual; ep.ld_res = ld_res; ep.scale = scale; ep.round_tf32 = round;
-    ep.rows_per_img = 1 << 30; ep.out = out; ep.ld_out = ldo;
+    ep.rows_per_img = rows_per_img; ep.out = out; ep.ld_out = ldo;
     if (use_tc) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.a1 = A; d.C1 = K; d.conv = 0; d.taps = 1; d.a_rows = a_rows; d.a_ld = lda; d.a_batch_rows = a_batch_rows;
       d.w = Wm; d.N_total = N; d.K_total = K; d.w_rows = w_rows; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
-      d.nbatch = nbatch; d.M_per_batch = M; d.epi = ep;
+      d.nbatch = nbatch; d.M_per_batch = M; d.epi_mode = -1; d.qstats = qstats; d.epi = ep;
       if (dry) return;
       TcGemmPlan* pl = nullptr;
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
@@ -401,7 +430,8 @@ struct Builder {
   const float* dense_all_ = nullptr;
   void tap(int idx, const Tensor& t) { if (!dry) e->taps[idx] = t; }
 
-  Tensor resblock(const Mod& m, Tensor x1, Tensor x2) {
+  Tensor resblock(const Mod& m, Tensor& x1, Tensor& x2) {
+    Tensor none;
     const int Cin = x1.C + x2.C, H = x1.H, Ho = m.up ? 2 * H : m.down ? H / 2 : H;
     const bool resample = m.up || m.down;
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
@@ -426,10 +456,10 @@ struct Builder {
       tfree(a0); a0 = a0r;
     }
     Tensor h1 = talloc(m.cout, Ho, Ho);
-    conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 0, h1);
+    conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 0, h1, /*want_stats=*/true);
     tfree(a0);
     Tensor a1 = talloc(m.cout, Ho, Ho);
-    gn(h1, Tensor(), m.gn1w, m.gn1b, 1, m.tc1 ? 1 : 0, a1, nullptr);
+    gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? 1 : 0, a1, nullptr);
     tfree(h1);
     Tensor s;
     const float* residual = x1.p;
@@ -442,19 +472,20 @@ struct Builder {
       tfree(raw); tfree(xr);
     } else if (x2.p) { set_error("ncsnpp: concat input without a skip convolution"); rc = 2; return Tensor(); }
     Tensor out = talloc(m.cout, Ho, Ho);
-    conv(m.tc1, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, residual, inv_s2, 0, out);
+    conv(m.tc1, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, residual, inv_s2, 0, out, /*want_stats=*/true);
     tfree(a1); tfree(s);
     return out;
   }
 
-  Tensor attn(const Mod& m, Tensor x) {
+  Tensor attn(const Mod& m, Tensor& x) {
+    Tensor none;
     const int C = x.C, T = x.H * x.W;
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
     const bool tc = m.tcattn;
     const float* Wqkv = e->W(m.nw[0]);          // [3C][C]
     const float* bqkv = e->W(m.nb[0]);          // [3C]
     Tensor a = talloc(C, x.H, x.W);
-    gn(x, Tensor(), m.gn0w, m.gn0b, 0, tc ? 1 : 0, a, nullptr);
+    gn(x, none, m.gn0w, m.gn0b, 0, tc ? 1 : 0, a, nullptr);
     long long qkb, vtb, sb, ob;
     float* qk = falloc((long long)B * T * 2 * C, &qkb);
     float* vT = falloc((long long)B * C * T, &vtb);
@@ -477,7 +508,7 @@ struct Builder {
     ffree(S, sb); ffree(vT, vtb);
     Tensor out = talloc(C, x.H, x.W);
     Tensor Ot; Ot.p = O; Ot.C = C; Ot.H = x.H; Ot.W = x.W;
-    conv(m.tc2, Ot, Tensor(), 1, m.nw[3], m.nb[3], C, -1, x.p, inv_s2, 0, out);   // NIN_3 + (x+h)/sqrt2 (:87-91)
+    conv(m.tc2, Ot, Tensor(), 1, m.nw[3], m.nb[3], C, -1, x.p, inv_s2, 0, out, /*want_stats=*/true);   // NIN_3 + (x+h)/sqrt2 (:87-91)
     ffree(O, ob);
     return out;
   }
@@ -522,11 +553,23 @@ struct Builder {
     {
       const Mod& m = e->mods[mi++];
       Tensor h0 = talloc(nf, R, R);
-      SimtConv s; memset(&s, 0, sizeof(s));
-      s.x1 = xc; s.C1 = ch; s.in_nchw = 1; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
-      s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = e->W(m.w); s.N = nf;
-      s.epi.bias = e->W(m.b); s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out = h0.p; s.epi.ld_out = nf;
-      op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * B * R * R * (double)nf * ch * 9);
+      if (m.tc0) {
+        // im2col patches [B*R*R][32] (TF32 grid) then one K=32 tcgen05 contraction with the flat-packed weights
+        long long pb; float* patches = falloc((long long)B * R * R * 32, &pb);
+        const int Bc = B;
+        op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, st); }, 6);
+        double* qs = nullptr;
+        if (fused_stats) { qs = qalloc(nf); h0.qs = qs; }
+        gemm(true, patches, 32, (long long)B * R * R, 0, e->W(m.w), 32, nf, 0, 1, B * R * R, nf, 32, e->W(m.b), nullptr, 0, 1.f, 0,
+             h0.p, nf, qs, R * R);
+        ffree(patches, pb);
+      } else {
+        SimtConv s; memset(&s, 0, sizeof(s));
+        s.x1 = xc; s.C1 = ch; s.in_nchw = 1; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
+        s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = e->W(m.w); s.N = nf;
+        s.epi.bias = e->W(m.b); s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out = h0.p; s.epi.ld_out = nf;
+        op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * B * R * R * (double)nf * ch * 9);
+      }
       hs.push_back(h0);
       tap(m.index, h0);
     }
@@ -536,7 +579,7 @@ struct Builder {
     for (int lvl = 0; lvl < L; ++lvl) {
       for (int b = 0; b < c.num_res_blocks; ++b) {
         const Mod& m = e->mods[mi++];
-        Tensor h = resblock(m, hs.back(), Tensor()); if (rc) return rc;
+        Tensor none; Tensor h = resblock(m, hs.back(), none); if (rc) return rc;
         tap(m.index, h);
         if (mi < e->mods.size() && e->mods[mi].kind == M_ATTN && e->mods[mi].res == h.H && lvl_has_attn(h.H)) {
           const Mod& ma = e->mods[mi++];
@@ -547,7 +590,7 @@ struct Builder {
       }
       if (lvl != L - 1) {
         const Mod& m = e->mods[mi++];
-        Tensor h = resblock(m, hs.back(), Tensor()); if (rc) return rc;
+        Tensor none; Tensor h = resblock(m, hs.back(), none); if (rc) return rc;
         tap(m.index, h);
         if (c.progressive_input == 1) {
           const Mod& mp = e->mods[mi++];
@@ -556,17 +599,23 @@ struct Builder {
           const int Hin = pyr.H, p = (e->firn - 2) + 2;
           const int Hp = Hin + ((p + 1) / 2) + (p / 2) - e->firn + 1;
           long long fb; float* fbuf = falloc((long long)B * pyr.C * Hp * Hp, &fb);
+          const bool tcp = mp.tc0 && !pyr_nchw;
           if (pyr_nchw) fir(pyr.p, B * pyr.C, Hin, Hin, 1, 1, 1, (p + 1) / 2, p / 2, 0, fbuf, 1.f);
-          else fir(pyr.p, B, Hin, Hin, pyr.C, 1, 1, (p + 1) / 2, p / 2, 0, fbuf, 1.f);
+          else fir(pyr.p, B, Hin, Hin, pyr.C, 1, 1, (p + 1) / 2, p / 2, tcp ? 1 : 0, fbuf, 1.f);
           Tensor np = talloc(mp.cout, h.H, h.W);
-          SimtConv s; memset(&s, 0, sizeof(s));
-          s.x1 = fbuf; s.C1 = pyr.C; s.in_nchw = pyr_nchw ? 1 : 0; s.in_scale = 1.f; s.H = Hp; s.W = Hp; s.R = s.S = 3; s.stride = 2; s.pad = 0;
-          s.OH = h.H; s.OW = h.W; s.nbatch = B; s.a_batched = 1; s.w = e->W(mp.w); s.N = mp.cout;
-          s.epi.bias = e->W(mp.b); s.epi.residual = h.p; s.epi.ld_res = mp.cout;
-          s.epi.scale = c.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
-          s.epi.rows_per_img = h.H * h.W; s.epi.out = np.p; s.epi.ld_out = mp.cout;
           if ((Hp - 3) / 2 + 1 != h.H) { set_error("ncsnpp: pyramid geometry mismatch (%d vs %d)", (Hp - 3) / 2 + 1, h.H); return 2; }
-          op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * B * h.H * h.W * (double)mp.cout * pyr.C * 9);
+          const float ps = c.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
+          if (tcp) {
+            Tensor fin; fin.p = fbuf; fin.C = pyr.C; fin.H = Hp; fin.W = Hp;
+            conv(true, fin, Tensor(), 9, mp.w, mp.b, mp.cout, -1, h.p, ps, 0, np, /*want_stats=*/true, /*stride=*/2, /*Hin=*/Hp);
+          } else {
+            SimtConv s; memset(&s, 0, sizeof(s));
+            s.x1 = fbuf; s.C1 = pyr.C; s.in_nchw = pyr_nchw ? 1 : 0; s.in_scale = 1.f; s.H = Hp; s.W = Hp; s.R = s.S = 3; s.stride = 2; s.pad = 0;
+            s.OH = h.H; s.OW = h.W; s.nbatch = B; s.a_batched = 1; s.w = e->W(mp.w); s.N = mp.cout;
+            s.epi.bias = e->W(mp.b); s.epi.residual = h.p; s.epi.ld_res = mp.cout; s.epi.scale = ps;
+            s.epi.rows_per_img = h.H * h.W; s.epi.out = np.p; s.epi.ld_out = mp.cout;
+            op(1, [=](cudaStream_t st) { return launch_conv_simt(s, st); }, 1, 2.0 * B * h.H * h.W * (double)mp.cout * pyr.C * 9);
+          }
           ffree(fbuf, fb);
           if (pyr_owned) tfree(pyr);
           tfree(h);
@@ -579,9 +628,9 @@ struct Builder {
     // ---- middle (ncsnpp.py:305-311) ----
     Tensor h;
     {
-      const Mod& m0 = e->mods[mi++]; h = resblock(m0, hs.back(), Tensor()); if (rc) return rc; tap(m0.index, h);
+      Tensor none; const Mod& m0 = e->mods[mi++]; h = resblock(m0, hs.back(), none); if (rc) return rc; tap(m0.index, h);
       const Mod& ma = e->mods[mi++]; Tensor h2 = attn(ma, h); if (rc) return rc; tfree(h); h = h2; tap(ma.index, h);
-      const Mod& m1 = e->mods[mi++]; Tensor h3 = resblock(m1, h, Tensor()); if (rc) return rc; tfree(h); h = h3; tap(m1.index, h);
+      const Mod& m1 = e->mods[mi++]; Tensor h3 = resblock(m1, h, none); if (rc) return rc; tfree(h); h = h3; tap(m1.index, h);
     }
     // ---- up path (ncsnpp.py:316-364) ----
     for (int lvl = L - 1; lvl >= 0; --lvl) {
@@ -596,30 +645,47 @@ struct Builder {
         const Mod& ma = e->mods[mi++]; Tensor h2 = attn(ma, h); if (rc) return rc; tfree(h); h = h2; tap(ma.index, h);
       }
       if (lvl != 0) {
-        const Mod& m = e->mods[mi++]; Tensor h2 = resblock(m, h, Tensor()); if (rc) return rc; tfree(h); h = h2; tap(m.index, h);
+        Tensor none; const Mod& m = e->mods[mi++]; Tensor h2 = resblock(m, h, none); if (rc) return rc; tfree(h); h = h2; tap(m.index, h);
       }
     }
     // ---- output head (ncsnpp.py:371-379) ----
     {
       const Mod& mg = e->mods[mi++];
       Tensor a = talloc(h.C, h.H, h.W);
-      gn(h, Tensor(), mg.w, mg.b, 1, 0, a, nullptr);
+      Tensor none; gn(h, none, mg.w, mg.b, 1, 0, a, nullptr);
       tfree(h);
       const Mod& mo = e->mods[mi++];
-      SimtConv s; memset(&s, 0, sizeof(s));
-      s.x1 = a.p; s.C1 = a.C; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
-      s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = e->W(mo.w); s.N = ch;
-      s.epi.bias = e->W(mo.b); s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out_nchw = 1; s.epi.ld_out = ch;
       const int sbs = c.scale_by_sigma;
-      op(1, [=](cudaStream_t st) {
-        SimtConv cc = s;
-        cc.epi.out = eng->out;
-        if (sbs) { cc.epi.per_img_div = eng->in_labels; cc.epi.div_stride = eng->uniform ? 0 : 1; }
-        return launch_conv_simt(cc, st);
-      }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
+      const float *wo = e->W(mo.w), *bo = e->W(mo.b);
+      const Tensor ain = a; const int Bc = B;
+      if (ch <= 4) {
+        op(1, [=](cudaStream_t st) {
+          return launch_conv3x3_small_n(ain.p, wo, bo, sbs ? eng->in_labels : nullptr, eng->uniform ? 0 : 1, eng->out,
+                                        Bc, R, R, ain.C, ch, st);
+        }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
+      } else {
+        SimtConv s; memset(&s, 0, sizeof(s));
+        s.x1 = a.p; s.C1 = a.C; s.in_scale = 1.f; s.H = R; s.W = R; s.R = s.S = 3; s.stride = 1; s.pad = 1;
+        s.OH = R; s.OW = R; s.nbatch = B; s.a_batched = 1; s.w = wo; s.N = ch;
+        s.epi.bias = bo; s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out_nchw = 1; s.epi.ld_out = ch;
+        op(1, [=](cudaStream_t st) {
+          SimtConv cc = s;
+          cc.epi.out = eng->out;
+          if (sbs) { cc.epi.per_img_div = eng->in_labels; cc.epi.div_stride = eng->uniform ? 0 : 1; }
+          return launch_conv_simt(cc, st);
+        }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
+      }
       tfree(a);
     }
     if (mi != e->mods.size()) { set_error("ncsnpp: plan walked %zu of %zu modules", mi, e->mods.size()); return 2; }
+    if (!dry && stats_top > 0) {
+      // the epilogue-accumulated GroupNorm sums start from zero every forward: one memset of the whole region
+      char* sb = stats_base; const long long sn = stats_top;
+      e->launches += 1;
+      e->ops.insert(e->ops.begin(), b200_ncsnpp::Op{6, 0.0, [=](cudaStream_t st) {
+        return cudaMemsetAsync(sb, 0, (size_t)sn, st) == cudaSuccess ? 0 : (set_error("stats memset failed"), 1);
+      }});
+    }
     (void)eb; (void)t1b; (void)t2b; (void)db; (void)xcb;
     return rc;
   }
@@ -659,13 +725,13 @@ int b200_ncsnpp_param_info(const b200_ncsnpp_t* h, int index, char* name, int na
   return 0;
 }
 
-long long b200_ncsnpp_weights_bytes(const b200_ncsnpp_t* h) { return h ? h->wcount * 4 : 0; }
+long long b200_ncsnpp_weights_bytes(const b200_ncsnpp_t* h) { return h ? h->wcount * 4 + 256 : 0; }
 
 int b200_ncsnpp_bind_weights(b200_ncsnpp_t* h, void* blob) {
   B200_REQUIRE(h && blob, "bind_weights: null argument");
-  B200_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 255) == 0, "bind_weights: blob must be 256-byte aligned");
   B200_REQUIRE(h->ops.empty(), "bind_weights: rebind after planning is not supported");
-  h->wblob = static_cast<float*>(blob);
+  // the blob is over-allocated by 256 B (b200_ncsnpp_weights_bytes) so any base can be aligned here
+  h->wblob = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(blob) + 255) & ~uintptr_t(255));
   return 0;
 }
 
@@ -679,6 +745,8 @@ int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* 
     B200_CHECK_CUDA(cudaMemcpyAsync(dst, src, p.count * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
+  if (p.pack == PK_CONV_FLAT32)   // OIHW (3x3, I*9 <= 32) -> [O][32] with k = tap*I + i (rest of the row stays zero)
+    return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st, p.I, 32);
   if (p.pack == PK_CONV)   // OIHW -> [tap][O][I]
     return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st);
   // NIN W[in][out] -> [out][in]
@@ -689,20 +757,23 @@ long long b200_ncsnpp_workspace_bytes(b200_ncsnpp_t* h, int batch) {
   if (!h || batch <= 0) return -1;
   Builder b(h, batch, nullptr, true);
   if (b.build()) return -1;
-  return b.arena.high_water() + 1024;
+  return ((b.arena.high_water() + 1023) & ~1023LL) + b.stats_top + 2048;   // + slack to align any caller pointer to 1024 B
 }
 
 int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long ws_bytes) {
   B200_REQUIRE(h && ws && batch > 0, "bind_workspace: bad argument");
   B200_REQUIRE(h->wblob, "bind_workspace: bind the weight blob first");
-  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "bind_workspace: workspace must be 1024-byte aligned");
   const long long need = b200_ncsnpp_workspace_bytes(h, batch);
   B200_REQUIRE(need >= 0, "bind_workspace: planning failed: %s", last_error());
   B200_REQUIRE(ws_bytes >= need, "bind_workspace: workspace too small (%lld < %lld bytes)", ws_bytes, need);
   for (auto* p : h->tcplans) tc_gemm_plan_destroy(p);
   h->tcplans.clear(); h->ops.clear(); h->taps.clear(); h->launches = 0;
-  h->B = batch; h->ws = static_cast<char*>(ws); h->ws_bytes = ws_bytes;
+  h->B = batch; h->ws_bytes = ws_bytes;
+  h->ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  Builder dry(h, batch, nullptr, true);
+  if (int r = dry.build()) return r;
   Builder b(h, batch, h->ws, false);
+  b.stats_base = h->ws + ((dry.arena.high_water() + 1023) & ~1023LL);   // quad sums live after the activation arena
   if (int r = b.build()) { h->ops.clear(); return r; }
   return 0;
 }
@@ -773,8 +844,9 @@ struct b200_pc {
   PhiloxMap map;
   cudaGraphExec_t gexec = nullptr; float* graph_x = nullptr; float* graph_xm = nullptr; cudaStream_t graph_stream = nullptr;
   unsigned long long graph_seed = 0;
+  cudaStream_t cap_stream = nullptr;   // the legacy default stream cannot be captured: capture on a private one
   long long launches_per_step = 0;
-  ~b200_pc() { if (gexec) cudaGraphExecDestroy(gexec); }
+  ~b200_pc() { if (gexec) cudaGraphExecDestroy(gexec); if (cap_stream) cudaStreamDestroy(cap_stream); }
 };
 
 namespace {
@@ -847,16 +919,16 @@ void b200_pc_destroy(b200_pc_t* pc) { delete pc; }
 
 long long b200_pc_workspace_bytes(const b200_pc_t* pc) {
   if (!pc) return -1;
-  b200_pc tmp = *pc; tmp.gexec = nullptr;
-  return pc_ws_layout(&tmp, nullptr) + 256;
+  b200_pc tmp = *pc; tmp.gexec = nullptr; tmp.cap_stream = nullptr;
+  return pc_ws_layout(&tmp, nullptr) + 512;
 }
 
 int b200_pc_bind_workspace(b200_pc_t* pc, void* ws, long long bytes, void* stream) {
   B200_REQUIRE(pc && ws, "pc_bind_workspace: null argument");
-  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "pc_bind_workspace: workspace must be 256-byte aligned");
-  const long long need = pc_ws_layout(pc, static_cast<char*>(ws));
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  const long long need = pc_ws_layout(pc, base) + (base - static_cast<char*>(ws));
   B200_REQUIRE(bytes >= need, "pc_bind_workspace: workspace too small (%lld < %lld)", bytes, need);
-  pc->ws = static_cast<char*>(ws);
+  pc->ws = base;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = pc->cfg.n_steps;
   B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_label, pc->h_label.data(), N * 4, cudaMemcpyHostToDevice, st));
@@ -887,9 +959,10 @@ int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_
     if (!pc->gexec || pc->graph_x != x || pc->graph_xm != x_mean || pc->graph_seed != seed || pc->graph_stream != st) {
       if (pc->gexec) { cudaGraphExecDestroy(pc->gexec); pc->gexec = nullptr; }
       cudaGraph_t g = nullptr;
-      B200_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const int r = pc_iteration(pc, x, x_mean, nullptr, nullptr, st);
-      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (!pc->cap_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&pc->cap_stream, cudaStreamNonBlocking));
+      B200_CHECK_CUDA(cudaStreamBeginCapture(pc->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int r = pc_iteration(pc, x, x_mean, nullptr, nullptr, pc->cap_stream);
+      const cudaError_t ce = cudaStreamEndCapture(pc->cap_stream, &g);
       if (r) { if (g) cudaGraphDestroy(g); return r; }
       B200_CHECK_CUDA(ce);
       B200_CHECK_CUDA(cudaGraphInstantiate(&pc->gexec, g, 0));

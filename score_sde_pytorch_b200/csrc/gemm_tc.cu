@@ -27,6 +27,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
+#include <cstring>
 
 namespace b200 {
 
@@ -38,12 +40,14 @@ constexpr int UMMA_K = 8;        // tf32
 constexpr int A_STAGE_BYTES = BM * BKE * 4;   // 16 KiB
 
 struct TcParams {
-  CUtensorMap tmA1, tmA2, tmW;
-  int conv, H, W, taps, pad, S;        // S = filter width (3 or 1)
+  CUtensorMap tmA1, tmA2, tmW, tmOut, tmRes;
+  int conv, H, W, taps, pad, S, stride;   // H, W: OUTPUT spatial size; S = filter width (3 or 1)
   int kchunks1, kchunks2, C1;
   int N_total, tiles_n;
   int nbatch, tiles_m_per_batch, M_per_batch;
   int a_batch_rows, w_batch_rows;
+  int epi_mode;                            // 0: direct register->global stores, 1: smem-staged TMA store (+TMA residual)
+  double* qstats;                          // optional [img][N_total/4][2] GroupNorm quad sums (sum, sum of squares)
   long long total_tiles;
   Epilogue epi;
 };
@@ -94,6 +98,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, ui
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -138,8 +153,12 @@ template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BKE * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_TILE_BYTES = BM * 32 * 4;         // one 128-row x 32-column fp32 chunk (128-B swizzled rows)
+  static constexpr int OUT_OFFSET = STAGES * STAGE_BYTES;   // 3 output staging chunks for the TMA store
+  static constexpr int RES_OFFSET = OUT_OFFSET + 3 * EPI_TILE_BYTES;   // 2 residual chunks landed by TMA
+  static constexpr int BAR_OFFSET = RES_OFFSET + 2 * EPI_TILE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-B alignment
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
 
 // ---------------------------------------------------------------------------
@@ -154,13 +173,14 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); mbar_init(&res_full[a], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-            if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 + dw, h0 + dh, img0);
+            if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
             else tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, arow0, 0, 0);
             tma_load_2d(&p.tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -238,8 +258,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       umma_commit(&tmem_full[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4) {
-    // ======================= epilogue =======================
+  } else if (warp >= 4 && p.epi_mode == 0) {
+    // ======================= epilogue (direct stores; validation / fallback path) =======================
     const int q = warp - 4;                    // TMEM lane quarter owned by this warp
     const int r = q * 32 + lane;               // row of the tile held by this thread
     const Epilogue& e = p.epi;
@@ -284,6 +304,117 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
+  
+  } else if (warp >= 4) {
+    // ======================= epilogue (smem-staged: TMA residual load, TMA store, GN quad sums) ==========
+    // Per 32-column chunk: TMEM -> registers, + bias + time-embedding row + residual (landed in smem
+    // by TMA one chunk ahead), scale, optional TF32 rounding; the finished 128x32 chunk is written to
+    // a 128-B-swizzled staging tile and stored with one TMA bulk store (full 128-B lines, asynchronous),
+    // three staging tiles deep.  Optionally the per-(image, 4-channel quad) sum / sum of squares of the
+    // stored values are reduced across the warp's rows and accumulated in fp64: the next GroupNorm
+    // needs no pass over the tensor to get its statistics.
+    const int q = warp - 4;
+    const int r = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    const Epilogue& e = p.epi;
+    constexpr int NCH = BN / 32;
+    float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET);
+    float* res_stage = reinterpret_cast<float*>(smem + L::RES_OFFSET);
+    const bool has_res = e.residual != nullptr;
+    const long long my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_chunks = my_tiles * NCH;
+    auto chunk_origin = [&](long long g, int& row0, int& col0) {
+      const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
+      const int nt = (int)(tile % p.tiles_n);
+      const long long mg = tile / p.tiles_n;
+      row0 = (int)(mg / p.tiles_m_per_batch) * p.M_per_batch + (int)(mg % p.tiles_m_per_batch) * BM;
+      col0 = nt * BN + (int)(g % NCH) * 32;
+    };
+    if (issuer && has_res) {
+      for (long long g = 0; g < 2 && g < total_chunks; ++g) {
+        int row0, col0; chunk_origin(g, row0, col0);
+        mbar_expect_tx(&res_full[g & 1], L::EPI_TILE_BYTES);
+        tma_load_2d(&p.tmRes, res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4), &res_full[g & 1], col0, row0);
+      }
+    }
+    const int sw = r & 7;                                 // 128-B swizzle phase of this thread's row
+    uint32_t acc = 0, acc_phase = 0;
+    int m = 0, img = 0; bool valid = false; long long gm = 0; float dv = 1.f;
+    for (long long g = 0; g < total_chunks; ++g) {
+      const int j = (int)(g % NCH);
+      int row0, col0; chunk_origin(g, row0, col0);
+      if (j == 0) {
+        const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
+        const long long mg = tile / p.tiles_n;
+        m = (int)(mg % p.tiles_m_per_batch) * BM + r;
+        valid = m < p.M_per_batch;
+        gm = (long long)(mg / p.tiles_m_per_batch) * p.M_per_batch + m;
+        img = valid ? (int)(gm / e.rows_per_img) : 0;
+        dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+      }
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
+      const float* rs = res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4) + r * 32;
+      if (has_res) mbar_wait(&res_full[g & 1], (uint32_t)((g >> 1) & 1));
+      float* os = out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4) + r * 32;
+      const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + col0 : nullptr;
+      float qs[8], qq[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 o = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                               __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+        if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+        if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+        if (has_res) { const float4 t = *reinterpret_cast<const float4*>(rs + ((c ^ sw) << 2)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+        o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
+        if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
+        if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        *reinterpret_cast<float4*>(os + ((c ^ sw) << 2)) = o;
+        if (p.qstats) {
+          qs[c] = valid ? (o.x + o.y) + (o.z + o.w) : 0.f;
+          qq[c] = valid ? (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w) : 0.f;
+        }
+      }
+      if (p.qstats) {
+        // rows of one warp belong to one image (rows_per_img % 32 == 0) or to two (rows_per_img == 16)
+        const bool halves = e.rows_per_img < 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            if (o == 16 && halves) break;
+            qs[c] += __shfl_xor_sync(0xffffffffu, qs[c], o);
+            qq[c] += __shfl_xor_sync(0xffffffffu, qq[c], o);
+          }
+        }
+        if ((lane == 0 || (halves && lane == 16)) && valid) {
+          double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (col0 >> 2)) * 2;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { atomicAdd(dst + 2 * c, (double)qs[c]); atomicAdd(dst + 2 * c + 1, (double)qq[c]); }
+        }
+      }
+      fence_async_smem();                                   // generic-proxy smem writes -> visible to the TMA engine
+      if (issuer) bulk_wait_read<1>();                      // store g-2 has drained: staging tile (g+1)%3 is free
+      epi_barrier();
+      if (issuer) {
+        tma_store_2d(&p.tmOut, out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4), col0, row0);
+        bulk_commit();
+        if (has_res && g + 2 < total_chunks) {
+          int r2, c2; chunk_origin(g + 2, r2, c2);
+          mbar_expect_tx(&res_full[g & 1], L::EPI_TILE_BYTES);
+          tma_load_2d(&p.tmRes, res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4), &res_full[g & 1], c2, r2);
+        }
+      }
+      if (j == NCH - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    if (issuer) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -311,11 +442,12 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   auto fn = get_encode_fn();
   B200_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm_tc: operand base %p not 16-byte aligned", (const void*)base);
   uint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -340,6 +472,7 @@ struct TcGemmPlan {
 };
 
 static int tc_configure();
+int tc_gemm_default_epi_mode();
 
 bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
   static const char* w;
@@ -349,6 +482,8 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
   if (d.taps != 1 && d.taps != 9) return fail("only 1x1 and 3x3 filters");
   if (d.conv) {
     if (d.nbatch != 1) return fail("conv mode is unbatched");
+    if (d.stride > 2) return fail("stride must be 1 or 2");
+    if (d.stride == 2 && d.a2) return fail("strided conv is single-source");
     const int HW = d.H * d.W;
     if (HW >= BM) {
       if (d.W >= BM) { if (d.W % BM) return fail("image width does not tile 128 pixels"); }
@@ -359,6 +494,7 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
     if (d.a_ld % 4) return fail("A row pitch must be a multiple of 4 floats");
   }
   if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
+  if (d.qstats && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("quad stats need rows_per_img % 32 == 0 or == 16");
   if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 floats");
   return true;
 }
@@ -372,7 +508,11 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   memset(&p, 0, sizeof(p));
   pl->bn = (d.N_total % 256 == 0) ? 256 : 128;
   p.conv = d.conv; p.H = d.conv ? d.H : 1; p.W = d.conv ? d.W : 1; p.taps = d.taps;
-  p.S = d.taps == 9 ? 3 : 1; p.pad = d.taps == 9 ? 1 : 0;
+  p.S = d.taps == 9 ? 3 : 1; p.pad = (d.taps == 9 && !d.valid_pad) ? 1 : 0;
+  p.stride = d.stride == 2 ? 2 : 1;
+  p.epi_mode = d.epi_mode < 0 ? tc_gemm_default_epi_mode() : d.epi_mode;
+  p.qstats = p.epi_mode == 1 ? d.qstats : nullptr;
+  B200_REQUIRE(!(d.qstats && p.epi_mode != 1), "gemm_tc: fused GroupNorm sums need the staged epilogue");
   p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
   p.N_total = d.N_total; p.tiles_n = d.N_total / pl->bn;
   p.a_batch_rows = d.a_batch_rows; p.w_batch_rows = d.w_batch_rows;
@@ -387,13 +527,17 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     if (HW >= BM) { box[1] = std::min(d.W, BM); box[2] = BM / box[1]; box[3] = 1; }
     else { box[1] = d.W; box[2] = d.H; box[3] = BM / HW; }
     box[0] = BKE;
+    // stride 2: the box *traverses* 2x as many pixels and TMA keeps every other one
+    const uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
+    box[1] *= p.stride; box[2] *= p.stride;
+    const int Hin = d.Hin ? d.Hin : d.H, Win = d.Win ? d.Win : d.W;
     for (int s = 0; s < 2; ++s) {
       const float* base = s ? d.a2 : d.a1;
       const int C = s ? d.C2 : d.C1;
       if (!base) continue;
-      uint64_t dims[4] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.nimg};
-      uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)d.W * C * 4, (uint64_t)HW * C * 4};
-      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box);
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)d.nimg};
+      uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)Win * C * 4, (uint64_t)Hin * Win * C * 4};
+      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box, estr);
       if (rc) { delete pl; return rc; }
     }
   } else {
@@ -416,6 +560,22 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
     if (rc) { delete pl; return rc; }
   }
+  if (p.epi_mode == 1) {
+    const uint64_t out_rows = (uint64_t)p.nbatch * (uint64_t)p.M_per_batch;
+    uint32_t box[2] = {32, BM};
+    {
+      uint64_t dims[2] = {(uint64_t)d.N_total, out_rows};
+      uint64_t str[1] = {(uint64_t)d.epi.ld_out * 4};
+      rc = encode_map(&p.tmOut, d.epi.out, 2, dims, str, box);
+      if (rc) { delete pl; return rc; }
+    }
+    if (d.epi.residual) {
+      uint64_t dims[2] = {(uint64_t)d.N_total, out_rows};
+      uint64_t str[1] = {(uint64_t)d.epi.ld_res * 4};
+      rc = encode_map(&p.tmRes, d.epi.residual, 2, dims, str, box);
+      if (rc) { delete pl; return rc; }
+    } else p.tmRes = p.tmOut;
+  }
   p.total_tiles = (long long)p.nbatch * p.tiles_m_per_batch * p.tiles_n;
   *out = pl;
   return 0;
@@ -423,13 +583,17 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
+int tc_gemm_default_epi_mode() {
+  static const int mode = [] { const char* v = getenv("B200_TC_EPILOGUE"); return (v && !strcmp(v, "direct")) ? 0 : 1; }();
+  return mode;
+}
 
 // Opt in to the large dynamic shared-memory carve-out once, outside any stream capture.
 static int tc_configure() {
   static bool configured = false;
   if (configured) return 0;
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 3>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 4>::TOTAL));
   configured = true;
   return 0;
 }
@@ -445,7 +609,7 @@ static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
 
 int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
   if (pl->prm.total_tiles == 0) return 0;
-  return pl->bn == 256 ? launch_impl<256, 4>(pl, st) : launch_impl<128, 6>(pl, st);
+  return pl->bn == 256 ? launch_impl<256, 3>(pl, st) : launch_impl<128, 4>(pl, st);
 }
 
 }  // namespace b200

@@ -10,10 +10,9 @@
 namespace b200 {
 
 // ---- elementwise.cu --------------------------------------------------------
-int launch_gn_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int G,
-                    float eps, float* stats, cudaStream_t st);
-int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const float* stats,
-                    const float* gamma, const float* beta, int B, int HW, int G, int act,
+int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st);
+int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
+                    const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
                     int round_out, float* y, float* raw, cudaStream_t st);
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
                      int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
@@ -30,7 +29,10 @@ int launch_linear_rows(const float* x, long long ldx, const float* W, const floa
 int launch_fill_from_table(const float* table, const int* step, float* dst, int n, cudaStream_t st);
 int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cudaStream_t st);
 int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, long long so, long long si,
-                       long long stp, int round_out, cudaStream_t st);
+                       long long stp, int round_out, cudaStream_t st, long long dt = 0, long long dO = 0);
+int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int H, int W, cudaStream_t st);
+int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
+                           float* out_nchw, int B, int H, int W, int C, int N, cudaStream_t st);
 
 // ---- conv_simt.cu : strict-fp32 CUDA-core implicit GEMM (any shape) ---------
 struct SimtConv {
@@ -59,8 +61,11 @@ struct TcGemmDesc {
   // A: NHWC activations, values already on the TF32 grid.
   const float* a1; int C1; const float* a2; int C2;     // two-source channel concat (a2 may be null)
   int conv;                 // 1: 4-D box gather with zero halo; 0: plain row-major [rows, K]
-  int H, W, nimg;           // conv geometry (stride 1, 'same' padding); gemm: unused
+  int H, W, nimg;           // conv: OUTPUT spatial size and image count; gemm: unused
   int taps;                 // 9 (3x3) or 1
+  int stride;               // conv: 1 (default when 0) or 2 (TMA element strides gather every other pixel)
+  int valid_pad;            // conv: 1 = no padding (VALID, input is Hin x Win), 0 = 'same' padding
+  int Hin, Win;             // conv: input spatial size (0 = same as H, W)
   long long a_rows;         // gemm: total rows of A; a_ld = row pitch in elements
   long long a_ld;
   int a_batch_rows;         // gemm: rows to advance per batch item (0 = shared)
@@ -69,6 +74,8 @@ struct TcGemmDesc {
   long long w_ld;           // row pitch of W in elements (0 = K_total)
   int w_batch_rows;         // rows to advance per batch item (0 = shared)
   int nbatch; int M_per_batch;   // gemm: rows of output per batch item; conv: nbatch=1, M=nimg*H*W
+  int epi_mode;             // 0 direct stores, 1 smem-staged TMA store, -1 = library default
+  double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
   Epilogue epi;
 };
 int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out);
