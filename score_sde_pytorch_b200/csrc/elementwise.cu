@@ -393,10 +393,52 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
 }
 
+// T == 256 (the 16x16 attention of NCSN++): one warp per row, two 128-bit accesses per lane each way,
+// two rows per warp iteration in flight.
+__global__ void __launch_bounds__(256) softmax_rows256_kernel(const float* __restrict__ s, float* __restrict__ p,
+                                                             long long rows, float scale, int round_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp_id * 2; row < rows; row += nwarps * 2) {
+    float4 a[2][2];
+    const bool two = row + 1 < rows;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float4* src = reinterpret_cast<const float4*>(s + (row + (two ? r : 0)) * 256);
+      a[r][0] = __ldg(src + lane); a[r][1] = __ldg(src + 32 + lane);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float* e = reinterpret_cast<float*>(a[r]);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] *= scale; mx = fmaxf(mx, e[i]); }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] = expf(e[i] - mx); sum += e[i]; }
+      sum = warp_sum(sum);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] = e[i] / sum; if (round_out) e[i] = round_tf32(e[i]); }
+      if (r == 0 || two) {
+        float4* dst = reinterpret_cast<float4*>(p + (row + r) * 256);
+        dst[lane] = a[r][0]; dst[32 + lane] = a[r][1];
+      }
+    }
+  }
+}
+
 int launch_softmax_rows(const float* s, float* p, long long rows, int T, float scale, int round_out,
                         cudaStream_t st) {
   B200_REQUIRE(T > 0 && T <= 1024, "softmax_rows: T=%d out of range (1..1024)", T);
   const int wpb = 8;
+  if (T == 256 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(p)) & 15) == 0) {
+    const long long blocks = std::min<long long>((rows / 2 + wpb - 1) / wpb + 1, 148LL * 16);
+    softmax_rows256_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(s, p, rows, scale, round_out);
+    B200_CHECK_LAUNCH();
+    return 0;
+  }
   softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(s, p, rows, T, scale, round_out);
   B200_CHECK_LAUNCH();
   return 0;
