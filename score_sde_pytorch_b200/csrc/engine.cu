@@ -295,7 +295,7 @@ struct Builder {
   bool fused_stats = false;
   Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0) {
     const char* v = getenv("B200_FUSED_GN_STATS");
-    fused_stats = (e_->cfg.precision == 0) && tc_gemm_default_epi_mode() == 1 && !(v && v[0] == '0');
+    fused_stats = (e_->cfg.precision == 0) && !(v && v[0] == '0');
     if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
   }
   double* qalloc(int C) {

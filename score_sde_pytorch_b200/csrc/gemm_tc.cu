@@ -47,6 +47,7 @@ struct TcParams {
   int nbatch, tiles_m_per_batch, M_per_batch;
   int a_batch_rows, w_batch_rows;
   int epi_mode;                            // 0: direct register->global stores, 1: smem-staged TMA store (+TMA residual)
+  int swap;                                // 1: operands swapped (D^T = W X^T): 128 output channels x 256 pixels per tile
   double* qstats;                          // optional [img][N_total/4][2] GroupNorm quad sums (sum, sum of squares)
   long long total_tiles;
   Epilogue epi;
@@ -149,24 +150,47 @@ __host__ __device__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STAGED>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BKE * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_TILE_BYTES = BM * 32 * 4;         // one 128-row x 32-column fp32 chunk (128-B swizzled rows)
   static constexpr int OUT_OFFSET = STAGES * STAGE_BYTES;   // 3 output staging chunks for the TMA store
-  static constexpr int RES_OFFSET = OUT_OFFSET + 3 * EPI_TILE_BYTES;   // 2 residual chunks landed by TMA
-  static constexpr int BAR_OFFSET = RES_OFFSET + 2 * EPI_TILE_BYTES;
+  static constexpr int RES_OFFSET = OUT_OFFSET + (STAGED ? 3 : 0) * EPI_TILE_BYTES;   // 2 residual chunks landed by TMA
+  static constexpr int BAR_OFFSET = RES_OFFSET + (STAGED ? 2 : 0) * EPI_TILE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-B alignment
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
 
+// GroupNorm quad sums of one 32-column chunk held one row per lane: reduce over the warp's rows
+// (one image per warp when rows_per_img % 32 == 0, two when rows_per_img == 16) and accumulate in fp64.
+__device__ __forceinline__ void direct_stats(const TcParams& p, const Epilogue& e, float (&qs)[8], float (&qq)[8],
+                                             int img, int n0, int lane) {
+  const bool halves = e.rows_per_img < 32;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      if (o == 16 && halves) break;
+      qs[c] += __shfl_xor_sync(0xffffffffu, qs[c], o);
+      qq[c] += __shfl_xor_sync(0xffffffffu, qq[c], o);
+    }
+  }
+  if (lane == 0 || (halves && lane == 16)) {
+    double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (n0 >> 2)) * 2;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (qs[c] != 0.f || qq[c] != 0.f) { atomicAdd(dst + 2 * c, (double)qs[c]); atomicAdd(dst + 2 * c + 1, (double)qq[c]); }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STAGED>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -212,7 +236,14 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         h0 = rem / p.W; w0 = rem % p.W;
       }
       const int arow0 = b * p.a_batch_rows + mt * BM;
-      const int wrow0 = b * p.w_batch_rows + nt * BN;
+      const int wrow0 = b * p.w_batch_rows + nt * (p.swap ? 128 : BN);
+      int img1 = 0, h1 = 0, w1 = 0;                     // swap mode: second 128-pixel box of the 256-pixel tile
+      if (p.swap) {
+        const long long p0 = (long long)mt * 256;
+        img0 = (int)(p0 / HW); h0 = (int)(p0 % HW) / p.W; w0 = (int)(p0 % HW) % p.W;
+        const long long p1 = p0 + 128;
+        img1 = (int)(p1 / HW); h1 = (int)(p1 % HW) / p.W; w1 = (int)(p1 % HW) % p.W;
+      }
       for (int src = 0; src < 2; ++src) {
         const int nch = src ? p.kchunks2 : p.kchunks1;
         if (nch == 0) continue;
@@ -225,9 +256,16 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-            if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
-            else tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, arow0, 0, 0);
-            tma_load_2d(&p.tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            if (p.swap) {
+              // first 16 KiB: 128 output channels x 32 k of W (UMMA A); next 32 KiB: 256 pixels x 32 k (UMMA B)
+              tma_load_2d(&p.tmW, sa, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+              tma_load_4d(tmA, sb, &full_bar[stage], kc * BKE, w0 + dw, h0 + dh, img0);
+              tma_load_4d(tmA, sb + A_STAGE_BYTES, &full_bar[stage], kc * BKE, w1 + dw, h1 + dh, img1);
+            } else {
+              if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
+              else tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, arow0, 0, 0);
+              tma_load_2d(&p.tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       umma_commit(&tmem_full[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4 && p.epi_mode == 0) {
+  } else if (warp >= 4 && !STAGED) {
     // ======================= epilogue (direct stores; validation / fallback path) =======================
     const int q = warp - 4;                    // TMEM lane quarter owned by this warp
     const int r = q * 32 + lane;               // row of the tile held by this thread
@@ -280,8 +318,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
+        const int n0 = nt * BN + j * 32;
+        float qs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, qq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (valid) {
-          const int n0 = nt * BN + j * 32;
           float* dst = e.out + gm * e.ld_out + n0;
           const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
           const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
@@ -296,16 +335,109 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
             if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
             *reinterpret_cast<float4*>(dst + c) = o;
+            qs[c >> 2] = (o.x + o.y) + (o.z + o.w);
+            qq[c >> 2] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
           }
         }
+        if (p.qstats) direct_stats(p, e, qs, qq, img, n0, lane);   // whole warp, convergent
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && STAGED && p.swap) {
+    // ======================= epilogue, swapped operands (BN == 256 instantiation only) ====================
+    // TMEM lane = output channel, column = pixel.  Per 32-pixel chunk the thread adds its channel's bias /
+    // time-embedding value and the residual, then scatters the 32 pixels of its channel into four
+    // [32 px][32 ch] 128-B-swizzled staging boxes (conflict free: a warp writes one 128-B row per pixel),
+    // stored by TMA.  GroupNorm quad sums: per-thread over the tile's 256 pixels, then across 4 lanes.
+    if constexpr (BN == 256 && STAGED) {
+      const int q = warp - 4;
+      const int t = q * 32 + lane;                              // channel within the 128-channel tile
+      const bool issuer = (threadIdx.x == 128);
+      const Epilogue& e = p.epi;
+      constexpr int NCH = 8;                                    // 256 pixels / 32
+      float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET);
+      float* res_stage = reinterpret_cast<float*>(smem + L::RES_OFFSET);
+      const bool has_res = e.residual != nullptr;
+      const long long my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const long long total_chunks = my_tiles * NCH;
+      auto chunk_origin = [&](long long g, int& row0, int& col0) {
+        const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
+        col0 = (int)(tile % p.tiles_n) * 128;
+        row0 = (int)(tile / p.tiles_n) * 256 + (int)(g % NCH) * 32;
+      };
+      auto load_res = [&](long long g) {
+        int row0, col0; chunk_origin(g, row0, col0);
+        float* dst = res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4);
+        mbar_expect_tx(&res_full[g & 1], L::EPI_TILE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx) tma_load_2d(&p.tmRes, dst + bx * 1024, &res_full[g & 1], col0 + bx * 32, row0);
+      };
+      if (issuer && has_res) { for (long long g = 0; g < 2 && g < total_chunks; ++g) load_res(g); }
+      // element (pixel i, channel t) of a chunk lives at: box q (1024 floats), row i (32 floats), 16-B chunk (lane>>2)^(i&7)
+      const int box_off = q * 1024 + (lane & 3);
+      const int ch16 = lane >> 2;
+      uint32_t acc = 0, acc_phase = 0;
+      int co = 0, img = 0; float bias_v = 0.f, row_v = 0.f, dv = 1.f, ssum = 0.f, ssq = 0.f;
+      for (long long g = 0; g < total_chunks; ++g) {
+        const int j = (int)(g % NCH);
+        int row0, col0; chunk_origin(g, row0, col0);
+        if (j == 0) {
+          co = col0 + t;
+          img = row0 / e.rows_per_img;                          // rows_per_img % 256 == 0: one image per tile
+          bias_v = e.bias ? __ldg(e.bias + co) : 0.f;
+          row_v = e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f;
+          dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+          ssum = 0.f; ssq = 0.f;
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + j * 32, v);
+        if (has_res) mbar_wait(&res_full[g & 1], (uint32_t)((g >> 1) & 1));
+        const float* rs = res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4) + box_off;
+        float* os = out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4) + box_off;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int off = i * 32 + ((ch16 ^ (i & 7)) << 2);
+          float o = __uint_as_float(v[i]) + bias_v + row_v;
+          if (has_res) o += rs[off];
+          o *= e.scale;
+          if (e.per_img_div) o /= dv;
+          if (e.round_tf32) o = round_tf32(o);
+          os[off] = o;
+          ssum += o; ssq += o * o;
+        }
+        fence_async_smem();
+        if (issuer) bulk_wait_read<1>();
+        epi_barrier();
+        if (issuer) {
+          const float* src = out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4);
+#pragma unroll
+          for (int bx = 0; bx < 4; ++bx) tma_store_2d(&p.tmOut, src + bx * 1024, col0 + bx * 32, row0);
+          bulk_commit();
+          if (has_res && g + 2 < total_chunks) load_res(g + 2);
+        }
+        if (j == NCH - 1) {
+          if (p.qstats) {
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+            if ((lane & 3) == 0) {
+              double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (co >> 2)) * 2;
+              atomicAdd(dst, (double)ssum); atomicAdd(dst + 1, (double)ssq);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+      }
+      if (issuer) bulk_wait_all();
+    }
+  } else if (warp >= 4 && STAGED) {
     // ======================= epilogue (smem-staged: TMA residual load, TMA store, GN quad sums) ==========
     // Per 32-column chunk: TMEM -> registers, + bias + time-embedding row + residual (landed in smem
     // by TMA one chunk ahead), scale, optional TF32 rounding; the finished 128x32 chunk is written to
@@ -510,11 +642,21 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   p.conv = d.conv; p.H = d.conv ? d.H : 1; p.W = d.conv ? d.W : 1; p.taps = d.taps;
   p.S = d.taps == 9 ? 3 : 1; p.pad = (d.taps == 9 && !d.valid_pad) ? 1 : 0;
   p.stride = d.stride == 2 ? 2 : 1;
-  p.epi_mode = d.epi_mode < 0 ? tc_gemm_default_epi_mode() : d.epi_mode;
-  p.qstats = p.epi_mode == 1 ? d.qstats : nullptr;
-  B200_REQUIRE(!(d.qstats && p.epi_mode != 1), "gemm_tc: fused GroupNorm sums need the staged epilogue");
+  {
+    // Swapped operands for 128-channel outputs: M=128,N=128 MMAs are shared-memory-bandwidth bound
+    // (8 KB of operand reads per 131k MACs); computing D^T = W X^T makes them M=128 (channels), N=256 (pixels).
+    static const bool allow_swap = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '0'); }();
+    const int req = d.epi_mode < 0 ? tc_gemm_default_epi_mode() : d.epi_mode;   // 0 direct, 1 staged, 2 auto
+    const long long Mtot = (long long)d.nimg * d.H * d.W;
+    const bool can_swap = allow_swap && d.conv && p.stride == 1 && d.N_total % 256 != 0 && (d.H * d.W) % 256 == 0 &&
+                          d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
+    p.swap = (can_swap && req != 0) ? 1 : 0;
+    p.epi_mode = req == 2 ? (p.swap ? 1 : 0) : req;
+    if (p.swap) pl->bn = 256;
+    p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
+  }
   p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
-  p.N_total = d.N_total; p.tiles_n = d.N_total / pl->bn;
+  p.N_total = d.N_total; p.tiles_n = p.swap ? d.N_total / 128 : d.N_total / pl->bn;
   p.a_batch_rows = d.a_batch_rows; p.w_batch_rows = d.w_batch_rows;
   p.epi = d.epi;
 
@@ -522,7 +664,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   if (d.conv) {
     const int HW = d.H * d.W;
     const long long M = (long long)d.nimg * HW;
-    p.nbatch = 1; p.M_per_batch = (int)M; p.tiles_m_per_batch = (int)((M + BM - 1) / BM);
+    p.nbatch = 1; p.M_per_batch = (int)M; p.tiles_m_per_batch = p.swap ? (int)(M / 256) : (int)((M + BM - 1) / BM);
     uint32_t box[4];
     if (HW >= BM) { box[1] = std::min(d.W, BM); box[2] = BM / box[1]; box[3] = 1; }
     else { box[1] = d.W; box[2] = d.H; box[3] = BM / HW; }
@@ -556,13 +698,13 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   {
     uint64_t dims[2] = {(uint64_t)d.K_total, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * 4};
-    uint32_t box[2] = {BKE, (uint32_t)pl->bn};
+    uint32_t box[2] = {BKE, (uint32_t)(p.swap ? 128 : pl->bn)};
     rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
     if (rc) { delete pl; return rc; }
   }
   if (p.epi_mode == 1) {
     const uint64_t out_rows = (uint64_t)p.nbatch * (uint64_t)p.M_per_batch;
-    uint32_t box[2] = {32, BM};
+    uint32_t box[2] = {32, (uint32_t)(p.swap ? 32 : BM)};
     {
       uint64_t dims[2] = {(uint64_t)d.N_total, out_rows};
       uint64_t str[1] = {(uint64_t)d.epi.ld_out * 4};
@@ -583,8 +725,16 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
+// B200_TC_EPILOGUE = direct | staged | auto (default).  auto: the smem-staged TMA epilogue where it measured
+// faster (the swapped-operand 128-channel convolutions), direct register->global stores with the deeper
+// operand ring elsewhere.  Returns 0 direct, 1 staged, 2 auto.
 int tc_gemm_default_epi_mode() {
-  static const int mode = [] { const char* v = getenv("B200_TC_EPILOGUE"); return (v && !strcmp(v, "direct")) ? 0 : 1; }();
+  static const int mode = [] {
+    const char* v = getenv("B200_TC_EPILOGUE");
+    if (v && !strcmp(v, "direct")) return 0;
+    if (v && !strcmp(v, "staged")) return 1;
+    return 2;
+  }();
   return mode;
 }
 
@@ -592,24 +742,27 @@ int tc_gemm_default_epi_mode() {
 static int tc_configure() {
   static bool configured = false;
   if (configured) return 0;
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 3>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 4>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 3, true>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 4, true>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4, false>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6, false>::TOTAL));
   configured = true;
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STAGED>
 static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, STAGED>;
   const int grid = (int)std::min<long long>(pl->prm.total_tiles, num_sms());
-  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL, st>>>(pl->prm);
+  gemm_tc_kernel<BN, STAGES, STAGED><<<grid, 256, L::TOTAL, st>>>(pl->prm);
   B200_CHECK_LAUNCH();
   return 0;
 }
 
 int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
   if (pl->prm.total_tiles == 0) return 0;
-  return pl->bn == 256 ? launch_impl<256, 3>(pl, st) : launch_impl<128, 4>(pl, st);
+  if (pl->prm.epi_mode == 1) return pl->bn == 256 ? launch_impl<256, 3, true>(pl, st) : launch_impl<128, 4, true>(pl, st);
+  return pl->bn == 256 ? launch_impl<256, 4, false>(pl, st) : launch_impl<128, 6, false>(pl, st);
 }
 
 }  // namespace b200

@@ -104,14 +104,16 @@ def test_native_pc_loop_matches_oracle_same_cuda_seed(dev, combo):
     sde, osde, eps = sde_lib.VPSDE(0.1, 20., N), SO.VP(0.1, 20., N), 1e-3
   pred = sampling.ReverseDiffusionPredictor if '_rd_' in combo else sampling.EulerMaruyamaPredictor
   corr = sampling.LangevinCorrector if combo.endswith('langevin') else sampling.NoneCorrector
+  snr = 0.16 if is_ve else 0.02      # the random-init VP model diverges to NaN under snr=0.16 Langevin steps (in the oracle too)
   torch.manual_seed(5)
   x0 = osde.prior_sampling(shape).to(dev)
   torch.cuda.manual_seed(77)
   ref, _ = SO.pc_sample(osde, _oracle_model(cfg, sd), shape, 'reverse_diffusion' if '_rd_' in combo else 'euler_maruyama',
-                        'langevin' if combo.endswith('langevin') else 'none', snr=0.16, n_steps=1, eps=eps,
+                        'langevin' if combo.endswith('langevin') else 'none', snr=snr, n_steps=1, eps=eps,
                         denoise=True, device=dev, x_init=x0)
+  assert torch.isfinite(ref).all(), 'oracle trajectory diverged: pick a tamer test configuration'
   off_ref = torch.cuda.default_generators[0].get_offset()
-  plan = _native_plan(model, sde, pred, corr, shape, dev, eps)
+  plan = _native_plan(model, sde, pred, corr, shape, dev, eps, snr=snr)
   torch.cuda.manual_seed(77)
   x, x_mean = plan.run(x0)
   assert torch.cuda.default_generators[0].get_offset() == off_ref     # same generator bookkeeping
