@@ -197,14 +197,15 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = tmem_empty + 2;                     // [4 epilogue warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); mbar_init(&res_full[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 8; ++a) mbar_init(&res_full[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -346,207 +347,231 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4 && STAGED && p.swap) {
-    // ======================= epilogue, swapped operands (BN == 256 instantiation only) ====================
-    // TMEM lane = output channel, column = pixel.  Per 32-pixel chunk the thread adds its channel's bias /
-    // time-embedding value and the residual, then scatters the 32 pixels of its channel into four
-    // [32 px][32 ch] 128-B-swizzled staging boxes (conflict free: a warp writes one 128-B row per pixel),
-    // stored by TMA.  GroupNorm quad sums: per-thread over the tile's 256 pixels, then across 4 lanes.
-    if constexpr (BN == 256 && STAGED) {
-      const int q = warp - 4;
-      const int t = q * 32 + lane;                              // channel within the 128-channel tile
-      const bool issuer = (threadIdx.x == 128);
-      const Epilogue& e = p.epi;
-      constexpr int NCH = 8;                                    // 256 pixels / 32
-      float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET);
-      float* res_stage = reinterpret_cast<float*>(smem + L::RES_OFFSET);
-      const bool has_res = e.residual != nullptr;
-      const long long my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-      const long long total_chunks = my_tiles * NCH;
-      auto chunk_origin = [&](long long g, int& row0, int& col0) {
-        const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
-        col0 = (int)(tile % p.tiles_n) * 128;
-        row0 = (int)(tile / p.tiles_n) * 256 + (int)(g % NCH) * 32;
-      };
-      auto load_res = [&](long long g) {
-        int row0, col0; chunk_origin(g, row0, col0);
-        float* dst = res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4);
-        mbar_expect_tx(&res_full[g & 1], L::EPI_TILE_BYTES);
+  } else if (warp >= 4 && STAGED) {
+    // ======================= epilogue (smem-staged, warp-private) =======================================
+    // Each of the four epilogue warps owns 32 TMEM lanes and works alone (no CTA-wide barrier): per
+    // 32-column chunk it pulls its 32x32 accumulator block TMEM -> registers (the next block's tcgen05.ld is
+    // already in flight), adds bias / time-embedding / residual (the residual block was landed in the warp's
+    // smem by TMA two chunks earlier), scales, optionally rounds to TF32, writes a 128-B-swizzled 4 KB staging
+    // block and hands it to one TMA bulk store (three staging blocks deep).  GroupNorm quad sums of the stored
+    // values are reduced across the warp with a halving butterfly (16 shuffles instead of 80) and accumulated in
+    // fp64 by 16 lanes in parallel.  Two block orientations:
+    //   normal : TMEM lane = output row (pixel), columns = channels; a lane writes 8 float4 of its row;
+    //   swap   : TMEM lane = output channel, columns = pixels (D^T = W X^T for 128-channel layers); a lane
+    //            scatters its channel's 32 pixels one word per staging row (a warp fills one 128-B row per pixel).
+    const int q = warp - 4;
+    const Epilogue& e = p.epi;
+    const bool swap = p.swap != 0;
+    const int NCH = swap ? 8 : BN / 32;                          // chunks per tile
+    constexpr int BLK = 32 * 32;                                 // floats per staging block
+    float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET) + q * 3 * BLK;   // [3][32 rows][32]
+    float* res_stage = reinterpret_cast<float*>(smem + L::RES_OFFSET) + q * 2 * BLK;   // [2][32 rows][32]
+    uint64_t* my_res_full = res_full + q * 2;
+    const bool has_res = e.residual != nullptr;
+    const long long my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_chunks = my_tiles * NCH;
+    // origin (first output row, first output column) of this warp's block of chunk g
+    auto block_origin = [&](long long g, int& row0, int& col0) {
+      const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
+      const int j = (int)(g % NCH);
+      if (swap) {
+        col0 = (int)(tile % p.tiles_n) * 128 + q * 32;
+        row0 = (int)(tile / p.tiles_n) * 256 + j * 32;
+      } else {
+        const long long mg = tile / p.tiles_n;
+        col0 = (int)(tile % p.tiles_n) * BN + j * 32;
+        row0 = (int)(mg / p.tiles_m_per_batch) * p.M_per_batch + (int)(mg % p.tiles_m_per_batch) * BM + q * 32;
+      }
+    };
+    auto load_res = [&](long long g) {                           // lane 0 only
+      int row0, col0; block_origin(g, row0, col0);
+      mbar_expect_tx(&my_res_full[g & 1], BLK * 4);
+      tma_load_2d(&p.tmRes, res_stage + (g & 1) * BLK, &my_res_full[g & 1], col0, row0);
+    };
+    auto issue_tmem_ld = [&](long long g, uint32_t (&v)[32]) {   // whole warp
+      const long long k = g / NCH;                               // local tile counter -> accumulator stage / phase
+      const int j = (int)(g % NCH);
+      const uint32_t acc = (uint32_t)(k & 1), ph = (uint32_t)((k >> 1) & 1);
+      if (j == 0) { mbar_wait(&tmem_full[acc], ph); tc_fence_after(); }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+    };
+    if (lane == 0 && has_res) { for (long long g = 0; g < 2 && g < total_chunks; ++g) load_res(g); }
+    float sw_sum = 0.f, sw_sq = 0.f;                             // swap mode: per-channel sums over the tile
+    auto process = [&](long long g, uint32_t (&v)[32]) {
+      const int j = (int)(g % NCH);
+      int row0, col0; block_origin(g, row0, col0);
+      if (lane == 0) bulk_wait_read<1>();                        // store g-2 drained -> staging block g%3 (last used by g-3) is free
+      __syncwarp();
+      if (has_res) mbar_wait(&my_res_full[g & 1], (uint32_t)((g >> 1) & 1));
+      const float* rs = res_stage + (g & 1) * BLK;
+      float* os = out_stage + (g % 3) * BLK;
+      if (!swap) {
+        const int r = lane, sw = r & 7;
+        const int m = row0 + r - (int)((blockIdx.x + (g / NCH) * gridDim.x) / p.tiles_n / p.tiles_m_per_batch) * p.M_per_batch;
+        const bool valid = m < p.M_per_batch;
+        const long long gm = (long long)row0 + r;
+        const int img = valid ? (int)(gm / e.rows_per_img) : 0;
+        const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+        const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + col0 : nullptr;
+        float st[16];
 #pragma unroll
-        for (int bx = 0; bx < 4; ++bx) tma_load_2d(&p.tmRes, dst + bx * 1024, &res_full[g & 1], col0 + bx * 32, row0);
-      };
-      if (issuer && has_res) { for (long long g = 0; g < 2 && g < total_chunks; ++g) load_res(g); }
-      // element (pixel i, channel t) of a chunk lives at: box q (1024 floats), row i (32 floats), 16-B chunk (lane>>2)^(i&7)
-      const int box_off = q * 1024 + (lane & 3);
-      const int ch16 = lane >> 2;
-      uint32_t acc = 0, acc_phase = 0;
-      int co = 0, img = 0; float bias_v = 0.f, row_v = 0.f, dv = 1.f, ssum = 0.f, ssq = 0.f;
-      for (long long g = 0; g < total_chunks; ++g) {
-        const int j = (int)(g % NCH);
-        int row0, col0; chunk_origin(g, row0, col0);
-        if (j == 0) {
-          co = col0 + t;
-          img = row0 / e.rows_per_img;                          // rows_per_img % 256 == 0: one image per tile
-          bias_v = e.bias ? __ldg(e.bias + co) : 0.f;
-          row_v = e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f;
-          dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
-          ssum = 0.f; ssq = 0.f;
-          mbar_wait(&tmem_full[acc], acc_phase);
-          tc_fence_after();
+        for (int c = 0; c < 8; ++c) {
+          float4 o = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                                 __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+          if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          if (has_res) { const float4 t = *reinterpret_cast<const float4*>(rs + r * 32 + ((c ^ sw) << 2)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
+          if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
+          if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+          *reinterpret_cast<float4*>(os + r * 32 + ((c ^ sw) << 2)) = o;
+          st[c] = valid ? (o.x + o.y) + (o.z + o.w) : 0.f;
+          st[8 + c] = valid ? (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w) : 0.f;
         }
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + j * 32, v);
-        if (has_res) mbar_wait(&res_full[g & 1], (uint32_t)((g >> 1) & 1));
-        const float* rs = res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4) + box_off;
-        float* os = out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4) + box_off;
+        if (p.qstats) {
+          // halving butterfly: after the steps below lane L holds the warp-wide (or half-warp-wide) total of
+          // entry idx(L) of st[16]; entries 0..7 = quad sums, 8..15 = quad sums of squares.
+          const bool halves = e.rows_per_img < 32;                // 16 rows per image: reduce the two half-warps separately
+          int idx = 0;
+          if (!halves) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool up = lane & 16;
+              const float send = up ? st[i] : st[i + 8];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+              st[i] = (up ? st[i + 8] : st[i]) + recv;
+            }
+            idx = (lane & 16) ? 8 : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool up = lane & 8;
+              const float send = up ? st[i] : st[i + 4];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+              st[i] = (up ? st[i + 4] : st[i]) + recv;
+            }
+            idx += (lane & 8) ? 4 : 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const bool up = lane & 4;
+              const float send = up ? st[i] : st[i + 2];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+              st[i] = (up ? st[i + 2] : st[i]) + recv;
+            }
+            idx += (lane & 4) ? 2 : 0;
+            {
+              const bool up = lane & 2;
+              const float send = up ? st[0] : st[1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+              st[0] = (up ? st[1] : st[0]) + recv;
+            }
+            idx += (lane & 2) ? 1 : 0;
+            st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool up = lane & 8;
+              const float send = up ? st[i] : st[i + 8];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+              st[i] = (up ? st[i + 8] : st[i]) + recv;
+            }
+            idx = (lane & 8) ? 8 : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool up = lane & 4;
+              const float send = up ? st[i] : st[i + 4];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+              st[i] = (up ? st[i + 4] : st[i]) + recv;
+            }
+            idx += (lane & 4) ? 4 : 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const bool up = lane & 2;
+              const float send = up ? st[i] : st[i + 2];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+              st[i] = (up ? st[i + 2] : st[i]) + recv;
+            }
+            idx += (lane & 2) ? 2 : 0;
+            {
+              const bool up = lane & 1;
+              const float send = up ? st[0] : st[1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+              st[0] = (up ? st[1] : st[0]) + recv;
+            }
+            idx += (lane & 1) ? 1 : 0;
+          }
+          // the image of the (half-)warp's rows: lane 0 (or lane 16) is its first row
+          const int img_w = __shfl_sync(0xffffffffu, img, halves ? (lane & 16) : 0);
+          const bool val_w = __shfl_sync(0xffffffffu, (int)valid, halves ? (lane & 16) : 0) != 0;
+          const bool writer = halves ? true : ((lane & 1) == 0);
+          if (writer && val_w && st[0] != 0.f) {
+            const int quad = idx & 7, which = idx >> 3;          // which: 0 = sum, 1 = sum of squares
+            atomicAdd(p.qstats + ((long long)img_w * (p.N_total >> 2) + (col0 >> 2) + quad) * 2 + which, (double)st[0]);
+          }
+        }
+      } else {
+        // swap: lane = channel col0 + lane, columns = 32 pixels row0..row0+31 (one image per tile)
+        const int co = col0 + lane, ch16 = lane >> 2, w4 = lane & 3;
+        const int img = row0 / e.rows_per_img;
+        const float bias_v = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
+        const float dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+        if (j == 0) { sw_sum = 0.f; sw_sq = 0.f; }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int off = i * 32 + ((ch16 ^ (i & 7)) << 2);
-          float o = __uint_as_float(v[i]) + bias_v + row_v;
+          const int off = i * 32 + ((ch16 ^ (i & 7)) << 2) + w4;
+          float o = __uint_as_float(v[i]) + bias_v;
           if (has_res) o += rs[off];
           o *= e.scale;
           if (e.per_img_div) o /= dv;
           if (e.round_tf32) o = round_tf32(o);
           os[off] = o;
-          ssum += o; ssq += o * o;
+          sw_sum += o; sw_sq += o * o;
         }
-        fence_async_smem();
-        if (issuer) bulk_wait_read<1>();
-        epi_barrier();
-        if (issuer) {
-          const float* src = out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4);
-#pragma unroll
-          for (int bx = 0; bx < 4; ++bx) tma_store_2d(&p.tmOut, src + bx * 1024, col0 + bx * 32, row0);
-          bulk_commit();
-          if (has_res && g + 2 < total_chunks) load_res(g + 2);
-        }
-        if (j == NCH - 1) {
-          if (p.qstats) {
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
-            if ((lane & 3) == 0) {
-              double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (co >> 2)) * 2;
-              atomicAdd(dst, (double)ssum); atomicAdd(dst + 1, (double)ssq);
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          acc ^= 1; if (acc == 0) acc_phase ^= 1;
-        }
-      }
-      if (issuer) bulk_wait_all();
-    }
-  } else if (warp >= 4 && STAGED) {
-    // ======================= epilogue (smem-staged: TMA residual load, TMA store, GN quad sums) ==========
-    // Per 32-column chunk: TMEM -> registers, + bias + time-embedding row + residual (landed in smem
-    // by TMA one chunk ahead), scale, optional TF32 rounding; the finished 128x32 chunk is written to
-    // a 128-B-swizzled staging tile and stored with one TMA bulk store (full 128-B lines, asynchronous),
-    // three staging tiles deep.  Optionally the per-(image, 4-channel quad) sum / sum of squares of the
-    // stored values are reduced across the warp's rows and accumulated in fp64: the next GroupNorm
-    // needs no pass over the tensor to get its statistics.
-    const int q = warp - 4;
-    const int r = q * 32 + lane;
-    const bool issuer = (threadIdx.x == 128);
-    const Epilogue& e = p.epi;
-    constexpr int NCH = BN / 32;
-    float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET);
-    float* res_stage = reinterpret_cast<float*>(smem + L::RES_OFFSET);
-    const bool has_res = e.residual != nullptr;
-    const long long my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long total_chunks = my_tiles * NCH;
-    auto chunk_origin = [&](long long g, int& row0, int& col0) {
-      const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
-      const int nt = (int)(tile % p.tiles_n);
-      const long long mg = tile / p.tiles_n;
-      row0 = (int)(mg / p.tiles_m_per_batch) * p.M_per_batch + (int)(mg % p.tiles_m_per_batch) * BM;
-      col0 = nt * BN + (int)(g % NCH) * 32;
-    };
-    if (issuer && has_res) {
-      for (long long g = 0; g < 2 && g < total_chunks; ++g) {
-        int row0, col0; chunk_origin(g, row0, col0);
-        mbar_expect_tx(&res_full[g & 1], L::EPI_TILE_BYTES);
-        tma_load_2d(&p.tmRes, res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4), &res_full[g & 1], col0, row0);
-      }
-    }
-    const int sw = r & 7;                                 // 128-B swizzle phase of this thread's row
-    uint32_t acc = 0, acc_phase = 0;
-    int m = 0, img = 0; bool valid = false; long long gm = 0; float dv = 1.f;
-    for (long long g = 0; g < total_chunks; ++g) {
-      const int j = (int)(g % NCH);
-      int row0, col0; chunk_origin(g, row0, col0);
-      if (j == 0) {
-        const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
-        const long long mg = tile / p.tiles_n;
-        m = (int)(mg % p.tiles_m_per_batch) * BM + r;
-        valid = m < p.M_per_batch;
-        gm = (long long)(mg / p.tiles_m_per_batch) * p.M_per_batch + m;
-        img = valid ? (int)(gm / e.rows_per_img) : 0;
-        dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-      }
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
-      const float* rs = res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4) + r * 32;
-      if (has_res) mbar_wait(&res_full[g & 1], (uint32_t)((g >> 1) & 1));
-      float* os = out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4) + r * 32;
-      const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + col0 : nullptr;
-      float qs[8], qq[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 o = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
-                               __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
-        if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-        if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-        if (has_res) { const float4 t = *reinterpret_cast<const float4*>(rs + ((c ^ sw) << 2)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-        o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-        if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
-        if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        *reinterpret_cast<float4*>(os + ((c ^ sw) << 2)) = o;
-        if (p.qstats) {
-          qs[c] = valid ? (o.x + o.y) + (o.z + o.w) : 0.f;
-          qq[c] = valid ? (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w) : 0.f;
-        }
-      }
-      if (p.qstats) {
-        // rows of one warp belong to one image (rows_per_img % 32 == 0) or to two (rows_per_img == 16)
-        const bool halves = e.rows_per_img < 32;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            if (o == 16 && halves) break;
-            qs[c] += __shfl_xor_sync(0xffffffffu, qs[c], o);
-            qq[c] += __shfl_xor_sync(0xffffffffu, qq[c], o);
+        if (p.qstats && j == NCH - 1) {
+          sw_sum += __shfl_xor_sync(0xffffffffu, sw_sum, 1); sw_sq += __shfl_xor_sync(0xffffffffu, sw_sq, 1);
+          sw_sum += __shfl_xor_sync(0xffffffffu, sw_sum, 2); sw_sq += __shfl_xor_sync(0xffffffffu, sw_sq, 2);
+          if ((lane & 3) == 0) {
+            double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (co >> 2)) * 2;
+            atomicAdd(dst, (double)sw_sum); atomicAdd(dst + 1, (double)sw_sq);
           }
         }
-        if ((lane == 0 || (halves && lane == 16)) && valid) {
-          double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (col0 >> 2)) * 2;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { atomicAdd(dst + 2 * c, (double)qs[c]); atomicAdd(dst + 2 * c + 1, (double)qq[c]); }
-        }
       }
-      fence_async_smem();                                   // generic-proxy smem writes -> visible to the TMA engine
-      if (issuer) bulk_wait_read<1>();                      // store g-2 has drained: staging tile (g+1)%3 is free
-      epi_barrier();
-      if (issuer) {
-        tma_store_2d(&p.tmOut, out_stage + (g % 3) * (L::EPI_TILE_BYTES / 4), col0, row0);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&p.tmOut, os, col0, row0);
         bulk_commit();
-        if (has_res && g + 2 < total_chunks) {
-          int r2, c2; chunk_origin(g + 2, r2, c2);
-          mbar_expect_tx(&res_full[g & 1], L::EPI_TILE_BYTES);
-          tma_load_2d(&p.tmRes, res_stage + (g & 1) * (L::EPI_TILE_BYTES / 4), &res_full[g & 1], c2, r2);
-        }
+        if (has_res && g + 2 < total_chunks) load_res(g + 2);
       }
-      if (j == NCH - 1) {
+      if (j == NCH - 1) {                                        // this warp has drained its lanes of the accumulator stage
+        const long long k = g / NCH;
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        if (lane == 0) mbar_arrive(&tmem_empty[k & 1]);
+      }
+    };
+    // software pipeline over chunks: the tcgen05.ld of chunk g+1 is in flight while chunk g is processed
+    uint32_t va[32], vb[32];
+    if (total_chunks > 0) issue_tmem_ld(0, va);
+    for (long long g = 0; g < total_chunks; g += 2) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (g + 1 < total_chunks) issue_tmem_ld(g + 1, vb);
+      process(g, va);
+      if (g + 1 < total_chunks) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (g + 2 < total_chunks) issue_tmem_ld(g + 2, va);
+        process(g + 1, vb);
       }
     }
-    if (issuer) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -651,7 +676,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     const bool can_swap = allow_swap && d.conv && p.stride == 1 && d.N_total % 256 != 0 && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
     p.swap = (can_swap && req != 0) ? 1 : 0;
-    p.epi_mode = req == 2 ? (p.swap ? 1 : 0) : req;
+    p.epi_mode = req == 0 ? 0 : 1;                  // auto == staged (measured: 132.8 vs 138 ms/step, profiles/r01_c3, r01_c4)
     if (p.swap) pl->bn = 256;
     p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
   }
@@ -704,7 +729,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   }
   if (p.epi_mode == 1) {
     const uint64_t out_rows = (uint64_t)p.nbatch * (uint64_t)p.M_per_batch;
-    uint32_t box[2] = {32, (uint32_t)(p.swap ? 32 : BM)};
+    uint32_t box[2] = {32, 32};                              // one epilogue warp's 32x32 block
     {
       uint64_t dims[2] = {(uint64_t)d.N_total, out_rows};
       uint64_t str[1] = {(uint64_t)d.epi.ld_out * 4};
