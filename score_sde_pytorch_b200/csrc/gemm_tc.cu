@@ -162,26 +162,81 @@ struct SmemLayout {
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
 
-// GroupNorm quad sums of one 32-column chunk held one row per lane: reduce over the warp's rows
-// (one image per warp when rows_per_img % 32 == 0, two when rows_per_img == 16) and accumulate in fp64.
-__device__ __forceinline__ void direct_stats(const TcParams& p, const Epilogue& e, float (&qs)[8], float (&qq)[8],
-                                             int img, int n0, int lane) {
+// GroupNorm quad sums of one 32-column chunk held one row per lane.  st[0..7] = per-quad sums of the lane's
+// row, st[8..15] = per-quad sums of squares (zeros for rows past the end).  Halving butterfly: each exchange
+// sends half of the live entries to the partner lane and adds the partner's other half, so after four
+// exchanges a lane holds ONE entry summed over 16 lanes (16 shuffles instead of 80); a final exchange
+// completes the 32-row sum.  rows_per_img == 16 (4x4 images): the two half-warps are different images and are
+// reduced separately.  The entry totals are then accumulated in fp64 by 16 (or 32) lanes in parallel.
+__device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilogue& e, float (&st)[16], int img,
+                                                  bool valid, int col0, int lane) {
   const bool halves = e.rows_per_img < 32;
+  int idx = 0;
+  if (!halves) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      if (o == 16 && halves) break;
-      qs[c] += __shfl_xor_sync(0xffffffffu, qs[c], o);
-      qq[c] += __shfl_xor_sync(0xffffffffu, qq[c], o);
+    for (int i = 0; i < 8; ++i) {
+      const bool up = lane & 16;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[i] : st[i + 8], 16);
+      st[i] = (up ? st[i + 8] : st[i]) + recv;
     }
+    idx = (lane & 16) ? 8 : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool up = lane & 8;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[i] : st[i + 4], 8);
+      st[i] = (up ? st[i + 4] : st[i]) + recv;
+    }
+    idx += (lane & 8) ? 4 : 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool up = lane & 4;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[i] : st[i + 2], 4);
+      st[i] = (up ? st[i + 2] : st[i]) + recv;
+    }
+    idx += (lane & 4) ? 2 : 0;
+    {
+      const bool up = lane & 2;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[0] : st[1], 2);
+      st[0] = (up ? st[1] : st[0]) + recv;
+    }
+    idx += (lane & 2) ? 1 : 0;
+    st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool up = lane & 8;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[i] : st[i + 8], 8);
+      st[i] = (up ? st[i + 8] : st[i]) + recv;
+    }
+    idx = (lane & 8) ? 8 : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool up = lane & 4;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[i] : st[i + 4], 4);
+      st[i] = (up ? st[i + 4] : st[i]) + recv;
+    }
+    idx += (lane & 4) ? 4 : 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool up = lane & 2;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[i] : st[i + 2], 2);
+      st[i] = (up ? st[i + 2] : st[i]) + recv;
+    }
+    idx += (lane & 2) ? 2 : 0;
+    {
+      const bool up = lane & 1;
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? st[0] : st[1], 1);
+      st[0] = (up ? st[1] : st[0]) + recv;
+    }
+    idx += (lane & 1) ? 1 : 0;
   }
-  if (lane == 0 || (halves && lane == 16)) {
-    double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (n0 >> 2)) * 2;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      if (qs[c] != 0.f || qq[c] != 0.f) { atomicAdd(dst + 2 * c, (double)qs[c]); atomicAdd(dst + 2 * c + 1, (double)qq[c]); }
-    }
+  // image / validity of the (half-)warp's rows: taken from its first row
+  const int img_w = __shfl_sync(0xffffffffu, img, halves ? (lane & 16) : 0);
+  const bool val_w = __shfl_sync(0xffffffffu, (int)valid, halves ? (lane & 16) : 0) != 0;
+  const bool writer = halves ? true : ((lane & 1) == 0);
+  if (writer && val_w && st[0] != 0.f) {
+    const int quad = idx & 7, which = idx >> 3;          // which: 0 = sum, 1 = sum of squares
+    atomicAdd(p.qstats + ((long long)img_w * (p.N_total >> 2) + (col0 >> 2) + quad) * 2 + which, (double)st[0]);
   }
 }
 
@@ -320,7 +375,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
         const int n0 = nt * BN + j * 32;
-        float qs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, qq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float st[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st[i] = 0.f;
         if (valid) {
           float* dst = e.out + gm * e.ld_out + n0;
           const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
@@ -336,11 +393,11 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
             if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
             *reinterpret_cast<float4*>(dst + c) = o;
-            qs[c >> 2] = (o.x + o.y) + (o.z + o.w);
-            qq[c >> 2] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+            st[c >> 2] = (o.x + o.y) + (o.z + o.w);
+            st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
           }
         }
-        if (p.qstats) direct_stats(p, e, qs, qq, img, n0, lane);   // whole warp, convergent
+        if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);   // whole warp, convergent
       }
       tc_fence_before();
       __syncwarp();
@@ -437,86 +494,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           st[c] = valid ? (o.x + o.y) + (o.z + o.w) : 0.f;
           st[8 + c] = valid ? (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w) : 0.f;
         }
-        if (p.qstats) {
-          // halving butterfly: after the steps below lane L holds the warp-wide (or half-warp-wide) total of
-          // entry idx(L) of st[16]; entries 0..7 = quad sums, 8..15 = quad sums of squares.
-          const bool halves = e.rows_per_img < 32;                // 16 rows per image: reduce the two half-warps separately
-          int idx = 0;
-          if (!halves) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool up = lane & 16;
-              const float send = up ? st[i] : st[i + 8];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-              st[i] = (up ? st[i + 8] : st[i]) + recv;
-            }
-            idx = (lane & 16) ? 8 : 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bool up = lane & 8;
-              const float send = up ? st[i] : st[i + 4];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-              st[i] = (up ? st[i + 4] : st[i]) + recv;
-            }
-            idx += (lane & 8) ? 4 : 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const bool up = lane & 4;
-              const float send = up ? st[i] : st[i + 2];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-              st[i] = (up ? st[i + 2] : st[i]) + recv;
-            }
-            idx += (lane & 4) ? 2 : 0;
-            {
-              const bool up = lane & 2;
-              const float send = up ? st[0] : st[1];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-              st[0] = (up ? st[1] : st[0]) + recv;
-            }
-            idx += (lane & 2) ? 1 : 0;
-            st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool up = lane & 8;
-              const float send = up ? st[i] : st[i + 8];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-              st[i] = (up ? st[i + 8] : st[i]) + recv;
-            }
-            idx = (lane & 8) ? 8 : 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bool up = lane & 4;
-              const float send = up ? st[i] : st[i + 4];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-              st[i] = (up ? st[i + 4] : st[i]) + recv;
-            }
-            idx += (lane & 4) ? 4 : 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const bool up = lane & 2;
-              const float send = up ? st[i] : st[i + 2];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-              st[i] = (up ? st[i + 2] : st[i]) + recv;
-            }
-            idx += (lane & 2) ? 2 : 0;
-            {
-              const bool up = lane & 1;
-              const float send = up ? st[0] : st[1];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-              st[0] = (up ? st[1] : st[0]) + recv;
-            }
-            idx += (lane & 1) ? 1 : 0;
-          }
-          // the image of the (half-)warp's rows: lane 0 (or lane 16) is its first row
-          const int img_w = __shfl_sync(0xffffffffu, img, halves ? (lane & 16) : 0);
-          const bool val_w = __shfl_sync(0xffffffffu, (int)valid, halves ? (lane & 16) : 0) != 0;
-          const bool writer = halves ? true : ((lane & 1) == 0);
-          if (writer && val_w && st[0] != 0.f) {
-            const int quad = idx & 7, which = idx >> 3;          // which: 0 = sum, 1 = sum of squares
-            atomicAdd(p.qstats + ((long long)img_w * (p.N_total >> 2) + (col0 >> 2) + quad) * 2 + which, (double)st[0]);
-          }
-        }
+        if (p.qstats) quad_stats_commit(p, e, st, img, valid, col0, lane);
       } else {
         // swap: lane = channel col0 + lane, columns = 32 pixels row0..row0+31 (one image per tile)
         const int co = col0 + lane, ch16 = lane >> 2, w4 = lane & 3;
@@ -582,6 +560,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   }
 }
 
+#include "gemm_tc2.cuh"
+
 // ---------------------------------------------------------------------------
 // Host side: tensor maps, plan, launch
 // ---------------------------------------------------------------------------
@@ -626,6 +606,7 @@ int num_sms() {
 struct TcGemmPlan {
   TcParams prm;
   int bn;
+  bool two_cta;
 };
 
 static int tc_configure();
@@ -675,10 +656,19 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     const long long Mtot = (long long)d.nimg * d.H * d.W;
     const bool can_swap = allow_swap && d.conv && p.stride == 1 && d.N_total % 256 != 0 && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
-    p.swap = (can_swap && req != 0) ? 1 : 0;
-    p.epi_mode = req == 0 ? 0 : 1;                  // auto == staged (measured: 132.8 vs 138 ms/step, profiles/r01_c3, r01_c4)
+    // auto (default): direct stores with the deepest operand ring.  Measured on the headline step
+    // (profiles/r01_*): direct 4/6-stage >= smem-staged TMA-store variants for every launch shape but the
+    // 128-channel residual convs, within box-to-box noise overall; B200_TC_EPILOGUE=staged selects the staged
+    // path (and the swapped-operand mode for 128-channel convs) for A/B runs.
+    p.swap = (can_swap && req == 1) ? 1 : 0;
+    p.epi_mode = req == 1 ? 1 : 0;
     if (p.swap) pl->bn = 256;
     p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
+    // CTA pairs (cta_group::2) for 256-column tiles: B200_TC_2CTA=1 opts in (0 = off, default until validated per round)
+    static const int two_cta_env = [] { const char* v = getenv("B200_TC_2CTA"); return v ? atoi(v) : 0; }();
+    const int tmb = d.conv ? 1 : (d.M_per_batch + BM - 1) / BM;
+    pl->two_cta = two_cta_env && !p.swap && d.N_total % 256 == 0 && (d.conv || d.nbatch == 1 || tmb % 2 == 0);
+    if (pl->two_cta) p.epi_mode = 0;
   }
   p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
   p.N_total = d.N_total; p.tiles_n = p.swap ? d.N_total / 128 : d.N_total / pl->bn;
@@ -723,7 +713,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   {
     uint64_t dims[2] = {(uint64_t)d.K_total, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * 4};
-    uint32_t box[2] = {BKE, (uint32_t)(p.swap ? 128 : pl->bn)};
+    uint32_t box[2] = {BKE, (uint32_t)((p.swap || pl->two_cta) ? 128 : pl->bn)};
     rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
     if (rc) { delete pl; return rc; }
   }
@@ -771,6 +761,7 @@ static int tc_configure() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 4, true>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4, false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6, false>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<6>::TOTAL));
   configured = true;
   return 0;
 }
@@ -786,6 +777,14 @@ static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
 
 int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
   if (pl->prm.total_tiles == 0) return 0;
+  if (pl->two_cta) {
+    const TcParams& q = pl->prm;
+    const long long pairs = (((long long)q.nbatch * q.tiles_m_per_batch + 1) / 2) * q.tiles_n;
+    const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
+    gemm_tc2_kernel<6><<<grid, 256, Smem2<6>::TOTAL, st>>>(pl->prm);
+    B200_CHECK_LAUNCH();
+    return 0;
+  }
   if (pl->prm.epi_mode == 1) return pl->bn == 256 ? launch_impl<256, 3, true>(pl, st) : launch_impl<128, 4, true>(pl, st);
   return pl->bn == 256 ? launch_impl<256, 4, false>(pl, st) : launch_impl<128, 6, false>(pl, st);
 }

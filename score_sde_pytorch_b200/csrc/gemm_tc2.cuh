@@ -1,0 +1,225 @@
+// Two-CTA (cta_group::2) variant of the tcgen05 implicit GEMM: a cluster of two CTAs on one TPC computes a
+// 256-row x 256-column output tile.  Included by gemm_tc.cu inside its anonymous namespace (it reuses the PTX
+// wrappers, TcParams, descriptors and the GroupNorm-sum helper defined there).
+//
+// Why: with one CTA per tile every K step writes 48 KB into shared memory (TMA) and reads 48 KB back (UMMA)
+// per 512 tensor-pipe cycles = 192 B/clk against the SM's ~128 B/clk shared-memory port, which caps the
+// tensor pipe near 67 % (measured 70 %, profiles/r01_*).  In a CTA pair each CTA stages its own 128 rows of A
+// and only HALF of the W tile (128 of the 256 output channels); the pair's tensor cores share the two W halves,
+// so a CTA writes 32 KB and reads 32 KB per K step = 128 B/clk.
+//
+// Roles per CTA (256 threads): warp 0 lane 0 TMA producer (both CTAs; transaction bytes are accounted on the
+// leader's `full` barrier), warp 1 lane 0 of the LEADER issues tcgen05.mma.cta_group::2 for the pair and
+// multicasts its commits to both CTAs' `empty` / `tmem_full` barriers, warp 2 allocates TMEM (cta_group::2),
+// warps 4..7 of each CTA drain their own 128 TMEM lanes (direct 128-bit stores, fused bias / time-embedding /
+// residual / scale / TF32 rounding / GroupNorm quad sums) and release the accumulator stage on the leader's
+// `tmem_empty` barrier (8 arrivals).
+
+template <int STAGES>
+struct Smem2 {
+  static constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES;          // A rows (16 KB) + this CTA's half of W (16 KB)
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* tm, void* dst, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* tm, void* dst, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit: arrive (once) on the barrier at this shared::cta offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  using L = Smem2<STAGES>;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;                                     // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // full: one arrive per CTA
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }      // empty: 4 warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kiters = (p.kchunks1 + p.kchunks2) * p.taps;
+  const int HW = p.H * p.W;
+  const long long tiles_m_total = (long long)p.nbatch * p.tiles_m_per_batch;
+  const long long pairs_m = (tiles_m_total + 1) / 2;
+  const long long total_pairs = pairs_m * p.tiles_n;
+  const long long cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    uint32_t stage = 0, phase = 0;
+    for (long long pair = cid; pair < total_pairs; pair += nclusters) {
+      const int nt = (int)(pair % p.tiles_n);
+      const long long mg = (pair / p.tiles_n) * 2 + rank;      // this CTA's 128-row tile (may be one past the end)
+      const int b = (int)(mg / p.tiles_m_per_batch);
+      const int mt = (int)(mg % p.tiles_m_per_batch);
+      int img0 = 0, h0 = 0, w0 = 0;
+      if (p.conv) {
+        const long long p0 = (long long)mt * BM;
+        img0 = (int)(p0 / HW);
+        const int rem = (int)(p0 % HW);
+        h0 = rem / p.W; w0 = rem % p.W;
+        if (mg >= tiles_m_total) img0 = 1 << 28;               // fully out of bounds -> TMA zero fill
+      }
+      const int arow0 = (mg >= tiles_m_total) ? (1 << 30) : b * p.a_batch_rows + mt * BM;
+      const int bsh = (int)((pair / p.tiles_n) * 2 / p.tiles_m_per_batch);   // batch of the pair (both CTAs share it)
+      const int wrow0 = bsh * p.w_batch_rows + nt * BN + (int)rank * 128;     // this CTA's half of the W tile
+      for (int src = 0; src < 2; ++src) {
+        const int nch = src ? p.kchunks2 : p.kchunks1;
+        if (nch == 0) continue;
+        const CUtensorMap* tmA = src ? &p.tmA2 : &p.tmA1;
+        const int wcol0 = src ? p.C1 : 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);            // own smem slot released by the pair's MMA commit
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            const uint32_t lead_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);     // bytes of BOTH CTAs land on this barrier
+            else mbar_arrive_cluster(lead_full);
+            if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
+            else tma2_load_4d(tmA, sa, lead_full, kc * BKE, arow0, 0, 0);
+            tma2_load_2d(&p.tmW, sb, lead_full, wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ======================= MMA issuer (leader CTA, for the pair) =======================
+    // instruction: M = 256 (128 rows per CTA), N = 256, K = 8 tf32; D fp32 in each CTA's own TMEM
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (long long pair = cid; pair < total_pairs; pair += nclusters) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa);
+        const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKE / UMMA_K; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        umma2_commit_mc(&empty_bar[stage]);                     // frees the slot in both CTAs
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma2_commit_mc(&tmem_full[acc]);                         // accumulator ready in both CTAs
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue (both CTAs, own 128 rows) =======================
+    const int q = warp - 4;
+    const int r = q * 32 + lane;
+    const Epilogue& e = p.epi;
+    uint32_t acc = 0, acc_phase = 0;
+    for (long long pair = cid; pair < total_pairs; pair += nclusters) {
+      const int nt = (int)(pair % p.tiles_n);
+      const long long mg = (pair / p.tiles_n) * 2 + rank;
+      const int b = (int)(mg / p.tiles_m_per_batch);
+      const int mt = (int)(mg % p.tiles_m_per_batch);
+      const int m = mt * BM + r;
+      const bool valid = (mg < tiles_m_total) && (m < p.M_per_batch);
+      const long long gm = (long long)b * p.M_per_batch + m;
+      const int img = valid ? (int)(gm / e.rows_per_img) : 0;
+      const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
+        const int n0 = nt * BN + j * 32;
+        float st[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st[i] = 0.f;
+        if (valid) {
+          float* dst = e.out + gm * e.ld_out + n0;
+          const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
+          const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                   __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
+            if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
+            if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            *reinterpret_cast<float4*>(dst + c) = o;
+            st[c >> 2] = (o.x + o.y) + (o.z + o.w);
+            st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          }
+        }
+        if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));   // leader's barrier, from either CTA
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peer's smem / barriers / TMEM stay valid until both are done
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}

@@ -97,14 +97,14 @@ def test_native_pc_loop_matches_oracle_same_cuda_seed(dev, combo):
   model = seeded_model(cfg, precision='fp32').to(dev)
   sd = {k: v.to(dev) for k, v in model.state_dict().items()}
   shape = (4, 3, 16, 16)
-  N = 12
+  N = 12 if is_ve else 30
   if is_ve:
     sde, osde, eps = sde_lib.VESDE(0.01, 50, N), SO.VE(0.01, 50, N), 1e-5
   else:
     sde, osde, eps = sde_lib.VPSDE(0.1, 20., N), SO.VP(0.1, 20., N), 1e-3
   pred = sampling.ReverseDiffusionPredictor if '_rd_' in combo else sampling.EulerMaruyamaPredictor
   corr = sampling.LangevinCorrector if combo.endswith('langevin') else sampling.NoneCorrector
-  snr = 0.16 if is_ve else 0.02      # the random-init VP model diverges to NaN under snr=0.16 Langevin steps (in the oracle too)
+  snr = 0.16 if is_ve else 0.01      # the random-init VP model diverges under larger Langevin steps (in the oracle too)
   torch.manual_seed(5)
   x0 = osde.prior_sampling(shape).to(dev)
   torch.cuda.manual_seed(77)
