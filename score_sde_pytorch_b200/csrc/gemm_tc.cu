@@ -244,7 +244,7 @@ __device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilo
 // Kernel
 // ---------------------------------------------------------------------------
 template <int BN, int STAGES, bool STAGED>
-__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using L = SmemLayout<BN, STAGES, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    // one arrival per epilogue warp: 4 (staged, 256 threads) or 8 (direct, 384 threads: two warps per TMEM lane quarter)
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], (blockDim.x >> 5) - 4); }
     for (int a = 0; a < 8; ++a) mbar_init(&res_full[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -353,8 +354,11 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4 && !STAGED) {
-    // ======================= epilogue (direct stores; validation / fallback path) =======================
-    const int q = warp - 4;                    // TMEM lane quarter owned by this warp
+    // ======================= epilogue (direct stores) =======================
+    // Eight warps: warp w may touch TMEM lanes 32*(w%4).., so warps 4..7 and 8..11 pair up on each lane quarter
+    // and split the tile's columns — twice the loads/stores in flight for the output-bound (small-K) launches.
+    const int q = (warp - 4) & 3;              // TMEM lane quarter owned by this warp
+    const int half = (warp - 4) >> 2;          // which half of the tile's columns
     const int r = q * 32 + lane;               // row of the tile held by this thread
     const Epilogue& e = p.epi;
     uint32_t acc = 0, acc_phase = 0;
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
         const int n0 = nt * BN + j * 32;
@@ -770,7 +774,7 @@ template <int BN, int STAGES, bool STAGED>
 static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, STAGED>;
   const int grid = (int)std::min<long long>(pl->prm.total_tiles, num_sms());
-  gemm_tc_kernel<BN, STAGES, STAGED><<<grid, 256, L::TOTAL, st>>>(pl->prm);
+  gemm_tc_kernel<BN, STAGES, STAGED><<<grid, STAGED ? 256 : 384, L::TOTAL, st>>>(pl->prm);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -781,7 +785,7 @@ int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
     const TcParams& q = pl->prm;
     const long long pairs = (((long long)q.nbatch * q.tiles_m_per_batch + 1) / 2) * q.tiles_n;
     const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
-    gemm_tc2_kernel<6><<<grid, 256, Smem2<6>::TOTAL, st>>>(pl->prm);
+    gemm_tc2_kernel<6><<<grid, 384, Smem2<6>::TOTAL, st>>>(pl->prm);
     B200_CHECK_LAUNCH();
     return 0;
   }

@@ -11,9 +11,9 @@
 // Roles per CTA (256 threads): warp 0 lane 0 TMA producer (both CTAs; transaction bytes are accounted on the
 // leader's `full` barrier), warp 1 lane 0 of the LEADER issues tcgen05.mma.cta_group::2 for the pair and
 // multicasts its commits to both CTAs' `empty` / `tmem_full` barriers, warp 2 allocates TMEM (cta_group::2),
-// warps 4..7 of each CTA drain their own 128 TMEM lanes (direct 128-bit stores, fused bias / time-embedding /
+// warps 4..11 of each CTA drain their own 128 TMEM lanes (direct 128-bit stores, fused bias / time-embedding /
 // residual / scale / TF32 rounding / GroupNorm quad sums) and release the accumulator stage on the leader's
-// `tmem_empty` barrier (8 arrivals).
+// `tmem_empty` barrier (16 arrivals).
 
 template <int STAGES>
 struct Smem2 {
@@ -32,8 +32,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
 }
+// Remote arrive.  NOT `.release.cluster`: that form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive
+// (measured: ~1600 cycles per K step in the peer's producer, halving the kernel's throughput — profiles/r01_c7).
+// The arrive only has to count; the data it guards is delivered by TMA complete_tx on the same barrier.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* tm, void* dst, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -59,7 +62,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
 }
 
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   using L = Smem2<STAGES>;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -76,7 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm_tc2_ker
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // full: one arrive per CTA
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }      // empty: 4 warps x 2 CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }     // empty: 8 warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -129,10 +132,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm_tc2_ker
             uint8_t* sb = sa + A_STAGE_BYTES;
             const uint32_t lead_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);     // bytes of BOTH CTAs land on this barrier
-            else mbar_arrive_cluster(lead_full);
             if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
             else tma2_load_4d(tmA, sa, lead_full, kc * BKE, arow0, 0, 0);
             tma2_load_2d(&p.tmW, sb, lead_full, wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            if (!leader) mbar_arrive_cluster(lead_full);                          // second of the barrier's two arrivals
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -163,7 +166,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm_tc2_ker
     }
   } else if (warp >= 4) {
     // ======================= epilogue (both CTAs, own 128 rows) =======================
-    const int q = warp - 4;
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;   // two warps per TMEM lane quarter, half the columns each
     const int r = q * 32 + lane;
     const Epilogue& e = p.epi;
     uint32_t acc = 0, acc_phase = 0;
@@ -180,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm_tc2_ker
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
         const int n0 = nt * BN + j * 32;

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/conv_isolated_$1.log; rm -f $L
+for args in "--c1 256 --cout 256 --hw 16" "--c1 256 --cout 256 --hw 16 --residual" "--c1 512 --cout 256 --hw 16" "--c1 256 --cout 256 --hw 8" "--c1 256 --cout 256 --hw 4" "--c1 256 --cout 256 --hw 32" "--c1 256 --cout 256 --hw 16 --k 1"; do
+  python tools/ncu_conv.py $args >> $L 2>&1
+  B200_TC_2CTA=1 python tools/ncu_conv.py $args >> $L 2>&1
+done
+cat $L
