@@ -292,6 +292,52 @@ __global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict_
   *reinterpret_cast<float4*>(y + (((long long)n * p.out_h + oy) * p.out_w + ox) * p.minor + cm) = acc;
 }
 
+// 2x upsampling (up=2, pad0=2, 4x4 FIR), one thread per INPUT pixel quad: the 3x3 input neighbourhood is loaded
+// once (9 float4) and produces the 2x2 output block (4 float4), 2.25 loads per output instead of 4.
+//   out[2i+ay][2j+ax] = sum over the two live taps per axis:  ay=0: (a=0, iy=i-1), (a=2, iy=i);  ay=1: (a=1, iy=i), (a=3, iy=i+1)
+__global__ void __launch_bounds__(256) fir4_up2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const FirParams p) {
+  const int mv = p.minor >> 2;
+  const long long total = (long long)p.major * p.in_h * p.in_w * mv;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cm = (int)(idx % mv) << 2;
+  long long t = idx / mv;
+  const int j = (int)(t % p.in_w); t /= p.in_w;
+  const int i = (int)(t % p.in_h);
+  const int n = (int)(t / p.in_h);
+  const float* xin = x + (long long)n * p.in_h * p.in_w * p.minor + cm;
+  float4 v[3][3];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int iy = i + dy - 1, ix = j + dx - 1;
+      v[dy][dx] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w)
+                      ? __ldg(reinterpret_cast<const float4*>(xin + ((long long)iy * p.in_w + ix) * p.minor))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  float* yout = y + (long long)n * p.out_h * p.out_w * p.minor + cm;
+#pragma unroll
+  for (int ay = 0; ay < 2; ++ay)
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 2; ++tx) {
+          const int a = ay + 2 * ty, b = ax + 2 * tx;          // live taps of this output phase
+          const int dy = ay + ty, dx = ax + tx;                // neighbourhood slot: iy = i - 1 + dy
+          const float w = p.k[(3 - a) * 4 + (3 - b)];
+          const float4 u = v[dy][dx];
+          acc.x += w * u.x; acc.y += w * u.y; acc.z += w * u.z; acc.w += w * u.w;
+        }
+      if (p.round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+      *reinterpret_cast<float4*>(yout + ((long long)(2 * i + ay) * p.out_w + (2 * j + ax)) * p.minor) = acc;
+    }
+}
+
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
                      int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_out, cudaStream_t st) {
@@ -310,6 +356,12 @@ int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int maj
   if (total == 0) return 0;
   if (vec && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && pad_x0 >= 0 && total < (1LL << 31) * 256) {
     const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (up_x == 2 && down_x == 1 && pad_x0 == 2 && p.out_h == 2 * in_h && p.out_w == 2 * in_w) {
+      const long long tin = (long long)major * in_h * in_w * (minor / 4);
+      fir4_up2_nhwc_kernel<<<(unsigned)((tin + 255) / 256), 256, 0, st>>>(x, y, p);
+      B200_CHECK_LAUNCH();
+      return 0;
+    }
     if (up_x == 2 && down_x == 1) { fir4_nhwc_kernel<2, 1><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
     if (up_x == 1 && down_x == 2) { fir4_nhwc_kernel<1, 2><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
     if (up_x == 1 && down_x == 1) { fir4_nhwc_kernel<1, 1><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }

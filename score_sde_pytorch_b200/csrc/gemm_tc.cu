@@ -671,7 +671,8 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // CTA pairs (cta_group::2) for 256-column tiles: B200_TC_2CTA=1 opts in (0 = off, default until validated per round)
     static const int two_cta_env = [] { const char* v = getenv("B200_TC_2CTA"); return v ? atoi(v) : 0; }();
     const int tmb = d.conv ? 1 : (d.M_per_batch + BM - 1) / BM;
-    pl->two_cta = two_cta_env && !p.swap && d.N_total % 256 == 0 && (d.conv || d.nbatch == 1 || tmb % 2 == 0);
+    // B200_TC_2CTA: 1 = 256-column tiles only, 2 = also the 128-column tiles (128-channel layers)
+    pl->two_cta = two_cta_env && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) && (d.conv || d.nbatch == 1 || tmb % 2 == 0);
     if (pl->two_cta) p.epi_mode = 0;
   }
   p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
@@ -717,7 +718,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   {
     uint64_t dims[2] = {(uint64_t)d.K_total, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * 4};
-    uint32_t box[2] = {BKE, (uint32_t)((p.swap || pl->two_cta) ? 128 : pl->bn)};
+    uint32_t box[2] = {BKE, (uint32_t)(pl->two_cta ? pl->bn / 2 : (p.swap ? 128 : pl->bn))};
     rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
     if (rc) { delete pl; return rc; }
   }
@@ -765,7 +766,8 @@ static int tc_configure() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 4, true>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4, false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6, false>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<6>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<256, 6>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<128, 8>::TOTAL));
   configured = true;
   return 0;
 }
@@ -785,7 +787,8 @@ int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
     const TcParams& q = pl->prm;
     const long long pairs = (((long long)q.nbatch * q.tiles_m_per_batch + 1) / 2) * q.tiles_n;
     const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
-    gemm_tc2_kernel<6><<<grid, 384, Smem2<6>::TOTAL, st>>>(pl->prm);
+    if (pl->bn == 256) gemm_tc2_kernel<256, 6><<<grid, 384, Smem2<256, 6>::TOTAL, st>>>(pl->prm);
+    else gemm_tc2_kernel<128, 8><<<grid, 384, Smem2<128, 8>::TOTAL, st>>>(pl->prm);
     B200_CHECK_LAUNCH();
     return 0;
   }

@@ -15,9 +15,9 @@
 // residual / scale / TF32 rounding / GroupNorm quad sums) and release the accumulator stage on the leader's
 // `tmem_empty` barrier (16 arrivals).
 
-template <int STAGES>
+template <int BN, int STAGES>
 struct Smem2 {
-  static constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES;          // A rows (16 KB) + this CTA's half of W (16 KB)
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / 2) * BKE * 4;   // A rows (16 KB) + this CTA's half of the W tile
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
@@ -61,10 +61,9 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
-template <int STAGES>
+template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
-  using L = Smem2<STAGES>;
-  constexpr int BN = 256;
+  using L = Smem2<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);   // used in the leader only
@@ -84,7 +83,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -118,7 +117,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
       }
       const int arow0 = (mg >= tiles_m_total) ? (1 << 30) : b * p.a_batch_rows + mt * BM;
       const int bsh = (int)((pair / p.tiles_n) * 2 / p.tiles_m_per_batch);   // batch of the pair (both CTAs share it)
-      const int wrow0 = bsh * p.w_batch_rows + nt * BN + (int)rank * 128;     // this CTA's half of the W tile
+      const int wrow0 = bsh * p.w_batch_rows + nt * BN + (int)rank * (BN / 2);   // this CTA's half of the W tile
       for (int src = 0; src < 2; ++src) {
         const int nch = src ? p.kchunks2 : p.kchunks1;
         if (nch == 0) continue;
@@ -143,8 +142,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ======================= MMA issuer (leader CTA, for the pair) =======================
-    // instruction: M = 256 (128 rows per CTA), N = 256, K = 8 tf32; D fp32 in each CTA's own TMEM
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    // instruction: M = 256 (128 rows per CTA), N = BN, K = 8 tf32; D fp32 in each CTA's own TMEM
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -223,6 +222,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   cluster_sync_all();                               // the peer's smem / barriers / TMEM stay valid until both are done
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }

@@ -5,4 +5,8 @@ for args in "--c1 256 --cout 256 --hw 16" "--c1 256 --cout 256 --hw 16 --residua
   python tools/ncu_conv.py $args >> $L 2>&1
   B200_TC_2CTA=1 python tools/ncu_conv.py $args >> $L 2>&1
 done
+for args in "--c1 128 --cout 128 --hw 32" "--c1 128 --cout 128 --hw 32 --residual" "--c1 256 --cout 128 --hw 32" "--c1 384 --cout 128 --hw 32 --k 1"; do
+  python tools/ncu_conv.py $args >> $L 2>&1
+  B200_TC_2CTA=2 python tools/ncu_conv.py $args >> $L 2>&1
+done
 cat $L
