@@ -689,7 +689,20 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
     if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
     const float4* src = reinterpret_cast<const float4*>(xb + ((long long)iy * W + ix) * C);
     const float4* wt = reinterpret_cast<const float4*>(sw + tap * N * C);
-    for (int c4 = 0; c4 < (C >> 2); ++c4) {
+    int c4 = 0;
+    for (; c4 + 4 <= (C >> 2); c4 += 4) {                    // four 128-bit loads in flight per thread
+      float4 a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = __ldg(src + c4 + u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          const float4 ww = wt[n * (C >> 2) + c4 + u];
+          acc[n] = fmaf(a[u].x, ww.x, fmaf(a[u].y, ww.y, fmaf(a[u].z, ww.z, fmaf(a[u].w, ww.w, acc[n]))));
+        }
+    }
+    for (; c4 < (C >> 2); ++c4) {
       const float4 a = __ldg(src + c4);
 #pragma unroll
       for (int n = 0; n < N; ++n) {

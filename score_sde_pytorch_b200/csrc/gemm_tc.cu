@@ -362,6 +362,60 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
     const int r = q * 32 + lane;               // row of the tile held by this thread
     const Epilogue& e = p.epi;
     uint32_t acc = 0, acc_phase = 0;
+    if (p.swap) {
+      // Swapped operands (D^T = W X^T, 128-channel layers): TMEM lane = output channel, column = pixel.  A warp's
+      // 32 lanes are 32 consecutive channels of one pixel, so every scalar load/store instruction below touches
+      // exactly one 128-byte line of the NHWC tensor (fully coalesced), and the M=128 x N=256 instruction keeps the
+      // single issuing thread ahead of the tensor pipe (N=128 instructions retire in 64 cycles, faster than one
+      // thread can issue them).
+      if constexpr (BN == 256) {
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          const int co = (int)(tile % p.tiles_n) * 128 + r;
+          const long long row_base = (tile / p.tiles_n) * 256;
+          const int img = (int)(row_base / e.rows_per_img);          // rows_per_img % 256 == 0: one image per tile
+          const float add = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
+          const float dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+          float ssum = 0.f, ssq = 0.f;
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int j = half * 4; j < half * 4 + 4; ++j) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
+            const long long pix0 = row_base + j * 32;
+            float* dst = e.out + pix0 * e.ld_out + co;
+            const float* res = e.residual ? e.residual + pix0 * e.ld_res + co : nullptr;
+            float rr[32];
+            if (res) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rr[i] = __ldg(res + (long long)i * e.ld_res);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float o = __uint_as_float(v[i]) + add;
+              if (res) o += rr[i];
+              o *= e.scale;
+              if (e.per_img_div) o /= dv;
+              if (e.round_tf32) o = round_tf32(o);
+              dst[(long long)i * e.ld_out] = o;
+              ssum += o; ssq += o * o;
+            }
+          }
+          if (p.qstats) {
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+            if ((lane & 3) == 0) {
+              double* qd = p.qstats + ((long long)img * (p.N_total >> 2) + (co >> 2)) * 2;
+              atomicAdd(qd, (double)ssum); atomicAdd(qd + 1, (double)ssq);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    } else
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % p.tiles_n);
       const long long mg = tile / p.tiles_n;
@@ -660,19 +714,23 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     const long long Mtot = (long long)d.nimg * d.H * d.W;
     const bool can_swap = allow_swap && d.conv && p.stride == 1 && d.N_total % 256 != 0 && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
-    // auto (default): direct stores with the deepest operand ring.  Measured on the headline step
-    // (profiles/r01_*): direct 4/6-stage >= smem-staged TMA-store variants for every launch shape but the
-    // 128-channel residual convs, within box-to-box noise overall; B200_TC_EPILOGUE=staged selects the staged
-    // path (and the swapped-operand mode for 128-channel convs) for A/B runs.
-    p.swap = (can_swap && req == 1) ? 1 : 0;
+    // auto (default): direct stores with the deepest operand ring (measured best for every launch shape,
+    // profiles/r01_c7_conv_isolated.log); 128-channel convolutions use the swapped-operand form.
+    // B200_TC_EPILOGUE=staged selects the smem-staged TMA-store epilogue for A/B runs.
+    p.swap = can_swap ? 1 : 0;
     p.epi_mode = req == 1 ? 1 : 0;
     if (p.swap) pl->bn = 256;
     p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
     // CTA pairs (cta_group::2) for 256-column tiles: B200_TC_2CTA=1 opts in (0 = off, default until validated per round)
-    static const int two_cta_env = [] { const char* v = getenv("B200_TC_2CTA"); return v ? atoi(v) : 0; }();
+    // CTA pairs (cta_group::2) for 256-column tiles: on by default when the launch has at least one 256-row pair
+    // per cluster slot (small launches fill the SMs better with single-CTA tiles).  B200_TC_2CTA=0 disables,
+    // =2 also pairs the 128-column tiles (measured: no gain, profiles/r01_c8_conv_isolated.log).
+    static const int two_cta_env = [] { const char* v = getenv("B200_TC_2CTA"); return v ? atoi(v) : 1; }();
     const int tmb = d.conv ? 1 : (d.M_per_batch + BM - 1) / BM;
-    // B200_TC_2CTA: 1 = 256-column tiles only, 2 = also the 128-column tiles (128-channel layers)
-    pl->two_cta = two_cta_env && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) && (d.conv || d.nbatch == 1 || tmb % 2 == 0);
+    const long long m_tiles = d.conv ? (Mtot + BM - 1) / BM : (long long)d.nbatch * tmb;
+    const long long n_tiles = d.N_total % 256 == 0 ? d.N_total / 256 : d.N_total / 128;
+    pl->two_cta = two_cta_env && req != 1 && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) &&
+                  (d.conv || d.nbatch == 1 || tmb % 2 == 0) && (m_tiles / 2) * n_tiles >= num_sms() / 2;
     if (pl->two_cta) p.epi_mode = 0;
   }
   p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
