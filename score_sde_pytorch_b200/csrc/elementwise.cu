@@ -632,7 +632,7 @@ int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, lon
 // [B*HW, 32] x [nf, 32]^T product instead of a 27-deep CUDA-core loop.
 // ============================================================================
 __global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __restrict__ x, float* __restrict__ patches,
-                                                            int B, int C, int H, int W) {
+                                                            int B, int C, int Hin, int Win, int H, int W, int stride, int pad) {
   const long long total = (long long)B * H * W * 8;            // 8 float4 per 32-wide row
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -646,18 +646,19 @@ __global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __rest
     float t = 0.f;
     if (k < 9 * C) {
       const int tap = k / C, c = k % C;
-      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) t = __ldg(x + (((long long)b * C + c) * H + iy) * W + ix);
+      const int iy = py * stride + tap / 3 - pad, ix = px * stride + tap % 3 - pad;
+      if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) t = __ldg(x + (((long long)b * C + c) * Hin + iy) * Win + ix);
     }
     v[j] = round_tf32(t);
   }
   *reinterpret_cast<float4*>(patches + pg * 32 + k4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int H, int W, cudaStream_t st) {
+int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
+                          int pad, cudaStream_t st) {
   B200_REQUIRE(9 * C <= 32, "im2col3x3: %d channels do not fit one 32-wide K step", C);
   const long long total = (long long)B * H * W * 8;
-  im2col3x3_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, patches, B, C, H, W);
+  im2col3x3_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, patches, B, C, Hin, Win, H, W, stride, pad);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -673,50 +674,59 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
                                                              const float* __restrict__ bias, const float* __restrict__ div,
                                                              long long div_stride, float* __restrict__ out_nchw,
                                                              int B, int H, int W, int C) {
+  // Eight lanes share one output pixel: lane `part` takes the float4s part, part+8, ... of the pixel's channel
+  // vector, so a warp-wide 128-bit load covers 4 pixels x 128 contiguous bytes (4 cache lines per instruction
+  // instead of 32 with one pixel per lane, which was L1-wavefront bound); the partial dot products are folded with
+  // three shuffles per output channel.
   extern __shared__ float sw[];   // [9][N][C]
   for (int i = threadIdx.x; i < 9 * N * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const long long pg = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (pg >= (long long)B * H * W) return;
-  const int px = (int)(pg % W), py = (int)((pg / W) % H), b = (int)(pg / ((long long)W * H));
+  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long pg = gt >> 3;
+  const int part = (int)(gt & 7);
+  const bool live = pg < (long long)B * H * W;
+  const long long pgc = live ? pg : 0;
+  const int px = (int)(pgc % W), py = (int)((pgc / W) % H), b = (int)(pgc / ((long long)W * H));
   float acc[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) acc[n] = 0.f;
   const float* xb = x + (long long)b * H * W * C;
+  const int nq = C >> 2;                                  // float4s per pixel
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    if (!live || iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
     const float4* src = reinterpret_cast<const float4*>(xb + ((long long)iy * W + ix) * C);
     const float4* wt = reinterpret_cast<const float4*>(sw + tap * N * C);
-    int c4 = 0;
-    for (; c4 + 4 <= (C >> 2); c4 += 4) {                    // four 128-bit loads in flight per thread
+    for (int c4 = part; c4 < nq; c4 += 32) {               // up to four 128-bit loads in flight
       float4 a[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = __ldg(src + c4 + u);
+      for (int u = 0; u < 4; ++u) a[u] = (c4 + 8 * u < nq) ? __ldg(src + c4 + 8 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u) {
+        if (c4 + 8 * u >= nq) break;
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-          const float4 ww = wt[n * (C >> 2) + c4 + u];
+          const float4 ww = wt[n * nq + c4 + 8 * u];
           acc[n] = fmaf(a[u].x, ww.x, fmaf(a[u].y, ww.y, fmaf(a[u].z, ww.z, fmaf(a[u].w, ww.w, acc[n]))));
         }
-    }
-    for (; c4 < (C >> 2); ++c4) {
-      const float4 a = __ldg(src + c4);
-#pragma unroll
-      for (int n = 0; n < N; ++n) {
-        const float4 ww = wt[n * (C >> 2) + c4];
-        acc[n] = fmaf(a.x, ww.x, fmaf(a.y, ww.y, fmaf(a.z, ww.z, fmaf(a.w, ww.w, acc[n]))));
       }
     }
   }
-  const float dv = div ? __ldg(div + b * div_stride) : 1.f;
 #pragma unroll
   for (int n = 0; n < N; ++n) {
-    float v = acc[n] + (bias ? __ldg(bias + n) : 0.f);
-    if (div) v = v / dv;
-    out_nchw[(((long long)b * N + n) * H + py) * W + px] = v;
+    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+  }
+  if (live && part == 0) {
+    const float dv = div ? __ldg(div + b * div_stride) : 1.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float v = acc[n] + (bias ? __ldg(bias + n) : 0.f);
+      if (div) v = v / dv;
+      out_nchw[(((long long)b * N + n) * H + py) * W + px] = v;
+    }
   }
 }
 
@@ -725,7 +735,7 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
   B200_REQUIRE(N >= 1 && N <= 4 && C % 4 == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
   const size_t smem = (size_t)9 * N * C * sizeof(float);
   B200_REQUIRE(smem <= 96 * 1024, "conv3x3_small_n: weights (%zu B) exceed shared memory", smem);
-  const long long total = (long long)B * H * W;
+  const long long total = (long long)B * H * W * 8;      // eight lanes per output pixel
   const unsigned blocks = (unsigned)((total + 255) / 256);
 #define B200_LAUNCH_SMALLN(NN)                                                                                      \
   do {                                                                                                              \
@@ -740,6 +750,70 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
     default: B200_LAUNCH_SMALLN(4); break;
   }
 #undef B200_LAUNCH_SMALLN
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// ============================================================================
+// Attention core for small token counts (T = H*W <= 64, e.g. the 4x4 bottleneck block): one CTA per image keeps
+// q, k, v [T, C] in shared memory, forms logits = q k^T * C^-1/2 (layerspp.py:82), softmax over keys (:83-85),
+// and h = P v (:86).  qkv is the [B*T, 3C] output of the fused projection (bias included).
+// ============================================================================
+__global__ void __launch_bounds__(256) attn_small_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                        int T, int C, float scale, int round_out) {
+  extern __shared__ float sm[];            // q[T][C] k[T][C] v[T][C] p[T][T]
+  float* sq = sm; float* sk = sq + T * C; float* sv = sk + T * C; float* sp = sv + T * C;
+  const int b = blockIdx.x;
+  const float* src = qkv + (long long)b * T * 3 * C;
+  for (int i = threadIdx.x; i < T * C / 4; i += blockDim.x) {
+    const int t = i / (C / 4), c = (i % (C / 4)) * 4;
+    *reinterpret_cast<float4*>(sq + t * C + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + c));
+    *reinterpret_cast<float4*>(sk + t * C + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + C + c));
+    *reinterpret_cast<float4*>(sv + t * C + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + 2 * C + c));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int e = warp; e < T * T; e += nw) {          // one warp per logit
+    const int i = e / T, j = e % T;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(sq[i * C + c], sk[j * C + c], a);
+    a = warp_sum(a);
+    if (lane == 0) sp[e] = a * scale;
+  }
+  __syncthreads();
+  for (int i = warp; i < T; i += nw) {              // softmax of row i
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sp[i * T + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) { const float ev = expf(sp[i * T + j] - mx); sp[i * T + j] = ev; sum += ev; }
+    sum = warp_sum(sum);
+    for (int j = lane; j < T; j += 32) sp[i * T + j] = sp[i * T + j] / sum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    const int t = i / C, c = i % C;
+    float a = 0.f;
+    for (int j = 0; j < T; ++j) a = fmaf(sp[t * T + j], sv[j * C + c], a);
+    out[((long long)b * T + t) * C + c] = round_out ? round_tf32(a) : a;
+  }
+}
+
+// called at plan time (outside any stream capture): opt in to > 48 KB of dynamic shared memory
+int launch_attn_small_configure(int T, int C) {
+  const size_t smem = ((size_t)3 * T * C + (size_t)T * T) * sizeof(float);
+  B200_REQUIRE(T <= 64 && C % 4 == 0 && smem <= 200 * 1024, "attn_small: T=%d C=%d unsupported", T, C);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  return 0;
+}
+
+int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st) {
+  const size_t smem = ((size_t)3 * T * C + (size_t)T * T) * sizeof(float);
+  attn_small_kernel<<<B, 256, smem, st>>>(qkv, out, T, C, scale, round_out);
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -209,12 +209,13 @@ int build_graph(b200_ncsnpp* e) {
     Mod m; m.kind = M_ATTN; m.index = (int)e->mods.size(); m.cin1 = C; m.cout = C; m.res = res;
     const int T = res * res;
     m.tcattn = (e->cfg.precision == 0) && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
+    m.tc0 = (e->cfg.precision == 0) && (C % 128 == 0) && (m.tcattn || T <= 64);   // q/k/v projections on tensor cores
     m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {C}, PK_COPY, 0, 0, 0, 0);
     m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {C}, PK_COPY, 0, 0, 0, 0);
     // q,k,v projection weights packed as one [3C][C] block (rows: q, k, v), biases as one [3C] vector
     const long long wbase = e->wcount; e->wcount += 3LL * C * C;
     const long long bbase = e->wcount; e->wcount += (3LL * C + 63) & ~63LL;
-    const bool tcproj = m.tcattn;
+    const bool tcproj = m.tc0;
     for (int k = 0; k < 3; ++k) {
       m.nw[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".W"), {C, C}, PK_NIN, 1, C, C, tcproj, wbase + (long long)k * C * C);
       m.nb[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".b"), {C}, PK_COPY, 0, 0, 0, 0, bbase + (long long)k * C);
@@ -248,7 +249,10 @@ int build_graph(b200_ncsnpp* e) {
         Mod m; m.kind = M_PYR_DOWN; m.index = (int)e->mods.size(); m.cin1 = pyr_ch; m.cout = in_ch; m.res = all_res[lvl];
         // FIR-padded stride-2 VALID conv: on tcgen05 via TMA element strides when the channel counts tile
         m.tc0 = tc_ok(e, pyr_ch, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 9);
-        m.w = add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, m.tc0);
+        // image-channel pyramid level (3 channels): im2col patches + one K=32 contraction, like the input conv
+        m.tc2 = (c.precision == 0) && (9 * pyr_ch <= 32) && tc_ok(e, 32, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 1);
+        m.w = m.tc2 ? add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV_FLAT32, 9, in_ch, pyr_ch, 1, -1, (long long)in_ch * 32)
+                    : add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, m.tc0);
         m.b = add_param(e, nm("Conv2d_0.bias"), {in_ch}, PK_COPY, 0, 0, 0, 0);
         e->mods.push_back(m);
         pyr_ch = in_ch;
@@ -403,7 +407,7 @@ struct Builder {
   void gemm(bool use_tc, const float* A, long long lda, long long a_rows, int a_batch_rows, const float* Wm, long long ldw,
             long long w_rows, int w_batch_rows, int nbatch, int M, int N, int K, const float* bias,
             const float* residual, long long ld_res, float scale, int round, float* out, long long ldo,
-            double* qstats = nullptr, int rows_per_img = 1 << 30) {
+            double* qstats = nullptr, int rows_per_img = 1 << 30, bool no_pair = false) {
     Epilogue ep; memset(&ep, 0, sizeof(ep));
     ep.bias = bias; ep.residual = residual; ep.ld_res = ld_res; ep.scale = scale; ep.round_tf32 = round;
     ep.rows_per_img = rows_per_img; ep.out = out; ep.ld_out = ldo;
@@ -411,7 +415,7 @@ struct Builder {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.a1 = A; d.C1 = K; d.conv = 0; d.taps = 1; d.a_rows = a_rows; d.a_ld = lda; d.a_batch_rows = a_batch_rows;
       d.w = Wm; d.N_total = N; d.K_total = K; d.w_rows = w_rows; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
-      d.nbatch = nbatch; d.M_per_batch = M; d.epi_mode = -1; d.qstats = qstats; d.epi = ep;
+      d.nbatch = nbatch; d.M_per_batch = M; d.epi_mode = -1; d.qstats = qstats; d.no_pair = no_pair ? 1 : 0; d.epi = ep;
       if (dry) return;
       TcGemmPlan* pl = nullptr;
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
@@ -482,30 +486,44 @@ struct Builder {
     const int C = x.C, T = x.H * x.W;
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
     const bool tc = m.tcattn;
+    const bool small = !m.tcattn && m.tc0 && T <= 64;   // few tokens: projections on tensor cores, core in one CTA per image
     const float* Wqkv = e->W(m.nw[0]);          // [3C][C]
     const float* bqkv = e->W(m.nb[0]);          // [3C]
-    Tensor a = talloc(C, x.H, x.W);
-    gn(x, none, m.gn0w, m.gn0b, 0, tc ? 1 : 0, a, nullptr);
-    long long qkb, vtb, sb, ob;
-    float* qk = falloc((long long)B * T * 2 * C, &qkb);
-    float* vT = falloc((long long)B * C * T, &vtb);
-    const long long BT = (long long)B * T;
-    // q,k = a Wq^T + bq | a Wk^T + bk   (layerspp.py:78-79) in one N=2C contraction
-    gemm(tc, a.p, C, BT, 0 /* rows enumerated flat */, Wqkv, C, 2LL * C, 0, 1, (int)BT, 2 * C, C, bqkv, nullptr, 0, 1.f, tc, qk, 2 * C);
-    // v^T[b][c][t] = sum_i Wv[c][i] a[b][t][i]   (bias bv is added after the PV product: softmax rows sum to 1)
-    gemm(tc, Wqkv + 2LL * C * C, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc, vT, T);
-    tfree(a);
-    float* S = falloc(BT * T, &sb);
-    // logits[b][q][k] = q . k   (layerspp.py:82), scaled inside the softmax
-    gemm(tc, qk, 2 * C, BT, T, qk + C, 2 * C, BT, T, B, T, T, C, nullptr, nullptr, 0, 1.f, 0, S, T);
-    ffree(qk, qkb);
     const float sc = 1.0f / std::sqrt((float)C);   // int(C) ** -0.5
+    const long long BT = (long long)B * T;
     const int Bc = B;
-    op(1, [=](cudaStream_t st) { return launch_softmax_rows(S, S, (long long)Bc * T, T, sc, tc ? 1 : 0, st); }, 4);
-    float* O = falloc(BT * C, &ob);
-    // h[b][q][c] = sum_k P[q][k] v[k][c] + bv[c]   (layerspp.py:86)
-    gemm(tc, S, T, BT, T, vT, T, (long long)B * C, C, B, T, C, T, bqkv + 2 * C, nullptr, 0, 1.f, m.tc2 ? 1 : 0, O, C);
-    ffree(S, sb); ffree(vT, vtb);
+    Tensor a = talloc(C, x.H, x.W);
+    gn(x, none, m.gn0w, m.gn0b, 0, (tc || small) ? 1 : 0, a, nullptr);
+    long long ob; float* O = nullptr;
+    if (small) {
+      long long qb; float* qkv = falloc(BT * 3 * C, &qb);
+      // q | k | v = a [Wq; Wk; Wv]^T + [bq; bk; bv]   (layerspp.py:78-80) as one N=3C contraction
+      gemm(true, a.p, C, BT, 0, Wqkv, C, 3LL * C, 0, 1, (int)BT, 3 * C, C, bqkv, nullptr, 0, 1.f, 0, qkv, 3 * C);
+      tfree(a);
+      O = falloc(BT * C, &ob);
+      const int rnd = m.tc2 ? 1 : 0;
+      if (!dry) { if (int r = launch_attn_small_configure(T, C)) { rc = r; } }
+      op(1, [=](cudaStream_t st) { return launch_attn_small(qkv, O, Bc, T, C, sc, rnd, st); }, 4);
+      ffree(qkv, qb);
+    } else {
+      long long qkb, vtb, sb;
+      float* qk = falloc((long long)B * T * 2 * C, &qkb);
+      float* vT = falloc((long long)B * C * T, &vtb);
+      // q,k = a Wq^T + bq | a Wk^T + bk   (layerspp.py:78-79) in one N=2C contraction
+      gemm(tc, a.p, C, BT, 0 /* rows enumerated flat */, Wqkv, C, 2LL * C, 0, 1, (int)BT, 2 * C, C, bqkv, nullptr, 0, 1.f, tc, qk, 2 * C);
+      // v^T[b][c][t] = sum_i Wv[c][i] a[b][t][i]   (bias bv is added after the PV product: softmax rows sum to 1)
+      gemm(tc, Wqkv + 2LL * C * C, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc, vT, T, nullptr, 1 << 30, /*no_pair=*/true);
+      tfree(a);
+      float* S = falloc(BT * T, &sb);
+      // logits[b][q][k] = q . k   (layerspp.py:82), scaled inside the softmax
+      gemm(tc, qk, 2 * C, BT, T, qk + C, 2 * C, BT, T, B, T, T, C, nullptr, nullptr, 0, 1.f, 0, S, T, nullptr, 1 << 30, /*no_pair=*/true);
+      ffree(qk, qkb);
+      op(1, [=](cudaStream_t st) { return launch_softmax_rows(S, S, (long long)Bc * T, T, sc, tc ? 1 : 0, st); }, 4);
+      O = falloc(BT * C, &ob);
+      // h[b][q][c] = sum_k P[q][k] v[k][c] + bv[c]   (layerspp.py:86)
+      gemm(tc, S, T, BT, T, vT, T, (long long)B * C, C, B, T, C, T, bqkv + 2 * C, nullptr, 0, 1.f, m.tc2 ? 1 : 0, O, C);
+      ffree(S, sb); ffree(vT, vtb);
+    }
     Tensor out = talloc(C, x.H, x.W);
     Tensor Ot; Ot.p = O; Ot.C = C; Ot.H = x.H; Ot.W = x.W;
     conv(m.tc2, Ot, Tensor(), 1, m.nw[3], m.nb[3], C, -1, x.p, inv_s2, 0, out, /*want_stats=*/true);   // NIN_3 + (x+h)/sqrt2 (:87-91)
@@ -557,11 +575,9 @@ struct Builder {
         // im2col patches [B*R*R][32] (TF32 grid) then one K=32 tcgen05 contraction with the flat-packed weights
         long long pb; float* patches = falloc((long long)B * R * R * 32, &pb);
         const int Bc = B;
-        op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, st); }, 6);
-        double* qs = nullptr;
-        if (fused_stats) { qs = qalloc(nf); h0.qs = qs; }
-        gemm(true, patches, 32, (long long)B * R * R, 0, e->W(m.w), 32, nf, 0, 1, B * R * R, nf, 32, e->W(m.b), nullptr, 0, 1.f, 0,
-             h0.p, nf, qs, R * R);
+        op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, R, R, 1, 1, st); }, 6);
+        Tensor pt; pt.p = patches; pt.C = 32; pt.H = R; pt.W = R;      // patches as a 32-channel NHWC image: a 1x1 conv
+        conv(true, pt, Tensor(), 1, m.w, m.b, nf, -1, nullptr, 1.f, 0, h0, /*want_stats=*/true);
         ffree(patches, pb);
       } else {
         SimtConv s; memset(&s, 0, sizeof(s));
@@ -600,12 +616,20 @@ struct Builder {
           const int Hp = Hin + ((p + 1) / 2) + (p / 2) - e->firn + 1;
           long long fb; float* fbuf = falloc((long long)B * pyr.C * Hp * Hp, &fb);
           const bool tcp = mp.tc0 && !pyr_nchw;
+          const bool flat = mp.tc2 && pyr_nchw;
           if (pyr_nchw) fir(pyr.p, B * pyr.C, Hin, Hin, 1, 1, 1, (p + 1) / 2, p / 2, 0, fbuf, 1.f);
           else fir(pyr.p, B, Hin, Hin, pyr.C, 1, 1, (p + 1) / 2, p / 2, tcp ? 1 : 0, fbuf, 1.f);
           Tensor np = talloc(mp.cout, h.H, h.W);
           if ((Hp - 3) / 2 + 1 != h.H) { set_error("ncsnpp: pyramid geometry mismatch (%d vs %d)", (Hp - 3) / 2 + 1, h.H); return 2; }
           const float ps = c.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
-          if (tcp) {
+          if (flat) {
+            long long pb2; float* patches = falloc((long long)B * h.H * h.W * 32, &pb2);
+            const int Bc = B, pc = pyr.C, oh = h.H, ow = h.W;
+            op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(fbuf, patches, Bc, pc, Hp, Hp, oh, ow, 2, 0, st); }, 6);
+            Tensor pt; pt.p = patches; pt.C = 32; pt.H = h.H; pt.W = h.W;
+            conv(true, pt, Tensor(), 1, mp.w, mp.b, mp.cout, -1, h.p, ps, 0, np, /*want_stats=*/true);
+            ffree(patches, pb2);
+          } else if (tcp) {
             Tensor fin; fin.p = fbuf; fin.C = pyr.C; fin.H = Hp; fin.W = Hp;
             conv(true, fin, Tensor(), 9, mp.w, mp.b, mp.cout, -1, h.p, ps, 0, np, /*want_stats=*/true, /*stride=*/2, /*Hin=*/Hp);
           } else {

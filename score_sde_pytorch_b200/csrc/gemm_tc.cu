@@ -729,7 +729,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     const int tmb = d.conv ? 1 : (d.M_per_batch + BM - 1) / BM;
     const long long m_tiles = d.conv ? (Mtot + BM - 1) / BM : (long long)d.nbatch * tmb;
     const long long n_tiles = d.N_total % 256 == 0 ? d.N_total / 256 : d.N_total / 128;
-    pl->two_cta = two_cta_env && req != 1 && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) &&
+    pl->two_cta = two_cta_env && !d.no_pair && req != 1 && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) &&
                   (d.conv || d.nbatch == 1 || tmb % 2 == 0) && (m_tiles / 2) * n_tiles >= num_sms() / 2;
     if (pl->two_cta) p.epi_mode = 0;
   }

@@ -30,7 +30,10 @@ int launch_fill_from_table(const float* table, const int* step, float* dst, int 
 int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cudaStream_t st);
 int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, long long so, long long si,
                        long long stp, int round_out, cudaStream_t st, long long dt = 0, long long dO = 0);
-int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int H, int W, cudaStream_t st);
+int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
+                          int pad, cudaStream_t st);
+int launch_attn_small_configure(int T, int C);
+int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st);
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
                            float* out_nchw, int B, int H, int W, int C, int N, cudaStream_t st);
 
@@ -75,6 +78,7 @@ struct TcGemmDesc {
   int w_batch_rows;         // rows to advance per batch item (0 = shared)
   int nbatch; int M_per_batch;   // gemm: rows of output per batch item; conv: nbatch=1, M=nimg*H*W
   int epi_mode;             // 0 direct stores, 1 smem-staged TMA store, -1 = library default
+  int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
   Epilogue epi;
 };
