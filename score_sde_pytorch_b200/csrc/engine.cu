@@ -441,7 +441,10 @@ struct Builder {
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
     Tensor a0 = talloc(Cin, H, H);
     Tensor raw; // TF32-rounded copy of the (concatenated) block input for the tensor-core skip conv
-    if (m.has_conv2 && m.tc2 && !resample) raw = talloc(Cin, H, H);
+    // B200_SKIP_TRUNC=1 (experiment): feed the 1x1 skip conv the un-rounded block input directly (the tensor
+    // core truncates it to TF32) instead of a round-to-nearest copy -> one fewer activation write per block
+    static const bool skip_trunc = [] { const char* v = getenv("B200_SKIP_TRUNC"); return v && v[0] == '1'; }();
+    if (m.has_conv2 && m.tc2 && !resample && !skip_trunc) raw = talloc(Cin, H, H);
     gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? 1 : 0, a0, raw.p);
     Tensor xr;
     if (resample) {
@@ -470,7 +473,8 @@ struct Builder {
     if (m.has_conv2) {
       s = talloc(m.cout, Ho, Ho);
       if (resample) conv(m.tc2, xr, Tensor(), 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
-      else if (m.tc2) conv(true, raw, Tensor(), 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
+      else if (m.tc2 && raw.p) conv(true, raw, Tensor(), 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
+      else if (m.tc2) conv(true, x1, x2, 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
       else conv(false, x1, x2, 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
       residual = s.p;
       tfree(raw); tfree(xr);

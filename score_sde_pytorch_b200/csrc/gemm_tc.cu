@@ -712,7 +712,9 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     static const bool allow_swap = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '0'); }();
     const int req = d.epi_mode < 0 ? tc_gemm_default_epi_mode() : d.epi_mode;   // 0 direct, 1 staged, 2 auto
     const long long Mtot = (long long)d.nimg * d.H * d.W;
-    const bool can_swap = allow_swap && d.conv && p.stride == 1 && d.N_total % 256 != 0 && (d.H * d.W) % 256 == 0 &&
+    // B200_TC_SWAP=2 (experiment): also swap 1x1 convolutions with 256-multiple channel counts (output-bound launches)
+    static const bool swap_1x1 = [] { const char* v = getenv("B200_TC_SWAP"); return v && v[0] == '2'; }();
+    const bool can_swap = allow_swap && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1)) && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
     // auto (default): direct stores with the deepest operand ring (measured best for every launch shape,
     // profiles/r01_c7_conv_isolated.log); 128-channel convolutions use the swapped-operand form.
