@@ -68,6 +68,13 @@ B200_API int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2
                                 const float* w_packed, const float* bias, int c_out, int ksize,
                                 const float* rowvec, long long rowvec_ld, const float* residual, float scale,
                                 int round_tf32, float* out, int impl, void* stream);
+/* 3x3 convolution with a fused 1x1 skip projection (a BigGAN resblock's tail, layerspp.py:268-274):
+ * out = (conv3x3(x; w) + bias + [s1 | s2] w_skip^T + bias_skip + residual) * scale, tcgen05 path only.
+ * w_skip is [c_out][cs1 + cs2]; s1/s2 are NHWC tensors of the output's spatial size. */
+B200_API int b200_conv_skip_nhwc_f32(const float* x, int c, const float* s1, int cs1, const float* s2, int cs2,
+                                     int batch, int h, int w, const float* w_packed, const float* bias,
+                                     const float* w_skip, const float* bias_skip, int c_out, const float* residual,
+                                     float scale, int round_tf32, float* out, void* stream);
 B200_API int b200_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int c_out, int c_in, int ksize,
                                        int round_tf32, void* stream);
 /* batched C[b] = A[b] (M x K, pitch lda) * W[b]^T (N x K, pitch ldw), row-major out pitch ldo. */

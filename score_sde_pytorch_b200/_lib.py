@@ -54,6 +54,8 @@ SIGNATURES = {
   'b200_randn_like_torch_f32': (c_int, [c_void_p, c_ll, c_ull, c_ull, P(c_ull), c_void_p, c_void_p]),
   'b200_conv_nhwc_f32': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_void_p, c_ll, c_void_p, c_float, c_int, c_void_p, c_int, c_void_p]),
+  'b200_conv_skip_nhwc_f32': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p]),
   'b200_pack_conv_weight_f32': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
   'b200_gemm_nt_f32': (c_int, [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                c_int, c_void_p, c_ll, c_int, c_void_p]),

@@ -115,6 +115,26 @@ int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int bat
   return launch_conv_simt(s, st);
 }
 
+int b200_conv_skip_nhwc_f32(const float* x, int c, const float* s1, int cs1, const float* s2, int cs2, int batch, int h,
+                            int w, const float* w_packed, const float* bias, const float* w_skip,
+                            const float* bias_skip, int c_out, const float* residual, float scale, int round_tf32,
+                            float* out, void* stream) {
+  B200_REQUIRE(x && s1 && w_packed && w_skip && out, "conv_skip_nhwc: null pointer");
+  Epilogue ep; memset(&ep, 0, sizeof(ep));
+  ep.bias = bias; ep.rowvec = bias_skip; ep.rowvec_ld = 0; ep.residual = residual; ep.ld_res = c_out;
+  ep.scale = scale; ep.round_tf32 = round_tf32; ep.rows_per_img = h * w; ep.out = out; ep.ld_out = c_out;
+  TcGemmDesc d; memset(&d, 0, sizeof(d));
+  d.a1 = x; d.C1 = c; d.conv = 1; d.H = h; d.W = w; d.nimg = batch; d.taps = 9;
+  d.w = w_packed; d.N_total = c_out; d.K_total = c; d.w_rows = 9LL * c_out; d.nbatch = 1;
+  d.a3 = s1; d.C3 = cs1; d.a4 = s2; d.C4 = s2 ? cs2 : 0; d.w2 = w_skip;
+  d.epi_mode = -1; d.epi = ep;
+  TcGemmPlan* pl = nullptr;
+  if (int r = tc_gemm_plan_create(d, &pl)) return r;
+  const int r = tc_gemm_launch(pl, static_cast<cudaStream_t>(stream));
+  tc_gemm_plan_destroy(pl);
+  return r;
+}
+
 int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const float* w, long long ldw, int w_batch_rows,
                      int nbatch, int m, int n, int k, const float* bias, int round_tf32, float* out, long long ldo,
                      int impl, void* stream) {

@@ -104,6 +104,14 @@ struct b200_ncsnpp {
   int B = 0; char* ws = nullptr; long long ws_bytes = 0;
   struct Op { int kind; double flops; std::function<int(cudaStream_t)> fn; };
   std::vector<Op> ops;
+  // Two half-batch "lanes" (ops2 = the second half's plan, empty when the batch is not split).  The lanes are
+  // independent within one network evaluation, so forward() issues them on two streams: while one lane's
+  // HBM-bound GroupNorm/FIR pass streams, the other lane's tcgen05 contraction owns the tensor pipes.
+  std::vector<Op> ops2;
+  int B0 = 0;                                  // images in lane 0 (lane 1 holds B - B0)
+  cudaStream_t lane_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const float* in_x_l[2] = {nullptr, nullptr}; const float* in_labels_l[2] = {nullptr, nullptr}; float* out_l[2] = {nullptr, nullptr};
+
   std::vector<TcGemmPlan*> tcplans;
   std::map<int, Tensor> taps;
   long long launches = 0;
@@ -111,7 +119,12 @@ struct b200_ncsnpp {
   const float* in_x = nullptr; const float* in_labels = nullptr; float* out = nullptr; int uniform = 0;
 
   const float* W(int pi) const { return wblob + params[pi].off; }
-  ~b200_ncsnpp() { for (auto* p : tcplans) tc_gemm_plan_destroy(p); }
+  ~b200_ncsnpp() {
+    for (auto* p : tcplans) tc_gemm_plan_destroy(p);
+    if (lane_stream) cudaStreamDestroy(lane_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
 };
 
 namespace {
@@ -297,7 +310,8 @@ struct Builder {
   b200_ncsnpp* e; int B; char* base; bool dry; Arena arena; int rc = 0;
   char* stats_base = nullptr; long long stats_top = 0;   // bump region for GroupNorm quad sums, zeroed once per forward
   bool fused_stats = false;
-  Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0) {
+  int lane = 0;                                // which half-batch plan this builder fills (ops or ops2)
+  Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_, int lane_ = 0) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0), lane(lane_) {
     const char* v = getenv("B200_FUSED_GN_STATS");
     fused_stats = (e_->cfg.precision == 0) && !(v && v[0] == '0');
     if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
@@ -327,7 +341,7 @@ struct Builder {
   void op(int launches, std::function<int(cudaStream_t)> f, int kind = 6, double flops = 0.0) {
     if (dry) return;
     e->launches += launches;
-    e->ops.push_back({kind, flops, std::move(f)});
+    (lane ? e->ops2 : e->ops).push_back({kind, flops, std::move(f)});
   }
 
   // make sure tensor t has quad sums: produced by its tcgen05 epilogue, else by one streaming pass
@@ -361,7 +375,7 @@ struct Builder {
   // 3x3 / 1x1 'same' convolution on NHWC tensors, stride 1.
   void conv(bool use_tc, Tensor a1, Tensor a2, int taps, int pw, int pb, int Cout, int dense_row /* -1 = none */,
             const float* residual, float scale, int round, Tensor& out, bool want_stats = false, int stride = 1,
-            int Hin = 0) {
+            int Hin = 0, Tensor x3 = Tensor(), Tensor x4 = Tensor(), int pw2 = -1, int pb2 = -1) {
     Epilogue ep; memset(&ep, 0, sizeof(ep));
     ep.bias = e->W(pb);
     ep.rowvec = nullptr;   // patched at launch (depends on the per-call buffers)
@@ -370,7 +384,8 @@ struct Builder {
     b200_ncsnpp* eng = e;
     const float* dense_all = dense_all_;
     const int sumC = e->sumC;
-    const double cflops = 2.0 * B * out.H * out.W * (double)Cout * (a1.C + a2.C) * taps;
+    const double cflops = 2.0 * B * out.H * out.W * (double)Cout * ((a1.C + a2.C) * taps + x3.C + x4.C);
+    if (x3.p && !use_tc) { set_error("ncsnpp: fused skip projection needs the tensor-core path"); rc = 2; return; }
     if (use_tc) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = out.H; d.W = out.W; d.nimg = B; d.taps = taps;
@@ -378,6 +393,11 @@ struct Builder {
       d.w = e->W(pw); d.N_total = Cout; d.K_total = a1.C + a2.C; d.w_rows = (long long)taps * Cout; d.nbatch = 1;
       d.epi_mode = -1;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
+      if (x3.p) {   // fused skip projection: its bias rides in the (image-independent) row-vector slot
+        if (dense_row >= 0) { set_error("ncsnpp: fused skip projection on a conv with a time-embedding bias"); rc = 2; return; }
+        d.a3 = x3.p; d.C3 = x3.C; d.a4 = x4.p; d.C4 = x4.C; d.w2 = e->W(pw2);
+        ep.rowvec = e->W(pb2); ep.rowvec_ld = 0;
+      }
       if (want_stats && fused_stats && (ep.rows_per_img % 32 == 0 || ep.rows_per_img == 16)) { out.qs = qalloc(Cout); d.qstats = out.qs; }
       d.epi = ep;
       if (dry) return;
@@ -470,6 +490,16 @@ struct Builder {
     tfree(h1);
     Tensor s;
     const float* residual = x1.p;
+    // Fused skip projection (default): Conv_2(x) (layerspp.py:270) is accumulated inside the second 3x3 convolution
+    // as extra K steps instead of a separate launch + a residual round trip through HBM.  B200_FUSE_SKIP=0 disables.
+    static const bool fuse_skip = [] { const char* v = getenv("B200_FUSE_SKIP"); return !(v && v[0] == '0'); }();
+    if (m.has_conv2 && fuse_skip && m.tc1 && m.tc2 && (resample || raw.p || skip_trunc)) {
+      Tensor out = talloc(m.cout, Ho, Ho);
+      Tensor e1 = resample ? xr : raw.p ? raw : x1, e2 = (resample || raw.p) ? Tensor() : x2;
+      conv(true, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, nullptr, inv_s2, 0, out, /*want_stats=*/true, 1, 0, e1, e2, m.c2w, m.c2b);
+      tfree(a1); tfree(raw); tfree(xr);
+      return out;
+    }
     if (m.has_conv2) {
       s = talloc(m.cout, Ho, Ho);
       if (resample) conv(m.tc2, xr, Tensor(), 1, m.c2w, m.c2b, m.cout, -1, nullptr, 1.f, 0, s);
@@ -540,6 +570,7 @@ struct Builder {
     const int nf = c.nf, R = c.image_size, ch = c.num_channels, sumC = e->sumC;
     b200_ncsnpp* eng = e;
     const int Bc = B;
+    const int ln = lane;
     // ---- time embedding (ncsnpp.py:236-255) + all Dense_0(act(temb)) rows (layerspp.py:263) ----
     long long eb, t1b, t2b, db, xcb;
     float* emb = falloc((long long)B * 2 * nf, &eb);
@@ -553,7 +584,7 @@ struct Builder {
       const float *Wd = e->wblob + e->dense_w_off, *bd = e->wblob + e->dense_b_off;
       op(4, [=](cudaStream_t st) {
         const int rows = eng->uniform ? 1 : Bc;
-        if (int r = launch_fourier_embed(eng->in_labels, 1, Wf, nf, rows, emb, st)) return r;
+        if (int r = launch_fourier_embed(eng->in_labels_l[ln], 1, Wf, nf, rows, emb, st)) return r;
         if (int r = launch_linear_rows(emb, 2 * nf, W1, b1, rows, 4 * nf, 2 * nf, 0, t1, 4 * nf, st)) return r;
         if (int r = launch_linear_rows(t1, 4 * nf, W2, b2, rows, 4 * nf, 4 * nf, 1, t2, 4 * nf, st)) return r;
         return launch_linear_rows(t2, 4 * nf, Wd, bd, rows, sumC, 4 * nf, 1, dense_all, sumC, st);
@@ -565,8 +596,8 @@ struct Builder {
       const long long n = (long long)B * ch * R * R;
       const int centered = c.centered;
       op(1, [=](cudaStream_t st) {
-        if (centered) return cudaMemcpyAsync(xc, eng->in_x, n * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : (set_error("memcpy failed"), 1);
-        affine_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, st>>>(eng->in_x, xc, n, -0.5f, 2.0f);
+        if (centered) return cudaMemcpyAsync(xc, eng->in_x_l[ln], n * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : (set_error("memcpy failed"), 1);
+        affine_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, st>>>(eng->in_x_l[ln], xc, n, -0.5f, 2.0f);
         return cudaGetLastError() == cudaSuccess ? 0 : (set_error("affine launch failed"), 1);
       });
     }
@@ -688,7 +719,7 @@ struct Builder {
       const Tensor ain = a; const int Bc = B;
       if (ch <= 4) {
         op(1, [=](cudaStream_t st) {
-          return launch_conv3x3_small_n(ain.p, wo, bo, sbs ? eng->in_labels : nullptr, eng->uniform ? 0 : 1, eng->out,
+          return launch_conv3x3_small_n(ain.p, wo, bo, sbs ? eng->in_labels_l[ln] : nullptr, eng->uniform ? 0 : 1, eng->out_l[ln],
                                         Bc, R, R, ain.C, ch, st);
         }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
       } else {
@@ -698,8 +729,8 @@ struct Builder {
         s.epi.bias = bo; s.epi.scale = 1.f; s.epi.rows_per_img = R * R; s.epi.out_nchw = 1; s.epi.ld_out = ch;
         op(1, [=](cudaStream_t st) {
           SimtConv cc = s;
-          cc.epi.out = eng->out;
-          if (sbs) { cc.epi.per_img_div = eng->in_labels; cc.epi.div_stride = eng->uniform ? 0 : 1; }
+          cc.epi.out = eng->out_l[ln];
+          if (sbs) { cc.epi.per_img_div = eng->in_labels_l[ln]; cc.epi.div_stride = eng->uniform ? 0 : 1; }
           return launch_conv_simt(cc, st);
         }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
       }
@@ -710,7 +741,8 @@ struct Builder {
       // the epilogue-accumulated GroupNorm sums start from zero every forward: one memset of the whole region
       char* sb = stats_base; const long long sn = stats_top;
       e->launches += 1;
-      e->ops.insert(e->ops.begin(), b200_ncsnpp::Op{6, 0.0, [=](cudaStream_t st) {
+      auto& lops = lane ? e->ops2 : e->ops;
+      lops.insert(lops.begin(), b200_ncsnpp::Op{6, 0.0, [=](cudaStream_t st) {
         return cudaMemsetAsync(sb, 0, (size_t)sn, st) == cudaSuccess ? 0 : (set_error("stats memset failed"), 1);
       }});
     }
@@ -781,11 +813,31 @@ int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* 
   return launch_pack_weight(src, dst, 1, p.O, p.I, 1, p.O, 0, p.round, st);
 }
 
+namespace {
+// Lane split of a batch: two halves when the batch is large enough for every launch of a half to fill the GPU,
+// one lane otherwise (and always one with keep_activations, whose taps address whole-batch tensors).
+// B200_LANES=1 forces a single lane.
+int lane0_images(const b200_ncsnpp* h, int batch) {
+  static const int lanes_env = [] { const char* v = getenv("B200_LANES"); return v ? atoi(v) : 2; }();
+  if (lanes_env < 2 || h->cfg.keep_activations || batch < 128) return batch;
+  return (batch + 1) / 2;
+}
+long long lane_bytes(b200_ncsnpp* h, int images, long long* arena_out) {
+  Builder b(h, images, nullptr, true);
+  if (b.build()) return -1;
+  const long long a = (b.arena.high_water() + 1023) & ~1023LL;
+  if (arena_out) *arena_out = a;
+  return a + ((b.stats_top + 1023) & ~1023LL);
+}
+}  // namespace
+
 long long b200_ncsnpp_workspace_bytes(b200_ncsnpp_t* h, int batch) {
   if (!h || batch <= 0) return -1;
-  Builder b(h, batch, nullptr, true);
-  if (b.build()) return -1;
-  return ((b.arena.high_water() + 1023) & ~1023LL) + b.stats_top + 2048;   // + slack to align any caller pointer to 1024 B
+  const int b0 = lane0_images(h, batch);
+  long long total = lane_bytes(h, b0, nullptr);
+  if (total < 0) return -1;
+  if (b0 < batch) { const long long t1 = lane_bytes(h, batch - b0, nullptr); if (t1 < 0) return -1; total += t1; }
+  return total + 2048;   // + slack to align any caller pointer to 1024 B
 }
 
 int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long ws_bytes) {
@@ -795,23 +847,62 @@ int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long 
   B200_REQUIRE(need >= 0, "bind_workspace: planning failed: %s", last_error());
   B200_REQUIRE(ws_bytes >= need, "bind_workspace: workspace too small (%lld < %lld bytes)", ws_bytes, need);
   for (auto* p : h->tcplans) tc_gemm_plan_destroy(p);
-  h->tcplans.clear(); h->ops.clear(); h->taps.clear(); h->launches = 0;
+  h->tcplans.clear(); h->ops.clear(); h->ops2.clear(); h->taps.clear(); h->launches = 0;
   h->B = batch; h->ws_bytes = ws_bytes;
   h->ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
-  Builder dry(h, batch, nullptr, true);
-  if (int r = dry.build()) return r;
-  Builder b(h, batch, h->ws, false);
-  b.stats_base = h->ws + ((dry.arena.high_water() + 1023) & ~1023LL);   // quad sums live after the activation arena
-  if (int r = b.build()) { h->ops.clear(); return r; }
+  h->B0 = lane0_images(h, batch);
+  char* base = h->ws;
+  for (int lane = 0; lane < (h->B0 < batch ? 2 : 1); ++lane) {
+    const int images = lane ? batch - h->B0 : h->B0;
+    long long arena_bytes = 0;
+    const long long lb = lane_bytes(h, images, &arena_bytes);
+    if (lb < 0) return 1;
+    Builder b(h, images, base, false, lane);
+    b.stats_base = base + arena_bytes;   // quad sums live after the lane's activation arena
+    if (int r = b.build()) { h->ops.clear(); h->ops2.clear(); return r; }
+    base += lb;
+  }
+  if (!h->ops2.empty() && !h->lane_stream) {
+    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking));
+    B200_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    B200_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   return 0;
 }
+
+namespace {
+void set_call_args(b200_ncsnpp* h, const float* x, const float* labels, int uniform, float* out) {
+  h->in_x = x; h->in_labels = labels; h->out = out; h->uniform = uniform;
+  const long long per_img = (long long)h->cfg.num_channels * h->cfg.image_size * h->cfg.image_size;
+  h->in_x_l[0] = x; h->in_labels_l[0] = labels; h->out_l[0] = out;
+  h->in_x_l[1] = x + h->B0 * per_img; h->in_labels_l[1] = uniform ? labels : labels + h->B0; h->out_l[1] = out + h->B0 * per_img;
+}
+}  // namespace
 
 int b200_ncsnpp_forward(b200_ncsnpp_t* h, const float* x, const float* labels, int uniform, float* out, void* stream) {
   B200_REQUIRE(h && x && labels && out, "forward: null argument");
   B200_REQUIRE(!h->ops.empty(), "forward: no plan bound (call b200_ncsnpp_bind_workspace)");
-  h->in_x = x; h->in_labels = labels; h->out = out; h->uniform = uniform;
+  set_call_args(h, x, labels, uniform, out);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (auto& o : h->ops) if (int r = o.fn(st)) return r;
+  if (h->ops2.empty()) {
+    for (auto& o : h->ops) if (int r = o.fn(st)) return r;
+    return 0;
+  }
+  // fork: lane 1 runs on the engine's side stream, ordered after everything already queued on `st`
+  // (event record/wait pairs are also what stream capture turns into parallel graph branches)
+  B200_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
+  B200_CHECK_CUDA(cudaStreamWaitEvent(h->lane_stream, h->ev_fork, 0));
+  const size_t n = std::max(h->ops.size(), h->ops2.size());
+  int rc = 0;
+  for (size_t i = 0; i < n && !rc; ++i) {       // interleaved issue so eager (non-graph) launches overlap too
+    if (i < h->ops.size()) rc = h->ops[i].fn(st);
+    if (!rc && i < h->ops2.size()) rc = h->ops2[i].fn(h->lane_stream);
+  }
+  // join (also on failure, so a capture in progress is left well-formed)
+  const cudaError_t e1 = cudaEventRecord(h->ev_join, h->lane_stream);
+  const cudaError_t e2 = cudaStreamWaitEvent(st, h->ev_join, 0);
+  if (rc) return rc;
+  B200_CHECK_CUDA(e1); B200_CHECK_CUDA(e2);
   return 0;
 }
 
@@ -819,25 +910,29 @@ int b200_ncsnpp_profile_forward(b200_ncsnpp_t* h, const float* x, const float* l
                                 void* stream, float ms_by_kind[8], double flops_by_kind[8], long long ops_by_kind[8]) {
   B200_REQUIRE(h && x && labels && out && ms_by_kind, "profile_forward: null argument");
   B200_REQUIRE(!h->ops.empty(), "profile_forward: no plan bound");
-  h->in_x = x; h->in_labels = labels; h->out = out; h->uniform = uniform;
+  set_call_args(h, x, labels, uniform, out);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int k = 0; k < 8; ++k) { ms_by_kind[k] = 0.f; if (flops_by_kind) flops_by_kind[k] = 0.0; if (ops_by_kind) ops_by_kind[k] = 0; }
-  std::vector<cudaEvent_t> ev(h->ops.size() + 1);
+  // both lanes serially on ONE stream: each launch is timed alone (no overlap), which is what a per-kernel roofline needs
+  std::vector<const b200_ncsnpp::Op*> all;
+  for (auto& o : h->ops) all.push_back(&o);
+  for (auto& o : h->ops2) all.push_back(&o);
+  std::vector<cudaEvent_t> ev(all.size() + 1);
   for (auto& e : ev) B200_CHECK_CUDA(cudaEventCreate(&e));
   int rc = 0;
   B200_CHECK_CUDA(cudaEventRecord(ev[0], st));
-  for (size_t i = 0; i < h->ops.size() && !rc; ++i) {
-    rc = h->ops[i].fn(st);
+  for (size_t i = 0; i < all.size() && !rc; ++i) {
+    rc = all[i]->fn(st);
     cudaEventRecord(ev[i + 1], st);
   }
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("profile_forward: stream sync failed"); rc = 1; }
   if (!rc) {
-    for (size_t i = 0; i < h->ops.size(); ++i) {
+    for (size_t i = 0; i < all.size(); ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-      const int k = h->ops[i].kind & 7;
+      const int k = all[i]->kind & 7;
       ms_by_kind[k] += ms;
-      if (flops_by_kind) flops_by_kind[k] += h->ops[i].flops;
+      if (flops_by_kind) flops_by_kind[k] += all[i]->flops;
       if (ops_by_kind) ops_by_kind[k] += 1;
     }
   }

@@ -41,8 +41,10 @@ constexpr int A_STAGE_BYTES = BM * BKE * 4;   // 16 KiB
 
 struct TcParams {
   CUtensorMap tmA1, tmA2, tmW, tmOut, tmRes;
+  CUtensorMap tmA3, tmA4, tmW2;            // optional extra 1x1 K phase (fused skip projection): out += [A3|A4] W2^T
   int conv, H, W, taps, pad, S, stride;   // H, W: OUTPUT spatial size; S = filter width (3 or 1)
   int kchunks1, kchunks2, C1;
+  int kchunks3, kchunks4, C3;              // extra phase: channel chunks of its (two-source) input
   int N_total, tiles_n;
   int nbatch, tiles_m_per_batch, M_per_batch;
   int a_batch_rows, w_batch_rows;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kiters = (p.kchunks1 + p.kchunks2) * p.taps;
+  const int kiters = (p.kchunks1 + p.kchunks2) * p.taps + p.kchunks3 + p.kchunks4;
   const int HW = p.H * p.W;
 
   if (warp == 0 && lane == 0) {
@@ -301,13 +303,16 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
         const long long p1 = p0 + 128;
         img1 = (int)(p1 / HW); h1 = (int)(p1 % HW) / p.W; w1 = (int)(p1 % HW) % p.W;
       }
-      for (int src = 0; src < 2; ++src) {
-        const int nch = src ? p.kchunks2 : p.kchunks1;
+      // sources 0,1: the (two-source) filter input, all taps; sources 2,3: the extra 1x1 phase (centre tap, own weights)
+      for (int src = 0; src < 4; ++src) {
+        const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
         if (nch == 0) continue;
-        const CUtensorMap* tmA = src ? &p.tmA2 : &p.tmA1;
-        const int wcol0 = src ? p.C1 : 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
+        const CUtensorMap* tmA = src == 0 ? &p.tmA1 : src == 1 ? &p.tmA2 : src == 2 ? &p.tmA3 : &p.tmA4;
+        const CUtensorMap* tmW = src < 2 ? &p.tmW : &p.tmW2;
+        const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
+        const int ntaps = src < 2 ? p.taps : 1;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
           for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -315,13 +320,13 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             if (p.swap) {
               // first 16 KiB: 128 output channels x 32 k of W (UMMA A); next 32 KiB: 256 pixels x 32 k (UMMA B)
-              tma_load_2d(&p.tmW, sa, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+              tma_load_2d(tmW, sa, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
               tma_load_4d(tmA, sb, &full_bar[stage], kc * BKE, w0 + dw, h0 + dh, img0);
               tma_load_4d(tmA, sb + A_STAGE_BYTES, &full_bar[stage], kc * BKE, w1 + dw, h1 + dh, img1);
             } else {
               if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
               else tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, arow0, 0, 0);
-              tma_load_2d(&p.tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+              tma_load_2d(tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -689,6 +694,10 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
     if (d.nbatch > 1 && (d.M_per_batch % BM)) return fail("batched gemm needs M_per_batch % 128 == 0");
     if (d.a_ld % 4) return fail("A row pitch must be a multiple of 4 floats");
   }
+  if (d.a3) {
+    if (!d.conv || d.stride == 2 || !d.w2) return fail("extra 1x1 phase needs a stride-1 convolution and its weights");
+    if (d.C3 % BKE || d.C3 <= 0 || (d.a4 && d.C4 % BKE)) return fail("extra-phase channel counts must be multiples of 32");
+  }
   if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
   if (d.qstats && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("quad stats need rows_per_img % 32 == 0 or == 16");
   if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 floats");
@@ -712,8 +721,9 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     static const bool allow_swap = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '0'); }();
     const int req = d.epi_mode < 0 ? tc_gemm_default_epi_mode() : d.epi_mode;   // 0 direct, 1 staged, 2 auto
     const long long Mtot = (long long)d.nimg * d.H * d.W;
-    // B200_TC_SWAP=2 (experiment): also swap 1x1 convolutions with 256-multiple channel counts (output-bound launches)
-    static const bool swap_1x1 = [] { const char* v = getenv("B200_TC_SWAP"); return v && v[0] == '2'; }();
+    // 1x1 convolutions with 256-multiple channel counts are output-bound launches: the swapped form's coalesced
+    // epilogue measured 12-20 % faster (profiles/r01_c11_exp.log).  B200_TC_SWAP=1 restricts swapping to 128-channel outputs.
+    static const bool swap_1x1 = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '1'); }();
     const bool can_swap = allow_swap && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1)) && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
     // auto (default): direct stores with the deepest operand ring (measured best for every launch shape,
@@ -775,12 +785,39 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     }
   }
   if (!d.a2) p.tmA2 = p.tmA1;
+  p.tmA3 = p.tmA1; p.tmA4 = p.tmA1;
+  if (d.a3) {
+    // extra 1x1 phase: same pixel box as the main input (stride 1, same spatial size), its own channel counts
+    const int HW = d.H * d.W;
+    uint32_t box[4];
+    if (HW >= BM) { box[1] = std::min(d.W, BM); box[2] = BM / box[1]; box[3] = 1; }
+    else { box[1] = d.W; box[2] = d.H; box[3] = BM / HW; }
+    box[0] = BKE;
+    for (int s = 0; s < 2; ++s) {
+      const float* base = s ? d.a4 : d.a3;
+      const int C = s ? d.C4 : d.C3;
+      if (!base) continue;
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.nimg};
+      uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)d.W * C * 4, (uint64_t)d.H * d.W * C * 4};
+      rc = encode_map(s ? &p.tmA4 : &p.tmA3, base, 4, dims, str, box);
+      if (rc) { delete pl; return rc; }
+    }
+    p.kchunks3 = d.C3 / BKE; p.kchunks4 = d.a4 ? d.C4 / BKE : 0; p.C3 = d.C3;
+  }
   {
     uint64_t dims[2] = {(uint64_t)d.K_total, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * 4};
     uint32_t box[2] = {BKE, (uint32_t)(pl->two_cta ? pl->bn / 2 : (p.swap ? 128 : pl->bn))};
     rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
     if (rc) { delete pl; return rc; }
+    p.tmW2 = p.tmW;
+    if (d.a3) {
+      const uint64_t K3 = (uint64_t)d.C3 + (d.a4 ? d.C4 : 0);
+      uint64_t dims2[2] = {K3, (uint64_t)d.N_total};
+      uint64_t str2[1] = {K3 * 4};
+      rc = encode_map(&p.tmW2, d.w2, 2, dims2, str2, box);
+      if (rc) { delete pl; return rc; }
+    }
   }
   if (p.epi_mode == 1) {
     const uint64_t out_rows = (uint64_t)p.nbatch * (uint64_t)p.M_per_batch;

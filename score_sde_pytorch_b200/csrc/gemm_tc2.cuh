@@ -92,7 +92,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kiters = (p.kchunks1 + p.kchunks2) * p.taps;
+  const int kiters = (p.kchunks1 + p.kchunks2) * p.taps + p.kchunks3 + p.kchunks4;
   const int HW = p.H * p.W;
   const long long tiles_m_total = (long long)p.nbatch * p.tiles_m_per_batch;
   const long long pairs_m = (tiles_m_total + 1) / 2;
@@ -118,13 +118,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
       const int arow0 = (mg >= tiles_m_total) ? (1 << 30) : b * p.a_batch_rows + mt * BM;
       const int bsh = (int)((pair / p.tiles_n) * 2 / p.tiles_m_per_batch);   // batch of the pair (both CTAs share it)
       const int wrow0 = bsh * p.w_batch_rows + nt * BN + (int)rank * (BN / 2);   // this CTA's half of the W tile
-      for (int src = 0; src < 2; ++src) {
-        const int nch = src ? p.kchunks2 : p.kchunks1;
+      for (int src = 0; src < 4; ++src) {                        // 2,3: the extra 1x1 phase (see gemm_tc_kernel)
+        const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
         if (nch == 0) continue;
-        const CUtensorMap* tmA = src ? &p.tmA2 : &p.tmA1;
-        const int wcol0 = src ? p.C1 : 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
+        const CUtensorMap* tmA = src == 0 ? &p.tmA1 : src == 1 ? &p.tmA2 : src == 2 ? &p.tmA3 : &p.tmA4;
+        const CUtensorMap* tmW = src < 2 ? &p.tmW : &p.tmW2;
+        const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
+        const int ntaps = src < 2 ? p.taps : 1;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
           for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);            // own smem slot released by the pair's MMA commit
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -133,7 +135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);     // bytes of BOTH CTAs land on this barrier
             if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
             else tma2_load_4d(tmA, sa, lead_full, kc * BKE, arow0, 0, 0);
-            tma2_load_2d(&p.tmW, sb, lead_full, wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            tma2_load_2d(tmW, sb, lead_full, wcol0 + kc * BKE, wrow0 + tap * p.N_total);
             if (!leader) mbar_arrive_cluster(lead_full);                          // second of the barrier's two arrivals
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }

@@ -77,6 +77,9 @@ struct TcGemmDesc {
   long long w_ld;           // row pitch of W in elements (0 = K_total)
   int w_batch_rows;         // rows to advance per batch item (0 = shared)
   int nbatch; int M_per_batch;   // gemm: rows of output per batch item; conv: nbatch=1, M=nimg*H*W
+  // optional extra 1x1 phase accumulated into the same tile (a resblock's skip projection fused into its second
+  // 3x3 convolution): out += [a3 | a4] w2^T, w2 = [N_total][C3 + C4]; same spatial size as the output, stride 1
+  const float* a3; int C3; const float* a4; int C4; const float* w2;
   int epi_mode;             // 0 direct stores, 1 smem-staged TMA store, -1 = library default
   int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)

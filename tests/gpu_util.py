@@ -47,6 +47,16 @@ def conv_nhwc(x1, x2, wp, bias, cout, ksize, rowvec=None, rowvec_ld=0, residual=
   return out
 
 
+def conv_skip_nhwc(x, s1, s2, wp, bias, wskip, bias_skip, cout, residual=None, scale=1.0, round_out=False):
+  B, H, W, C = x.shape
+  out = torch.empty(B, H, W, cout, device=x.device, dtype=torch.float32)
+  _lib.call('b200_conv_skip_nhwc_f32', _lib.ptr(x), C, _lib.ptr(s1), s1.shape[3], _lib.ptr(s2),
+            s2.shape[3] if s2 is not None else 0, B, H, W, _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(wskip),
+            _lib.ptr(bias_skip), cout, _lib.ptr(residual), float(scale), int(round_out), _lib.ptr(out),
+            _lib.stream_ptr(x.device))
+  return out
+
+
 def gemm_nt(a, w, nbatch, m, n, k, lda=None, ldw=None, a_batch_rows=None, w_batch_rows=None, bias=None,
             round_out=False, impl=0):
   lda = k if lda is None else lda

@@ -66,6 +66,43 @@ def test_tcgen05_conv_matches_cuda_core_conv(dev, case):
   assert torch.equal(y2, rt(y))
 
 
+SKIP_CASES = [
+    dict(B=2, H=16, W=16, C=256, S1=256, S2=256, Cout=256),     # up-path block: concat skip input, single-CTA tiles
+    dict(B=160, H=16, W=16, C=256, S1=256, S2=128, Cout=256),   # enough tiles for the CTA-pair kernel
+    dict(B=2, H=32, W=32, C=128, S1=256, S2=128, Cout=128),     # swapped-operand form (128 output channels)
+    dict(B=3, H=4, W=4, C=256, S1=256, S2=0, Cout=256),         # partial tile
+    dict(B=4, H=8, W=8, C=256, S1=128, S2=0, Cout=256),         # level change 128 -> 256
+]
+
+
+@pytest.mark.parametrize('case', SKIP_CASES, ids=lambda c: 'B{B}_{H}x{W}_{C}|{S1}+{S2}->{Cout}'.format(**c))
+def test_tcgen05_conv_with_fused_skip_projection(dev, case):
+  """Resblock tail (layerspp.py:268-274): (Conv_1(h) + Conv_2(x)) / sqrt(2) as ONE contraction whose K loop
+  appends the 1x1 projection of the (two-source) block input to the nine taps of the 3x3 filter."""
+  import gpu_util
+  B, H, W, C, S1, S2, Cout = (case[x] for x in ('B', 'H', 'W', 'C', 'S1', 'S2', 'Cout'))
+  torch.manual_seed(16)
+  rt = gpu_util.round_tf32
+  x = rt(torch.randn(B, H, W, C, device=dev))
+  s1 = rt(torch.randn(B, H, W, S1, device=dev))
+  s2 = rt(torch.randn(B, H, W, S2, device=dev)) if S2 else None
+  w = rt(torch.randn(Cout, C, 3, 3, device=dev) / np.sqrt(C * 9))
+  ws = rt(torch.randn(Cout, S1 + S2, device=dev) / np.sqrt(S1 + S2))
+  bias, bias_s = torch.randn(Cout, device=dev), torch.randn(Cout, device=dev)
+  wp = gpu_util.pack_conv_weight(w)
+  sc = 0.7071067690849304
+  y = gpu_util.conv_skip_nhwc(x, s1, s2, wp, bias, ws.contiguous(), bias_s, Cout, scale=sc)
+  torch.cuda.synchronize()
+  sx = s1 if s2 is None else torch.cat([s1, s2], 3)
+  ref = (F.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1) + sx @ ws.t() + bias_s) * sc
+  assert torch.allclose(y, ref, rtol=2e-4, atol=3e-4), (y - ref).abs().max().item()
+  # equals the unfused pair of launches (1x1 projection, then 3x3 with a residual) up to summation order
+  wsp = gpu_util.pack_conv_weight(ws.reshape(Cout, S1 + S2, 1, 1))
+  s = gpu_util.conv_nhwc(s1, s2, wsp, bias_s, Cout, 1, impl=1)
+  y2 = gpu_util.conv_nhwc(x, None, wp, bias, Cout, 3, residual=s, scale=sc, impl=1)
+  assert torch.allclose(y, y2, rtol=1e-5, atol=2e-5), (y - y2).abs().max().item()
+
+
 def test_tcgen05_batched_gemm_attention_shapes(dev):
   import gpu_util
   rt = gpu_util.round_tf32
