@@ -127,6 +127,13 @@ B200_API long long b200_ncsnpp_launches_per_forward(const b200_ncsnpp_t* h);
 B200_API int b200_ncsnpp_profile_forward(b200_ncsnpp_t* h, const float* x_nchw, const float* labels,
                                          int labels_uniform, float* out_nchw, void* stream,
                                          float ms_by_kind[8], double flops_by_kind[8], long long ops_by_kind[8]);
+/* Per-op view of the bound plan (both half-batch lanes, lane 0 first): a shape label, the kind index used by
+ * b200_ncsnpp_profile_forward, the algorithmic FLOPs, and one CUDA-event-timed duration per op (run serially). */
+B200_API long long b200_ncsnpp_num_ops(const b200_ncsnpp_t* h);
+B200_API int b200_ncsnpp_op_info(const b200_ncsnpp_t* h, long long index, char* name, int name_cap, int* kind,
+                                 double* flops);
+B200_API int b200_ncsnpp_profile_ops(b200_ncsnpp_t* h, const float* x, const float* labels, int labels_uniform,
+                                     float* out, void* stream, float* ms_per_op, long long cap);
 
 /* ---- predictor–corrector loop --------------------------------------------------
  * Replaces the body of pc_sampler (sampling.py:390-409) with

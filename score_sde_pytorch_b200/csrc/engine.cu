@@ -102,7 +102,7 @@ struct b200_ncsnpp {
   float fir2d[64]; int firn = 0;
   // plan
   int B = 0; char* ws = nullptr; long long ws_bytes = 0;
-  struct Op { int kind; double flops; std::function<int(cudaStream_t)> fn; };
+  struct Op { int kind; double flops; std::function<int(cudaStream_t)> fn; std::string name; };
   std::vector<Op> ops;
   // Two half-batch "lanes" (ops2 = the second half's plan, empty when the batch is not split).  The lanes are
   // independent within one network evaluation, so forward() issues them on two streams: while one lane's
@@ -311,6 +311,10 @@ struct Builder {
   char* stats_base = nullptr; long long stats_top = 0;   // bump region for GroupNorm quad sums, zeroed once per forward
   bool fused_stats = false;
   int lane = 0;                                // which half-batch plan this builder fills (ops or ops2)
+  std::string next_name;                       // label of the next op (shape summary for the per-op profile)
+  void name(const char* fmt, ...) {
+    char buf[160]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap); next_name = buf;
+  }
   Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_, int lane_ = 0) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0), lane(lane_) {
     const char* v = getenv("B200_FUSED_GN_STATS");
     fused_stats = (e_->cfg.precision == 0) && !(v && v[0] == '0');
@@ -341,7 +345,9 @@ struct Builder {
   void op(int launches, std::function<int(cudaStream_t)> f, int kind = 6, double flops = 0.0) {
     if (dry) return;
     e->launches += launches;
-    (lane ? e->ops2 : e->ops).push_back({kind, flops, std::move(f)});
+    static const char* kind_names[] = {"tcgen05", "cuda-core contraction", "groupnorm", "fir", "softmax", "time embedding", "misc", "?"};
+    (lane ? e->ops2 : e->ops).push_back({kind, flops, std::move(f), next_name.empty() ? std::string(kind_names[kind & 7]) : next_name});
+    next_name.clear();
   }
 
   // make sure tensor t has quad sums: produced by its tcgen05 epilogue, else by one streaming pass
@@ -349,6 +355,7 @@ struct Builder {
     if (t.qs || !t.p) return;
     t.qs = qalloc(t.C);
     const Tensor tt = t; const int Bc = B;
+    name("gn_quad_stats %d @%d", t.C, t.H);
     op(1, [=](cudaStream_t st) { return launch_gn_quad_stats(tt.p, tt.C, Bc, tt.H * tt.W, tt.qs, st); }, 2);
   }
   void gn(Tensor& x1, Tensor& x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
@@ -356,6 +363,7 @@ struct Builder {
     ensure_qs(x1); ensure_qs(x2);
     const float *g = e->W(pgw), *bt = e->W(pgb);
     const Tensor a = x1, b = x2; const int Bc = B;
+    name("gn_apply %d+%d @%d%s%s", x1.C, x2.C, x1.H, act ? " silu" : "", raw ? " +raw" : "");
     op(1, [=](cudaStream_t st) {
       return launch_gn_apply(a.p, a.C, b.p, b.C, a.qs, b.qs, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, st);
     }, 2);
@@ -367,6 +375,7 @@ struct Builder {
     std::vector<float> k(e->firn * e->firn);
     for (size_t i = 0; i < k.size(); ++i) k[i] = e->fir2d[i] * gain;
     const int n = e->firn;
+    name("fir up%d down%d %d @%d", up, down, minor == 1 ? major / B : minor, H);
     op(1, [=](cudaStream_t st) {
       return launch_upfirdn2d(x, k.data(), y, major, H, W, minor, n, n, up, up, down, down, pad0, pad1, pad0, pad1, round, st);
     }, 3);
@@ -404,6 +413,9 @@ struct Builder {
       TcGemmPlan* pl = nullptr;
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
       e->tcplans.push_back(pl);
+      name("conv%s %d+%d->%d @%d%s%s%s [%s]", taps == 9 ? "3x3" : "1x1", a1.C, a2.C, Cout, out.H, stride == 2 ? " s2" : "",
+           x3.p ? " +skipproj" : "", residual ? " +res" : "", tc_gemm_form(pl));
+      if (x3.p) next_name += " " + std::to_string(x3.C + x4.C);
       op(1, [=](cudaStream_t st) {
         if (dense_row >= 0) tc_gemm_set_rowvec_ld(pl, eng->uniform ? 0 : sumC);
         return tc_gemm_launch(pl, st);
@@ -415,6 +427,7 @@ struct Builder {
       s.OH = a1.H; s.OW = a1.W; s.nbatch = B; s.a_batched = 1; s.w = e->W(pw); s.N = Cout;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
       s.epi = ep;
+      name("conv%s %d+%d->%d @%d [cuda-core]", taps == 9 ? "3x3" : "1x1", a1.C, a2.C, Cout, out.H);
       op(1, [=](cudaStream_t st) {
         SimtConv c = s;
         if (dense_row >= 0) c.epi.rowvec_ld = eng->uniform ? 0 : sumC;
@@ -440,6 +453,7 @@ struct Builder {
       TcGemmPlan* pl = nullptr;
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
       e->tcplans.push_back(pl);
+      name("gemm %dx(%dx%dx%d)%s [%s]", nbatch, M, N, K, residual ? " +res" : "", tc_gemm_form(pl));
       op(1, [=](cudaStream_t st) { return tc_gemm_launch(pl, st); }, 0, 2.0 * nbatch * (double)M * N * K);
     } else {
       SimtConv s; memset(&s, 0, sizeof(s));
@@ -537,6 +551,7 @@ struct Builder {
       O = falloc(BT * C, &ob);
       const int rnd = m.tc2 ? 1 : 0;
       if (!dry) { if (int r = launch_attn_small_configure(T, C)) { rc = r; } }
+      name("attn_small T=%d C=%d", T, C);
       op(1, [=](cudaStream_t st) { return launch_attn_small(qkv, O, Bc, T, C, sc, rnd, st); }, 4);
       ffree(qkv, qb);
     } else {
@@ -552,6 +567,7 @@ struct Builder {
       // logits[b][q][k] = q . k   (layerspp.py:82), scaled inside the softmax
       gemm(tc, qk, 2 * C, BT, T, qk + C, 2 * C, BT, T, B, T, T, C, nullptr, nullptr, 0, 1.f, 0, S, T, nullptr, 1 << 30, /*no_pair=*/true);
       ffree(qk, qkb);
+      name("softmax T=%d", T);
       op(1, [=](cudaStream_t st) { return launch_softmax_rows(S, S, (long long)Bc * T, T, sc, tc ? 1 : 0, st); }, 4);
       O = falloc(BT * C, &ob);
       // h[b][q][c] = sum_k P[q][k] v[k][c] + bv[c]   (layerspp.py:86)
@@ -610,6 +626,7 @@ struct Builder {
         // im2col patches [B*R*R][32] (TF32 grid) then one K=32 tcgen05 contraction with the flat-packed weights
         long long pb; float* patches = falloc((long long)B * R * R * 32, &pb);
         const int Bc = B;
+        name("im2col 3x3 %d @%d", ch, R);
         op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, R, R, 1, 1, st); }, 6);
         Tensor pt; pt.p = patches; pt.C = 32; pt.H = R; pt.W = R;      // patches as a 32-channel NHWC image: a 1x1 conv
         conv(true, pt, Tensor(), 1, m.w, m.b, nf, -1, nullptr, 1.f, 0, h0, /*want_stats=*/true);
@@ -660,6 +677,7 @@ struct Builder {
           if (flat) {
             long long pb2; float* patches = falloc((long long)B * h.H * h.W * 32, &pb2);
             const int Bc = B, pc = pyr.C, oh = h.H, ow = h.W;
+            name("im2col 3x3 s2 %d @%d", pc, oh);
             op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(fbuf, patches, Bc, pc, Hp, Hp, oh, ow, 2, 0, st); }, 6);
             Tensor pt; pt.p = patches; pt.C = 32; pt.H = h.H; pt.W = h.W;
             conv(true, pt, Tensor(), 1, mp.w, mp.b, mp.cout, -1, h.p, ps, 0, np, /*want_stats=*/true);
@@ -718,6 +736,7 @@ struct Builder {
       const float *wo = e->W(mo.w), *bo = e->W(mo.b);
       const Tensor ain = a; const int Bc = B;
       if (ch <= 4) {
+        name("conv3x3 %d->%d @%d nchw-out [small-n]", a.C, ch, R);
         op(1, [=](cudaStream_t st) {
           return launch_conv3x3_small_n(ain.p, wo, bo, sbs ? eng->in_labels_l[ln] : nullptr, eng->uniform ? 0 : 1, eng->out_l[ln],
                                         Bc, R, R, ain.C, ch, st);
@@ -936,6 +955,39 @@ int b200_ncsnpp_profile_forward(b200_ncsnpp_t* h, const float* x, const float* l
       if (ops_by_kind) ops_by_kind[k] += 1;
     }
   }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+long long b200_ncsnpp_num_ops(const b200_ncsnpp_t* h) { return h ? (long long)(h->ops.size() + h->ops2.size()) : 0; }
+
+int b200_ncsnpp_op_info(const b200_ncsnpp_t* h, long long index, char* name, int name_cap, int* kind, double* flops) {
+  B200_REQUIRE(h && index >= 0 && index < (long long)(h->ops.size() + h->ops2.size()), "op_info: index out of range");
+  const b200_ncsnpp::Op& o = index < (long long)h->ops.size() ? h->ops[index] : h->ops2[index - h->ops.size()];
+  if (name && name_cap > 0) { strncpy(name, o.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (kind) *kind = o.kind;
+  if (flops) *flops = o.flops;
+  return 0;
+}
+
+int b200_ncsnpp_profile_ops(b200_ncsnpp_t* h, const float* x, const float* labels, int uniform, float* out, void* stream,
+                            float* ms_per_op, long long cap) {
+  B200_REQUIRE(h && x && labels && out && ms_per_op, "profile_ops: null argument");
+  B200_REQUIRE(!h->ops.empty(), "profile_ops: no plan bound");
+  const long long n = (long long)(h->ops.size() + h->ops2.size());
+  B200_REQUIRE(cap >= n, "profile_ops: need room for %lld ops", n);
+  set_call_args(h, x, labels, uniform, out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) B200_CHECK_CUDA(cudaEventCreate(&e));
+  int rc = 0;
+  B200_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  for (long long i = 0; i < n && !rc; ++i) {
+    rc = (i < (long long)h->ops.size() ? h->ops[i] : h->ops2[i - h->ops.size()]).fn(st);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("profile_ops: stream sync failed"); rc = 1; }
+  if (!rc) for (long long i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
   for (auto& e : ev) cudaEventDestroy(e);
   return rc;
 }

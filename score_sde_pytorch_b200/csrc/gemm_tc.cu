@@ -841,6 +841,12 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
 }
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
+const char* tc_gemm_form(const TcGemmPlan* p) {
+  if (p->two_cta) return p->bn == 256 ? "pair256" : "pair128";
+  if (p->prm.swap) return p->prm.epi_mode == 1 ? "swap/staged" : "swap";
+  if (p->prm.epi_mode == 1) return p->bn == 256 ? "single256/staged" : "single128/staged";
+  return p->bn == 256 ? "single256" : "single128";
+}
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
 // B200_TC_EPILOGUE = direct | staged | auto (default).  auto: the smem-staged TMA epilogue where it measured
 // faster (the swapped-operand 128-channel convolutions), direct register->global stores with the deeper

@@ -89,6 +89,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out);
 void tc_gemm_plan_destroy(TcGemmPlan* p);
 int tc_gemm_launch(const TcGemmPlan* p, cudaStream_t st);
 bool tc_gemm_supported(const TcGemmDesc& d, const char** why);
+const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap" (+"/staged")
 
 // ---- pc_update.cu -----------------------------------------------------------
 struct PhiloxMap {          // torch.randn_like's launch geometry for `numel` elements

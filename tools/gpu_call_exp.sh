@@ -11,6 +11,8 @@ run lanes1 B200_LANES=1
 run nofuse B200_FUSE_SKIP=0
 run old B200_LANES=1 B200_FUSE_SKIP=0
 run default2 A=1
+timeout 300 python tools/profile_ops.py --batch 1024 --md gpurun_out/ops_${TAG}.md > /dev/null 2>> $L; echo "profile_ops exit $?" >> $L
+B200_LANES=1 timeout 300 python tools/profile_ops.py --batch 1024 --md gpurun_out/ops_${TAG}_lanes1.md > /dev/null 2>> $L
 grep -v "^$" $L | tail -30
 for f in gpurun_out/bench_${TAG}_*.json; do echo $f; python -c "
 import json
