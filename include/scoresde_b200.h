@@ -77,6 +77,13 @@ B200_API int b200_conv_skip_nhwc_f32(const float* x, int c, const float* s1, int
                                      float scale, int round_tf32, float* out, void* stream);
 B200_API int b200_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int c_out, int c_in, int ksize,
                                        int round_tf32, void* stream);
+/* Fused attention core of AttnBlockpp (layerspp.py:82-91) for T=256 tokens x C=256 channels per image:
+ * out = (softmax(q k^T / sqrt(C)) v + b_v) W3^T + b_3 + x) * out_scale, tcgen05 only.
+ * qk = [nimg*T][2C] (q | k), vT = [nimg][C][T] (v transposed, without b_v), w3 = [C_out][C_in]; all TF32-representable.
+ * qstats (optional, zero-initialised by the caller) receives out's GroupNorm quad sums [nimg][C/4][2]. */
+B200_API int b200_attention_core_f32(const float* qk, const float* vT, const float* w3, const float* bv,
+                                     const float* b3, const float* x, float* out, double* qstats, int nimg,
+                                     int t, int c, float out_scale, void* stream);
 /* batched C[b] = A[b] (M x K, pitch lda) * W[b]^T (N x K, pitch ldw), row-major out pitch ldo. */
 B200_API int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const float* w, long long ldw,
                               int w_batch_rows, int nbatch, int m, int n, int k, const float* bias,

@@ -135,6 +135,20 @@ int b200_conv_skip_nhwc_f32(const float* x, int c, const float* s1, int cs1, con
   return r;
 }
 
+int b200_attention_core_f32(const float* qk, const float* vT, const float* w3, const float* bv, const float* b3,
+                            const float* x, float* out, double* qstats, int nimg, int t, int c, float out_scale,
+                            void* stream) {
+  B200_REQUIRE(tc_attn_supported(t, c), "attention_core: only T=256, C=256 is implemented (got T=%d C=%d)", t, c);
+  TcAttnDesc d; memset(&d, 0, sizeof(d));
+  d.qk = qk; d.vT = vT; d.w3 = w3; d.bv = bv; d.b3 = b3; d.x = x; d.out = out; d.qstats = qstats;
+  d.nimg = nimg; d.T = t; d.C = c; d.out_scale = out_scale;
+  TcAttnPlan* pl = nullptr;
+  if (int r = tc_attn_plan_create(d, &pl)) return r;
+  const int r = tc_attn_launch(pl, static_cast<cudaStream_t>(stream));
+  tc_attn_plan_destroy(pl);
+  return r;
+}
+
 int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const float* w, long long ldw, int w_batch_rows,
                      int nbatch, int m, int n, int k, const float* bias, int round_tf32, float* out, long long ldo,
                      int impl, void* stream) {

@@ -1,0 +1,250 @@
+// Fused attention core for the 16x16-resolution AttnBlockpp (layerspp.py:74-91) with T = 256 tokens and
+// C = 256 channels per image: logits, softmax, P.V, the output projection NIN_3, the residual add, the 1/sqrt(2)
+// rescale and the next GroupNorm's quad sums in ONE kernel, so the [T,T] logits / probabilities and the
+// attention output never touch HBM.  Included by gemm_tc.cu inside its anonymous namespace (PTX wrappers,
+// descriptors, quad_stats helper).
+//
+// One tile = 128 query rows of one image (two tiles per image); persistent CTAs, 384 threads:
+//   warp 0 lane 0  TMA producer: 24 loads per tile through a 2-stage ring of 48 KB slots
+//                  (8 x {Q 128x32 + K 256x32}, 8 x V^T 256x32 keys, 8 x W3 256x32), running ahead across phases;
+//   warp 1 lane 0  MMA issuer, three chained contractions per tile, all M=128 x N=256 x K=256 (tf32):
+//                    S = Q K^T           -> TMEM columns [0,256)
+//                    O = E V             -> TMEM columns [256,512)   (A operand = E from shared memory)
+//                    Y = O' W3^T         -> TMEM columns [256,512)   (A operand = O' from shared memory)
+//   warp 2         TMEM allocation (all 512 columns);
+//   warps 4..11    two warps per TMEM lane quarter, each owning 128 of the 256 columns of its rows:
+//                    softmax : row max (exchange with the partner warp), E = exp((s-max)/sqrt(C)) rounded to TF32
+//                              into the 128 KB K-major SWIZZLE_128B operand buffer, row sums kept in registers;
+//                    convert : O' = O / rowsum + b_v (softmax rows sum to 1, so V's bias is added after P.V),
+//                              rounded to TF32 into the same operand buffer (E is dead once O is complete);
+//                    final   : (Y + b_3 + x) / sqrt(2), GroupNorm quad sums, direct 128-bit stores.
+// The issuer starts the next tile's S while the epilogue warps are still in `final` (S columns are free since
+// the softmax), so only the softmax and convert phases expose tensor-pipe bubbles.
+//
+// Deferred normalisation: the reference rounds nothing; here E (not E/rowsum) is the TF32 operand and the
+// division happens in fp32 on the accumulator - one rounding per operand, as everywhere else in the engine.
+
+constexpr int AT_T = 256, AT_C = 256;
+struct AttnSmem {
+  static constexpr int PBUF = 0;                                   // 8 K-blocks x (128 rows x 128 B)
+  static constexpr int RING = 128 * 1024;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + 256 * BKE * 4;   // 16 KB + 32 KB
+  static constexpr int STAGES = 2;
+  static constexpr int XCHG = RING + STAGES * STAGE_BYTES;          // [2 halves][128 rows] floats
+  static constexpr int BAR_OFFSET = XCHG + 1024;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
+};
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmVT, tmW3;
+  const float* bv;          // [C] bias of NIN_2 (added after P.V)
+  const float* b3;          // [C] bias of NIN_3
+  const float* x;           // [B*T][C] block input (residual)
+  float* out;               // [B*T][C]
+  double* qstats;           // optional [B][C/4][2]
+  float logit_scale;        // C^-0.5 * log2(e)
+  float out_scale;          // 1/sqrt(2) with skip_rescale, else 1
+  int nimg;
+};
+
+// address of 16-byte chunk `c4` (0..7) of row r in K-block kb of the swizzled operand buffer
+__device__ __forceinline__ float4* pbuf_chunk(uint8_t* pbuf, int kb, int r, int c4) {
+  return reinterpret_cast<float4*>(pbuf + kb * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+__global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  using L = AttnSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* pbuf = smem + L::PBUF;
+  uint8_t* ring = smem + L::RING;
+  float* xchg = reinterpret_cast<float*>(smem + L::XCHG);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* s_full = empty_bar + L::STAGES;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* o_full = p_ready + 1;
+  uint64_t* o_ready = o_full + 1;
+  uint64_t* y_full = o_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(y_full, 1);
+    mbar_init(p_ready, 8); mbar_init(o_ready, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long total_tiles = 2LL * p.nimg;
+  constexpr int KB = AT_C / BKE;   // 8 K blocks in every phase (C = T = 256)
+
+  if (warp == 0 && lane == 0) {
+    // ======================= TMA producer =======================
+    uint32_t stage = 0, phase = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = (int)(tile >> 1), qh = (int)(tile & 1);
+      for (int ph = 0; ph < 3; ++ph) {
+        for (int kc = 0; kc < KB; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (ph == 0) {
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            tma_load_2d(&p.tmQ, sa, &full_bar[stage], kc * BKE, b * AT_T + qh * BM);
+            tma_load_2d(&p.tmK, sb, &full_bar[stage], AT_C + kc * BKE, b * AT_T);
+          } else if (ph == 1) {
+            mbar_expect_tx(&full_bar[stage], 256 * BKE * 4);
+            tma_load_2d(&p.tmVT, sb, &full_bar[stage], kc * BKE, b * AT_C);
+          } else {
+            mbar_expect_tx(&full_bar[stage], 256 * BKE * 4);
+            tma_load_2d(&p.tmW3, sb, &full_bar[stage], kc * BKE, 0);
+          }
+          if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = make_idesc<256>();
+    uint32_t stage = 0, phase = 0, tpar = 0;
+    const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 256;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tpar ^= 1) {
+      for (int ph = 0; ph < 3; ++ph) {
+        if (ph == 1) { mbar_wait(p_ready, tpar); tc_fence_after(); }   // E is in shared memory
+        if (ph == 2) { mbar_wait(o_ready, tpar); tc_fence_after(); }   // O' is in shared memory, O columns drained
+        const uint32_t d_tmem = ph == 0 ? s_tmem : o_tmem;
+        for (int kc = 0; kc < KB; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * L::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(ph == 0 ? sa : smem_u32(pbuf + kc * 16384));
+          const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BKE / UMMA_K; ++k) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(ph == 0 ? s_full : ph == 1 ? o_full : y_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= softmax / convert / final =======================
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const int r = q * 32 + lane;                       // query row of the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tpar = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tpar ^= 1) {
+      const int b = (int)(tile >> 1), qh = (int)(tile & 1);
+      const long long gm = (long long)b * AT_T + qh * BM + r;
+      // ---- softmax over this row's 256 logits (this thread: columns half*128 .. +128) ----
+      mbar_wait(s_full, tpar);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + half * 128 + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      xchg[half * 128 + r] = mx;
+      pair_barrier(q);
+      mx = fmaxf(mx, xchg[(half ^ 1) * 128 + r]);
+      const float moff = mx * p.logit_scale;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + half * 128 + j * 32, v);
+        const int kb = half * 4 + j;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 e;
+          e.x = round_tf32(exp2f(fmaf(__uint_as_float(v[c]), p.logit_scale, -moff)));
+          e.y = round_tf32(exp2f(fmaf(__uint_as_float(v[c + 1]), p.logit_scale, -moff)));
+          e.z = round_tf32(exp2f(fmaf(__uint_as_float(v[c + 2]), p.logit_scale, -moff)));
+          e.w = round_tf32(exp2f(fmaf(__uint_as_float(v[c + 3]), p.logit_scale, -moff)));
+          sum += (e.x + e.y) + (e.z + e.w);
+          *pbuf_chunk(pbuf, kb, r, c >> 2) = e;
+        }
+      }
+      pair_barrier(q);                                  // the partner has read this thread's max: the slot is free
+      xchg[half * 128 + r] = sum;
+      fence_async_smem();                               // E (generic-proxy writes) -> visible to the tensor core
+      pair_barrier(q);
+      sum += xchg[(half ^ 1) * 128 + r];
+      const float inv = 1.0f / sum;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // ---- O' = O / rowsum + b_v -> operand buffer (K = channel) ----
+      mbar_wait(o_full, tpar);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + 256 + half * 128 + j * 32, v);
+        const int kb = half * 4 + j;
+        const float* bvp = p.bv + kb * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(bvp + c));
+          float4 o;
+          o.x = round_tf32(fmaf(__uint_as_float(v[c]), inv, t.x));
+          o.y = round_tf32(fmaf(__uint_as_float(v[c + 1]), inv, t.y));
+          o.z = round_tf32(fmaf(__uint_as_float(v[c + 2]), inv, t.z));
+          o.w = round_tf32(fmaf(__uint_as_float(v[c + 3]), inv, t.w));
+          *pbuf_chunk(pbuf, kb, r, c >> 2) = o;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_ready);
+      // ---- final: (Y + b_3 + x) * out_scale, quad sums, store ----
+      mbar_wait(y_full, tpar);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + 256 + half * 128 + j * 32, v);
+        const int n0 = half * 128 + j * 32;
+        float st[16];
+        float* dst = p.out + gm * AT_C + n0;
+        const float* res = p.x + gm * AT_C + n0;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.b3 + n0 + c));
+          const float4 xr = __ldg(reinterpret_cast<const float4*>(res + c));
+          float4 o;
+          o.x = (__uint_as_float(v[c]) + t.x + xr.x) * p.out_scale;
+          o.y = (__uint_as_float(v[c + 1]) + t.y + xr.y) * p.out_scale;
+          o.z = (__uint_as_float(v[c + 2]) + t.z + xr.z) * p.out_scale;
+          o.w = (__uint_as_float(v[c + 3]) + t.w + xr.w) * p.out_scale;
+          *reinterpret_cast<float4*>(dst + c) = o;
+          st[c >> 2] = (o.x + o.y) + (o.z + o.w);
+          st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+        }
+        if (p.qstats) quad_stats_commit_raw(p.qstats, AT_C, AT_T, st, b, true, n0, lane);
+      }
+      tc_fence_before();   // orders these TMEM reads before the p_ready arrival that lets the next tile's E V overwrite O/Y
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}

@@ -113,6 +113,7 @@ struct b200_ncsnpp {
   const float* in_x_l[2] = {nullptr, nullptr}; const float* in_labels_l[2] = {nullptr, nullptr}; float* out_l[2] = {nullptr, nullptr};
 
   std::vector<TcGemmPlan*> tcplans;
+  std::vector<TcAttnPlan*> attnplans;
   std::map<int, Tensor> taps;
   long long launches = 0;
   // per-call arguments read by the closures
@@ -121,6 +122,7 @@ struct b200_ncsnpp {
   const float* W(int pi) const { return wblob + params[pi].off; }
   ~b200_ncsnpp() {
     for (auto* p : tcplans) tc_gemm_plan_destroy(p);
+    for (auto* p : attnplans) tc_attn_plan_destroy(p);
     if (lane_stream) cudaStreamDestroy(lane_stream);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -563,6 +565,25 @@ struct Builder {
       // v^T[b][c][t] = sum_i Wv[c][i] a[b][t][i]   (bias bv is added after the PV product: softmax rows sum to 1)
       gemm(tc, Wqkv + 2LL * C * C, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc, vT, T, nullptr, 1 << 30, /*no_pair=*/true);
       tfree(a);
+      // Fused core (default): logits, softmax, P.V, NIN_3, residual, rescale and quad sums in one kernel; the
+      // [T,T] logits/probabilities and the attention output stay on chip.  B200_FUSED_ATTN=0 -> separate launches.
+      static const bool fuse_attn = [] { const char* v = getenv("B200_FUSED_ATTN"); return !(v && v[0] == '0'); }();
+      if (tc && m.tc2 && fuse_attn && tc_attn_supported(T, C)) {
+        Tensor out = talloc(C, x.H, x.W);
+        if (fused_stats) out.qs = qalloc(C);
+        if (!dry) {
+          TcAttnDesc d; memset(&d, 0, sizeof(d));
+          d.qk = qk; d.vT = vT; d.w3 = e->W(m.nw[3]); d.bv = bqkv + 2 * C; d.b3 = e->W(m.nb[3]); d.x = x.p; d.out = out.p;
+          d.qstats = out.qs; d.nimg = B; d.T = T; d.C = C; d.out_scale = inv_s2;
+          TcAttnPlan* pl = nullptr;
+          if (int r = tc_attn_plan_create(d, &pl)) { rc = r; return Tensor(); }
+          e->attnplans.push_back(pl);
+          name("attention core T=%d C=%d (QK^T, softmax, PV, NIN_3 +res) [fused]", T, C);
+          op(1, [=](cudaStream_t st) { return tc_attn_launch(pl, st); }, 0, 2.0 * B * T * ((double)T * C * 2 + (double)C * C));
+        }
+        ffree(qk, qkb); ffree(vT, vtb);
+        return out;
+      }
       float* S = falloc(BT * T, &sb);
       // logits[b][q][k] = q . k   (layerspp.py:82), scaled inside the softmax
       gemm(tc, qk, 2 * C, BT, T, qk + C, 2 * C, BT, T, B, T, T, C, nullptr, nullptr, 0, 1.f, 0, S, T, nullptr, 1 << 30, /*no_pair=*/true);
@@ -866,6 +887,8 @@ int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long 
   B200_REQUIRE(need >= 0, "bind_workspace: planning failed: %s", last_error());
   B200_REQUIRE(ws_bytes >= need, "bind_workspace: workspace too small (%lld < %lld bytes)", ws_bytes, need);
   for (auto* p : h->tcplans) tc_gemm_plan_destroy(p);
+  for (auto* p : h->attnplans) tc_attn_plan_destroy(p);
+  h->attnplans.clear();
   h->tcplans.clear(); h->ops.clear(); h->ops2.clear(); h->taps.clear(); h->launches = 0;
   h->B = batch; h->ws_bytes = ws_bytes;
   h->ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));

@@ -170,9 +170,9 @@ struct SmemLayout {
 // exchanges a lane holds ONE entry summed over 16 lanes (16 shuffles instead of 80); a final exchange
 // completes the 32-row sum.  rows_per_img == 16 (4x4 images): the two half-warps are different images and are
 // reduced separately.  The entry totals are then accumulated in fp64 by 16 (or 32) lanes in parallel.
-__device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilogue& e, float (&st)[16], int img,
-                                                  bool valid, int col0, int lane) {
-  const bool halves = e.rows_per_img < 32;
+__device__ __forceinline__ void quad_stats_commit_raw(double* qstats, int n_total, int rows_per_img, float (&st)[16],
+                                                      int img, bool valid, int col0, int lane) {
+  const bool halves = rows_per_img < 32;
   int idx = 0;
   if (!halves) {
 #pragma unroll
@@ -238,8 +238,12 @@ __device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilo
   const bool writer = halves ? true : ((lane & 1) == 0);
   if (writer && val_w && st[0] != 0.f) {
     const int quad = idx & 7, which = idx >> 3;          // which: 0 = sum, 1 = sum of squares
-    atomicAdd(p.qstats + ((long long)img_w * (p.N_total >> 2) + (col0 >> 2) + quad) * 2 + which, (double)st[0]);
+    atomicAdd(qstats + ((long long)img_w * (n_total >> 2) + (col0 >> 2) + quad) * 2 + which, (double)st[0]);
   }
+}
+__device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilogue& e, float (&st)[16], int img,
+                                                  bool valid, int col0, int lane) {
+  quad_stats_commit_raw(p.qstats, p.N_total, e.rows_per_img, st, img, valid, col0, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -624,6 +628,7 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
 }
 
 #include "gemm_tc2.cuh"
+#include "attn_tc.cuh"
 
 // ---------------------------------------------------------------------------
 // Host side: tensor maps, plan, launch
@@ -861,6 +866,54 @@ int tc_gemm_default_epi_mode() {
   return mode;
 }
 
+// ---- fused attention core (attn_tc.cuh) ----
+struct TcAttnPlan { AttnParams prm; };
+
+bool tc_attn_supported(int T, int C) { return T == AT_T && C == AT_C; }
+
+int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out) {
+  B200_REQUIRE(tc_attn_supported(d.T, d.C), "attn_tc: only T=256, C=256 (got T=%d C=%d)", d.T, d.C);
+  B200_REQUIRE(d.qk && d.vT && d.w3 && d.bv && d.b3 && d.x && d.out && d.nimg > 0, "attn_tc: null argument");
+  if (int r = tc_configure()) return r;
+  TcAttnPlan* pl = new TcAttnPlan();
+  AttnParams& p = pl->prm;
+  memset(&p, 0, sizeof(p));
+  int rc = 0;
+  {
+    uint64_t dims[2] = {(uint64_t)2 * AT_C, (uint64_t)d.nimg * AT_T};
+    uint64_t str[1] = {(uint64_t)2 * AT_C * 4};
+    uint32_t boxq[2] = {BKE, (uint32_t)BM}, boxk[2] = {BKE, 256};
+    rc = encode_map(&p.tmQ, d.qk, 2, dims, str, boxq);
+    if (!rc) rc = encode_map(&p.tmK, d.qk, 2, dims, str, boxk);
+  }
+  if (!rc) {
+    uint64_t dims[2] = {(uint64_t)AT_T, (uint64_t)d.nimg * AT_C};
+    uint64_t str[1] = {(uint64_t)AT_T * 4};
+    uint32_t box[2] = {BKE, 256};
+    rc = encode_map(&p.tmVT, d.vT, 2, dims, str, box);
+  }
+  if (!rc) {
+    uint64_t dims[2] = {(uint64_t)AT_C, (uint64_t)AT_C};
+    uint64_t str[1] = {(uint64_t)AT_C * 4};
+    uint32_t box[2] = {BKE, 256};
+    rc = encode_map(&p.tmW3, d.w3, 2, dims, str, box);
+  }
+  if (rc) { delete pl; return rc; }
+  p.bv = d.bv; p.b3 = d.b3; p.x = d.x; p.out = d.out; p.qstats = d.qstats; p.nimg = d.nimg;
+  p.logit_scale = (float)((1.0 / std::sqrt((double)AT_C)) * 1.4426950408889634);
+  p.out_scale = d.out_scale;
+  *out = pl;
+  return 0;
+}
+void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
+int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
+  const long long tiles = 2LL * pl->prm.nimg;
+  const int grid = (int)std::min<long long>(tiles, num_sms());
+  attn_tc_kernel<<<grid, 384, AttnSmem::TOTAL, st>>>(pl->prm);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
 // Opt in to the large dynamic shared-memory carve-out once, outside any stream capture.
 static int tc_configure() {
   static bool configured = false;
@@ -871,6 +924,7 @@ static int tc_configure() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6, false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<256, 6>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<128, 8>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
   configured = true;
   return 0;
 }

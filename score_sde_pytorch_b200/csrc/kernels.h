@@ -89,6 +89,24 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out);
 void tc_gemm_plan_destroy(TcGemmPlan* p);
 int tc_gemm_launch(const TcGemmPlan* p, cudaStream_t st);
 bool tc_gemm_supported(const TcGemmDesc& d, const char** why);
+// fused attention core (logits, softmax, P.V, NIN_3, residual, rescale, quad sums) for T=256 tokens x C=256 channels
+struct TcAttnPlan;
+struct TcAttnDesc {
+  const float* qk;          // [nimg*T][2C]: q | k rows (TF32 grid)
+  const float* vT;          // [nimg][C][T]: v transposed, without its bias (TF32 grid)
+  const float* w3;          // [C][C] NIN_3 as [out][in] (TF32 grid)
+  const float* bv;          // [C] bias of NIN_2
+  const float* b3;          // [C] bias of NIN_3
+  const float* x;           // [nimg*T][C] block input (residual)
+  float* out;               // [nimg*T][C]
+  double* qstats;           // optional GroupNorm quad sums of out
+  int nimg, T, C;
+  float out_scale;
+};
+bool tc_attn_supported(int T, int C);
+int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out);
+void tc_attn_plan_destroy(TcAttnPlan* p);
+int tc_attn_launch(const TcAttnPlan* p, cudaStream_t st);
 const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap" (+"/staged")
 
 // ---- pc_update.cu -----------------------------------------------------------

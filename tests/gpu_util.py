@@ -57,6 +57,16 @@ def conv_skip_nhwc(x, s1, s2, wp, bias, wskip, bias_skip, cout, residual=None, s
   return out
 
 
+def attention_core(qk, vT, w3, bv, b3, x, out_scale, want_stats=False):
+  """qk [nimg*T, 2C], vT [nimg, C, T], w3 [C, C] (out, in), x [nimg*T, C] -> out [nimg*T, C] (+ quad sums)."""
+  nimg, C, T = vT.shape
+  out = torch.empty_like(x)
+  qs = torch.zeros(nimg, C // 4, 2, device=x.device, dtype=torch.float64) if want_stats else None
+  _lib.call('b200_attention_core_f32', _lib.ptr(qk), _lib.ptr(vT), _lib.ptr(w3), _lib.ptr(bv), _lib.ptr(b3), _lib.ptr(x),
+            _lib.ptr(out), _lib.ptr(qs), nimg, T, C, float(out_scale), _lib.stream_ptr(x.device))
+  return (out, qs) if want_stats else out
+
+
 def gemm_nt(a, w, nbatch, m, n, k, lda=None, ldw=None, a_batch_rows=None, w_batch_rows=None, bias=None,
             round_out=False, impl=0):
   lda = k if lda is None else lda

@@ -103,6 +103,44 @@ def test_tcgen05_conv_with_fused_skip_projection(dev, case):
   assert torch.allclose(y, y2, rtol=1e-5, atol=2e-5), (y - y2).abs().max().item()
 
 
+@pytest.mark.parametrize('nimg', [1, 3, 200])
+def test_fused_attention_core_matches_torch(dev, nimg):
+  """layerspp.py:82-91 in one kernel: softmax(q k^T / sqrt(C)) v + b_v, NIN_3, (x + h)/sqrt(2), and the quad sums of
+  the result.  nimg=200 -> 400 tiles on 148 persistent CTAs (ring/TMEM reuse across tiles, odd tile counts)."""
+  import gpu_util
+  rt = gpu_util.round_tf32
+  torch.manual_seed(21 + nimg)
+  T = C = 256
+  q = rt(torch.randn(nimg, T, C, device=dev) * 1.5)
+  k = rt(torch.randn(nimg, T, C, device=dev) * 1.5)
+  v = rt(torch.randn(nimg, T, C, device=dev))
+  w3 = rt(torch.randn(C, C, device=dev) / 16)           # [out][in]
+  bv, b3 = torch.randn(C, device=dev), torch.randn(C, device=dev)
+  x = torch.randn(nimg * T, C, device=dev)
+  qk = torch.cat([q, k], 2).reshape(nimg * T, 2 * C).contiguous()
+  vT = v.transpose(1, 2).contiguous()
+  sc = 0.7071067690849304
+  out, qs = gpu_util.attention_core(qk, vT, w3, bv, b3, x, sc, want_stats=True)
+  torch.cuda.synchronize()
+  P = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * (C ** -0.5), dim=-1)
+  h = torch.bmm(P, v) + bv
+  ref = ((h.reshape(nimg * T, C) @ w3.t() + b3) + x) * sc
+  err = ((out - ref).norm() / ref.norm()).item()
+  assert err < 3e-4, err                                  # TF32 operands (E, O') inside the chain
+  assert (out - ref).abs().max().item() < 5e-3
+  # quad sums of what was stored
+  o4 = out.reshape(nimg, T, C // 4, 4).double()
+  assert torch.allclose(qs[..., 0], o4.sum((1, 3)), rtol=1e-5, atol=1e-3)
+  assert torch.allclose(qs[..., 1], (o4 * o4).sum((1, 3)), rtol=1e-5, atol=1e-3)
+  # peaked softmax rows (large logits): the max subtraction must keep exp() in range
+  qk2 = (qk * 6).contiguous()
+  out2 = gpu_util.attention_core(rt(qk2), vT, w3, bv, b3, x, sc)
+  P2 = torch.softmax(torch.bmm(rt(q * 6), rt(k * 6).transpose(1, 2)) * (C ** -0.5), dim=-1)
+  ref2 = (((torch.bmm(P2, v) + bv).reshape(nimg * T, C) @ w3.t() + b3) + x) * sc
+  assert torch.isfinite(out2).all()
+  assert ((out2 - ref2).norm() / ref2.norm()).item() < 3e-4
+
+
 def test_tcgen05_batched_gemm_attention_shapes(dev):
   import gpu_util
   rt = gpu_util.round_tf32

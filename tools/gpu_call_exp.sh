@@ -1,19 +1,16 @@
 #!/bin/bash
-# experiments: two-lane forward (GroupNorm/FIR of one half-batch under the other's contractions), fused skip projection
+# experiments: fused attention core
 mkdir -p gpurun_out
 TAG=$1; L=gpurun_out/exp_$TAG.log; rm -f $L
-timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_engine.py -q -m gpu -x --tb=short -p no:cacheprovider >> $L 2>&1; echo "tests exit $?" >> $L
-B200_LANES=1 B200_FUSE_SKIP=0 timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu --tb=short -p no:cacheprovider -k "tf32_cifar10" >> $L 2>&1; echo "tests(lanes1,nofuse) exit $?" >> $L
+timeout 300 python -m pytest tests/test_gpu_tc.py -q -m gpu -x --tb=short -p no:cacheprovider -k "fused_attention" >> $L 2>&1; echo "attn tests exit $?" >> $L
+timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_engine.py -q -m gpu --tb=short -p no:cacheprovider -s >> $L 2>&1; echo "tests exit $?" >> $L
 timeout 300 python __graft_entry__.py smoke >> $L 2>&1; echo "smoke exit $?" >> $L
 run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_${TAG}_$name.json 2>> $L; }
 run default A=1
-run lanes1 B200_LANES=1
-run nofuse B200_FUSE_SKIP=0
-run old B200_LANES=1 B200_FUSE_SKIP=0
+run noattn B200_FUSED_ATTN=0
 run default2 A=1
 timeout 300 python tools/profile_ops.py --batch 1024 --md gpurun_out/ops_${TAG}.md > /dev/null 2>> $L; echo "profile_ops exit $?" >> $L
-B200_LANES=1 timeout 300 python tools/profile_ops.py --batch 1024 --md gpurun_out/ops_${TAG}_lanes1.md > /dev/null 2>> $L
-grep -v "^$" $L | tail -30
+grep -v "^$" $L | tail -40
 for f in gpurun_out/bench_${TAG}_*.json; do echo $f; python -c "
 import json
 d=json.loads(open('$f').read().strip().splitlines()[-1]); r=d['roofline']
