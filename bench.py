@@ -145,11 +145,14 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def measure_tf32_peak(dev):
-  """cuBLAS TF32 GEMM throughput on this device (the measured denominator for kind::tf32 work)."""
+def measure_tf32_peak(dev, f16=False):
+  """cuBLAS GEMM throughput on this device in the operand format the engine computes in: TF32 (kind::tf32
+  work) or fp16 with fp32 accumulation (kind::f16 work) - the measured denominator of the tensor roofline."""
   n = 8192
   a = torch.randn(n, n, device=dev)
   b = torch.randn(n, n, device=dev)
+  if f16:
+    a, b = a.half(), b.half()
   old = torch.backends.cuda.matmul.allow_tf32
   torch.backends.cuda.matmul.allow_tf32 = True
   try:
@@ -256,14 +259,15 @@ def run_gpu_arm(args):
     by_kind = {k: dict(ms=round(ms_k[i], 4), gflop=round(fl_k[i] / 1e9, 2), launches=int(n_k[i])) for i, k in enumerate(kinds)}
     fwd_ms = sum(ms_k[i] for i in range(7))
     tc_ms, tc_flops, tc_n = ms_k[0], fl_k[0], max(int(n_k[0]), 1)
-    tf32_peak = measure_tf32_peak(dev)
+    f16 = args.precision == 'f16'
+    tf32_peak = measure_tf32_peak(dev, f16)
     achieved = (tc_flops / tc_n) / ((tc_ms / tc_n) * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     t_hbm_ms = ALG_BYTES_PER_IMG_STEP * B / (peaks['hbm_gbs'] * 1e9) * 1e3
-    roofline = dict(bound='tensor', kernel='gemm_tc_kernel (tcgen05 kind::tf32 implicit GEMM)',
+    roofline = dict(bound='tensor', kernel=f"gemm_tc_kernel / gemm_tc2_kernel (tcgen05 kind::{'f16' if f16 else 'tf32'} implicit GEMM)",
                     achieved=round(achieved, 2), peak=round(tf32_peak, 2), unit='TFLOP/s',
                     frac=round(achieved / tf32_peak, 4) if tf32_peak else None,
-                    peak_source='cuBLAS TF32 8192^3 GEMM measured in this run (MEASURED_PEAKS.json holds bf16 only: '
-                                f"{peaks['bf16_tflops_sustained']} TF/s sustained, {peaks['source']})",
+                    peak_source=(f"cuBLAS {'fp16' if f16 else 'TF32'} 8192^3 GEMM measured in this run (MEASURED_PEAKS.json holds bf16 only: "
+                                 f"{peaks['bf16_tflops_sustained']} TF/s sustained, {peaks['source']})"),
                     frac_of_measured_bf16_sustained=round(achieved / peaks['bf16_tflops_sustained'], 4),
                     alg_flop_per_launch=tc_flops / tc_n, avg_launch_ms=tc_ms / tc_n, launches_per_forward=tc_n,
                     kernel_share_of_forward=round(tc_ms / fwd_ms, 4) if fwd_ms else None,
@@ -275,7 +279,8 @@ def run_gpu_arm(args):
     line = dict(metric='PC-sampler images/sec, NCSN++ CIFAR-10 1000-step VE', value=round(value, 4), unit='images/s',
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_per_step, 4),
                 higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='tf32' if args.precision == 'tf32' else 'f32', data='synthetic',
+                dtype={'tf32': 'tf32', 'f16': 'f16 operands (11-bit significand, as tf32), f32 accumulate and activations', 'fp32': 'f32'}[args.precision],
+                data='synthetic',
                 config=dict(workload='NCSN++ cont. CIFAR-10 32x32 VE-SDE PC sampler (1000 steps), batch 1024 per GPU'
                             if B == 1024 else f'NCSN++ cont. CIFAR-10 32x32 VE-SDE PC sampler (1000 steps), batch {B} per GPU',
                             batch_per_gpu=B, global_batch=B * world, sampler_steps=N_SAMPLER_STEPS,
@@ -303,7 +308,7 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--batch', type=int, default=1024, help='images per GPU (BASELINE.json configs[1]: 1024)')
   ap.add_argument('--cpu-batch', type=int, default=8, help='batch of the bounded CPU sample')
-  ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
+  ap.add_argument('--precision', default='tf32', choices=['tf32', 'f16', 'fp32'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'ours':

@@ -63,7 +63,9 @@ B200_API int b200_randn_like_torch_f32(float* out, long long numel, unsigned lon
 /* ---- one contraction (3x3 / 1x1 convolution on NHWC, 'same' padding, stride 1) ----
  * Exported so the tcgen05 path can be checked against the CUDA-core path and torch.
  * w_packed is [taps][c_out][c_in] (see b200_pack_conv_weight_f32). impl: 0 = fp32 CUDA cores,
- * 1 = tcgen05 TF32 (inputs must already be TF32-representable for exactness claims). */
+ * 1 = tcgen05 TF32 (inputs must already be TF32-representable for exactness claims),
+ * 2 = tcgen05 fp16: x1, x2 and w_packed hold IEEE fp16 elements (same layouts; round_tf32 = 2 packs / stores fp16);
+ *     out is fp32 unless round_tf32 == 2. */
 B200_API int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int batch, int h, int w,
                                 const float* w_packed, const float* bias, int c_out, int ksize,
                                 const float* rowvec, long long rowvec_ld, const float* residual, float scale,
@@ -79,11 +81,12 @@ B200_API int b200_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int
                                        int round_tf32, void* stream);
 /* Fused attention core of AttnBlockpp (layerspp.py:82-91) for T=256 tokens x C=256 channels per image:
  * out = (softmax(q k^T / sqrt(C)) v + b_v) W3^T + b_3 + x) * out_scale, tcgen05 only.
- * qk = [nimg*T][2C] (q | k), vT = [nimg][C][T] (v transposed, without b_v), w3 = [C_out][C_in]; all TF32-representable.
+ * qk = [nimg*T][2C] (q | k), vT = [nimg][C][T] (v transposed, without b_v), w3 = [C_out][C_in]; TF32-representable
+ * fp32 (operand_f16 = 0) or IEEE fp16 elements (operand_f16 = 1).
  * qstats (optional, zero-initialised by the caller) receives out's GroupNorm quad sums [nimg][C/4][2]. */
 B200_API int b200_attention_core_f32(const float* qk, const float* vT, const float* w3, const float* bv,
                                      const float* b3, const float* x, float* out, double* qstats, int nimg,
-                                     int t, int c, float out_scale, void* stream);
+                                     int t, int c, float out_scale, int operand_f16, void* stream);
 /* batched C[b] = A[b] (M x K, pitch lda) * W[b]^T (N x K, pitch ldw), row-major out pitch ldo. */
 B200_API int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const float* w, long long ldw,
                               int w_batch_rows, int nbatch, int m, int n, int k, const float* bias,
@@ -104,7 +107,9 @@ typedef struct {
   int centered, scale_by_sigma, skip_rescale, conditional;
   int progressive_input;        /* 0 = none, 1 = residual */
   int fir_taps;  float fir_kernel[8];   /* separable taps, e.g. {1,3,3,1} */
-  int precision;                /* 0 = TF32 tensor cores where shapes allow, 1 = strict fp32 CUDA cores */
+  int precision;                /* 0 = tensor cores on TF32-rounded fp32 operands where shapes allow, 1 = strict fp32
+                                 * CUDA cores, 2 = tensor cores on fp16 operands (same 11-bit significand as TF32,
+                                 * fp32 accumulation; activations between layers stay fp32) */
   int keep_activations;         /* debug: never recycle activation buffers so b200_ncsnpp_tap works */
 } b200_ncsnpp_config;
 

@@ -98,8 +98,9 @@ int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int bat
   ep.bias = bias; ep.rowvec = rowvec; ep.rowvec_ld = rowvec_ld; ep.residual = residual; ep.ld_res = c_out;
   ep.scale = scale; ep.round_tf32 = round_tf32; ep.rows_per_img = h * w; ep.out = out; ep.ld_out = c_out;
   if (!x2) c2 = 0;
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {
     TcGemmDesc d; memset(&d, 0, sizeof(d));
+    d.f16 = impl == 2;
     d.a1 = x1; d.C1 = c1; d.a2 = x2; d.C2 = c2; d.conv = 1; d.H = h; d.W = w; d.nimg = batch; d.taps = ksize * ksize;
     d.w = w_packed; d.N_total = c_out; d.K_total = c1 + c2; d.w_rows = (long long)ksize * ksize * c_out; d.nbatch = 1;
     d.epi_mode = -1; d.epi = ep;
@@ -137,11 +138,11 @@ int b200_conv_skip_nhwc_f32(const float* x, int c, const float* s1, int cs1, con
 
 int b200_attention_core_f32(const float* qk, const float* vT, const float* w3, const float* bv, const float* b3,
                             const float* x, float* out, double* qstats, int nimg, int t, int c, float out_scale,
-                            void* stream) {
+                            int operand_f16, void* stream) {
   B200_REQUIRE(tc_attn_supported(t, c), "attention_core: only T=256, C=256 is implemented (got T=%d C=%d)", t, c);
   TcAttnDesc d; memset(&d, 0, sizeof(d));
   d.qk = qk; d.vT = vT; d.w3 = w3; d.bv = bv; d.b3 = b3; d.x = x; d.out = out; d.qstats = qstats;
-  d.nimg = nimg; d.T = t; d.C = c; d.out_scale = out_scale;
+  d.nimg = nimg; d.T = t; d.C = c; d.out_scale = out_scale; d.f16 = operand_f16 ? 1 : 0;
   TcAttnPlan* pl = nullptr;
   if (int r = tc_attn_plan_create(d, &pl)) return r;
   const int r = tc_attn_launch(pl, static_cast<cudaStream_t>(stream));
@@ -156,8 +157,9 @@ int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Epilogue ep; memset(&ep, 0, sizeof(ep));
   ep.bias = bias; ep.scale = 1.f; ep.round_tf32 = round_tf32; ep.rows_per_img = m; ep.out = out; ep.ld_out = ldo;
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {
     TcGemmDesc d; memset(&d, 0, sizeof(d));
+    d.f16 = impl == 2;
     d.a1 = a; d.C1 = k; d.conv = 0; d.taps = 1; d.a_ld = lda; d.a_batch_rows = a_batch_rows;
     d.a_rows = a_batch_rows ? (long long)a_batch_rows * (nbatch - 1) + m : m;
     d.w = w; d.N_total = n; d.K_total = k; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;

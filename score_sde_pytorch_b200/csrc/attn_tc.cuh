@@ -24,12 +24,18 @@
 // Deferred normalisation: the reference rounds nothing; here E (not E/rowsum) is the TF32 operand and the
 // division happens in fp32 on the accumulator - one rounding per operand, as everywhere else in the engine.
 
+// Operand formats: TF32-grid fp32 (kind::tf32; a 128-byte K block = 32 elements, 8 K blocks per contraction,
+// 128 KB operand buffer, 2-stage ring) or fp16 (kind::f16; 64 elements per K block, 4 K blocks, 64 KB operand
+// buffer, 3-stage ring).
 constexpr int AT_T = 256, AT_C = 256;
+template <bool F16>
 struct AttnSmem {
-  static constexpr int PBUF = 0;                                   // 8 K-blocks x (128 rows x 128 B)
-  static constexpr int RING = 128 * 1024;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + 256 * BKE * 4;   // 16 KB + 32 KB
-  static constexpr int STAGES = 2;
+  static constexpr int KB = F16 ? 4 : 8;                            // 128-byte K blocks per contraction (K = 256 elements)
+  static constexpr int BKA = F16 ? 64 : 32;                         // elements per K block
+  static constexpr int PBUF = 0;                                    // KB x (128 rows x 128 B)
+  static constexpr int RING = KB * 16384;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + 256 * 128;     // 16 KB + 32 KB
+  static constexpr int STAGES = F16 ? 3 : 2;
   static constexpr int XCHG = RING + STAGES * STAGE_BYTES;          // [2 halves][128 rows] floats
   static constexpr int BAR_OFFSET = XCHG + 1024;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
@@ -48,14 +54,35 @@ struct AttnParams {
   int nimg;
 };
 
-// address of 16-byte chunk `c4` (0..7) of row r in K-block kb of the swizzled operand buffer
-__device__ __forceinline__ float4* pbuf_chunk(uint8_t* pbuf, int kb, int r, int c4) {
-  return reinterpret_cast<float4*>(pbuf + kb * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4));
+// address of 16-byte chunk `c16` (0..7) of row r in K-block kb of the swizzled operand buffer
+__device__ __forceinline__ uint8_t* pbuf_chunk(uint8_t* pbuf, int kb, int r, int c16) {
+  return pbuf + kb * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4);
+}
+// write 32 consecutive K elements (k0 .. k0+31, k0 % 32 == 0) of operand row r: TF32-rounded fp32 or fp16
+template <bool F16>
+__device__ __forceinline__ void pbuf_store32(uint8_t* pbuf, int r, int k0, const float (&v)[32]) {
+  if (F16) {
+    const int kb = k0 >> 6, c0 = (k0 & 63) >> 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 u;
+      u.x = pack_half2(v[8 * c], v[8 * c + 1]); u.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
+      u.z = pack_half2(v[8 * c + 4], v[8 * c + 5]); u.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
+      *reinterpret_cast<uint4*>(pbuf_chunk(pbuf, kb, r, c0 + c)) = u;
+    }
+  } else {
+    const int kb = k0 >> 5;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<float4*>(pbuf_chunk(pbuf, kb, r, c)) =
+          make_float4(round_tf32(v[4 * c]), round_tf32(v[4 * c + 1]), round_tf32(v[4 * c + 2]), round_tf32(v[4 * c + 3]));
+  }
 }
 __device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
+template <bool F16>
 __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
-  using L = AttnSmem;
+  using L = AttnSmem<F16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* pbuf = smem + L::PBUF;
@@ -87,7 +114,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long total_tiles = 2LL * p.nimg;
-  constexpr int KB = AT_C / BKE;   // 8 K blocks in every phase (C = T = 256)
+  constexpr int KB = L::KB;        // K blocks in every phase (C = T = 256 elements)
+  constexpr int BKA = L::BKA;
 
   if (warp == 0 && lane == 0) {
     // ======================= TMA producer =======================
@@ -101,14 +129,14 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (ph == 0) {
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-            tma_load_2d(&p.tmQ, sa, &full_bar[stage], kc * BKE, b * AT_T + qh * BM);
-            tma_load_2d(&p.tmK, sb, &full_bar[stage], AT_C + kc * BKE, b * AT_T);
+            tma_load_2d(&p.tmQ, sa, &full_bar[stage], kc * BKA, b * AT_T + qh * BM);
+            tma_load_2d(&p.tmK, sb, &full_bar[stage], AT_C + kc * BKA, b * AT_T);
           } else if (ph == 1) {
-            mbar_expect_tx(&full_bar[stage], 256 * BKE * 4);
-            tma_load_2d(&p.tmVT, sb, &full_bar[stage], kc * BKE, b * AT_C);
+            mbar_expect_tx(&full_bar[stage], 256 * 128);
+            tma_load_2d(&p.tmVT, sb, &full_bar[stage], kc * BKA, b * AT_C);
           } else {
-            mbar_expect_tx(&full_bar[stage], 256 * BKE * 4);
-            tma_load_2d(&p.tmW3, sb, &full_bar[stage], kc * BKE, 0);
+            mbar_expect_tx(&full_bar[stage], 256 * 128);
+            tma_load_2d(&p.tmW3, sb, &full_bar[stage], kc * BKA, 0);
           }
           if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -116,7 +144,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
     }
   } else if (warp == 1 && lane == 0) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = make_idesc<256>();
+    constexpr uint32_t idesc = F16 ? make_idesc_f16<256>() : make_idesc<256>();
     uint32_t stage = 0, phase = 0, tpar = 0;
     const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 256;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tpar ^= 1) {
@@ -130,8 +158,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           const uint32_t sa = smem_u32(ring + stage * L::STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(ph == 0 ? sa : smem_u32(pbuf + kc * 16384));
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BKE / UMMA_K; ++k) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+          umma_kstep<F16>(d_tmem, adesc, bdesc, idesc, kc);
           umma_commit(&empty_bar[stage]);
           if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -167,17 +194,13 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       for (int j = 0; j < 4; ++j) {
         uint32_t v[32];
         tmem_ld32(lane_addr + half * 128 + j * 32, v);
-        const int kb = half * 4 + j;
+        float ev[32];
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float4 e;
-          e.x = round_tf32(exp2f(fmaf(__uint_as_float(v[c]), p.logit_scale, -moff)));
-          e.y = round_tf32(exp2f(fmaf(__uint_as_float(v[c + 1]), p.logit_scale, -moff)));
-          e.z = round_tf32(exp2f(fmaf(__uint_as_float(v[c + 2]), p.logit_scale, -moff)));
-          e.w = round_tf32(exp2f(fmaf(__uint_as_float(v[c + 3]), p.logit_scale, -moff)));
-          sum += (e.x + e.y) + (e.z + e.w);
-          *pbuf_chunk(pbuf, kb, r, c >> 2) = e;
+        for (int c = 0; c < 32; ++c) {
+          ev[c] = exp2f(fmaf(__uint_as_float(v[c]), p.logit_scale, -moff));
+          sum += ev[c];
         }
+        pbuf_store32<F16>(pbuf, r, half * 128 + j * 32, ev);
       }
       pair_barrier(q);                                  // the partner has read this thread's max: the slot is free
       xchg[half * 128 + r] = sum;
@@ -195,18 +218,18 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       for (int j = 0; j < 4; ++j) {
         uint32_t v[32];
         tmem_ld32(lane_addr + 256 + half * 128 + j * 32, v);
-        const int kb = half * 4 + j;
-        const float* bvp = p.bv + kb * 32;
+        const int ch0 = half * 128 + j * 32;
+        const float* bvp = p.bv + ch0;
+        float ov[32];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(bvp + c));
-          float4 o;
-          o.x = round_tf32(fmaf(__uint_as_float(v[c]), inv, t.x));
-          o.y = round_tf32(fmaf(__uint_as_float(v[c + 1]), inv, t.y));
-          o.z = round_tf32(fmaf(__uint_as_float(v[c + 2]), inv, t.z));
-          o.w = round_tf32(fmaf(__uint_as_float(v[c + 3]), inv, t.w));
-          *pbuf_chunk(pbuf, kb, r, c >> 2) = o;
+          ov[c] = fmaf(__uint_as_float(v[c]), inv, t.x);
+          ov[c + 1] = fmaf(__uint_as_float(v[c + 1]), inv, t.y);
+          ov[c + 2] = fmaf(__uint_as_float(v[c + 2]), inv, t.z);
+          ov[c + 3] = fmaf(__uint_as_float(v[c + 3]), inv, t.w);
         }
+        pbuf_store32<F16>(pbuf, r, ch0, ov);
       }
       fence_async_smem();
       tc_fence_before();

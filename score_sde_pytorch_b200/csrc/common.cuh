@@ -48,6 +48,36 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// Operand-grid stores.  Tensors that feed a tensor-core contraction are written by their producer in one of
+// three forms, selected by an integer `mode` that travels with the launch:
+//   0  fp32 as computed;
+//   1  fp32 rounded to the TF32 grid (operands of tcgen05 kind::tf32);
+//   2  IEEE fp16, round-to-nearest-even (operands of tcgen05 kind::f16).  Same 11-bit significand as TF32, half the
+//      bytes in HBM and shared memory; `base` then addresses __half elements and `idx` counts halves.
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+  return r;
+}
+__device__ __forceinline__ void store_operand4(float* base, long long idx, float4 v, int mode) {
+  if (mode == 2) {
+    uint2 u; u.x = pack_half2(v.x, v.y); u.y = pack_half2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = u;
+  } else {
+    if (mode == 1) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    *reinterpret_cast<float4*>(base + idx) = v;
+  }
+}
+__device__ __forceinline__ void store_operand1(float* base, long long idx, float v, int mode) {
+  if (mode == 2) {
+    uint16_t h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    reinterpret_cast<uint16_t*>(base)[idx] = h;
+  } else {
+    base[idx] = mode == 1 ? round_tf32(v) : v;
+  }
+}
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -82,7 +112,7 @@ struct Epilogue {
   const float* per_img_div; // [images] divide (scale_by_sigma) or null
   long long div_stride;     // 0 = same divisor for every image
   float scale;              // multiplies after the adds (1/sqrt(2) for skip_rescale)
-  int round_tf32;           // round the stored value to TF32
+  int round_tf32;           // store mode of `out`: 0 fp32, 1 fp32 on the TF32 grid, 2 fp16 (see store_operand4)
   int rows_per_img;         // H_out*W_out in conv mode, rows per batch item in gemm mode
   float* out;
   long long ld_out;         // elements between consecutive rows of out (NHWC: C_out_total)

@@ -105,7 +105,7 @@ __device__ __forceinline__ float4 gn_norm4(float4 v, float2 mr, float4 ga, float
   o.z = (v.z - mr.x) * mr.y * ga.z + be.z;
   o.w = (v.w - mr.x) * mr.y * ga.w + be.w;
   if (act) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-  if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+  (void)round_out;   // the store applies the operand mode (store_operand4)
   return o;
 }
 
@@ -137,23 +137,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long o = (ib + pix + u * L) * C + c0;
-        *reinterpret_cast<float4*>(y + o) = gn_norm4(v[u], mr, ga, be, act, round_out);
-        if (raw) {
-          float4 r = v[u];
-          if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-          *reinterpret_cast<float4*>(raw + o) = r;
-        }
+        store_operand4(y, o, gn_norm4(v[u], mr, ga, be, act, round_out), round_out);
+        if (raw) store_operand4(raw, o, v[u], round_out);
       }
     }
     for (; pix < p1; pix += L) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)pix * Cs));
       const long long o = (ib + pix) * C + c0;
-      *reinterpret_cast<float4*>(y + o) = gn_norm4(v, mr, ga, be, act, round_out);
-      if (raw) {
-        float4 r = v;
-        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-        *reinterpret_cast<float4*>(raw + o) = r;
-      }
+      store_operand4(y, o, gn_norm4(v, mr, ga, be, act, round_out), round_out);
+      if (raw) store_operand4(raw, o, v, round_out);
     }
   } else {
     for (long long u = (long long)p0 * Q + threadIdx.x; u < (long long)p1 * Q; u += blockDim.x) {
@@ -164,12 +156,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
       const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
       const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
       const long long o = (ib + pix) * C + c0;
-      *reinterpret_cast<float4*>(y + o) = gn_norm4(v, mr, ga, be, act, round_out);
-      if (raw) {
-        float4 r = v;
-        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-        *reinterpret_cast<float4*>(raw + o) = r;
-      }
+      store_operand4(y, o, gn_norm4(v, mr, ga, be, act, round_out), round_out);
+      if (raw) store_operand4(raw, o, v, round_out);
     }
   }
 }
@@ -244,13 +232,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict_
         }
       }
     }
-    float* dst = y + (((long long)n * p.out_h + oy) * p.out_w + ox) * p.minor + cm;
-    if (p.round_out) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = round_tf32(acc[v]);
-    }
-    if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    else dst[0] = acc[0];
+    const long long o = (((long long)n * p.out_h + oy) * p.out_w + ox) * p.minor + cm;
+    if (VEC == 4) store_operand4(y, o, make_float4(acc[0], acc[1], acc[2], acc[3]), p.round_out);
+    else store_operand1(y, o, acc[0], p.round_out);
   }
 }
 
@@ -288,8 +272,7 @@ __global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict_
       acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
     }
   }
-  if (p.round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
-  *reinterpret_cast<float4*>(y + (((long long)n * p.out_h + oy) * p.out_w + ox) * p.minor + cm) = acc;
+  store_operand4(y, (((long long)n * p.out_h + oy) * p.out_w + ox) * p.minor + cm, acc, p.round_out);
 }
 
 // 2x upsampling (up=2, pad0=2, 4x4 FIR), one thread per INPUT pixel quad: the 3x3 input neighbourhood is loaded
@@ -317,7 +300,7 @@ __global__ void __launch_bounds__(256) fir4_up2_nhwc_kernel(const float* __restr
                       ? __ldg(reinterpret_cast<const float4*>(xin + ((long long)iy * p.in_w + ix) * p.minor))
                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  float* yout = y + (long long)n * p.out_h * p.out_w * p.minor + cm;
+  const long long yout = (long long)n * p.out_h * p.out_w * p.minor + cm;
 #pragma unroll
   for (int ay = 0; ay < 2; ++ay)
 #pragma unroll
@@ -333,8 +316,7 @@ __global__ void __launch_bounds__(256) fir4_up2_nhwc_kernel(const float* __restr
           const float4 u = v[dy][dx];
           acc.x += w * u.x; acc.y += w * u.y; acc.z += w * u.z; acc.w += w * u.w;
         }
-      if (p.round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
-      *reinterpret_cast<float4*>(yout + ((long long)(2 * i + ay) * p.out_w + (2 * j + ax)) * p.minor) = acc;
+      store_operand4(y, yout + ((long long)(2 * i + ay) * p.out_w + (2 * j + ax)) * p.minor, acc, p.round_out);
     }
 }
 
@@ -612,7 +594,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restr
     const int o = (int)(t % O);
     const int tap = (int)(t / O);
     const float v = src[o * so + i * si + tap * stp];
-    dst[tap * dt + o * dO + i] = round_out ? round_tf32(v) : v;
+    store_operand1(dst, tap * dt + o * dO + i, v, round_out);
   }
 }
 int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, long long so, long long si,
@@ -632,12 +614,14 @@ int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, lon
 // [B*HW, 32] x [nf, 32]^T product instead of a 27-deep CUDA-core loop.
 // ============================================================================
 __global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __restrict__ x, float* __restrict__ patches,
-                                                            int B, int C, int Hin, int Win, int H, int W, int stride, int pad) {
-  const long long total = (long long)B * H * W * 8;            // 8 float4 per 32-wide row
+                                                            int B, int C, int Hin, int Win, int H, int W, int stride, int pad,
+                                                            int mode /* 1: 32 TF32 floats per row, 2: 64 halves per row */) {
+  const int qshift = mode == 2 ? 4 : 3;                        // quads per row: 8 (32-wide) or 16 (64-wide)
+  const long long total = ((long long)B * H * W) << qshift;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int k4 = (int)(i & 7) << 2;
-  const long long pg = i >> 3;
+  const int k4 = (int)(i & ((1 << qshift) - 1)) << 2;
+  const long long pg = i >> qshift;
   const int px = (int)(pg % W), py = (int)((pg / W) % H), b = (int)(pg / ((long long)W * H));
   float v[4];
 #pragma unroll
@@ -649,16 +633,17 @@ __global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __rest
       const int iy = py * stride + tap / 3 - pad, ix = px * stride + tap % 3 - pad;
       if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) t = __ldg(x + (((long long)b * C + c) * Hin + iy) * Win + ix);
     }
-    v[j] = round_tf32(t);
+    v[j] = t;
   }
-  *reinterpret_cast<float4*>(patches + pg * 32 + k4) = make_float4(v[0], v[1], v[2], v[3]);
+  store_operand4(patches, pg * (mode == 2 ? 64 : 32) + k4, make_float4(v[0], v[1], v[2], v[3]), mode);
 }
 
 int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
-                          int pad, cudaStream_t st) {
+                          int pad, int mode, cudaStream_t st) {
   B200_REQUIRE(9 * C <= 32, "im2col3x3: %d channels do not fit one 32-wide K step", C);
-  const long long total = (long long)B * H * W * 8;
-  im2col3x3_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, patches, B, C, Hin, Win, H, W, stride, pad);
+  B200_REQUIRE(mode == 1 || mode == 2, "im2col3x3: operand mode %d", mode);
+  const long long total = (long long)B * H * W * (mode == 2 ? 16 : 8);
+  im2col3x3_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, patches, B, C, Hin, Win, H, W, stride, pad, mode);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -795,7 +780,7 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const float* __restrict
     const int t = i / C, c = i % C;
     float a = 0.f;
     for (int j = 0; j < T; ++j) a = fmaf(sp[t * T + j], sv[j * C + c], a);
-    out[((long long)b * T + t) * C + c] = round_out ? round_tf32(a) : a;
+    store_operand1(out, ((long long)b * T + t) * C + c, a, round_out);
   }
 }
 

@@ -144,9 +144,12 @@ int add_param(b200_ncsnpp* e, const std::string& name, std::vector<long long> sh
   return (int)e->params.size() - 1;
 }
 
+// precision: 0 = tensor cores on TF32-grid fp32 operands, 1 = strict fp32 CUDA cores, 2 = tensor cores on fp16 operands
+// (same 11-bit significand as TF32, fp32 accumulation; half the operand bytes and twice the MMA rate)
 bool tc_ok(const b200_ncsnpp* e, int C1, int C2, int Cout, int H, int W, int taps) {
-  if (e->cfg.precision != 0) return false;
+  if (e->cfg.precision == 1) return false;
   TcGemmDesc d; memset(&d, 0, sizeof(d));
+  d.f16 = e->cfg.precision == 2;
   d.C1 = C1; d.C2 = C2; d.a2 = C2 ? (const float*)1 : nullptr; d.conv = 1; d.H = H; d.W = W; d.nimg = 1; d.taps = taps;
   d.N_total = Cout; d.K_total = C1 + C2; d.nbatch = 1; d.epi.ld_out = Cout; d.epi.ld_res = Cout;
   return tc_gemm_supported(d, nullptr);
@@ -171,6 +174,9 @@ int build_graph(b200_ncsnpp* e) {
       }
   }
   const int nf = c.nf, L = c.num_levels, nrb = c.num_res_blocks, ch = c.num_channels;
+  const bool tcmode = c.precision != 1;
+  const int om = c.precision == 2 ? 2 : 1;      // operand store mode of tensor-core inputs (store_operand4)
+  const int flatk = om == 2 ? 64 : 32;          // elements of one 128-byte K step (im2col contraction depth)
   std::vector<int> all_res(L);
   for (int i = 0; i < L; ++i) all_res[i] = c.image_size >> i;
   auto has_attn = [&](int r) { for (int i = 0; i < c.num_attn_resolutions; ++i) if (c.attn_resolutions[i] == r) return true; return false; };
@@ -203,7 +209,7 @@ int build_graph(b200_ncsnpp* e) {
     m.tc2 = m.has_conv2 && tc_ok(e, cin, 0, cout, ro, ro, 1);
     m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {cin}, PK_COPY, 0, 0, 0, 0);
     m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {cin}, PK_COPY, 0, 0, 0, 0);
-    m.c0w = add_param(e, nm("Conv_0.weight"), {cout, cin, 3, 3}, PK_CONV, 9, cout, cin, m.tc0);
+    m.c0w = add_param(e, nm("Conv_0.weight"), {cout, cin, 3, 3}, PK_CONV, 9, cout, cin, m.tc0 ? om : 0);
     m.c0b = add_param(e, nm("Conv_0.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
     m.dw = add_param(e, nm("Dense_0.weight"), {cout, 4 * nf}, PK_COPY, 0, 0, 0, 0, 0);   // offset fixed below
     m.db = add_param(e, nm("Dense_0.bias"), {cout}, PK_COPY, 0, 0, 0, 0, 0);
@@ -212,10 +218,10 @@ int build_graph(b200_ncsnpp* e) {
     e->sumC += cout;
     m.gn1w = add_param(e, nm("GroupNorm_1.weight"), {cout}, PK_COPY, 0, 0, 0, 0);
     m.gn1b = add_param(e, nm("GroupNorm_1.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
-    m.c1w = add_param(e, nm("Conv_1.weight"), {cout, cout, 3, 3}, PK_CONV, 9, cout, cout, m.tc1);
+    m.c1w = add_param(e, nm("Conv_1.weight"), {cout, cout, 3, 3}, PK_CONV, 9, cout, cout, m.tc1 ? om : 0);
     m.c1b = add_param(e, nm("Conv_1.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
     if (m.has_conv2) {
-      m.c2w = add_param(e, nm("Conv_2.weight"), {cout, cin, 1, 1}, PK_CONV, 1, cout, cin, m.tc2);
+      m.c2w = add_param(e, nm("Conv_2.weight"), {cout, cin, 1, 1}, PK_CONV, 1, cout, cin, m.tc2 ? om : 0);
       m.c2b = add_param(e, nm("Conv_2.bias"), {cout}, PK_COPY, 0, 0, 0, 0);
     }
     e->mods.push_back(m);
@@ -223,8 +229,10 @@ int build_graph(b200_ncsnpp* e) {
   auto add_attn = [&](int C, int res) {
     Mod m; m.kind = M_ATTN; m.index = (int)e->mods.size(); m.cin1 = C; m.cout = C; m.res = res;
     const int T = res * res;
-    m.tcattn = (e->cfg.precision == 0) && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
-    m.tc0 = (e->cfg.precision == 0) && (C % 128 == 0) && (m.tcattn || T <= 64);   // q/k/v projections on tensor cores
+    m.tcattn = tcmode && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
+    // fp16 operands: the logits/probabilities never leave the chip, so only the fused core is implemented
+    if (om == 2 && !tc_attn_supported(T, C)) m.tcattn = false;
+    m.tc0 = tcmode && (C % 128 == 0) && (m.tcattn || T <= 64);   // q/k/v projections on tensor cores
     m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {C}, PK_COPY, 0, 0, 0, 0);
     m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {C}, PK_COPY, 0, 0, 0, 0);
     // q,k,v projection weights packed as one [3C][C] block (rows: q, k, v), biases as one [3C] vector
@@ -232,11 +240,12 @@ int build_graph(b200_ncsnpp* e) {
     const long long bbase = e->wcount; e->wcount += (3LL * C + 63) & ~63LL;
     const bool tcproj = m.tc0;
     for (int k = 0; k < 3; ++k) {
-      m.nw[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".W"), {C, C}, PK_NIN, 1, C, C, tcproj, wbase + (long long)k * C * C);
+      m.nw[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".W"), {C, C}, PK_NIN, 1, C, C, tcproj ? om : 0,
+                          wbase + (long long)k * C * C / ((tcproj && om == 2) ? 2 : 1));   // fp16: the three blocks stay contiguous as [3C][C] halves
       m.nb[k] = add_param(e, nmi(m.index, "NIN_" + std::to_string(k) + ".b"), {C}, PK_COPY, 0, 0, 0, 0, bbase + (long long)k * C);
     }
-    m.tc2 = tc_ok(e, C, 0, C, res, res, 1);   // output projection as a 1x1 conv over pixels
-    m.nw[3] = add_param(e, nmi(m.index, "NIN_3.W"), {C, C}, PK_NIN, 1, C, C, m.tc2);
+    m.tc2 = tc_ok(e, C, 0, C, res, res, 1) && (om != 2 || m.tcattn || T <= 64);   // output projection as a 1x1 conv over pixels
+    m.nw[3] = add_param(e, nmi(m.index, "NIN_3.W"), {C, C}, PK_NIN, 1, C, C, m.tc2 ? om : 0);
     m.nb[3] = add_param(e, nmi(m.index, "NIN_3.b"), {C}, PK_COPY, 0, 0, 0, 0);
     e->mods.push_back(m);
   };
@@ -244,8 +253,8 @@ int build_graph(b200_ncsnpp* e) {
   // input conv
   { Mod m; m.kind = M_CONV_IN; m.index = (int)e->mods.size(); m.cin1 = ch; m.cout = nf; m.res = c.image_size;
     // on tensor cores the 3x3 input conv is one K=32 contraction over im2col patches: weights packed [nf][32]
-    m.tc0 = (c.precision == 0) && (9 * ch <= 32) && (nf % 128 == 0);
-    m.w = m.tc0 ? add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV_FLAT32, 9, nf, ch, 1, -1, (long long)nf * 32)
+    m.tc0 = tcmode && (9 * ch <= 32) && (nf % 128 == 0);
+    m.w = m.tc0 ? add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV_FLAT32, 9, nf, ch, om, -1, (long long)nf * 32)
                 : add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV, 9, nf, ch, 0);
     m.b = add_param(e, nm("bias"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
   std::vector<int> hs_c = {nf};
@@ -265,9 +274,9 @@ int build_graph(b200_ncsnpp* e) {
         // FIR-padded stride-2 VALID conv: on tcgen05 via TMA element strides when the channel counts tile
         m.tc0 = tc_ok(e, pyr_ch, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 9);
         // image-channel pyramid level (3 channels): im2col patches + one K=32 contraction, like the input conv
-        m.tc2 = (c.precision == 0) && (9 * pyr_ch <= 32) && tc_ok(e, 32, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 1);
-        m.w = m.tc2 ? add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV_FLAT32, 9, in_ch, pyr_ch, 1, -1, (long long)in_ch * 32)
-                    : add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, m.tc0);
+        m.tc2 = tcmode && (9 * pyr_ch <= 32) && tc_ok(e, flatk, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 1);
+        m.w = m.tc2 ? add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV_FLAT32, 9, in_ch, pyr_ch, om, -1, (long long)in_ch * 32)
+                    : add_param(e, nm("Conv2d_0.weight"), {in_ch, pyr_ch, 3, 3}, PK_CONV, 9, in_ch, pyr_ch, m.tc0 ? om : 0);
         m.b = add_param(e, nm("Conv2d_0.bias"), {in_ch}, PK_COPY, 0, 0, 0, 0);
         e->mods.push_back(m);
         pyr_ch = in_ch;
@@ -313,13 +322,15 @@ struct Builder {
   char* stats_base = nullptr; long long stats_top = 0;   // bump region for GroupNorm quad sums, zeroed once per forward
   bool fused_stats = false;
   int lane = 0;                                // which half-batch plan this builder fills (ops or ops2)
+  int om = 1;                                  // operand store mode of tensor-core inputs: 1 TF32-grid fp32, 2 fp16
   std::string next_name;                       // label of the next op (shape summary for the per-op profile)
   void name(const char* fmt, ...) {
     char buf[160]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap); next_name = buf;
   }
   Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_, int lane_ = 0) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0), lane(lane_) {
     const char* v = getenv("B200_FUSED_GN_STATS");
-    fused_stats = (e_->cfg.precision == 0) && !(v && v[0] == '0');
+    fused_stats = (e_->cfg.precision != 1) && !(v && v[0] == '0');
+    om = e_->cfg.precision == 2 ? 2 : 1;
     if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
   }
   double* qalloc(int C) {
@@ -402,7 +413,7 @@ struct Builder {
       d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = out.H; d.W = out.W; d.nimg = B; d.taps = taps;
       d.stride = stride; d.valid_pad = stride == 2 ? 1 : 0; d.Hin = Hin ? Hin : out.H; d.Win = Hin ? Hin : out.W;
       d.w = e->W(pw); d.N_total = Cout; d.K_total = a1.C + a2.C; d.w_rows = (long long)taps * Cout; d.nbatch = 1;
-      d.epi_mode = -1;
+      d.epi_mode = -1; d.f16 = om == 2;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
       if (x3.p) {   // fused skip projection: its bias rides in the (image-independent) row-vector slot
         if (dense_row >= 0) { set_error("ncsnpp: fused skip projection on a conv with a time-embedding bias"); rc = 2; return; }
@@ -451,6 +462,7 @@ struct Builder {
       d.a1 = A; d.C1 = K; d.conv = 0; d.taps = 1; d.a_rows = a_rows; d.a_ld = lda; d.a_batch_rows = a_batch_rows;
       d.w = Wm; d.N_total = N; d.K_total = K; d.w_rows = w_rows; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
       d.nbatch = nbatch; d.M_per_batch = M; d.epi_mode = -1; d.qstats = qstats; d.no_pair = no_pair ? 1 : 0; d.epi = ep;
+      d.f16 = om == 2;
       if (dry) return;
       TcGemmPlan* pl = nullptr;
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
@@ -480,8 +492,8 @@ struct Builder {
     // B200_SKIP_TRUNC=1 (experiment): feed the 1x1 skip conv the un-rounded block input directly (the tensor
     // core truncates it to TF32) instead of a round-to-nearest copy -> one fewer activation write per block
     static const bool skip_trunc = [] { const char* v = getenv("B200_SKIP_TRUNC"); return v && v[0] == '1'; }();
-    if (m.has_conv2 && m.tc2 && !resample && !skip_trunc) raw = talloc(Cin, H, H);
-    gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? 1 : 0, a0, raw.p);
+    if (m.has_conv2 && m.tc2 && !resample && (!skip_trunc || om == 2)) raw = talloc(Cin, H, H);
+    gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? om : 0, a0, raw.p);
     Tensor xr;
     if (resample) {
       if (x2.p) { set_error("ncsnpp: resampling block with a two-source input"); rc = 2; return Tensor(); }
@@ -489,12 +501,12 @@ struct Builder {
       xr = talloc(Cin, Ho, Ho);
       if (m.up) {   // upsample_2d: up=2, pad=(2,1), gain*4 (up_or_down_sampling.py:218-224)
         const int p = e->firn - 2;
-        fir(a0.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc0, a0r.p, 4.f);
-        fir(x1.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc2, xr.p, 4.f);
+        fir(a0.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc0 ? om : 0, a0r.p, 4.f);
+        fir(x1.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc2 ? om : 0, xr.p, 4.f);
       } else {      // downsample_2d: down=2, pad=(1,1) (up_or_down_sampling.py:252-257)
         const int p = e->firn - 2;
-        fir(a0.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc0, a0r.p, 1.f);
-        fir(x1.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc2, xr.p, 1.f);
+        fir(a0.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc0 ? om : 0, a0r.p, 1.f);
+        fir(x1.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc2 ? om : 0, xr.p, 1.f);
       }
       tfree(a0); a0 = a0r;
     }
@@ -502,7 +514,7 @@ struct Builder {
     conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 0, h1, /*want_stats=*/true);
     tfree(a0);
     Tensor a1 = talloc(m.cout, Ho, Ho);
-    gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? 1 : 0, a1, nullptr);
+    gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? om : 0, a1, nullptr);
     tfree(h1);
     Tensor s;
     const float* residual = x1.p;
@@ -537,13 +549,16 @@ struct Builder {
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
     const bool tc = m.tcattn;
     const bool small = !m.tcattn && m.tc0 && T <= 64;   // few tokens: projections on tensor cores, core in one CTA per image
-    const float* Wqkv = e->W(m.nw[0]);          // [3C][C]
+    const float* Wqkv = e->W(m.nw[0]);          // [3C][C] (fp32 slots; fp16 elements when om == 2)
+    // Wv = rows 2C.. of the packed block: the offset counts ELEMENTS of the operand format
+    const float* wv = om == 2 && m.tc0 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(Wqkv) + 2LL * C * C)
+                                        : Wqkv + 2LL * C * C;
     const float* bqkv = e->W(m.nb[0]);          // [3C]
     const float sc = 1.0f / std::sqrt((float)C);   // int(C) ** -0.5
     const long long BT = (long long)B * T;
     const int Bc = B;
     Tensor a = talloc(C, x.H, x.W);
-    gn(x, none, m.gn0w, m.gn0b, 0, (tc || small) ? 1 : 0, a, nullptr);
+    gn(x, none, m.gn0w, m.gn0b, 0, (tc || small) ? om : 0, a, nullptr);
     long long ob; float* O = nullptr;
     if (small) {
       long long qb; float* qkv = falloc(BT * 3 * C, &qb);
@@ -551,7 +566,7 @@ struct Builder {
       gemm(true, a.p, C, BT, 0, Wqkv, C, 3LL * C, 0, 1, (int)BT, 3 * C, C, bqkv, nullptr, 0, 1.f, 0, qkv, 3 * C);
       tfree(a);
       O = falloc(BT * C, &ob);
-      const int rnd = m.tc2 ? 1 : 0;
+      const int rnd = m.tc2 ? om : 0;
       if (!dry) { if (int r = launch_attn_small_configure(T, C)) { rc = r; } }
       name("attn_small T=%d C=%d", T, C);
       op(1, [=](cudaStream_t st) { return launch_attn_small(qkv, O, Bc, T, C, sc, rnd, st); }, 4);
@@ -561,20 +576,23 @@ struct Builder {
       float* qk = falloc((long long)B * T * 2 * C, &qkb);
       float* vT = falloc((long long)B * C * T, &vtb);
       // q,k = a Wq^T + bq | a Wk^T + bk   (layerspp.py:78-79) in one N=2C contraction
-      gemm(tc, a.p, C, BT, 0 /* rows enumerated flat */, Wqkv, C, 2LL * C, 0, 1, (int)BT, 2 * C, C, bqkv, nullptr, 0, 1.f, tc, qk, 2 * C);
+      gemm(tc, a.p, C, BT, 0 /* rows enumerated flat */, Wqkv, C, 2LL * C, 0, 1, (int)BT, 2 * C, C, bqkv, nullptr, 0, 1.f, tc ? om : 0, qk, 2 * C);
       // v^T[b][c][t] = sum_i Wv[c][i] a[b][t][i]   (bias bv is added after the PV product: softmax rows sum to 1)
-      gemm(tc, Wqkv + 2LL * C * C, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc, vT, T, nullptr, 1 << 30, /*no_pair=*/true);
+      gemm(tc, wv, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc ? om : 0, vT, T, nullptr, 1 << 30, /*no_pair=*/true);
       tfree(a);
       // Fused core (default): logits, softmax, P.V, NIN_3, residual, rescale and quad sums in one kernel; the
       // [T,T] logits/probabilities and the attention output stay on chip.  B200_FUSED_ATTN=0 -> separate launches.
       static const bool fuse_attn = [] { const char* v = getenv("B200_FUSED_ATTN"); return !(v && v[0] == '0'); }();
+      if (om == 2 && !(tc && m.tc2 && fuse_attn && tc_attn_supported(T, C))) {
+        set_error("ncsnpp: fp16 operand mode needs the fused attention core (T=%d C=%d, B200_FUSED_ATTN)", T, C); rc = 2; return Tensor();
+      }
       if (tc && m.tc2 && fuse_attn && tc_attn_supported(T, C)) {
         Tensor out = talloc(C, x.H, x.W);
         if (fused_stats) out.qs = qalloc(C);
         if (!dry) {
           TcAttnDesc d; memset(&d, 0, sizeof(d));
           d.qk = qk; d.vT = vT; d.w3 = e->W(m.nw[3]); d.bv = bqkv + 2 * C; d.b3 = e->W(m.nb[3]); d.x = x.p; d.out = out.p;
-          d.qstats = out.qs; d.nimg = B; d.T = T; d.C = C; d.out_scale = inv_s2;
+          d.qstats = out.qs; d.nimg = B; d.T = T; d.C = C; d.out_scale = inv_s2; d.f16 = om == 2;
           TcAttnPlan* pl = nullptr;
           if (int r = tc_attn_plan_create(d, &pl)) { rc = r; return Tensor(); }
           e->attnplans.push_back(pl);
@@ -645,11 +663,11 @@ struct Builder {
       Tensor h0 = talloc(nf, R, R);
       if (m.tc0) {
         // im2col patches [B*R*R][32] (TF32 grid) then one K=32 tcgen05 contraction with the flat-packed weights
-        long long pb; float* patches = falloc((long long)B * R * R * 32, &pb);
-        const int Bc = B;
+        long long pb; float* patches = falloc((long long)B * R * R * 32, &pb);   // 128 B per pixel: 32 fp32 or 64 fp16
+        const int Bc = B, omc = om;
         name("im2col 3x3 %d @%d", ch, R);
-        op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, R, R, 1, 1, st); }, 6);
-        Tensor pt; pt.p = patches; pt.C = 32; pt.H = R; pt.W = R;      // patches as a 32-channel NHWC image: a 1x1 conv
+        op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, R, R, 1, 1, omc, st); }, 6);
+        Tensor pt; pt.p = patches; pt.C = om == 2 ? 64 : 32; pt.H = R; pt.W = R;   // patches as a one-K-step NHWC image: a 1x1 conv
         conv(true, pt, Tensor(), 1, m.w, m.b, nf, -1, nullptr, 1.f, 0, h0, /*want_stats=*/true);
         ffree(patches, pb);
       } else {
@@ -691,16 +709,16 @@ struct Builder {
           const bool tcp = mp.tc0 && !pyr_nchw;
           const bool flat = mp.tc2 && pyr_nchw;
           if (pyr_nchw) fir(pyr.p, B * pyr.C, Hin, Hin, 1, 1, 1, (p + 1) / 2, p / 2, 0, fbuf, 1.f);
-          else fir(pyr.p, B, Hin, Hin, pyr.C, 1, 1, (p + 1) / 2, p / 2, tcp ? 1 : 0, fbuf, 1.f);
+          else fir(pyr.p, B, Hin, Hin, pyr.C, 1, 1, (p + 1) / 2, p / 2, tcp ? om : 0, fbuf, 1.f);
           Tensor np = talloc(mp.cout, h.H, h.W);
           if ((Hp - 3) / 2 + 1 != h.H) { set_error("ncsnpp: pyramid geometry mismatch (%d vs %d)", (Hp - 3) / 2 + 1, h.H); return 2; }
           const float ps = c.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
           if (flat) {
             long long pb2; float* patches = falloc((long long)B * h.H * h.W * 32, &pb2);
-            const int Bc = B, pc = pyr.C, oh = h.H, ow = h.W;
+            const int Bc = B, pc = pyr.C, oh = h.H, ow = h.W, omc = om;
             name("im2col 3x3 s2 %d @%d", pc, oh);
-            op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(fbuf, patches, Bc, pc, Hp, Hp, oh, ow, 2, 0, st); }, 6);
-            Tensor pt; pt.p = patches; pt.C = 32; pt.H = h.H; pt.W = h.W;
+            op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(fbuf, patches, Bc, pc, Hp, Hp, oh, ow, 2, 0, omc, st); }, 6);
+            Tensor pt; pt.p = patches; pt.C = om == 2 ? 64 : 32; pt.H = h.H; pt.W = h.W;
             conv(true, pt, Tensor(), 1, mp.w, mp.b, mp.cout, -1, h.p, ps, 0, np, /*want_stats=*/true);
             ffree(patches, pb2);
           } else if (tcp) {
@@ -846,7 +864,7 @@ int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* 
     return 0;
   }
   if (p.pack == PK_CONV_FLAT32)   // OIHW (3x3, I*9 <= 32) -> [O][32] with k = tap*I + i (rest of the row stays zero)
-    return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st, p.I, 32);
+    return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st, p.I, p.round == 2 ? 64 : 32);
   if (p.pack == PK_CONV)   // OIHW -> [tap][O][I]
     return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st);
   // NIN W[in][out] -> [out][in]

@@ -48,6 +48,8 @@ struct TcParams {
   int N_total, tiles_n;
   int nbatch, tiles_m_per_batch, M_per_batch;
   int a_batch_rows, w_batch_rows;
+  int f16;                                 // 1: A and W are fp16 (tcgen05 kind::f16, 64-channel K steps); 0: TF32-grid fp32 (32-channel K steps)
+  int bke;                                 // channels per K step: one 128-byte swizzle row = 32 fp32 or 64 fp16
   int epi_mode;                            // 0: direct register->global stores, 1: smem-staged TMA store (+TMA residual)
   int swap;                                // 1: operands swapped (D^T = W X^T): 128 output channels x 256 pixels per tile
   double* qstats;                          // optional [img][N_total/4][2] GroupNorm quad sums (sum, sum of squares)
@@ -122,6 +124,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the four MMAs of one 128-byte K step: 4 x K=8 (tf32) or 4 x K=16 (f16); either way +32 B per slice
+template <bool F16>
+__device__ __forceinline__ void umma_kstep(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, int it) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // advance 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+    if (F16) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+    else umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+  }
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -150,6 +169,11 @@ template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc() {
   // D fp32 (1<<4), A tf32 (2<<7), B tf32 (2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24.
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_f16() {
+  // kind::f16: D fp32 (1<<4), A fp16 (0<<7), B fp16 (0<<10)
+  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 template <int BN, int STAGES, bool STAGED>
@@ -282,6 +306,7 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
 
   const int kiters = (p.kchunks1 + p.kchunks2) * p.taps + p.kchunks3 + p.kchunks4;
   const int HW = p.H * p.W;
+  const int bke = p.bke;
 
   if (warp == 0 && lane == 0) {
     // ======================= TMA producer =======================
@@ -324,13 +349,13 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             if (p.swap) {
               // first 16 KiB: 128 output channels x 32 k of W (UMMA A); next 32 KiB: 256 pixels x 32 k (UMMA B)
-              tma_load_2d(tmW, sa, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
-              tma_load_4d(tmA, sb, &full_bar[stage], kc * BKE, w0 + dw, h0 + dh, img0);
-              tma_load_4d(tmA, sb + A_STAGE_BYTES, &full_bar[stage], kc * BKE, w1 + dw, h1 + dh, img1);
+              tma_load_2d(tmW, sa, &full_bar[stage], wcol0 + kc * bke, wrow0 + tap * p.N_total);
+              tma_load_4d(tmA, sb, &full_bar[stage], kc * bke, w0 + dw, h0 + dh, img0);
+              tma_load_4d(tmA, sb + A_STAGE_BYTES, &full_bar[stage], kc * bke, w1 + dw, h1 + dh, img1);
             } else {
-              if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
-              else tma_load_4d(tmA, sa, &full_bar[stage], kc * BKE, arow0, 0, 0);
-              tma_load_2d(tmW, sb, &full_bar[stage], wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+              if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * bke, w0 * p.stride + dw, h0 * p.stride + dh, img0);
+              else tma_load_4d(tmA, sa, &full_bar[stage], kc * bke, arow0, 0, 0);
+              tma_load_2d(tmW, sb, &full_bar[stage], wcol0 + kc * bke, wrow0 + tap * p.N_total);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -339,7 +364,8 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
     }
   } else if (warp == 1 && lane == 0) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = make_idesc<BN>();
+    const bool f16 = p.f16 != 0;
+    const uint32_t idesc = f16 ? make_idesc_f16<BN>() : make_idesc<BN>();
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -351,11 +377,8 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(sa);
         const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
-#pragma unroll
-        for (int k = 0; k < BKE / UMMA_K; ++k) {
-          // advance 8 fp32 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
-          umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-        }
+        if (f16) umma_kstep<true>(d_tmem, adesc, bdesc, idesc, it);
+        else umma_kstep<false>(d_tmem, adesc, bdesc, idesc, it);
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -458,8 +481,9 @@ __global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __
             if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
             if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
-            if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            *reinterpret_cast<float4*>(dst + c) = o;
+            if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            if (e.round_tf32 == 2) store_operand4(e.out, gm * e.ld_out + n0 + c, o, 2);   // fp16 operand for the next contraction
+            else *reinterpret_cast<float4*>(dst + c) = o;
             st[c >> 2] = (o.x + o.y) + (o.z + o.w);
             st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
           }
@@ -647,13 +671,13 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+               const uint32_t* box, const uint32_t* elem_strides = nullptr, bool f16 = false) {
   auto fn = get_encode_fn();
   B200_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm_tc: operand base %p not 16-byte aligned", (const void*)base);
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims,
+  CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d "
@@ -683,7 +707,8 @@ int tc_gemm_default_epi_mode();
 bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
   static const char* w;
   auto fail = [&](const char* m) { w = m; if (why) *why = w; return false; };
-  if (d.C1 % BKE || d.C2 % BKE || d.C1 <= 0) return fail("channel counts must be multiples of 32");
+  const int bke = d.f16 ? 64 : BKE;
+  if (d.C1 % bke || d.C2 % bke || d.C1 <= 0) return fail("channel counts must be multiples of 32 (tf32) / 64 (f16)");
   if (d.N_total % 128) return fail("N must be a multiple of 128");
   if (d.taps != 1 && d.taps != 9) return fail("only 1x1 and 3x3 filters");
   if (d.conv) {
@@ -697,15 +722,16 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
     } else if (BM % HW) return fail("image size does not divide 128 pixels");
   } else {
     if (d.nbatch > 1 && (d.M_per_batch % BM)) return fail("batched gemm needs M_per_batch % 128 == 0");
-    if (d.a_ld % 4) return fail("A row pitch must be a multiple of 4 floats");
+    if (d.a_ld % (d.f16 ? 8 : 4)) return fail("A row pitch must be a multiple of 16 bytes");
   }
   if (d.a3) {
     if (!d.conv || d.stride == 2 || !d.w2) return fail("extra 1x1 phase needs a stride-1 convolution and its weights");
-    if (d.C3 % BKE || d.C3 <= 0 || (d.a4 && d.C4 % BKE)) return fail("extra-phase channel counts must be multiples of 32");
+    if (d.C3 % bke || d.C3 <= 0 || (d.a4 && d.C4 % bke)) return fail("extra-phase channel counts must be multiples of 32 (tf32) / 64 (f16)");
   }
   if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
   if (d.qstats && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("quad stats need rows_per_img % 32 == 0 or == 16");
-  if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 floats");
+  if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 elements");
+  if (d.epi.round_tf32 == 2 && d.qstats) return fail("fp16 outputs carry no GroupNorm sums");
   return true;
 }
 
@@ -720,6 +746,11 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   p.conv = d.conv; p.H = d.conv ? d.H : 1; p.W = d.conv ? d.W : 1; p.taps = d.taps;
   p.S = d.taps == 9 ? 3 : 1; p.pad = (d.taps == 9 && !d.valid_pad) ? 1 : 0;
   p.stride = d.stride == 2 ? 2 : 1;
+  p.f16 = d.f16 ? 1 : 0;
+  const bool f16 = d.f16 != 0;
+  const int bke = f16 ? 64 : BKE;            // elements per 128-byte K step
+  const uint64_t es = f16 ? 2 : 4;           // operand element size
+  p.bke = bke;
   {
     // Swapped operands for 128-channel outputs: M=128,N=128 MMAs are shared-memory-bandwidth bound
     // (8 KB of operand reads per 131k MACs); computing D^T = W X^T makes them M=128 (channels), N=256 (pixels).
@@ -735,7 +766,8 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // profiles/r01_c7_conv_isolated.log); 128-channel convolutions use the swapped-operand form.
     // B200_TC_EPILOGUE=staged selects the smem-staged TMA-store epilogue for A/B runs.
     p.swap = can_swap ? 1 : 0;
-    p.epi_mode = req == 1 ? 1 : 0;
+    p.epi_mode = (req == 1 && d.epi.round_tf32 != 2) ? 1 : 0;   // fp16 outputs: direct stores only
+    if (p.swap && d.epi.round_tf32 == 2) p.swap = 0;            // (the swapped epilogue writes fp32)
     if (p.swap) pl->bn = 256;
     p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
     // CTA pairs (cta_group::2) for 256-column tiles: B200_TC_2CTA=1 opts in (0 = off, default until validated per round)
@@ -750,7 +782,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
                   (d.conv || d.nbatch == 1 || tmb % 2 == 0) && (m_tiles / 2) * n_tiles >= num_sms() / 2;
     if (pl->two_cta) p.epi_mode = 0;
   }
-  p.kchunks1 = d.C1 / BKE; p.kchunks2 = d.a2 ? d.C2 / BKE : 0; p.C1 = d.C1;
+  p.kchunks1 = d.C1 / bke; p.kchunks2 = d.a2 ? d.C2 / bke : 0; p.C1 = d.C1;
   p.N_total = d.N_total; p.tiles_n = p.swap ? d.N_total / 128 : d.N_total / pl->bn;
   p.a_batch_rows = d.a_batch_rows; p.w_batch_rows = d.w_batch_rows;
   p.epi = d.epi;
@@ -763,7 +795,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     uint32_t box[4];
     if (HW >= BM) { box[1] = std::min(d.W, BM); box[2] = BM / box[1]; box[3] = 1; }
     else { box[1] = d.W; box[2] = d.H; box[3] = BM / HW; }
-    box[0] = BKE;
+    box[0] = (uint32_t)bke;
     // stride 2: the box *traverses* 2x as many pixels and TMA keeps every other one
     const uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
     box[1] *= p.stride; box[2] *= p.stride;
@@ -773,19 +805,19 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
       const int C = s ? d.C2 : d.C1;
       if (!base) continue;
       uint64_t dims[4] = {(uint64_t)C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)d.nimg};
-      uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)Win * C * 4, (uint64_t)Hin * Win * C * 4};
-      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box, estr);
+      uint64_t str[3] = {(uint64_t)C * es, (uint64_t)Win * C * es, (uint64_t)Hin * Win * C * es};
+      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box, estr, f16);
       if (rc) { delete pl; return rc; }
     }
   } else {
     p.nbatch = d.nbatch; p.M_per_batch = d.M_per_batch; p.tiles_m_per_batch = (d.M_per_batch + BM - 1) / BM;
-    uint32_t box[4] = {BKE, BM, 1, 1};
+    uint32_t box[4] = {(uint32_t)bke, BM, 1, 1};
     for (int s = 0; s < 2; ++s) {
       const float* base = s ? d.a2 : d.a1;
       if (!base) continue;
       uint64_t dims[4] = {(uint64_t)(s ? d.C2 : d.C1), (uint64_t)d.a_rows, 1, 1};
-      uint64_t str[3] = {(uint64_t)d.a_ld * 4, (uint64_t)d.a_ld * 4 * d.a_rows, (uint64_t)d.a_ld * 4 * d.a_rows};
-      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box);
+      uint64_t str[3] = {(uint64_t)d.a_ld * es, (uint64_t)d.a_ld * es * d.a_rows, (uint64_t)d.a_ld * es * d.a_rows};
+      rc = encode_map(s ? &p.tmA2 : &p.tmA1, base, 4, dims, str, box, nullptr, f16);
       if (rc) { delete pl; return rc; }
     }
   }
@@ -797,30 +829,30 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     uint32_t box[4];
     if (HW >= BM) { box[1] = std::min(d.W, BM); box[2] = BM / box[1]; box[3] = 1; }
     else { box[1] = d.W; box[2] = d.H; box[3] = BM / HW; }
-    box[0] = BKE;
+    box[0] = (uint32_t)bke;
     for (int s = 0; s < 2; ++s) {
       const float* base = s ? d.a4 : d.a3;
       const int C = s ? d.C4 : d.C3;
       if (!base) continue;
       uint64_t dims[4] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.nimg};
-      uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)d.W * C * 4, (uint64_t)d.H * d.W * C * 4};
-      rc = encode_map(s ? &p.tmA4 : &p.tmA3, base, 4, dims, str, box);
+      uint64_t str[3] = {(uint64_t)C * es, (uint64_t)d.W * C * es, (uint64_t)d.H * d.W * C * es};
+      rc = encode_map(s ? &p.tmA4 : &p.tmA3, base, 4, dims, str, box, nullptr, f16);
       if (rc) { delete pl; return rc; }
     }
-    p.kchunks3 = d.C3 / BKE; p.kchunks4 = d.a4 ? d.C4 / BKE : 0; p.C3 = d.C3;
+    p.kchunks3 = d.C3 / bke; p.kchunks4 = d.a4 ? d.C4 / bke : 0; p.C3 = d.C3;
   }
   {
     uint64_t dims[2] = {(uint64_t)d.K_total, (uint64_t)d.w_rows};
-    uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * 4};
-    uint32_t box[2] = {BKE, (uint32_t)(pl->two_cta ? pl->bn / 2 : (p.swap ? 128 : pl->bn))};
-    rc = encode_map(&p.tmW, d.w, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)(d.w_ld ? d.w_ld : d.K_total) * es};
+    uint32_t box[2] = {(uint32_t)bke, (uint32_t)(pl->two_cta ? pl->bn / 2 : (p.swap ? 128 : pl->bn))};
+    rc = encode_map(&p.tmW, d.w, 2, dims, str, box, nullptr, f16);
     if (rc) { delete pl; return rc; }
     p.tmW2 = p.tmW;
     if (d.a3) {
       const uint64_t K3 = (uint64_t)d.C3 + (d.a4 ? d.C4 : 0);
       uint64_t dims2[2] = {K3, (uint64_t)d.N_total};
-      uint64_t str2[1] = {K3 * 4};
-      rc = encode_map(&p.tmW2, d.w2, 2, dims2, str2, box);
+      uint64_t str2[1] = {K3 * es};
+      rc = encode_map(&p.tmW2, d.w2, 2, dims2, str2, box, nullptr, f16);
       if (rc) { delete pl; return rc; }
     }
   }
@@ -867,7 +899,7 @@ int tc_gemm_default_epi_mode() {
 }
 
 // ---- fused attention core (attn_tc.cuh) ----
-struct TcAttnPlan { AttnParams prm; };
+struct TcAttnPlan { AttnParams prm; bool f16; };
 
 bool tc_attn_supported(int T, int C) { return T == AT_T && C == AT_C; }
 
@@ -878,25 +910,29 @@ int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out) {
   TcAttnPlan* pl = new TcAttnPlan();
   AttnParams& p = pl->prm;
   memset(&p, 0, sizeof(p));
+  pl->f16 = d.f16 != 0;
+  const bool f16 = pl->f16;
+  const uint64_t es = f16 ? 2 : 4;
+  const uint32_t bka = f16 ? 64 : 32;
   int rc = 0;
   {
     uint64_t dims[2] = {(uint64_t)2 * AT_C, (uint64_t)d.nimg * AT_T};
-    uint64_t str[1] = {(uint64_t)2 * AT_C * 4};
-    uint32_t boxq[2] = {BKE, (uint32_t)BM}, boxk[2] = {BKE, 256};
-    rc = encode_map(&p.tmQ, d.qk, 2, dims, str, boxq);
-    if (!rc) rc = encode_map(&p.tmK, d.qk, 2, dims, str, boxk);
+    uint64_t str[1] = {(uint64_t)2 * AT_C * es};
+    uint32_t boxq[2] = {bka, (uint32_t)BM}, boxk[2] = {bka, 256};
+    rc = encode_map(&p.tmQ, d.qk, 2, dims, str, boxq, nullptr, f16);
+    if (!rc) rc = encode_map(&p.tmK, d.qk, 2, dims, str, boxk, nullptr, f16);
   }
   if (!rc) {
     uint64_t dims[2] = {(uint64_t)AT_T, (uint64_t)d.nimg * AT_C};
-    uint64_t str[1] = {(uint64_t)AT_T * 4};
-    uint32_t box[2] = {BKE, 256};
-    rc = encode_map(&p.tmVT, d.vT, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)AT_T * es};
+    uint32_t box[2] = {bka, 256};
+    rc = encode_map(&p.tmVT, d.vT, 2, dims, str, box, nullptr, f16);
   }
   if (!rc) {
     uint64_t dims[2] = {(uint64_t)AT_C, (uint64_t)AT_C};
-    uint64_t str[1] = {(uint64_t)AT_C * 4};
-    uint32_t box[2] = {BKE, 256};
-    rc = encode_map(&p.tmW3, d.w3, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)AT_C * es};
+    uint32_t box[2] = {bka, 256};
+    rc = encode_map(&p.tmW3, d.w3, 2, dims, str, box, nullptr, f16);
   }
   if (rc) { delete pl; return rc; }
   p.bv = d.bv; p.b3 = d.b3; p.x = d.x; p.out = d.out; p.qstats = d.qstats; p.nimg = d.nimg;
@@ -909,7 +945,8 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
   const long long tiles = 2LL * pl->prm.nimg;
   const int grid = (int)std::min<long long>(tiles, num_sms());
-  attn_tc_kernel<<<grid, 384, AttnSmem::TOTAL, st>>>(pl->prm);
+  if (pl->f16) attn_tc_kernel<true><<<grid, 384, AttnSmem<true>::TOTAL, st>>>(pl->prm);
+  else attn_tc_kernel<false><<<grid, 384, AttnSmem<false>::TOTAL, st>>>(pl->prm);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -924,7 +961,8 @@ static int tc_configure() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6, false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<256, 6>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<128, 8>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<false>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<true>::TOTAL));
   configured = true;
   return 0;
 }

@@ -55,6 +55,13 @@ __device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t adesc, uint
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // commit: arrive (once) on the barrier at this shared::cta offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -133,9 +140,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             uint8_t* sb = sa + A_STAGE_BYTES;
             const uint32_t lead_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);     // bytes of BOTH CTAs land on this barrier
-            if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * BKE, w0 * p.stride + dw, h0 * p.stride + dh, img0);
-            else tma2_load_4d(tmA, sa, lead_full, kc * BKE, arow0, 0, 0);
-            tma2_load_2d(tmW, sb, lead_full, wcol0 + kc * BKE, wrow0 + tap * p.N_total);
+            if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * p.bke, w0 * p.stride + dw, h0 * p.stride + dh, img0);
+            else tma2_load_4d(tmA, sa, lead_full, kc * p.bke, arow0, 0, 0);
+            tma2_load_2d(tmW, sb, lead_full, wcol0 + kc * p.bke, wrow0 + tap * p.N_total);
             if (!leader) mbar_arrive_cluster(lead_full);                          // second of the barrier's two arrivals
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -145,7 +152,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   } else if (warp == 1 && lane == 0 && leader) {
     // ======================= MMA issuer (leader CTA, for the pair) =======================
     // instruction: M = 256 (128 rows per CTA), N = BN, K = 8 tf32; D fp32 in each CTA's own TMEM
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const bool f16 = p.f16 != 0;
+    const uint32_t idesc = (1u << 4) | (f16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -157,8 +165,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(sa);
         const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+        if (f16) {
 #pragma unroll
-        for (int k = 0; k < BKE / UMMA_K; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        }
         umma2_commit_mc(&empty_bar[stage]);                     // frees the slot in both CTAs
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -204,8 +217,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
             if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
-            if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            *reinterpret_cast<float4*>(dst + c) = o;
+            if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            if (e.round_tf32 == 2) store_operand4(e.out, gm * e.ld_out + n0 + c, o, 2);   // fp16 operand for the next contraction
+            else *reinterpret_cast<float4*>(dst + c) = o;
             st[c >> 2] = (o.x + o.y) + (o.z + o.w);
             st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
           }

@@ -31,7 +31,7 @@ int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cuda
 int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, long long so, long long si,
                        long long stp, int round_out, cudaStream_t st, long long dt = 0, long long dO = 0);
 int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
-                          int pad, cudaStream_t st);
+                          int pad, int mode, cudaStream_t st);
 int launch_attn_small_configure(int T, int C);
 int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st);
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
@@ -80,6 +80,7 @@ struct TcGemmDesc {
   // optional extra 1x1 phase accumulated into the same tile (a resblock's skip projection fused into its second
   // 3x3 convolution): out += [a3 | a4] w2^T, w2 = [N_total][C3 + C4]; same spatial size as the output, stride 1
   const float* a3; int C3; const float* a4; int C4; const float* w2;
+  int f16;                  // 1: a1..a4, w, w2 hold fp16 elements (tcgen05 kind::f16, 64-channel K steps); pitches stay in elements
   int epi_mode;             // 0 direct stores, 1 smem-staged TMA store, -1 = library default
   int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
@@ -102,6 +103,7 @@ struct TcAttnDesc {
   double* qstats;           // optional GroupNorm quad sums of out
   int nimg, T, C;
   float out_scale;
+  int f16;                  // 1: qk, vT, w3 hold fp16 elements
 };
 bool tc_attn_supported(int T, int C);
 int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out);

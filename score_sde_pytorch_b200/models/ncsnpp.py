@@ -102,8 +102,10 @@ def _pyramid_down(cin, cout):
 
 @utils.register_model(name='ncsnpp')
 class NCSNpp(nn.Module):
-  """NCSN++ model (engine-backed).  ``precision``: ``'tf32'`` (tcgen05 tensor cores,
-  default) or ``'fp32'`` (strict fp32 on CUDA cores; validation mode)."""
+  """NCSN++ model (engine-backed).  ``precision``: ``'tf32'`` (tcgen05 tensor cores on TF32-rounded
+  fp32 operands, default), ``'f16'`` (tcgen05 on fp16 operands: the same 11-bit significand as TF32
+  with fp32 accumulation and fp32 activations between layers, half the operand traffic and twice the
+  MMA rate) or ``'fp32'`` (strict fp32 on CUDA cores; validation mode)."""
 
   def __init__(self, config, precision=None, keep_activations=False):
     super().__init__()
@@ -179,9 +181,9 @@ class NCSNpp(nn.Module):
     c.fir_taps = len(m.fir_kernel)
     for i, v in enumerate(m.fir_kernel):
       c.fir_kernel[i] = float(v)
-    if self.precision not in ('tf32', 'fp32'):
-      raise ValueError(f"precision must be 'tf32' or 'fp32', got {self.precision!r}")
-    c.precision = 0 if self.precision == 'tf32' else 1
+    if self.precision not in ('tf32', 'fp32', 'f16'):
+      raise ValueError(f"precision must be 'tf32', 'fp32' or 'f16', got {self.precision!r}")
+    c.precision = {'tf32': 0, 'fp32': 1, 'f16': 2}[self.precision]
     c.keep_activations = int(self.keep_activations)
     return c
 

@@ -29,10 +29,11 @@ def to_nchw(x):
   return x.permute(0, 3, 1, 2).contiguous()
 
 
-def pack_conv_weight(w, round_tf32_=False):
+def pack_conv_weight(w, round_tf32_=False, f16=False):
+  """OIHW fp32 -> [taps][O][I]; f16=True packs IEEE fp16 elements (operand mode 2)."""
   o, i, k, _ = w.shape
-  out = torch.empty(k * k, o, i, device=w.device, dtype=torch.float32)
-  _lib.call('b200_pack_conv_weight_f32', _lib.ptr(w.contiguous()), _lib.ptr(out), o, i, k, int(round_tf32_),
+  out = torch.empty(k * k, o, i, device=w.device, dtype=torch.float16 if f16 else torch.float32)
+  _lib.call('b200_pack_conv_weight_f32', _lib.ptr(w.contiguous()), _lib.ptr(out), o, i, k, 2 if f16 else int(round_tf32_),
             _lib.stream_ptr(w.device))
   return out
 
@@ -58,12 +59,15 @@ def conv_skip_nhwc(x, s1, s2, wp, bias, wskip, bias_skip, cout, residual=None, s
 
 
 def attention_core(qk, vT, w3, bv, b3, x, out_scale, want_stats=False):
-  """qk [nimg*T, 2C], vT [nimg, C, T], w3 [C, C] (out, in), x [nimg*T, C] -> out [nimg*T, C] (+ quad sums)."""
+  """qk [nimg*T, 2C], vT [nimg, C, T], w3 [C, C] (out, in), x [nimg*T, C] -> out [nimg*T, C] (+ quad sums).
+  fp16 qk/vT/w3 select the kind::f16 variant."""
   nimg, C, T = vT.shape
+  f16 = qk.dtype == torch.float16
+  assert vT.dtype == qk.dtype and w3.dtype == qk.dtype
   out = torch.empty_like(x)
   qs = torch.zeros(nimg, C // 4, 2, device=x.device, dtype=torch.float64) if want_stats else None
   _lib.call('b200_attention_core_f32', _lib.ptr(qk), _lib.ptr(vT), _lib.ptr(w3), _lib.ptr(bv), _lib.ptr(b3), _lib.ptr(x),
-            _lib.ptr(out), _lib.ptr(qs), nimg, T, C, float(out_scale), _lib.stream_ptr(x.device))
+            _lib.ptr(out), _lib.ptr(qs), nimg, T, C, float(out_scale), int(f16), _lib.stream_ptr(x.device))
   return (out, qs) if want_stats else out
 
 

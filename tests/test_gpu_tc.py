@@ -66,6 +66,33 @@ def test_tcgen05_conv_matches_cuda_core_conv(dev, case):
   assert torch.equal(y2, rt(y))
 
 
+F16_CASES = [c for c in CASES if c['C1'] % 64 == 0 and c['C2'] % 64 == 0]
+
+
+@pytest.mark.parametrize('case', F16_CASES, ids=lambda c: 'B{B}_{H}x{W}_{C1}+{C2}->{Cout}_k{k}'.format(**c))
+def test_tcgen05_f16_conv_matches_torch(dev, case):
+  """kind::f16 form of the same contraction: activations and packed weights are IEEE fp16 in memory (64-channel
+  K steps), accumulation and epilogue are fp32.  fp16 x fp16 products are exact in fp32, so against torch's fp32
+  convolution of the SAME fp16-representable values only the summation order differs."""
+  import gpu_util
+  B, H, W, C1, C2, Cout, k = (case[x] for x in ('B', 'H', 'W', 'C1', 'C2', 'Cout', 'k'))
+  torch.manual_seed(6)
+  x1 = torch.randn(B, H, W, C1, device=dev).half()
+  x2 = torch.randn(B, H, W, C2, device=dev).half() if C2 else None
+  w = (torch.randn(Cout, C1 + C2, k, k, device=dev) / np.sqrt((C1 + C2) * k * k)).half().float()
+  bias = torch.randn(Cout, device=dev)
+  rowvec = torch.randn(B, Cout, device=dev)
+  res = torch.randn(B, H, W, Cout, device=dev)
+  wp = gpu_util.pack_conv_weight(w, f16=True)
+  assert torch.equal(wp.float().reshape(k * k, Cout, C1 + C2), w.permute(2, 3, 0, 1).reshape(k * k, Cout, C1 + C2))
+  kw = dict(rowvec=rowvec, rowvec_ld=Cout, residual=res, scale=0.7071067690849304)
+  y = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=2, **kw)
+  torch.cuda.synchronize()
+  xc = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], 3)
+  tref = (F.conv2d(xc.permute(0, 3, 1, 2), w, bias, padding=k // 2).permute(0, 2, 3, 1) + rowvec[:, None, None, :] + res) * 0.7071067690849304
+  assert torch.allclose(y, tref, rtol=2e-4, atol=2e-4), (y - tref).abs().max().item()
+
+
 SKIP_CASES = [
     dict(B=2, H=16, W=16, C=256, S1=256, S2=256, Cout=256),     # up-path block: concat skip input, single-CTA tiles
     dict(B=160, H=16, W=16, C=256, S1=256, S2=128, Cout=256),   # enough tiles for the CTA-pair kernel
@@ -141,6 +168,32 @@ def test_fused_attention_core_matches_torch(dev, nimg):
   assert ((out2 - ref2).norm() / ref2.norm()).item() < 3e-4
 
 
+@pytest.mark.parametrize('nimg', [2, 150])
+def test_fused_attention_core_f16_matches_torch(dev, nimg):
+  """The kind::f16 variant (fp16 q|k, v^T, W3 in memory; E and O' staged as fp16; 3-stage ring)."""
+  import gpu_util
+  torch.manual_seed(31 + nimg)
+  T = C = 256
+  q = (torch.randn(nimg, T, C, device=dev) * 1.5).half()
+  k = (torch.randn(nimg, T, C, device=dev) * 1.5).half()
+  v = torch.randn(nimg, T, C, device=dev).half()
+  w3 = (torch.randn(C, C, device=dev) / 16).half()
+  bv, b3 = torch.randn(C, device=dev), torch.randn(C, device=dev)
+  x = torch.randn(nimg * T, C, device=dev)
+  qk = torch.cat([q, k], 2).reshape(nimg * T, 2 * C).contiguous()
+  vT = v.transpose(1, 2).contiguous()
+  sc = 0.7071067690849304
+  out, qs = gpu_util.attention_core(qk, vT, w3, bv, b3, x, sc, want_stats=True)
+  torch.cuda.synchronize()
+  P = torch.softmax(torch.bmm(q.float(), k.float().transpose(1, 2)) * (C ** -0.5), dim=-1)
+  h = torch.bmm(P, v.float()) + bv
+  ref = ((h.reshape(nimg * T, C) @ w3.float().t() + b3) + x) * sc
+  err = ((out - ref).norm() / ref.norm()).item()
+  assert err < 3e-4, err
+  o4 = out.reshape(nimg, T, C // 4, 4).double()
+  assert torch.allclose(qs[..., 0], o4.sum((1, 3)), rtol=1e-5, atol=1e-3)
+
+
 def test_tcgen05_batched_gemm_attention_shapes(dev):
   import gpu_util
   rt = gpu_util.round_tf32
@@ -164,10 +217,13 @@ def test_tcgen05_batched_gemm_attention_shapes(dev):
   assert torch.allclose(out, a @ Wqk.t() + b, rtol=2e-4, atol=2e-3)
 
 
-def test_forward_tf32_cifar10_matches_oracle_within_parity_bound(dev):
+@pytest.mark.parametrize('precision', ['tf32', 'f16'])
+def test_forward_tf32_cifar10_matches_oracle_within_parity_bound(dev, precision):
+  """Both tensor-core operand formats (TF32-rounded fp32, fp16: 11-bit significands either way) against the
+  strict-fp32 oracle and the reference's own CPU output, same bound."""
   g = golden('ncsnpp_cifar10_ve.npz')
   cfg = golden_config('cifar10_ve')
-  model = seeded_model(cfg, precision='tf32', keep_activations=True).to(dev)
+  model = seeded_model(cfg, precision=precision, keep_activations=True).to(dev)
   sd = {k: v.to(dev) for k, v in model.state_dict().items()}
   x, sigma = torch.from_numpy(g['x']).to(dev), torch.from_numpy(g['sigma']).to(dev)
   taps = {}
@@ -183,7 +239,7 @@ def test_forward_tf32_cifar10_matches_oracle_within_parity_bound(dev):
   worst = sorted(rows, key=lambda r: -r[1])[:5]
   assert all(r[1] < 5e-3 for r in rows), f'worst modules (index, rel-L2): {worst}'
   e_or, e_gold = rel_l2(y, ref), rel_l2(y, torch.from_numpy(g['y']).to(dev))
-  print(f'cifar10 tf32 single-eval rel-L2 vs GPU oracle {e_or:.3e}, vs reference CPU golden {e_gold:.3e}; worst taps {worst}')
+  print(f'cifar10 {precision} single-eval rel-L2 vs GPU oracle {e_or:.3e}, vs reference CPU golden {e_gold:.3e}; worst taps {worst}')
   assert e_or < TOL_PARITY and e_gold < TOL_PARITY
 
 
@@ -196,11 +252,12 @@ def test_forward_fp32_cifar10_matches_oracle(dev):
   assert rel_l2(y, torch.from_numpy(g['y']).to(dev)) < 1e-4
 
 
-def test_pc_sampler_tf32_cifar10_K_steps_within_parity_bound(dev):
+@pytest.mark.parametrize('precision', ['tf32', 'f16'])
+def test_pc_sampler_tf32_cifar10_K_steps_within_parity_bound(dev, precision):
   """K PC iterations (2K network evaluations) of the headline sampler at B=8 vs the strict-fp32 oracle."""
   from score_sde_pytorch_b200 import sampling, sde_lib, native
   cfg = golden_config('cifar10_ve')
-  model = seeded_model(cfg, precision='tf32').to(dev)
+  model = seeded_model(cfg, precision=precision).to(dev)
   sd = {k: v.to(dev) for k, v in model.state_dict().items()}
   shape = (8, 3, 32, 32)
   K = 10
@@ -216,5 +273,5 @@ def test_pc_sampler_tf32_cifar10_K_steps_within_parity_bound(dev):
   torch.cuda.manual_seed(1)
   x, x_mean = plan.run(x0, first_step=0, num_steps=K)
   e = rel_l2(x_mean, ref)
-  print(f'cifar10 tf32 {K}-step PC rel-L2 vs oracle: {e:.3e}')
+  print(f'cifar10 {precision} {K}-step PC rel-L2 vs oracle: {e:.3e}')
   assert e < TOL_PARITY
