@@ -275,6 +275,26 @@ def run_gpu_arm(args):
                     hbm_fraction_of_step=round(t_hbm_ms / ms_per_step, 4),
                     step_tensor_fraction=round((ALG_FLOP_PER_IMG_STEP * B / (tf32_peak * 1e12) * 1e3) / ms_per_step, 4) if tf32_peak else None,
                     forward_ms_by_kind=by_kind)
+    # ---- the other tensor-core operand format, same model / batch / steps, device-resident timing only ----
+    variants = None
+    if world == 1 and not args.no_variants and args.precision in ('f16', 'tf32'):
+      other = 'tf32' if args.precision == 'f16' else 'f16'
+      torch.manual_seed(0)
+      model2 = NCSNpp(cfg, precision=other).to(dev)
+      plan2 = native.match_pc_plan(sde=sde, model=model2, predictor=sampling.ReverseDiffusionPredictor,
+                                   corrector=sampling.LangevinCorrector, shape=shape, snr=cfg.sampling.snr, n_steps=1,
+                                   probability_flow=False, continuous=True, eps=1e-5, device=dev)
+      x2 = x_host.to(dev)
+      plan2.run(x2, first_step=0, num_steps=args.warmup, clone=False)
+      torch.cuda.synchronize()
+      g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      g0.record()
+      plan2.run(x2, first_step=args.warmup, num_steps=args.steps, clone=False)
+      g1.record()
+      torch.cuda.synchronize()
+      ms2 = g0.elapsed_time(g1) / args.steps
+      variants = {other: dict(value=round(B / (N_SAMPLER_STEPS * ms2 * 1e-3), 4), unit='images/s', ms_per_step=round(ms2, 4))}
+      del plan2, model2
     cpu = cpu_pc_steps(args.cpu_batch, 2, 1) if world == 1 and not args.no_cpu else None
     line = dict(metric='PC-sampler images/sec, NCSN++ CIFAR-10 1000-step VE', value=round(value, 4), unit='images/s',
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_per_step, 4),
@@ -293,6 +313,8 @@ def run_gpu_arm(args):
                          d2h_bytes_per_step=int(np.prod(shape)) * 4, ms_per_step=round(ms_e2e / e2e_steps, 4)),
                 gpu_launches=int(plan.launches_per_step()) * args.steps,
                 roofline=roofline, finite=finite)
+    if variants is not None:
+      line['variants'] = variants
     if cpu is not None:
       line['cpu_baseline'] = dict(value=cpu['value'], unit='images/s', cores=cpu['cores'], kind='port', sample=cpu['sample'])
     print(json.dumps(line), flush=True)
@@ -308,7 +330,10 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--batch', type=int, default=1024, help='images per GPU (BASELINE.json configs[1]: 1024)')
   ap.add_argument('--cpu-batch', type=int, default=8, help='batch of the bounded CPU sample')
-  ap.add_argument('--precision', default='tf32', choices=['tf32', 'f16', 'fp32'])
+  ap.add_argument('--precision', default='f16', choices=['tf32', 'f16', 'fp32'],
+                  help="tensor-core operand format: 'f16' (default) and 'tf32' both carry 11-bit significands with fp32 "
+                       "accumulation and meet the same 1e-3 parity bound (tests/test_gpu_tc.py); 'fp32' = CUDA cores")
+  ap.add_argument('--no-variants', action='store_true', help='skip timing the other operand format')
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'ours':

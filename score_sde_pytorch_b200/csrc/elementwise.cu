@@ -123,29 +123,33 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
   const long long ib = (long long)b * HW;
   if (blockDim.x % Q == 0) {
     const int L = blockDim.x / Q, c0 = (threadIdx.x % Q) << 2, lane = threadIdx.x / Q;
-    const float2 mr = group_mean_rstd(q1, C1, q2, C2, b, c0, cpg, n, eps);
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
     const bool first = c0 < C1;
     const float* src = first ? x1 + ib * C1 + c0 : x2 + ib * C2 + (c0 - C1);
     const int Cs = first ? C1 : C2;
+    // The first batch of loads is issued BEFORE the (fp64 divide / sqrt) statistics so that their latency hides
+    // it; eight 128-bit loads per thread in flight keep a short-lived CTA close to the HBM rate.
+    constexpr int U = 8;
+    float4 v[U];
     int pix = p0 + lane;
-    for (; pix + 3 * L < p1; pix += 4 * L) {
-      float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(pix + u * L) * Cs));
+    for (int u = 0; u < U; ++u)
+      if (pix + u * L < p1) v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(pix + u * L) * Cs));
+    const float2 mr = group_mean_rstd(q1, C1, q2, C2, b, c0, cpg, n, eps);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    while (pix < p1) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long o = (ib + pix + u * L) * C + c0;
-        store_operand4(y, o, gn_norm4(v[u], mr, ga, be, act, round_out), round_out);
-        if (raw) store_operand4(raw, o, v[u], round_out);
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * L < p1) {
+          const long long o = (ib + pix + u * L) * C + c0;
+          store_operand4(y, o, gn_norm4(v[u], mr, ga, be, act, round_out), round_out);
+          if (raw) store_operand4(raw, o, v[u], round_out);
+        }
       }
-    }
-    for (; pix < p1; pix += L) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)pix * Cs));
-      const long long o = (ib + pix) * C + c0;
-      store_operand4(y, o, gn_norm4(v, mr, ga, be, act, round_out), round_out);
-      if (raw) store_operand4(raw, o, v, round_out);
+      pix += U * L;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pix + u * L < p1) v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(pix + u * L) * Cs));
     }
   } else {
     for (long long u = (long long)p0 * Q + threadIdx.x; u < (long long)p1 * Q; u += blockDim.x) {
@@ -169,9 +173,9 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0,
                "gn_apply: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
   const int Q = C / 4;
-  // aim for ~16 float4 per thread, at least one block per image
+  // aim for ~32 float4 per thread (four 8-deep batches), at least one block per image
   const long long per_img_units = (long long)HW * Q;
-  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (GN_THREADS * 16LL), 64));
+  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (GN_THREADS * 32LL), 64));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
   gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);

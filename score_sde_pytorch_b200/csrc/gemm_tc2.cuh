@@ -208,6 +208,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
           float* dst = e.out + gm * e.ld_out + n0;
           const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
           const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
+          uint2 pend = make_uint2(0u, 0u);
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
@@ -218,8 +219,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
             if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
             if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            if (e.round_tf32 == 2) store_operand4(e.out, gm * e.ld_out + n0 + c, o, 2);   // fp16 operand for the next contraction
-            else *reinterpret_cast<float4*>(dst + c) = o;
+            if (e.round_tf32 == 2) {   // fp16 operand for the next contraction: two quads -> one 16-byte store
+              const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+              if ((c & 4) == 0) pend = hq;
+              else *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + gm * e.ld_out + n0 + c - 4) = make_uint4(pend.x, pend.y, hq.x, hq.y);
+            } else *reinterpret_cast<float4*>(dst + c) = o;
             st[c >> 2] = (o.x + o.y) + (o.z + o.w);
             st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
           }
