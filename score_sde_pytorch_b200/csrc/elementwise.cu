@@ -7,6 +7,7 @@
 // channels here) never straddles a float4.
 #include "common.cuh"
 #include "kernels.h"
+#include <cuda_fp16.h>
 
 namespace b200 {
 
@@ -98,6 +99,17 @@ __device__ __forceinline__ float2 group_mean_rstd(const double* __restrict__ q1,
   return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
+// SiLU for outputs that are rounded to an 11-bit significand right after (operand modes 1, 2): ex2.approx +
+// rcp.approx (relative error ~1e-6, two orders below the rounding) instead of the IEEE exp/divide sequences,
+// which made this HBM-streaming kernel instruction-bound (~25 -> ~8 instructions per element).
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// y = v * sc + sh with sc = rstd * gamma, sh = beta - mean * sc folded per channel by the caller
+__device__ __forceinline__ float4 gn_affine4(float4 v, float4 sc, float4 sh, int act) {
+  float4 o;
+  o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+  if (act) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
+  return o;
+}
 __device__ __forceinline__ float4 gn_norm4(float4 v, float2 mr, float4 ga, float4 be, int act, int round_out) {
   float4 o;
   o.x = (v.x - mr.x) * mr.y * ga.x + be.x;
@@ -126,9 +138,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const bool first = c0 < C1;
     const float* src = first ? x1 + ib * C1 + c0 : x2 + ib * C2 + (c0 - C1);
     const int Cs = first ? C1 : C2;
-    // The first batch of loads is issued BEFORE the (fp64 divide / sqrt) statistics so that their latency hides
-    // it; eight 128-bit loads per thread in flight keep a short-lived CTA close to the HBM rate.
-    constexpr int U = 8;
+    // The first batch of loads is issued BEFORE the (fp64 divide / sqrt) statistics so that their latency hides it.
+    constexpr int U = 4;
     float4 v[U];
     int pix = p0 + lane;
 #pragma unroll
@@ -137,12 +148,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const float2 mr = group_mean_rstd(q1, C1, q2, C2, b, c0, cpg, n, eps);
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const bool fast = round_out != 0;       // the stored value keeps 11 significand bits: approximate SiLU is exact enough
+    const float4 sc = make_float4(mr.y * ga.x, mr.y * ga.y, mr.y * ga.z, mr.y * ga.w);
+    const float4 sh = make_float4(fmaf(-mr.x, sc.x, be.x), fmaf(-mr.x, sc.y, be.y), fmaf(-mr.x, sc.z, be.z), fmaf(-mr.x, sc.w, be.w));
     while (pix < p1) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (pix + u * L < p1) {
           const long long o = (ib + pix + u * L) * C + c0;
-          store_operand4(y, o, gn_norm4(v[u], mr, ga, be, act, round_out), round_out);
+          store_operand4(y, o, fast ? gn_affine4(v[u], sc, sh, act) : gn_norm4(v[u], mr, ga, be, act, round_out), round_out);
           if (raw) store_operand4(raw, o, v[u], round_out);
         }
       }
@@ -173,12 +187,17 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0,
                "gn_apply: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
   const int Q = C / 4;
-  // aim for ~32 float4 per thread (four 8-deep batches), at least one block per image
+  // Small CTAs (the smallest multiple of the quad count >= 128 threads: 128 or 192 here) so that several fit in the
+  // registers a persistent tcgen05 CTA leaves free (112 regs x 384 threads = 43 K of 64 K): this pass then streams
+  // under the OTHER half-batch lane's contraction instead of waiting for its SMs.
+  int threads = GN_THREADS;
+  for (int t = 128; t <= GN_THREADS; t += 32) if (t % Q == 0) { threads = t; break; }
+  // aim for ~16 float4 per thread (four 4-deep batches), at least one block per image
   const long long per_img_units = (long long)HW * Q;
-  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (GN_THREADS * 32LL), 64));
+  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (threads * 16LL), 64));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
-  gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
+  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -662,7 +681,7 @@ template <int N>
 __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w /* [9][N][C] */,
                                                              const float* __restrict__ bias, const float* __restrict__ div,
                                                              long long div_stride, float* __restrict__ out_nchw,
-                                                             int B, int H, int W, int C) {
+                                                             int B, int H, int W, int C, int x_f16) {
   // Eight lanes share one output pixel: lane `part` takes the float4s part, part+8, ... of the pixel's channel
   // vector, so a warp-wide 128-bit load covers 4 pixels x 128 contiguous bytes (4 cache lines per instruction
   // instead of 32 with one pixel per lane, which was L1-wavefront bound); the partial dot products are folded with
@@ -681,6 +700,38 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
   for (int n = 0; n < N; ++n) acc[n] = 0.f;
   const float* xb = x + (long long)b * H * W * C;
   const int nq = C >> 2;                                  // float4s per pixel
+  if (x_f16) {
+    // fp16 activations (operand mode 2): a lane's 128-bit load carries 8 channels, half the L1/L2 bytes of the
+    // nine-fold tap re-reads that bound this kernel
+    const uint16_t* xh = reinterpret_cast<const uint16_t*>(x) + (long long)b * H * W * C;
+    const int n8 = C >> 3;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      if (!live || iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(xh + ((long long)iy * W + ix) * C);
+      const float4* wt = reinterpret_cast<const float4*>(sw + tap * N * C);
+      for (int c8 = part; c8 < n8; c8 += 16) {
+        uint4 a[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) a[u] = (c8 + 8 * u < n8) ? __ldg(src + c8 + 8 * u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (c8 + 8 * u >= n8) break;
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].y));
+          const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].z));
+          const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].w));
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            const float4 w0 = wt[n * nq + 2 * (c8 + 8 * u)], w1 = wt[n * nq + 2 * (c8 + 8 * u) + 1];
+            acc[n] = fmaf(f0.x, w0.x, fmaf(f0.y, w0.y, fmaf(f1.x, w0.z, fmaf(f1.y, w0.w, acc[n]))));
+            acc[n] = fmaf(f2.x, w1.x, fmaf(f2.y, w1.y, fmaf(f3.x, w1.z, fmaf(f3.y, w1.w, acc[n]))));
+          }
+        }
+      }
+    }
+  } else
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
@@ -720,8 +771,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
 }
 
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
-                           float* out_nchw, int B, int H, int W, int C, int N, cudaStream_t st) {
-  B200_REQUIRE(N >= 1 && N <= 4 && C % 4 == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
+                           float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st) {
+  B200_REQUIRE(N >= 1 && N <= 4 && C % (x_f16 ? 8 : 4) == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
   const size_t smem = (size_t)9 * N * C * sizeof(float);
   B200_REQUIRE(smem <= 96 * 1024, "conv3x3_small_n: weights (%zu B) exceed shared memory", smem);
   const long long total = (long long)B * H * W * 8;      // eight lanes per output pixel
@@ -730,7 +781,7 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
       B200_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_n_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3x3_small_n_kernel<NN><<<blocks, 256, smem, st>>>(x, w, bias, div, div_stride, out_nchw, B, H, W, C);       \
+    conv3x3_small_n_kernel<NN><<<blocks, 256, smem, st>>>(x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16); \
   } while (0)
   switch (N) {
     case 1: B200_LAUNCH_SMALLN(1); break;

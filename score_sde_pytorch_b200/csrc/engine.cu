@@ -768,7 +768,10 @@ struct Builder {
     {
       const Mod& mg = e->mods[mi++];
       Tensor a = talloc(h.C, h.H, h.W);
-      Tensor none; gn(h, none, mg.w, mg.b, 1, 0, a, nullptr);
+      // fp16 operand mode: the head's input is stored as fp16 too (the CUDA-core head is bound by its nine-fold
+      // tap re-reads through L1/L2, so half the bytes is half the time); same 11-bit rounding as every other conv input
+      const int head_f16 = (om == 2 && ch <= 4 && h.C % 8 == 0) ? 1 : 0;
+      Tensor none; gn(h, none, mg.w, mg.b, 1, head_f16 ? 2 : 0, a, nullptr);
       tfree(h);
       const Mod& mo = e->mods[mi++];
       const int sbs = c.scale_by_sigma;
@@ -778,7 +781,7 @@ struct Builder {
         name("conv3x3 %d->%d @%d nchw-out [small-n]", a.C, ch, R);
         op(1, [=](cudaStream_t st) {
           return launch_conv3x3_small_n(ain.p, wo, bo, sbs ? eng->in_labels_l[ln] : nullptr, eng->uniform ? 0 : 1, eng->out_l[ln],
-                                        Bc, R, R, ain.C, ch, st);
+                                        Bc, R, R, ain.C, ch, head_f16, st);
         }, 1, 2.0 * B * R * R * (double)ch * a.C * 9);
       } else {
         SimtConv s; memset(&s, 0, sizeof(s));

@@ -274,7 +274,7 @@ __device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilo
 // Kernel
 // ---------------------------------------------------------------------------
 template <int BN, int STAGES, bool STAGED>
-__global__ void __launch_bounds__(STAGED ? 256 : 384, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using L = SmemLayout<BN, STAGES, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -786,6 +786,10 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     pl->two_cta = two_cta_env && !d.no_pair && req != 1 && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) &&
                   (d.conv || d.nbatch == 1 || tmb % 2 == 0) && (m_tiles / 2) * n_tiles >= num_sms() / 2;
     if (pl->two_cta) p.epi_mode = 0;
+    // Launches too small to give every SM a 256-column tile (the 4x4-resolution convolutions of a half-batch
+    // lane: 64 tiles on 148 SMs) are cut into 128-column tiles instead: twice the CTAs at work.
+    static const bool split_small = [] { const char* v = getenv("B200_TC_SPLIT_SMALL"); return !(v && v[0] == '0'); }();
+    if (split_small && !pl->two_cta && !p.swap && pl->bn == 256 && p.epi_mode == 0 && m_tiles * n_tiles <= num_sms() / 2) pl->bn = 128;
   }
   p.kchunks1 = d.C1 / bke; p.kchunks2 = d.a2 ? d.C2 / bke : 0; p.C1 = d.C1;
   p.N_total = d.N_total; p.tiles_n = p.swap ? d.N_total / 128 : d.N_total / pl->bn;
