@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tpar ^= 1) {
       const int b = (int)(tile >> 1), qh = (int)(tile & 1);
       const long long gm = (long long)b * AT_T + qh * BM + r;
+#pragma unroll
+      for (int i = 0; i < 128; i += 32) prefetch_l2(p.x + gm * AT_C + half * 128 + i);   // residual row -> L2 for `final`
       // ---- softmax over this row's 256 logits (this thread: columns half*128 .. +128) ----
       mbar_wait(s_full, tpar);
       tc_fence_after();

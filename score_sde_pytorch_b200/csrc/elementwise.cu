@@ -687,7 +687,17 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
   // instead of 32 with one pixel per lane, which was L1-wavefront bound); the partial dot products are folded with
   // three shuffles per output channel.
   extern __shared__ float sw[];   // [9][N][C]
-  for (int i = threadIdx.x; i < 9 * N * C; i += blockDim.x) sw[i] = w[i];
+  if (x_f16) {
+    // fp16 input: lane `part` owns 8 consecutive channels per 64-channel block.  Its two weight float4s are stored
+    // so that the eight lanes of a pixel read 128 contiguous bytes per LDS.128 (conflict-free), i.e. within a block
+    // channel c = 8*part + 4*k + e sits at float ((2*blk + k)*8 + part)*4 + e.
+    for (int i = threadIdx.x; i < 9 * N * C; i += blockDim.x) {
+      const int c = i % C, row = i / C, blk = c >> 6, prt = (c >> 3) & 7, k = (c >> 2) & 1, e = c & 3;
+      sw[row * C + (((2 * blk + k) * 8 + prt) << 2) + e] = w[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < 9 * N * C; i += blockDim.x) sw[i] = w[i];
+  }
   __syncthreads();
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long pg = gt >> 3;
@@ -724,7 +734,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
           const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].w));
 #pragma unroll
           for (int n = 0; n < N; ++n) {
-            const float4 w0 = wt[n * nq + 2 * (c8 + 8 * u)], w1 = wt[n * nq + 2 * (c8 + 8 * u) + 1];
+            const int blk = (c8 + 8 * u) >> 3;       // c8 + 8u = 8*blk + part
+            const float4 w0 = wt[n * nq + (2 * blk) * 8 + part], w1 = wt[n * nq + (2 * blk + 1) * 8 + part];
             acc[n] = fmaf(f0.x, w0.x, fmaf(f0.y, w0.y, fmaf(f1.x, w0.z, fmaf(f1.y, w0.w, acc[n]))));
             acc[n] = fmaf(f2.x, w1.x, fmaf(f2.y, w1.y, fmaf(f3.x, w1.z, fmaf(f3.y, w1.w, acc[n]))));
           }
@@ -772,7 +783,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
 
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
                            float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st) {
-  B200_REQUIRE(N >= 1 && N <= 4 && C % (x_f16 ? 8 : 4) == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
+  B200_REQUIRE(N >= 1 && N <= 4 && C % (x_f16 ? 64 : 4) == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
   const size_t smem = (size_t)9 * N * C * sizeof(float);
   B200_REQUIRE(smem <= 96 * 1024, "conv3x3_small_n: weights (%zu B) exceed shared memory", smem);
   const long long total = (long long)B * H * W * 8;      // eight lanes per output pixel

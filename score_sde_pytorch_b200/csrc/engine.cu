@@ -770,7 +770,7 @@ struct Builder {
       Tensor a = talloc(h.C, h.H, h.W);
       // fp16 operand mode: the head's input is stored as fp16 too (the CUDA-core head is bound by its nine-fold
       // tap re-reads through L1/L2, so half the bytes is half the time); same 11-bit rounding as every other conv input
-      const int head_f16 = (om == 2 && ch <= 4 && h.C % 8 == 0) ? 1 : 0;
+      const int head_f16 = (om == 2 && ch <= 4 && h.C % 64 == 0) ? 1 : 0;
       Tensor none; gn(h, none, mg.w, mg.b, 1, head_f16 ? 2 : 0, a, nullptr);
       tfree(h);
       const Mod& mo = e->mods[mi++];

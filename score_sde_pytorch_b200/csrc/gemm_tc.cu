@@ -114,6 +114,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Pull one 128-byte line towards L2 without occupying a register: the epilogues use it for their residual rows
+// while they still wait for the accumulator, so the later loads hit L2 instead of paying an HBM round trip
+// inside the per-chunk critical path (the 112-register cap that lets GroupNorm CTAs co-reside leaves no room
+// for a register-held prefetch).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -408,6 +414,11 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
           const float add = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
           const float dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
           float ssum = 0.f, ssq = 0.f;
+          if (e.residual) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)   // this lane's share of the warp's 128 residual lines (one per pixel)
+              prefetch_l2(e.residual + (row_base + half * 128 + j * 32 + lane) * e.ld_res + (int)(tile % p.tiles_n) * 128 + q * 32);
+          }
           mbar_wait(&tmem_full[acc], acc_phase);
           tc_fence_after();
 #pragma unroll 1
@@ -458,6 +469,10 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
       const long long gm = (long long)b * p.M_per_batch + m;
       const int img = valid ? (int)(gm / e.rows_per_img) : 0;
       const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+      if (e.residual && valid) {
+#pragma unroll
+        for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + gm * e.ld_res + nt * BN + half * (BN / 2) + i);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1

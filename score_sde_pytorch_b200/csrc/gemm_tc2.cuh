@@ -194,6 +194,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
       const long long gm = (long long)b * p.M_per_batch + m;
       const int img = valid ? (int)(gm / e.rows_per_img) : 0;
       const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+      if (e.residual && valid) {   // residual rows -> L2 while the accumulator is still being produced
+#pragma unroll
+        for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + gm * e.ld_res + nt * BN + half * (BN / 2) + i);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1

@@ -94,11 +94,20 @@ def test_groupnorm_silu_nhwc(dev, cfg):
             _lib.stream_ptr(dev))
   assert torch.allclose(gpu_util.to_nchw(y), ref, rtol=2e-5, atol=2e-5)
   assert torch.equal(gpu_util.to_nchw(raw), xc)
-  # TF32-rounded variant is the RN rounding of the fp32 result
+  # Operand modes: values on the TF32 grid (mode 1) / IEEE fp16 (mode 2), each within one rounding of the fp32
+  # result (these modes use the approximate-SiLU path, ~1e-6 relative, two orders below the 2^-11 rounding)
   _lib.call('b200_groupnorm_nhwc_f32', _lib.ptr(n1), C1, _lib.ptr(n2), C2,
             _lib.ptr(gamma), _lib.ptr(beta), B, H * W, G, 1e-6, int(silu), 1, _lib.ptr(stats), _lib.ptr(raw), None,
             _lib.stream_ptr(dev))
-  assert torch.equal(raw, gpu_util.round_tf32(y))
+  assert torch.equal(raw, gpu_util.round_tf32(raw))                       # on the grid
+  assert ((raw - y).abs() <= y.abs() * 2.0 ** -11 + 2e-6).all()           # one rounding away
+  yh = torch.empty(B, H, W, C, device=dev, dtype=torch.float16)
+  rawh = torch.empty(B, H, W, C, device=dev, dtype=torch.float16)
+  _lib.call('b200_groupnorm_nhwc_f32', _lib.ptr(n1), C1, _lib.ptr(n2), C2,
+            _lib.ptr(gamma), _lib.ptr(beta), B, H * W, G, 1e-6, int(silu), 2, _lib.ptr(stats), _lib.ptr(yh), _lib.ptr(rawh),
+            _lib.stream_ptr(dev))
+  assert ((yh.float() - y).abs() <= y.abs() * 2.0 ** -11 + 2e-6).all()
+  assert torch.equal(rawh, gpu_util.to_nhwc(xc).half())                   # the raw copy is exactly the RN fp16 of the input
 
 
 @pytest.mark.parametrize('T', [16, 256, 100, 1024])
