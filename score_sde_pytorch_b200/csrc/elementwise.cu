@@ -869,4 +869,33 @@ int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float s
   return 0;
 }
 
+// The streaming kernels that run between contractions ask for the SAME shared-memory / L1 split as the tcgen05
+// kernels (maximum shared memory).  An SM keeps one split at a time and only re-partitions when it is idle, so a
+// kernel preferring the default split (maximum L1) cannot place CTAs next to a resident contraction CTA - which
+// is exactly what the two half-batch lanes need (GroupNorm / FIR of one lane under the other lane's contraction).
+// Called once at plan time, outside any stream capture.
+int elementwise_configure() {
+  static bool done = false;
+  if (done) return 0;
+  if (const char* v = getenv("B200_CARVEOUT")) if (v[0] == '0') { done = true; return 0; }   // A/B switch
+  const int carve = cudaSharedmemCarveoutMaxShared;
+#define B200_CARVE(k) B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve))
+  B200_CARVE(gn_quad_stats_kernel);
+  B200_CARVE(gn_apply_kernel);
+  B200_CARVE(fir4_up2_nhwc_kernel);
+  B200_CARVE((fir4_nhwc_kernel<2, 1>));
+  B200_CARVE((fir4_nhwc_kernel<1, 2>));
+  B200_CARVE((fir4_nhwc_kernel<1, 1>));
+  B200_CARVE(upfirdn2d_kernel<4>);
+  B200_CARVE(upfirdn2d_kernel<1>);
+  B200_CARVE(im2col3x3_nchw_kernel);
+  B200_CARVE(conv3x3_small_n_kernel<3>);
+  B200_CARVE(attn_small_kernel);
+  B200_CARVE(linear_rows_kernel);
+  B200_CARVE(fourier_embed_kernel);
+#undef B200_CARVE
+  done = true;
+  return 0;
+}
+
 }  // namespace b200
