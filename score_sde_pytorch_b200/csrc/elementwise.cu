@@ -187,9 +187,8 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0,
                "gn_apply: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
   const int Q = C / 4;
-  // Small CTAs (the smallest multiple of the quad count >= 128 threads: 128 or 192 here) so that several fit in the
-  // registers a persistent tcgen05 CTA leaves free (112 regs x 384 threads = 43 K of 64 K): this pass then streams
-  // under the OTHER half-batch lane's contraction instead of waiting for its SMs.
+  // Small CTAs (the smallest multiple of the quad count >= 128 threads: 128 or 192 here): finer-grained tail, and
+  // several fit in the registers a persistent tcgen05 CTA leaves free (112 regs x 384 threads = 43 K of 64 K).
   int threads = GN_THREADS;
   for (int t = 128; t <= GN_THREADS; t += 32) if (t % Q == 0) { threads = t; break; }
   // aim for ~16 float4 per thread (four 4-deep batches), at least one block per image
@@ -866,35 +865,6 @@ int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float s
   const size_t smem = ((size_t)3 * T * C + (size_t)T * T) * sizeof(float);
   attn_small_kernel<<<B, 256, smem, st>>>(qkv, out, T, C, scale, round_out);
   B200_CHECK_LAUNCH();
-  return 0;
-}
-
-// The streaming kernels that run between contractions ask for the SAME shared-memory / L1 split as the tcgen05
-// kernels (maximum shared memory).  An SM keeps one split at a time and only re-partitions when it is idle, so a
-// kernel preferring the default split (maximum L1) cannot place CTAs next to a resident contraction CTA - which
-// is exactly what the two half-batch lanes need (GroupNorm / FIR of one lane under the other lane's contraction).
-// Called once at plan time, outside any stream capture.
-int elementwise_configure() {
-  static bool done = false;
-  if (done) return 0;
-  if (const char* v = getenv("B200_CARVEOUT")) if (v[0] == '0') { done = true; return 0; }   // A/B switch
-  const int carve = cudaSharedmemCarveoutMaxShared;
-#define B200_CARVE(k) B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve))
-  B200_CARVE(gn_quad_stats_kernel);
-  B200_CARVE(gn_apply_kernel);
-  B200_CARVE(fir4_up2_nhwc_kernel);
-  B200_CARVE((fir4_nhwc_kernel<2, 1>));
-  B200_CARVE((fir4_nhwc_kernel<1, 2>));
-  B200_CARVE((fir4_nhwc_kernel<1, 1>));
-  B200_CARVE(upfirdn2d_kernel<4>);
-  B200_CARVE(upfirdn2d_kernel<1>);
-  B200_CARVE(im2col3x3_nchw_kernel);
-  B200_CARVE(conv3x3_small_n_kernel<3>);
-  B200_CARVE(attn_small_kernel);
-  B200_CARVE(linear_rows_kernel);
-  B200_CARVE(fourier_embed_kernel);
-#undef B200_CARVE
-  done = true;
   return 0;
 }
 

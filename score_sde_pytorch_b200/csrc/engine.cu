@@ -914,7 +914,6 @@ int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long 
   h->B = batch; h->ws_bytes = ws_bytes;
   h->ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
   h->B0 = lane0_images(h, batch);
-  if (int r = elementwise_configure()) return r;
   char* base = h->ws;
   for (int lane = 0; lane < (h->B0 < batch ? 2 : 1); ++lane) {
     const int images = lane ? batch - h->B0 : h->B0;

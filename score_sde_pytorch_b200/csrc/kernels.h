@@ -33,7 +33,6 @@ int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, lon
 int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
                           int pad, int mode, cudaStream_t st);
 int launch_attn_small_configure(int T, int C);
-int elementwise_configure();   // shared-memory carve-out of the streaming kernels (co-residency with tcgen05 CTAs)
 int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st);
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
                            float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st);
