@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
     const double* __restrict__ q1, const double* __restrict__ q2,
     const float* __restrict__ gamma, const float* __restrict__ beta,
-    int HW, int G, float eps, int act, int round_out, float* __restrict__ y, float* __restrict__ raw) {
+    int HW, int G, float eps, int act, int round_out, float* __restrict__ y, float* __restrict__ raw, int x1_f16) {
   const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
@@ -138,13 +138,25 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const bool first = c0 < C1;
     const float* src = first ? x1 + ib * C1 + c0 : x2 + ib * C2 + (c0 - C1);
     const int Cs = first ? C1 : C2;
+    // x1 may be an fp16 tensor (the mid-block conv output in fp16 operand mode): 8-byte loads, widened here
+    const bool xh = x1_f16 && first;
+    const uint16_t* srch = reinterpret_cast<const uint16_t*>(x1) + ib * C1 + c0;
+    auto load4 = [&](int px) -> float4 {
+      if (xh) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(srch + (long long)px * Cs));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b2.x, b2.y);
+      }
+      return __ldg(reinterpret_cast<const float4*>(src + (long long)px * Cs));
+    };
     // The first batch of loads is issued BEFORE the (fp64 divide / sqrt) statistics so that their latency hides it.
     constexpr int U = 4;
     float4 v[U];
     int pix = p0 + lane;
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (pix + u * L < p1) v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(pix + u * L) * Cs));
+      if (pix + u * L < p1) v[u] = load4(pix + u * L);
     const float2 mr = group_mean_rstd(q1, C1, q2, C2, b, c0, cpg, n, eps);
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
       pix += U * L;
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (pix + u * L < p1) v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(pix + u * L) * Cs));
+        if (pix + u * L < p1) v[u] = load4(pix + u * L);
     }
   } else {
     for (long long u = (long long)p0 * Q + threadIdx.x; u < (long long)p1 * Q; u += blockDim.x) {
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
 
 int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
                     const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
-                    int round_out, float* y, float* raw, cudaStream_t st) {
+                    int round_out, float* y, float* raw, cudaStream_t st, int x1_f16) {
   const int C = C1 + C2;
   B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0,
                "gn_apply: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
@@ -191,12 +203,13 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   // several fit in the registers a persistent tcgen05 CTA leaves free (112 regs x 384 threads = 43 K of 64 K).
   int threads = GN_THREADS;
   for (int t = 128; t <= GN_THREADS; t += 32) if (t % Q == 0) { threads = t; break; }
+  B200_REQUIRE(!x1_f16 || (threads % Q == 0 && !raw), "gn_apply: fp16 input needs the quad-per-thread path (C=%d) and no raw copy", C);
   // aim for ~16 float4 per thread (four 4-deep batches), at least one block per image
   const long long per_img_units = (long long)HW * Q;
   int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (threads * 16LL), 64));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
-  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
+  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw, x1_f16);
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -41,7 +41,11 @@ struct Mod {
   int w = -1, b = -1;
 };
 
-struct Tensor { float* p = nullptr; int C = 0, H = 0, W = 0; long long bytes = 0; double* qs = nullptr; /* GroupNorm quad sums [B][C/4][2] */ };
+struct Tensor {
+  float* p = nullptr; int C = 0, H = 0, W = 0; long long bytes = 0;
+  double* qs = nullptr;   // GroupNorm quad sums [B][C/4][2]
+  bool f16 = false;       // elements are IEEE fp16 (mid-block conv output in fp16 operand mode)
+};
 
 class Arena {
  public:
@@ -376,9 +380,9 @@ struct Builder {
     ensure_qs(x1); ensure_qs(x2);
     const float *g = e->W(pgw), *bt = e->W(pgb);
     const Tensor a = x1, b = x2; const int Bc = B;
-    name("gn_apply %d+%d @%d%s%s", x1.C, x2.C, x1.H, act ? " silu" : "", raw ? " +raw" : "");
+    name("gn_apply %d+%d @%d%s%s%s", x1.C, x2.C, x1.H, act ? " silu" : "", raw ? " +raw" : "", x1.f16 ? " f16-in" : "");
     op(1, [=](cudaStream_t st) {
-      return launch_gn_apply(a.p, a.C, b.p, b.C, a.qs, b.qs, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, st);
+      return launch_gn_apply(a.p, a.C, b.p, b.C, a.qs, b.qs, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, st, a.f16 ? 1 : 0);
     }, 2);
   }
 
@@ -511,7 +515,13 @@ struct Builder {
       tfree(a0); a0 = a0r;
     }
     Tensor h1 = talloc(m.cout, Ho, Ho);
-    conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 0, h1, /*want_stats=*/true);
+    // fp16 operand mode: the mid-block tensor (Conv_0 output, only ever read by GroupNorm_1) is stored as fp16;
+    // its GroupNorm sums are accumulated from the fp32 accumulators in the epilogue.  B200_H1_F16=0 keeps it fp32.
+    static const bool h1_f16_env = [] { const char* v = getenv("B200_H1_F16"); return !(v && v[0] == '0'); }();
+    const bool h1_f16 = h1_f16_env && om == 2 && m.tc0 && m.tc1 && fused_stats && (Ho * Ho) % 32 == 0 && (m.cout % 128 == 0);
+    h1.f16 = h1_f16;
+    conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, h1_f16 ? 2 : 0, h1, /*want_stats=*/true);
+    if (h1_f16 && !h1.qs) { set_error("ncsnpp: fp16 mid-block tensor without fused GroupNorm sums"); rc = 2; return Tensor(); }
     tfree(a0);
     Tensor a1 = talloc(m.cout, Ho, Ho);
     gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? om : 0, a1, nullptr);

@@ -276,11 +276,42 @@ __device__ __forceinline__ void quad_stats_commit(const TcParams& p, const Epilo
   quad_stats_commit_raw(p.qstats, p.N_total, e.rows_per_img, st, img, valid, col0, lane);
 }
 
+// One 32-pixel chunk of the swapped-operand epilogue (lane = output channel, v[i] = pixel i of the chunk), specialised
+// on what the launch needs so the per-element instruction stream is minimal: the profile of the first version
+// (profiles/r01_c19_ncu_swap_f16.md) showed the eight epilogue warps ISSUE-bound at ~40 instructions per element
+// (runtime-uniform branches, an IEEE divide path for an unused divisor, 64-bit index multiplies) - longer than the
+// fp16 main loop of a 128-channel convolution.  RES: add the residual; MODE 0 fp32 store, 1 TF32-rounded, 2 fp16.
+template <bool RES, int MODE>
+__device__ __forceinline__ void swap_chunk(const uint32_t (&v)[32], float add, float scale, float* out, const float* res,
+                                           long long ld_out, long long ld_res, float& ssum, float& ssq) {
+  float rr[32];
+  if (RES) {
+    const float* rp = res;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { rr[i] = __ldg(rp); rp += ld_res; }
+  }
+  float* op = out;                                        // MODE 2: `out` addresses fp16 elements, ld_out counts them
+  uint16_t* oh = reinterpret_cast<uint16_t*>(out);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float o = __uint_as_float(v[i]) + add;
+    if (RES) o += rr[i];
+    o *= scale;
+    if (MODE == 1) o = round_tf32(o);
+    if (MODE == 2) {
+      uint16_t h;
+      asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(o));
+      *oh = h; oh += ld_out;
+    } else { *op = o; op += ld_out; }
+    ssum += o; ssq = fmaf(o, o, ssq);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------
 template <int BN, int STAGES, bool STAGED>
-__global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using L = SmemLayout<BN, STAGES, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -412,7 +443,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
           const long long row_base = (tile / p.tiles_n) * 256;
           const int img = (int)(row_base / e.rows_per_img);          // rows_per_img % 256 == 0: one image per tile
           const float add = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
-          const float dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
           float ssum = 0.f, ssq = 0.f;
           if (e.residual) {
 #pragma unroll
@@ -421,27 +451,25 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
           }
           mbar_wait(&tmem_full[acc], acc_phase);
           tc_fence_after();
+          const int mode = e.round_tf32;
+          const bool has_res = e.residual != nullptr;
 #pragma unroll 1
           for (int j = half * 4; j < half * 4 + 4; ++j) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
             const long long pix0 = row_base + j * 32;
-            float* dst = e.out + pix0 * e.ld_out + co;
-            const float* res = e.residual ? e.residual + pix0 * e.ld_res + co : nullptr;
-            float rr[32];
-            if (res) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) rr[i] = __ldg(res + (long long)i * e.ld_res);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float o = __uint_as_float(v[i]) + add;
-              if (res) o += rr[i];
-              o *= e.scale;
-              if (e.per_img_div) o /= dv;
-              if (e.round_tf32) o = round_tf32(o);
-              dst[(long long)i * e.ld_out] = o;
-              ssum += o; ssq += o * o;
+            const float* res = has_res ? e.residual + pix0 * e.ld_res + co : nullptr;
+            // element offset of (pix0, co); fp16 outputs count halves from the same base pointer
+            float* dst = mode == 2 ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(e.out) + pix0 * e.ld_out + co)
+                                   : e.out + pix0 * e.ld_out + co;
+            if (has_res) {
+              if (mode == 0) swap_chunk<true, 0>(v, add, e.scale, dst, res, e.ld_out, e.ld_res, ssum, ssq);
+              else if (mode == 1) swap_chunk<true, 1>(v, add, e.scale, dst, res, e.ld_out, e.ld_res, ssum, ssq);
+              else swap_chunk<true, 2>(v, add, e.scale, dst, res, e.ld_out, e.ld_res, ssum, ssq);
+            } else {
+              if (mode == 0) swap_chunk<false, 0>(v, add, e.scale, dst, res, e.ld_out, e.ld_res, ssum, ssq);
+              else if (mode == 1) swap_chunk<false, 1>(v, add, e.scale, dst, res, e.ld_out, e.ld_res, ssum, ssq);
+              else swap_chunk<false, 2>(v, add, e.scale, dst, res, e.ld_out, e.ld_res, ssum, ssq);
             }
           }
           if (p.qstats) {
@@ -468,7 +496,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
       const bool valid = m < p.M_per_batch;
       const long long gm = (long long)b * p.M_per_batch + m;
       const int img = valid ? (int)(gm / e.rows_per_img) : 0;
-      const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
       if (e.residual && valid) {
 #pragma unroll
         for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + gm * e.ld_res + nt * BN + half * (BN / 2) + i);
@@ -496,7 +523,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
             if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-            if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
             if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
             if (e.round_tf32 == 2) {   // fp16 operand for the next contraction: two quads -> one 16-byte store
               const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
@@ -587,8 +613,7 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
         const bool valid = m < p.M_per_batch;
         const long long gm = (long long)row0 + r;
         const int img = valid ? (int)(gm / e.rows_per_img) : 0;
-        const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
-        const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + col0 : nullptr;
+          const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + col0 : nullptr;
         float st[16];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -598,7 +623,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
           if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
           if (has_res) { const float4 t = *reinterpret_cast<const float4*>(rs + r * 32 + ((c ^ sw) << 2)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
           o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-          if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
           if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
           *reinterpret_cast<float4*>(os + r * 32 + ((c ^ sw) << 2)) = o;
           st[c] = valid ? (o.x + o.y) + (o.z + o.w) : 0.f;
@@ -610,7 +634,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
         const int co = col0 + lane, ch16 = lane >> 2, w4 = lane & 3;
         const int img = row0 / e.rows_per_img;
         const float bias_v = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
-        const float dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
         if (j == 0) { sw_sum = 0.f; sw_sq = 0.f; }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -618,7 +641,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 112) gemm_tc_kernel(const __grid_cons
           float o = __uint_as_float(v[i]) + bias_v;
           if (has_res) o += rs[off];
           o *= e.scale;
-          if (e.per_img_div) o /= dv;
           if (e.round_tf32) o = round_tf32(o);
           os[off] = o;
           sw_sum += o; sw_sq += o * o;
@@ -748,9 +770,9 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
     if (d.C3 % bke || d.C3 <= 0 || (d.a4 && d.C4 % bke)) return fail("extra-phase channel counts must be multiples of 32 (tf32) / 64 (f16)");
   }
   if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
+  if (d.epi.per_img_div) return fail("per-image divisor is SIMT-only (the sigma-scaled head runs on CUDA cores)");
   if (d.qstats && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("quad stats need rows_per_img % 32 == 0 or == 16");
   if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 elements");
-  if (d.epi.round_tf32 == 2 && d.qstats) return fail("fp16 outputs carry no GroupNorm sums");
   if (d.epi.round_tf32 == 2 && d.epi.ld_out % 8) return fail("fp16 output pitch must be a multiple of 8 elements");
   return true;
 }
@@ -787,7 +809,6 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // B200_TC_EPILOGUE=staged selects the smem-staged TMA-store epilogue for A/B runs.
     p.swap = can_swap ? 1 : 0;
     p.epi_mode = (req == 1 && d.epi.round_tf32 != 2) ? 1 : 0;   // fp16 outputs: direct stores only
-    if (p.swap && d.epi.round_tf32 == 2) p.swap = 0;            // (the swapped epilogue writes fp32)
     if (p.swap) pl->bn = 256;
     p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
     // CTA pairs (cta_group::2) for 256-column tiles: B200_TC_2CTA=1 opts in (0 = off, default until validated per round)

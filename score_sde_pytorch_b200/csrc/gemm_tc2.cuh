@@ -193,7 +193,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
       const bool valid = (mg < tiles_m_total) && (m < p.M_per_batch);
       const long long gm = (long long)b * p.M_per_batch + m;
       const int img = valid ? (int)(gm / e.rows_per_img) : 0;
-      const float dv = (valid && e.per_img_div) ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
       if (e.residual && valid) {   // residual rows -> L2 while the accumulator is still being produced
 #pragma unroll
         for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + gm * e.ld_res + nt * BN + half * (BN / 2) + i);
@@ -221,7 +220,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-            if (e.per_img_div) { o.x /= dv; o.y /= dv; o.z /= dv; o.w /= dv; }
             if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
             if (e.round_tf32 == 2) {   // fp16 operand for the next contraction: two quads -> one 16-byte store
               const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));

@@ -13,7 +13,7 @@ namespace b200 {
 int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st);
 int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
                     const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
-                    int round_out, float* y, float* raw, cudaStream_t st);
+                    int round_out, float* y, float* raw, cudaStream_t st, int x1_f16 = 0);
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
                      int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_out, cudaStream_t st);
