@@ -145,6 +145,20 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def load_traffic(precision):
+  """DRAM bytes per launch of the contraction kernels from the committed ncu metrics pass of one PC step
+  (profiles/traffic_<precision>.json, written by tools/summarize_traffic.py); None when no capture is committed."""
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', f'traffic_{precision}.json')
+  try:
+    k = json.load(open(path))['kernels']
+    for name, d in k.items():
+      if name.startswith('tcgen05'):
+        return round(d['dram_bytes_per_launch'])
+  except (OSError, KeyError, ValueError):
+    pass
+  return None
+
+
 def measure_tf32_peak(dev, f16=False):
   """cuBLAS GEMM throughput on this device in the operand format the engine computes in: TF32 (kind::tf32
   work) or fp16 with fp32 accumulation (kind::f16 work) - the measured denominator of the tensor roofline."""
@@ -255,6 +269,15 @@ def run_gpu_arm(args):
     for _ in range(2):
       _lib.call('b200_ncsnpp_profile_forward', eng['h'], _lib.ptr(xin), _lib.ptr(lab), 1, _lib.ptr(out),
                 _lib.stream_ptr(dev), ms_k, fl_k, n_k)
+    # algorithmic HBM bytes of the contraction launches (operands once + outputs once), from the plan
+    n_ops = int(_lib.load().b200_ncsnpp_num_ops(eng['h']))
+    tc_alg_bytes = 0.0
+    kind_c, bytes_c = ctypes.c_int(), ctypes.c_double()
+    for i in range(n_ops):
+      _lib.call('b200_ncsnpp_op_info', eng['h'], i, None, 0, ctypes.byref(kind_c), None)
+      if kind_c.value == 0:
+        _lib.call('b200_ncsnpp_op_bytes', eng['h'], i, ctypes.byref(bytes_c))
+        tc_alg_bytes += bytes_c.value
     kinds = ['tcgen05_contraction', 'cuda_core_contraction', 'groupnorm', 'fir', 'softmax', 'time_embedding', 'misc']
     by_kind = {k: dict(ms=round(ms_k[i], 4), gflop=round(fl_k[i] / 1e9, 2), launches=int(n_k[i])) for i, k in enumerate(kinds)}
     fwd_ms = sum(ms_k[i] for i in range(7))
@@ -271,7 +294,7 @@ def run_gpu_arm(args):
                     frac_of_measured_bf16_sustained=round(achieved / peaks['bf16_tflops_sustained'], 4),
                     alg_flop_per_launch=tc_flops / tc_n, avg_launch_ms=tc_ms / tc_n, launches_per_forward=tc_n,
                     kernel_share_of_forward=round(tc_ms / fwd_ms, 4) if fwd_ms else None,
-                    traffic=None,
+                    traffic=load_traffic(args.precision), alg_hbm_bytes_per_launch=round(tc_alg_bytes / tc_n),
                     hbm_fraction_of_step=round(t_hbm_ms / ms_per_step, 4),
                     step_tensor_fraction=round((ALG_FLOP_PER_IMG_STEP * B / (tf32_peak * 1e12) * 1e3) / ms_per_step, 4) if tf32_peak else None,
                     forward_ms_by_kind=by_kind)

@@ -144,6 +144,8 @@ B200_API int b200_ncsnpp_profile_forward(b200_ncsnpp_t* h, const float* x_nchw, 
 B200_API long long b200_ncsnpp_num_ops(const b200_ncsnpp_t* h);
 B200_API int b200_ncsnpp_op_info(const b200_ncsnpp_t* h, long long index, char* name, int name_cap, int* kind,
                                  double* flops);
+/* algorithmic HBM bytes of op `index` (operands read once + outputs written once; 0 for ops that do not report it) */
+B200_API int b200_ncsnpp_op_bytes(const b200_ncsnpp_t* h, long long index, double* bytes);
 B200_API int b200_ncsnpp_profile_ops(b200_ncsnpp_t* h, const float* x, const float* labels, int labels_uniform,
                                      float* out, void* stream, float* ms_per_op, long long cap);
 

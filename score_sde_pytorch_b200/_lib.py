@@ -70,6 +70,7 @@ SIGNATURES = {
   'b200_ncsnpp_load_param': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
   'b200_ncsnpp_num_ops': (c_ll, [c_void_p]),
   'b200_ncsnpp_op_info': (c_int, [c_void_p, c_ll, c_char_p, c_int, P(c_int), P(ctypes.c_double)]),
+  'b200_ncsnpp_op_bytes': (c_int, [c_void_p, c_ll, P(ctypes.c_double)]),
   'b200_ncsnpp_profile_ops': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_ll]),
   'b200_ncsnpp_workspace_bytes': (c_ll, [c_void_p, c_int]),
   'b200_ncsnpp_bind_workspace': (c_int, [c_void_p, c_int, c_void_p, c_ll]),

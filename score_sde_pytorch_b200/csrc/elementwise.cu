@@ -123,11 +123,12 @@ __device__ __forceinline__ float4 gn_norm4(float4 v, float2 mr, float4 ga, float
 
 // grid = (pixel splits, images).  blockDim % (C/4) == 0: a thread keeps one channel quad (so its
 // group statistics, gamma and beta are loaded once) and walks pixels with 4 loads in flight.
+template <bool XH>   // XH: x1 holds fp16 elements (the mid-block conv output in fp16 operand mode)
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
     const double* __restrict__ q1, const double* __restrict__ q2,
     const float* __restrict__ gamma, const float* __restrict__ beta,
-    int HW, int G, float eps, int act, int round_out, float* __restrict__ y, float* __restrict__ raw, int x1_f16) {
+    int HW, int G, float eps, int act, int round_out, float* __restrict__ y, float* __restrict__ raw) {
   const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
@@ -138,11 +139,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const bool first = c0 < C1;
     const float* src = first ? x1 + ib * C1 + c0 : x2 + ib * C2 + (c0 - C1);
     const int Cs = first ? C1 : C2;
-    // x1 may be an fp16 tensor (the mid-block conv output in fp16 operand mode): 8-byte loads, widened here
-    const bool xh = x1_f16 && first;
+    // XH: 8-byte fp16 loads, widened here (single-source launches only, checked by the launcher)
     const uint16_t* srch = reinterpret_cast<const uint16_t*>(x1) + ib * C1 + c0;
     auto load4 = [&](int px) -> float4 {
-      if (xh) {
+      if (XH) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(srch + (long long)px * Cs));
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
         const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
@@ -209,7 +209,9 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (threads * 16LL), 64));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
-  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw, x1_f16);
+  B200_REQUIRE(!x1_f16 || C2 == 0, "gn_apply: fp16 input is single-source");
+  if (x1_f16) gn_apply_kernel<true><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
+  else gn_apply_kernel<false><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
   return 0;
 }

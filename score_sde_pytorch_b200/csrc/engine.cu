@@ -106,7 +106,7 @@ struct b200_ncsnpp {
   float fir2d[64]; int firn = 0;
   // plan
   int B = 0; char* ws = nullptr; long long ws_bytes = 0;
-  struct Op { int kind; double flops; std::function<int(cudaStream_t)> fn; std::string name; };
+  struct Op { int kind; double flops; std::function<int(cudaStream_t)> fn; std::string name; double bytes; /* algorithmic HBM bytes: operands read once + outputs written once */ };
   std::vector<Op> ops;
   // Two half-batch "lanes" (ops2 = the second half's plan, empty when the batch is not split).  The lanes are
   // independent within one network evaluation, so forward() issues them on two streams: while one lane's
@@ -328,6 +328,7 @@ struct Builder {
   int lane = 0;                                // which half-batch plan this builder fills (ops or ops2)
   int om = 1;                                  // operand store mode of tensor-core inputs: 1 TF32-grid fp32, 2 fp16
   std::string next_name;                       // label of the next op (shape summary for the per-op profile)
+  double next_bytes = 0.0;                     // algorithmic HBM bytes of the next op
   void name(const char* fmt, ...) {
     char buf[160]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap); next_name = buf;
   }
@@ -363,8 +364,8 @@ struct Builder {
     if (dry) return;
     e->launches += launches;
     static const char* kind_names[] = {"tcgen05", "cuda-core contraction", "groupnorm", "fir", "softmax", "time embedding", "misc", "?"};
-    (lane ? e->ops2 : e->ops).push_back({kind, flops, std::move(f), next_name.empty() ? std::string(kind_names[kind & 7]) : next_name});
-    next_name.clear();
+    (lane ? e->ops2 : e->ops).push_back({kind, flops, std::move(f), next_name.empty() ? std::string(kind_names[kind & 7]) : next_name, next_bytes});
+    next_name.clear(); next_bytes = 0.0;
   }
 
   // make sure tensor t has quad sums: produced by its tcgen05 epilogue, else by one streaming pass
@@ -433,6 +434,12 @@ struct Builder {
       name("conv%s %d+%d->%d @%d%s%s%s [%s]", taps == 9 ? "3x3" : "1x1", a1.C, a2.C, Cout, out.H, stride == 2 ? " s2" : "",
            x3.p ? " +skipproj" : "", residual ? " +res" : "", tc_gemm_form(pl));
       if (x3.p) next_name += " " + std::to_string(x3.C + x4.C);
+      {
+        const double es = om == 2 ? 2.0 : 4.0, px = (double)B * out.H * out.W;
+        const double in_px = (double)B * (Hin ? (double)Hin * Hin : (double)out.H * out.W);
+        next_bytes = in_px * (a1.C + a2.C) * es + px * (x3.C + x4.C) * es + px * Cout * (round == 2 ? 2.0 : 4.0) +
+                     (residual ? px * Cout * 4.0 : 0.0) + ((double)taps * (a1.C + a2.C) + x3.C + x4.C) * Cout * es;
+      }
       op(1, [=](cudaStream_t st) {
         if (dense_row >= 0) tc_gemm_set_rowvec_ld(pl, eng->uniform ? 0 : sumC);
         return tc_gemm_launch(pl, st);
@@ -472,6 +479,11 @@ struct Builder {
       if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return; }
       e->tcplans.push_back(pl);
       name("gemm %dx(%dx%dx%d)%s [%s]", nbatch, M, N, K, residual ? " +res" : "", tc_gemm_form(pl));
+      {
+        const double es = om == 2 ? 2.0 : 4.0;
+        next_bytes = (double)(a_batch_rows ? nbatch : 1) * M * K * es + (double)(w_batch_rows ? nbatch : 1) * N * K * es +
+                     (double)nbatch * M * N * (round == 2 ? 2.0 : 4.0) + (residual ? (double)nbatch * M * N * 4.0 : 0.0);
+      }
       op(1, [=](cudaStream_t st) { return tc_gemm_launch(pl, st); }, 0, 2.0 * nbatch * (double)M * N * K);
     } else {
       SimtConv s; memset(&s, 0, sizeof(s));
@@ -607,6 +619,7 @@ struct Builder {
           if (int r = tc_attn_plan_create(d, &pl)) { rc = r; return Tensor(); }
           e->attnplans.push_back(pl);
           name("attention core T=%d C=%d (QK^T, softmax, PV, NIN_3 +res) [fused]", T, C);
+          next_bytes = (double)B * T * C * ((om == 2 ? 2.0 : 4.0) * 3 + 8.0) + (double)C * C * (om == 2 ? 2.0 : 4.0);
           op(1, [=](cudaStream_t st) { return tc_attn_launch(pl, st); }, 0, 2.0 * B * T * ((double)T * C * 2 + (double)C * C));
         }
         ffree(qk, qkb); ffree(vT, vtb);
@@ -815,7 +828,7 @@ struct Builder {
       auto& lops = lane ? e->ops2 : e->ops;
       lops.insert(lops.begin(), b200_ncsnpp::Op{6, 0.0, [=](cudaStream_t st) {
         return cudaMemsetAsync(sb, 0, (size_t)sn, st) == cudaSuccess ? 0 : (set_error("stats memset failed"), 1);
-      }});
+      }, "zero GroupNorm sums", 0.0});
     }
     (void)eb; (void)t1b; (void)t2b; (void)db; (void)xcb;
     return rc;
@@ -1021,6 +1034,12 @@ int b200_ncsnpp_op_info(const b200_ncsnpp_t* h, long long index, char* name, int
   if (name && name_cap > 0) { strncpy(name, o.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
   if (kind) *kind = o.kind;
   if (flops) *flops = o.flops;
+  return 0;
+}
+
+int b200_ncsnpp_op_bytes(const b200_ncsnpp_t* h, long long index, double* bytes) {
+  B200_REQUIRE(h && bytes && index >= 0 && index < (long long)(h->ops.size() + h->ops2.size()), "op_bytes: index out of range");
+  *bytes = (index < (long long)h->ops.size() ? h->ops[index] : h->ops2[index - h->ops.size()]).bytes;
   return 0;
 }
 
