@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
       return __ldg(reinterpret_cast<const float4*>(src + (long long)px * Cs));
     };
     // The first batch of loads is issued BEFORE the (fp64 divide / sqrt) statistics so that their latency hides it.
-    constexpr int U = 4;
+    constexpr int U = XH ? 8 : 4;   // fp16 input: half the bytes per load, twice the loads in flight
     float4 v[U];
     int pix = p0 + lane;
 #pragma unroll

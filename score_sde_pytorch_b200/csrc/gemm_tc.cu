@@ -307,6 +307,49 @@ __device__ __forceinline__ void swap_chunk(const uint32_t (&v)[32], float add, f
   }
 }
 
+// One 32-column chunk of the row-per-lane epilogue (lane = output row, v[c] = column n0 + c), specialised like
+// swap_chunk: RES residual add, MODE store format (0 fp32, 1 TF32-rounded fp32, 2 fp16 as 16-byte stores of 8),
+// STATS GroupNorm quad sums of the stored fp32 values into st[0..7] (sums) / st[8..15] (sums of squares).
+template <bool RES, int MODE, bool STATS>
+__device__ __forceinline__ void row_chunk(const uint32_t (&v)[32], const Epilogue& e, long long gm, int n0, int img, float (&st)[16]) {
+  const float* bias = e.bias ? e.bias + n0 : nullptr;
+  const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
+  const float* res = RES ? e.residual + gm * e.ld_res + n0 : nullptr;
+  float* dst = e.out + gm * e.ld_out + n0;
+  uint16_t* dh = reinterpret_cast<uint16_t*>(e.out) + gm * e.ld_out + n0;
+  const float scale = e.scale;
+  uint2 pend = make_uint2(0u, 0u);
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) {
+    float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+    if (bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+    if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+    if (RES) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+    o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
+    if (MODE == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    if (MODE == 2) {
+      const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+      if ((c & 4) == 0) pend = hq;
+      else *reinterpret_cast<uint4*>(dh + c - 4) = make_uint4(pend.x, pend.y, hq.x, hq.y);
+    } else {
+      *reinterpret_cast<float4*>(dst + c) = o;
+    }
+    if (STATS) {
+      st[c >> 2] = (o.x + o.y) + (o.z + o.w);
+      st[8 + (c >> 2)] = fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+    }
+  }
+}
+// runtime-uniform selection of the specialisation (one branch tree per chunk instead of several per element)
+__device__ __forceinline__ void row_chunk_dispatch(const uint32_t (&v)[32], const Epilogue& e, bool has_res, bool stats,
+                                                   long long gm, int n0, int img, float (&st)[16]) {
+  const int mode = e.round_tf32;
+#define B200_ROW(R, M) do { if (stats) row_chunk<R, M, true>(v, e, gm, n0, img, st); else row_chunk<R, M, false>(v, e, gm, n0, img, st); } while (0)
+  if (has_res) { if (mode == 0) B200_ROW(true, 0); else if (mode == 1) B200_ROW(true, 1); else B200_ROW(true, 2); }
+  else { if (mode == 0) B200_ROW(false, 0); else if (mode == 1) B200_ROW(false, 1); else B200_ROW(false, 2); }
+#undef B200_ROW
+}
+
 // ---------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------
@@ -510,29 +553,7 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        if (valid) {
-          float* dst = e.out + gm * e.ld_out + n0;
-          const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
-          const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
-          uint2 pend = make_uint2(0u, 0u);
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
-                                   __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-            if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-            if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            if (e.round_tf32 == 2) {   // fp16 operand for the next contraction: two quads -> one 16-byte store
-              const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
-              if ((c & 4) == 0) pend = hq;
-              else *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + gm * e.ld_out + n0 + c - 4) = make_uint4(pend.x, pend.y, hq.x, hq.y);
-            } else *reinterpret_cast<float4*>(dst + c) = o;
-            st[c >> 2] = (o.x + o.y) + (o.z + o.w);
-            st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-          }
-        }
+        if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
         if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);   // whole warp, convergent
       }
       tc_fence_before();
@@ -802,7 +823,10 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // 1x1 convolutions with 256-multiple channel counts are output-bound launches: the swapped form's coalesced
     // epilogue measured 12-20 % faster (profiles/r01_c11_exp.log).  B200_TC_SWAP=1 restricts swapping to 128-channel outputs.
     static const bool swap_1x1 = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '1'); }();
-    const bool can_swap = allow_swap && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1)) && (d.H * d.W) % 256 == 0 &&
+    // B200_TC_SWAP=3 (experiment): swap every eligible convolution, B200_TC_SWAP=4: those with a residual
+    static const int swap_all = [] { const char* v = getenv("B200_TC_SWAP"); return v ? atoi(v) : 0; }();
+    const bool swap_more = swap_all == 3 || (swap_all == 4 && d.epi.residual != nullptr);
+    const bool can_swap = allow_swap && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1) || swap_more) && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
     // auto (default): direct stores with the deepest operand ring (measured best for every launch shape,
     // profiles/r01_c7_conv_isolated.log); 128-channel convolutions use the swapped-operand form.

@@ -207,29 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        if (valid) {
-          float* dst = e.out + gm * e.ld_out + n0;
-          const float* res = e.residual ? e.residual + gm * e.ld_res + n0 : nullptr;
-          const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
-          uint2 pend = make_uint2(0u, 0u);
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
-                                   __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-            if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            if (res) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-            if (e.round_tf32 == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            if (e.round_tf32 == 2) {   // fp16 operand for the next contraction: two quads -> one 16-byte store
-              const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
-              if ((c & 4) == 0) pend = hq;
-              else *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + gm * e.ld_out + n0 + c - 4) = make_uint4(pend.x, pend.y, hq.x, hq.y);
-            } else *reinterpret_cast<float4*>(dst + c) = o;
-            st[c >> 2] = (o.x + o.y) + (o.z + o.w);
-            st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-          }
-        }
+        if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
         if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);
       }
       tc_fence_before();

@@ -1,15 +1,21 @@
 #!/bin/bash
-# fp16 operand mode: gn_apply prefetch, 16-byte fp16 epilogue stores, bench variants
+# experiments: row_chunk epilogue, swapped form for 256-channel convs with a residual
 mkdir -p gpurun_out
 TAG=$1; L=gpurun_out/exp_$TAG.log; rm -f $L
+for args in "--c1 256 --cout 256 --hw 16 --batch 512" "--c1 256 --cout 256 --hw 16 --batch 512 --residual" "--c1 512 --cout 256 --hw 16 --batch 512" "--c1 256 --cout 256 --hw 32 --batch 512"; do
+  python tools/ncu_conv.py --f16 $args >> $L 2>&1
+  B200_TC_SWAP=3 python tools/ncu_conv.py --f16 $args >> $L 2>&1
+done
 timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_engine.py tests/test_gpu_kernels.py -q -m gpu --tb=short -p no:cacheprovider >> $L 2>&1; echo "tests exit $?" >> $L
-timeout 300 python __graft_entry__.py smoke >> $L 2>&1; echo "smoke exit $?" >> $L
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${TAG}.json 2>> $L; echo "bench exit $?" >> $L
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-variants > gpurun_out/bench_${TAG}_$name.json 2>> $L; }
+run default A=1
+run swap4 B200_TC_SWAP=4
+run swap3 B200_TC_SWAP=3
+run default2 A=1
 timeout 300 python tools/profile_ops.py --batch 1024 --precision f16 --md gpurun_out/ops_${TAG}_f16.md > /dev/null 2>> $L; echo "profile_ops exit $?" >> $L
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/ncu_step.py --batch 1024 --precision f16 > gpurun_out/ncu_list_$TAG.log 2>&1; echo "nculist exit $?" >> $L
-grep -v "^$" $L | tail -30
-python -c "
+grep -v "^$" $L | tail -24
+for f in gpurun_out/bench_${TAG}_*.json; do echo $f; python -c "
 import json
-d=json.loads(open('gpurun_out/bench_${TAG}.json').read().strip().splitlines()[-1]); r=d['roofline']
-print(d['value'],'img/s',d['ms_per_step'],'ms/step e2e',d['e2e']['value'],'peak',r['peak'],'frac',r['frac'],'tc_ms',r['forward_ms_by_kind']['tcgen05_contraction']['ms'],'gn_ms',r['forward_ms_by_kind']['groupnorm']['ms'], d['clocks'], d.get('variants'), d.get('cpu_baseline'))
-"
+d=json.loads(open('$f').read().strip().splitlines()[-1]); r=d['roofline']
+print(d['value'],'img/s',d['ms_per_step'],'ms/step peak',r['peak'],'tc_ms',r['forward_ms_by_kind']['tcgen05_contraction']['ms'],'gn_ms',r['forward_ms_by_kind']['groupnorm']['ms'], d['clocks']['sm_mhz'])
+"; done
