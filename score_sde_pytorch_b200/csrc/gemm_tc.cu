@@ -48,6 +48,7 @@ struct TcParams {
   int N_total, tiles_n;
   int nbatch, tiles_m_per_batch, M_per_batch;
   int a_batch_rows, w_batch_rows;
+  int epi_t;                               // direct epilogue: 1 = transpose 32x32 blocks through smem for coalesced global access
   int f16;                                 // 1: A and W are fp16 (tcgen05 kind::f16, 64-channel K steps); 0: TF32-grid fp32 (32-channel K steps)
   int bke;                                 // channels per K step: one 128-byte swizzle row = 32 fp32 or 64 fp16
   int epi_mode;                            // 0: direct register->global stores, 1: smem-staged TMA store (+TMA residual)
@@ -189,7 +190,8 @@ struct SmemLayout {
   static constexpr int EPI_TILE_BYTES = BM * 32 * 4;         // one 128-row x 32-column fp32 chunk (128-B swizzled rows)
   static constexpr int OUT_OFFSET = STAGES * STAGE_BYTES;   // 3 output staging chunks for the TMA store
   static constexpr int RES_OFFSET = OUT_OFFSET + (STAGED ? 3 : 0) * EPI_TILE_BYTES;   // 2 residual chunks landed by TMA
-  static constexpr int BAR_OFFSET = RES_OFFSET + (STAGED ? 2 : 0) * EPI_TILE_BYTES;
+  static constexpr int TRN_OFFSET = RES_OFFSET + (STAGED ? 2 : 0) * EPI_TILE_BYTES;   // direct epilogue: 8 warps x 4 KB transposition scratch
+  static constexpr int BAR_OFFSET = TRN_OFFSET + (STAGED ? 0 : 8 * 4096);
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-B alignment
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
@@ -340,6 +342,83 @@ __device__ __forceinline__ void row_chunk(const uint32_t (&v)[32], const Epilogu
     }
   }
 }
+// Coalesced form of the same chunk.  A lane that owns one accumulator ROW touches 32 different 128-byte lines with
+// every 128-bit load/store (the in-step ncu capture of the +residual 256-channel convolution showed the eight
+// epilogue warps bound by L1 wavefronts, tensor pipe 48 % vs 70 % without the residual).  Here the warp first
+// transposes its 32x32 block through 4 KB of warp-private shared memory (XOR-swizzled 16-byte slots: conflict-free
+// both ways), after which lane l owns column quad l%8 of rows l/8, l/8+4, ...: eight consecutive lanes cover one
+// 128-byte line, a warp instruction covers 4 lines instead of 32, bias / time-embedding quads are loaded once per
+// chunk, and the GroupNorm quad sums need 2 shuffle steps instead of the 16-shuffle butterfly.
+//   gm0: global row of the block's first row; rows_valid: rows of the block inside the matrix (0..32);
+//   img0: image of the first row; rows of one block span two images only when rows_per_img == 16.
+template <bool RES, int MODE, bool STATS>
+__device__ __forceinline__ void row_chunk_t(const uint32_t (&v)[32], uint8_t* tbuf, const Epilogue& e, double* qstats, int n_total,
+                                            long long gm0, int rows_valid, int n0, int img0, int lane) {
+#pragma unroll
+  for (int qd = 0; qd < 8; ++qd)
+    *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((qd ^ (lane & 7)) << 4)) = make_uint4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+  __syncwarp();
+  const int cq = lane & 7, r0 = lane >> 3, col = n0 + cq * 4;
+  const bool two_img = e.rows_per_img < 32;
+  float4 addA = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.bias) addA = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  float4 addB = addA;
+  if (e.rowvec) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(e.rowvec + img0 * e.rowvec_ld + col));
+    addA.x += t.x; addA.y += t.y; addA.z += t.z; addA.w += t.w;
+    if (two_img) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(e.rowvec + (img0 + 1) * e.rowvec_ld + col));
+      addB.x += u.x; addB.y += u.y; addB.z += u.z; addB.w += u.w;
+    } else addB = addA;
+  }
+  const float scale = e.scale;
+  float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = r0 + 4 * i;
+    float4 o = *reinterpret_cast<const float4*>(tbuf + row * 128 + ((cq ^ (row & 7)) << 4));
+    if (row < rows_valid) {
+      const long long g = gm0 + row;
+      const bool second = two_img && i >= 4;                 // rows 16..31 of the block: the next image
+      const float4 ad = second ? addB : addA;
+      o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+      if (RES) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.residual + g * e.ld_res + col)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+      o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
+      if (MODE == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      if (MODE == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.out) + g * e.ld_out + col) = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+      else *reinterpret_cast<float4*>(e.out + g * e.ld_out + col) = o;
+      if (STATS) {
+        const float s = (o.x + o.y) + (o.z + o.w), q2 = fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+        if (second) { sB += s; qB += q2; } else { sA += s; qA += q2; }
+      }
+    }
+  }
+  __syncwarp();                                            // the scratch block is free for the next chunk
+  if (STATS) {
+    sA += __shfl_xor_sync(0xffffffffu, sA, 8); qA += __shfl_xor_sync(0xffffffffu, qA, 8);
+    sA += __shfl_xor_sync(0xffffffffu, sA, 16); qA += __shfl_xor_sync(0xffffffffu, qA, 16);
+    if (two_img) {
+      sB += __shfl_xor_sync(0xffffffffu, sB, 8); qB += __shfl_xor_sync(0xffffffffu, qB, 8);
+      sB += __shfl_xor_sync(0xffffffffu, sB, 16); qB += __shfl_xor_sync(0xffffffffu, qB, 16);
+    }
+    if (r0 == 0 && rows_valid > 0) {
+      double* qd = qstats + ((long long)img0 * (n_total >> 2) + (col >> 2)) * 2;
+      atomicAdd(qd, (double)sA); atomicAdd(qd + 1, (double)qA);
+      if (two_img && rows_valid > 16) { qd += (long long)(n_total >> 2) * 2; atomicAdd(qd, (double)sB); atomicAdd(qd + 1, (double)qB); }
+    }
+  }
+}
+__device__ __forceinline__ void row_chunk_t_dispatch(const uint32_t (&v)[32], uint8_t* tbuf, const Epilogue& e, double* qstats, int n_total,
+                                                     long long gm0, int rows_valid, int n0, int img0, int lane) {
+  const int mode = e.round_tf32;
+  const bool has_res = e.residual != nullptr, stats = qstats != nullptr;
+#define B200_ROWT(R, M) do { if (stats) row_chunk_t<R, M, true>(v, tbuf, e, qstats, n_total, gm0, rows_valid, n0, img0, lane); \
+                             else row_chunk_t<R, M, false>(v, tbuf, e, qstats, n_total, gm0, rows_valid, n0, img0, lane); } while (0)
+  if (has_res) { if (mode == 0) B200_ROWT(true, 0); else if (mode == 1) B200_ROWT(true, 1); else B200_ROWT(true, 2); }
+  else { if (mode == 0) B200_ROWT(false, 0); else if (mode == 1) B200_ROWT(false, 1); else B200_ROWT(false, 2); }
+#undef B200_ROWT
+}
+
 // runtime-uniform selection of the specialisation (one branch tree per chunk instead of several per element)
 __device__ __forceinline__ void row_chunk_dispatch(const uint32_t (&v)[32], const Epilogue& e, bool has_res, bool stats,
                                                    long long gm, int n0, int img, float (&st)[16]) {
@@ -553,8 +632,18 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
-        if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);   // whole warp, convergent
+        if (p.epi_t) {
+          if constexpr (!STAGED) {
+            const int row0 = mt * BM + q * 32;                                   // first row of this warp's 32x32 block
+            const int rows_valid = min(32, max(0, p.M_per_batch - row0));
+            const long long gm0 = (long long)b * p.M_per_batch + row0;
+            row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid, n0,
+                                 rows_valid > 0 ? (int)(gm0 / e.rows_per_img) : 0, lane);
+          }
+        } else {
+          if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
+          if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);   // whole warp, convergent
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -810,6 +899,11 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   p.S = d.taps == 9 ? 3 : 1; p.pad = (d.taps == 9 && !d.valid_pad) ? 1 : 0;
   p.stride = d.stride == 2 ? 2 : 1;
   p.f16 = d.f16 ? 1 : 0;
+  {
+    static const bool epi_t = [] { const char* v = getenv("B200_TC_EPI_T"); return !(v && v[0] == '0'); }();
+    // two images per 32-row block only for 4x4 images (rows_per_img == 16); otherwise blocks must not straddle images
+    p.epi_t = epi_t && (d.epi.rows_per_img == 16 || d.epi.rows_per_img % 32 == 0 || (!d.epi.rowvec && !d.qstats)) ? 1 : 0;
+  }
   const bool f16 = d.f16 != 0;
   const int bke = f16 ? 64 : BKE;            // elements per 128-byte K step
   const uint64_t es = f16 ? 2 : 4;           // operand element size

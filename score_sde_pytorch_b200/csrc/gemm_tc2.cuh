@@ -18,7 +18,8 @@
 template <int BN, int STAGES>
 struct Smem2 {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / 2) * BKE * 4;   // A rows (16 KB) + this CTA's half of the W tile
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TRN_OFFSET = STAGES * STAGE_BYTES;                  // 8 epilogue warps x 4 KB transposition scratch
+  static constexpr int BAR_OFFSET = TRN_OFFSET + 8 * 4096;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
@@ -207,8 +208,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
-        if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);
+        if (p.epi_t) {
+          const int row0 = mt * BM + q * 32;
+          const int rows_valid = (mg < tiles_m_total) ? min(32, max(0, p.M_per_batch - row0)) : 0;
+          const long long gm0 = (long long)b * p.M_per_batch + row0;
+          row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid, n0,
+                               rows_valid > 0 ? (int)(gm0 / e.rows_per_img) : 0, lane);
+        } else {
+          if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
+          if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();

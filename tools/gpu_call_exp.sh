@@ -1,16 +1,16 @@
 #!/bin/bash
-# experiments: row_chunk epilogue, swapped form for 256-channel convs with a residual
+# experiment: transposed (coalesced) direct epilogue
 mkdir -p gpurun_out
 TAG=$1; L=gpurun_out/exp_$TAG.log; rm -f $L
-for args in "--c1 256 --cout 256 --hw 16 --batch 512" "--c1 256 --cout 256 --hw 16 --batch 512 --residual" "--c1 512 --cout 256 --hw 16 --batch 512" "--c1 256 --cout 256 --hw 32 --batch 512"; do
+for args in "--c1 256 --cout 256 --hw 16 --batch 512" "--c1 256 --cout 256 --hw 16 --batch 512 --residual" "--c1 256 --cout 256 --hw 8 --batch 512 --residual" "--c1 256 --cout 256 --hw 4 --batch 512 --residual"; do
+  B200_TC_EPI_T=0 python tools/ncu_conv.py --f16 $args >> $L 2>&1
   python tools/ncu_conv.py --f16 $args >> $L 2>&1
-  B200_TC_SWAP=3 python tools/ncu_conv.py --f16 $args >> $L 2>&1
 done
 timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_engine.py tests/test_gpu_kernels.py -q -m gpu --tb=short -p no:cacheprovider >> $L 2>&1; echo "tests exit $?" >> $L
+B200_TC_2CTA=0 B200_TC_SWAP=0 timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu --tb=short -p no:cacheprovider -k "tcgen05 or cifar10" >> $L 2>&1; echo "tests(single-cta, no swap) exit $?" >> $L
 run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-variants > gpurun_out/bench_${TAG}_$name.json 2>> $L; }
 run default A=1
-run swap4 B200_TC_SWAP=4
-run swap3 B200_TC_SWAP=3
+run rowlane B200_TC_EPI_T=0
 run default2 A=1
 timeout 300 python tools/profile_ops.py --batch 1024 --precision f16 --md gpurun_out/ops_${TAG}_f16.md > /dev/null 2>> $L; echo "profile_ops exit $?" >> $L
 grep -v "^$" $L | tail -24
