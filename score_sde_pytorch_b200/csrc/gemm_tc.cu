@@ -36,7 +36,6 @@ namespace {
 
 constexpr int BM = 128;          // rows (pixels) per tile == UMMA M
 constexpr int BKE = 32;          // fp32 elements per K step == one 128-byte swizzle row
-constexpr int UMMA_K = 8;        // tf32
 constexpr int A_STAGE_BYTES = BM * BKE * 4;   // 16 KiB
 
 struct TcParams {
@@ -48,7 +47,6 @@ struct TcParams {
   int N_total, tiles_n;
   int nbatch, tiles_m_per_batch, M_per_batch;
   int a_batch_rows, w_batch_rows;
-  int epi_t;                               // direct epilogue: 1 = transpose 32x32 blocks through smem for coalesced global access
   int f16;                                 // 1: A and W are fp16 (tcgen05 kind::f16, 64-channel K steps); 0: TF32-grid fp32 (32-channel K steps)
   int bke;                                 // channels per K step: one 128-byte swizzle row = 32 fp32 or 64 fp16
   int epi_mode;                            // 0: direct register->global stores, 1: smem-staged TMA store (+TMA residual)
@@ -113,7 +111,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Pull one 128-byte line towards L2 without occupying a register: the epilogues use it for their residual rows
 // while they still wait for the accumulator, so the later loads hit L2 instead of paying an HBM round trip
@@ -309,42 +306,12 @@ __device__ __forceinline__ void swap_chunk(const uint32_t (&v)[32], float add, f
   }
 }
 
-// One 32-column chunk of the row-per-lane epilogue (lane = output row, v[c] = column n0 + c), specialised like
-// swap_chunk: RES residual add, MODE store format (0 fp32, 1 TF32-rounded fp32, 2 fp16 as 16-byte stores of 8),
-// STATS GroupNorm quad sums of the stored fp32 values into st[0..7] (sums) / st[8..15] (sums of squares).
-template <bool RES, int MODE, bool STATS>
-__device__ __forceinline__ void row_chunk(const uint32_t (&v)[32], const Epilogue& e, long long gm, int n0, int img, float (&st)[16]) {
-  const float* bias = e.bias ? e.bias + n0 : nullptr;
-  const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + n0 : nullptr;
-  const float* res = RES ? e.residual + gm * e.ld_res + n0 : nullptr;
-  float* dst = e.out + gm * e.ld_out + n0;
-  uint16_t* dh = reinterpret_cast<uint16_t*>(e.out) + gm * e.ld_out + n0;
-  const float scale = e.scale;
-  uint2 pend = make_uint2(0u, 0u);
-#pragma unroll
-  for (int c = 0; c < 32; c += 4) {
-    float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-    if (bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-    if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-    if (RES) { const float4 t = __ldg(reinterpret_cast<const float4*>(res + c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-    o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
-    if (MODE == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    if (MODE == 2) {
-      const uint2 hq = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
-      if ((c & 4) == 0) pend = hq;
-      else *reinterpret_cast<uint4*>(dh + c - 4) = make_uint4(pend.x, pend.y, hq.x, hq.y);
-    } else {
-      *reinterpret_cast<float4*>(dst + c) = o;
-    }
-    if (STATS) {
-      st[c >> 2] = (o.x + o.y) + (o.z + o.w);
-      st[8 + (c >> 2)] = fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
-    }
-  }
-}
-// Coalesced form of the same chunk.  A lane that owns one accumulator ROW touches 32 different 128-byte lines with
+// One 32-row x 32-column block of the direct epilogue (row-major outputs), specialised like swap_chunk: RES residual
+// add, MODE store format (0 fp32, 1 TF32-rounded fp32, 2 fp16), STATS GroupNorm quad sums of the stored fp32 values.
+// tcgen05.ld hands each lane one accumulator ROW; storing from that layout touches 32 different 128-byte lines with
 // every 128-bit load/store (the in-step ncu capture of the +residual 256-channel convolution showed the eight
-// epilogue warps bound by L1 wavefronts, tensor pipe 48 % vs 70 % without the residual).  Here the warp first
+// epilogue warps bound by L1 wavefronts, tensor pipe 48 % vs 70 % without the residual; measured A/B of the two
+// forms: 173 -> 153 us for that launch, -2.2 % per PC step, profiles/r01_c23_*).  So the warp first
 // transposes its 32x32 block through 4 KB of warp-private shared memory (XOR-swizzled 16-byte slots: conflict-free
 // both ways), after which lane l owns column quad l%8 of rows l/8, l/8+4, ...: eight consecutive lanes cover one
 // 128-byte line, a warp instruction covers 4 lines instead of 32, bias / time-embedding quads are loaded once per
@@ -417,16 +384,6 @@ __device__ __forceinline__ void row_chunk_t_dispatch(const uint32_t (&v)[32], ui
   if (has_res) { if (mode == 0) B200_ROWT(true, 0); else if (mode == 1) B200_ROWT(true, 1); else B200_ROWT(true, 2); }
   else { if (mode == 0) B200_ROWT(false, 0); else if (mode == 1) B200_ROWT(false, 1); else B200_ROWT(false, 2); }
 #undef B200_ROWT
-}
-
-// runtime-uniform selection of the specialisation (one branch tree per chunk instead of several per element)
-__device__ __forceinline__ void row_chunk_dispatch(const uint32_t (&v)[32], const Epilogue& e, bool has_res, bool stats,
-                                                   long long gm, int n0, int img, float (&st)[16]) {
-  const int mode = e.round_tf32;
-#define B200_ROW(R, M) do { if (stats) row_chunk<R, M, true>(v, e, gm, n0, img, st); else row_chunk<R, M, false>(v, e, gm, n0, img, st); } while (0)
-  if (has_res) { if (mode == 0) B200_ROW(true, 0); else if (mode == 1) B200_ROW(true, 1); else B200_ROW(true, 2); }
-  else { if (mode == 0) B200_ROW(false, 0); else if (mode == 1) B200_ROW(false, 1); else B200_ROW(false, 2); }
-#undef B200_ROW
 }
 
 // ---------------------------------------------------------------------------
@@ -614,13 +571,13 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
       const long long mg = tile / p.tiles_n;
       const int b = (int)(mg / p.tiles_m_per_batch);
       const int mt = (int)(mg % p.tiles_m_per_batch);
-      const int m = mt * BM + r;
-      const bool valid = m < p.M_per_batch;
-      const long long gm = (long long)b * p.M_per_batch + m;
-      const int img = valid ? (int)(gm / e.rows_per_img) : 0;
-      if (e.residual && valid) {
+      const int row0 = mt * BM + q * 32;                                   // first row of this warp's 32-row blocks
+      const int rows_valid = min(32, max(0, p.M_per_batch - row0));
+      const long long gm0 = (long long)b * p.M_per_batch + row0;
+      const int img0 = rows_valid > 0 ? (int)(gm0 / e.rows_per_img) : 0;
+      if (e.residual && lane < rows_valid) {   // residual rows -> L2 while the accumulator is still being produced
 #pragma unroll
-        for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + gm * e.ld_res + nt * BN + half * (BN / 2) + i);
+        for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + (gm0 + lane) * e.ld_res + nt * BN + half * (BN / 2) + i);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -628,22 +585,9 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
       for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
-        const int n0 = nt * BN + j * 32;
-        float st[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        if (p.epi_t) {
-          if constexpr (!STAGED) {
-            const int row0 = mt * BM + q * 32;                                   // first row of this warp's 32x32 block
-            const int rows_valid = min(32, max(0, p.M_per_batch - row0));
-            const long long gm0 = (long long)b * p.M_per_batch + row0;
-            row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid, n0,
-                                 rows_valid > 0 ? (int)(gm0 / e.rows_per_img) : 0, lane);
-          }
-        } else {
-          if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
-          if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);   // whole warp, convergent
-        }
+        if constexpr (!STAGED)
+          row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid,
+                               nt * BN + j * 32, img0, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -881,7 +825,8 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
   }
   if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
   if (d.epi.per_img_div) return fail("per-image divisor is SIMT-only (the sigma-scaled head runs on CUDA cores)");
-  if (d.qstats && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("quad stats need rows_per_img % 32 == 0 or == 16");
+  // a 32-row epilogue block spans two images only for 4x4 images (rows_per_img == 16)
+  if ((d.qstats || d.epi.rowvec) && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("per-image epilogue terms need rows_per_img % 32 == 0 or == 16");
   if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 elements");
   if (d.epi.round_tf32 == 2 && d.epi.ld_out % 8) return fail("fp16 output pitch must be a multiple of 8 elements");
   return true;
@@ -899,11 +844,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   p.S = d.taps == 9 ? 3 : 1; p.pad = (d.taps == 9 && !d.valid_pad) ? 1 : 0;
   p.stride = d.stride == 2 ? 2 : 1;
   p.f16 = d.f16 ? 1 : 0;
-  {
-    static const bool epi_t = [] { const char* v = getenv("B200_TC_EPI_T"); return !(v && v[0] == '0'); }();
-    // two images per 32-row block only for 4x4 images (rows_per_img == 16); otherwise blocks must not straddle images
-    p.epi_t = epi_t && (d.epi.rows_per_img == 16 || d.epi.rows_per_img % 32 == 0 || (!d.epi.rowvec && !d.qstats)) ? 1 : 0;
-  }
+
   const bool f16 = d.f16 != 0;
   const int bke = f16 ? 64 : BKE;            // elements per 128-byte K step
   const uint64_t es = f16 ? 2 : 4;           // operand element size

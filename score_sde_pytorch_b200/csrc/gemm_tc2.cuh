@@ -182,7 +182,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   } else if (warp >= 4) {
     // ======================= epilogue (both CTAs, own 128 rows) =======================
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;   // two warps per TMEM lane quarter, half the columns each
-    const int r = q * 32 + lane;
     const Epilogue& e = p.epi;
     uint32_t acc = 0, acc_phase = 0;
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
@@ -190,13 +189,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
       const long long mg = (pair / p.tiles_n) * 2 + rank;
       const int b = (int)(mg / p.tiles_m_per_batch);
       const int mt = (int)(mg % p.tiles_m_per_batch);
-      const int m = mt * BM + r;
-      const bool valid = (mg < tiles_m_total) && (m < p.M_per_batch);
-      const long long gm = (long long)b * p.M_per_batch + m;
-      const int img = valid ? (int)(gm / e.rows_per_img) : 0;
-      if (e.residual && valid) {   // residual rows -> L2 while the accumulator is still being produced
+      const int row0 = mt * BM + q * 32;                                   // first row of this warp's 32-row blocks
+      const int rows_valid = (mg < tiles_m_total) ? min(32, max(0, p.M_per_batch - row0)) : 0;
+      const long long gm0 = (long long)b * p.M_per_batch + row0;
+      const int img0 = rows_valid > 0 ? (int)(gm0 / e.rows_per_img) : 0;
+      if (e.residual && lane < rows_valid) {   // residual rows -> L2 while the accumulator is still being produced
 #pragma unroll
-        for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + gm * e.ld_res + nt * BN + half * (BN / 2) + i);
+        for (int i = 0; i < BN / 2; i += 32) prefetch_l2(e.residual + (gm0 + lane) * e.ld_res + nt * BN + half * (BN / 2) + i);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -204,20 +203,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
       for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
-        const int n0 = nt * BN + j * 32;
-        float st[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        if (p.epi_t) {
-          const int row0 = mt * BM + q * 32;
-          const int rows_valid = (mg < tiles_m_total) ? min(32, max(0, p.M_per_batch - row0)) : 0;
-          const long long gm0 = (long long)b * p.M_per_batch + row0;
-          row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid, n0,
-                               rows_valid > 0 ? (int)(gm0 / e.rows_per_img) : 0, lane);
-        } else {
-          if (valid) row_chunk_dispatch(v, e, e.residual != nullptr, p.qstats != nullptr, gm, n0, img, st);
-          if (p.qstats) quad_stats_commit(p, e, st, img, valid, n0, lane);
-        }
+        row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid,
+                             nt * BN + j * 32, img0, lane);
       }
       tc_fence_before();
       __syncwarp();
