@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
       return __ldg(reinterpret_cast<const float4*>(src + (long long)px * Cs));
     };
     // The first batch of loads is issued BEFORE the (fp64 divide / sqrt) statistics so that their latency hides it.
-    constexpr int U = XH ? 8 : 4;   // fp16 input: half the bytes per load, twice the loads in flight
+    constexpr int U = 4;
     float4 v[U];
     int pix = p0 + lane;
 #pragma unroll
@@ -206,7 +206,8 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   B200_REQUIRE(!x1_f16 || (threads % Q == 0 && !raw), "gn_apply: fp16 input needs the quad-per-thread path (C=%d) and no raw copy", C);
   // aim for ~16 float4 per thread (four 4-deep batches), at least one block per image
   const long long per_img_units = (long long)HW * Q;
-  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / (threads * 16LL), 64));
+  static const int work = [] { const char* v = getenv("B200_GN_WORK"); return v ? std::max(4, atoi(v)) : 16; }();   // tuning knob
+  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / ((long long)threads * work), 64));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
   B200_REQUIRE(!x1_f16 || C2 == 0, "gn_apply: fp16 input is single-source");
