@@ -98,8 +98,13 @@ def cpu_pc_steps(batch, steps, warmup, threads=None):
   from oracle import ncsnpp_oracle as NO
   from oracle import sampling_oracle as SO
   from score_sde_pytorch_b200.models.ncsnpp import NCSNpp
-  if threads:
-    torch.set_num_threads(threads)
+  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank: override it)
+  if not threads:
+    try:
+      threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+      threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
   cfg = headline_config()
   torch.manual_seed(0)
   sd = NCSNpp(cfg).state_dict()

@@ -238,30 +238,25 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(o_ready);
       // ---- final: (Y + b_3 + x) * out_scale, quad sums, store ----
+      // Through the same coalescing block routine as the convolution epilogues.  Its 4 KB transposition scratch is
+      // this warp's slice of the operand buffer: O' is dead once Y is complete, and the slice (rows of this warp's
+      // lane quarter in K block `half`) is next written by the quarter's half-0 warp only after the pair barrier of
+      // the next tile's softmax, i.e. after this warp has left `final`.
       mbar_wait(y_full, tpar);
       tc_fence_after();
+      {
+        Epilogue ep;
+        ep.bias = p.b3; ep.rowvec = nullptr; ep.rowvec_ld = 0; ep.residual = p.x; ep.ld_res = AT_C; ep.per_img_div = nullptr;
+        ep.div_stride = 0; ep.scale = p.out_scale; ep.round_tf32 = 0; ep.rows_per_img = AT_T; ep.out = p.out; ep.ld_out = AT_C;
+        ep.out_nchw = 0;
+        const long long gm0 = (long long)b * AT_T + qh * BM + q * 32;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + 256 + half * 128 + j * 32, v);
-        const int n0 = half * 128 + j * 32;
-        float st[16];
-        float* dst = p.out + gm * AT_C + n0;
-        const float* res = p.x + gm * AT_C + n0;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.b3 + n0 + c));
-          const float4 xr = __ldg(reinterpret_cast<const float4*>(res + c));
-          float4 o;
-          o.x = (__uint_as_float(v[c]) + t.x + xr.x) * p.out_scale;
-          o.y = (__uint_as_float(v[c + 1]) + t.y + xr.y) * p.out_scale;
-          o.z = (__uint_as_float(v[c + 2]) + t.z + xr.z) * p.out_scale;
-          o.w = (__uint_as_float(v[c + 3]) + t.w + xr.w) * p.out_scale;
-          *reinterpret_cast<float4*>(dst + c) = o;
-          st[c >> 2] = (o.x + o.y) + (o.z + o.w);
-          st[8 + (c >> 2)] = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + 256 + half * 128 + j * 32, v);
+          if (p.qstats) row_chunk_t<true, 0, true>(v, pbuf + (warp - 4) * 4096, ep, p.qstats, AT_C, gm0, 32, half * 128 + j * 32, b, lane);
+          else row_chunk_t<true, 0, false>(v, pbuf + (warp - 4) * 4096, ep, p.qstats, AT_C, gm0, 32, half * 128 + j * 32, b, lane);
         }
-        if (p.qstats) quad_stats_commit_raw(p.qstats, AT_C, AT_T, st, b, true, n0, lane);
       }
       tc_fence_before();   // orders these TMEM reads before the p_ready arrival that lets the next tile's E V overwrite O/Y
     }
