@@ -192,6 +192,97 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
   }
 }
 
+// ---- lean streaming form -------------------------------------------------------------------------------
+// The generic kernel above turned out instruction-bound (ncu, profiles/r01_c26_ncu_gn_apply.md: 26 instructions
+// per element, issue slots 78 % busy, DRAM 41-67 %): per-element guards, 64-bit index multiplies, both SiLU paths
+// compiled into one loop, and an fp64 divide + square root per thread.  Here every launch property is a template
+// parameter, the per-quad scale / shift (rstd*gamma, beta - mean*rstd*gamma) are computed once per CTA into shared
+// memory (fp64 only for mean and variance; the reciprocal square root is taken in fp32), the main loop runs
+// unguarded over full batches of four pixels with pointer increments, and a short guarded tail finishes.
+//   XH: x1 holds fp16;  MODE: store format of y / raw (0 fp32 exact SiLU, 1 TF32 grid, 2 fp16; 1, 2 use the
+//   approximate SiLU);  ACT: SiLU;  RAW: also store the rounded copy of the input.
+template <bool XH, int MODE, bool ACT, bool RAW>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_stream_kernel(
+    const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+    const double* __restrict__ q1, const double* __restrict__ q2,
+    const float* __restrict__ gamma, const float* __restrict__ beta,
+    int HW, int G, float eps, double inv_n, float* __restrict__ y, float* __restrict__ raw) {
+  __shared__ float4 s_sc[128], s_sh[128];
+  const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
+  if (threadIdx.x < Q) {
+    const int c0 = threadIdx.x << 2, g0 = (c0 / cpg) * cpg;
+    double s = 0.0, ss = 0.0;
+    for (int c = g0; c < g0 + cpg; c += 4) {
+      const double* src = (c < C1) ? q1 + ((long long)b * (C1 >> 2) + (c >> 2)) * 2
+                                   : q2 + ((long long)b * (C2 >> 2) + ((c - C1) >> 2)) * 2;
+      s += src[0]; ss += src[1];
+    }
+    const double mean = s * inv_n;
+    const float var = fmaxf((float)(ss * inv_n - mean * mean), 0.f);
+    const float rstd = rsqrtf(var + eps), mu = (float)mean;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+    s_sc[threadIdx.x] = sc;
+    s_sh[threadIdx.x] = make_float4(fmaf(-mu, sc.x, be.x), fmaf(-mu, sc.y, be.y), fmaf(-mu, sc.z, be.z), fmaf(-mu, sc.w, be.w));
+  }
+  __syncthreads();
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const int L = blockDim.x / Q, qd = threadIdx.x % Q, lane = threadIdx.x / Q, c0 = qd << 2;
+  const float4 sc = s_sc[qd], sh = s_sh[qd];
+  const long long ib = (long long)b * HW;
+  const bool first = c0 < C1;
+  const int Cs = first ? C1 : C2;
+  int pix = p0 + lane;
+  // element offsets advance by a fixed stride per pixel step
+  const float* src = first ? x1 + (ib + pix) * C1 + c0 : x2 + (ib + pix) * C2 + (c0 - C1);
+  const uint16_t* srch = reinterpret_cast<const uint16_t*>(x1) + (ib + pix) * C1 + c0;
+  const long long sstep = (long long)L * Cs, ostep = (long long)L * C;
+  long long o = (ib + pix) * C + c0;
+  auto load4 = [&](long long off) -> float4 {
+    if (XH) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(srch + off));
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      return make_float4(a.x, a.y, c2.x, c2.y);
+    }
+    return __ldg(reinterpret_cast<const float4*>(src + off));
+  };
+  auto emit = [&](float4 v, long long oo) {
+    float4 r;
+    r.x = fmaf(v.x, sc.x, sh.x); r.y = fmaf(v.y, sc.y, sh.y); r.z = fmaf(v.z, sc.z, sh.z); r.w = fmaf(v.w, sc.w, sh.w);
+    if (ACT) {
+      if (MODE == 0) { r.x = silu_f(r.x); r.y = silu_f(r.y); r.z = silu_f(r.z); r.w = silu_f(r.w); }
+      else { r.x = silu_fast(r.x); r.y = silu_fast(r.y); r.z = silu_fast(r.z); r.w = silu_fast(r.w); }
+    }
+    store_operand4(y, oo, r, MODE);
+    if (RAW) store_operand4(raw, oo, v, MODE);
+  };
+  for (; pix + 3 * L < p1; pix += 4 * L) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = load4(u * sstep);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(v[u], o + u * ostep);
+    src += 4 * sstep; srch += 4 * sstep; o += 4 * ostep;
+  }
+  for (; pix < p1; pix += L) {
+    emit(load4(0), o);
+    src += sstep; srch += sstep; o += ostep;
+  }
+}
+
+template <bool XH, int MODE>
+static void gn_stream_launch(dim3 grid, int threads, cudaStream_t st, int act, bool has_raw, const float* x1, int C1, const float* x2,
+                             int C2, const double* q1, const double* q2, const float* gamma, const float* beta, int HW, int G,
+                             float eps, double inv_n, float* y, float* raw) {
+#define B200_GNS(A, R) gn_apply_stream_kernel<XH, MODE, A, R><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw)
+  if (act) { if (has_raw) B200_GNS(true, true); else B200_GNS(true, false); }
+  else { if (has_raw) B200_GNS(false, true); else B200_GNS(false, false); }
+#undef B200_GNS
+}
+
 int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
                     const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
                     int round_out, float* y, float* raw, cudaStream_t st, int x1_f16) {
@@ -211,6 +302,16 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
   B200_REQUIRE(!x1_f16 || C2 == 0, "gn_apply: fp16 input is single-source");
+  static const bool stream_form = [] { const char* v = getenv("B200_GN_STREAM"); return !(v && v[0] == '0'); }();
+  if (stream_form && threads % Q == 0 && Q <= 128 && (!x1_f16 || round_out == 2)) {
+    const double inv_n = 1.0 / ((double)HW * (C / G));
+    if (x1_f16) gn_stream_launch<true, 2>(grid, threads, st, act, raw != nullptr, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw);
+    else if (round_out == 2) gn_stream_launch<false, 2>(grid, threads, st, act, raw != nullptr, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw);
+    else if (round_out == 1) gn_stream_launch<false, 1>(grid, threads, st, act, raw != nullptr, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw);
+    else gn_stream_launch<false, 0>(grid, threads, st, act, raw != nullptr, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw);
+    B200_CHECK_LAUNCH();
+    return 0;
+  }
   if (x1_f16) gn_apply_kernel<true><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
   else gn_apply_kernel<false><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
