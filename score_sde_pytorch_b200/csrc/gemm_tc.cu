@@ -340,6 +340,17 @@ __device__ __forceinline__ void row_chunk_t(const uint32_t (&v)[32], uint8_t* tb
   }
   const float scale = e.scale;
   float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+  // all eight residual quads are requested before the first store: the output may alias the residual as far as
+  // the compiler knows, so loads left inside the store loop are serialised behind the stores (seen as one
+  // long-scoreboard stall per row in the attention kernel's profile)
+  float4 rr[8];
+  if (RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r0 + 4 * i;
+      rr[i] = row < rows_valid ? __ldg(reinterpret_cast<const float4*>(e.residual + (gm0 + row) * e.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = r0 + 4 * i;
@@ -349,7 +360,7 @@ __device__ __forceinline__ void row_chunk_t(const uint32_t (&v)[32], uint8_t* tb
       const bool second = two_img && i >= 4;                 // rows 16..31 of the block: the next image
       const float4 ad = second ? addB : addA;
       o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-      if (RES) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.residual + g * e.ld_res + col)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+      if (RES) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
       o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
       if (MODE == 1) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       if (MODE == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.out) + g * e.ld_out + col) = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));

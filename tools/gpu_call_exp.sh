@@ -5,7 +5,7 @@ TAG=$1; L=gpurun_out/exp_$TAG.log; rm -f $L
 timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_engine.py tests/test_gpu_kernels.py -q -m gpu --tb=short -p no:cacheprovider -s 2>&1 | grep -v "^$" | tail -15 >> $L; echo "tests exit $?" >> $L
 run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-variants > gpurun_out/bench_${TAG}_$name.json 2>> $L; }
 run default A=1
-run gnold B200_GN_STREAM=0
+run lanes1 B200_LANES=1
 run default2 A=1
 timeout 300 python tools/profile_ops.py --batch 1024 --precision f16 --md gpurun_out/ops_${TAG}_f16.md > /dev/null 2>> $L; echo "profile_ops exit $?" >> $L
 grep -v "^$" $L | tail -24
