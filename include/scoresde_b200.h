@@ -111,6 +111,8 @@ typedef struct {
                                  * CUDA cores, 2 = tensor cores on fp16 operands (same 11-bit significand as TF32,
                                  * fp32 accumulation; activations between layers stay fp32) */
   int keep_activations;         /* debug: never recycle activation buffers so b200_ncsnpp_tap works */
+  int lanes;                    /* 0/1: one plan over the whole batch (default); 2: two half-batch plans on two
+                                 * streams (batches >= 128).  Measured: no gain on a power-capped B200, see DESIGN.md */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

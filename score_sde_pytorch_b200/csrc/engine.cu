@@ -898,12 +898,13 @@ int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* 
 }
 
 namespace {
-// Lane split of a batch: two halves when the batch is large enough for every launch of a half to fill the GPU,
-// one lane otherwise (and always one with keep_activations, whose taps address whole-batch tensors).
-// B200_LANES=1 forces a single lane.
+// Lane split of a batch (cfg.lanes == 2, or B200_LANES=2 in the environment): two halves when the batch is large
+// enough for every launch of a half to fill the GPU; one lane otherwise, by default, and always with
+// keep_activations (its taps address whole-batch tensors).
 int lane0_images(const b200_ncsnpp* h, int batch) {
-  static const int lanes_env = [] { const char* v = getenv("B200_LANES"); return v ? atoi(v) : 2; }();
-  if (lanes_env < 2 || h->cfg.keep_activations || batch < 128) return batch;
+  static const int lanes_env = [] { const char* v = getenv("B200_LANES"); return v ? atoi(v) : 0; }();
+  const int lanes = lanes_env ? lanes_env : h->cfg.lanes;
+  if (lanes < 2 || h->cfg.keep_activations || batch < 128) return batch;
   return (batch + 1) / 2;
 }
 long long lane_bytes(b200_ncsnpp* h, int images, long long* arena_out) {

@@ -107,7 +107,7 @@ class NCSNpp(nn.Module):
   with fp32 accumulation and fp32 activations between layers, half the operand traffic and twice the
   MMA rate) or ``'fp32'`` (strict fp32 on CUDA cores; validation mode)."""
 
-  def __init__(self, config, precision=None, keep_activations=False):
+  def __init__(self, config, precision=None, keep_activations=False, lanes=1):
     super().__init__()
     self.config = config
     m = config.model
@@ -121,6 +121,7 @@ class NCSNpp(nn.Module):
     self.register_buffer('sigmas', torch.tensor(utils.get_sigmas(config)))   # fp64, as ncsnpp.py:42
     self.precision = (precision or getattr(m, 'precision', 'tf32')).lower()
     self.keep_activations = bool(keep_activations)
+    self.lanes = int(getattr(m, 'lanes', lanes))   # 2: evaluate batches >= 128 as two half-batch lanes on two streams
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
     L = len(ch_mult)
     all_res = [config.data.image_size // (2 ** i) for i in range(L)]
@@ -185,6 +186,7 @@ class NCSNpp(nn.Module):
       raise ValueError(f"precision must be 'tf32', 'fp32' or 'f16', got {self.precision!r}")
     c.precision = {'tf32': 0, 'fp32': 1, 'f16': 2}[self.precision]
     c.keep_activations = int(self.keep_activations)
+    c.lanes = self.lanes
     return c
 
   def native_param_table(self):

@@ -69,10 +69,10 @@ def test_forward_batch_replan_and_uniform_labels(dev):
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32'])
 def test_forward_two_lane_split_batch_matches_oracle(dev, precision):
-  """Batches >= 128 are evaluated as two half-batch lanes on two streams (GroupNorm of one lane under the
-  other's contractions).  Odd batch -> uneven halves; per-image labels -> the second lane's label offset."""
+  """``lanes=2``: batches >= 128 are evaluated as two half-batch lanes on two streams (GroupNorm of one lane
+  under the other's contractions).  Odd batch -> uneven halves; per-image labels -> the second lane's label offset."""
   cfg = golden_config('tiny')
-  model = seeded_model(cfg, precision=precision).to(dev)
+  model = seeded_model(cfg, precision=precision, lanes=2).to(dev)
   sd = {k: v.to(dev) for k, v in model.state_dict().items()}
   torch.manual_seed(5)
   B = 131
