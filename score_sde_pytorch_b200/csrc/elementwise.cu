@@ -752,37 +752,55 @@ int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, lon
 // 9*C <= 32 (C = 3 for images).  The 3->nf 3x3 conv (ncsnpp.py:268) then runs on tcgen05 as a
 // [B*HW, 32] x [nf, 32]^T product instead of a 27-deep CUDA-core loop.
 // ============================================================================
+template <int C>   // image channels (9*C <= 32); compile-time so the patch lives in registers
 __global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __restrict__ x, float* __restrict__ patches,
-                                                            int B, int C, int Hin, int Win, int H, int W, int stride, int pad,
+                                                            int B, int Hin, int Win, int H, int W, int stride, int pad,
                                                             int mode /* 1: 32 TF32 floats per row, 2: 64 halves per row */) {
-  const int qshift = mode == 2 ? 4 : 3;                        // quads per row: 8 (32-wide) or 16 (64-wide)
-  const long long total = ((long long)B * H * W) << qshift;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int k4 = (int)(i & ((1 << qshift) - 1)) << 2;
-  const long long pg = i >> qshift;
+  // One thread per output pixel: consecutive lanes read consecutive pixels of one channel plane (coalesced; the first
+  // version gave each lane a different (tap, channel) and paid ~64 L1 wavefronts per pixel), then the thread writes
+  // its whole 128-byte row.
+  const long long pg = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pg >= (long long)B * H * W) return;
   const int px = (int)(pg % W), py = (int)((pg / W) % H), b = (int)(pg / ((long long)W * H));
-  float v[4];
+  float v[32];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = k4 + j;
-    float t = 0.f;
-    if (k < 9 * C) {
-      const int tap = k / C, c = k % C;
-      const int iy = py * stride + tap / 3 - pad, ix = px * stride + tap % 3 - pad;
-      if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) t = __ldg(x + (((long long)b * C + c) * Hin + iy) * Win + ix);
-    }
-    v[j] = t;
+  for (int k = 0; k < 32; ++k) v[k] = 0.f;
+  const float* xb = x + (long long)b * C * Hin * Win;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = py * stride + tap / 3 - pad, ix = px * stride + tap % 3 - pad;
+    const bool in = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      v[tap * C + c] = in ? __ldg(xb + ((long long)c * Hin + iy) * Win + ix) : 0.f;
   }
-  store_operand4(patches, pg * (mode == 2 ? 64 : 32) + k4, make_float4(v[0], v[1], v[2], v[3]), mode);
+  if (mode == 2) {
+    uint16_t* row = reinterpret_cast<uint16_t*>(patches) + pg * 64;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(row + 8 * q) = make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
+                                                          pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
+#pragma unroll
+    for (int q = 4; q < 8; ++q) *reinterpret_cast<uint4*>(row + 8 * q) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    float* row = patches + pg * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(row + 4 * q) = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]), round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
+  }
 }
 
 int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
                           int pad, int mode, cudaStream_t st) {
-  B200_REQUIRE(9 * C <= 32, "im2col3x3: %d channels do not fit one 32-wide K step", C);
+  B200_REQUIRE(C >= 1 && C <= 3, "im2col3x3: %d channels unsupported (1..3 image channels)", C);
   B200_REQUIRE(mode == 1 || mode == 2, "im2col3x3: operand mode %d", mode);
-  const long long total = (long long)B * H * W * (mode == 2 ? 16 : 8);
-  im2col3x3_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, patches, B, C, Hin, Win, H, W, stride, pad, mode);
+  const long long total = (long long)B * H * W;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  switch (C) {
+    case 1: im2col3x3_nchw_kernel<1><<<blocks, 256, 0, st>>>(x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
+    case 2: im2col3x3_nchw_kernel<2><<<blocks, 256, 0, st>>>(x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
+    default: im2col3x3_nchw_kernel<3><<<blocks, 256, 0, st>>>(x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
+  }
   B200_CHECK_LAUNCH();
   return 0;
 }

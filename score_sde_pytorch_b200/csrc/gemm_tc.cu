@@ -1053,10 +1053,34 @@ int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out) {
   p.bv = d.bv; p.b3 = d.b3; p.x = d.x; p.out = d.out; p.qstats = d.qstats; p.nimg = d.nimg;
   p.logit_scale = (float)((1.0 / std::sqrt((double)AT_C)) * 1.4426950408889634);
   p.out_scale = d.out_scale;
+  if (const char* v = getenv("B200_ATTN_DBG")) if (v[0] == '1') {   // developer aid: per-phase clock stamps of CTA 0
+    B200_CHECK_CUDA(cudaMalloc(&p.dbg, 16 * 7 * sizeof(long long)));
+    B200_CHECK_CUDA(cudaMemset(p.dbg, 0, 16 * 7 * sizeof(long long)));
+  }
   *out = pl;
   return 0;
 }
-void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
+void tc_attn_plan_destroy(TcAttnPlan* p) {
+  if (p && p->prm.dbg) {
+    long long h[16 * 7];
+    if (cudaMemcpy(h, p->prm.dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char* names[6] = {"wait S", "softmax", "wait O", "convert", "wait Y", "final"};
+      double acc[6] = {0, 0, 0, 0, 0, 0}, gap = 0; int n = 0;
+      for (int t = 1; t < 13; ++t) {
+        if (!h[t * 7 + 6]) break;
+        for (int k = 0; k < 6; ++k) acc[k] += (double)(h[t * 7 + k + 1] - h[t * 7 + k]);
+        gap += (double)(h[t * 7] - h[(t - 1) * 7 + 6]); ++n;
+      }
+      if (n) {
+        fprintf(stderr, "attn_tc phases (cycles, mean of %d tiles of CTA 0):", n);
+        for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.0f |", names[k], acc[k] / n);
+        fprintf(stderr, " between tiles %.0f\n", gap / n);
+      }
+    }
+    cudaFree(p->prm.dbg);
+  }
+  delete p;
+}
 int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
   const long long tiles = 2LL * pl->prm.nimg;
   const int grid = (int)std::min<long long>(tiles, num_sms());
