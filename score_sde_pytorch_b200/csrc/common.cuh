@@ -117,6 +117,7 @@ struct Epilogue {
   float* out;
   long long ld_out;         // elements between consecutive rows of out (NHWC: C_out_total)
   int out_nchw;             // conv mode only: write [img][n][pix] instead of [m][n]
+  int n_valid;              // out_nchw on the tensor-core path: only output channels < n_valid exist (0 = all)
 };
 
 }  // namespace b200

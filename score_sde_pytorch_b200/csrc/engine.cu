@@ -21,7 +21,7 @@ using namespace b200;
 namespace {
 
 enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RESBLOCK, M_ATTN, M_PYR_DOWN, M_GN_OUT, M_CONV_OUT };
-enum PackKind { PK_COPY = 0, PK_CONV = 1, PK_NIN = 2, PK_CONV_FLAT32 = 3 };
+enum PackKind { PK_COPY = 0, PK_CONV = 1, PK_NIN = 2, PK_CONV_FLAT32 = 3, PK_CONV_PAD128 = 4 };
 
 struct Param {
   std::string name;
@@ -306,7 +306,14 @@ int build_graph(b200_ncsnpp* e) {
   { Mod m; m.kind = M_GN_OUT; m.index = (int)e->mods.size(); m.cin1 = in_ch;
     m.w = add_param(e, nm("weight"), {in_ch}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {in_ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
   { Mod m; m.kind = M_CONV_OUT; m.index = (int)e->mods.size(); m.cin1 = in_ch; m.cout = ch; m.res = c.image_size;
-    m.w = add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0); m.b = add_param(e, nm("bias"), {ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+    // Head on tensor cores: the ch (3) output channels become rows 0..ch-1 of a zero-padded 128-row weight tile
+    // ([9][128][in_ch]; bias padded likewise), run as a swapped-operand convolution whose epilogue stores only those
+    // rows, as NCHW, divided by sigma.  2.3x faster than the CUDA-core head despite the 125 idle rows.
+    m.tc0 = tcmode && ch <= 32 && tc_ok(e, in_ch, 0, 128, c.image_size, c.image_size, 9) && (c.image_size * c.image_size) % 256 == 0 &&
+            c.image_size <= 128;
+    m.w = m.tc0 ? add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV_PAD128, 9, ch, in_ch, om, -1, 9LL * 128 * in_ch)
+                : add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0);
+    m.b = add_param(e, nm("bias"), {ch}, PK_COPY, 0, 0, 0, 0, -1, m.tc0 ? 128 : 0); e->mods.push_back(m); }
 
   // contiguous Dense_0 block: one [sumC][4nf] matrix + [sumC] bias for a single batched linear
   e->dense_w_off = e->wcount; e->wcount += ((long long)e->sumC * 4 * nf + 63) & ~63LL;
@@ -793,14 +800,32 @@ struct Builder {
       Tensor a = talloc(h.C, h.H, h.W);
       // fp16 operand mode: the head's input is stored as fp16 too (the CUDA-core head is bound by its nine-fold
       // tap re-reads through L1/L2, so half the bytes is half the time); same 11-bit rounding as every other conv input
-      const int head_f16 = (om == 2 && ch <= 4 && h.C % 64 == 0) ? 1 : 0;
-      Tensor none; gn(h, none, mg.w, mg.b, 1, head_f16 ? 2 : 0, a, nullptr);
+      const Mod& mo = e->mods[mi];
+      const int head_f16 = (!mo.tc0 && om == 2 && ch <= 4 && h.C % 64 == 0) ? 1 : 0;
+      Tensor none; gn(h, none, mg.w, mg.b, 1, mo.tc0 ? om : head_f16 ? 2 : 0, a, nullptr);
       tfree(h);
-      const Mod& mo = e->mods[mi++];
+      ++mi;
       const int sbs = c.scale_by_sigma;
       const float *wo = e->W(mo.w), *bo = e->W(mo.b);
       const Tensor ain = a; const int Bc = B;
-      if (ch <= 4) {
+      if (mo.tc0) {
+        TcGemmDesc d; memset(&d, 0, sizeof(d));
+        d.a1 = a.p; d.C1 = a.C; d.conv = 1; d.H = R; d.W = R; d.nimg = B; d.taps = 9; d.stride = 1;
+        d.w = wo; d.N_total = 128; d.K_total = a.C; d.w_rows = 9LL * 128; d.nbatch = 1; d.epi_mode = 0; d.f16 = om == 2;
+        d.epi.bias = bo; d.epi.scale = 1.f; d.epi.rows_per_img = R * R; d.epi.out_nchw = 1; d.epi.n_valid = ch; d.epi.ld_out = 128;
+        d.epi.out = reinterpret_cast<float*>(uintptr_t(16));   // patched per call (tc_gemm_set_head)
+        if (!dry) {
+          TcGemmPlan* pl = nullptr;
+          if (int r = tc_gemm_plan_create(d, &pl)) { rc = r; return r; }
+          e->tcplans.push_back(pl);
+          name("conv3x3 %d->%d(pad 128) @%d nchw-out /sigma [%s]", a.C, ch, R, tc_gemm_form(pl));
+          next_bytes = (double)B * R * R * (a.C * (om == 2 ? 2.0 : 4.0) + ch * 4.0);
+          op(1, [=](cudaStream_t st) {
+            tc_gemm_set_head(pl, eng->out_l[ln], sbs ? eng->in_labels_l[ln] : nullptr, eng->uniform ? 0 : 1);
+            return tc_gemm_launch(pl, st);
+          }, 0, 2.0 * B * R * R * (double)ch * a.C * 9);
+        }
+      } else if (ch <= 4) {
         name("conv3x3 %d->%d @%d nchw-out [small-n]", a.C, ch, R);
         op(1, [=](cudaStream_t st) {
           return launch_conv3x3_small_n(ain.p, wo, bo, sbs ? eng->in_labels_l[ln] : nullptr, eng->uniform ? 0 : 1, eng->out_l[ln],
@@ -891,6 +916,8 @@ int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* 
   }
   if (p.pack == PK_CONV_FLAT32)   // OIHW (3x3, I*9 <= 32) -> [O][32] with k = tap*I + i (rest of the row stays zero)
     return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st, p.I, p.round == 2 ? 64 : 32);
+  if (p.pack == PK_CONV_PAD128)   // OIHW -> [tap][128][I], rows >= O stay zero
+    return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st, 128LL * p.I, p.I);
   if (p.pack == PK_CONV)   // OIHW -> [tap][O][I]
     return launch_pack_weight(src, dst, p.taps, p.O, p.I, (long long)p.I * p.taps, p.taps, 1, p.round, st);
   // NIN W[in][out] -> [out][in]

@@ -534,6 +534,34 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
           const int img = (int)(row_base / e.rows_per_img);          // rows_per_img % 256 == 0: one image per tile
           const float add = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
           float ssum = 0.f, ssq = 0.f;
+          if (e.out_nchw) {
+            // Network head (ncsnpp.py:374-380): the 128-row weight tile is zero-padded above the n_valid image
+            // channels, so only lanes < n_valid of lane quarter 0 hold results: (acc + bias) / sigma[img], written
+            // as NCHW with 128-bit stores along the pixel axis.  The other warps just release the accumulator.
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            if (q == 0) {
+              const float dv = e.per_img_div ? __ldg(e.per_img_div + img * e.div_stride) : 1.f;
+              const int hw = e.rows_per_img, pix_in_img = (int)(row_base - (long long)img * hw);
+#pragma unroll 1
+              for (int j = half * 4; j < half * 4 + 4; ++j) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + acc * BN + j * 32, v);
+                if (lane < e.n_valid) {
+                  float* dst = e.out + ((long long)img * e.n_valid + lane) * hw + pix_in_img + j * 32;
+#pragma unroll
+                  for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(dst + i) = make_float4((__uint_as_float(v[i]) + add) / dv, (__uint_as_float(v[i + 1]) + add) / dv,
+                                                                      (__uint_as_float(v[i + 2]) + add) / dv, (__uint_as_float(v[i + 3]) + add) / dv);
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            continue;
+          }
           if (e.residual) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)   // this lane's share of the warp's 128 residual lines (one per pixel)
@@ -834,8 +862,11 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
     if (!d.conv || d.stride == 2 || !d.w2) return fail("extra 1x1 phase needs a stride-1 convolution and its weights");
     if (d.C3 % bke || d.C3 <= 0 || (d.a4 && d.C4 % bke)) return fail("extra-phase channel counts must be multiples of 32 (tf32) / 64 (f16)");
   }
-  if (d.epi.out_nchw) return fail("NCHW output is SIMT-only");
-  if (d.epi.per_img_div) return fail("per-image divisor is SIMT-only (the sigma-scaled head runs on CUDA cores)");
+  if (d.epi.out_nchw) {   // network head: zero-padded 128-row weight tile, swapped form, NCHW store of the real channels
+    if (!(d.conv && d.N_total == 128 && d.epi.n_valid > 0 && d.epi.n_valid <= 32 && (d.H * d.W) % 256 == 0 && d.W <= BM && d.stride != 2 &&
+          !d.qstats && !d.epi.residual && !d.epi.rowvec && d.epi.round_tf32 == 0))
+      return fail("NCHW head needs a 128-row padded weight tile, HW % 256 == 0 and a plain epilogue");
+  } else if (d.epi.per_img_div) return fail("per-image divisor only with the NCHW head epilogue");
   // a 32-row epilogue block spans two images only for 4x4 images (rows_per_img == 16)
   if ((d.qstats || d.epi.rowvec) && !(d.epi.rows_per_img % 32 == 0 || d.epi.rows_per_img == 16)) return fail("per-image epilogue terms need rows_per_img % 32 == 0 or == 16");
   if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 elements");
@@ -1000,6 +1031,9 @@ const char* tc_gemm_form(const TcGemmPlan* p) {
   return p->bn == 256 ? "single256" : "single128";
 }
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
+void tc_gemm_set_head(TcGemmPlan* p, float* out_nchw, const float* per_img_div, long long div_stride) {
+  p->prm.epi.out = out_nchw; p->prm.epi.per_img_div = per_img_div; p->prm.epi.div_stride = div_stride;
+}
 // B200_TC_EPILOGUE = direct | staged | auto (default).  auto: the smem-staged TMA epilogue where it measured
 // faster (the swapped-operand 128-channel convolutions), direct register->global stores with the deeper
 // operand ring elsewhere.  Returns 0 direct, 1 staged, 2 auto.

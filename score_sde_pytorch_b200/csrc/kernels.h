@@ -109,6 +109,7 @@ bool tc_attn_supported(int T, int C);
 int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out);
 void tc_attn_plan_destroy(TcAttnPlan* p);
 int tc_attn_launch(const TcAttnPlan* p, cudaStream_t st);
+void tc_gemm_set_head(TcGemmPlan* p, float* out_nchw, const float* per_img_div, long long div_stride);   // per-call pointers of the NCHW head
 const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap" (+"/staged")
 
 // ---- pc_update.cu -----------------------------------------------------------
