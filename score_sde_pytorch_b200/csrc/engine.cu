@@ -309,7 +309,8 @@ int build_graph(b200_ncsnpp* e) {
     // Head on tensor cores: the ch (3) output channels become rows 0..ch-1 of a zero-padded 128-row weight tile
     // ([9][128][in_ch]; bias padded likewise), run as a swapped-operand convolution whose epilogue stores only those
     // rows, as NCHW, divided by sigma.  2.3x faster than the CUDA-core head despite the 125 idle rows.
-    m.tc0 = tcmode && ch <= 32 && tc_ok(e, in_ch, 0, 128, c.image_size, c.image_size, 9) && (c.image_size * c.image_size) % 256 == 0 &&
+    static const bool tc_head = [] { const char* v = getenv("B200_TC_HEAD"); return !(v && v[0] == '0'); }();
+    m.tc0 = tc_head && tcmode && ch <= 32 && tc_ok(e, in_ch, 0, 128, c.image_size, c.image_size, 9) && (c.image_size * c.image_size) % 256 == 0 &&
             c.image_size <= 128;
     m.w = m.tc0 ? add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV_PAD128, 9, ch, in_ch, om, -1, 9LL * 128 * in_ch)
                 : add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0);
