@@ -70,16 +70,18 @@ __device__ __forceinline__ void pbuf_store32(uint8_t* pbuf, int r, int k0, const
       uint4 u;
       u.x = pack_half2(v[8 * c], v[8 * c + 1]); u.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
       u.z = pack_half2(v[8 * c + 4], v[8 * c + 5]); u.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
-      *reinterpret_cast<uint4*>(pbuf_chunk(pbuf, kb, r, c0 + c)) = u;
+      sts128(smem_u32(pbuf_chunk(pbuf, kb, r, c0 + c)), u.x, u.y, u.z, u.w);
     }
   } else {
     const int kb = k0 >> 5;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<float4*>(pbuf_chunk(pbuf, kb, r, c)) =
-          make_float4(round_tf32(v[4 * c]), round_tf32(v[4 * c + 1]), round_tf32(v[4 * c + 2]), round_tf32(v[4 * c + 3]));
+      sts128(smem_u32(pbuf_chunk(pbuf, kb, r, c)), __float_as_uint(round_tf32(v[4 * c])), __float_as_uint(round_tf32(v[4 * c + 1])),
+             __float_as_uint(round_tf32(v[4 * c + 2])), __float_as_uint(round_tf32(v[4 * c + 3])));
   }
 }
+__device__ __forceinline__ float lds32(uint32_t saddr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ void sts32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 __device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
 template <bool F16>
@@ -191,9 +193,10 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
-      xchg[half * 128 + r] = mx;
+      const uint32_t xmine = smem_u32(xchg) + (half * 128 + r) * 4, xother = smem_u32(xchg) + ((half ^ 1) * 128 + r) * 4;
+      sts32(xmine, mx);
       pair_barrier(q);
-      mx = fmaxf(mx, xchg[(half ^ 1) * 128 + r]);
+      mx = fmaxf(mx, lds32(xother));
       const float moff = mx * p.logit_scale;
       float sum = 0.f;
 #pragma unroll 1
@@ -209,10 +212,10 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         pbuf_store32<F16>(pbuf, r, half * 128 + j * 32, ev);
       }
       pair_barrier(q);                                  // the partner has read this thread's max: the slot is free
-      xchg[half * 128 + r] = sum;
+      sts32(xmine, sum);
       fence_async_smem();                               // E (generic-proxy writes) -> visible to the tensor core
       pair_barrier(q);
-      sum += xchg[(half ^ 1) * 128 + r];
+      sum += lds32(xother);
       const float inv = 1.0f / sum;
       tc_fence_before();
       __syncwarp();

@@ -118,6 +118,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // for a register-held prefetch).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Explicit shared-space 128-bit accesses.  Through a generic pointer the compiler emitted LD.E / ST.E for the
+// epilogue's transposition scratch (it cannot prove the address space of a pointer derived from the dynamic smem
+// base), i.e. long-scoreboard loads that it then serialised one row at a time: the attention kernel's `final`
+// phase spent most of its samples waiting on them (profiles/r01_c31_ncu_attn_tc_f16.md).
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -321,9 +334,10 @@ __device__ __forceinline__ void swap_chunk(const uint32_t (&v)[32], float add, f
 template <bool RES, int MODE, bool STATS>
 __device__ __forceinline__ void row_chunk_t(const uint32_t (&v)[32], uint8_t* tbuf, const Epilogue& e, double* qstats, int n_total,
                                             long long gm0, int rows_valid, int n0, int img0, int lane) {
+  const uint32_t tb = smem_u32(tbuf);
 #pragma unroll
   for (int qd = 0; qd < 8; ++qd)
-    *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((qd ^ (lane & 7)) << 4)) = make_uint4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+    sts128(tb + lane * 128 + ((qd ^ (lane & 7)) << 4), v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
   __syncwarp();
   const int cq = lane & 7, r0 = lane >> 3, col = n0 + cq * 4;
   const bool two_img = e.rows_per_img < 32;
@@ -354,7 +368,7 @@ __device__ __forceinline__ void row_chunk_t(const uint32_t (&v)[32], uint8_t* tb
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = r0 + 4 * i;
-    float4 o = *reinterpret_cast<const float4*>(tbuf + row * 128 + ((cq ^ (row & 7)) << 4));
+    float4 o = lds128(tb + row * 128 + ((cq ^ (row & 7)) << 4));
     if (row < rows_valid) {
       const long long g = gm0 + row;
       const bool second = two_img && i >= 4;                 // rows 16..31 of the block: the next image
