@@ -383,15 +383,13 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict_
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                        const FirParams p) {
+  // grid = (x chunks over out_w * minor/4, out_h, images): no 64-bit div/mod chain per thread (the flat-index
+  // version spent more instructions decoding its index than filtering)
   const int mv = p.minor >> 2;
-  const long long total = (long long)p.major * p.out_h * p.out_w * mv;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int cm = (int)(i % mv) << 2;
-  long long t = i / mv;
-  const int ox = (int)(t % p.out_w); t /= p.out_w;
-  const int oy = (int)(t % p.out_h);
-  const int n = (int)(t / p.out_h);
+  const unsigned xi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xi >= (unsigned)(p.out_w * mv)) return;
+  const int cm = (int)(xi % (unsigned)mv) << 2, ox = (int)(xi / (unsigned)mv);
+  const int oy = blockIdx.y, n = blockIdx.z;
   const float* xin = x + (long long)n * p.in_h * p.in_w * p.minor + cm;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -420,14 +418,10 @@ __global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) fir4_up2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            const FirParams p) {
   const int mv = p.minor >> 2;
-  const long long total = (long long)p.major * p.in_h * p.in_w * mv;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cm = (int)(idx % mv) << 2;
-  long long t = idx / mv;
-  const int j = (int)(t % p.in_w); t /= p.in_w;
-  const int i = (int)(t % p.in_h);
-  const int n = (int)(t / p.in_h);
+  const unsigned xi = blockIdx.x * blockDim.x + threadIdx.x;   // grid = (x chunks over in_w * minor/4, in_h, images)
+  if (xi >= (unsigned)(p.in_w * mv)) return;
+  const int cm = (int)(xi % (unsigned)mv) << 2, j = (int)(xi / (unsigned)mv);
+  const int i = blockIdx.y, n = blockIdx.z;
   const float* xin = x + (long long)n * p.in_h * p.in_w * p.minor + cm;
   float4 v[3][3];
 #pragma unroll
@@ -475,17 +469,20 @@ int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int maj
   const bool vec = (minor % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0);
   const long long total = (long long)major * p.out_h * p.out_w * (vec ? minor / 4 : minor);
   if (total == 0) return 0;
-  if (vec && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && pad_x0 >= 0 && total < (1LL << 31) * 256) {
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (vec && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && pad_x0 >= 0 && major <= 65535 &&
+      p.out_h <= 65535 && (long long)p.out_w * (minor / 4) < (1LL << 31)) {
+    const int mv = minor / 4;
+    const int threads = (p.out_w * mv >= 256) ? 256 : 128;
+    const dim3 grid((unsigned)((p.out_w * mv + threads - 1) / threads), (unsigned)p.out_h, (unsigned)major);
     if (up_x == 2 && down_x == 1 && pad_x0 == 2 && p.out_h == 2 * in_h && p.out_w == 2 * in_w) {
-      const long long tin = (long long)major * in_h * in_w * (minor / 4);
-      fir4_up2_nhwc_kernel<<<(unsigned)((tin + 255) / 256), 256, 0, st>>>(x, y, p);
+      const int tin = (in_w * mv >= 256) ? 256 : 128;
+      fir4_up2_nhwc_kernel<<<dim3((unsigned)((in_w * mv + tin - 1) / tin), (unsigned)in_h, (unsigned)major), tin, 0, st>>>(x, y, p);
       B200_CHECK_LAUNCH();
       return 0;
     }
-    if (up_x == 2 && down_x == 1) { fir4_nhwc_kernel<2, 1><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
-    if (up_x == 1 && down_x == 2) { fir4_nhwc_kernel<1, 2><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
-    if (up_x == 1 && down_x == 1) { fir4_nhwc_kernel<1, 1><<<blocks, 256, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 2 && down_x == 1) { fir4_nhwc_kernel<2, 1><<<grid, threads, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 1 && down_x == 2) { fir4_nhwc_kernel<1, 2><<<grid, threads, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 1 && down_x == 1) { fir4_nhwc_kernel<1, 1><<<grid, threads, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
   }
   const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
   if (vec) upfirdn2d_kernel<4><<<grid, 256, 0, st>>>(x, y, p);
