@@ -917,12 +917,14 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // B200_TC_SWAP=3 (experiment): swap every eligible convolution, B200_TC_SWAP=4: those with a residual
     static const int swap_all = [] { const char* v = getenv("B200_TC_SWAP"); return v ? atoi(v) : 0; }();
     const bool swap_more = swap_all == 3 || (swap_all == 4 && d.epi.residual != nullptr);
-    const bool can_swap = allow_swap && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1) || swap_more) && (d.H * d.W) % 256 == 0 &&
+    // (the NCHW head epilogue exists only in the swapped form, so B200_TC_SWAP=0 does not apply to it)
+    const bool can_swap = (allow_swap || d.epi.out_nchw) && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1) || swap_more) && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
     // auto (default): direct stores with the deepest operand ring (measured best for every launch shape,
     // profiles/r01_c7_conv_isolated.log); 128-channel convolutions use the swapped-operand form.
     // B200_TC_EPILOGUE=staged selects the smem-staged TMA-store epilogue for A/B runs.
     p.swap = can_swap ? 1 : 0;
+    if (d.epi.out_nchw && !p.swap) { delete pl; B200_REQUIRE(false, "gemm_tc: the NCHW head needs the swapped-operand form"); }
     p.epi_mode = (req == 1 && d.epi.round_tf32 != 2) ? 1 : 0;   // fp16 outputs: direct stores only
     if (p.swap) pl->bn = 256;
     p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
