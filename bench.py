@@ -98,13 +98,13 @@ def cpu_pc_steps(batch, steps, warmup, threads=None):
   from oracle import ncsnpp_oracle as NO
   from oracle import sampling_oracle as SO
   from score_sde_pytorch_b200.models.ncsnpp import NCSNpp
-  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank: override it)
-  if not threads:
-    try:
-      threads = len(os.sched_getaffinity(0))
-    except AttributeError:
-      threads = os.cpu_count() or 1
-  torch.set_num_threads(threads)
+  # torch's own default (one thread per physical core) is the fastest setting for this workload: using every
+  # hyper-thread of the 128-way host made the oracle ~70x slower (127 s vs 1.8 s per iteration).  torchrun exports
+  # OMP_NUM_THREADS=1 to every rank, which would reduce the CPU arm to one core: undo that.
+  if threads:
+    torch.set_num_threads(threads)
+  elif torch.get_num_threads() <= 1:
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
   cfg = headline_config()
   torch.manual_seed(0)
   sd = NCSNpp(cfg).state_dict()
