@@ -1,28 +1,29 @@
 // tcgen05 / TMEM / TMA implicit GEMM for the NCSN++ contractions (3x3 and 1x1
-// convolutions, NIN projections, the batched attention products) on sm_100a.
+// convolutions, NIN projections, the attention products) on sm_100a.
 //
-//   out[b][m, n] = epi( sum_{src, tap, c} A_src(b, m, tap, c) * W(b)[tap][n][koff_src + c] )
+//   out[b][m, n] = epi( sum_{src, tap, c} A_src(b, m, tap, c) * W(b)[tap][n][koff_src + c]
+//                       (+ an optional extra 1x1 phase: the fused skip projection) )
 //
-// Operands are fp32 bit patterns already rounded to the TF32 grid by their producers
-// (GroupNorm-apply / softmax / previous epilogue for A, the weight packer for W), so the
-// tensor core's operand truncation is exact and the only contraction error is the TF32
-// operand rounding itself; accumulation is fp32 in TMEM.
+// Operands are written by their producers in the contraction's format: fp32 bit patterns
+// rounded to the TF32 grid (kind::tf32, 32 channels per 128-byte K step) or IEEE fp16
+// (kind::f16, 64 channels per K step); either way 11 significand bits, fp32 accumulation in TMEM.
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
-//   warp 0 lane 0 : TMA producer.  Per K step it lands one 128-row x 32-channel A tile
-//                   (a 4-D box of the NHWC tensor shifted by the filter tap; the zero
-//                   halo of 'same' padding comes from TMA out-of-bounds fill) and one
-//                   BN-row x 32-channel W tile, both with the 128-byte swizzle, into a
-//                   STAGES-deep shared-memory ring guarded by full/empty mbarriers.
-//   warp 1 lane 0 : MMA issuer.  Four tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per
-//                   stage from shared-memory descriptors into one of two TMEM
-//                   accumulator stages; tcgen05.commit releases the smem slot and, after
-//                   the last K step, publishes the accumulator.
-//   warp 2        : allocates / frees the 2*BN TMEM columns.
-//   warps 4..7    : epilogue.  tcgen05.ld 32 lanes x 32 columns at a time, fused
-//                   bias + time-embedding row + residual + scale (+ TF32 rounding),
-//                   128-bit stores.  Runs concurrently with the next tile's main loop
-//                   thanks to the second accumulator stage.
+// Kernels (persistent, warp-specialised, 384 threads unless noted):
+//   gemm_tc_kernel<BN, STAGES, false>  one CTA per tile: 128 rows x BN columns, or - `swap` - 128 output
+//                                      channels x 256 pixels (D^T = W X^T) for 128-channel convolutions,
+//                                      1x1 convolutions and the network head;
+//   gemm_tc2_kernel<BN, STAGES>        gemm_tc2.cuh: a CTA pair (cta_group::2) per 256-row tile, each CTA
+//                                      stages its own A rows and half of the W tile;
+//   attn_tc_kernel<F16>                attn_tc.cuh: QK^T, softmax, PV, NIN_3 + residual in one kernel;
+//   gemm_tc_kernel<BN, STAGES, true>   256 threads: the smem-staged TMA-store epilogue kept for A/B runs.
+// Roles: warp 0 lane 0 TMA producer (4-D box of the NHWC tensor shifted by the filter tap, zero halo and
+// tail rows from out-of-bounds fill, SWIZZLE_128B, STAGES-deep ring with full/empty mbarriers); warp 1
+// lane 0 MMA issuer (four MMAs per K step into one of two TMEM accumulator stages, tcgen05.commit frees
+// the slot / publishes the accumulator); warp 2 TMEM allocation; warps 4..11 epilogue, two per TMEM lane
+// quarter: tcgen05.ld, then a block routine compiled per (residual, store format, stats) combination -
+// `row_chunk_t` (row-major outputs: 32x32 blocks transposed through warp-private shared memory so global
+// accesses are coalesced) or `swap_chunk` (lane = channel, already coalesced) - with bias, time-embedding
+// row, residual, scale, fp32 / TF32 / fp16 store and the GroupNorm quad sums fused.
 #include "kernels.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
