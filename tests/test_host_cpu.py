@@ -174,3 +174,25 @@ def test_product_model_has_no_cpu_path():
   cfg.model.resblock_type = 'ddpm'
   with pytest.raises(NotImplementedError):
     seeded_model(cfg)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+  """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the same
+  metric/unit/config keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e block."""
+  import json
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, OMP_NUM_THREADS='1')      # what torchrun exports to every rank
+  out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                        '--cpu-batch', '1'], capture_output=True, text=True, timeout=900, env=env, cwd=root)
+  assert out.returncode == 0, out.stderr[-2000:]
+  line = json.loads(out.stdout.strip().splitlines()[-1])
+  assert line['impl'] == 'reference' and line['unit'] == 'images/s' and line['higher_is_better'] is True
+  assert line['metric'].startswith('PC-sampler images/sec') and line['value'] > 0 and line['n_gpus'] == 1
+  cb = line['cpu_baseline']
+  assert cb['kind'] == 'port' and cb['value'] == line['value'] and cb['cores'] >= 1 and 'PC iterations' in cb['sample']
+  assert line['e2e'] == {'value': line['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+  if (os.cpu_count() or 1) >= 4:
+    assert cb['cores'] > 1        # OMP_NUM_THREADS=1 from the launcher must not reduce the arm to one core
