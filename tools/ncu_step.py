@@ -18,7 +18,7 @@ from score_sde_pytorch_b200.models.ncsnpp import NCSNpp              # noqa: E40
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=1024)
-ap.add_argument('--precision', default='tf32')
+ap.add_argument('--precision', default='f16')
 args = ap.parse_args()
 dev = torch.device('cuda:0')
 cfg = headline_config()
