@@ -164,6 +164,7 @@ class NCSNpp(nn.Module):
     self.all_modules = nn.ModuleList(mods)
     self._engine = None        # (handle, blob, workspace, batch, weights_version)
     self._weights_version = 0
+    self._link_parameters()    # lets models.ema.ExponentialMovingAverage tell this module to repack
 
   # ---- native engine plumbing ------------------------------------------------
   def _native_config(self):
@@ -212,8 +213,16 @@ class NCSNpp(nn.Module):
     return out
 
   def invalidate_weights(self):
-    """Call after mutating parameters in place (e.g. ``ema.copy_to``) so the engine repacks."""
+    """Call after mutating parameters in place so the engine repacks its device copy.  This package's
+    ``models.ema.ExponentialMovingAverage.copy_to`` / ``restore`` do it automatically (through the owner link
+    set below); with any other in-place writer (the reference's EMA class, manual ``p.data.copy_``) call it."""
     self._weights_version += 1
+
+  def _link_parameters(self):
+    import weakref
+    ref = weakref.ref(self)
+    for p in self.parameters():
+      p._b200_owner = ref
 
   def load_state_dict(self, state_dict, strict=True, **kw):
     sd = {(k[7:] if k.startswith('module.') else k): v for k, v in state_dict.items()}

@@ -196,3 +196,71 @@ def test_bench_reference_arm_prints_the_contract_line():
   assert line['e2e'] == {'value': line['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
   if (os.cpu_count() or 1) >= 4:
     assert cb['cores'] > 1        # OMP_NUM_THREADS=1 from the launcher must not reduce the arm to one core
+
+
+def test_ema_matches_reference_update_rule_and_notifies_the_engine_module(tmp_path):
+  """models/ema.py:34-51 semantics (decay ramp min(decay, (1+n)/(10+n)), positional shadow list over the trainable
+  parameters), checkpoint round trip in the reference's file format (utils.py:7-30), and the engine hook: copy_to /
+  restore bump the owning NCSNpp's weight version so the packed device copy is rebuilt."""
+  from score_sde_pytorch_b200 import utils as butils
+  from score_sde_pytorch_b200.models.ema import ExponentialMovingAverage
+  from score_sde_pytorch_b200.models.ncsnpp import NCSNpp
+  cfg = golden_config('tiny')
+  torch.manual_seed(0)
+  model = NCSNpp(cfg)
+  params = list(model.parameters())
+  trainable = [p for p in params if p.requires_grad]
+  assert len(trainable) == len(params) - 1          # the Fourier projection W is frozen, as in the reference
+  ema = ExponentialMovingAverage(params, decay=0.999)
+  assert len(ema.shadow_params) == len(trainable)
+  start = [p.detach().clone() for p in trainable]
+  with torch.no_grad():
+    for p in trainable:
+      p.add_(1.0)
+  ema.update(params)                                # n = 1: decay = min(0.999, 2/11)
+  d = 2.0 / 11.0
+  for s, p0 in zip(ema.shadow_params, start):
+    assert torch.allclose(s, p0 + (1.0 - d), atol=1e-6)
+  ema.update(params)                                # n = 2: decay = 3/12
+  d2 = 3.0 / 12.0
+  for s, p0 in zip(ema.shadow_params, start):
+    assert torch.allclose(s, p0 + 1.0 - d2 * d, atol=1e-6)
+  with pytest.raises(ValueError):
+    ExponentialMovingAverage(params, decay=1.5)
+  # store / copy_to / restore, each notifying the engine-backed module
+  v0 = model._weights_version
+  ema.store(params)
+  ema.copy_to(params)
+  assert model._weights_version == v0 + 1
+  assert all(torch.equal(p, s) for p, s in zip(trainable, ema.shadow_params))
+  ema.restore(params)
+  assert model._weights_version == v0 + 2
+  assert all(torch.allclose(p, p0 + 1.0) for p, p0 in zip(trainable, start))
+  # checkpoint round trip in the reference's format
+  path = str(tmp_path / 'ckpt' / 'checkpoint_1.pth')
+  state = dict(optimizer=torch.optim.Adam(model.parameters(), lr=1e-3), model=model, ema=ema, step=7)
+  assert butils.restore_checkpoint(path, state, 'cpu') is state          # missing file: unchanged state, directory created
+  butils.save_checkpoint(path, state)
+  torch.manual_seed(1)
+  model2 = NCSNpp(cfg)
+  ema2 = ExponentialMovingAverage(model2.parameters(), decay=0.5)
+  state2 = butils.restore_checkpoint(path, dict(optimizer=None, model=model2, ema=ema2, step=0), 'cpu')
+  assert state2['step'] == 7 and ema2.decay == 0.999 and ema2.num_updates == 2
+  assert all(torch.equal(a, b) for a, b in zip(model2.state_dict().values(), model.state_dict().values()))
+  assert all(torch.equal(a, b) for a, b in zip(ema2.shadow_params, ema.shadow_params))
+  # a DataParallel-era checkpoint (keys prefixed with 'module.') loads too
+  torch.save({'optimizer': {}, 'model': {'module.' + k: v for k, v in model.state_dict().items()}, 'ema': ema.state_dict(), 'step': 3}, path)
+  state3 = butils.restore_checkpoint(path, dict(optimizer=None, model=model2, ema=ema2, step=0), 'cpu')
+  assert state3['step'] == 3
+
+
+@pytest.mark.parametrize('name', ['tiny', 'tiny_noattn', 'cifar10_ve'])
+def test_parameter_list_matches_the_reference_order(name):
+  """EMA shadow parameters in reference checkpoints are positional (models/ema.py:27-28): same names, shapes and
+  requires_grad flags in the same `parameters()` order as the reference's NCSNpp (tools/make_param_order.py)."""
+  import json
+  import os
+  ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'param_order.json')))[name]
+  model = seeded_model(golden_config(name))
+  mine = [[n, list(p.shape), bool(p.requires_grad)] for n, p in model.named_parameters()]
+  assert mine == ref
