@@ -264,3 +264,23 @@ def test_parameter_list_matches_the_reference_order(name):
   model = seeded_model(golden_config(name))
   mine = [[n, list(p.shape), bool(p.requires_grad)] for n, p in model.named_parameters()]
   assert mine == ref
+
+
+def test_profile_tooling_reads_the_committed_artifacts():
+  """The roofline block of bench.py takes `traffic` from profiles/traffic_f16.json (written by
+  tools/summarize_traffic.py from an ncu metrics pass); the launch-list summariser must keep parsing the committed CSV."""
+  import glob
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  sys.path.insert(0, root)
+  import bench
+  t = bench.load_traffic('f16')
+  assert isinstance(t, int) and t > 10_000_000            # DRAM bytes per contraction launch
+  assert bench.load_traffic('no-such-precision') is None
+  csvs = sorted(glob.glob(os.path.join(root, 'profiles', '*launches_pc_step*_f16.csv')))
+  assert csvs, 'no committed launch list'
+  out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'summarize_launches.py'), csvs[-1]],
+                       capture_output=True, text=True, timeout=120)
+  assert out.returncode == 0 and 'gemm_tc' in out.stdout and 'gn_apply' in out.stdout
