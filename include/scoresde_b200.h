@@ -113,6 +113,11 @@ typedef struct {
   int keep_activations;         /* debug: never recycle activation buffers so b200_ncsnpp_tap works */
   int lanes;                    /* 0/1: one plan over the whole batch (default); 2: two half-batch plans on two
                                  * streams (batches >= 128).  Measured: no gain on a power-capped B200, see DESIGN.md */
+  int cuda_core_head;           /* 1: the output convolution (ncsnpp.py:374-380) runs on CUDA cores with an fp32 input in
+                                 * every precision mode (costs ~1.4 % of a step, buys back ~1e-4 of rel-L2); 0: tensor cores */
+  int separate_groupnorm;       /* 1: every GroupNorm+SiLU as its own streaming pass (the round-1 plan, kept for A/B and
+                                 * as the checked alternative); 0: fused into the producing contraction's epilogue
+                                 * wherever one image's pixels are produced by one kernel launch */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

@@ -29,7 +29,8 @@ class NcsnppConfig(ctypes.Structure):
               ('centered', c_int), ('scale_by_sigma', c_int), ('skip_rescale', c_int), ('conditional', c_int),
               ('progressive_input', c_int),
               ('fir_taps', c_int), ('fir_kernel', c_float * 8),
-              ('precision', c_int), ('keep_activations', c_int), ('lanes', c_int)]
+              ('precision', c_int), ('keep_activations', c_int), ('lanes', c_int),
+              ('cuda_core_head', c_int), ('separate_groupnorm', c_int)]
 
 
 class PcConfig(ctypes.Structure):

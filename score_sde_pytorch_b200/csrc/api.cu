@@ -103,7 +103,7 @@ int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int bat
     d.f16 = impl == 2;
     d.a1 = x1; d.C1 = c1; d.a2 = x2; d.C2 = c2; d.conv = 1; d.H = h; d.W = w; d.nimg = batch; d.taps = ksize * ksize;
     d.w = w_packed; d.N_total = c_out; d.K_total = c1 + c2; d.w_rows = (long long)ksize * ksize * c_out; d.nbatch = 1;
-    d.epi_mode = -1; d.epi = ep;
+    d.epi = ep;
     TcGemmPlan* pl = nullptr;
     if (int r = tc_gemm_plan_create(d, &pl)) return r;
     const int r = tc_gemm_launch(pl, st);
@@ -128,7 +128,7 @@ int b200_conv_skip_nhwc_f32(const float* x, int c, const float* s1, int cs1, con
   d.a1 = x; d.C1 = c; d.conv = 1; d.H = h; d.W = w; d.nimg = batch; d.taps = 9;
   d.w = w_packed; d.N_total = c_out; d.K_total = c; d.w_rows = 9LL * c_out; d.nbatch = 1;
   d.a3 = s1; d.C3 = cs1; d.a4 = s2; d.C4 = s2 ? cs2 : 0; d.w2 = w_skip;
-  d.epi_mode = -1; d.epi = ep;
+  d.epi = ep;
   TcGemmPlan* pl = nullptr;
   if (int r = tc_gemm_plan_create(d, &pl)) return r;
   const int r = tc_gemm_launch(pl, static_cast<cudaStream_t>(stream));
@@ -164,7 +164,7 @@ int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, const floa
     d.a_rows = a_batch_rows ? (long long)a_batch_rows * (nbatch - 1) + m : m;
     d.w = w; d.N_total = n; d.K_total = k; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
     d.w_rows = w_batch_rows ? (long long)w_batch_rows * (nbatch - 1) + n : n;
-    d.nbatch = nbatch; d.M_per_batch = m; d.epi_mode = -1; d.epi = ep;
+    d.nbatch = nbatch; d.M_per_batch = m; d.epi = ep;
     TcGemmPlan* pl = nullptr;
     if (int r = tc_gemm_plan_create(d, &pl)) return r;
     const int r = tc_gemm_launch(pl, st);

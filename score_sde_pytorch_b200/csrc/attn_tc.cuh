@@ -52,9 +52,7 @@ struct AttnParams {
   float logit_scale;        // C^-0.5 * log2(e)
   float out_scale;          // 1/sqrt(2) with skip_rescale, else 1
   int nimg;
-  long long* dbg;           // optional phase time stamps (B200_ATTN_DBG=1): [tile < 16][7] clock64 values of CTA 0, warp 4
 };
-#define ATTN_STAMP(k) do { if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tile / gridDim.x < 16) p.dbg[(tile / gridDim.x) * 7 + (k)] = clock64(); } while (0)
 
 // address of 16-byte chunk `c16` (0..7) of row r in K-block kb of the swizzled operand buffer
 __device__ __forceinline__ uint8_t* pbuf_chunk(uint8_t* pbuf, int kb, int r, int c16) {
@@ -178,12 +176,10 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tpar ^= 1) {
       const int b = (int)(tile >> 1), qh = (int)(tile & 1);
       const long long gm = (long long)b * AT_T + qh * BM + r;
-      ATTN_STAMP(0);
 #pragma unroll
       for (int i = 0; i < 128; i += 32) prefetch_l2(p.x + gm * AT_C + half * 128 + i);   // residual row -> L2 for `final`
       // ---- softmax over this row's 256 logits (this thread: columns half*128 .. +128) ----
       mbar_wait(s_full, tpar);
-      ATTN_STAMP(1);
       tc_fence_after();
       float mx = -INFINITY;
 #pragma unroll 1
@@ -220,10 +216,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      ATTN_STAMP(2);
       // ---- O' = O / rowsum + b_v -> operand buffer (K = channel) ----
       mbar_wait(o_full, tpar);
-      ATTN_STAMP(3);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
@@ -246,14 +240,12 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_ready);
-      ATTN_STAMP(4);
       // ---- final: (Y + b_3 + x) * out_scale, quad sums, store ----
       // Through the same coalescing block routine as the convolution epilogues.  Its 4 KB transposition scratch is
       // this warp's slice of the operand buffer: O' is dead once Y is complete, and the slice (rows of this warp's
       // lane quarter in K block `half`) is next written by the quarter's half-0 warp only after the pair barrier of
       // the next tile's softmax, i.e. after this warp has left `final`.
       mbar_wait(y_full, tpar);
-      ATTN_STAMP(5);
       tc_fence_after();
       {
         Epilogue ep;
@@ -270,7 +262,6 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         }
       }
       tc_fence_before();   // orders these TMEM reads before the p_ready arrival that lets the next tile's E V overwrite O/Y
-      ATTN_STAMP(6);
     }
   }
   tc_fence_before();

@@ -297,13 +297,12 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   B200_REQUIRE(!x1_f16 || (threads % Q == 0 && !raw), "gn_apply: fp16 input needs the quad-per-thread path (C=%d) and no raw copy", C);
   // aim for ~16 float4 per thread (four 4-deep batches), at least one block per image
   const long long per_img_units = (long long)HW * Q;
-  static const int work = [] { const char* v = getenv("B200_GN_WORK"); return v ? std::max(4, atoi(v)) : 16; }();   // tuning knob
+  const int work = 16;
   int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / ((long long)threads * work), 64));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
   B200_REQUIRE(!x1_f16 || C2 == 0, "gn_apply: fp16 input is single-source");
-  static const bool stream_form = [] { const char* v = getenv("B200_GN_STREAM"); return !(v && v[0] == '0'); }();
-  if (stream_form && threads % Q == 0 && Q <= 128 && (!x1_f16 || round_out == 2)) {
+  if (threads % Q == 0 && Q <= 128 && (!x1_f16 || round_out == 2)) {
     const double inv_n = 1.0 / ((double)HW * (C / G));
     if (x1_f16) gn_stream_launch<true, 2>(grid, threads, st, act, raw != nullptr, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw);
     else if (round_out == 2) gn_stream_launch<false, 2>(grid, threads, st, act, raw != nullptr, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw);

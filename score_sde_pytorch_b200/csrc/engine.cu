@@ -14,7 +14,6 @@
 
 namespace b200 {
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld);
-int tc_gemm_default_epi_mode();
 }
 using namespace b200;
 
@@ -309,8 +308,9 @@ int build_graph(b200_ncsnpp* e) {
     // Head on tensor cores: the ch (3) output channels become rows 0..ch-1 of a zero-padded 128-row weight tile
     // ([9][128][in_ch]; bias padded likewise), run as a swapped-operand convolution whose epilogue stores only those
     // rows, as NCHW, divided by sigma.  2.3x faster than the CUDA-core head despite the 125 idle rows.
-    static const bool tc_head = [] { const char* v = getenv("B200_TC_HEAD"); return !(v && v[0] == '0'); }();
-    m.tc0 = tc_head && tcmode && ch <= 32 && tc_ok(e, in_ch, 0, 128, c.image_size, c.image_size, 9) && (c.image_size * c.image_size) % 256 == 0 &&
+    // cfg.cuda_core_head = 1 keeps the head on CUDA cores with an fp32 input (it is the one convolution with no later
+    // layer to average its operand rounding: +1e-4 of the parity budget on tensor cores).
+    m.tc0 = !c.cuda_core_head && tcmode && ch <= 32 && tc_ok(e, in_ch, 0, 128, c.image_size, c.image_size, 9) && (c.image_size * c.image_size) % 256 == 0 &&
             c.image_size <= 128;
     m.w = m.tc0 ? add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV_PAD128, 9, ch, in_ch, om, -1, 9LL * 128 * in_ch)
                 : add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0);
@@ -341,8 +341,7 @@ struct Builder {
     char buf[160]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap); next_name = buf;
   }
   Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_, int lane_ = 0) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0), lane(lane_) {
-    const char* v = getenv("B200_FUSED_GN_STATS");
-    fused_stats = (e_->cfg.precision != 1) && !(v && v[0] == '0');
+    fused_stats = e_->cfg.precision != 1;
     om = e_->cfg.precision == 2 ? 2 : 1;
     if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
   }
@@ -426,7 +425,7 @@ struct Builder {
       d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = out.H; d.W = out.W; d.nimg = B; d.taps = taps;
       d.stride = stride; d.valid_pad = stride == 2 ? 1 : 0; d.Hin = Hin ? Hin : out.H; d.Win = Hin ? Hin : out.W;
       d.w = e->W(pw); d.N_total = Cout; d.K_total = a1.C + a2.C; d.w_rows = (long long)taps * Cout; d.nbatch = 1;
-      d.epi_mode = -1; d.f16 = om == 2;
+      d.f16 = om == 2;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
       if (x3.p) {   // fused skip projection: its bias rides in the (image-independent) row-vector slot
         if (dense_row >= 0) { set_error("ncsnpp: fused skip projection on a conv with a time-embedding bias"); rc = 2; return; }
@@ -480,7 +479,7 @@ struct Builder {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.a1 = A; d.C1 = K; d.conv = 0; d.taps = 1; d.a_rows = a_rows; d.a_ld = lda; d.a_batch_rows = a_batch_rows;
       d.w = Wm; d.N_total = N; d.K_total = K; d.w_rows = w_rows; d.w_ld = ldw; d.w_batch_rows = w_batch_rows;
-      d.nbatch = nbatch; d.M_per_batch = M; d.epi_mode = -1; d.qstats = qstats; d.no_pair = no_pair ? 1 : 0; d.epi = ep;
+      d.nbatch = nbatch; d.M_per_batch = M; d.qstats = qstats; d.no_pair = no_pair ? 1 : 0; d.epi = ep;
       d.f16 = om == 2;
       if (dry) return;
       TcGemmPlan* pl = nullptr;
@@ -513,10 +512,7 @@ struct Builder {
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
     Tensor a0 = talloc(Cin, H, H);
     Tensor raw; // TF32-rounded copy of the (concatenated) block input for the tensor-core skip conv
-    // B200_SKIP_TRUNC=1 (experiment): feed the 1x1 skip conv the un-rounded block input directly (the tensor
-    // core truncates it to TF32) instead of a round-to-nearest copy -> one fewer activation write per block
-    static const bool skip_trunc = [] { const char* v = getenv("B200_SKIP_TRUNC"); return v && v[0] == '1'; }();
-    if (m.has_conv2 && m.tc2 && !resample && (!skip_trunc || om == 2)) raw = talloc(Cin, H, H);
+    if (m.has_conv2 && m.tc2 && !resample) raw = talloc(Cin, H, H);
     gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? om : 0, a0, raw.p);
     Tensor xr;
     if (resample) {
@@ -536,9 +532,8 @@ struct Builder {
     }
     Tensor h1 = talloc(m.cout, Ho, Ho);
     // fp16 operand mode: the mid-block tensor (Conv_0 output, only ever read by GroupNorm_1) is stored as fp16;
-    // its GroupNorm sums are accumulated from the fp32 accumulators in the epilogue.  B200_H1_F16=0 keeps it fp32.
-    static const bool h1_f16_env = [] { const char* v = getenv("B200_H1_F16"); return !(v && v[0] == '0'); }();
-    const bool h1_f16 = h1_f16_env && om == 2 && m.tc0 && m.tc1 && fused_stats && (Ho * Ho) % 32 == 0 && (m.cout % 128 == 0);
+    // its GroupNorm sums are accumulated from the fp32 accumulators in the epilogue.
+    const bool h1_f16 = om == 2 && m.tc0 && m.tc1 && fused_stats && (Ho * Ho) % 32 == 0 && (m.cout % 128 == 0);
     h1.f16 = h1_f16;
     conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, h1_f16 ? 2 : 0, h1, /*want_stats=*/true);
     if (h1_f16 && !h1.qs) { set_error("ncsnpp: fp16 mid-block tensor without fused GroupNorm sums"); rc = 2; return Tensor(); }
@@ -549,11 +544,10 @@ struct Builder {
     Tensor s;
     const float* residual = x1.p;
     // Fused skip projection (default): Conv_2(x) (layerspp.py:270) is accumulated inside the second 3x3 convolution
-    // as extra K steps instead of a separate launch + a residual round trip through HBM.  B200_FUSE_SKIP=0 disables.
-    static const bool fuse_skip = [] { const char* v = getenv("B200_FUSE_SKIP"); return !(v && v[0] == '0'); }();
-    if (m.has_conv2 && fuse_skip && m.tc1 && m.tc2 && (resample || raw.p || skip_trunc)) {
+    // as extra K steps instead of a separate launch + a residual round trip through HBM.
+    if (m.has_conv2 && m.tc1 && m.tc2 && (resample || raw.p)) {
       Tensor out = talloc(m.cout, Ho, Ho);
-      Tensor e1 = resample ? xr : raw.p ? raw : x1, e2 = (resample || raw.p) ? Tensor() : x2;
+      Tensor e1 = resample ? xr : raw, e2 = Tensor();
       conv(true, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, nullptr, inv_s2, 0, out, /*want_stats=*/true, 1, 0, e1, e2, m.c2w, m.c2b);
       tfree(a1); tfree(raw); tfree(xr);
       return out;
@@ -611,12 +605,11 @@ struct Builder {
       gemm(tc, wv, C, C, 0, a.p, C, BT, T, B, C, T, C, nullptr, nullptr, 0, 1.f, tc ? om : 0, vT, T, nullptr, 1 << 30, /*no_pair=*/true);
       tfree(a);
       // Fused core (default): logits, softmax, P.V, NIN_3, residual, rescale and quad sums in one kernel; the
-      // [T,T] logits/probabilities and the attention output stay on chip.  B200_FUSED_ATTN=0 -> separate launches.
-      static const bool fuse_attn = [] { const char* v = getenv("B200_FUSED_ATTN"); return !(v && v[0] == '0'); }();
-      if (om == 2 && !(tc && m.tc2 && fuse_attn && tc_attn_supported(T, C))) {
-        set_error("ncsnpp: fp16 operand mode needs the fused attention core (T=%d C=%d, B200_FUSED_ATTN)", T, C); rc = 2; return Tensor();
+      // [T,T] logits/probabilities and the attention output stay on chip; other token counts (tf32 mode) use separate launches.
+      if (om == 2 && !(tc && m.tc2 && tc_attn_supported(T, C))) {
+        set_error("ncsnpp: fp16 operand mode needs the fused attention core (T=%d C=%d)", T, C); rc = 2; return Tensor();
       }
-      if (tc && m.tc2 && fuse_attn && tc_attn_supported(T, C)) {
+      if (tc && m.tc2 && tc_attn_supported(T, C)) {
         Tensor out = talloc(C, x.H, x.W);
         if (fused_stats) out.qs = qalloc(C);
         if (!dry) {
@@ -812,7 +805,7 @@ struct Builder {
       if (mo.tc0) {
         TcGemmDesc d; memset(&d, 0, sizeof(d));
         d.a1 = a.p; d.C1 = a.C; d.conv = 1; d.H = R; d.W = R; d.nimg = B; d.taps = 9; d.stride = 1;
-        d.w = wo; d.N_total = 128; d.K_total = a.C; d.w_rows = 9LL * 128; d.nbatch = 1; d.epi_mode = 0; d.f16 = om == 2;
+        d.w = wo; d.N_total = 128; d.K_total = a.C; d.w_rows = 9LL * 128; d.nbatch = 1; d.f16 = om == 2;
         d.epi.bias = bo; d.epi.scale = 1.f; d.epi.rows_per_img = R * R; d.epi.out_nchw = 1; d.epi.n_valid = ch; d.epi.ld_out = 128;
         d.epi.out = reinterpret_cast<float*>(uintptr_t(16));   // patched per call (tc_gemm_set_head)
         if (!dry) {
@@ -926,12 +919,11 @@ int b200_ncsnpp_load_param(b200_ncsnpp_t* h, int index, const float* src, void* 
 }
 
 namespace {
-// Lane split of a batch (cfg.lanes == 2, or B200_LANES=2 in the environment): two halves when the batch is large
+// Lane split of a batch (cfg.lanes == 2): two halves when the batch is large
 // enough for every launch of a half to fill the GPU; one lane otherwise, by default, and always with
 // keep_activations (its taps address whole-batch tensors).
 int lane0_images(const b200_ncsnpp* h, int batch) {
-  static const int lanes_env = [] { const char* v = getenv("B200_LANES"); return v ? atoi(v) : 0; }();
-  const int lanes = lanes_env ? lanes_env : h->cfg.lanes;
+  const int lanes = h->cfg.lanes;
   if (lanes < 2 || h->cfg.keep_activations || batch < 128) return batch;
   return (batch + 1) / 2;
 }
@@ -1163,6 +1155,11 @@ int pc_iteration(b200_pc* pc, float* x, float* x_mean, const float* noise_c, con
     if (int r = launch_predictor_apply(x, x_mean, pc->net_out, noise_p, pc->map, pc->d_offset, pc->d_step, cps, call,
                                        sc, 1, st)) return r;
   }
+  if (!c.predictor && x_mean) {
+    // NonePredictor.update_fn returns (x, x) (sampling.py:241-250): the "mean" handed to the denoise step of
+    // pc_sampler (:409) is the noisy state after the corrector, not the last Langevin mean
+    B200_CHECK_CUDA(cudaMemcpyAsync(x_mean, x, (size_t)pc->numel * 4, cudaMemcpyDeviceToDevice, st));
+  }
   return launch_step_increment(pc->d_step, st);
 }
 
@@ -1187,7 +1184,7 @@ int b200_pc_create(b200_ncsnpp_t* model, const b200_pc_config* cfg, int batch, b
   cp(pc->h_pa, cfg->pa, 1.f); cp(pc->h_pb, cfg->pb, 0.f); cp(pc->h_pc, cfg->pc, 0.f);
   pc->cfg.label = pc->cfg.score_scale = pc->cfg.alpha = pc->cfg.pa = pc->cfg.pb = pc->cfg.pc = nullptr;
   const long long cps = (cfg->corrector ? cfg->n_corrector_steps : 0) + (cfg->predictor ? 1 : 0);
-  pc->launches_per_step = cps * model->launches + (cfg->corrector ? cfg->n_corrector_steps * 3 : 0) + (cfg->predictor ? 1 : 0) + 2;
+  pc->launches_per_step = cps * model->launches + (cfg->corrector ? cfg->n_corrector_steps * 3 : 0) + 1 /* predictor apply, or the x -> x_mean copy */ + 2;
   *out = pc;
   return 0;
 }

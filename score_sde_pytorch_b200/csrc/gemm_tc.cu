@@ -40,7 +40,7 @@ constexpr int BKE = 32;          // fp32 elements per K step == one 128-byte swi
 constexpr int A_STAGE_BYTES = BM * BKE * 4;   // 16 KiB
 
 struct TcParams {
-  CUtensorMap tmA1, tmA2, tmW, tmOut, tmRes;
+  CUtensorMap tmA1, tmA2, tmW;
   CUtensorMap tmA3, tmA4, tmW2;            // optional extra 1x1 K phase (fused skip projection): out += [A3|A4] W2^T
   int conv, H, W, taps, pad, S, stride;   // H, W: OUTPUT spatial size; S = filter width (3 or 1)
   int kchunks1, kchunks2, C1;
@@ -50,7 +50,6 @@ struct TcParams {
   int a_batch_rows, w_batch_rows;
   int f16;                                 // 1: A and W are fp16 (tcgen05 kind::f16, 64-channel K steps); 0: TF32-grid fp32 (32-channel K steps)
   int bke;                                 // channels per K step: one 128-byte swizzle row = 32 fp32 or 64 fp16
-  int epi_mode;                            // 0: direct register->global stores, 1: smem-staged TMA store (+TMA residual)
   int swap;                                // 1: operands swapped (D^T = W X^T): 128 output channels x 256 pixels per tile
   double* qstats;                          // optional [img][N_total/4][2] GroupNorm quad sums (sum, sum of squares)
   long long total_tiles;
@@ -103,14 +102,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, ui
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Pull one 128-byte line towards L2 without occupying a register: the epilogues use it for their residual rows
@@ -194,15 +185,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16() {
   return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN, int STAGES, bool STAGED>
+template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BKE * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_TILE_BYTES = BM * 32 * 4;         // one 128-row x 32-column fp32 chunk (128-B swizzled rows)
-  static constexpr int OUT_OFFSET = STAGES * STAGE_BYTES;   // 3 output staging chunks for the TMA store
-  static constexpr int RES_OFFSET = OUT_OFFSET + (STAGED ? 3 : 0) * EPI_TILE_BYTES;   // 2 residual chunks landed by TMA
-  static constexpr int TRN_OFFSET = RES_OFFSET + (STAGED ? 2 : 0) * EPI_TILE_BYTES;   // direct epilogue: 8 warps x 4 KB transposition scratch
-  static constexpr int BAR_OFFSET = TRN_OFFSET + (STAGED ? 0 : 8 * 4096);
+  static constexpr int TRN_OFFSET = STAGES * STAGE_BYTES;   // 8 epilogue warps x 4 KB transposition scratch
+  static constexpr int BAR_OFFSET = TRN_OFFSET + 8 * 4096;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-B alignment
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
@@ -415,25 +403,23 @@ __device__ __forceinline__ void row_chunk_t_dispatch(const uint32_t (&v)[32], ui
 // ---------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------
-template <int BN, int STAGES, bool STAGED>
-__global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-  using L = SmemLayout<BN, STAGES, STAGED>;
+template <int BN, int STAGES>
+__global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;                     // [4 epilogue warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    // one arrival per epilogue warp: 4 (staged, 256 threads) or 8 (direct, 384 threads: two warps per TMEM lane quarter)
+    // one arrival per epilogue warp (384 threads: two warps per TMEM lane quarter)
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], (blockDim.x >> 5) - 4); }
-    for (int a = 0; a < 8; ++a) mbar_init(&res_full[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -527,7 +513,7 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
       umma_commit(&tmem_full[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4 && !STAGED) {
+  } else if (warp >= 4) {
     // ======================= epilogue (direct stores) =======================
     // Eight warps: warp w may touch TMEM lanes 32*(w%4).., so warps 4..7 and 8..11 pair up on each lane quarter
     // and split the tile's columns — twice the loads/stores in flight for the output-bound (small-K) launches.
@@ -639,8 +625,7 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
       for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32, v);
-        if constexpr (!STAGED)
-          row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid,
+        row_chunk_t_dispatch(v, smem + L::TRN_OFFSET + (warp - 4) * 4096, e, p.qstats, p.N_total, gm0, rows_valid,
                                nt * BN + j * 32, img0, lane);
       }
       tc_fence_before();
@@ -648,148 +633,6 @@ __global__ void __maxnreg__(STAGED ? 232 : 160) gemm_tc_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4 && STAGED) {
-    // ======================= epilogue (smem-staged, warp-private) =======================================
-    // Each of the four epilogue warps owns 32 TMEM lanes and works alone (no CTA-wide barrier): per
-    // 32-column chunk it pulls its 32x32 accumulator block TMEM -> registers (the next block's tcgen05.ld is
-    // already in flight), adds bias / time-embedding / residual (the residual block was landed in the warp's
-    // smem by TMA two chunks earlier), scales, optionally rounds to TF32, writes a 128-B-swizzled 4 KB staging
-    // block and hands it to one TMA bulk store (three staging blocks deep).  GroupNorm quad sums of the stored
-    // values are reduced across the warp with a halving butterfly (16 shuffles instead of 80) and accumulated in
-    // fp64 by 16 lanes in parallel.  Two block orientations:
-    //   normal : TMEM lane = output row (pixel), columns = channels; a lane writes 8 float4 of its row;
-    //   swap   : TMEM lane = output channel, columns = pixels (D^T = W X^T for 128-channel layers); a lane
-    //            scatters its channel's 32 pixels one word per staging row (a warp fills one 128-B row per pixel).
-    const int q = warp - 4;
-    const Epilogue& e = p.epi;
-    const bool swap = p.swap != 0;
-    const int NCH = swap ? 8 : BN / 32;                          // chunks per tile
-    constexpr int BLK = 32 * 32;                                 // floats per staging block
-    float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET) + q * 3 * BLK;   // [3][32 rows][32]
-    float* res_stage = reinterpret_cast<float*>(smem + L::RES_OFFSET) + q * 2 * BLK;   // [2][32 rows][32]
-    uint64_t* my_res_full = res_full + q * 2;
-    const bool has_res = e.residual != nullptr;
-    const long long my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long total_chunks = my_tiles * NCH;
-    // origin (first output row, first output column) of this warp's block of chunk g
-    auto block_origin = [&](long long g, int& row0, int& col0) {
-      const long long tile = blockIdx.x + (g / NCH) * gridDim.x;
-      const int j = (int)(g % NCH);
-      if (swap) {
-        col0 = (int)(tile % p.tiles_n) * 128 + q * 32;
-        row0 = (int)(tile / p.tiles_n) * 256 + j * 32;
-      } else {
-        const long long mg = tile / p.tiles_n;
-        col0 = (int)(tile % p.tiles_n) * BN + j * 32;
-        row0 = (int)(mg / p.tiles_m_per_batch) * p.M_per_batch + (int)(mg % p.tiles_m_per_batch) * BM + q * 32;
-      }
-    };
-    auto load_res = [&](long long g) {                           // lane 0 only
-      int row0, col0; block_origin(g, row0, col0);
-      mbar_expect_tx(&my_res_full[g & 1], BLK * 4);
-      tma_load_2d(&p.tmRes, res_stage + (g & 1) * BLK, &my_res_full[g & 1], col0, row0);
-    };
-    auto issue_tmem_ld = [&](long long g, uint32_t (&v)[32]) {   // whole warp
-      const long long k = g / NCH;                               // local tile counter -> accumulator stage / phase
-      const int j = (int)(g % NCH);
-      const uint32_t acc = (uint32_t)(k & 1), ph = (uint32_t)((k >> 1) & 1);
-      if (j == 0) { mbar_wait(&tmem_full[acc], ph); tc_fence_after(); }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + j * 32;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-    };
-    if (lane == 0 && has_res) { for (long long g = 0; g < 2 && g < total_chunks; ++g) load_res(g); }
-    float sw_sum = 0.f, sw_sq = 0.f;                             // swap mode: per-channel sums over the tile
-    auto process = [&](long long g, uint32_t (&v)[32]) {
-      const int j = (int)(g % NCH);
-      int row0, col0; block_origin(g, row0, col0);
-      if (lane == 0) bulk_wait_read<1>();                        // store g-2 drained -> staging block g%3 (last used by g-3) is free
-      __syncwarp();
-      if (has_res) mbar_wait(&my_res_full[g & 1], (uint32_t)((g >> 1) & 1));
-      const float* rs = res_stage + (g & 1) * BLK;
-      float* os = out_stage + (g % 3) * BLK;
-      if (!swap) {
-        const int r = lane, sw = r & 7;
-        const int m = row0 + r - (int)((blockIdx.x + (g / NCH) * gridDim.x) / p.tiles_n / p.tiles_m_per_batch) * p.M_per_batch;
-        const bool valid = m < p.M_per_batch;
-        const long long gm = (long long)row0 + r;
-        const int img = valid ? (int)(gm / e.rows_per_img) : 0;
-          const float* rv = e.rowvec ? e.rowvec + img * e.rowvec_ld + col0 : nullptr;
-        float st[16];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 o = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
-                                 __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
-          if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-          if (rv) { const float4 t = __ldg(reinterpret_cast<const float4*>(rv + 4 * c)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-          if (has_res) { const float4 t = *reinterpret_cast<const float4*>(rs + r * 32 + ((c ^ sw) << 2)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-          o.x *= e.scale; o.y *= e.scale; o.z *= e.scale; o.w *= e.scale;
-          if (e.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-          *reinterpret_cast<float4*>(os + r * 32 + ((c ^ sw) << 2)) = o;
-          st[c] = valid ? (o.x + o.y) + (o.z + o.w) : 0.f;
-          st[8 + c] = valid ? (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w) : 0.f;
-        }
-        if (p.qstats) quad_stats_commit(p, e, st, img, valid, col0, lane);
-      } else {
-        // swap: lane = channel col0 + lane, columns = 32 pixels row0..row0+31 (one image per tile)
-        const int co = col0 + lane, ch16 = lane >> 2, w4 = lane & 3;
-        const int img = row0 / e.rows_per_img;
-        const float bias_v = (e.bias ? __ldg(e.bias + co) : 0.f) + (e.rowvec ? __ldg(e.rowvec + img * e.rowvec_ld + co) : 0.f);
-        if (j == 0) { sw_sum = 0.f; sw_sq = 0.f; }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int off = i * 32 + ((ch16 ^ (i & 7)) << 2) + w4;
-          float o = __uint_as_float(v[i]) + bias_v;
-          if (has_res) o += rs[off];
-          o *= e.scale;
-          if (e.round_tf32) o = round_tf32(o);
-          os[off] = o;
-          sw_sum += o; sw_sq += o * o;
-        }
-        if (p.qstats && j == NCH - 1) {
-          sw_sum += __shfl_xor_sync(0xffffffffu, sw_sum, 1); sw_sq += __shfl_xor_sync(0xffffffffu, sw_sq, 1);
-          sw_sum += __shfl_xor_sync(0xffffffffu, sw_sum, 2); sw_sq += __shfl_xor_sync(0xffffffffu, sw_sq, 2);
-          if ((lane & 3) == 0) {
-            double* dst = p.qstats + ((long long)img * (p.N_total >> 2) + (co >> 2)) * 2;
-            atomicAdd(dst, (double)sw_sum); atomicAdd(dst + 1, (double)sw_sq);
-          }
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&p.tmOut, os, col0, row0);
-        bulk_commit();
-        if (has_res && g + 2 < total_chunks) load_res(g + 2);
-      }
-      if (j == NCH - 1) {                                        // this warp has drained its lanes of the accumulator stage
-        const long long k = g / NCH;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[k & 1]);
-      }
-    };
-    // software pipeline over chunks: the tcgen05.ld of chunk g+1 is in flight while chunk g is processed
-    uint32_t va[32], vb[32];
-    if (total_chunks > 0) issue_tmem_ld(0, va);
-    for (long long g = 0; g < total_chunks; g += 2) {
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (g + 1 < total_chunks) issue_tmem_ld(g + 1, vb);
-      process(g, va);
-      if (g + 1 < total_chunks) {
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (g + 2 < total_chunks) issue_tmem_ld(g + 2, va);
-        process(g + 1, vb);
-      }
-    }
-    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -851,7 +694,6 @@ struct TcGemmPlan {
 };
 
 static int tc_configure();
-int tc_gemm_default_epi_mode();
 
 bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
   static const char* w;
@@ -907,43 +749,26 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   const uint64_t es = f16 ? 2 : 4;           // operand element size
   p.bke = bke;
   {
-    // Swapped operands for 128-channel outputs: M=128,N=128 MMAs are shared-memory-bandwidth bound
-    // (8 KB of operand reads per 131k MACs); computing D^T = W X^T makes them M=128 (channels), N=256 (pixels).
-    static const bool allow_swap = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '0'); }();
-    const int req = d.epi_mode < 0 ? tc_gemm_default_epi_mode() : d.epi_mode;   // 0 direct, 1 staged, 2 auto
+    // Form selection (each choice measured against the alternatives in round 1):
+    //  * swapped operands (D^T = W X^T: 128 output channels x 256 pixels per tile) for 128-channel outputs, whose
+    //    M=128,N=128 MMAs are issue-bound, and for 1x1 convolutions (output-bound launches: the swapped form's
+    //    epilogue is perfectly coalesced, 12-20 % faster, profiles/r01_c11_exp.log); the NCHW head exists only in this form;
+    //  * CTA pairs (cta_group::2) for 256-column tiles when the launch has at least one 256-row pair per cluster
+    //    slot (small launches fill the SMs better with single-CTA tiles); `no_pair` in the descriptor opts out;
+    //  * launches too small to give every SM a 256-column tile are cut into 128-column tiles: twice the CTAs at work.
     const long long Mtot = (long long)d.nimg * d.H * d.W;
-    // 1x1 convolutions with 256-multiple channel counts are output-bound launches: the swapped form's coalesced
-    // epilogue measured 12-20 % faster (profiles/r01_c11_exp.log).  B200_TC_SWAP=1 restricts swapping to 128-channel outputs.
-    static const bool swap_1x1 = [] { const char* v = getenv("B200_TC_SWAP"); return !(v && v[0] == '1'); }();
-    // B200_TC_SWAP=3 (experiment): swap every eligible convolution, B200_TC_SWAP=4: those with a residual
-    static const int swap_all = [] { const char* v = getenv("B200_TC_SWAP"); return v ? atoi(v) : 0; }();
-    const bool swap_more = swap_all == 3 || (swap_all == 4 && d.epi.residual != nullptr);
-    // (the NCHW head epilogue exists only in the swapped form, so B200_TC_SWAP=0 does not apply to it)
-    const bool can_swap = (allow_swap || d.epi.out_nchw) && d.conv && p.stride == 1 && (d.N_total % 256 != 0 || (swap_1x1 && d.taps == 1) || swap_more) && (d.H * d.W) % 256 == 0 &&
+    const bool can_swap = d.conv && p.stride == 1 && (d.N_total % 256 != 0 || d.taps == 1) && (d.H * d.W) % 256 == 0 &&
                           d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
-    // auto (default): direct stores with the deepest operand ring (measured best for every launch shape,
-    // profiles/r01_c7_conv_isolated.log); 128-channel convolutions use the swapped-operand form.
-    // B200_TC_EPILOGUE=staged selects the smem-staged TMA-store epilogue for A/B runs.
     p.swap = can_swap ? 1 : 0;
     if (d.epi.out_nchw && !p.swap) { delete pl; B200_REQUIRE(false, "gemm_tc: the NCHW head needs the swapped-operand form"); }
-    p.epi_mode = (req == 1 && d.epi.round_tf32 != 2) ? 1 : 0;   // fp16 outputs: direct stores only
     if (p.swap) pl->bn = 256;
-    p.qstats = d.qstats;      // both epilogues accumulate the GroupNorm quad sums
-    // CTA pairs (cta_group::2) for 256-column tiles: B200_TC_2CTA=1 opts in (0 = off, default until validated per round)
-    // CTA pairs (cta_group::2) for 256-column tiles: on by default when the launch has at least one 256-row pair
-    // per cluster slot (small launches fill the SMs better with single-CTA tiles).  B200_TC_2CTA=0 disables,
-    // =2 also pairs the 128-column tiles (measured: no gain, profiles/r01_c8_conv_isolated.log).
-    static const int two_cta_env = [] { const char* v = getenv("B200_TC_2CTA"); return v ? atoi(v) : 1; }();
+    p.qstats = d.qstats;
     const int tmb = d.conv ? 1 : (d.M_per_batch + BM - 1) / BM;
     const long long m_tiles = d.conv ? (Mtot + BM - 1) / BM : (long long)d.nbatch * tmb;
     const long long n_tiles = d.N_total % 256 == 0 ? d.N_total / 256 : d.N_total / 128;
-    pl->two_cta = two_cta_env && !d.no_pair && req != 1 && !p.swap && (d.N_total % 256 == 0 || two_cta_env >= 2) &&
+    pl->two_cta = !d.no_pair && !p.swap && d.N_total % 256 == 0 &&
                   (d.conv || d.nbatch == 1 || tmb % 2 == 0) && (m_tiles / 2) * n_tiles >= num_sms() / 2;
-    if (pl->two_cta) p.epi_mode = 0;
-    // Launches too small to give every SM a 256-column tile (the 4x4-resolution convolutions of a half-batch
-    // lane: 64 tiles on 148 SMs) are cut into 128-column tiles instead: twice the CTAs at work.
-    static const bool split_small = [] { const char* v = getenv("B200_TC_SPLIT_SMALL"); return !(v && v[0] == '0'); }();
-    if (split_small && !pl->two_cta && !p.swap && pl->bn == 256 && p.epi_mode == 0 && m_tiles * n_tiles <= num_sms() / 2) pl->bn = 128;
+    if (!pl->two_cta && !p.swap && pl->bn == 256 && m_tiles * n_tiles <= num_sms() / 2) pl->bn = 128;
   }
   p.kchunks1 = d.C1 / bke; p.kchunks2 = d.a2 ? d.C2 / bke : 0; p.C1 = d.C1;
   p.N_total = d.N_total; p.tiles_n = p.swap ? d.N_total / 128 : d.N_total / pl->bn;
@@ -1019,22 +844,6 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
       if (rc) { delete pl; return rc; }
     }
   }
-  if (p.epi_mode == 1) {
-    const uint64_t out_rows = (uint64_t)p.nbatch * (uint64_t)p.M_per_batch;
-    uint32_t box[2] = {32, 32};                              // one epilogue warp's 32x32 block
-    {
-      uint64_t dims[2] = {(uint64_t)d.N_total, out_rows};
-      uint64_t str[1] = {(uint64_t)d.epi.ld_out * 4};
-      rc = encode_map(&p.tmOut, d.epi.out, 2, dims, str, box);
-      if (rc) { delete pl; return rc; }
-    }
-    if (d.epi.residual) {
-      uint64_t dims[2] = {(uint64_t)d.N_total, out_rows};
-      uint64_t str[1] = {(uint64_t)d.epi.ld_res * 4};
-      rc = encode_map(&p.tmRes, d.epi.residual, 2, dims, str, box);
-      if (rc) { delete pl; return rc; }
-    } else p.tmRes = p.tmOut;
-  }
   p.total_tiles = (long long)p.nbatch * p.tiles_m_per_batch * p.tiles_n;
   *out = pl;
   return 0;
@@ -1042,28 +851,14 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 const char* tc_gemm_form(const TcGemmPlan* p) {
-  if (p->two_cta) return p->bn == 256 ? "pair256" : "pair128";
-  if (p->prm.swap) return p->prm.epi_mode == 1 ? "swap/staged" : "swap";
-  if (p->prm.epi_mode == 1) return p->bn == 256 ? "single256/staged" : "single128/staged";
+  if (p->two_cta) return "pair256";
+  if (p->prm.swap) return "swap";
   return p->bn == 256 ? "single256" : "single128";
 }
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
 void tc_gemm_set_head(TcGemmPlan* p, float* out_nchw, const float* per_img_div, long long div_stride) {
   p->prm.epi.out = out_nchw; p->prm.epi.per_img_div = per_img_div; p->prm.epi.div_stride = div_stride;
 }
-// B200_TC_EPILOGUE = direct | staged | auto (default).  auto: the smem-staged TMA epilogue where it measured
-// faster (the swapped-operand 128-channel convolutions), direct register->global stores with the deeper
-// operand ring elsewhere.  Returns 0 direct, 1 staged, 2 auto.
-int tc_gemm_default_epi_mode() {
-  static const int mode = [] {
-    const char* v = getenv("B200_TC_EPILOGUE");
-    if (v && !strcmp(v, "direct")) return 0;
-    if (v && !strcmp(v, "staged")) return 1;
-    return 2;
-  }();
-  return mode;
-}
-
 // ---- fused attention core (attn_tc.cuh) ----
 struct TcAttnPlan { AttnParams prm; bool f16; };
 
@@ -1104,34 +899,10 @@ int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out) {
   p.bv = d.bv; p.b3 = d.b3; p.x = d.x; p.out = d.out; p.qstats = d.qstats; p.nimg = d.nimg;
   p.logit_scale = (float)((1.0 / std::sqrt((double)AT_C)) * 1.4426950408889634);
   p.out_scale = d.out_scale;
-  if (const char* v = getenv("B200_ATTN_DBG")) if (v[0] == '1') {   // developer aid: per-phase clock stamps of CTA 0
-    B200_CHECK_CUDA(cudaMalloc(&p.dbg, 16 * 7 * sizeof(long long)));
-    B200_CHECK_CUDA(cudaMemset(p.dbg, 0, 16 * 7 * sizeof(long long)));
-  }
   *out = pl;
   return 0;
 }
-void tc_attn_plan_destroy(TcAttnPlan* p) {
-  if (p && p->prm.dbg) {
-    long long h[16 * 7];
-    if (cudaMemcpy(h, p->prm.dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      static const char* names[6] = {"wait S", "softmax", "wait O", "convert", "wait Y", "final"};
-      double acc[6] = {0, 0, 0, 0, 0, 0}, gap = 0; int n = 0;
-      for (int t = 1; t < 13; ++t) {
-        if (!h[t * 7 + 6]) break;
-        for (int k = 0; k < 6; ++k) acc[k] += (double)(h[t * 7 + k + 1] - h[t * 7 + k]);
-        gap += (double)(h[t * 7] - h[(t - 1) * 7 + 6]); ++n;
-      }
-      if (n) {
-        fprintf(stderr, "attn_tc phases (cycles, mean of %d tiles of CTA 0):", n);
-        for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.0f |", names[k], acc[k] / n);
-        fprintf(stderr, " between tiles %.0f\n", gap / n);
-      }
-    }
-    cudaFree(p->prm.dbg);
-  }
-  delete p;
-}
+void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
   const long long tiles = 2LL * pl->prm.nimg;
   const int grid = (int)std::min<long long>(tiles, num_sms());
@@ -1145,23 +916,20 @@ int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
 static int tc_configure() {
   static bool configured = false;
   if (configured) return 0;
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 3, true>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 4, true>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4, false>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6, false>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, 4>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128, 6>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<256, 6>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<128, 8>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<true>::TOTAL));
   configured = true;
   return 0;
 }
 
-template <int BN, int STAGES, bool STAGED>
+template <int BN, int STAGES>
 static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES, STAGED>;
+  using L = SmemLayout<BN, STAGES>;
   const int grid = (int)std::min<long long>(pl->prm.total_tiles, num_sms());
-  gemm_tc_kernel<BN, STAGES, STAGED><<<grid, STAGED ? 256 : 384, L::TOTAL, st>>>(pl->prm);
+  gemm_tc_kernel<BN, STAGES><<<grid, 384, L::TOTAL, st>>>(pl->prm);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -1172,13 +940,11 @@ int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
     const TcParams& q = pl->prm;
     const long long pairs = (((long long)q.nbatch * q.tiles_m_per_batch + 1) / 2) * q.tiles_n;
     const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
-    if (pl->bn == 256) gemm_tc2_kernel<256, 6><<<grid, 384, Smem2<256, 6>::TOTAL, st>>>(pl->prm);
-    else gemm_tc2_kernel<128, 8><<<grid, 384, Smem2<128, 8>::TOTAL, st>>>(pl->prm);
+    gemm_tc2_kernel<256, 6><<<grid, 384, Smem2<256, 6>::TOTAL, st>>>(pl->prm);
     B200_CHECK_LAUNCH();
     return 0;
   }
-  if (pl->prm.epi_mode == 1) return pl->bn == 256 ? launch_impl<256, 3, true>(pl, st) : launch_impl<128, 4, true>(pl, st);
-  return pl->bn == 256 ? launch_impl<256, 4, false>(pl, st) : launch_impl<128, 6, false>(pl, st);
+  return pl->bn == 256 ? launch_impl<256, 4>(pl, st) : launch_impl<128, 6>(pl, st);
 }
 
 }  // namespace b200

@@ -81,7 +81,6 @@ struct TcGemmDesc {
   // 3x3 convolution): out += [a3 | a4] w2^T, w2 = [N_total][C3 + C4]; same spatial size as the output, stride 1
   const float* a3; int C3; const float* a4; int C4; const float* w2;
   int f16;                  // 1: a1..a4, w, w2 hold fp16 elements (tcgen05 kind::f16, 64-channel K steps); pitches stay in elements
-  int epi_mode;             // 0 direct stores, 1 smem-staged TMA store, -1 = library default
   int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
   Epilogue epi;
@@ -110,7 +109,7 @@ int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out);
 void tc_attn_plan_destroy(TcAttnPlan* p);
 int tc_attn_launch(const TcAttnPlan* p, cudaStream_t st);
 void tc_gemm_set_head(TcGemmPlan* p, float* out_nchw, const float* per_img_div, long long div_stride);   // per-call pointers of the NCHW head
-const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap" (+"/staged")
+const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap"
 
 // ---- pc_update.cu -----------------------------------------------------------
 struct PhiloxMap {          // torch.randn_like's launch geometry for `numel` elements

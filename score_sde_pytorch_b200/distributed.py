@@ -75,6 +75,14 @@ def gather_samples(samples, dst=0):
   if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
     return samples
   world, rank = dist.get_world_size(), dist.get_rank()
+  if samples.shape[0] == 0:
+    # an empty shard may not know the image geometry: learn it from the other ranks
+    geo = torch.tensor(list(samples.shape[1:]) + [0] * (3 - (samples.dim() - 1)), dtype=torch.long, device=samples.device)
+    dist.all_reduce(geo, op=dist.ReduceOp.MAX)
+    samples = samples.new_empty((0,) + tuple(int(v) for v in geo.tolist()))
+  else:
+    geo = torch.tensor(list(samples.shape[1:]), dtype=torch.long, device=samples.device)
+    dist.all_reduce(geo, op=dist.ReduceOp.MAX)
   sizes = [torch.zeros(1, dtype=torch.long, device=samples.device) for _ in range(world)]
   dist.all_gather(sizes, torch.tensor([samples.shape[0]], dtype=torch.long, device=samples.device))
   sizes = [int(s.item()) for s in sizes]
@@ -99,5 +107,13 @@ def sharded_pc_sample(sampling_fn_factory, model, total_batch, seed):
   if torch.cuda.is_available():
     torch.cuda.manual_seed(rank_seed(seed, rank))
   if b == 0:
-    return None, 0
+    # more ranks than images: contribute an empty batch so that gather_samples (a collective) still lines up
+    try:
+      probe = next(model.parameters())
+      device = probe.device
+    except (StopIteration, AttributeError):
+      device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+    shape = getattr(sampling_fn_factory, 'sample_shape', None)
+    tail = tuple(shape[1:]) if shape is not None else (0, 0, 0)
+    return torch.empty((0,) + tail, dtype=torch.float32, device=device), 0
   return sampling_fn_factory(b)(model)

@@ -107,7 +107,8 @@ class NCSNpp(nn.Module):
   with fp32 accumulation and fp32 activations between layers, half the operand traffic and twice the
   MMA rate) or ``'fp32'`` (strict fp32 on CUDA cores; validation mode)."""
 
-  def __init__(self, config, precision=None, keep_activations=False, lanes=1):
+  def __init__(self, config, precision=None, keep_activations=False, lanes=1, cuda_core_head=None,
+               separate_groupnorm=None):
     super().__init__()
     self.config = config
     m = config.model
@@ -122,6 +123,9 @@ class NCSNpp(nn.Module):
     self.precision = (precision or getattr(m, 'precision', 'tf32')).lower()
     self.keep_activations = bool(keep_activations)
     self.lanes = int(getattr(m, 'lanes', lanes))   # 2: evaluate batches >= 128 as two half-batch lanes on two streams
+    # per-engine execution options (fields of b200_ncsnpp_config; nothing is read from the environment)
+    self.cuda_core_head = bool(getattr(m, 'cuda_core_head', False) if cuda_core_head is None else cuda_core_head)
+    self.separate_groupnorm = bool(getattr(m, 'separate_groupnorm', False) if separate_groupnorm is None else separate_groupnorm)
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
     L = len(ch_mult)
     all_res = [config.data.image_size // (2 ** i) for i in range(L)]
@@ -165,6 +169,9 @@ class NCSNpp(nn.Module):
     self._engine = None        # (handle, blob, workspace, batch, weights_version)
     self._weights_version = 0
     self._link_parameters()    # lets models.ema.ExponentialMovingAverage tell this module to repack
+    # fires for direct loads and for loads through a wrapper (DataParallel(model).load_state_dict calls
+    # _load_from_state_dict on the children, not the override below)
+    self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_weights())
 
   # ---- native engine plumbing ------------------------------------------------
   def _native_config(self):
@@ -188,6 +195,8 @@ class NCSNpp(nn.Module):
     c.precision = {'tf32': 0, 'fp32': 1, 'f16': 2}[self.precision]
     c.keep_activations = int(self.keep_activations)
     c.lanes = self.lanes
+    c.cuda_core_head = int(self.cuda_core_head)
+    c.separate_groupnorm = int(self.separate_groupnorm)
     return c
 
   def native_param_table(self):
@@ -226,14 +235,24 @@ class NCSNpp(nn.Module):
 
   def load_state_dict(self, state_dict, strict=True, **kw):
     sd = {(k[7:] if k.startswith('module.') else k): v for k, v in state_dict.items()}
-    out = super().load_state_dict(sd, strict=strict, **kw)
-    self.invalidate_weights()
-    return out
+    return super().load_state_dict(sd, strict=strict, **kw)   # the post hook below invalidates the packed weights
 
   def _release(self):
+    """Destroy the native engine.  Every cached PC plan holds a pointer to it, so they are released first."""
+    for plan in self.__dict__.get('_pc_plans', {}).values():
+      plan._release()
     if self._engine is not None:
       _lib.load().b200_ncsnpp_destroy(self._engine['h'])
       self._engine = None
+
+  @staticmethod
+  def _explicit_device(device):
+    """``torch.device('cuda') != torch.device('cuda:0')``: normalise to an explicit index so the engine cache
+    does not thrash between a sampler created with ``device='cuda'`` and direct ``model(x, t)`` calls."""
+    device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:
+      device = torch.device('cuda', torch.cuda.current_device())
+    return device
 
   def __del__(self):
     try:
@@ -242,7 +261,10 @@ class NCSNpp(nn.Module):
       pass
 
   def engine(self, batch, device):
-    """Create / re-plan the native engine for ``batch`` images on ``device``."""
+    """Create / re-plan the native engine for ``batch`` images on ``device``.  ``eng['gen']`` is a monotonically
+    increasing plan generation: it changes whenever the engine, its workspace or its plan is rebuilt, which is what
+    dependants (captured CUDA graphs in ``native.PcPlan``) key their validity on."""
+    device = self._explicit_device(device)
     eng = self._engine
     if eng is not None and (eng['device'] != device or eng['precision'] != self.precision):
       self._release()
@@ -254,8 +276,9 @@ class NCSNpp(nn.Module):
       nbytes = _lib.load().b200_ncsnpp_weights_bytes(h)
       blob = torch.zeros(nbytes // 4 + 64, dtype=torch.float32, device=device)
       _lib.call('b200_ncsnpp_bind_weights', h, _lib.ptr(blob))
+      self._generation = getattr(self, '_generation', 0) + 1
       eng = dict(h=h, blob=blob, ws=None, batch=0, wver=-1, device=device, precision=self.precision,
-                 table=self._param_table(h))
+                 table=self._param_table(h), gen=self._generation)
       self._engine = eng
     if eng['wver'] != self._weights_version:
       sd = dict(self.named_parameters())
@@ -277,6 +300,8 @@ class NCSNpp(nn.Module):
         eng['ws'] = torch.empty(need // 4 + 256, dtype=torch.float32, device=device)
       _lib.call('b200_ncsnpp_bind_workspace', eng['h'], batch, _lib.ptr(eng['ws']), eng['ws'].numel() * 4)
       eng['batch'] = batch
+      self._generation += 1
+      eng['gen'] = self._generation
     return eng
 
   def forward(self, x, time_cond, labels_uniform=False):

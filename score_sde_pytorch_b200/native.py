@@ -89,7 +89,7 @@ class PcPlan:
   """A native PC loop bound to one model, SDE, sampler configuration and batch shape."""
 
   def __init__(self, model, sde, predictor_kind, corrector_kind, shape, snr, n_steps, probability_flow, eps, device):
-    self.model, self.sde, self.shape, self.device = model, sde, tuple(shape), torch.device(device)
+    self.model, self.sde, self.shape, self.device = model, sde, tuple(shape), model._explicit_device(device)
     self.predictor_kind, self.corrector_kind = predictor_kind, corrector_kind
     self.snr, self.n_steps, self.probability_flow, self.eps = float(snr), int(n_steps), bool(probability_flow), float(eps)
     self.tables = build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps)
@@ -112,7 +112,7 @@ class PcPlan:
 
   def _ensure(self):
     eng = self.model.engine(self.shape[0], self.device)
-    key = (id(eng), eng['batch'], id(eng['ws']))
+    key = eng['gen']   # monotonically increasing: bumped on engine re-create, workspace realloc and re-plan
     if self._pc is not None and self._engine_id == key:
       return eng
     self._release()
@@ -211,7 +211,11 @@ def match_pc_plan(sde, model, predictor, corrector, shape, snr, n_steps, probabi
     return None   # the reference itself fails here (subVPSDE has no .alphas, sampling.py:267-269)
   if ck == 'langevin' and n_steps < 1:
     return None
-  key = (id(sde), pk, ck, tuple(shape), float(snr), int(n_steps), bool(probability_flow), float(eps), str(device))
+  # keyed on the SDE's parameters (not id(sde): a freed-and-reallocated SDE object must not hit a stale plan)
+  sde_key = (type(sde).__name__, int(sde.N)) + tuple(
+      float(getattr(sde, a)) for a in ('sigma_min', 'sigma_max', 'beta_0', 'beta_1') if hasattr(sde, a))
+  key = (sde_key, pk, ck, tuple(shape), float(snr), int(n_steps), bool(probability_flow), float(eps),
+         str(model._explicit_device(device)))
   cache = model.__dict__.setdefault('_pc_plans', {})
   plan = cache.get(key)
   if plan is None:
