@@ -91,20 +91,103 @@ def headline_config():
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's sampler on the host cores
+# CPU arm: the UNMODIFIED reference (baseline/_ref, installed by tools/install_ref.sh) on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_pc_steps(batch, steps, warmup, threads=None):
-  """Time PC iterations of the oracle (plain PyTorch fp32 restatement of the reference path)."""
+REF_DIR = os.path.join(REPO, 'baseline', '_ref')
+REF_EXT_DIR = os.path.join(REPO, 'baseline', '_ref_ext')
+
+
+def physical_cores():
+  """Physical cores this process may run on (hyper-thread siblings counted once), capped by the affinity mask."""
+  try:
+    allowed = sorted(os.sched_getaffinity(0))
+  except AttributeError:
+    allowed = list(range(os.cpu_count() or 1))
+  seen, cores = set(), []
+  for cpu in allowed:
+    try:
+      with open(f'/sys/devices/system/cpu/cpu{cpu}/topology/core_id') as fh:
+        core = fh.read().strip()
+      with open(f'/sys/devices/system/cpu/cpu{cpu}/topology/physical_package_id') as fh:
+        pkg = fh.read().strip()
+      key = (pkg, core)
+    except OSError:
+      key = ('?', cpu)
+    if key not in seen:
+      seen.add(key)
+      cores.append(cpu)
+  return cores
+
+
+def import_reference():
+  """Import the reference's own modules from baseline/_ref (never from /root/reference: that path does not exist on
+  the GPU box).  `ml_collections` is not installed: its ConfigDict is only used as an attribute dict by the
+  reference's config files, so a 6-line stand-in is injected into sys.modules.  Returns the module namespace."""
+  import types
+  if not os.path.isdir(REF_DIR):
+    raise FileNotFoundError(f'{REF_DIR} missing: run tools/install_ref.sh where /root/reference exists')
+  if 'ml_collections' not in sys.modules:
+    class ConfigDict(dict):
+      def __getattr__(self, k):
+        try:
+          return self[k]
+        except KeyError:
+          raise AttributeError(k)
+      __setattr__ = dict.__setitem__
+    m = types.ModuleType('ml_collections')
+    m.ConfigDict = ConfigDict
+    sys.modules['ml_collections'] = m
+  os.environ.setdefault('TORCH_EXTENSIONS_DIR', REF_EXT_DIR)      # the two JIT extensions of op/ were pre-built there
+  os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0')
+  # our own package has modules of the same names (sampling, sde_lib, ...) under score_sde_pytorch_b200/, never
+  # top-level, so putting the reference first on sys.path shadows nothing of ours
+  if REF_DIR not in sys.path:
+    sys.path.insert(0, REF_DIR)
+  import importlib
+  ns = types.SimpleNamespace()
+  ns.sde_lib = importlib.import_module('sde_lib')
+  ns.sampling = importlib.import_module('sampling')
+  ns.mutils = importlib.import_module('models.utils')
+  ns.ncsnpp = importlib.import_module('models.ncsnpp')            # registers 'ncsnpp'; JIT-loads op/ on first import
+  ns.config = importlib.import_module('configs.ve.cifar10_ncsnpp_continuous')
+  assert os.path.realpath(ns.sampling.__file__).startswith(os.path.realpath(REF_DIR)), ns.sampling.__file__
+  return ns
+
+
+def reference_pc_steps(batch, steps, warmup):
+  """Time PC iterations of the reference itself: its NCSNpp module, its VESDE, and its
+  shared_corrector_update_fn / shared_predictor_update_fn called exactly as pc_sampler does (sampling.py:390-409)."""
+  ref = import_reference()
+  cfg = ref.config.get_config()
+  cfg.device = torch.device('cpu')
+  cfg.model.init_scale = 1.0
+  torch.manual_seed(0)
+  model = ref.mutils.get_model(cfg.model.name)(cfg).eval()       # no DataParallel on the CPU
+  sde = ref.sde_lib.VESDE(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+  shape = (batch, 3, 32, 32)
+  torch.manual_seed(1)
+  x = sde.prior_sampling(shape)
+  ts = torch.linspace(sde.T, 1e-5, sde.N)
+  pred = ref.sampling.get_predictor(cfg.sampling.predictor.lower())
+  corr = ref.sampling.get_corrector(cfg.sampling.corrector.lower())
+  times = []
+  with torch.no_grad():
+    for i in range(warmup + steps):
+      t0 = time.perf_counter()
+      vec_t = torch.ones(batch) * ts[i]
+      x, _ = ref.sampling.shared_corrector_update_fn(x, vec_t, sde, model, corr, True, cfg.sampling.snr, cfg.sampling.n_steps_each)
+      x, x_mean = ref.sampling.shared_predictor_update_fn(x, vec_t, sde, model, pred, False, True)
+      if i >= warmup:
+        times.append(time.perf_counter() - t0)
+  assert torch.isfinite(x_mean).all()
+  return times, 'reference'
+
+
+def port_pc_steps(batch, steps, warmup):
+  """Fallback when baseline/_ref is absent: the oracle port (plain PyTorch fp32 restatement of the same path)."""
   from oracle import ncsnpp_oracle as NO
   from oracle import sampling_oracle as SO
   from score_sde_pytorch_b200.models.ncsnpp import NCSNpp
-  # torch's own default (one thread per physical core) is the fastest setting for this workload: using every
-  # hyper-thread of the 128-way host made the oracle ~70x slower (127 s vs 1.8 s per iteration).  torchrun exports
-  # OMP_NUM_THREADS=1 to every rank, which would reduce the CPU arm to one core: undo that.
-  if threads:
-    torch.set_num_threads(threads)
-  elif torch.get_num_threads() <= 1:
-    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
   cfg = headline_config()
   torch.manual_seed(0)
   sd = NCSNpp(cfg).state_dict()
@@ -123,25 +206,73 @@ def cpu_pc_steps(batch, steps, warmup, threads=None):
       x, _ = SO.reverse_diffusion_step(sde, model, x, vec_t)
       if i >= warmup:
         times.append(time.perf_counter() - t0)
-  t_step = float(np.mean(times))
-  return dict(value=batch / (N_SAMPLER_STEPS * t_step), unit='images/s', cores=torch.get_num_threads(), kind='port',
-              sample=f'{steps} PC iterations (2 network evals each) of the oracle port at batch {batch} after {warmup} warm-up, '
-                     f'{t_step:.3f} s/iteration, extrapolated to {N_SAMPLER_STEPS} iterations',
-              host_cpus=os.cpu_count(), ms_per_step=t_step * 1e3)
+  return times, 'port'
+
+
+def cpu_pc_steps(batch, steps, warmup):
+  """One CPU-arm measurement in THIS process (threads already pinned by run_reference_arm's re-exec)."""
+  threads = int(os.environ.get('B200_BENCH_CPU_THREADS', '0')) or len(physical_cores())
+  torch.set_num_threads(threads)
+  try:
+    times, kind = reference_pc_steps(batch, steps, warmup)
+  except (FileNotFoundError, ImportError) as err:
+    print(f'bench: reference unavailable ({err}); timing the oracle port instead', file=sys.stderr)
+    times, kind = port_pc_steps(batch, steps, warmup)
+  t_med, t_mean = float(np.median(times)), float(np.mean(times))
+  spread = (max(times) - min(times)) / t_med if len(times) > 1 else 0.0
+  what = ("the reference's own NCSNpp + shared_corrector_update_fn/shared_predictor_update_fn (baseline/_ref, unmodified)"
+          if kind == 'reference' else 'the oracle port (baseline/_ref absent)')
+  return dict(value=batch / (N_SAMPLER_STEPS * t_med), unit='images/s', cores=threads, kind=kind,
+              sample=f'{steps} PC iterations (2 network evals each) of {what} at batch {batch} after {warmup} warm-up; '
+                     f'median {t_med:.3f} s/iteration (mean {t_mean:.3f}, spread {spread:.1%}), extrapolated to '
+                     f'{N_SAMPLER_STEPS} iterations; {threads} threads pinned to physical cores',
+              host_cpus=os.cpu_count(), ms_per_step=t_med * 1e3, iter_seconds=[round(t, 4) for t in times])
+
+
+def pinned_env():
+  """Environment for the CPU arm: one OpenMP thread per physical core, bound to it.  torchrun exports
+  OMP_NUM_THREADS=1 to every rank (which would reduce the arm to one core), so this overrides it."""
+  cores = physical_cores()
+  n = min(len(cores), 64)
+  env = dict(os.environ)
+  env.update(OMP_NUM_THREADS=str(n), MKL_NUM_THREADS=str(n), OMP_PROC_BIND='close', OMP_PLACES='cores',
+             GOMP_CPU_AFFINITY=' '.join(str(c) for c in cores[:n]), KMP_AFFINITY='granularity=core,compact',
+             B200_BENCH_CPU_THREADS=str(n), B200_BENCH_CPU_PINNED='1', CUDA_VISIBLE_DEVICES='')
+  return env
+
+
+def cpu_arm_subprocess(batch, steps, warmup):
+  """Run the CPU arm in a fresh, pinned process (thread pools of the GPU arm's process are already initialised) and
+  return its parsed JSON line."""
+  cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(steps), '--warmup', str(warmup),
+         '--cpu-batch', str(batch)]
+  env = pinned_env()
+  for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT', 'TORCHELASTIC_RUN_ID'):
+    env.pop(k, None)
+  out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+  for line in reversed(out.stdout.strip().splitlines()):
+    if line.startswith('{'):
+      return json.loads(line)
+  raise RuntimeError(f'CPU arm produced no JSON line:\n{out.stderr[-2000:]}')
 
 
 def run_reference_arm(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  if os.environ.get('B200_BENCH_CPU_PINNED') != '1':
+    # thread count and binding must be in the environment before libgomp starts: re-exec once
+    os.execve(sys.executable, [sys.executable] + sys.argv, pinned_env())
   batch = args.cpu_batch
-  r = cpu_pc_steps(batch, args.steps, args.warmup)
+  steps = max(args.steps, 5)                 # >= 5 timed iterations: the median is the reported figure
+  r = cpu_pc_steps(batch, steps, max(args.warmup, 1))
   line = dict(impl='reference', metric='PC-sampler images/sec, NCSN++ CIFAR-10 1000-step VE', value=r['value'],
-              unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=r['ms_per_step'],
+              unit='images/s', n_gpus=args.gpus, steps=steps, warmup=max(args.warmup, 1), ms_per_step=r['ms_per_step'],
               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
               config=dict(workload='NCSN++ cont. CIFAR-10 32x32 VE-SDE PC sampler (1000 steps); CPU arm: bounded sample at '
                                    f'batch {batch}', batch_per_gpu=batch, sampler_steps=N_SAMPLER_STEPS),
-              cpu_baseline=dict(value=r['value'], unit='images/s', cores=r['cores'], kind='port', sample=r['sample']),
+              cpu_baseline=dict(value=r['value'], unit='images/s', cores=r['cores'], kind=r['kind'], sample=r['sample'],
+                                iter_seconds=r['iter_seconds']),
               e2e=dict(value=r['value'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
               gpu_launches=0)
   print(json.dumps(line), flush=True)
@@ -188,6 +319,100 @@ def measure_tf32_peak(dev, f16=False):
   return best
 
 
+def check_parity(plan, model, cfg, sde, shape, dev, K, precision):
+  from oracle import ncsnpp_oracle as NO, sampling_oracle as SO
+  old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  try:
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    osde = SO.VE(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+    torch.manual_seed(1234)
+    x0 = osde.prior_sampling(shape).to(dev)
+    B = shape[0]
+    # the oracle's eager activations at batch 1024 need several GB per layer: evaluate the network in chunks (the
+    # Langevin step size couples the images through batch means of norms, so the LOOP still runs on the full batch)
+    chunk = 128
+
+    def net(a, l):
+      return torch.cat([NO.ncsnpp_forward(sd, cfg, a[i:i + chunk], l[i:i + chunk]) for i in range(0, B, chunk)])
+    torch.cuda.manual_seed(4321)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+      ref, _ = SO.pc_sample(osde, net, shape, eps=1e-5, device=dev, x_init=x0, num_iters=K)
+    torch.cuda.synchronize()
+    t_oracle = time.perf_counter() - t0
+    torch.cuda.manual_seed(4321)
+    _, xm = plan.run(x0, first_step=0, num_steps=K)
+    a, b = xm.double().flatten(1), ref.double().flatten(1)
+    rel = ((a - b).norm(dim=1) / b.norm(dim=1)).cpu().numpy()
+    return dict(max_rel_l2=float(rel.max()), p99_rel_l2=float(np.percentile(rel, 99)), median_rel_l2=float(np.median(rel)),
+                precision=precision, K=K, batch=B, bound=1e-3,
+                oracle='strict-fp32 PyTorch restatement on the same GPU (cudnn/matmul TF32 off), same prior draw and CUDA noise stream',
+                oracle_seconds=round(t_oracle, 1))
+  finally:
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def timed_steps(plan, x0, warmup, steps):
+  plan.run(x0, first_step=0, num_steps=warmup, clone=False)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  plan.run(x0, first_step=warmup, num_steps=steps, clone=False)
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / steps
+
+
+def profile_kinds(model, B, dev, x0):
+  """Per-kind device time of one eager forward (CUDA events around every launch)."""
+  import ctypes
+  from score_sde_pytorch_b200 import _lib
+  eng = model.engine(B, dev)
+  ms_k = (ctypes.c_float * 8)(); fl_k = (ctypes.c_double * 8)(); n_k = (ctypes.c_longlong * 8)()
+  xin = x0.clone(); lab = torch.full((B,), 1.0, device=dev); out = torch.empty_like(xin)
+  for _ in range(2):
+    _lib.call('b200_ncsnpp_profile_forward', eng['h'], _lib.ptr(xin), _lib.ptr(lab), 1, _lib.ptr(out),
+              _lib.stream_ptr(dev), ms_k, fl_k, n_k)
+  return eng, ms_k, fl_k, n_k
+
+
+def underfilled_launches(model, B, dev, x0, sms=148):
+  """Strong-scaling diagnosis: per-op time at this batch and which contraction launches have fewer tiles than SMs."""
+  import ctypes
+  from score_sde_pytorch_b200 import _lib
+  eng = model.engine(B, dev)
+  n = int(_lib.load().b200_ncsnpp_num_ops(eng['h']))
+  ms = (ctypes.c_float * n)()
+  xin = x0.clone(); lab = torch.full((B,), 1.0, device=dev); out = torch.empty_like(xin)
+  for _ in range(2):
+    _lib.call('b200_ncsnpp_profile_ops', eng['h'], _lib.ptr(xin), _lib.ptr(lab), 1, _lib.ptr(out), _lib.stream_ptr(dev), ms, n)
+  rows = {}
+  name = ctypes.create_string_buffer(200); kind = ctypes.c_int(); fl = ctypes.c_double()
+  for i in range(n):
+    _lib.call('b200_ncsnpp_op_info', eng['h'], i, name, 200, ctypes.byref(kind), ctypes.byref(fl))
+    r = rows.setdefault(name.value.decode(), dict(kind=kind.value, launches=0, ms=0.0, flops=0.0))
+    r['launches'] += 1; r['ms'] += ms[i]; r['flops'] += fl.value
+  out_rows = []
+  for k, r in sorted(rows.items(), key=lambda kv: -kv[1]['ms']):
+    if r['kind'] != 0:
+      continue
+    # tiles of a launch: M = B*H*W pixels over 128- (single), 256- (pair / swap) pixel tiles
+    import re
+    m = re.search(r'@(\d+)', k)
+    if not m:
+      continue
+    res = int(m.group(1))
+    px_per_tile = 128 if 'single' in k else 256
+    ctas = B * res * res // px_per_tile * (2 if 'pair' in k else 1)
+    if 'single128' in k:
+      ctas *= 2
+    out_rows.append(dict(op=k, launches=r['launches'], ms=round(r['ms'], 4), ctas=ctas, fills_sms=bool(ctas >= sms),
+                         tflops=round(r['flops'] / max(r['ms'], 1e-9) / 1e9, 1)))
+  return out_rows
+
+
 def run_gpu_arm(args):
   import torch.distributed as dist
   from score_sde_pytorch_b200 import native, sampling, sde_lib, _lib
@@ -206,7 +431,8 @@ def run_gpu_arm(args):
 
   cfg = headline_config()
   cfg.device = dev
-  B = args.batch
+  # weak (headline): args.batch images on every GPU; strong: args.batch images in total, an equal share per GPU
+  B = args.batch if args.scaling == 'weak' else max(1, args.batch // world)
   shape = (B, 3, 32, 32)
   torch.manual_seed(0)                       # same random-init weights on every rank ...
   model = NCSNpp(cfg, precision=args.precision).to(dev)
@@ -222,6 +448,16 @@ def run_gpu_arm(args):
   torch.cuda.manual_seed(1 + rank)
   x_host = sde.prior_sampling(shape).pin_memory()
   out_host = torch.empty(shape).pin_memory()
+
+  # ---- parity at the measured configuration: K PC iterations at the full batch through the engine's
+  # plan and through the strict-fp32 GPU oracle, same prior draw, same CUDA noise stream.  The oracle is the checker
+  # here, never the thing timed.  Runs on rank 0 only, before any timing; the run FAILS above the north-star bound.
+  parity = None
+  if rank == 0 and args.parity_steps > 0:
+    parity = check_parity(plan, model, cfg, sde, shape, dev, args.parity_steps, args.precision)
+    if not (parity['max_rel_l2'] <= 1e-3):
+      print(json.dumps(dict(error='parity check failed', parity=parity)), flush=True)
+      raise SystemExit(3)
 
   def barrier():
     torch.cuda.synchronize()
@@ -268,12 +504,7 @@ def run_gpu_arm(args):
   if rank == 0:
     peaks = load_peaks()
     # ---- per-kind device time of one eager forward (events around every launch) ----
-    eng = model.engine(B, dev)
-    ms_k = (ctypes.c_float * 8)(); fl_k = (ctypes.c_double * 8)(); n_k = (ctypes.c_longlong * 8)()
-    xin = x0.clone(); lab = torch.full((B,), 1.0, device=dev); out = torch.empty_like(xin)
-    for _ in range(2):
-      _lib.call('b200_ncsnpp_profile_forward', eng['h'], _lib.ptr(xin), _lib.ptr(lab), 1, _lib.ptr(out),
-                _lib.stream_ptr(dev), ms_k, fl_k, n_k)
+    eng, ms_k, fl_k, n_k = profile_kinds(model, B, dev, x0)
     # algorithmic HBM bytes of the contraction launches (operands once + outputs once), from the plan
     n_ops = int(_lib.load().b200_ncsnpp_num_ops(eng['h']))
     tc_alg_bytes = 0.0
@@ -291,17 +522,23 @@ def run_gpu_arm(args):
     tf32_peak = measure_tf32_peak(dev, f16)
     achieved = (tc_flops / tc_n) / ((tc_ms / tc_n) * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     t_hbm_ms = ALG_BYTES_PER_IMG_STEP * B / (peaks['hbm_gbs'] * 1e9) * 1e3
+    # Denominators.  fp16 operands run at the bf16 tensor rate, so MEASURED_PEAKS.json's bf16 figures apply directly:
+    # per-launch event timing isolates each kernel -> the BURST peak is the fair denominator for `frac`; the whole
+    # step is a long back-to-back run -> the SUSTAINED peak for step_tensor_fraction.  TF32 runs at half those rates.
+    rate = 1.0 if f16 else 0.5
+    burst, sustained = peaks['bf16_tflops'] * rate, peaks['bf16_tflops_sustained'] * rate
     roofline = dict(bound='tensor', kernel=f"gemm_tc_kernel / gemm_tc2_kernel (tcgen05 kind::{'f16' if f16 else 'tf32'} implicit GEMM)",
-                    achieved=round(achieved, 2), peak=round(tf32_peak, 2), unit='TFLOP/s',
-                    frac=round(achieved / tf32_peak, 4) if tf32_peak else None,
-                    peak_source=(f"cuBLAS {'fp16' if f16 else 'TF32'} 8192^3 GEMM measured in this run (MEASURED_PEAKS.json holds bf16 only: "
-                                 f"{peaks['bf16_tflops_sustained']} TF/s sustained, {peaks['source']})"),
-                    frac_of_measured_bf16_sustained=round(achieved / peaks['bf16_tflops_sustained'], 4),
+                    achieved=round(achieved, 2), peak=round(burst, 2), unit='TFLOP/s',
+                    frac=round(achieved / burst, 4),
+                    peak_source=(f"{peaks['source']}: bf16 burst {peaks['bf16_tflops']} TF/s" + ('' if f16 else ' x 0.5 (TF32 rate)')),
+                    frac_of_sustained=round(achieved / sustained, 4), peak_sustained=round(sustained, 2),
+                    cublas_in_run=round(tf32_peak, 2), frac_of_cublas_in_run=round(achieved / tf32_peak, 4) if tf32_peak else None,
                     alg_flop_per_launch=tc_flops / tc_n, avg_launch_ms=tc_ms / tc_n, launches_per_forward=tc_n,
                     kernel_share_of_forward=round(tc_ms / fwd_ms, 4) if fwd_ms else None,
                     traffic=load_traffic(args.precision), alg_hbm_bytes_per_launch=round(tc_alg_bytes / tc_n),
                     hbm_fraction_of_step=round(t_hbm_ms / ms_per_step, 4),
-                    step_tensor_fraction=round((ALG_FLOP_PER_IMG_STEP * B / (tf32_peak * 1e12) * 1e3) / ms_per_step, 4) if tf32_peak else None,
+                    step_tensor_fraction=round((ALG_FLOP_PER_IMG_STEP * B / (sustained * 1e12) * 1e3) / ms_per_step, 4),
+                    step_tflops=round(ALG_FLOP_PER_IMG_STEP * B / (ms_per_step * 1e-3) / 1e12, 1),
                     forward_ms_by_kind=by_kind)
     # ---- the other tensor-core operand format, same model / batch / steps, device-resident timing only ----
     variants = None
@@ -312,21 +549,38 @@ def run_gpu_arm(args):
       plan2 = native.match_pc_plan(sde=sde, model=model2, predictor=sampling.ReverseDiffusionPredictor,
                                    corrector=sampling.LangevinCorrector, shape=shape, snr=cfg.sampling.snr, n_steps=1,
                                    probability_flow=False, continuous=True, eps=1e-5, device=dev)
-      x2 = x_host.to(dev)
-      plan2.run(x2, first_step=0, num_steps=args.warmup, clone=False)
-      torch.cuda.synchronize()
-      g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      g0.record()
-      plan2.run(x2, first_step=args.warmup, num_steps=args.steps, clone=False)
-      g1.record()
-      torch.cuda.synchronize()
-      ms2 = g0.elapsed_time(g1) / args.steps
+      ms2 = timed_steps(plan2, x_host.to(dev), args.warmup, args.steps)
       variants = {other: dict(value=round(B / (N_SAMPLER_STEPS * ms2 * 1e-3), 4), unit='images/s', ms_per_step=round(ms2, 4))}
       del plan2, model2
-    cpu = cpu_pc_steps(args.cpu_batch, 2, 1) if world == 1 and not args.no_cpu else None
+    # ---- strong-scaling probe: the same 1024-image job cut over 8 GPUs is 128 images per GPU; time that
+    # per-GPU share here and name the launches that under-fill the 148 SMs ----
+    strong = None
+    if world == 1 and not args.no_strong and B == 1024:
+      sb = 128
+      splan = native.match_pc_plan(sde=sde, model=model, predictor=sampling.ReverseDiffusionPredictor,
+                                   corrector=sampling.LangevinCorrector, shape=(sb, 3, 32, 32), snr=cfg.sampling.snr, n_steps=1,
+                                   probability_flow=False, continuous=True, eps=1e-5, device=dev)
+      xs = x_host[:sb].to(dev)
+      ms_s = timed_steps(splan, xs, args.warmup, args.steps)
+      _, msk, _, nk = profile_kinds(model, sb, dev, xs)
+      rows = underfilled_launches(model, sb, dev, xs)
+      under = [r for r in rows if not r['fills_sms']]
+      strong = dict(batch_per_gpu=sb, ms_per_step=round(ms_s, 4), images_per_s_per_gpu=round(sb / (N_SAMPLER_STEPS * ms_s * 1e-3), 4),
+                    projected_8gpu_images_per_s=round(8 * sb / (N_SAMPLER_STEPS * ms_s * 1e-3), 4),
+                    efficiency_vs_batch_1024=round((sb / ms_s) / (B / ms_per_step), 4),
+                    forward_ms_by_kind={k: round(msk[i], 4) for i, k in enumerate(kinds)},
+                    underfilled_contractions=dict(count=sum(r['launches'] for r in under), ms=round(sum(r['ms'] for r in under), 4),
+                                                  of_total_ms=round(sum(r['ms'] for r in rows), 4), top=under[:8]))
+      del splan
+    cpu = None
+    if world == 1 and not args.no_cpu:
+      try:
+        cpu = cpu_arm_subprocess(args.cpu_batch, 5, 1)['cpu_baseline']
+      except Exception as err:   # the GPU measurement stands on its own; say why the CPU leg is missing
+        cpu = dict(value=None, unit='images/s', cores=0, kind='unavailable', sample=f'{type(err).__name__}: {err}'[:300])
     line = dict(metric='PC-sampler images/sec, NCSN++ CIFAR-10 1000-step VE', value=round(value, 4), unit='images/s',
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_per_step, 4),
-                higher_is_better=True, scaling='weak', vs_baseline=None,
+                higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype={'tf32': 'tf32', 'f16': 'f16 operands (11-bit significand, as tf32), f32 accumulate and activations', 'fp32': 'f32'}[args.precision],
                 data='synthetic',
                 config=dict(workload='NCSN++ cont. CIFAR-10 32x32 VE-SDE PC sampler (1000 steps), batch 1024 per GPU'
@@ -344,7 +598,11 @@ def run_gpu_arm(args):
     if variants is not None:
       line['variants'] = variants
     if cpu is not None:
-      line['cpu_baseline'] = dict(value=cpu['value'], unit='images/s', cores=cpu['cores'], kind='port', sample=cpu['sample'])
+      line['cpu_baseline'] = dict(value=cpu['value'], unit='images/s', cores=cpu['cores'], kind=cpu['kind'], sample=cpu['sample'])
+    if strong is not None:
+      line['strong_scaling'] = strong
+    if parity is not None:
+      line['parity'] = parity
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
@@ -363,6 +621,11 @@ def main():
                        "accumulation and meet the same 1e-3 parity bound (tests/test_gpu_tc.py); 'fp32' = CUDA cores")
   ap.add_argument('--no-variants', action='store_true', help='skip timing the other operand format')
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  ap.add_argument('--no-strong', action='store_true', help='skip the 128-images-per-GPU strong-scaling probe')
+  ap.add_argument('--parity-steps', type=int, default=10,
+                  help='PC iterations of the in-run parity check against the strict-fp32 GPU oracle at the full batch (0 = skip)')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help="'weak' (default, headline): --batch images per GPU; 'strong': --batch images in total, cut over the ranks")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'ours':
     args.warmup = 3

@@ -92,6 +92,30 @@ class VP:
     return self.alphas.to(t.device)[idx]
 
 
+class SubVP(VP):
+  """sde_lib.py:167-204: same drift and mean as VP; diffusion sqrt(beta_t (1 - e^{-2 beta_0 t - (beta_1-beta_0) t^2})),
+  marginal std 1 - e^{2 log_mean_coeff} (no square root).  No `alphas` table: the reference's Langevin corrector
+  has no sub-VP branch that works (sampling.py:267-271 reads sde.alphas only for VPSDE, alpha = 1 otherwise)."""
+  kind = 'subvp'
+
+  def sde(self, x, t):                                                                        # :183-188
+    beta_t = self.beta_0 + t * (self.beta_1 - self.beta_0)
+    discount = 1. - torch.exp(-2 * self.beta_0 * t - (self.beta_1 - self.beta_0) * t ** 2)
+    return -0.5 * beta_t[:, None, None, None] * x, torch.sqrt(beta_t * discount)
+
+  def std(self, t):                                                                           # :190-194
+    lmc = -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+    return 1 - torch.exp(2. * lmc)
+
+  def discretize(self, x, t):                                                                 # base class, sde_lib.py:52-69
+    dt = 1 / self.N
+    drift, diffusion = self.sde(x, t)
+    return drift * dt, diffusion * torch.sqrt(torch.tensor(dt, device=t.device))
+
+  def langevin_alpha(self, t):
+    return torch.ones_like(t)                                                                 # sampling.py:270-271
+
+
 def langevin_step(sde, model, x, t, snr, n_steps, continuous=True):
   """sampling.py:262-282."""
   alpha = sde.langevin_alpha(t)
@@ -148,6 +172,8 @@ def pc_sample(sde, model, shape, predictor='reverse_diffusion', corrector='lange
         x, x_mean = reverse_diffusion_step(sde, model, x, vec_t, continuous)
       elif predictor == 'euler_maruyama':
         x, x_mean = euler_maruyama_step(sde, model, x, vec_t, continuous)
+      else:
+        x_mean = x                                   # NonePredictor.update_fn returns (x, x), sampling.py:249-250
       if trace is not None:
         trace.append(x.clone())
     return (x_mean if denoise else x), sde.N * (n_steps + 1)

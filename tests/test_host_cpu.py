@@ -65,6 +65,33 @@ def test_get_sampling_fn_vp_em_plumbing():
   assert rel_l2(s, torch.from_numpy(g['rd_langevin'])) < 1e-5
 
 
+def test_generic_pc_loop_none_predictor_and_subvp_match_reference():
+  """Host mirror (generic loop) vs the round-2 reference goldens: predictor=None hands the noisy state to the denoise
+  step (sampling.py:241-250); sub-VP under both predictors."""
+  g = golden('pc_extra_tiny.npz')
+  cfg = golden_config('tiny')
+  cfg.device = torch.device('cpu')
+  model = TorchModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny.npz')['x'].shape)
+  fn = sampling.get_pc_sampler(sde_lib.VESDE(0.01, 50, 12), shape, None, sampling.LangevinCorrector, lambda v: v, snr=0.16,
+                               n_steps=1, continuous=True, denoise=True, eps=1e-5, device='cpu')
+  torch.manual_seed(31)
+  s, nfe = fn(model)
+  assert nfe == int(g['ve_none_langevin_nfe'])
+  assert rel_l2(s, torch.from_numpy(g['ve_none_langevin'])) < 1e-5
+  cfg = golden_config('tiny_vp')
+  cfg.device = torch.device('cpu')
+  model = TorchModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny_vp.npz')['x'].shape)
+  sde = sde_lib.subVPSDE(0.1, 20., 20)
+  for tag, pred, seed in (('subvp_em_none', sampling.EulerMaruyamaPredictor, 32), ('subvp_rd_none', sampling.ReverseDiffusionPredictor, 33)):
+    fn = sampling.get_pc_sampler(sde, shape, pred, sampling.NoneCorrector, lambda v: v, snr=0.16, n_steps=1,
+                                 continuous=True, denoise=True, eps=1e-3, device='cpu')
+    torch.manual_seed(seed)
+    s, _ = fn(model)
+    assert rel_l2(s, torch.from_numpy(g[tag])) < 1e-5, tag
+
+
 def test_registries_and_errors():
   assert sampling.get_predictor('reverse_diffusion') is sampling.ReverseDiffusionPredictor
   assert sampling.get_corrector('langevin') is sampling.LangevinCorrector
@@ -192,7 +219,10 @@ def test_bench_reference_arm_prints_the_contract_line():
   assert line['impl'] == 'reference' and line['unit'] == 'images/s' and line['higher_is_better'] is True
   assert line['metric'].startswith('PC-sampler images/sec') and line['value'] > 0 and line['n_gpus'] == 1
   cb = line['cpu_baseline']
-  assert cb['kind'] == 'port' and cb['value'] == line['value'] and cb['cores'] >= 1 and 'PC iterations' in cb['sample']
+  # the UNMODIFIED reference from baseline/_ref (tools/install_ref.sh) when it is installed, else the oracle port
+  want = 'reference' if os.path.isdir(os.path.join(root, 'baseline', '_ref', 'models')) else 'port'
+  assert cb['kind'] == want and cb['value'] == line['value'] and cb['cores'] >= 1 and 'PC iterations' in cb['sample']
+  assert line['steps'] >= 5 and len(cb['iter_seconds']) == line['steps']      # the median of >= 5 iterations is reported
   assert line['e2e'] == {'value': line['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
   if (os.cpu_count() or 1) >= 4:
     assert cb['cores'] > 1        # OMP_NUM_THREADS=1 from the launcher must not reduce the arm to one core

@@ -86,6 +86,29 @@ def test_pc_sampler_oracle_matches_reference_vp():
   assert rel_l2(s, torch.from_numpy(g['rd_langevin'])) < 1e-5
 
 
+def test_pc_sampler_oracle_matches_reference_none_predictor_and_subvp():
+  """Round-2 pins (tools/make_golden_r2.py): a 'none' predictor hands x (not the Langevin mean) to the denoise step;
+  the sub-VP SDE under both predictors."""
+  g = golden('pc_extra_tiny.npz')
+  cfg = golden_config('tiny')
+  shape = tuple(golden('ncsnpp_tiny.npz')['x'].shape)
+  model = _OracleModel(cfg)        # (re-seeds the generator for its weights: build it before seeding the sampler)
+  torch.manual_seed(31)
+  s, nfe = SO.pc_sample(SO.VE(0.01, 50, 12), model, shape, 'none', 'langevin', snr=0.16, n_steps=1, eps=1e-5)
+  assert nfe == int(g['ve_none_langevin_nfe'])
+  assert rel_l2(s, torch.from_numpy(g['ve_none_langevin'])) < 1e-5
+  cfg = golden_config('tiny_vp')
+  model = _OracleModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny_vp.npz')['x'].shape)
+  sde = SO.SubVP(0.1, 20., 20)
+  torch.manual_seed(32)
+  s, _ = SO.pc_sample(sde, model, shape, 'euler_maruyama', 'none', eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['subvp_em_none'])) < 1e-5
+  torch.manual_seed(33)
+  s, _ = SO.pc_sample(sde, model, shape, 'reverse_diffusion', 'none', eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['subvp_rd_none'])) < 1e-5
+
+
 def test_sde_tables_match_reference():
   g = golden('sde_tables.npz')
   ve = SO.VE(0.01, 50, 1000)
