@@ -116,8 +116,9 @@ typedef struct {
   int cuda_core_head;           /* 1: the output convolution (ncsnpp.py:374-380) runs on CUDA cores with an fp32 input in
                                  * every precision mode (costs ~1.4 % of a step, buys back ~1e-4 of rel-L2); 0: tensor cores */
   int separate_groupnorm;       /* 1: every GroupNorm+SiLU as its own streaming pass (the round-1 plan, kept for A/B and
-                                 * as the checked alternative); 0: fused into the producing contraction's epilogue
-                                 * wherever one image's pixels are produced by one kernel launch */
+                                 * as the checked alternative); 0: in fp16 operand mode GroupNorm+SiLU is applied ON LOAD by
+                                 * the consuming 3x3 convolution (csrc/gemm_tcg.cuh) wherever the shape allows
+                                 * (256-channel outputs at 16x16 / 32x32), so the normalised tensor never reaches HBM */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

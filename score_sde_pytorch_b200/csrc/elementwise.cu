@@ -317,6 +317,46 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   return 0;
 }
 
+// GroupNorm folded into per-(image, channel) affine coefficients: scale = rstd * gamma, shift = beta - mean * scale,
+// from the same fp64 quad sums and with the same fp32 operations as gn_apply_stream_kernel (so a consumer that applies
+// fma(x, scale, shift) reproduces that kernel bit for bit).  Consumed by the convolutions that normalise their input on
+// load (gemm_tcg.cuh): the [B][C] tables are ~1e-3 of the activation bytes, the normalised tensor is never stored.
+__global__ void __launch_bounds__(128) gn_coeff_kernel(const double* __restrict__ q1, int C1, const double* __restrict__ q2, int C2,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int G,
+                                                       float eps, double inv_n, float* __restrict__ scale, float* __restrict__ shift) {
+  const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
+  const int qd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qd >= Q) return;
+  const int c0 = qd << 2, g0 = (c0 / cpg) * cpg;
+  double s = 0.0, ss = 0.0;
+  for (int c = g0; c < g0 + cpg; c += 4) {
+    const double* src = (c < C1) ? q1 + ((long long)b * (C1 >> 2) + (c >> 2)) * 2
+                                 : q2 + ((long long)b * (C2 >> 2) + ((c - C1) >> 2)) * 2;
+    s += src[0]; ss += src[1];
+  }
+  const double mean = s * inv_n;
+  const float var = fmaxf((float)(ss * inv_n - mean * mean), 0.f);
+  const float rstd = rsqrtf(var + eps), mu = (float)mean;
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  *reinterpret_cast<float4*>(scale + (long long)b * C + c0) = sc;
+  *reinterpret_cast<float4*>(shift + (long long)b * C + c0) =
+      make_float4(fmaf(-mu, sc.x, be.x), fmaf(-mu, sc.y, be.y), fmaf(-mu, sc.z, be.z), fmaf(-mu, sc.w, be.w));
+}
+
+int launch_gn_coeff(int C1, int C2, const double* q1, const double* q2, const float* gamma, const float* beta, int B, int HW,
+                    int G, float eps, float* scale, float* shift, cudaStream_t st) {
+  const int C = C1 + C2;
+  B200_REQUIRE(C % 4 == 0 && C1 % 4 == 0 && C % G == 0 && (C / G) % 4 == 0, "gn_coeff: C=%d (C1=%d) G=%d must give 4-aligned groups", C, C1, G);
+  B200_REQUIRE(q1 && (C2 == 0 || q2) && scale && shift, "gn_coeff: null pointer");
+  const double inv_n = 1.0 / ((double)HW * (C / G));
+  dim3 grid((C / 4 + 127) / 128, B);
+  gn_coeff_kernel<<<grid, 128, 0, st>>>(q1, C1, q2, C2, gamma, beta, G, eps, inv_n, scale, shift);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
 // ============================================================================
 // upfirdn2d: zero-insert upsample (up), zero pad, correlate with the flipped FIR,
 // decimate (down).  Successor of the reference's native op

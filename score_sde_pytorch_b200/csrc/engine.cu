@@ -14,6 +14,7 @@
 
 namespace b200 {
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld);
+void tcg_set_rowvec_ld(TcgPlan* p, long long ld);
 }
 using namespace b200;
 
@@ -117,6 +118,7 @@ struct b200_ncsnpp {
 
   std::vector<TcGemmPlan*> tcplans;
   std::vector<TcAttnPlan*> attnplans;
+  std::vector<TcgPlan*> tcgplans;
   std::map<int, Tensor> taps;
   long long launches = 0;
   // per-call arguments read by the closures
@@ -126,6 +128,7 @@ struct b200_ncsnpp {
   ~b200_ncsnpp() {
     for (auto* p : tcplans) tc_gemm_plan_destroy(p);
     for (auto* p : attnplans) tc_attn_plan_destroy(p);
+    for (auto* p : tcgplans) tcg_plan_destroy(p);
     if (lane_stream) cudaStreamDestroy(lane_stream);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -333,6 +336,7 @@ struct Builder {
   b200_ncsnpp* e; int B; char* base; bool dry; Arena arena; int rc = 0;
   char* stats_base = nullptr; long long stats_top = 0;   // bump region for GroupNorm quad sums, zeroed once per forward
   bool fused_stats = false;
+  bool gn_on_load = false;                     // GroupNorm+SiLU applied by the consuming convolution (gemm_tcg.cuh) where shapes allow
   int lane = 0;                                // which half-batch plan this builder fills (ops or ops2)
   int om = 1;                                  // operand store mode of tensor-core inputs: 1 TF32-grid fp32, 2 fp16
   std::string next_name;                       // label of the next op (shape summary for the per-op profile)
@@ -343,6 +347,7 @@ struct Builder {
   Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_, int lane_ = 0) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0), lane(lane_) {
     fused_stats = e_->cfg.precision != 1;
     om = e_->cfg.precision == 2 ? 2 : 1;
+    gn_on_load = om == 2 && !e_->cfg.separate_groupnorm;
     if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
   }
   double* qalloc(int C) {
@@ -392,6 +397,64 @@ struct Builder {
     op(1, [=](cudaStream_t st) {
       return launch_gn_apply(a.p, a.C, b.p, b.C, a.qs, b.qs, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, st, a.f16 ? 1 : 0);
     }, 2);
+  }
+
+  // ---- GroupNorm on load (gemm_tcg.cuh): coefficient tables + the convolution that consumes them ----
+  bool tcg_shape_ok(int C1, int C2, int Cout, int H, int W, int C3 = 0, int C4 = 0) const {
+    if (!gn_on_load || !fused_stats) return false;
+    TcgDesc d; memset(&d, 0, sizeof(d));
+    d.a1 = (const void*)16; d.C1 = C1; d.a2 = C2 ? (const void*)16 : nullptr; d.C2 = C2;
+    d.a3 = C3 ? (const void*)16 : nullptr; d.C3 = C3; d.a4 = C4 ? (const void*)16 : nullptr; d.C4 = C4; d.w2 = C3 ? (const float*)16 : nullptr;
+    d.H = H; d.W = W; d.nimg = 1; d.N_total = Cout; d.epi.ld_out = Cout; d.epi.ld_res = Cout; d.epi.rows_per_img = H * W;
+    return tcg_supported(d, nullptr);
+  }
+  struct Coef { float* scale = nullptr; float* shift = nullptr; long long bytes = 0; };
+  Coef gncoef(Tensor& x1, Tensor& x2, int pgw, int pgb) {
+    const int C = x1.C + x2.C, G = std::min(C / 4, 32), HW = x1.H * x1.W;
+    ensure_qs(x1); ensure_qs(x2);
+    Coef c;
+    c.scale = falloc(2LL * B * C, &c.bytes); c.shift = c.scale + (long long)B * C;
+    const float *g = e->W(pgw), *bt = e->W(pgb);
+    const Tensor a = x1, b = x2; const int Bc = B; const Coef cc = c;
+    name("gn_coeff %d+%d @%d", x1.C, x2.C, x1.H);
+    op(1, [=](cudaStream_t st) { return launch_gn_coeff(a.C, b.C, a.qs, b.qs, g, bt, Bc, HW, G, 1e-6f, cc.scale, cc.shift, st); }, 2);
+    return c;
+  }
+  // out = epi(Conv3x3(SiLU(GN(cat[a1, a2]))) [+ Conv1x1(cat[x3, x4])]); a*/x* are read in their stored format (fp32 or fp16)
+  void convg(Tensor a1, Tensor a2, const Coef& cf, int pw, int pb, int Cout, int dense_row, const float* residual, float scale,
+             int round, Tensor& out, Tensor x3 = Tensor(), Tensor x4 = Tensor(), int pw2 = -1, int pb2 = -1) {
+    TcgDesc d; memset(&d, 0, sizeof(d));
+    d.a1 = a1.p; d.C1 = a1.C; d.a1_f16 = a1.f16; d.a2 = a2.p; d.C2 = a2.C; d.a2_f16 = a2.f16;
+    d.gn_scale = cf.scale; d.gn_shift = cf.shift; d.act = 1;
+    d.H = out.H; d.W = out.W; d.nimg = B; d.w = e->W(pw); d.N_total = Cout;
+    Epilogue ep; memset(&ep, 0, sizeof(ep));
+    ep.bias = e->W(pb); ep.residual = residual; ep.ld_res = Cout; ep.scale = scale; ep.round_tf32 = round;
+    ep.rows_per_img = out.H * out.W; ep.out = out.p; ep.ld_out = Cout;
+    if (dense_row >= 0) ep.rowvec = dense_all_ + dense_row;
+    if (x3.p) {
+      if (dense_row >= 0) { set_error("ncsnpp: fused skip projection on a conv with a time-embedding bias"); rc = 2; return; }
+      d.a3 = x3.p; d.C3 = x3.C; d.a3_f16 = x3.f16; d.a4 = x4.p; d.C4 = x4.C; d.a4_f16 = x4.f16; d.w2 = e->W(pw2);
+      ep.rowvec = e->W(pb2); ep.rowvec_ld = 0;
+    }
+    if (fused_stats) { out.qs = qalloc(Cout); d.qstats = out.qs; }
+    d.epi = ep;
+    if (dry) return;
+    TcgPlan* pl = nullptr;
+    if (int r = tcg_plan_create(d, &pl)) { rc = r; return; }
+    e->tcgplans.push_back(pl);
+    name("conv3x3 gn+silu %d+%d->%d @%d%s%s [pair256-gn]", a1.C, a2.C, Cout, out.H, x3.p ? " +skipproj" : "", residual ? " +res" : "");
+    if (x3.p) next_name += " " + std::to_string(x3.C + x4.C);
+    {
+      const double px = (double)B * out.H * out.W;
+      next_bytes = px * (a1.C * (a1.f16 ? 2.0 : 4.0) + a2.C * (a2.f16 ? 2.0 : 4.0) + x3.C * (x3.f16 ? 2.0 : 4.0) + x4.C * (x4.f16 ? 2.0 : 4.0)) +
+                   px * Cout * (round == 2 ? 2.0 : 4.0) + (residual ? px * Cout * 4.0 : 0.0) + (9.0 * (a1.C + a2.C) + x3.C + x4.C) * Cout * 2.0;
+    }
+    b200_ncsnpp* eng = e; const int sumC = e->sumC;
+    const double cflops = 2.0 * B * out.H * out.W * (double)Cout * ((a1.C + a2.C) * 9 + x3.C + x4.C);
+    op(1, [=](cudaStream_t st) {
+      if (dense_row >= 0) tcg_set_rowvec_ld(pl, eng->uniform ? 0 : sumC);
+      return tcg_launch(pl, st);
+    }, 0, cflops);
   }
 
   void fir(const float* x, int major, int H, int W, int minor, int up, int down, int pad0, int pad1, int round, float* y,
@@ -510,15 +573,25 @@ struct Builder {
     const int Cin = x1.C + x2.C, H = x1.H, Ho = m.up ? 2 * H : m.down ? H / 2 : H;
     const bool resample = m.up || m.down;
     const float inv_s2 = e->cfg.skip_rescale ? 1.0f / (float)std::sqrt(2.0) : 1.0f;
-    Tensor a0 = talloc(Cin, H, H);
-    Tensor raw; // TF32-rounded copy of the (concatenated) block input for the tensor-core skip conv
-    if (m.has_conv2 && m.tc2 && !resample) raw = talloc(Cin, H, H);
-    gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? om : 0, a0, raw.p);
+    // GroupNorm on load (fp16 operand mode, 256-channel outputs at 16x16 / 32x32): GroupNorm_1 + SiLU is applied by Conv_1
+    // while it builds its operand (g1), GroupNorm_0 + SiLU by Conv_0 when no FIR resampling sits in between (g0).  The
+    // skip projection then reads the block input itself (fp32 -> fp16 on load), so no rounded copy is written either.
+    const bool h1_f16 = om == 2 && m.tc0 && m.tc1 && fused_stats && (Ho * Ho) % 32 == 0 && (m.cout % 128 == 0);
+    const bool skip_ok = !m.has_conv2 || (m.tc2 && (resample ? Cin % 64 == 0 : (x1.C % 64 == 0 && x2.C % 64 == 0)));
+    const bool g1 = m.tc0 && m.tc1 && h1_f16 && skip_ok && tcg_shape_ok(m.cout, 0, m.cout, Ho, Ho);
+    const bool g0 = g1 && !resample && tcg_shape_ok(x1.C, x2.C, m.cout, Ho, Ho);
+    Tensor a0, raw;   // raw: operand-format copy of the (concatenated) block input for the tensor-core skip conv
+    if (!g0) {
+      a0 = talloc(Cin, H, H);
+      if (m.has_conv2 && m.tc2 && !resample && !g1) raw = talloc(Cin, H, H);
+      gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? om : 0, a0, raw.p);
+    }
     Tensor xr;
     if (resample) {
       if (x2.p) { set_error("ncsnpp: resampling block with a two-source input"); rc = 2; return Tensor(); }
       Tensor a0r = talloc(Cin, Ho, Ho);
       xr = talloc(Cin, Ho, Ho);
+      xr.f16 = m.tc2 && om == 2;
       if (m.up) {   // upsample_2d: up=2, pad=(2,1), gain*4 (up_or_down_sampling.py:218-224)
         const int p = e->firn - 2;
         fir(a0.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc0 ? om : 0, a0r.p, 4.f);
@@ -533,11 +606,29 @@ struct Builder {
     Tensor h1 = talloc(m.cout, Ho, Ho);
     // fp16 operand mode: the mid-block tensor (Conv_0 output, only ever read by GroupNorm_1) is stored as fp16;
     // its GroupNorm sums are accumulated from the fp32 accumulators in the epilogue.
-    const bool h1_f16 = om == 2 && m.tc0 && m.tc1 && fused_stats && (Ho * Ho) % 32 == 0 && (m.cout % 128 == 0);
     h1.f16 = h1_f16;
-    conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, h1_f16 ? 2 : 0, h1, /*want_stats=*/true);
+    if (g0) {
+      Coef c0 = gncoef(x1, x2, m.gn0w, m.gn0b);
+      convg(x1, x2, c0, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 2, h1);
+      ffree(c0.scale, c0.bytes);
+    } else {
+      conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, h1_f16 ? 2 : 0, h1, /*want_stats=*/true);
+      tfree(a0);
+    }
     if (h1_f16 && !h1.qs) { set_error("ncsnpp: fp16 mid-block tensor without fused GroupNorm sums"); rc = 2; return Tensor(); }
-    tfree(a0);
+    if (g1) {
+      Coef c1 = gncoef(h1, none, m.gn1w, m.gn1b);
+      Tensor out = talloc(m.cout, Ho, Ho);
+      if (m.has_conv2) {
+        if (resample) convg(h1, none, c1, m.c1w, m.c1b, m.cout, -1, nullptr, inv_s2, 0, out, xr, Tensor(), m.c2w, m.c2b);
+        else convg(h1, none, c1, m.c1w, m.c1b, m.cout, -1, nullptr, inv_s2, 0, out, x1, x2, m.c2w, m.c2b);
+      } else {
+        convg(h1, none, c1, m.c1w, m.c1b, m.cout, -1, x1.p, inv_s2, 0, out);
+      }
+      ffree(c1.scale, c1.bytes);
+      tfree(h1); tfree(xr);
+      return out;
+    }
     Tensor a1 = talloc(m.cout, Ho, Ho);
     gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? om : 0, a1, nullptr);
     tfree(h1);
@@ -548,6 +639,7 @@ struct Builder {
     if (m.has_conv2 && m.tc1 && m.tc2 && (resample || raw.p)) {
       Tensor out = talloc(m.cout, Ho, Ho);
       Tensor e1 = resample ? xr : raw, e2 = Tensor();
+      e1.f16 = false;   // conv() addresses operands by the engine-wide operand mode
       conv(true, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, nullptr, inv_s2, 0, out, /*want_stats=*/true, 1, 0, e1, e2, m.c2w, m.c2b);
       tfree(a1); tfree(raw); tfree(xr);
       return out;
@@ -954,6 +1046,8 @@ int b200_ncsnpp_bind_workspace(b200_ncsnpp_t* h, int batch, void* ws, long long 
   for (auto* p : h->tcplans) tc_gemm_plan_destroy(p);
   for (auto* p : h->attnplans) tc_attn_plan_destroy(p);
   h->attnplans.clear();
+  for (auto* p : h->tcgplans) tcg_plan_destroy(p);
+  h->tcgplans.clear();
   h->tcplans.clear(); h->ops.clear(); h->ops2.clear(); h->taps.clear(); h->launches = 0;
   h->B = batch; h->ws_bytes = ws_bytes;
   h->ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));

@@ -27,6 +27,7 @@
 #include "kernels.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -645,6 +646,7 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
 
 #include "gemm_tc2.cuh"
 #include "attn_tc.cuh"
+#include "gemm_tcg.cuh"
 
 // ---------------------------------------------------------------------------
 // Host side: tensor maps, plan, launch
@@ -912,6 +914,76 @@ int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
   return 0;
 }
 
+// ---- convolution with GroupNorm (+SiLU) applied on load (gemm_tcg.cuh) ----
+struct TcgPlan { TcgParams prm; };
+
+bool tcg_supported(const TcgDesc& d, const char** why) {
+  static const char* w;
+  auto fail = [&](const char* m) { w = m; if (why) *why = w; return false; };
+  if (d.W != 16 && d.W != 32) return fail("image width must be 16 or 32");
+  if (d.H <= 0 || (d.H * d.W) % 128 || d.H % (128 / d.W)) return fail("image rows do not tile 128 pixels");
+  if (d.N_total % 256) return fail("C_out must be a multiple of 256");
+  if (d.C1 <= 0 || d.C1 % 64 || d.C2 % 64 || d.C3 % 64 || d.C4 % 64) return fail("channel counts must be multiples of 64");
+  if ((d.a2 == nullptr) != (d.C2 == 0) || (d.a3 == nullptr) != (d.C3 == 0) || (d.a4 == nullptr) != (d.C4 == 0)) return fail("source / channel-count mismatch");
+  if (d.a4 && !d.a3) return fail("second extra source without the first");
+  if (d.a3 && !d.w2) return fail("extra 1x1 phase without weights");
+  if ((d.gn_scale == nullptr) != (d.gn_shift == nullptr)) return fail("GroupNorm scale and shift come together");
+  if (d.epi.out_nchw || d.epi.per_img_div) return fail("plain NHWC epilogue only");
+  if (d.epi.ld_out % 4 || (d.epi.residual && d.epi.ld_res % 4)) return fail("output pitch must be a multiple of 4 elements");
+  if (d.epi.round_tf32 == 2 && d.epi.ld_out % 8) return fail("fp16 output pitch must be a multiple of 8 elements");
+  if (d.epi.rows_per_img != d.H * d.W) return fail("rows_per_img must be H*W");
+  return true;
+}
+
+int tcg_plan_create(const TcgDesc& d, TcgPlan** out) {
+  const char* why = nullptr;
+  B200_REQUIRE(tcg_supported(d, &why), "gemm_tcg: unsupported shape: %s", why ? why : "?");
+  B200_REQUIRE(d.a1 && d.w && d.nimg > 0, "gemm_tcg: null argument");
+  if (int r = tc_configure()) return r;
+  TcgPlan* pl = new TcgPlan();
+  TcgParams& p = pl->prm;
+  memset(&p, 0, sizeof(p));
+  p.src[0] = d.a1; p.srcC[0] = d.C1; p.srcF16[0] = d.a1_f16; p.kch[0] = d.C1 / 64;
+  p.src[1] = d.a2; p.srcC[1] = d.C2; p.srcF16[1] = d.a2_f16; p.kch[1] = d.a2 ? d.C2 / 64 : 0;
+  p.src[2] = d.a3; p.srcC[2] = d.C3; p.srcF16[2] = d.a3_f16; p.kch[2] = d.a3 ? d.C3 / 64 : 0;
+  p.src[3] = d.a4; p.srcC[3] = d.C4; p.srcF16[3] = d.a4_f16; p.kch[3] = d.a4 ? d.C4 / 64 : 0;
+  for (int s = 0; s < 4; ++s)
+    if (p.src[s] && (reinterpret_cast<uintptr_t>(p.src[s]) & 15)) { delete pl; B200_REQUIRE(false, "gemm_tcg: source %d not 16-byte aligned", s); }
+  p.scale = d.gn_scale; p.shift = d.gn_shift; p.Cgn = d.C1 + d.C2; p.act = d.act;
+  p.H = d.H; p.W = d.W; p.R = 128 / d.W;
+  p.N_total = d.N_total; p.tiles_n = d.N_total / 256;
+  p.tiles_m = (long long)d.nimg * d.H * d.W / 128;
+  p.qstats = d.qstats; p.epi = d.epi;
+  {
+    const uint64_t K = (uint64_t)d.C1 + d.C2;
+    uint64_t dims[2] = {K, (uint64_t)9 * d.N_total};
+    uint64_t str[1] = {K * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = encode_map(&p.tmW, d.w, 2, dims, str, box, nullptr, true);
+    p.tmW2 = p.tmW;
+    if (!rc && d.a3) {
+      const uint64_t K3 = (uint64_t)d.C3 + d.C4;
+      uint64_t dims2[2] = {K3, (uint64_t)d.N_total};
+      uint64_t str2[1] = {K3 * 2};
+      rc = encode_map(&p.tmW2, d.w2, 2, dims2, str2, box, nullptr, true);
+    }
+    if (rc) { delete pl; return rc; }
+  }
+  *out = pl;
+  return 0;
+}
+void tcg_plan_destroy(TcgPlan* p) { delete p; }
+void tcg_set_rowvec_ld(TcgPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }
+int tcg_launch(const TcgPlan* pl, cudaStream_t st) {
+  const TcgParams& q = pl->prm;
+  const long long pairs = ((q.tiles_m + 1) / 2) * q.tiles_n;
+  if (pairs == 0) return 0;
+  const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
+  conv_gn2_kernel<<<grid, TG_THREADS, SmemG::TOTAL, st>>>(q);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
 // Opt in to the large dynamic shared-memory carve-out once, outside any stream capture.
 static int tc_configure() {
   static bool configured = false;
@@ -921,6 +993,7 @@ static int tc_configure() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<256, 6>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<true>::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemG::TOTAL));
   configured = true;
   return 0;
 }

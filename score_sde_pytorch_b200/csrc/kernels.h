@@ -14,6 +14,8 @@ int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cu
 int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
                     const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
                     int round_out, float* y, float* raw, cudaStream_t st, int x1_f16 = 0);
+int launch_gn_coeff(int C1, int C2, const double* q1, const double* q2, const float* gamma, const float* beta, int B, int HW,
+                    int G, float eps, float* scale, float* shift, cudaStream_t st);
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
                      int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, int round_out, cudaStream_t st);
@@ -108,6 +110,24 @@ bool tc_attn_supported(int T, int C);
 int tc_attn_plan_create(const TcAttnDesc& d, TcAttnPlan** out);
 void tc_attn_plan_destroy(TcAttnPlan* p);
 int tc_attn_launch(const TcAttnPlan* p, cudaStream_t st);
+// 3x3 convolution with GroupNorm (+SiLU) applied on load (gemm_tcg.cuh): fp16 operands, CTA pairs, W in {16, 32}
+struct TcgPlan;
+struct TcgDesc {
+  // 3x3 phase: up to two channel-concatenated NHWC sources (fp32 or fp16 elements), normalised on load
+  const void* a1; int C1; int a1_f16; const void* a2; int C2; int a2_f16;
+  const float* gn_scale; const float* gn_shift;   // [nimg][C1+C2] from launch_gn_coeff (both null: identity)
+  int act;                                        // SiLU after the affine
+  int H, W, nimg;
+  const float* w; int N_total;                    // fp16 [9][N_total][C1+C2]
+  // optional extra 1x1 phase (skip projection): out += [a3 | a4] w2^T, sources converted to fp16 on load
+  const void* a3; int C3; int a3_f16; const void* a4; int C4; int a4_f16; const float* w2;   // w2: fp16 [N_total][C3+C4]
+  double* qstats;
+  Epilogue epi;
+};
+bool tcg_supported(const TcgDesc& d, const char** why);
+int tcg_plan_create(const TcgDesc& d, TcgPlan** out);
+void tcg_plan_destroy(TcgPlan* p);
+int tcg_launch(const TcgPlan* p, cudaStream_t st);
 void tc_gemm_set_head(TcGemmPlan* p, float* out_nchw, const float* per_img_div, long long div_stride);   // per-call pointers of the NCHW head
 const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap"
 
