@@ -95,7 +95,7 @@ B200_API int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, c
 /* ---- NCSN++ score network ----------------------------------------------------
  * Replaces models/ncsnpp.py:38-381 (+ models/layerspp.py, models/layers.py:29-124,515-555,
  * models/up_or_down_sampling.py, op/) for configurations with Fourier embedding,
- * BigGAN residual blocks, FIR resampling, progressive='none' and
+ * (or positional) embedding, BigGAN residual blocks, FIR or naive resampling, progressive='none' and
  * progressive_input in {'none','residual'}.  forward(x[B,C,H,W], time_cond[B]) -> [B,C,H,W]
  * like NCSNpp.forward (models/ncsnpp.py:232). */
 typedef struct b200_ncsnpp b200_ncsnpp_t;
@@ -119,6 +119,11 @@ typedef struct {
                                  * as the checked alternative); 0: in fp16 operand mode GroupNorm+SiLU is applied ON LOAD by
                                  * the consuming 3x3 convolution (csrc/gemm_tcg.cuh) wherever the shape allows
                                  * (256-channel outputs at 16x16 / 32x32), so the normalised tensor never reaches HBM */
+  int embedding_type;           /* 0: Gaussian Fourier features of log(sigma) (layerspp.py:32-41, all_modules[0].W); 1: sinusoidal
+                                 * positional embedding of the time label (layers.py:515-529, ncsnpp.py:242-247): no module,
+                                 * the frequency table is the pseudo-parameter "pos_freqs" [nf/2] */
+  int naive_resample;           /* 0: FIR up/down-sampling in the resblocks (fir=True); 1: nearest-neighbour 2x upsampling and
+                                 * 2x2 mean downsampling (fir=False, up_or_down_sampling.py:59-69; the DDPM++ family) */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

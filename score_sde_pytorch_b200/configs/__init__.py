@@ -101,3 +101,40 @@ def tiny_ncsnpp(nf=32, image_size=16, num_res_blocks=1, ch_mult=(1, 2), attn_res
   c.model.init_scale = 1.0
   c.data.image_size = image_size
   return c
+
+
+def vp_cifar10_ddpmpp_continuous():
+  """``configs/vp/cifar10_ddpmpp_continuous.py:21-63`` — DDPM++ cont. (VP): naive 2x resampling (``fir=False``),
+  sinusoidal positional time embedding, no input pyramid, centred data, Euler-Maruyama predictor only."""
+  c = ve_cifar10_ncsnpp_continuous()
+  c.training.sde = 'vpsde'
+  c.training.reduce_mean = True
+  c.sampling.predictor = 'euler_maruyama'
+  c.sampling.corrector = 'none'
+  c.data.centered = True
+  m = c.model
+  m.scale_by_sigma = False
+  m.ema_rate = 0.9999
+  m.fir = False
+  m.progressive_input = 'none'
+  m.embedding_type = 'positional'
+  return c
+
+
+def subvp_cifar10_ddpmpp_continuous():
+  """``configs/subvp/cifar10_ddpmpp_continuous.py`` — the same network under the sub-VP SDE."""
+  c = vp_cifar10_ddpmpp_continuous()
+  c.training.sde = 'subvpsde'
+  return c
+
+
+def tiny_ddpmpp(nf=32, image_size=16, num_res_blocks=1, ch_mult=(1, 2), attn_resolutions=(8,)):
+  """A small DDPM++ of the same family (test fixture sized; not a reference config)."""
+  c = vp_cifar10_ddpmpp_continuous()
+  c.model.nf = nf
+  c.model.ch_mult = tuple(ch_mult)
+  c.model.num_res_blocks = num_res_blocks
+  c.model.attn_resolutions = tuple(attn_resolutions)
+  c.model.init_scale = 1.0
+  c.data.image_size = image_size
+  return c

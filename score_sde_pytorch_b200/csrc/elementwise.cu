@@ -658,20 +658,24 @@ int launch_softmax_rows(const float* s, float* p, long long rows, int T, float s
 // fourier: emb[r] = [sin(p), cos(p)], p = ((log(sigma_r) * W_j) * 2) * fp32(pi) with the
 // reference's operation order; accurate sinf/cosf/logf (phases reach ~1e3 rad).
 // ============================================================================
+// positional != 0: sinusoidal embedding of the label itself (models/layers.py:515-529): emb = [sin(t f_j), cos(t f_j)],
+// f = exp(-j log(10000) / (half - 1)) precomputed by the host with the reference's torch ops; W then holds `nf` = half
+// frequencies and a row of emb has 2 * nf entries.
 __global__ void fourier_embed_kernel(const float* __restrict__ sigma, long long sigma_stride,
-                                     const float* __restrict__ W, int nf, float* __restrict__ emb) {
+                                     const float* __restrict__ W, int nf, float* __restrict__ emb, int positional) {
   const int r = blockIdx.x;
-  const float lv = logf(sigma[r * sigma_stride]);
+  const float t = sigma[r * sigma_stride];
+  const float lv = positional ? t : logf(t);
   for (int j = threadIdx.x; j < nf; j += blockDim.x) {
-    const float ph = ((lv * W[j]) * 2.0f) * 3.14159265358979323846f;
+    const float ph = positional ? lv * W[j] : ((lv * W[j]) * 2.0f) * 3.14159265358979323846f;
     emb[(long long)r * 2 * nf + j] = sinf(ph);
     emb[(long long)r * 2 * nf + nf + j] = cosf(ph);
   }
 }
 
 int launch_fourier_embed(const float* sigma, long long sigma_stride, const float* W, int nf, int rows,
-                         float* emb, cudaStream_t st) {
-  fourier_embed_kernel<<<rows, 128, 0, st>>>(sigma, sigma_stride, W, nf, emb);
+                         float* emb, cudaStream_t st, int positional) {
+  fourier_embed_kernel<<<rows, 128, 0, st>>>(sigma, sigma_stride, W, nf, emb, positional);
   B200_CHECK_LAUNCH();
   return 0;
 }

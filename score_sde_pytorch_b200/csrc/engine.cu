@@ -186,7 +186,11 @@ int build_graph(b200_ncsnpp* e) {
   std::vector<int> all_res(L);
   for (int i = 0; i < L; ++i) all_res[i] = c.image_size >> i;
   auto has_attn = [&](int r) { for (int i = 0; i < c.num_attn_resolutions; ++i) if (c.attn_resolutions[i] == r) return true; return false; };
-  auto nm = [&](const char* suffix) { return "all_modules." + std::to_string((int)e->mods.size()) + "." + suffix; };
+  // The positional embedding has no module in all_modules (ncsnpp.py:79-83): its Mod below takes no index, so every
+  // later module's index is its position in `mods` minus one.
+  const int ishift = c.embedding_type == 1 ? 1 : 0;
+  auto cur = [&]() { return (int)e->mods.size() - ishift; };
+  auto nm = [&](const char* suffix) { return "all_modules." + std::to_string(cur()) + "." + suffix; };
   auto nmi = [&](int idx, const std::string& suffix) { return "all_modules." + std::to_string(idx) + "." + suffix; };
 
   // --- first pass: count Dense_0 rows so their packed rows are contiguous ---
@@ -197,15 +201,24 @@ int build_graph(b200_ncsnpp* e) {
   {  // sigmas buffer is a state_dict key of the reference (ncsnpp.py:42) but unused on this path
     // (it is fp64 there; the host skips it when loading)
   }
-  // 0: Fourier projection
-  { Mod m; m.kind = M_FOURIER; m.index = (int)e->mods.size(); m.w = add_param(e, nm("W"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
-  { Mod m; m.kind = M_LINEAR; m.index = (int)e->mods.size(); m.cin1 = 2 * nf; m.cout = 4 * nf;
-    m.w = add_param(e, nm("weight"), {4 * nf, 2 * nf}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {4 * nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
-  { Mod m; m.kind = M_LINEAR; m.index = (int)e->mods.size(); m.cin1 = 4 * nf; m.cout = 4 * nf;
+  B200_REQUIRE(c.embedding_type == 0 || c.embedding_type == 1, "ncsnpp: embedding_type=%d unknown", c.embedding_type);
+  B200_REQUIRE(!(c.embedding_type == 1 && c.scale_by_sigma), "ncsnpp: positional embedding with scale_by_sigma is not supported");
+  B200_REQUIRE(!(c.naive_resample && c.progressive_input == 1), "ncsnpp: the residual input pyramid needs FIR resampling");
+  // 0: Fourier projection (all_modules[0].W [nf]) or the positional frequency table (pseudo-parameter [nf/2])
+  const int emb_dim = c.embedding_type == 1 ? nf : 2 * nf;
+  if (c.embedding_type == 1) {
+    B200_REQUIRE(nf % 2 == 0 && nf >= 4, "ncsnpp: positional embedding needs an even nf >= 4");
+    Mod m; m.kind = M_FOURIER; m.index = -1; m.w = add_param(e, "pos_freqs", {nf / 2}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m);
+  } else {
+    Mod m; m.kind = M_FOURIER; m.index = cur(); m.w = add_param(e, nm("W"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m);
+  }
+  { Mod m; m.kind = M_LINEAR; m.index = cur(); m.cin1 = emb_dim; m.cout = 4 * nf;
+    m.w = add_param(e, nm("weight"), {4 * nf, emb_dim}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {4 * nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+  { Mod m; m.kind = M_LINEAR; m.index = cur(); m.cin1 = 4 * nf; m.cout = 4 * nf;
     m.w = add_param(e, nm("weight"), {4 * nf, 4 * nf}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {4 * nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
 
   auto add_resblock = [&](int cin1, int cin2, int cout, int up, int down, int res_in) {
-    Mod m; m.kind = M_RESBLOCK; m.index = (int)e->mods.size();
+    Mod m; m.kind = M_RESBLOCK; m.index = cur();
     const int cin = cin1 + cin2;
     m.cin1 = cin1; m.cin2 = cin2; m.cout = cout; m.up = up; m.down = down; m.res = res_in;
     m.has_conv2 = (cin != cout) || up || down;
@@ -233,7 +246,7 @@ int build_graph(b200_ncsnpp* e) {
     e->mods.push_back(m);
   };
   auto add_attn = [&](int C, int res) {
-    Mod m; m.kind = M_ATTN; m.index = (int)e->mods.size(); m.cin1 = C; m.cout = C; m.res = res;
+    Mod m; m.kind = M_ATTN; m.index = cur(); m.cin1 = C; m.cout = C; m.res = res;
     const int T = res * res;
     m.tcattn = tcmode && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
     // fp16 operands: the logits/probabilities never leave the chip, so only the fused core is implemented
@@ -257,7 +270,7 @@ int build_graph(b200_ncsnpp* e) {
   };
 
   // input conv
-  { Mod m; m.kind = M_CONV_IN; m.index = (int)e->mods.size(); m.cin1 = ch; m.cout = nf; m.res = c.image_size;
+  { Mod m; m.kind = M_CONV_IN; m.index = cur(); m.cin1 = ch; m.cout = nf; m.res = c.image_size;
     // on tensor cores the 3x3 input conv is one K=32 contraction over im2col patches: weights packed [nf][32]
     m.tc0 = tcmode && (9 * ch <= 32) && (nf % 128 == 0);
     m.w = m.tc0 ? add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV_FLAT32, 9, nf, ch, om, -1, (long long)nf * 32)
@@ -276,7 +289,7 @@ int build_graph(b200_ncsnpp* e) {
     if (lvl != L - 1) {
       add_resblock(in_ch, 0, in_ch, 0, 1, all_res[lvl]);
       if (c.progressive_input == 1) {
-        Mod m; m.kind = M_PYR_DOWN; m.index = (int)e->mods.size(); m.cin1 = pyr_ch; m.cout = in_ch; m.res = all_res[lvl];
+        Mod m; m.kind = M_PYR_DOWN; m.index = cur(); m.cin1 = pyr_ch; m.cout = in_ch; m.res = all_res[lvl];
         // FIR-padded stride-2 VALID conv: on tcgen05 via TMA element strides when the channel counts tile
         m.tc0 = tc_ok(e, pyr_ch, 0, in_ch, all_res[lvl] / 2, all_res[lvl] / 2, 9);
         // image-channel pyramid level (3 channels): im2col patches + one K=32 contraction, like the input conv
@@ -305,9 +318,9 @@ int build_graph(b200_ncsnpp* e) {
     if (lvl != 0) add_resblock(in_ch, 0, in_ch, 1, 0, all_res[lvl]);
   }
   B200_REQUIRE(hs_c.empty(), "ncsnpp: internal skip-stack mismatch");
-  { Mod m; m.kind = M_GN_OUT; m.index = (int)e->mods.size(); m.cin1 = in_ch;
+  { Mod m; m.kind = M_GN_OUT; m.index = cur(); m.cin1 = in_ch;
     m.w = add_param(e, nm("weight"), {in_ch}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {in_ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
-  { Mod m; m.kind = M_CONV_OUT; m.index = (int)e->mods.size(); m.cin1 = in_ch; m.cout = ch; m.res = c.image_size;
+  { Mod m; m.kind = M_CONV_OUT; m.index = cur(); m.cin1 = in_ch; m.cout = ch; m.res = c.image_size;
     // Head on tensor cores: the ch (3) output channels become rows 0..ch-1 of a zero-padded 128-row weight tile
     // ([9][128][in_ch]; bias padded likewise), run as a swapped-operand convolution whose epilogue stores only those
     // rows, as NCHW, divided by sigma.  2.3x faster than the CUDA-core head despite the 125 idle rows.
@@ -457,12 +470,26 @@ struct Builder {
     }, 0, cflops);
   }
 
+  // 2x resampling of a resblock (layerspp.py:244-256).  fir=True: upsample_2d / downsample_2d with the configured FIR
+  // (up_or_down_sampling.py:218-224, 252-257); fir=False: naive_upsample_2d (nearest-neighbour repeat) and
+  // naive_downsample_2d (2x2 mean) (:59-69), expressed as the same upfirdn2d with a 2x2 box: up=2, pad (1,0), taps 1
+  // -> out[2i] = out[2i+1] = x[i]; down=2, pad (0,0), taps 1/4 -> the mean of each 2x2 cell.
+  void resample2x(const float* x, int H, int C, bool up, int round, float* y) {
+    if (e->cfg.naive_resample) {
+      fir(x, B, H, H, C, up ? 2 : 1, up ? 1 : 2, up ? 1 : 0, 0, round, y, up ? 1.f : 0.25f, /*box=*/true);
+      return;
+    }
+    const int p = e->firn - 2;
+    if (up) fir(x, B, H, H, C, 2, 1, (p + 1) / 2 + 1, p / 2, round, y, 4.f);
+    else fir(x, B, H, H, C, 1, 2, (p + 1) / 2, p / 2, round, y, 1.f);
+  }
+
   void fir(const float* x, int major, int H, int W, int minor, int up, int down, int pad0, int pad1, int round, float* y,
-           float gain) {
+           float gain, bool box = false) {
     // kernel taps scaled by `gain` (x factor^2 when upsampling, up_or_down_sampling.py:220)
-    std::vector<float> k(e->firn * e->firn);
-    for (size_t i = 0; i < k.size(); ++i) k[i] = e->fir2d[i] * gain;
-    const int n = e->firn;
+    std::vector<float> k(box ? 4 : e->firn * e->firn);
+    for (size_t i = 0; i < k.size(); ++i) k[i] = box ? gain : e->fir2d[i] * gain;
+    const int n = box ? 2 : e->firn;
     name("fir up%d down%d %d @%d", up, down, minor == 1 ? major / B : minor, H);
     op(1, [=](cudaStream_t st) {
       return launch_upfirdn2d(x, k.data(), y, major, H, W, minor, n, n, up, up, down, down, pad0, pad1, pad0, pad1, round, st);
@@ -592,15 +619,8 @@ struct Builder {
       Tensor a0r = talloc(Cin, Ho, Ho);
       xr = talloc(Cin, Ho, Ho);
       xr.f16 = m.tc2 && om == 2;
-      if (m.up) {   // upsample_2d: up=2, pad=(2,1), gain*4 (up_or_down_sampling.py:218-224)
-        const int p = e->firn - 2;
-        fir(a0.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc0 ? om : 0, a0r.p, 4.f);
-        fir(x1.p, B, H, H, Cin, 2, 1, (p + 1) / 2 + 1, p / 2, m.tc2 ? om : 0, xr.p, 4.f);
-      } else {      // downsample_2d: down=2, pad=(1,1) (up_or_down_sampling.py:252-257)
-        const int p = e->firn - 2;
-        fir(a0.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc0 ? om : 0, a0r.p, 1.f);
-        fir(x1.p, B, H, H, Cin, 1, 2, (p + 1) / 2, p / 2, m.tc2 ? om : 0, xr.p, 1.f);
-      }
+      resample2x(a0.p, H, Cin, m.up != 0, m.tc0 ? om : 0, a0r.p);
+      resample2x(x1.p, H, Cin, m.up != 0, m.tc2 ? om : 0, xr.p);
       tfree(a0); a0 = a0r;
     }
     Tensor h1 = talloc(m.cout, Ho, Ho);
@@ -744,6 +764,7 @@ struct Builder {
     const int ln = lane;
     // ---- time embedding (ncsnpp.py:236-255) + all Dense_0(act(temb)) rows (layerspp.py:263) ----
     long long eb, t1b, t2b, db, xcb;
+    const int positional = c.embedding_type == 1 ? 1 : 0, emb_dim = positional ? nf : 2 * nf;
     float* emb = falloc((long long)B * 2 * nf, &eb);
     float* t1 = falloc((long long)B * 4 * nf, &t1b);
     float* t2 = falloc((long long)B * 4 * nf, &t2b);
@@ -755,8 +776,8 @@ struct Builder {
       const float *Wd = e->wblob + e->dense_w_off, *bd = e->wblob + e->dense_b_off;
       op(4, [=](cudaStream_t st) {
         const int rows = eng->uniform ? 1 : Bc;
-        if (int r = launch_fourier_embed(eng->in_labels_l[ln], 1, Wf, nf, rows, emb, st)) return r;
-        if (int r = launch_linear_rows(emb, 2 * nf, W1, b1, rows, 4 * nf, 2 * nf, 0, t1, 4 * nf, st)) return r;
+        if (int r = launch_fourier_embed(eng->in_labels_l[ln], 1, Wf, positional ? nf / 2 : nf, rows, emb, st, positional)) return r;
+        if (int r = launch_linear_rows(emb, emb_dim, W1, b1, rows, 4 * nf, emb_dim, 0, t1, 4 * nf, st)) return r;
         if (int r = launch_linear_rows(t1, 4 * nf, W2, b2, rows, 4 * nf, 4 * nf, 1, t2, 4 * nf, st)) return r;
         return launch_linear_rows(t2, 4 * nf, Wd, bd, rows, sumC, 4 * nf, 1, dense_all, sumC, st);
       }, 5);

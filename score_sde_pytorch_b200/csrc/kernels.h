@@ -25,7 +25,7 @@ int launch_fused_bias_act(const float* x, const float* b, const float* ref, floa
 int launch_softmax_rows(const float* s, float* p, long long rows, int T, float scale, int round_out,
                         cudaStream_t st);
 int launch_fourier_embed(const float* sigma, long long sigma_stride, const float* W, int nf, int rows,
-                         float* emb, cudaStream_t st);
+                         float* emb, cudaStream_t st, int positional = 0);
 int launch_linear_rows(const float* x, long long ldx, const float* W, const float* bias, int rows, int N,
                        int K, int act_in, float* y, long long ldy, cudaStream_t st);
 int launch_fill_from_table(const float* table, const int* step, float* dst, int n, cudaStream_t st);

@@ -23,8 +23,9 @@ import torch.nn as nn
 from . import utils
 from .. import _lib
 
-_SUPPORTED = ("engine supports embedding_type='fourier', conditional=True, resblock_type='biggan', fir=True, "
-              "progressive='none', progressive_input in {'none','residual'}")
+_SUPPORTED = ("engine supports embedding_type in {'fourier','positional'}, conditional=True, resblock_type='biggan', "
+              "fir in {True, False} (progressive_input='residual' needs fir=True), progressive='none', "
+              "progressive_input in {'none','residual'}; positional embeddings need scale_by_sigma=False")
 
 
 def _variance_scaling_uniform(shape, scale, in_axis=1, out_axis=0):
@@ -112,14 +113,17 @@ class NCSNpp(nn.Module):
     super().__init__()
     self.config = config
     m = config.model
-    if (m.embedding_type.lower() != 'fourier' or not m.conditional or m.resblock_type.lower() != 'biggan'
-        or not m.fir or m.progressive.lower() != 'none'
-        or m.progressive_input.lower() not in ('none', 'residual')):
+    emb = m.embedding_type.lower()
+    if (emb not in ('fourier', 'positional') or not m.conditional or m.resblock_type.lower() != 'biggan'
+        or m.progressive.lower() != 'none' or m.progressive_input.lower() not in ('none', 'residual')
+        or (not m.fir and m.progressive_input.lower() == 'residual')
+        or (emb == 'positional' and m.scale_by_sigma)):
       raise NotImplementedError(f'NCSNpp: {_SUPPORTED}')
     if m.nonlinearity.lower() != 'swish':
       raise NotImplementedError('NCSNpp: engine implements the swish (SiLU) nonlinearity only')
-    assert config.training.continuous, "Fourier features are only used for continuous training."
+    assert emb != 'fourier' or config.training.continuous, "Fourier features are only used for continuous training."
     self.register_buffer('sigmas', torch.tensor(utils.get_sigmas(config)))   # fp64, as ncsnpp.py:42
+    self.embedding_type = emb
     self.precision = (precision or getattr(m, 'precision', 'tf32')).lower()
     self.keep_activations = bool(keep_activations)
     self.lanes = int(getattr(m, 'lanes', lanes))   # 2: evaluate batches >= 128 as two half-batch lanes on two streams
@@ -132,7 +136,19 @@ class NCSNpp(nn.Module):
     channels = config.data.num_channels
     init_scale = m.init_scale
     temb_dim = nf * 4
-    mods = [_Fourier(nf, m.fourier_scale), _dense(2 * nf, temb_dim), _dense(temb_dim, temb_dim)]
+    if emb == 'fourier':
+      mods = [_Fourier(nf, m.fourier_scale), _dense(2 * nf, temb_dim), _dense(temb_dim, temb_dim)]
+    else:
+      # Sinusoidal embedding of the time label (models/layers.py:515-529): no parameters.  The frequency table is
+      # built with the reference's own torch ops (so the engine multiplies by bit-identical fp32 frequencies) and kept
+      # as a non-persistent buffer: it is not a state_dict key of the reference.
+      mods = [_dense(nf, temb_dim), _dense(temb_dim, temb_dim)]
+      half = nf // 2
+      if nf % 2 or half < 2:
+        raise NotImplementedError('NCSNpp: positional embedding needs an even nf >= 4')
+      import math
+      f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+      self.register_buffer('pos_freqs', f, persistent=False)
     mods.append(_conv(channels, nf, 3))
     hs_c = [nf]
     in_ch, pyr_ch = nf, channels
@@ -197,6 +213,8 @@ class NCSNpp(nn.Module):
     c.lanes = self.lanes
     c.cuda_core_head = int(self.cuda_core_head)
     c.separate_groupnorm = int(self.separate_groupnorm)
+    c.embedding_type = 1 if self.embedding_type == 'positional' else 0
+    c.naive_resample = 0 if m.fir else 1
     return c
 
   def native_param_table(self):
@@ -282,6 +300,8 @@ class NCSNpp(nn.Module):
       self._engine = eng
     if eng['wver'] != self._weights_version:
       sd = dict(self.named_parameters())
+      if self.embedding_type == 'positional':
+        sd['pos_freqs'] = self.pos_freqs
       st = _lib.stream_ptr(device)
       for i, (name, shape) in enumerate(eng['table']):
         p = sd[name]

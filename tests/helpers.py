@@ -31,6 +31,12 @@ def golden_config(name):
     c = configs.ve_cifar10_ncsnpp_continuous()
     c.model.init_scale = 1.0
     return c
+  if name == 'tiny_ddpmpp':
+    return configs.tiny_ddpmpp()
+  if name == 'cifar10_ddpmpp':
+    c = configs.vp_cifar10_ddpmpp_continuous()
+    c.model.init_scale = 1.0
+    return c
   raise KeyError(name)
 
 

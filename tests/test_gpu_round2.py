@@ -258,3 +258,39 @@ def test_cuda_and_cuda0_name_the_same_engine(dev):
   torch.manual_seed(0); torch.cuda.manual_seed(0)
   s2, _ = fn(model)
   assert model._engine['h'].value == h and torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize('batch', [2, 40])
+def test_groupnorm_on_load_convolution_matches_the_separate_pass(dev, batch):
+  """fp16 operand mode: the 256-channel convolutions at 16x16 / 32x32 apply GroupNorm + SiLU while they build their
+  operand (csrc/gemm_tcg.cuh: transform warps, three shifted operand copies, CTA pairs) instead of reading a tensor
+  written by a stand-alone GroupNorm pass.  Both plans round every operand identically (same coefficients, same SiLU,
+  same fp16 rounding), so the whole network must agree to accumulation-order noise, module by module, and the new plan
+  must have fewer launches.  Batch 40 gives every fused launch several tiles per cluster (persistent loop, ring
+  wrap-around, odd tile counts); batch 2 leaves most CTAs idle."""
+  import gpu_util
+  cfg = golden_config('cifar10_ve')
+  sep = seeded_model(cfg, precision='f16', keep_activations=True, separate_groupnorm=True).to(dev)
+  fus = seeded_model(cfg, precision='f16', keep_activations=True).to(dev)
+  sd = {k: v.to(dev) for k, v in sep.state_dict().items()}
+  torch.manual_seed(11)
+  sigma = torch.exp(torch.rand(batch) * 8.5 - 4.6).to(dev)
+  x = (torch.randn(batch, 3, 32, 32) * (sigma.cpu()[:, None, None, None] + 0.5)).to(dev)
+  with torch.no_grad():
+    y0 = sep(x, sigma).clone()
+    y1 = fus(x, sigma).clone()
+    ref = _oracle_net(cfg, sd)(x, sigma)
+  assert fus.launches_per_forward() <= sep.launches_per_forward()
+  worst = 0.0
+  for idx in range(4, 57):
+    try:
+      t0, t1 = sep.tap(idx), fus.tap(idx)
+    except RuntimeError:
+      continue      # module without a recorded activation (pyramid combine)
+    e = rel_l2(t1, t0)
+    worst = max(worst, e)
+    assert e < 1e-4, f'all_modules[{idx}]: GroupNorm-on-load plan differs from the separate-pass plan by {e:.3e}'
+  e_out = rel_l2(y1, y0)
+  print(f'gn-on-load vs separate pass (batch {batch}): worst module {worst:.2e}, output {e_out:.2e}; vs oracle: '
+        f'fused {rel_l2(y1, ref):.3e} separate {rel_l2(y0, ref):.3e}; launches {fus.launches_per_forward()} vs {sep.launches_per_forward()}')
+  assert e_out < 1e-4

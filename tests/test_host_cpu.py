@@ -193,6 +193,30 @@ def test_engine_param_table_matches_module_and_reference_names():
   assert sum(p.numel() for p in seeded_model(golden_config('cifar10_ve')).parameters()) == 62758915
 
 
+def test_ddpmpp_engine_param_table_has_the_reference_names_plus_the_frequency_table():
+  """DDPM++ (fir=False, positional embedding, no pyramid): the positional embedding has no module in the reference's
+  all_modules (ncsnpp.py:79-83), so every later index is one lower than in the Fourier family; the engine's only extra
+  input is the frequency table, which is NOT a state_dict key (non-persistent buffer built with the reference's ops)."""
+  import math
+  for name in ('tiny_ddpmpp', 'cifar10_ddpmpp'):
+    cfg = golden_config(name)
+    m = seeded_model(cfg)
+    table = m.native_param_table()
+    sd = dict(m.named_parameters())
+    assert table[0][0] == 'pos_freqs' and table[0][1] == (cfg.model.nf // 2,)
+    assert sorted(n for n, _ in table[1:]) == sorted(sd)
+    for n, shape in table[1:]:
+      assert tuple(sd[n].shape) == shape
+    assert 'pos_freqs' not in m.state_dict() and 'all_modules.0.weight' in sd and sd['all_modules.0.weight'].shape[1] == cfg.model.nf
+    half = cfg.model.nf // 2
+    want = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    assert torch.equal(m.pos_freqs, want)
+  cfg = golden_config('tiny_ddpmpp')
+  cfg.model.scale_by_sigma = True          # would need sigmas[time_cond.long()] (ncsnpp.py:245): not supported, must say so
+  with pytest.raises(NotImplementedError):
+    seeded_model(cfg)
+
+
 def test_product_model_has_no_cpu_path():
   m = seeded_model(golden_config('tiny'))
   with pytest.raises(RuntimeError, match='CUDA'):

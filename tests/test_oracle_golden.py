@@ -18,7 +18,7 @@ def test_upfirdn2d_oracle_matches_reference(name):
   assert torch.equal(y, torch.from_numpy(g[name + '_y']))
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_vp', 'tiny_noattn'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_vp', 'tiny_noattn', 'tiny_ddpmpp'])
 def test_ncsnpp_oracle_matches_reference(name):
   g = golden(f'ncsnpp_{name}.npz')
   cfg = golden_config(name)
@@ -33,9 +33,10 @@ def test_ncsnpp_oracle_matches_reference(name):
   assert rel_l2(y, torch.from_numpy(g['y'])) < 2e-6
 
 
-def test_ncsnpp_oracle_matches_reference_cifar10():
-  g = golden('ncsnpp_cifar10_ve.npz')
-  cfg = golden_config('cifar10_ve')
+@pytest.mark.parametrize('name', ['cifar10_ve', 'cifar10_ddpmpp'])
+def test_ncsnpp_oracle_matches_reference_cifar10(name):
+  g = golden(f'ncsnpp_{name}.npz')
+  cfg = golden_config(name)
   sd = seeded_model(cfg).state_dict()
   taps = {}
   with torch.no_grad():
@@ -107,6 +108,23 @@ def test_pc_sampler_oracle_matches_reference_none_predictor_and_subvp():
   torch.manual_seed(33)
   s, _ = SO.pc_sample(sde, model, shape, 'reverse_diffusion', 'none', eps=1e-3)
   assert rel_l2(s, torch.from_numpy(g['subvp_rd_none'])) < 1e-5
+
+
+def test_pc_sampler_oracle_matches_reference_ddpmpp():
+  """DDPM++ (tools/make_golden_ddpmpp.py): the config's own sampler - Euler-Maruyama, no corrector -
+  under the VP and sub-VP SDEs, through the reference's get_pc_sampler on the reference's NCSNpp(fir=False,
+  embedding_type='positional')."""
+  g = golden('pc_ddpmpp_tiny.npz')
+  cfg = golden_config('tiny_ddpmpp')
+  model = _OracleModel(cfg)
+  shape = tuple(golden('ncsnpp_tiny_ddpmpp.npz')['x'].shape)
+  torch.manual_seed(41)
+  s, nfe = SO.pc_sample(SO.VP(0.1, 20., 20), model, shape, 'euler_maruyama', 'none', eps=1e-3)
+  assert nfe == int(g['vp_em_none_nfe'])
+  assert rel_l2(s, torch.from_numpy(g['vp_em_none'])) < 1e-5
+  torch.manual_seed(42)
+  s, _ = SO.pc_sample(SO.SubVP(0.1, 20., 20), model, shape, 'euler_maruyama', 'none', eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['subvp_em_none'])) < 1e-5
 
 
 def test_sde_tables_match_reference():
