@@ -200,6 +200,30 @@ B200_API int b200_pc_step_external(b200_pc_t* pc, float* x, float* x_mean, int s
                                    const float* noise_corrector, const float* noise_predictor, void* stream);
 B200_API long long b200_pc_launches_per_step(const b200_pc_t* pc);
 
+/* ---- probability-flow ODE sampler: device-resident Dormand-Prince 5(4) -------------------------
+ * Replaces the host-side state and stage arithmetic of sampling.py:414-485 (scipy.integrate.solve_ivp on a float64
+ * numpy array: two PCIe crossings of the whole state per function evaluation).  The float64 state y, y_new and the
+ * seven stage derivatives K[7][n] stay in device memory; scipy's step-size controller runs on the host
+ * (score_sde_pytorch_b200/ode.py) and reads back one double per attempted step.  All pointers are device pointers
+ * except coef_host / e_host (<= 8 doubles, passed by value into the launch). */
+/* y_stage = y + h * sum_{j<nk} coef[j] * K[j] (float64; nk = 0: y itself); optional float64 copy (y_out) and float32
+ * copy (x32: the network input, `.type(torch.float32)` in the reference's ode_func) */
+B200_API int b200_ode_stage_f64(const double* y, const double* k, long long n, const double* coef_host, int nk, double h,
+                                double* y_out, float* x32, void* stream);
+/* K_s = (double) drift, drift = c_f * x32 - (g2 * score) * 0.5f, score = std > 0 ? -(net_out / std) : net_out, in unfused
+ * fp32 like rsde.sde with probability_flow=True (sde_lib.py:93-100) over get_score_fn (models/utils.py:129-178);
+ * scalars_dev = {c_f, g2, std} */
+B200_API int b200_ode_drift_f64(const float* x32, const float* net_out, long long n, const float* scalars_dev, double* k_out,
+                                void* stream);
+/* ws[0] = sum_i ((h * sum_{j<nk} e[j] K[j][i]) / (atol + max(|y_i|, |y_new_i|) * rtol))^2   (RungeKutta._estimate_error_norm);
+ * ws: b200_ode_workspace_doubles() doubles; deterministic two-pass reduction */
+B200_API long long b200_ode_workspace_doubles(void);
+B200_API int b200_ode_error_sumsq_f64(const double* y, const double* y_new, const double* k, long long n, const double* e_host,
+                                      int nk, double h, double rtol, double atol, double* ws, void* stream);
+/* ws[0] = sum_i (((v - v2)_i) / (atol + |y0_i| * rtol))^2, v2 optional: the three norms of scipy's select_initial_step */
+B200_API int b200_ode_scaled_sumsq_f64(const double* v, const double* v2, const double* y0, long long n, double rtol, double atol,
+                                       double* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

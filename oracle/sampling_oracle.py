@@ -177,3 +177,27 @@ def pc_sample(sde, model, shape, predictor='reverse_diffusion', corrector='lange
       if trace is not None:
         trace.append(x.clone())
     return (x_mean if denoise else x), sde.N * (n_steps + 1)
+
+
+def ode_sample(sde, model, shape, z=None, denoise=False, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3, device='cpu'):
+  """sampling.py:414-485 (get_ode_sampler / ode_sampler): the probability-flow ODE integrated with scipy's solve_ivp on
+  a flattened float64 numpy state; the right-hand side (``drift_fn``, :443-447) is ``rsde.sde(x, t)[0]`` with
+  ``probability_flow=True`` (sde_lib.py:93-100) on the float32 state; optional one-step denoise (:433-441) with the
+  reverse-diffusion predictor at ``t = eps``.  Returns ``(x, nfev)``."""
+  from scipy import integrate
+  with torch.no_grad():
+    x = (sde.prior_sampling(shape) if z is None else z).to(device)
+
+    def ode_func(t, flat):
+      xt = torch.from_numpy(flat.reshape(shape)).to(device).type(torch.float32)                 # :460-461
+      vec_t = torch.ones(shape[0], device=xt.device) * t                                        # :462
+      drift, diffusion = sde.sde(xt, vec_t)
+      drift = drift - diffusion[:, None, None, None] ** 2 * sde.score(model, xt, vec_t, True) * 0.5
+      return drift.detach().cpu().numpy().reshape((-1,))                                        # :464
+
+    sol = integrate.solve_ivp(ode_func, (sde.T, eps), x.detach().cpu().numpy().reshape((-1,)), rtol=rtol, atol=atol, method=method)
+    x = torch.tensor(sol.y[:, -1]).reshape(shape).to(device).type(torch.float32)                # :469
+    if denoise:                                                                                 # :472-473
+      vec_eps = torch.ones(shape[0], device=x.device) * eps
+      _, x = reverse_diffusion_step(sde, model, x, vec_eps, continuous=True, probability_flow=False)
+    return x, sol.nfev

@@ -60,7 +60,7 @@ struct TcgParams {
 
 __device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 v;
-  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
@@ -71,56 +71,93 @@ __device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
 __device__ __forceinline__ void transform_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_NTW) : "memory"); }
 __device__ __forceinline__ float silu_approx(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // == silu_fast (elementwise.cu)
 
-// eight consecutive channels of one pixel -> eight fp16 (four packed words)
-template <bool F16IN, bool AFFINE, bool ACT>
-__device__ __forceinline__ uint4 transform8(const void* gp, const float (&sc)[8], const float (&sh)[8]) {
+// eight consecutive channels of one pixel: raw bits as loaded (fp32: 32 B in a|b, fp16: 16 B in a)
+struct Raw8 { uint4 a, b; };
+template <bool F16IN>
+__device__ __forceinline__ Raw8 load_raw8(const void* gp) {
+  Raw8 r;
+  r.a = ldg128(gp);
+  r.b = F16IN ? make_uint4(0u, 0u, 0u, 0u) : ldg128(reinterpret_cast<const uint8_t*>(gp) + 16);
+  return r;
+}
+// -> eight fp16 (four packed words) after the affine (GroupNorm; scale 1 / shift 0 is the exact identity) and the
+// optional SiLU, computed in fp32
+template <bool F16IN>
+__device__ __forceinline__ uint4 apply8(const Raw8& r, const float (&sc)[8], const float (&sh)[8], bool act) {
   float v[8];
-  if (F16IN) {
-    const uint4 u = ldg128(gp);
-    if constexpr (!AFFINE && !ACT) return u;
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  if constexpr (F16IN) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
       v[2 * i] = f.x; v[2 * i + 1] = f.y;
     }
   } else {
-    const uint4 a = ldg128(gp), b = ldg128(reinterpret_cast<const uint8_t*>(gp) + 16);
-    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
-    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (AFFINE) v[i] = fmaf(v[i], sc[i], sh[i]);
-    if (ACT) v[i] = silu_approx(v[i]);
+  for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = silu_approx(v[i]);
   }
   return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
 // Build "copy 0" of one chunk: `rows` pixel rows starting at patch row 0 (image row ih0 = first image row of the
 // patch, may be -1; rows outside [0, H) are zero).  Thread `tid` (0..127) owns channel octet tid & 7 of pixel rows
-// (tid >> 3) + 16 j.
-template <bool F16IN, bool AFFINE, bool ACT>
+// (tid >> 3) + 16 j.  Software-pipelined in batches of four pixels per thread: the loads of batch b+1 are in flight
+// while batch b is transformed and stored (the first version loaded, transformed and stored batch by batch and was
+// bound by global-load latency: 16 KB in flight per SM for a third of the time, fused convolutions 2.3x slower than the
+// unfused pair, profiles/r02_g1_*).
+template <bool F16IN>
 __device__ __forceinline__ void build_copy0(uint32_t slot, const uint8_t* src_img, int C, int c0, int ih0, int H, int W, int rows,
-                                            const float (&sc)[8], const float (&sh)[8], int tid, bool tile_valid) {
+                                            const float (&sc)[8], const float (&sh)[8], bool act, int tid, bool tile_valid) {
   const int o = tid & 7;
   const int esz = F16IN ? 2 : 4;
   const int wshift = W == 32 ? 5 : 4;                     // W is 16 or 32
-  for (int pp0 = tid >> 3; pp0 < rows; pp0 += 64) {
-    uint4 r[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int pp = pp0 + 16 * u;
-      const int hh = pp >> wshift, w = pp & (W - 1), ih = ih0 + hh;
-      r[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (pp < rows && tile_valid && ih >= 0 && ih < H)
-        r[u] = transform8<F16IN, AFFINE, ACT>(src_img + ((long long)(ih * W + w) * C + c0) * esz, sc, sh);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int pp = pp0 + 16 * u;
-      if (pp < rows) sts128(slot + pp * 128 + ((o ^ (pp & 7)) << 4), r[u].x, r[u].y, r[u].z, r[u].w);
-    }
+  const uint32_t cb = (uint32_t)c0 * esz, pixb = (uint32_t)C * esz;
+  // item j of this thread: pixel row pp = (tid >> 3) + 16 j; two items per batch, two batches in flight
+  const int nitems = (rows - (tid >> 3) + 15) >> 4;
+  Raw8 a0, a1, b0, b1;
+  bool va0 = false, va1 = false, vb0 = false, vb1 = false;
+#define B200_TG_FETCH(J, R, V)                                                                   \
+  do {                                                                                           \
+    const int pp_ = (tid >> 3) + 16 * (J);                                                       \
+    const int ih_ = ih0 + (pp_ >> wshift);                                                       \
+    V = (J) < nitems && tile_valid && ih_ >= 0 && ih_ < H;                                       \
+    if (V) R = load_raw8<F16IN>(src_img + ((uint32_t)(ih_ * W + (pp_ & (W - 1))) * pixb + cb));   \
+  } while (0)
+#define B200_TG_EMIT(J, R, V)                                                                    \
+  do {                                                                                           \
+    if ((J) < nitems) {                                                                          \
+      const int pp_ = (tid >> 3) + 16 * (J);                                                     \
+      uint4 v_ = make_uint4(0u, 0u, 0u, 0u);                                                     \
+      if (V) v_ = apply8<F16IN>(R, sc, sh, act);                                                \
+      sts128(slot + pp_ * 128 + ((o ^ (pp_ & 7)) << 4), v_.x, v_.y, v_.z, v_.w);                 \
+    }                                                                                            \
+  } while (0)
+  B200_TG_FETCH(0, a0, va0); B200_TG_FETCH(1, a1, va1);
+#pragma unroll 1
+  for (int j = 0; j < nitems; j += 4) {
+    B200_TG_FETCH(j + 2, b0, vb0); B200_TG_FETCH(j + 3, b1, vb1);
+    B200_TG_EMIT(j, a0, va0); B200_TG_EMIT(j + 1, a1, va1);
+    B200_TG_FETCH(j + 4, a0, va0); B200_TG_FETCH(j + 5, a1, va1);
+    B200_TG_EMIT(j + 2, b0, vb0); B200_TG_EMIT(j + 3, b1, vb1);
+  }
+#undef B200_TG_FETCH
+#undef B200_TG_EMIT
+}
+// Pull the (R+2) x W patch of ALL channels of one source towards L2 (fire-and-forget, no registers): issued for the
+// NEXT tile while the current one is transformed, so build_copy0's loads pay L2 latency instead of HBM latency.
+__device__ __forceinline__ void prefetch_patch(const uint8_t* src_img, int C, int esz, int ih0, int H, int W, int rows_img, int tid) {
+  const int row_bytes = W * C * esz;                         // one image row, contiguous in NHWC
+  for (int hh = 0; hh < rows_img; ++hh) {
+    const int ih = ih0 + hh;
+    if (ih < 0 || ih >= H) continue;
+    const uint8_t* base = src_img + (long long)ih * row_bytes;
+    for (int off = tid * 128; off < row_bytes; off += 32 * TG_NTW * 128) prefetch_l2(base + off);
   }
 }
 // dst[hh][w] = copy0[hh][w + d] (zero where w + d leaves the row), d = -1 or +1
@@ -302,6 +339,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
       const long long p0 = mg * BM;
       const int img = valid ? (int)(p0 / HW) : 0;
       const int h0 = valid ? (int)(p0 % HW) / p.W : 0;
+      {   // the next tile's input patches -> L2 while this tile is being transformed
+        const long long pn = pair + nclusters;
+        const long long mgn = (pn / p.tiles_n) * 2 + rank;
+        if (pn < total_pairs && mgn < p.tiles_m) {
+          const long long pn0 = mgn * BM;
+          const int imgn = (int)(pn0 / HW), hn = (int)(pn0 % HW) / p.W;
+          for (int src = 0; src < 4; ++src) {
+            if (p.kch[src] == 0) continue;
+            const int esz = p.srcF16[src] ? 2 : 4;
+            prefetch_patch(reinterpret_cast<const uint8_t*>(p.src[src]) + (long long)imgn * HW * p.srcC[src] * esz, p.srcC[src], esz,
+                           src < 2 ? hn - 1 : hn, p.H, p.W, src < 2 ? p.R + 2 : p.R, tid);
+          }
+        }
+      }
       // ---- 3x3 phase: GroupNorm (+SiLU) on load, three shifted copies per chunk ----
       for (int src = 0; src < 2; ++src) {
         const int nch = p.kch[src];
@@ -325,15 +376,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
           }
           const uint32_t s0 = ts, s0addr = t_base + ts * TG_SLOT_BYTES;
           mbar_wait(&tempty[ts], tphase ^ 1);
-          if (p.scale) {
-            if (p.act) { if (f16in) build_copy0<true, true, true>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, tid, valid);
-                         else build_copy0<false, true, true>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, tid, valid); }
-            else { if (f16in) build_copy0<true, true, false>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, tid, valid);
-                   else build_copy0<false, true, false>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, tid, valid); }
-          } else {
-            if (f16in) build_copy0<true, false, false>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, tid, valid);
-            else build_copy0<false, false, false>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, tid, valid);
-          }
+          if (f16in) build_copy0<true>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, p.act != 0 && p.scale, tid, valid);
+          else build_copy0<false>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, p.act != 0 && p.scale, tid, valid);
           next_slot();
           fence_async_smem();
           transform_bar();                       // copy 0 complete: neighbours' pixels are readable
@@ -362,12 +406,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
         const int C = p.srcC[src];
         const bool f16in = p.srcF16[src] != 0;
         const uint8_t* img_base = reinterpret_cast<const uint8_t*>(p.src[src]) + (long long)img * HW * C * (f16in ? 2 : 4);
-        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int kc = 0; kc < nch; ++kc) {
           const int c0 = kc * 64 + o * 8;
           mbar_wait(&tempty[ts], tphase ^ 1);
-          if (f16in) build_copy0<true, false, false>(t_base + ts * TG_SLOT_BYTES, img_base, C, c0, h0, p.H, p.W, BM, one, one, tid, valid);
-          else build_copy0<false, false, false>(t_base + ts * TG_SLOT_BYTES, img_base, C, c0, h0, p.H, p.W, BM, one, one, tid, valid);
+          if (f16in) build_copy0<true>(t_base + ts * TG_SLOT_BYTES, img_base, C, c0, h0, p.H, p.W, BM, one, zero, false, tid, valid);
+          else build_copy0<false>(t_base + ts * TG_SLOT_BYTES, img_base, C, c0, h0, p.H, p.W, BM, one, zero, false, tid, valid);
           publish(ts);
           next_slot();
         }

@@ -264,11 +264,14 @@ def test_cuda_and_cuda0_name_the_same_engine(dev):
 def test_groupnorm_on_load_convolution_matches_the_separate_pass(dev, batch):
   """fp16 operand mode: the 256-channel convolutions at 16x16 / 32x32 apply GroupNorm + SiLU while they build their
   operand (csrc/gemm_tcg.cuh: transform warps, three shifted operand copies, CTA pairs) instead of reading a tensor
-  written by a stand-alone GroupNorm pass.  Both plans round every operand identically (same coefficients, same SiLU,
-  same fp16 rounding), so the whole network must agree to accumulation-order noise, module by module, and the new plan
-  must have fewer launches.  Batch 40 gives every fused launch several tiles per cluster (persistent loop, ring
-  wrap-around, odd tile counts); batch 2 leaves most CTAs idle."""
-  import gpu_util
+  written by a stand-alone GroupNorm pass.  Both plans round every operand the same way (same coefficients, same SiLU,
+  same fp16 rounding) but accumulate in a different order, and a 1e-6 difference in an fp32 accumulator flips the fp16
+  rounding of ~1 % of the mid-block elements by one ulp (1e-3): the plans therefore agree to a few 1e-4 per module, not
+  bit for bit (measured 2.9e-4 at all_modules[12]).  A real defect - a wrong halo column, a stale operand copy, a mis-ordered
+  filter tap - shows up at 1e-2 .. 1.  So: every module of the fused plan within 2e-3 of the separate-pass plan, and its
+  error against the strict-fp32 oracle no worse than the separate plan's (x1.25 + 1e-4), module by module.
+  Batch 40 gives every fused launch several tiles per cluster (persistent loop, ring wrap-around, odd tile counts);
+  batch 2 leaves most CTAs idle."""
   cfg = golden_config('cifar10_ve')
   sep = seeded_model(cfg, precision='f16', keep_activations=True, separate_groupnorm=True).to(dev)
   fus = seeded_model(cfg, precision='f16', keep_activations=True).to(dev)
@@ -276,21 +279,27 @@ def test_groupnorm_on_load_convolution_matches_the_separate_pass(dev, batch):
   torch.manual_seed(11)
   sigma = torch.exp(torch.rand(batch) * 8.5 - 4.6).to(dev)
   x = (torch.randn(batch, 3, 32, 32) * (sigma.cpu()[:, None, None, None] + 0.5)).to(dev)
+  taps = {}
   with torch.no_grad():
     y0 = sep(x, sigma).clone()
     y1 = fus(x, sigma).clone()
-    ref = _oracle_net(cfg, sd)(x, sigma)
+    ref = torch.cat([NO.ncsnpp_forward(sd, cfg, x[i:i + 8], sigma[i:i + 8], taps=(taps if i == 0 else None)) for i in range(0, batch, 8)])
+  nb = min(batch, 8)          # oracle activations are kept for the first chunk of images only
   assert fus.launches_per_forward() <= sep.launches_per_forward()
-  worst = 0.0
-  for idx in range(4, 57):
+  rows = []
+  for idx in sorted(taps):
     try:
-      t0, t1 = sep.tap(idx), fus.tap(idx)
+      t0, t1 = sep.tap(idx)[:nb], fus.tap(idx)[:nb]
     except RuntimeError:
       continue      # module without a recorded activation (pyramid combine)
-    e = rel_l2(t1, t0)
-    worst = max(worst, e)
-    assert e < 1e-4, f'all_modules[{idx}]: GroupNorm-on-load plan differs from the separate-pass plan by {e:.3e}'
-  e_out = rel_l2(y1, y0)
-  print(f'gn-on-load vs separate pass (batch {batch}): worst module {worst:.2e}, output {e_out:.2e}; vs oracle: '
-        f'fused {rel_l2(y1, ref):.3e} separate {rel_l2(y0, ref):.3e}; launches {fus.launches_per_forward()} vs {sep.launches_per_forward()}')
-  assert e_out < 1e-4
+    o = taps[idx]
+    rows.append((idx, rel_l2(t1, t0), rel_l2(t1, o), rel_l2(t0, o)))
+  worst = max(rows, key=lambda r: r[1])
+  print(f'gn-on-load vs separate pass (batch {batch}): worst module {worst[0]}: {worst[1]:.2e} (vs oracle fused {worst[2]:.2e} / separate {worst[3]:.2e}); '
+        f'output fused-vs-separate {rel_l2(y1, y0):.2e}, vs oracle fused {rel_l2(y1, ref):.3e} separate {rel_l2(y0, ref):.3e}; '
+        f'launches {fus.launches_per_forward()} vs {sep.launches_per_forward()}')
+  for idx, e_fs, e_f, e_s in rows:
+    assert e_fs < 2e-3, f'all_modules[{idx}]: GroupNorm-on-load plan differs from the separate-pass plan by {e_fs:.3e}'
+    assert e_f < 1.25 * e_s + 1e-4, f'all_modules[{idx}]: fused plan {e_f:.3e} vs oracle, separate plan {e_s:.3e}'
+  assert rel_l2(y1, y0) < 2e-3
+  assert rel_l2(y1, ref) < 1.25 * rel_l2(y0, ref) + 1e-4

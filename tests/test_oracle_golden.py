@@ -127,6 +127,22 @@ def test_pc_sampler_oracle_matches_reference_ddpmpp():
   assert rel_l2(s, torch.from_numpy(g['subvp_em_none'])) < 1e-5
 
 
+@pytest.mark.parametrize('case', ['ve', 'vp', 'subvp'])
+def test_ode_sampler_oracle_matches_reference(case):
+  """SURVEY 8 f3 pin (tools/make_golden_ode.py): the reference's get_ode_sampler (scipy RK45, rtol = atol = 1e-5) on the
+  reference's own networks; the sub-VP case with the one-step denoise."""
+  g = golden('ode_tiny.npz')
+  name, sde, eps, denoise = {'ve': ('tiny', SO.VE(0.01, 50, 1000), 1e-5, False),
+                             'vp': ('tiny_ddpmpp', SO.VP(0.1, 20., 1000), 1e-3, False),
+                             'subvp': ('tiny_ddpmpp', SO.SubVP(0.1, 20., 1000), 1e-3, True)}[case]
+  model = _OracleModel(golden_config(name))
+  z = torch.from_numpy(g[case + '_z'])
+  torch.manual_seed(52)
+  s, nfe = SO.ode_sample(sde, model, tuple(z.shape), z=z.clone(), denoise=denoise, eps=eps)
+  assert nfe == int(g[case + '_nfe'])
+  assert rel_l2(s, torch.from_numpy(g[case])) < 1e-5
+
+
 def test_sde_tables_match_reference():
   g = golden('sde_tables.npz')
   ve = SO.VE(0.01, 50, 1000)
