@@ -25,16 +25,16 @@
 // identity transform: fp32 block input -> fp16 operand, one un-shifted 128-row copy per chunk, so the rounded copy of
 // the block input that the GroupNorm pass used to write is gone as well.
 //
-// Roles per CTA (512 threads): warp 0 lane 0 weight TMA producer (both CTAs), warp 1 lane 0 of the leader issues
+// Roles per CTA (640 threads; setmaxnreg moves registers from the producer / issuer warpgroup to the epilogue warpgroups): warp 0 lane 0 weight TMA producer (both CTAs), warp 1 lane 0 of the leader issues
 // tcgen05.mma.cta_group::2 for the pair, warp 2 TMEM allocation, warps 4..11 epilogue (identical to gemm_tc2_kernel),
-// warps 12..15 transform.  Barriers: wfull/wempty (weight ring), tfull/tempty (ring of operand copies; tfull lives in
+// warps 12..19 transform.  Barriers: wfull/wempty (weight ring), tfull/tempty (ring of operand copies; tfull lives in
 // the leader and counts one arrival per transform warp of BOTH CTAs), tmem_full/tmem_empty.
 
 constexpr int TG_TS = 5;                    // operand-copy slots (three per chunk in flight + two being built)
 constexpr int TG_WS = 4;                    // weight ring stages
 constexpr int TG_SLOT_BYTES = 192 * 128;    // (R+2)*W <= 192 pixel rows of 64 fp16 channels
 constexpr int TG_W_BYTES = 128 * 128;       // this CTA's 128 of the 256 output channels x 64 k
-constexpr int TG_NTW = 4;                   // transform warps per CTA
+constexpr int TG_NTW = 8;                   // transform warps per CTA (two warpgroups)
 constexpr int TG_THREADS = 384 + 32 * TG_NTW;
 
 struct SmemG {
@@ -68,7 +68,6 @@ __device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
 }
-__device__ __forceinline__ void transform_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_NTW) : "memory"); }
 __device__ __forceinline__ float silu_approx(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // == silu_fast (elementwise.cu)
 
 // eight consecutive channels of one pixel: raw bits as loaded (fp32: 32 B in a|b, fp16: 16 B in a)
@@ -82,8 +81,11 @@ __device__ __forceinline__ Raw8 load_raw8(const void* gp) {
 }
 // -> eight fp16 (four packed words) after the affine (GroupNorm; scale 1 / shift 0 is the exact identity) and the
 // optional SiLU, computed in fp32
+struct Coef8 { float4 s0, s1, h0, h1; };      // scale[0..7], shift[0..7] of this thread's channel octet
 template <bool F16IN>
-__device__ __forceinline__ uint4 apply8(const Raw8& r, const float (&sc)[8], const float (&sh)[8], bool act) {
+__device__ __forceinline__ uint4 apply8(const Raw8 r, const Coef8 cf, bool act) {
+  const float sc[8] = {cf.s0.x, cf.s0.y, cf.s0.z, cf.s0.w, cf.s1.x, cf.s1.y, cf.s1.z, cf.s1.w};
+  const float sh[8] = {cf.h0.x, cf.h0.y, cf.h0.z, cf.h0.w, cf.h1.x, cf.h1.y, cf.h1.z, cf.h1.w};
   float v[8];
   if constexpr (F16IN) {
     const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
@@ -105,48 +107,42 @@ __device__ __forceinline__ uint4 apply8(const Raw8& r, const float (&sc)[8], con
   return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
-// Build "copy 0" of one chunk: `rows` pixel rows starting at patch row 0 (image row ih0 = first image row of the
-// patch, may be -1; rows outside [0, H) are zero).  Thread `tid` (0..127) owns channel octet tid & 7 of pixel rows
-// (tid >> 3) + 16 j.  Software-pipelined in batches of four pixels per thread: the loads of batch b+1 are in flight
-// while batch b is transformed and stored (the first version loaded, transformed and stored batch by batch and was
-// bound by global-load latency: 16 KB in flight per SM for a third of the time, fused convolutions 2.3x slower than the
-// unfused pair, profiles/r02_g1_*).
-template <bool F16IN>
-__device__ __forceinline__ void build_copy0(uint32_t slot, const uint8_t* src_img, int C, int c0, int ih0, int H, int W, int rows,
-                                            const float (&sc)[8], const float (&sh)[8], bool act, int tid, bool tile_valid) {
-  const int o = tid & 7;
-  const int esz = F16IN ? 2 : 4;
-  const int wshift = W == 32 ? 5 : 4;                     // W is 16 or 32
-  const uint32_t cb = (uint32_t)c0 * esz, pixb = (uint32_t)C * esz;
-  // item j of this thread: pixel row pp = (tid >> 3) + 16 j; two items per batch, two batches in flight
-  const int nitems = (rows - (tid >> 3) + 15) >> 4;
-  Raw8 a0, a1, b0, b1;
-  bool va0 = false, va1 = false, vb0 = false, vb1 = false;
-#define B200_TG_FETCH(J, R, V)                                                                   \
-  do {                                                                                           \
-    const int pp_ = (tid >> 3) + 16 * (J);                                                       \
-    const int ih_ = ih0 + (pp_ >> wshift);                                                       \
-    V = (J) < nitems && tile_valid && ih_ >= 0 && ih_ < H;                                       \
-    if (V) R = load_raw8<F16IN>(src_img + ((uint32_t)(ih_ * W + (pp_ & (W - 1))) * pixb + cb));   \
+// One chunk of the operand for one transform thread.  The patch is a CONTIGUOUS range of `32 * NI` NHWC pixels starting
+// one image row above the tile, so with 256 transform threads thread t owns channel octet t & 7 of patch pixels
+// pl + 32 j (pl = t >> 3), and everything about an item except j is a per-thread constant: its column w = pl & (W-1)
+// (W divides 32), its swizzle phase pl & 7, hence its shared-memory address in each of the three copies
+// (a0 / a1 / a2 + 4096 j) and its global address (gp + gstep j).  Copy -1 holds T[hh][w-1] at (hh, w): this thread's
+// value goes one pixel row further (pl + 1), except that the thread owning column W-1 writes the zero of column 0
+// instead (W-1 rows back: same swizzle phase); copy +1 mirrored.  Out-of-image halo rows (pixel index outside
+// [0, HW)) are zero in all copies.  Loads run two items ahead of the transform (registers: 2 x 2 x 32 B).
+template <bool F16IN, bool THREE>
+__device__ __forceinline__ void tg_build(int ni, uint32_t a0, uint32_t a1, uint32_t a2, bool z1, bool z2, const uint8_t* gp, uint32_t gstep,
+                                         int pix0, int HW, bool tile_valid, const Coef8 cf, bool act, Raw8 ra0, Raw8 ra1) {
+  Raw8 rb0, rb1;
+  // item j: valid iff its pixel index lies inside the image (halo rows above / below are zero)
+#define B200_TG_VALID(J) (tile_valid && (unsigned)(pix0 + 32 * (J)) < (unsigned)HW)
+#define B200_TG_LOAD(J, R) do { if ((J) < ni && B200_TG_VALID(J)) R = load_raw8<F16IN>(gp + (uint32_t)(J) * gstep); } while (0)
+#define B200_TG_EMIT(J, R)                                                                             \
+  do {                                                                                                 \
+    if ((J) < ni) {                                                                                    \
+      uint4 v_ = make_uint4(0u, 0u, 0u, 0u);                                                           \
+      if (B200_TG_VALID(J)) v_ = apply8<F16IN>(R, cf, act);                                            \
+      sts128(a0 + 4096u * (J), v_.x, v_.y, v_.z, v_.w);                                                \
+      if (THREE) {                                                                                     \
+        if (z1) sts128(a1 + 4096u * (J), 0u, 0u, 0u, 0u); else sts128(a1 + 4096u * (J), v_.x, v_.y, v_.z, v_.w); \
+        if (z2) sts128(a2 + 4096u * (J), 0u, 0u, 0u, 0u); else sts128(a2 + 4096u * (J), v_.x, v_.y, v_.z, v_.w); \
+      }                                                                                                \
+    }                                                                                                  \
   } while (0)
-#define B200_TG_EMIT(J, R, V)                                                                    \
-  do {                                                                                           \
-    if ((J) < nitems) {                                                                          \
-      const int pp_ = (tid >> 3) + 16 * (J);                                                     \
-      uint4 v_ = make_uint4(0u, 0u, 0u, 0u);                                                     \
-      if (V) v_ = apply8<F16IN>(R, sc, sh, act);                                                \
-      sts128(slot + pp_ * 128 + ((o ^ (pp_ & 7)) << 4), v_.x, v_.y, v_.z, v_.w);                 \
-    }                                                                                            \
-  } while (0)
-  B200_TG_FETCH(0, a0, va0); B200_TG_FETCH(1, a1, va1);
 #pragma unroll 1
-  for (int j = 0; j < nitems; j += 4) {
-    B200_TG_FETCH(j + 2, b0, vb0); B200_TG_FETCH(j + 3, b1, vb1);
-    B200_TG_EMIT(j, a0, va0); B200_TG_EMIT(j + 1, a1, va1);
-    B200_TG_FETCH(j + 4, a0, va0); B200_TG_FETCH(j + 5, a1, va1);
-    B200_TG_EMIT(j + 2, b0, vb0); B200_TG_EMIT(j + 3, b1, vb1);
+  for (int j = 0; j < ni; j += 4) {
+    B200_TG_LOAD(j + 2, rb0); B200_TG_LOAD(j + 3, rb1);
+    B200_TG_EMIT(j, ra0); B200_TG_EMIT(j + 1, ra1);
+    B200_TG_LOAD(j + 4, ra0); B200_TG_LOAD(j + 5, ra1);
+    B200_TG_EMIT(j + 2, rb0); B200_TG_EMIT(j + 3, rb1);
   }
-#undef B200_TG_FETCH
+#undef B200_TG_VALID
+#undef B200_TG_LOAD
 #undef B200_TG_EMIT
 }
 // Pull the (R+2) x W patch of ALL channels of one source towards L2 (fire-and-forget, no registers): issued for the
@@ -160,18 +156,6 @@ __device__ __forceinline__ void prefetch_patch(const uint8_t* src_img, int C, in
     for (int off = tid * 128; off < row_bytes; off += 32 * TG_NTW * 128) prefetch_l2(base + off);
   }
 }
-// dst[hh][w] = copy0[hh][w + d] (zero where w + d leaves the row), d = -1 or +1
-__device__ __forceinline__ void shift_copy(uint32_t dst, uint32_t src, int d, int W, int rows, int tid) {
-  const int o = tid & 7;
-  for (int pp = tid >> 3; pp < rows; pp += 16) {
-    const int w = pp & (W - 1);                           // W is 16 or 32
-    const int sp = pp + d;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if ((unsigned)(w + d) < (unsigned)W) v = lds128u(src + sp * 128 + ((o ^ (sp & 7)) << 4));
-    sts128(dst + pp * 128 + ((o ^ (pp & 7)) << 4), v.x, v.y, v.z, v.w);
-  }
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_gn2_kernel(const __grid_constant__ TcgParams p) {
   using L = SmemG;
   constexpr int BN = 256;
@@ -212,6 +196,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
   const long long cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int chunks33 = p.kch[0] + p.kch[1], chunks11 = p.kch[2] + p.kch[3];
 
+  // Register budget per warpgroup (the CTA's 64 K registers are allocated at launch for 640 threads x 96): producer / issuer
+  // / allocator warps give most of theirs back, the two epilogue warpgroups take them (their block routine holds two
+  // 32-register tiles), the two transform warpgroups 104.  128 x (40 + 2 x 128 + 2 x 104) = 64512 <= 65536.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // ======================= weight TMA producer (both CTAs) =======================
     uint32_t stage = 0, phase = 0;
@@ -286,8 +275,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
       umma2_commit_mc(&tmem_full[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4 && warp < 12) {
+  }
+  } else if (warp < 12) {
     // ======================= epilogue (both CTAs, own 128 rows) =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const Epilogue& e = p.epi;
     uint32_t acc = 0, acc_phase = 0;
@@ -316,104 +307,105 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 12) {
-    // ======================= transform (both CTAs, own 128 pixels) =======================
-    const int tid = threadIdx.x - 384, o = tid & 7;
+  } else {
+    // ======================= transform (both CTAs, own 128 pixels; 8 warps = 256 threads) =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int tid = threadIdx.x - 384, o = tid & 7, pl = tid >> 3;      // channel octet, patch pixel lane (0..31)
     const uint32_t t_base = smem_u32(smem);
     uint32_t ts = 0, tphase = 0;
-    // one arrival per transform warp on the LEADER's tfull barrier, after this warp's generic-proxy stores have
-    // been made visible to the async proxy (the tensor core reads the copy through it)
-    auto publish = [&](uint32_t slot_idx) {
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(&tfull[slot_idx]);
-        else mbar_arrive_cluster(map_to_cta(smem_u32(&tfull[slot_idx]), 0));
-      }
+    const int W = p.W, w = pl & (W - 1);
+    // per-thread constants of the three copies (see tg_build): row of item 0 and swizzle phase in each copy
+    const uint32_t off0 = (uint32_t)pl * 128 + (uint32_t)((o ^ (pl & 7)) << 4);
+    const bool z1 = w == W - 1, z2 = w == 0;
+    const int r1 = z1 ? pl - (W - 1) : pl + 1, r2 = z2 ? pl + (W - 1) : pl - 1;
+    const uint32_t off1 = (uint32_t)r1 * 128 + (uint32_t)((o ^ ((pl + 1) & 7)) << 4);
+    const uint32_t off2 = (uint32_t)r2 * 128 + (uint32_t)((o ^ ((pl - 1) & 7)) << 4);
+    auto arrive_full = [&](uint32_t slot_idx) {
+      if (leader) mbar_arrive(&tfull[slot_idx]);
+      else mbar_arrive_cluster(map_to_cta(smem_u32(&tfull[slot_idx]), 0));
     };
-    auto next_slot = [&]() { if (++ts == TG_TS) { ts = 0; tphase ^= 1; } };
-    const int rows33 = (p.R + 2) * p.W;
+    const bool w32 = W == 32;
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
       const long long mg = (pair / p.tiles_n) * 2 + rank;
       const bool valid = mg < p.tiles_m;
       const long long p0 = mg * BM;
       const int img = valid ? (int)(p0 / HW) : 0;
-      const int h0 = valid ? (int)(p0 % HW) / p.W : 0;
+      const int h0 = valid ? (int)(p0 % HW) / W : 0;
       {   // the next tile's input patches -> L2 while this tile is being transformed
         const long long pn = pair + nclusters;
         const long long mgn = (pn / p.tiles_n) * 2 + rank;
         if (pn < total_pairs && mgn < p.tiles_m) {
           const long long pn0 = mgn * BM;
-          const int imgn = (int)(pn0 / HW), hn = (int)(pn0 % HW) / p.W;
+          const int imgn = (int)(pn0 / HW), hn = (int)(pn0 % HW) / W;
           for (int src = 0; src < 4; ++src) {
             if (p.kch[src] == 0) continue;
             const int esz = p.srcF16[src] ? 2 : 4;
             prefetch_patch(reinterpret_cast<const uint8_t*>(p.src[src]) + (long long)imgn * HW * p.srcC[src] * esz, p.srcC[src], esz,
-                           src < 2 ? hn - 1 : hn, p.H, p.W, src < 2 ? p.R + 2 : p.R, tid);
+                           src < 2 ? hn - 1 : hn, p.H, W, src < 2 ? p.R + 2 : p.R, tid);
           }
         }
       }
-      // ---- 3x3 phase: GroupNorm (+SiLU) on load, three shifted copies per chunk ----
+      // ---- 3x3 phase: GroupNorm (+SiLU) on load, three shifted copies per chunk, written straight from registers ----
+      const int pix33 = (h0 - 1) * W + pl;                               // image pixel index of this thread's item 0 (may be < 0)
       for (int src = 0; src < 2; ++src) {
         const int nch = p.kch[src];
         if (nch == 0) continue;
         const int C = p.srcC[src];
         const bool f16in = p.srcF16[src] != 0;
-        const uint8_t* img_base = reinterpret_cast<const uint8_t*>(p.src[src]) + (long long)img * HW * C * (f16in ? 2 : 4);
-        const int cg0 = src == 1 ? p.srcC[0] : 0;
+        const uint32_t esz = f16in ? 2 : 4, pixb = (uint32_t)C * esz, gstep = 32 * pixb;
+        const uint8_t* gbase = reinterpret_cast<const uint8_t*>(p.src[src]) + ((long long)img * HW + pix33) * (long long)pixb + (uint32_t)(o * 8) * esz;
+        const int cg0 = (src == 1 ? p.srcC[0] : 0) + o * 8;
         for (int kc = 0; kc < nch; ++kc) {
-          const int c0 = kc * 64 + o * 8;
-          float sc[8], sh[8];
+          const uint8_t* gp = gbase + (uint32_t)(kc * 64) * esz;
+          Coef8 cf;
+          cf.s0 = cf.s1 = make_float4(1.f, 1.f, 1.f, 1.f); cf.h0 = cf.h1 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.scale) {
-            const float4* sp = reinterpret_cast<const float4*>(p.scale + (long long)img * p.Cgn + cg0 + c0);
-            const float4* hp = reinterpret_cast<const float4*>(p.shift + (long long)img * p.Cgn + cg0 + c0);
-            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0v = __ldg(hp), h1v = __ldg(hp + 1);
-            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-            sh[0] = h0v.x; sh[1] = h0v.y; sh[2] = h0v.z; sh[3] = h0v.w; sh[4] = h1v.x; sh[5] = h1v.y; sh[6] = h1v.z; sh[7] = h1v.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { sc[i] = 1.f; sh[i] = 0.f; }
+            const float4* sp = reinterpret_cast<const float4*>(p.scale + (long long)img * p.Cgn + cg0 + kc * 64);
+            const float4* hp = reinterpret_cast<const float4*>(p.shift + (long long)img * p.Cgn + cg0 + kc * 64);
+            cf.s0 = __ldg(sp); cf.s1 = __ldg(sp + 1); cf.h0 = __ldg(hp); cf.h1 = __ldg(hp + 1);
           }
-          const uint32_t s0 = ts, s0addr = t_base + ts * TG_SLOT_BYTES;
-          mbar_wait(&tempty[ts], tphase ^ 1);
-          if (f16in) build_copy0<true>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, p.act != 0 && p.scale, tid, valid);
-          else build_copy0<false>(s0addr, img_base, C, c0, h0 - 1, p.H, p.W, rows33, sc, sh, p.act != 0 && p.scale, tid, valid);
-          next_slot();
+          // first two items' loads go out before the slot waits
+          Raw8 ra0, ra1;
+          if (valid && (unsigned)pix33 < (unsigned)HW) { if (f16in) ra0 = load_raw8<true>(gp); else ra0 = load_raw8<false>(gp); }
+          if (valid && (unsigned)(pix33 + 32) < (unsigned)HW) { if (f16in) ra1 = load_raw8<true>(gp + gstep); else ra1 = load_raw8<false>(gp + gstep); }
+          const uint32_t s0 = ts, ph0 = tphase;
+          const uint32_t s1 = s0 + 1 == TG_TS ? 0 : s0 + 1, ph1 = s0 + 1 == TG_TS ? ph0 ^ 1 : ph0;
+          const uint32_t s2 = s1 + 1 == TG_TS ? 0 : s1 + 1, ph2 = s1 + 1 == TG_TS ? ph1 ^ 1 : ph1;
+          mbar_wait(&tempty[s0], ph0 ^ 1); mbar_wait(&tempty[s1], ph1 ^ 1); mbar_wait(&tempty[s2], ph2 ^ 1);
+          const uint32_t a0 = t_base + s0 * TG_SLOT_BYTES + off0, a1 = t_base + s1 * TG_SLOT_BYTES + off1, a2 = t_base + s2 * TG_SLOT_BYTES + off2;
+          const bool act = p.act != 0 && p.scale != nullptr;
+          if (f16in) tg_build<true, true>(w32 ? 6 : 5, a0, a1, a2, z1, z2, gp, gstep, pix33, HW, valid, cf, act, ra0, ra1);
+          else tg_build<false, true>(w32 ? 6 : 5, a0, a1, a2, z1, z2, gp, gstep, pix33, HW, valid, cf, act, ra0, ra1);
+          // this warp's generic-proxy stores -> visible to the async proxy (UMMA), then one arrival per copy
           fence_async_smem();
-          transform_bar();                       // copy 0 complete: neighbours' pixels are readable
-          if (lane == 0) {
-            if (leader) mbar_arrive(&tfull[s0]);
-            else mbar_arrive_cluster(map_to_cta(smem_u32(&tfull[s0]), 0));
-          }
-#pragma unroll 1
-          for (int d = -1; d <= 1; d += 2) {
-            mbar_wait(&tempty[ts], tphase ^ 1);
-            shift_copy(t_base + ts * TG_SLOT_BYTES, s0addr, d, p.W, rows33, tid);
-            publish(ts);
-            next_slot();
-          }
-          // copy 0 of this chunk is overwritten only TG_TS slots later, and every thread passes transform_bar()
-          // of the next chunk first, so no thread can still be reading it then
+          __syncwarp();
+          if (lane == 0) { arrive_full(s0); arrive_full(s1); arrive_full(s2); }
+          ts = s2 + 1 == TG_TS ? 0 : s2 + 1; tphase = s2 + 1 == TG_TS ? ph2 ^ 1 : ph2;
         }
       }
       // ---- extra 1x1 phase: identity transform (fp32 -> fp16), one un-shifted 128-row copy per chunk ----
-      // (the 1x1 chunks recycle slots without the per-chunk barrier of the 3x3 phase: make sure no transform thread is
-      // still deriving a shifted copy from a copy 0 that is about to be overwritten)
-      if (chunks11) transform_bar();
+      const int pix11 = h0 * W + pl;
       for (int src = 2; src < 4; ++src) {
         const int nch = p.kch[src];
         if (nch == 0) continue;
         const int C = p.srcC[src];
         const bool f16in = p.srcF16[src] != 0;
-        const uint8_t* img_base = reinterpret_cast<const uint8_t*>(p.src[src]) + (long long)img * HW * C * (f16in ? 2 : 4);
-        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint32_t esz = f16in ? 2 : 4, pixb = (uint32_t)C * esz, gstep = 32 * pixb;
+        const uint8_t* gbase = reinterpret_cast<const uint8_t*>(p.src[src]) + ((long long)img * HW + pix11) * (long long)pixb + (uint32_t)(o * 8) * esz;
+        Coef8 ident;
+        ident.s0 = ident.s1 = make_float4(1.f, 1.f, 1.f, 1.f); ident.h0 = ident.h1 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kc = 0; kc < nch; ++kc) {
-          const int c0 = kc * 64 + o * 8;
+          const uint8_t* gp = gbase + (uint32_t)(kc * 64) * esz;
+          Raw8 ra0, ra1;
+          if (valid) { if (f16in) { ra0 = load_raw8<true>(gp); ra1 = load_raw8<true>(gp + gstep); } else { ra0 = load_raw8<false>(gp); ra1 = load_raw8<false>(gp + gstep); } }
           mbar_wait(&tempty[ts], tphase ^ 1);
-          if (f16in) build_copy0<true>(t_base + ts * TG_SLOT_BYTES, img_base, C, c0, h0, p.H, p.W, BM, one, zero, false, tid, valid);
-          else build_copy0<false>(t_base + ts * TG_SLOT_BYTES, img_base, C, c0, h0, p.H, p.W, BM, one, zero, false, tid, valid);
-          publish(ts);
-          next_slot();
+          const uint32_t a0 = t_base + ts * TG_SLOT_BYTES + off0;
+          if (f16in) tg_build<true, false>(4, a0, a0, a0, false, false, gp, gstep, pix11, HW, valid, ident, false, ra0, ra1);
+          else tg_build<false, false>(4, a0, a0, a0, false, false, gp, gstep, pix11, HW, valid, ident, false, ra0, ra1);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) arrive_full(ts);
+          if (++ts == TG_TS) { ts = 0; tphase ^= 1; }
         }
       }
     }
