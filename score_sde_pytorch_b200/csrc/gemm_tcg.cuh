@@ -196,11 +196,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
   const long long cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int chunks33 = p.kch[0] + p.kch[1], chunks11 = p.kch[2] + p.kch[3];
 
-  // Register budget per warpgroup (the CTA's 64 K registers are allocated at launch for 640 threads x 96): producer / issuer
-  // / allocator warps give most of theirs back, the two epilogue warpgroups take them (their block routine holds two
-  // 32-register tiles), the two transform warpgroups 104.  128 x (40 + 2 x 128 + 2 x 104) = 64512 <= 65536.
+  // Register budget per warpgroup.  The CTA is launched with 640 threads x 96 registers; setmaxnreg.inc can only take what
+  // setmaxnreg.dec of the same CTA released, so the two must balance: the producer / issuer / allocator warpgroup drops to
+  // 32 (frees 128 x 64 = 8192), the two epilogue warpgroups rise to 120 (their block routine holds two 32-register tiles;
+  // 2 x 128 x 24 = 6144) and the two transform warpgroups to 104 (2 x 128 x 8 = 2048).
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0 && lane == 0) {
     // ======================= weight TMA producer (both CTAs) =======================
     uint32_t stage = 0, phase = 0;
@@ -278,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
   }
   } else if (warp < 12) {
     // ======================= epilogue (both CTAs, own 128 rows) =======================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const Epilogue& e = p.epi;
     uint32_t acc = 0, acc_phase = 0;
