@@ -979,7 +979,8 @@ int tcg_launch(const TcgPlan* pl, cudaStream_t st) {
   const long long pairs = ((q.tiles_m + 1) / 2) * q.tiles_n;
   if (pairs == 0) return 0;
   const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
-  conv_gn2_kernel<<<grid, TG_THREADS, SmemG::TOTAL, st>>>(q);
+  if (q.W == 32) conv_gn2_kernel<true><<<grid, TG_THREADS, SmemG::TOTAL, st>>>(q);
+  else conv_gn2_kernel<false><<<grid, TG_THREADS, SmemG::TOTAL, st>>>(q);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -993,7 +994,8 @@ static int tc_configure() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2<256, 6>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<false>::TOTAL));
   B200_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<true>::TOTAL));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemG::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemG::TOTAL));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemG::TOTAL));
   configured = true;
   return 0;
 }

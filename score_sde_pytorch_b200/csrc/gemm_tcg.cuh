@@ -68,7 +68,15 @@ __device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
 }
-__device__ __forceinline__ float silu_approx(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // == silu_fast (elementwise.cu)
+// SiLU on the MUFU pipe, five instructions: x * rcp(1 + 2^(-x log2 e)).  (__fdividef / __expf wrap the same two MUFU ops in
+// range-scaling code - 9-10 instructions per element, measured in the first version of the transform.)  x -> +inf: e flushes
+// to 0, y = x; x -> -inf: e = inf, rcp = 0, y = -0.  elementwise.cu's silu_fast is the same function.
+__device__ __forceinline__ float silu_approx(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 // eight consecutive channels of one pixel: raw bits as loaded (fp32: 32 B in a|b, fp16: 16 B in a)
 struct Raw8 { uint4 a, b; };
@@ -107,42 +115,47 @@ __device__ __forceinline__ uint4 apply8(const Raw8 r, const Coef8 cf, bool act) 
   return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
-// One chunk of the operand for one transform thread.  The patch is a CONTIGUOUS range of `32 * NI` NHWC pixels starting
-// one image row above the tile, so with 256 transform threads thread t owns channel octet t & 7 of patch pixels
-// pl + 32 j (pl = t >> 3), and everything about an item except j is a per-thread constant: its column w = pl & (W-1)
-// (W divides 32), its swizzle phase pl & 7, hence its shared-memory address in each of the three copies
-// (a0 / a1 / a2 + 4096 j) and its global address (gp + gstep j).  Copy -1 holds T[hh][w-1] at (hh, w): this thread's
-// value goes one pixel row further (pl + 1), except that the thread owning column W-1 writes the zero of column 0
-// instead (W-1 rows back: same swizzle phase); copy +1 mirrored.  Out-of-image halo rows (pixel index outside
-// [0, HW)) are zero in all copies.  Loads run two items ahead of the transform (registers: 2 x 2 x 32 B).
-template <bool F16IN, bool THREE>
-__device__ __forceinline__ void tg_build(int ni, uint32_t a0, uint32_t a1, uint32_t a2, bool z1, bool z2, const uint8_t* gp, uint32_t gstep,
-                                         int pix0, int HW, bool tile_valid, const Coef8 cf, bool act, Raw8 ra0, Raw8 ra1) {
+// One chunk of the operand for one transform thread, as straight-line code.  The patch is a CONTIGUOUS range of 32 * NI
+// NHWC pixels starting one image row above the tile, so with 256 transform threads thread t owns channel octet t & 7 of
+// patch pixels pl + 32 j (pl = t >> 3, j < NI), and everything about an item except j is a per-thread constant: its column
+// w = pl & (W-1) (W divides 32), its swizzle phase pl & 7, hence its shared-memory address in each of the three copies
+// (a0 / a1 / a2 + 4096 j, immediate offsets) and its global address (gp + gstep j).  Copy -1 holds T[hh][w-1] at (hh, w):
+// this thread's value goes one pixel row further (pl + 1), except that the thread owning column W-1 writes the zero of
+// column 0 instead (W-1 rows back: same swizzle phase): m1 = 0 for that thread, ~0 otherwise; copy +1 mirrored (m2).
+// Only the first and the last item can lie in a halo row outside the image: their results are ANDed with mfirst / mlast
+// (0 or ~0; fp16 zero is all-zero bits) and their loads are redirected to the neighbouring item's address by the caller,
+// so there is not a single branch per item.  Loads run two items ahead of the arithmetic (64 B per thread in flight).
+// The first version of this routine (runtime trip count, per-item validity branches, __fdividef/__expf) executed 265
+// instructions per item, 80 of them arithmetic; the transform, not the tensor pipe, set the pace (profiles/r02_g4_*).
+template <int NI, bool F16IN, bool THREE>
+__device__ __forceinline__ void tg_build(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t m1, uint32_t m2, const uint8_t* gp,
+                                         uint32_t gstep, uint32_t mfirst, uint32_t mlast, const Coef8 cf, bool act, Raw8 ra0, Raw8 ra1) {
   Raw8 rb0, rb1;
-  // item j: valid iff its pixel index lies inside the image (halo rows above / below are zero)
-#define B200_TG_VALID(J) (tile_valid && (unsigned)(pix0 + 32 * (J)) < (unsigned)HW)
-#define B200_TG_LOAD(J, R) do { if ((J) < ni && B200_TG_VALID(J)) R = load_raw8<F16IN>(gp + (uint32_t)(J) * gstep); } while (0)
+  const uint8_t* glast = gp + (uint32_t)(NI - 1) * gstep - (mlast ? 0u : gstep);     // a halo item reads its (valid) neighbour
+#define B200_TG_PTR(J) ((J) == NI - 1 ? glast : gp + (uint32_t)(J) * gstep)
 #define B200_TG_EMIT(J, R)                                                                             \
   do {                                                                                                 \
-    if ((J) < ni) {                                                                                    \
-      uint4 v_ = make_uint4(0u, 0u, 0u, 0u);                                                           \
-      if (B200_TG_VALID(J)) v_ = apply8<F16IN>(R, cf, act);                                            \
-      sts128(a0 + 4096u * (J), v_.x, v_.y, v_.z, v_.w);                                                \
-      if (THREE) {                                                                                     \
-        if (z1) sts128(a1 + 4096u * (J), 0u, 0u, 0u, 0u); else sts128(a1 + 4096u * (J), v_.x, v_.y, v_.z, v_.w); \
-        if (z2) sts128(a2 + 4096u * (J), 0u, 0u, 0u, 0u); else sts128(a2 + 4096u * (J), v_.x, v_.y, v_.z, v_.w); \
-      }                                                                                                \
+    uint4 v_ = apply8<F16IN>(R, cf, act);                                                              \
+    if ((J) == 0) { v_.x &= mfirst; v_.y &= mfirst; v_.z &= mfirst; v_.w &= mfirst; }                  \
+    if ((J) == NI - 1) { v_.x &= mlast; v_.y &= mlast; v_.z &= mlast; v_.w &= mlast; }                 \
+    sts128(a0 + 4096u * (J), v_.x, v_.y, v_.z, v_.w);                                                  \
+    if (THREE) {                                                                                       \
+      sts128(a1 + 4096u * (J), v_.x & m1, v_.y & m1, v_.z & m1, v_.w & m1);                            \
+      sts128(a2 + 4096u * (J), v_.x & m2, v_.y & m2, v_.z & m2, v_.w & m2);                            \
     }                                                                                                  \
   } while (0)
-#pragma unroll 1
-  for (int j = 0; j < ni; j += 4) {
-    B200_TG_LOAD(j + 2, rb0); B200_TG_LOAD(j + 3, rb1);
-    B200_TG_EMIT(j, ra0); B200_TG_EMIT(j + 1, ra1);
-    B200_TG_LOAD(j + 4, ra0); B200_TG_LOAD(j + 5, ra1);
-    B200_TG_EMIT(j + 2, rb0); B200_TG_EMIT(j + 3, rb1);
+#pragma unroll
+  for (int j = 0; j < NI; j += 4) {
+    if (j + 2 < NI) rb0 = load_raw8<F16IN>(B200_TG_PTR(j + 2));
+    if (j + 3 < NI) rb1 = load_raw8<F16IN>(B200_TG_PTR(j + 3));
+    B200_TG_EMIT(j, ra0);
+    if (j + 1 < NI) B200_TG_EMIT(j + 1, ra1);
+    if (j + 4 < NI) ra0 = load_raw8<F16IN>(B200_TG_PTR(j + 4));
+    if (j + 5 < NI) ra1 = load_raw8<F16IN>(B200_TG_PTR(j + 5));
+    if (j + 2 < NI) B200_TG_EMIT(j + 2, rb0);
+    if (j + 3 < NI) B200_TG_EMIT(j + 3, rb1);
   }
-#undef B200_TG_VALID
-#undef B200_TG_LOAD
+#undef B200_TG_PTR
 #undef B200_TG_EMIT
 }
 // Pull the (R+2) x W patch of ALL channels of one source towards L2 (fire-and-forget, no registers): issued for the
@@ -156,6 +169,7 @@ __device__ __forceinline__ void prefetch_patch(const uint8_t* src_img, int C, in
     for (int off = tid * 128; off < row_bytes; off += 32 * TG_NTW * 128) prefetch_l2(base + off);
   }
 }
+template <bool W32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_gn2_kernel(const __grid_constant__ TcgParams p) {
   using L = SmemG;
   constexpr int BN = 256;
@@ -314,10 +328,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
     const int tid = threadIdx.x - 384, o = tid & 7, pl = tid >> 3;      // channel octet, patch pixel lane (0..31)
     const uint32_t t_base = smem_u32(smem);
     uint32_t ts = 0, tphase = 0;
-    const int W = p.W, w = pl & (W - 1);
+    constexpr int W = W32 ? 32 : 16, NI3 = W32 ? 6 : 5;                  // (R + 2) * W = 32 * NI3 patch pixels
+    const int w = pl & (W - 1);
     // per-thread constants of the three copies (see tg_build): row of item 0 and swizzle phase in each copy
     const uint32_t off0 = (uint32_t)pl * 128 + (uint32_t)((o ^ (pl & 7)) << 4);
     const bool z1 = w == W - 1, z2 = w == 0;
+    const uint32_t m1 = z1 ? 0u : 0xffffffffu, m2 = z2 ? 0u : 0xffffffffu;
     const int r1 = z1 ? pl - (W - 1) : pl + 1, r2 = z2 ? pl + (W - 1) : pl - 1;
     const uint32_t off1 = (uint32_t)r1 * 128 + (uint32_t)((o ^ ((pl + 1) & 7)) << 4);
     const uint32_t off2 = (uint32_t)r2 * 128 + (uint32_t)((o ^ ((pl - 1) & 7)) << 4);
@@ -325,7 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
       if (leader) mbar_arrive(&tfull[slot_idx]);
       else mbar_arrive_cluster(map_to_cta(smem_u32(&tfull[slot_idx]), 0));
     };
-    const bool w32 = W == 32;
+    const bool act = p.act != 0 && p.scale != nullptr;
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
       const long long mg = (pair / p.tiles_n) * 2 + rank;
       const bool valid = mg < p.tiles_m;
@@ -347,6 +363,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
         }
       }
       // ---- 3x3 phase: GroupNorm (+SiLU) on load, three shifted copies per chunk, written straight from registers ----
+      // only item 0 (top halo row) and item NI3-1 (bottom halo row) can lie outside the image; a tile past the end is all zero
+      const uint32_t mfirst = (valid && !(h0 == 0 && pl < W)) ? 0xffffffffu : 0u;
+      const uint32_t mlast = (valid && !(h0 + p.R == p.H && pl >= 32 - W)) ? 0xffffffffu : 0u;
+      const uint32_t mmid = valid ? 0xffffffffu : 0u;
       const int pix33 = (h0 - 1) * W + pl;                               // image pixel index of this thread's item 0 (may be < 0)
       for (int src = 0; src < 2; ++src) {
         const int nch = p.kch[src];
@@ -365,18 +385,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
             const float4* hp = reinterpret_cast<const float4*>(p.shift + (long long)img * p.Cgn + cg0 + kc * 64);
             cf.s0 = __ldg(sp); cf.s1 = __ldg(sp + 1); cf.h0 = __ldg(hp); cf.h1 = __ldg(hp + 1);
           }
-          // first two items' loads go out before the slot waits
+          if (!valid) { cf.s0 = cf.s1 = cf.h0 = cf.h1 = make_float4(0.f, 0.f, 0.f, 0.f); }   // tile past the end: SiLU(0) = 0 everywhere
+          // first two items' loads go out before the slot waits (item 0 reads item 1's address when it is a halo row)
           Raw8 ra0, ra1;
-          if (valid && (unsigned)pix33 < (unsigned)HW) { if (f16in) ra0 = load_raw8<true>(gp); else ra0 = load_raw8<false>(gp); }
-          if (valid && (unsigned)(pix33 + 32) < (unsigned)HW) { if (f16in) ra1 = load_raw8<true>(gp + gstep); else ra1 = load_raw8<false>(gp + gstep); }
+          const uint8_t* g0 = mfirst ? gp : gp + gstep;
+          if (f16in) { ra0 = load_raw8<true>(g0); ra1 = load_raw8<true>(gp + gstep); }
+          else { ra0 = load_raw8<false>(g0); ra1 = load_raw8<false>(gp + gstep); }
           const uint32_t s0 = ts, ph0 = tphase;
           const uint32_t s1 = s0 + 1 == TG_TS ? 0 : s0 + 1, ph1 = s0 + 1 == TG_TS ? ph0 ^ 1 : ph0;
           const uint32_t s2 = s1 + 1 == TG_TS ? 0 : s1 + 1, ph2 = s1 + 1 == TG_TS ? ph1 ^ 1 : ph1;
           mbar_wait(&tempty[s0], ph0 ^ 1); mbar_wait(&tempty[s1], ph1 ^ 1); mbar_wait(&tempty[s2], ph2 ^ 1);
           const uint32_t a0 = t_base + s0 * TG_SLOT_BYTES + off0, a1 = t_base + s1 * TG_SLOT_BYTES + off1, a2 = t_base + s2 * TG_SLOT_BYTES + off2;
-          const bool act = p.act != 0 && p.scale != nullptr;
-          if (f16in) tg_build<true, true>(w32 ? 6 : 5, a0, a1, a2, z1, z2, gp, gstep, pix33, HW, valid, cf, act, ra0, ra1);
-          else tg_build<false, true>(w32 ? 6 : 5, a0, a1, a2, z1, z2, gp, gstep, pix33, HW, valid, cf, act, ra0, ra1);
+          if (f16in) tg_build<NI3, true, true>(a0, a1, a2, m1, m2, gp, gstep, mfirst, mlast, cf, act, ra0, ra1);
+          else tg_build<NI3, false, true>(a0, a1, a2, m1, m2, gp, gstep, mfirst, mlast, cf, act, ra0, ra1);
           // this warp's generic-proxy stores -> visible to the async proxy (UMMA), then one arrival per copy
           fence_async_smem();
           __syncwarp();
@@ -394,15 +415,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
         const uint32_t esz = f16in ? 2 : 4, pixb = (uint32_t)C * esz, gstep = 32 * pixb;
         const uint8_t* gbase = reinterpret_cast<const uint8_t*>(p.src[src]) + ((long long)img * HW + pix11) * (long long)pixb + (uint32_t)(o * 8) * esz;
         Coef8 ident;
-        ident.s0 = ident.s1 = make_float4(1.f, 1.f, 1.f, 1.f); ident.h0 = ident.h1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        ident.s0 = ident.s1 = valid ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ident.h0 = ident.h1 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kc = 0; kc < nch; ++kc) {
           const uint8_t* gp = gbase + (uint32_t)(kc * 64) * esz;
           Raw8 ra0, ra1;
-          if (valid) { if (f16in) { ra0 = load_raw8<true>(gp); ra1 = load_raw8<true>(gp + gstep); } else { ra0 = load_raw8<false>(gp); ra1 = load_raw8<false>(gp + gstep); } }
+          if (f16in) { ra0 = load_raw8<true>(gp); ra1 = load_raw8<true>(gp + gstep); } else { ra0 = load_raw8<false>(gp); ra1 = load_raw8<false>(gp + gstep); }
           mbar_wait(&tempty[ts], tphase ^ 1);
           const uint32_t a0 = t_base + ts * TG_SLOT_BYTES + off0;
-          if (f16in) tg_build<true, false>(4, a0, a0, a0, false, false, gp, gstep, pix11, HW, valid, ident, false, ra0, ra1);
-          else tg_build<false, false>(4, a0, a0, a0, false, false, gp, gstep, pix11, HW, valid, ident, false, ra0, ra1);
+          if (f16in) tg_build<4, true, false>(a0, a0, a0, 0u, 0u, gp, gstep, mmid, mmid, ident, false, ra0, ra1);
+          else tg_build<4, false, false>(a0, a0, a0, 0u, 0u, gp, gstep, mmid, mmid, ident, false, ra0, ra1);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) arrive_full(ts);
