@@ -83,6 +83,9 @@ class ClockSampler:
                 reasons=sorted(reasons), samples=len(sm))
 
 
+SEPARATE_GROUPNORM_DEFAULT = False   # the plan bench.py measures by default (flip after an A/B; both are in `variants`)
+
+
 def headline_config():
   from score_sde_pytorch_b200 import configs
   cfg = configs.ve_cifar10_ncsnpp_continuous()
@@ -435,7 +438,7 @@ def run_gpu_arm(args):
   B = args.batch if args.scaling == 'weak' else max(1, args.batch // world)
   shape = (B, 3, 32, 32)
   torch.manual_seed(0)                       # same random-init weights on every rank ...
-  model = NCSNpp(cfg, precision=args.precision).to(dev)
+  model = NCSNpp(cfg, precision=args.precision, separate_groupnorm=args.separate_groupnorm).to(dev)
   if world > 1:                              # ... and broadcast once over NCCL/NVLink anyway (the production path)
     from score_sde_pytorch_b200 import distributed as bdist
     bdist.broadcast_parameters(model, src=0)
@@ -552,6 +555,18 @@ def run_gpu_arm(args):
       ms2 = timed_steps(plan2, x_host.to(dev), args.warmup, args.steps)
       variants = {other: dict(value=round(B / (N_SAMPLER_STEPS * ms2 * 1e-3), 4), unit='images/s', ms_per_step=round(ms2, 4))}
       del plan2, model2
+      if args.precision == 'f16':
+        # A/B of the two GroupNorm plans in the same run, on the same box (the separate streaming pass of round 1 vs
+        # GroupNorm applied on load by the consuming convolution): whichever is not the headline plan is timed here
+        torch.manual_seed(0)
+        model3 = NCSNpp(cfg, precision='f16', separate_groupnorm=not args.separate_groupnorm).to(dev)
+        plan3 = native.match_pc_plan(sde=sde, model=model3, predictor=sampling.ReverseDiffusionPredictor,
+                                     corrector=sampling.LangevinCorrector, shape=shape, snr=cfg.sampling.snr, n_steps=1,
+                                     probability_flow=False, continuous=True, eps=1e-5, device=dev)
+        ms3 = timed_steps(plan3, x_host.to(dev), args.warmup, args.steps)
+        variants['f16_groupnorm_' + ('on_load' if args.separate_groupnorm else 'separate_pass')] = dict(
+            value=round(B / (N_SAMPLER_STEPS * ms3 * 1e-3), 4), unit='images/s', ms_per_step=round(ms3, 4))
+        del plan3, model3
     # ---- strong-scaling probe: the same 1024-image job cut over 8 GPUs is 128 images per GPU; time that
     # per-GPU share here and name the launches that under-fill the 148 SMs ----
     strong = None
@@ -589,7 +604,9 @@ def run_gpu_arm(args):
                             step='one PC iteration = Langevin corrector + reverse-diffusion predictor (2 score evaluations)',
                             parallelism=f'{world} independent chains shards (weights broadcast once, no in-loop collective)',
                             l2='per-step working set (activations) exceeds the 126 MB L2 by >100x; no explicit flush',
-                            weights='random init, init_scale=1, torch.manual_seed(0)', precision=args.precision),
+                            weights='random init, init_scale=1, torch.manual_seed(0)', precision=args.precision,
+                            groupnorm='separate streaming pass' if args.separate_groupnorm else
+                            'applied on load by the consuming convolution where supported (256-channel outputs at 16x16 / 32x32), separate pass elsewhere'),
                 clocks=clk,
                 e2e=dict(value=round(e2e_value, 4), unit='images/s', h2d_bytes_per_step=int(np.prod(shape)) * 4,
                          d2h_bytes_per_step=int(np.prod(shape)) * 4, ms_per_step=round(ms_e2e / e2e_steps, 4)),
@@ -620,6 +637,10 @@ def main():
                   help="tensor-core operand format: 'f16' (default) and 'tf32' both carry 11-bit significands with fp32 "
                        "accumulation and meet the same 1e-3 parity bound (tests/test_gpu_tc.py); 'fp32' = CUDA cores")
   ap.add_argument('--no-variants', action='store_true', help='skip timing the other operand format')
+  ap.add_argument('--separate-groupnorm', dest='separate_groupnorm', action='store_true', default=SEPARATE_GROUPNORM_DEFAULT,
+                  help='GroupNorm+SiLU as stand-alone streaming passes (round-1 plan)')
+  ap.add_argument('--groupnorm-on-load', dest='separate_groupnorm', action='store_false',
+                  help='GroupNorm+SiLU applied on load by the consuming convolution where supported (csrc/gemm_tcg.cuh)')
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   ap.add_argument('--no-strong', action='store_true', help='skip the 128-images-per-GPU strong-scaling probe')
   ap.add_argument('--parity-steps', type=int, default=10,

@@ -406,6 +406,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
         }
       }
       // ---- extra 1x1 phase: identity transform (fp32 -> fp16), one un-shifted 128-row copy per chunk ----
+      // A chunk is only four MMAs (512 tensor cycles) but 32 KB of fp32 input per CTA, so this phase runs at load latency
+      // unless the loads are far ahead: a whole chunk (4 items per thread) is requested while the previous one is converted
+      // and stored (measured with a two-item prefetch: the skip-projection convolutions at 0.69 PFLOP/s, profiles/r02_g5_*).
       const int pix11 = h0 * W + pl;
       for (int src = 2; src < 4; ++src) {
         const int nch = p.kch[src];
@@ -417,19 +420,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
         Coef8 ident;
         ident.s0 = ident.s1 = valid ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
         ident.h0 = ident.h1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        Raw8 q0, q1, q2, q3, n0, n1, n2, n3;
+#define B200_TG_LOAD4(G, A, B, C_, D)                                                                                   \
+        do { if (f16in) { A = load_raw8<true>(G); B = load_raw8<true>((G) + gstep); C_ = load_raw8<true>((G) + 2 * gstep); D = load_raw8<true>((G) + 3 * gstep); } \
+             else { A = load_raw8<false>(G); B = load_raw8<false>((G) + gstep); C_ = load_raw8<false>((G) + 2 * gstep); D = load_raw8<false>((G) + 3 * gstep); } } while (0)
+#define B200_TG_STORE1(J, R)                                                                                            \
+        do { const uint4 v_ = f16in ? apply8<true>(R, ident, false) : apply8<false>(R, ident, false);                  \
+             sts128(a0 + 4096u * (J), v_.x, v_.y, v_.z, v_.w); } while (0)
+        B200_TG_LOAD4(gbase, q0, q1, q2, q3);
         for (int kc = 0; kc < nch; ++kc) {
-          const uint8_t* gp = gbase + (uint32_t)(kc * 64) * esz;
-          Raw8 ra0, ra1;
-          if (f16in) { ra0 = load_raw8<true>(gp); ra1 = load_raw8<true>(gp + gstep); } else { ra0 = load_raw8<false>(gp); ra1 = load_raw8<false>(gp + gstep); }
+          if (kc + 1 < nch) { const uint8_t* gn = gbase + (uint32_t)((kc + 1) * 64) * esz; B200_TG_LOAD4(gn, n0, n1, n2, n3); }
           mbar_wait(&tempty[ts], tphase ^ 1);
           const uint32_t a0 = t_base + ts * TG_SLOT_BYTES + off0;
-          if (f16in) tg_build<4, true, false>(a0, a0, a0, 0u, 0u, gp, gstep, mmid, mmid, ident, false, ra0, ra1);
-          else tg_build<4, false, false>(a0, a0, a0, 0u, 0u, gp, gstep, mmid, mmid, ident, false, ra0, ra1);
+          B200_TG_STORE1(0, q0); B200_TG_STORE1(1, q1); B200_TG_STORE1(2, q2); B200_TG_STORE1(3, q3);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) arrive_full(ts);
           if (++ts == TG_TS) { ts = 0; tphase ^= 1; }
+          q0 = n0; q1 = n1; q2 = n2; q3 = n3;
         }
+#undef B200_TG_LOAD4
+#undef B200_TG_STORE1
       }
     }
   }
