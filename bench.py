@@ -83,7 +83,7 @@ class ClockSampler:
                 reasons=sorted(reasons), samples=len(sm))
 
 
-SEPARATE_GROUPNORM_DEFAULT = False   # the plan bench.py measures by default (flip after an A/B; both are in `variants`)
+SEPARATE_GROUPNORM_DEFAULT = True   # the plan bench.py measures by default = the package default (the faster one in the same-run A/B; both are in `variants`)
 
 
 def headline_config():

@@ -129,7 +129,11 @@ class NCSNpp(nn.Module):
     self.lanes = int(getattr(m, 'lanes', lanes))   # 2: evaluate batches >= 128 as two half-batch lanes on two streams
     # per-engine execution options (fields of b200_ncsnpp_config; nothing is read from the environment)
     self.cuda_core_head = bool(getattr(m, 'cuda_core_head', False) if cuda_core_head is None else cuda_core_head)
-    self.separate_groupnorm = bool(getattr(m, 'separate_groupnorm', False) if separate_groupnorm is None else separate_groupnorm)
+    # GroupNorm+SiLU as stand-alone streaming passes (True, default) or applied on load by the consuming convolution where
+    # supported (False; csrc/gemm_tcg.cuh).  Measured in the same run on the same B200: 62.41 vs 63.39 ms per PC step at
+    # batch 1024 (profiles/r02_g6_bench.json) - at the board's power cap the transform's arithmetic costs more than
+    # the 4.5 GB/evaluation of HBM traffic it removes, so the separate pass stays the default.
+    self.separate_groupnorm = bool(getattr(m, 'separate_groupnorm', True) if separate_groupnorm is None else separate_groupnorm)
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
     L = len(ch_mult)
     all_res = [config.data.image_size // (2 ** i) for i in range(L)]

@@ -274,7 +274,7 @@ def test_groupnorm_on_load_convolution_matches_the_separate_pass(dev, batch):
   batch 2 leaves most CTAs idle."""
   cfg = golden_config('cifar10_ve')
   sep = seeded_model(cfg, precision='f16', keep_activations=True, separate_groupnorm=True).to(dev)
-  fus = seeded_model(cfg, precision='f16', keep_activations=True).to(dev)
+  fus = seeded_model(cfg, precision='f16', keep_activations=True, separate_groupnorm=False).to(dev)
   sd = {k: v.to(dev) for k, v in sep.state_dict().items()}
   torch.manual_seed(11)
   sigma = torch.exp(torch.rand(batch) * 8.5 - 4.6).to(dev)
