@@ -95,8 +95,8 @@ B200_API int b200_gemm_nt_f32(const float* a, long long lda, int a_batch_rows, c
 /* ---- NCSN++ score network ----------------------------------------------------
  * Replaces models/ncsnpp.py:38-381 (+ models/layerspp.py, models/layers.py:29-124,515-555,
  * models/up_or_down_sampling.py, op/) for configurations with Fourier embedding,
- * (or positional) embedding, BigGAN residual blocks, FIR or naive resampling, progressive='none' and
- * progressive_input in {'none','residual'}.  forward(x[B,C,H,W], time_cond[B]) -> [B,C,H,W]
+ * (or positional) embedding, BigGAN residual blocks, FIR or naive resampling, progressive in {'none','output_skip'}
+ * and progressive_input in {'none','residual','input_skip'} (Combine method 'sum').  forward(x[B,C,H,W], time_cond[B]) -> [B,C,H,W]
  * like NCSNpp.forward (models/ncsnpp.py:232). */
 typedef struct b200_ncsnpp b200_ncsnpp_t;
 
@@ -105,7 +105,7 @@ typedef struct {
   int num_levels;  int ch_mult[8];
   int num_attn_resolutions;  int attn_resolutions[8];
   int centered, scale_by_sigma, skip_rescale, conditional;
-  int progressive_input;        /* 0 = none, 1 = residual */
+  int progressive_input;        /* 0 = none, 1 = residual, 2 = input_skip (Combine 'sum', layerspp.py:44-59) */
   int fir_taps;  float fir_kernel[8];   /* separable taps, e.g. {1,3,3,1} */
   int precision;                /* 0 = tensor cores on TF32-rounded fp32 operands where shapes allow, 1 = strict fp32
                                  * CUDA cores, 2 = tensor cores on fp16 operands (same 11-bit significand as TF32,
@@ -124,6 +124,9 @@ typedef struct {
                                  * the frequency table is the pseudo-parameter "pos_freqs" [nf/2] */
   int naive_resample;           /* 0: FIR up/down-sampling in the resblocks (fir=True); 1: nearest-neighbour 2x upsampling and
                                  * 2x2 mean downsampling (fir=False, up_or_down_sampling.py:59-69; the DDPM++ family) */
+  int progressive;              /* 0 = none; 1 = output_skip (ncsnpp.py:190-203, 325-341, 366-367): every level adds
+                                 * conv3x3(SiLU(GroupNorm(h))) in image channels to the upsampled pyramid, which is the output
+                                 * (the high-resolution NCSN++ family: configs/ve/{ffhq,celebahq}_*_ncsnpp_continuous.py) */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

@@ -138,3 +138,56 @@ def tiny_ddpmpp(nf=32, image_size=16, num_res_blocks=1, ch_mult=(1, 2), attn_res
   c.model.init_scale = 1.0
   c.data.image_size = image_size
   return c
+
+
+def ve_ffhq_1024_ncsnpp_continuous():
+  """``configs/ve/ffhq_ncsnpp_continuous.py`` over ``configs/default_lsun_configs.py``: the 1024x1024 NCSN++ -
+  nf=16, eight levels, ``progressive='output_skip'``, ``progressive_input='input_skip'``, attention at 16x16."""
+  c = ve_cifar10_ncsnpp_continuous()
+  c.data.dataset = 'FFHQ'
+  c.data.image_size = 1024
+  c.training.batch_size = 8
+  c.eval.batch_size = 8
+  m = c.model
+  m.sigma_max = 1348
+  m.num_scales = 2000
+  m.ema_rate = 0.9999
+  m.nf = 16
+  m.ch_mult = (1, 2, 4, 8, 16, 32, 32, 32)
+  m.num_res_blocks = 1
+  m.attn_resolutions = (16,)
+  m.dropout = 0.
+  m.progressive = 'output_skip'
+  m.progressive_input = 'input_skip'
+  m.progressive_combine = 'sum'
+  return c
+
+
+def ve_celebahq_256_ncsnpp_continuous():
+  """``configs/ve/celebahq_256_ncsnpp_continuous.py``: 256x256, nf=128, ch_mult (1,1,2,2,2,2,2), two blocks per level,
+  output_skip / input_skip pyramids."""
+  c = ve_cifar10_ncsnpp_continuous()
+  c.data.dataset = 'CelebAHQ'
+  c.data.image_size = 256
+  c.eval.batch_size = 64
+  m = c.model
+  m.sigma_max = 348
+  m.ema_rate = 0.999
+  m.nf = 128
+  m.ch_mult = (1, 1, 2, 2, 2, 2, 2)
+  m.num_res_blocks = 2
+  m.attn_resolutions = (16,)
+  m.progressive = 'output_skip'
+  m.progressive_input = 'input_skip'
+  m.progressive_combine = 'sum'
+  return c
+
+
+def tiny_progressive(nf=32, image_size=32, num_res_blocks=1, ch_mult=(1, 1, 2), attn_resolutions=(8,), fir=True):
+  """A small member of the high-resolution family (three levels, output_skip + input_skip); test fixture sized."""
+  c = tiny_ncsnpp(nf=nf, image_size=image_size, num_res_blocks=num_res_blocks, ch_mult=ch_mult, attn_resolutions=attn_resolutions)
+  c.model.progressive = 'output_skip'
+  c.model.progressive_input = 'input_skip'
+  c.model.progressive_combine = 'sum'
+  c.model.fir = fir
+  return c

@@ -862,7 +862,8 @@ template <int N>
 __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w /* [9][N][C] */,
                                                              const float* __restrict__ bias, const float* __restrict__ div,
                                                              long long div_stride, float* __restrict__ out_nchw,
-                                                             int B, int H, int W, int C, int x_f16) {
+                                                             int B, int H, int W, int C, int x_f16,
+                                                             const float* __restrict__ add_nchw) {
   // Eight lanes share one output pixel: lane `part` takes the float4s part, part+8, ... of the pixel's channel
   // vector, so a warp-wide 128-bit load covers 4 pixels x 128 contiguous bytes (4 cache lines per instruction
   // instead of 32 with one pixel per lane, which was L1-wavefront bound); the partial dot products are folded with
@@ -956,14 +957,16 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       float v = acc[n] + (bias ? __ldg(bias + n) : 0.f);
+      const long long oi = (((long long)b * N + n) * H + py) * W + px;
+      if (add_nchw) v = __ldg(add_nchw + oi) + v;      // output_skip: pyramid = upsample(pyramid) + conv (ncsnpp.py:341)
       if (div) v = v / dv;
-      out_nchw[(((long long)b * N + n) * H + py) * W + px] = v;
+      out_nchw[oi] = v;
     }
   }
 }
 
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
-                           float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st) {
+                           float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st, const float* add_nchw) {
   B200_REQUIRE(N >= 1 && N <= 4 && C % (x_f16 ? 64 : 4) == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
   const size_t smem = (size_t)9 * N * C * sizeof(float);
   B200_REQUIRE(smem <= 96 * 1024, "conv3x3_small_n: weights (%zu B) exceed shared memory", smem);
@@ -973,7 +976,7 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
       B200_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_n_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3x3_small_n_kernel<NN><<<blocks, 256, smem, st>>>(x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16); \
+    conv3x3_small_n_kernel<NN><<<blocks, 256, smem, st>>>(x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16, add_nchw); \
   } while (0)
   switch (N) {
     case 1: B200_LAUNCH_SMALLN(1); break;

@@ -20,7 +20,7 @@ using namespace b200;
 
 namespace {
 
-enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RESBLOCK, M_ATTN, M_PYR_DOWN, M_GN_OUT, M_CONV_OUT };
+enum ModKind { M_FOURIER, M_LINEAR, M_CONV_IN, M_RESBLOCK, M_ATTN, M_PYR_DOWN, M_GN_OUT, M_CONV_OUT, M_COMBINE };
 enum PackKind { PK_COPY = 0, PK_CONV = 1, PK_NIN = 2, PK_CONV_FLAT32 = 3, PK_CONV_PAD128 = 4 };
 
 struct Param {
@@ -204,6 +204,10 @@ int build_graph(b200_ncsnpp* e) {
   B200_REQUIRE(c.embedding_type == 0 || c.embedding_type == 1, "ncsnpp: embedding_type=%d unknown", c.embedding_type);
   B200_REQUIRE(!(c.embedding_type == 1 && c.scale_by_sigma), "ncsnpp: positional embedding with scale_by_sigma is not supported");
   B200_REQUIRE(!(c.naive_resample && c.progressive_input == 1), "ncsnpp: the residual input pyramid needs FIR resampling");
+  B200_REQUIRE(c.progressive_input >= 0 && c.progressive_input <= 2, "ncsnpp: progressive_input=%d unknown", c.progressive_input);
+  B200_REQUIRE(c.progressive == 0 || c.progressive == 1, "ncsnpp: progressive=%d unknown (0 none, 1 output_skip)", c.progressive);
+  B200_REQUIRE((c.progressive == 0 && c.progressive_input != 2) || c.num_channels <= 4,
+               "ncsnpp: the output_skip / input_skip pyramids carry the image channels (<= 4), got %d", c.num_channels);
   // 0: Fourier projection (all_modules[0].W [nf]) or the positional frequency table (pseudo-parameter [nf/2])
   const int emb_dim = c.embedding_type == 1 ? nf : 2 * nf;
   if (c.embedding_type == 1) {
@@ -288,6 +292,13 @@ int build_graph(b200_ncsnpp* e) {
     }
     if (lvl != L - 1) {
       add_resblock(in_ch, 0, in_ch, 0, 1, all_res[lvl]);
+      if (c.progressive_input == 2) {
+        // Combine(dim1 = image channels, dim2 = in_ch, method 'sum') (layerspp.py:44-59, ncsnpp.py:163-166): Conv_0 is a 1x1
+        Mod m; m.kind = M_COMBINE; m.index = cur(); m.cin1 = ch; m.cout = in_ch; m.res = all_res[lvl] / 2;
+        m.w = add_param(e, nm("Conv_0.weight"), {in_ch, ch, 1, 1}, PK_CONV, 1, in_ch, ch, 0);
+        m.b = add_param(e, nm("Conv_0.bias"), {in_ch}, PK_COPY, 0, 0, 0, 0);
+        e->mods.push_back(m);
+      }
       if (c.progressive_input == 1) {
         Mod m; m.kind = M_PYR_DOWN; m.index = cur(); m.cin1 = pyr_ch; m.cout = in_ch; m.res = all_res[lvl];
         // FIR-padded stride-2 VALID conv: on tcgen05 via TMA element strides when the channel counts tile
@@ -315,9 +326,19 @@ int build_graph(b200_ncsnpp* e) {
       in_ch = out_ch;
     }
     if (has_attn(all_res[lvl])) add_attn(in_ch, all_res[lvl]);
+    if (c.progressive == 1) {
+      // output_skip (ncsnpp.py:190-203, 325-341): GroupNorm + SiLU + conv3x3 (in_ch -> image channels) at every level;
+      // the image-channel pyramid is upsampled and summed, and IS the network output
+      { Mod m; m.kind = M_GN_OUT; m.index = cur(); m.cin1 = in_ch; m.res = all_res[lvl];
+        m.w = add_param(e, nm("weight"), {in_ch}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {in_ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+      { Mod m; m.kind = M_CONV_OUT; m.index = cur(); m.cin1 = in_ch; m.cout = ch; m.res = all_res[lvl]; m.tc0 = false;
+        m.w = add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0);
+        m.b = add_param(e, nm("bias"), {ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
+    }
     if (lvl != 0) add_resblock(in_ch, 0, in_ch, 1, 0, all_res[lvl]);
   }
   B200_REQUIRE(hs_c.empty(), "ncsnpp: internal skip-stack mismatch");
+  if (c.progressive != 1) {
   { Mod m; m.kind = M_GN_OUT; m.index = cur(); m.cin1 = in_ch;
     m.w = add_param(e, nm("weight"), {in_ch}, PK_COPY, 0, 0, 0, 0); m.b = add_param(e, nm("bias"), {in_ch}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
   { Mod m; m.kind = M_CONV_OUT; m.index = cur(); m.cin1 = in_ch; m.cout = ch; m.res = c.image_size;
@@ -331,6 +352,7 @@ int build_graph(b200_ncsnpp* e) {
     m.w = m.tc0 ? add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV_PAD128, 9, ch, in_ch, om, -1, 9LL * 128 * in_ch)
                 : add_param(e, nm("weight"), {ch, in_ch, 3, 3}, PK_CONV, 9, ch, in_ch, 0);
     m.b = add_param(e, nm("bias"), {ch}, PK_COPY, 0, 0, 0, 0, -1, m.tc0 ? 128 : 0); e->mods.push_back(m); }
+  }
 
   // contiguous Dense_0 block: one [sumC][4nf] matrix + [sumC] bias for a single batched linear
   e->dense_w_off = e->wcount; e->wcount += ((long long)e->sumC * 4 * nf + 63) & ~63LL;
@@ -482,6 +504,15 @@ struct Builder {
     const int p = e->firn - 2;
     if (up) fir(x, B, H, H, C, 2, 1, (p + 1) / 2 + 1, p / 2, round, y, 4.f);
     else fir(x, B, H, H, C, 1, 2, (p + 1) / 2, p / 2, round, y, 1.f);
+  }
+
+  // the same 2x resampling on [planes][H][W] tensors (image-channel pyramids kept NCHW): Downsample / Upsample with
+  // with_conv=False (layerspp.py:113-126, 150-163): downsample_2d / upsample_2d, or avg_pool2d / nearest when fir=False
+  void resample2x_planes(const float* x, int planes, int H, bool up, float* y) {
+    if (e->cfg.naive_resample) { fir(x, planes, H, H, 1, up ? 2 : 1, up ? 1 : 2, up ? 1 : 0, 0, 0, y, up ? 1.f : 0.25f, /*box=*/true); return; }
+    const int p = e->firn - 2;
+    if (up) fir(x, planes, H, H, 1, 2, 1, (p + 1) / 2 + 1, p / 2, 0, y, 4.f);
+    else fir(x, planes, H, H, 1, 1, 2, (p + 1) / 2, p / 2, 0, y, 1.f);
   }
 
   void fir(const float* x, int major, int H, int W, int minor, int up, int down, int pad0, int pad1, int round, float* y,
@@ -818,7 +849,7 @@ struct Builder {
       tap(m.index, h0);
     }
     // input pyramid (progressive_input='residual', ncsnpp.py:289-301): starts as the network input
-    Tensor pyr; pyr.p = xc; pyr.C = ch; pyr.H = R; pyr.W = R; bool pyr_nchw = true; bool pyr_owned = false;
+    Tensor pyr; pyr.p = xc; pyr.C = ch; pyr.H = R; pyr.W = R; bool pyr_nchw = true; bool pyr_owned = false; long long pyr_bytes = 0;
     const int L = c.num_levels;
     for (int lvl = 0; lvl < L; ++lvl) {
       for (int b = 0; b < c.num_res_blocks; ++b) {
@@ -836,6 +867,27 @@ struct Builder {
         const Mod& m = e->mods[mi++];
         Tensor none; Tensor h = resblock(m, hs.back(), none); if (rc) return rc;
         tap(m.index, h);
+        if (c.progressive_input == 2) {
+          // input_skip (ncsnpp.py:289-292): the image pyramid is downsampled (no parameters) and a 1x1 convolution of it is
+          // added to h: Combine(method='sum') (layerspp.py:44-59)
+          const Mod& mc = e->mods[mi++];
+          const int Hin = pyr.H, Hn = Hin / 2;
+          long long nb; float* npyr = falloc((long long)B * ch * Hn * Hn, &nb);
+          resample2x_planes(pyr.p, B * ch, Hin, false, npyr);
+          if (pyr_owned) ffree(pyr.p, pyr_bytes);
+          pyr.p = npyr; pyr.H = pyr.W = Hn; pyr_owned = true; pyr_bytes = nb;
+          if (Hn != h.H) { set_error("ncsnpp: input pyramid geometry mismatch (%d vs %d)", Hn, h.H); return 2; }
+          Tensor out = talloc(mc.cout, h.H, h.W);
+          SimtConv sc; memset(&sc, 0, sizeof(sc));
+          sc.x1 = npyr; sc.C1 = ch; sc.in_nchw = 1; sc.in_scale = 1.f; sc.H = Hn; sc.W = Hn; sc.R = sc.S = 1; sc.stride = 1; sc.pad = 0;
+          sc.OH = Hn; sc.OW = Hn; sc.nbatch = B; sc.a_batched = 1; sc.w = e->W(mc.w); sc.N = mc.cout;
+          sc.epi.bias = e->W(mc.b); sc.epi.residual = h.p; sc.epi.ld_res = mc.cout; sc.epi.scale = 1.f;
+          sc.epi.rows_per_img = Hn * Hn; sc.epi.out = out.p; sc.epi.ld_out = mc.cout;
+          name("combine sum: conv1x1 %d->%d @%d +h [cuda-core]", ch, mc.cout, Hn);
+          op(1, [=](cudaStream_t st) { return launch_conv_simt(sc, st); }, 1, 2.0 * B * Hn * Hn * (double)mc.cout * ch);
+          tfree(h);
+          h = out; tap(mc.index, h);
+        }
         if (c.progressive_input == 1) {
           const Mod& mp = e->mods[mi++];
           // Downsample(fir, with_conv): FIR with pad (2,2) then 3x3 stride-2 VALID conv + bias
@@ -886,6 +938,7 @@ struct Builder {
       const Mod& m1 = e->mods[mi++]; Tensor h3 = resblock(m1, h, none); if (rc) return rc; tfree(h); h = h3; tap(m1.index, h);
     }
     // ---- up path (ncsnpp.py:316-364) ----
+    float* opyr = nullptr; long long opyr_bytes = 0;      // output_skip pyramid [B][ch][H][W] of the previous (coarser) level
     for (int lvl = L - 1; lvl >= 0; --lvl) {
       for (int b = 0; b < c.num_res_blocks + 1; ++b) {
         const Mod& m = e->mods[mi++];
@@ -897,12 +950,40 @@ struct Builder {
       if (e->mods[mi].kind == M_ATTN) {
         const Mod& ma = e->mods[mi++]; Tensor h2 = attn(ma, h); if (rc) return rc; tfree(h); h = h2; tap(ma.index, h);
       }
+      if (c.progressive == 1) {
+        // output_skip (ncsnpp.py:325-341): pyramid = upsample(pyramid) + conv3x3(SiLU(GroupNorm(h))) in image channels;
+        // the level-0 sum is the network output (divided by sigma when scale_by_sigma, :377-379)
+        const Mod& mg = e->mods[mi++]; const Mod& mo = e->mods[mi++];
+        const int Hl = h.H;
+        Tensor a = talloc(h.C, Hl, Hl);
+        const int hf16 = (om == 2 && h.C % 64 == 0) ? 1 : 0;
+        Tensor none; gn(h, none, mg.w, mg.b, 1, hf16 ? 2 : 0, a, nullptr);
+        long long ub = 0; float* up = nullptr;
+        if (opyr) {
+          up = falloc((long long)B * ch * Hl * Hl, &ub);
+          resample2x_planes(opyr, B * ch, Hl / 2, true, up);
+          ffree(opyr, opyr_bytes); opyr = nullptr;
+        }
+        long long nb = 0; float* dst = nullptr;
+        if (lvl != 0) dst = falloc((long long)B * ch * Hl * Hl, &nb);
+        const float *wo = e->W(mo.w), *bo = e->W(mo.b);
+        const Tensor ain = a; const int Bc2 = B, sbs = c.scale_by_sigma, last = lvl == 0;
+        if (ch > 4) { set_error("ncsnpp: output_skip needs <= 4 image channels"); return 2; }
+        name("conv3x3 %d->%d @%d nchw-out +pyramid [small-n]", a.C, ch, Hl);
+        op(1, [=](cudaStream_t st) {
+          return launch_conv3x3_small_n(ain.p, wo, bo, (last && sbs) ? eng->in_labels_l[ln] : nullptr, eng->uniform ? 0 : 1,
+                                        last ? eng->out_l[ln] : dst, Bc2, Hl, Hl, ain.C, ch, hf16, st, up);
+        }, 1, 2.0 * B * Hl * Hl * (double)ch * a.C * 9);
+        tfree(a);
+        if (up) ffree(up, ub);
+        opyr = dst; opyr_bytes = nb;
+      }
       if (lvl != 0) {
         Tensor none; const Mod& m = e->mods[mi++]; Tensor h2 = resblock(m, h, none); if (rc) return rc; tfree(h); h = h2; tap(m.index, h);
       }
     }
-    // ---- output head (ncsnpp.py:371-379) ----
-    {
+    // ---- output head (ncsnpp.py:371-379); with output_skip the pyramid already is the output ----
+    if (c.progressive != 1) {
       const Mod& mg = e->mods[mi++];
       Tensor a = talloc(h.C, h.H, h.W);
       // fp16 operand mode: the head's input is stored as fp16 too (the CUDA-core head is bound by its nine-fold

@@ -37,7 +37,8 @@ int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin,
 int launch_attn_small_configure(int T, int C);
 int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st);
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
-                           float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st);
+                           float* out_nchw, int B, int H, int W, int C, int N, int x_f16, cudaStream_t st,
+                           const float* add_nchw = nullptr);
 
 // ---- conv_simt.cu : strict-fp32 CUDA-core implicit GEMM (any shape) ---------
 struct SimtConv {

@@ -24,8 +24,9 @@ from . import utils
 from .. import _lib
 
 _SUPPORTED = ("engine supports embedding_type in {'fourier','positional'}, conditional=True, resblock_type='biggan', "
-              "fir in {True, False} (progressive_input='residual' needs fir=True), progressive='none', "
-              "progressive_input in {'none','residual'}; positional embeddings need scale_by_sigma=False")
+              "fir in {True, False} (progressive_input='residual' needs fir=True), progressive in {'none','output_skip'}, "
+              "progressive_input in {'none','residual','input_skip'} with progressive_combine='sum'; "
+              "positional embeddings need scale_by_sigma=False")
 
 
 def _variance_scaling_uniform(shape, scale, in_axis=1, out_axis=0):
@@ -92,6 +93,13 @@ def _attn(c, init_scale):
   return h
 
 
+def _combine(dim1, dim2):
+  """``layerspp.Combine`` (``layerspp.py:44-59``): ``Conv_0`` is a 1x1 convolution dim1 -> dim2."""
+  h = _Holder()
+  h.Conv_0 = _conv(dim1, dim2, 1)
+  return h
+
+
 def _pyramid_down(cin, cout):
   h = _Holder()
   inner = _Holder()
@@ -115,7 +123,9 @@ class NCSNpp(nn.Module):
     m = config.model
     emb = m.embedding_type.lower()
     if (emb not in ('fourier', 'positional') or not m.conditional or m.resblock_type.lower() != 'biggan'
-        or m.progressive.lower() != 'none' or m.progressive_input.lower() not in ('none', 'residual')
+        or m.progressive.lower() not in ('none', 'output_skip')
+        or m.progressive_input.lower() not in ('none', 'residual', 'input_skip')
+        or (m.progressive_input.lower() == 'input_skip' and str(getattr(m, 'progressive_combine', 'sum')).lower() != 'sum')
         or (not m.fir and m.progressive_input.lower() == 'residual')
         or (emb == 'positional' and m.scale_by_sigma)):
       raise NotImplementedError(f'NCSNpp: {_SUPPORTED}')
@@ -166,7 +176,9 @@ class NCSNpp(nn.Module):
         hs_c.append(in_ch)
       if lvl != L - 1:
         mods.append(_resblock(in_ch, in_ch, temb_dim, init_scale, down=True))
-        if m.progressive_input.lower() == 'residual':
+        if m.progressive_input.lower() == 'input_skip':
+          mods.append(_combine(channels, in_ch))
+        elif m.progressive_input.lower() == 'residual':
           mods.append(_pyramid_down(pyr_ch, in_ch))
           pyr_ch = in_ch
         hs_c.append(in_ch)
@@ -180,11 +192,15 @@ class NCSNpp(nn.Module):
         in_ch = out_ch
       if all_res[lvl] in m.attn_resolutions:
         mods.append(_attn(in_ch, init_scale))
+      if m.progressive.lower() == 'output_skip':      # ncsnpp.py:190-203
+        mods.append(_gn(in_ch))
+        mods.append(_conv(in_ch, channels, 3, init_scale))
       if lvl != 0:
         mods.append(_resblock(in_ch, in_ch, temb_dim, init_scale, up=True))
     assert not hs_c
-    mods.append(_gn(in_ch))
-    mods.append(_conv(in_ch, channels, 3, init_scale))
+    if m.progressive.lower() != 'output_skip':
+      mods.append(_gn(in_ch))
+      mods.append(_conv(in_ch, channels, 3, init_scale))
     self.all_modules = nn.ModuleList(mods)
     self._engine = None        # (handle, blob, workspace, batch, weights_version)
     self._weights_version = 0
@@ -206,7 +222,8 @@ class NCSNpp(nn.Module):
       c.attn_resolutions[i] = int(v)
     c.centered, c.scale_by_sigma = int(bool(cfg.data.centered)), int(bool(m.scale_by_sigma))
     c.skip_rescale, c.conditional = int(bool(m.skip_rescale)), int(bool(m.conditional))
-    c.progressive_input = 1 if m.progressive_input.lower() == 'residual' else 0
+    c.progressive_input = {'none': 0, 'residual': 1, 'input_skip': 2}[m.progressive_input.lower()]
+    c.progressive = 1 if m.progressive.lower() == 'output_skip' else 0
     c.fir_taps = len(m.fir_kernel)
     for i, v in enumerate(m.fir_kernel):
       c.fir_kernel[i] = float(v)

@@ -37,6 +37,12 @@ def golden_config(name):
     c = configs.vp_cifar10_ddpmpp_continuous()
     c.model.init_scale = 1.0
     return c
+  if name == 'tiny_progressive':
+    return configs.tiny_progressive()
+  if name in ('celebahq_256', 'ffhq_1024'):
+    c = configs.ve_celebahq_256_ncsnpp_continuous() if name == 'celebahq_256' else configs.ve_ffhq_1024_ncsnpp_continuous()
+    c.model.init_scale = 1.0
+    return c
   raise KeyError(name)
 
 

@@ -217,6 +217,30 @@ def test_ddpmpp_engine_param_table_has_the_reference_names_plus_the_frequency_ta
     seeded_model(cfg)
 
 
+def test_progressive_family_param_tables_match_module():
+  """output_skip / input_skip: engine parameter table == module parameters for a small member and for the
+  full-size CelebA-HQ-256 / FFHQ-1024 configurations (whose state_dict layouts tools/make_golden_progressive.py loads
+  into the reference's constructor with strict=True: 65 574 549 and 105 785 896 parameters)."""
+  for name, nparams in (('tiny_progressive', None), ('celebahq_256', 65574549), ('ffhq_1024', 105785896)):
+    cfg = golden_config(name)
+    m = seeded_model(cfg)
+    table = m.native_param_table()
+    sd = dict(m.named_parameters())
+    assert sorted(n for n, _ in table) == sorted(sd), name
+    for n, shape in table:
+      assert tuple(sd[n].shape) == shape
+    if nparams:
+      assert sum(p.numel() for p in m.parameters()) == nparams
+  cfg = golden_config('tiny_progressive')
+  cfg.model.progressive_combine = 'cat'
+  with pytest.raises(NotImplementedError):
+    seeded_model(cfg)
+  cfg = golden_config('tiny_progressive')
+  cfg.model.progressive = 'residual'
+  with pytest.raises(NotImplementedError):
+    seeded_model(cfg)
+
+
 def test_product_model_has_no_cpu_path():
   m = seeded_model(golden_config('tiny'))
   with pytest.raises(RuntimeError, match='CUDA'):

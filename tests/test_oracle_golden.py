@@ -18,7 +18,7 @@ def test_upfirdn2d_oracle_matches_reference(name):
   assert torch.equal(y, torch.from_numpy(g[name + '_y']))
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_vp', 'tiny_noattn', 'tiny_ddpmpp'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_vp', 'tiny_noattn', 'tiny_ddpmpp', 'tiny_progressive'])
 def test_ncsnpp_oracle_matches_reference(name):
   g = golden(f'ncsnpp_{name}.npz')
   cfg = golden_config(name)
