@@ -255,7 +255,10 @@ int build_graph(b200_ncsnpp* e) {
     m.tcattn = tcmode && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
     // fp16 operands: the logits/probabilities never leave the chip, so only the fused core is implemented
     if (om == 2 && !tc_attn_supported(T, C)) m.tcattn = false;
-    m.tc0 = tcmode && (C % 128 == 0) && (m.tcattn || T <= 64);   // q/k/v projections on tensor cores
+    // few tokens: q, k, v and the logits of one image fit one CTA's shared memory (attn_small_kernel); otherwise (e.g. the
+    // 8x8, 512-channel bottleneck of FFHQ-1024) the block runs as separate contractions on CUDA cores
+    const bool small_ok = T <= 64 && ((size_t)3 * T * C + (size_t)T * T) * sizeof(float) <= 200 * 1024;
+    m.tc0 = tcmode && (C % 128 == 0) && (m.tcattn || small_ok);   // q/k/v projections on tensor cores
     m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {C}, PK_COPY, 0, 0, 0, 0);
     m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {C}, PK_COPY, 0, 0, 0, 0);
     // q,k,v projection weights packed as one [3C][C] block (rows: q, k, v), biases as one [3C] vector

@@ -18,7 +18,7 @@ def dev():
   return torch.device('cuda:0')
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'f16'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])     # (32/64-channel layers: off the fp16 tiling; full-size f16 below)
 def test_progressive_tiny_matches_oracle_and_reference_golden(dev, precision):
   g = golden('ncsnpp_tiny_progressive.npz')
   cfg = golden_config('tiny_progressive')
