@@ -201,3 +201,68 @@ def ode_sample(sde, model, shape, z=None, denoise=False, rtol=1e-5, atol=1e-5, m
       vec_eps = torch.ones(shape[0], device=x.device) * eps
       _, x = reverse_diffusion_step(sde, model, x, vec_eps, continuous=True, probability_flow=False)
     return x, sol.nfev
+
+
+# ---- controllable generation (controllable_generation.py) ------------------------------------------------------------
+_COLOR_M = torch.tensor([[5.7735014e-01, -8.1649649e-01, 4.7008697e-08],
+                         [5.7735026e-01, 4.0824834e-01, 7.0710671e-01],
+                         [5.7735026e-01, 4.0824822e-01, -7.0710683e-01]])                       # :109-111
+
+
+def _marginal(sde, x, t):
+  """(mean, std) of p_t(x(t) | x(0)): sde_lib.py:233-236 (VE), :141-145 (VP), :190-194 (sub-VP)."""
+  if sde.kind == 've':
+    return x, sde.sigma(t)
+  lmc = -0.25 * t ** 2 * (sde.beta_1 - sde.beta_0) - 0.5 * t * sde.beta_0
+  return torch.exp(lmc)[:, None, None, None] * x, sde.std(t)
+
+
+def _pc_update(sde, model, x, vec_t, which, name, snr, n_steps, continuous):
+  if which == 'corrector':
+    return langevin_step(sde, model, x, vec_t, snr, n_steps, continuous) if name == 'langevin' else (x, x)
+  if name == 'reverse_diffusion':
+    return reverse_diffusion_step(sde, model, x, vec_t, continuous)
+  if name == 'euler_maruyama':
+    return euler_maruyama_step(sde, model, x, vec_t, continuous)
+  return x, x
+
+
+def inpaint_sample(sde, model, data, mask, predictor='reverse_diffusion', corrector='langevin', snr=0.16, n_steps=1,
+                   continuous=True, denoise=True, eps=1e-5):
+  """controllable_generation.py:57-78 with the update of :43-52."""
+  with torch.no_grad():
+    x = data * mask + sde.prior_sampling(data.shape).to(data.device) * (1. - mask)                # :71
+    timesteps = torch.linspace(sde.T, eps, sde.N)
+    x_mean = x
+    for i in range(sde.N):
+      for which, name in (('corrector', corrector), ('predictor', predictor)):                    # :75-76
+        vec_t = torch.ones(data.shape[0], device=data.device) * timesteps[i]
+        x, x_mean = _pc_update(sde, model, x, vec_t, which, name, snr, n_steps, continuous)
+        mean, std = _marginal(sde, data, vec_t)
+        noisy = mean + torch.randn_like(x) * std[:, None, None, None]                             # :48
+        x = x * (1. - mask) + noisy * mask
+        x_mean = x * (1. - mask) + mean * mask                                                    # :50 (uses the blended x)
+    return x_mean if denoise else x
+
+
+def colorize_sample(sde, model, gray, predictor='reverse_diffusion', corrector='langevin', snr=0.16, n_steps=1,
+                    continuous=True, denoise=True, eps=1e-5):
+  """controllable_generation.py:172-196 with the update of :137-146."""
+  M = _COLOR_M.to(gray.device)
+  invM = torch.inverse(_COLOR_M).to(gray.device)
+  dec = lambda v: torch.einsum('bihw,ij->bjhw', v, M)
+  cou = lambda v: torch.einsum('bihw,ij->bjhw', v, invM)
+  with torch.no_grad():
+    mask = torch.cat([torch.ones_like(gray[:, :1]), torch.zeros_like(gray[:, 1:])], dim=1)        # :152-155
+    x = cou(dec(gray) * mask + dec(sde.prior_sampling(gray.shape).to(gray.device) * (1. - mask)))  # :186-188
+    timesteps = torch.linspace(sde.T, eps, sde.N)
+    x_mean = x
+    for i in range(sde.N):
+      for which, name in (('corrector', corrector), ('predictor', predictor)):
+        vec_t = torch.ones(gray.shape[0], device=gray.device) * timesteps[i]
+        x, x_mean = _pc_update(sde, model, x, vec_t, which, name, snr, n_steps, continuous)
+        mean, std = _marginal(sde, dec(gray), vec_t)
+        noisy = mean + torch.randn_like(x) * std[:, None, None, None]
+        x = cou(dec(x) * (1. - mask) + noisy * mask)
+        x_mean = cou(dec(x) * (1. - mask) + mean * mask)
+    return x_mean if denoise else x
