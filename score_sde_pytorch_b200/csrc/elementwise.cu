@@ -324,6 +324,61 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   return 0;
 }
 
+// ---- GroupNorm for group sizes that are not a multiple of four channels -------------------------------------------------
+// nn.GroupNorm(min(C/4, 32), C) gives 6 channels per group for C = 192 (the 128+64 concatenation of FFHQ-1024's up
+// path): such groups straddle the aligned channel quads the fused statistics are kept in.  These rare layers take a plain
+// two-kernel path: per-(image, group) mean / rstd in fp64, then an elementwise apply over the (two-source) tensor.
+__global__ void __launch_bounds__(256) gn_generic_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                                               int HW, int G, float eps, float2* __restrict__ mr) {
+  const int C = C1 + C2, cpg = C / G, g = blockIdx.x, b = blockIdx.y;
+  double s = 0.0, ss = 0.0;
+  for (long long i = threadIdx.x; i < (long long)HW * cpg; i += blockDim.x) {
+    const int pix = (int)(i / cpg), c = g * cpg + (int)(i % cpg);
+    const float v = c < C1 ? x1[((long long)b * HW + pix) * C1 + c] : x2[((long long)b * HW + pix) * C2 + (c - C1)];
+    s += v; ss += (double)v * v;
+  }
+  __shared__ double sh[2][8];
+  s = warp_sum_d(s); ss = warp_sum_d(ss);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, q = 0.0;
+    for (int w = 0; w < 8; ++w) { a += sh[0][w]; q += sh[1][w]; }
+    const double n = (double)HW * cpg, mean = a / n;
+    const float var = fmaxf((float)(q / n - mean * mean), 0.f);
+    mr[(long long)b * G + g] = make_float2((float)mean, rsqrtf(var + eps));
+  }
+}
+__global__ void __launch_bounds__(256) gn_generic_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                                               const float2* __restrict__ mr, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int B, int HW, int G, int act,
+                                                               int round_out, float* __restrict__ y, float* __restrict__ raw) {
+  const int C = C1 + C2, cpg = C / G;
+  const long long total = (long long)B * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bp = i / C;                            // b * HW + pix
+    const int b = (int)(bp / HW);
+    const float v = c < C1 ? x1[bp * C1 + c] : x2[bp * C2 + (c - C1)];
+    const float2 m = mr[(long long)b * G + c / cpg];
+    float o = (v - m.x) * m.y * __ldg(gamma + c) + __ldg(beta + c);
+    if (act) o = round_out ? silu_fast(o) : silu_f(o);
+    store_operand1(y, i, o, round_out);
+    if (raw) store_operand1(raw, i, v, round_out);
+  }
+}
+int launch_gn_generic(const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, int B, int HW, int G,
+                      float eps, int act, int round_out, float* y, float* raw, float* mr_ws, cudaStream_t st) {
+  const int C = C1 + C2;
+  B200_REQUIRE(C % G == 0 && mr_ws, "gn_generic: C=%d G=%d", C, G);
+  gn_generic_stats_kernel<<<dim3(G, B), 256, 0, st>>>(x1, C1, x2, C2, HW, G, eps, reinterpret_cast<float2*>(mr_ws));
+  const long long total = (long long)B * HW * C;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  gn_generic_apply_kernel<<<grid, 256, 0, st>>>(x1, C1, x2, C2, reinterpret_cast<const float2*>(mr_ws), gamma, beta, B, HW, G, act, round_out, y, raw);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
 // GroupNorm folded into per-(image, channel) affine coefficients: scale = rstd * gamma, shift = beta - mean * scale,
 // from the same fp64 quad sums and with the same fp32 operations as gn_apply_stream_kernel (so a consumer that applies
 // fma(x, scale, shift) reproduces that kernel bit for bit).  Consumed by the convolutions that normalise their input on

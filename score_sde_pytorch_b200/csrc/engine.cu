@@ -428,6 +428,17 @@ struct Builder {
   }
   void gn(Tensor& x1, Tensor& x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
     const int C = x1.C + x2.C, G = std::min(C / 4, 32), HW = x1.H * x1.W;
+    if ((C / G) % 4 != 0) {
+      // groups that are not whole channel quads (C = 192 -> 6 channels per group): the generic two-kernel path
+      if (x1.f16 || x2.f16) { set_error("ncsnpp: GroupNorm with %d-channel groups on an fp16 tensor", C / G); rc = 2; return; }
+      long long mb; float* mr = falloc(2LL * B * G, &mb);
+      const float *g = e->W(pgw), *bt = e->W(pgb);
+      const Tensor a = x1, b = x2; const int Bc = B;
+      name("gn_generic %d+%d @%d (%d-channel groups)", x1.C, x2.C, x1.H, C / G);
+      op(2, [=](cudaStream_t st) { return launch_gn_generic(a.p, a.C, b.p, b.C, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, mr, st); }, 2);
+      ffree(mr, mb);
+      return;
+    }
     ensure_qs(x1); ensure_qs(x2);
     const float *g = e->W(pgw), *bt = e->W(pgb);
     const Tensor a = x1, b = x2; const int Bc = B;

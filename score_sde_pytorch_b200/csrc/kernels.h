@@ -14,6 +14,8 @@ int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cu
 int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
                     const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
                     int round_out, float* y, float* raw, cudaStream_t st, int x1_f16 = 0);
+int launch_gn_generic(const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, int B, int HW, int G,
+                      float eps, int act, int round_out, float* y, float* raw, float* mr_ws, cudaStream_t st);
 int launch_gn_coeff(int C1, int C2, const double* q1, const double* q2, const float* gamma, const float* beta, int B, int HW,
                     int G, float eps, float* scale, float* shift, cudaStream_t st);
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,

@@ -13,7 +13,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench                                                # noqa: E402
-from score_sde_pytorch_b200.op import upfirdn2d as ours     # noqa: E402
+from score_sde_pytorch_b200.op import upfirdn2d as ours_upfirdn2d     # noqa: E402  (the function; the package re-exports it)
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--md', default=None)
@@ -54,9 +54,9 @@ for name, shape, kk, up, down, pad in cases:
   torch.manual_seed(0)
   x = torch.randn(*shape, device=dev)
   kt = torch.tensor(kk, device=dev)
-  y = ours.upfirdn2d(x, kt, up=up, down=down, pad=pad)
+  y = ours_upfirdn2d(x, kt, up=up, down=down, pad=pad)
   nbytes = (x.numel() + y.numel()) * 4
-  t_ours = timed(lambda: ours.upfirdn2d(x, kt, up=up, down=down, pad=pad))
+  t_ours = timed(lambda: ours_upfirdn2d(x, kt, up=up, down=down, pad=pad))
   if ref_upfirdn2d is not None:
     yr = ref_upfirdn2d(x, kt, up=up, down=down, pad=pad)
     t_ref = timed(lambda: ref_upfirdn2d(x, kt, up=up, down=down, pad=pad))
