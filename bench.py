@@ -567,6 +567,16 @@ def run_gpu_arm(args):
         variants['f16_groupnorm_' + ('on_load' if args.separate_groupnorm else 'separate_pass')] = dict(
             value=round(B / (N_SAMPLER_STEPS * ms3 * 1e-3), 4), unit='images/s', ms_per_step=round(ms3, 4))
         del plan3, model3
+        # A/B of programmatic dependent launch (the headline plan uses the package default)
+        torch.manual_seed(0)
+        model4 = NCSNpp(cfg, precision='f16', separate_groupnorm=args.separate_groupnorm, pdl=not model.pdl).to(dev)
+        plan4 = native.match_pc_plan(sde=sde, model=model4, predictor=sampling.ReverseDiffusionPredictor,
+                                     corrector=sampling.LangevinCorrector, shape=shape, snr=cfg.sampling.snr, n_steps=1,
+                                     probability_flow=False, continuous=True, eps=1e-5, device=dev)
+        ms4 = timed_steps(plan4, x_host.to(dev), args.warmup, args.steps)
+        variants['f16_pdl_' + ('off' if model.pdl else 'on')] = dict(value=round(B / (N_SAMPLER_STEPS * ms4 * 1e-3), 4), unit='images/s',
+                                                                   ms_per_step=round(ms4, 4))
+        del plan4, model4
     # ---- strong-scaling probe: the same 1024-image job cut over 8 GPUs is 128 images per GPU; time that
     # per-GPU share here and name the launches that under-fill the 148 SMs ----
     strong = None

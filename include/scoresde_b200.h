@@ -127,6 +127,9 @@ typedef struct {
   int progressive;              /* 0 = none; 1 = output_skip (ncsnpp.py:190-203, 325-341, 366-367): every level adds
                                  * conv3x3(SiLU(GroupNorm(h))) in image channels to the upsampled pyramid, which is the output
                                  * (the high-resolution NCSN++ family: configs/ve/{ffhq,celebahq}_*_ncsnpp_continuous.py) */
+  int pdl;                      /* 1: every launch of a forward / PC iteration carries the programmatic-dependent-launch attribute
+                                 * (each kernel waits for its predecessor with griddepcontrol.wait after its own prologue, so launch
+                                 * latency, barrier init and TMEM allocation of kernel k+1 overlap the tail of kernel k) */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

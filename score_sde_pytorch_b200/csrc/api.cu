@@ -6,6 +6,11 @@
 #include <cstring>
 
 namespace b200 {
+namespace { thread_local bool tl_pdl = false; }
+bool pdl_active() { return tl_pdl; }
+PdlScope::PdlScope(bool on) : prev(tl_pdl) { tl_pdl = on; }
+PdlScope::~PdlScope() { tl_pdl = prev; }
+
 
 static thread_local char g_err[1024] = "";
 

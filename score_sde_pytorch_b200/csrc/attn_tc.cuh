@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait(); pdl_trigger();   // prologue done; nothing above touched global memory (common.cuh)
   const long long total_tiles = 2LL * p.nimg;
   constexpr int KB = L::KB;        // K blocks in every phase (C = T = 256 elements)
   constexpr int BKA = L::BKA;

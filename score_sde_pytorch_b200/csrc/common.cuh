@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <string>
+#include <utility>
 
 namespace b200 {
 
@@ -94,6 +95,30 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Every kernel of this library starts with griddepcontrol.wait - which returns once the preceding kernel of the stream has
+// completed and its memory is visible, i.e. ordinary stream order - followed by griddepcontrol.launch_dependents, which
+// lets the NEXT kernel's CTAs be scheduled as soon as all of this kernel's CTAs are running.  The tensor-core kernels put
+// the pair after their prologue (barrier init, TMEM allocation), so that prologue and the launch latency of kernel k+1
+// overlap the tail of kernel k (464 launches per PC step).  Without the launch attribute both instructions are no-ops.
+// Host side: launch_kernel() adds cudaLaunchAttributeProgrammaticStreamSerialization when the calling engine asked for it
+// (b200_ncsnpp_config.pdl; a thread-local scope set by the forward / PC-loop entry points - nothing process-global).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_active();                                   // api.cu
+struct PdlScope { bool prev; explicit PdlScope(bool on); ~PdlScope(); };
+template <typename... KP, typename... A>
+inline void launch_kernel(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at = {};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  const bool on = pdl_active();
+  cfg.attrs = on ? &at : nullptr; cfg.numAttrs = on ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);   // a failure is picked up by B200_CHECK_LAUNCH()
 }
 
 // ---- the one contraction descriptor both conv back-ends implement ----------

@@ -18,6 +18,7 @@ constexpr int BK = 16;
 
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConv p) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads per CTA");
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -171,12 +172,12 @@ int launch_conv_simt(const SimtConv& p, cudaStream_t st) {
     constexpr int BM = 256, BN = 8;
     const long long tiles = (long long)p.nbatch * ceil_div(rows_per_img, BM) * ceil_div(p.N, BN);
     const int grid = (int)std::min<long long>(tiles, 148LL * 8);
-    conv_simt_kernel<BM, BN, 1, 8><<<grid, 256, 0, st>>>(p);
+    launch_kernel(conv_simt_kernel<BM, BN, 1, 8>, dim3(grid), dim3(256), 0, st, p);
   } else {
     constexpr int BM = 64, BN = 64;
     const long long tiles = (long long)p.nbatch * ceil_div(rows_per_img, BM) * ceil_div(p.N, BN);
     const int grid = (int)std::min<long long>(tiles, 148LL * 8);
-    conv_simt_kernel<BM, BN, 4, 4><<<grid, 256, 0, st>>>(p);
+    launch_kernel(conv_simt_kernel<BM, BN, 4, 4>, dim3(grid), dim3(256), 0, st, p);
   }
   B200_CHECK_LAUNCH();
   return 0;

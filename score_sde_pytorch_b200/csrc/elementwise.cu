@@ -27,6 +27,7 @@ constexpr int GN_THREADS = 384;   // divisible by C/4 for every channel count of
 
 __global__ void __launch_bounds__(GN_THREADS) gn_quad_stats_kernel(
     const float* __restrict__ x, int C, int HW, double* __restrict__ qsums /* [B][C/4][2] */) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   extern __shared__ double sred[];   // [lanes][Q][2]
   const int Q = C >> 2, b = blockIdx.x;
   const float* px = x + (long long)b * HW * C;
@@ -78,7 +79,7 @@ int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cu
   const int Q = C / 4;
   const size_t smem = (GN_THREADS % Q == 0) ? (size_t)GN_THREADS * 2 * sizeof(double) : (size_t)2 * Q * sizeof(double);
   B200_REQUIRE(smem <= 48 * 1024, "gn_quad_stats: C=%d too large", C);
-  gn_quad_stats_kernel<<<B, GN_THREADS, smem, st>>>(x, C, HW, qsums);
+  launch_kernel(gn_quad_stats_kernel, dim3(B), dim3(GN_THREADS), smem, st, x, C, HW, qsums);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
     const double* __restrict__ q1, const double* __restrict__ q2,
     const float* __restrict__ gamma, const float* __restrict__ beta,
     int HW, int G, float eps, int act, int round_out, float* __restrict__ y, float* __restrict__ raw) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_stream_kernel(
     const double* __restrict__ q1, const double* __restrict__ q2,
     const float* __restrict__ gamma, const float* __restrict__ beta,
     int HW, int G, float eps, double inv_n, float* __restrict__ y, float* __restrict__ raw) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   __shared__ float4 s_sc[128], s_sh[128];
   const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
   if (threadIdx.x < Q) {
@@ -284,7 +287,7 @@ template <bool XH, int MODE>
 static void gn_stream_launch(dim3 grid, int threads, cudaStream_t st, int act, bool has_raw, const float* x1, int C1, const float* x2,
                              int C2, const double* q1, const double* q2, const float* gamma, const float* beta, int HW, int G,
                              float eps, double inv_n, float* y, float* raw) {
-#define B200_GNS(A, R) gn_apply_stream_kernel<XH, MODE, A, R><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw)
+#define B200_GNS(A, R) launch_kernel(gn_apply_stream_kernel<XH, MODE, A, R>, dim3(grid), dim3(threads), 0, st, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, inv_n, y, raw)
   if (act) { if (has_raw) B200_GNS(true, true); else B200_GNS(true, false); }
   else { if (has_raw) B200_GNS(false, true); else B200_GNS(false, false); }
 #undef B200_GNS
@@ -318,8 +321,8 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
     B200_CHECK_LAUNCH();
     return 0;
   }
-  if (x1_f16) gn_apply_kernel<true><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
-  else gn_apply_kernel<false><<<grid, threads, 0, st>>>(x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
+  if (x1_f16) launch_kernel(gn_apply_kernel<true>, dim3(grid), dim3(threads), 0, st, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
+  else launch_kernel(gn_apply_kernel<false>, dim3(grid), dim3(threads), 0, st, x1, C1, x2, C2, q1, q2, gamma, beta, HW, G, eps, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -330,6 +333,7 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
 // two-kernel path: per-(image, group) mean / rstd in fp64, then an elementwise apply over the (two-source) tensor.
 __global__ void __launch_bounds__(256) gn_generic_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                                                int HW, int G, float eps, float2* __restrict__ mr) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int C = C1 + C2, cpg = C / G, g = blockIdx.x, b = blockIdx.y;
   double s = 0.0, ss = 0.0;
   for (long long i = threadIdx.x; i < (long long)HW * cpg; i += blockDim.x) {
@@ -353,6 +357,7 @@ __global__ void __launch_bounds__(256) gn_generic_apply_kernel(const float* __re
                                                                const float2* __restrict__ mr, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, int B, int HW, int G, int act,
                                                                int round_out, float* __restrict__ y, float* __restrict__ raw) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int C = C1 + C2, cpg = C / G;
   const long long total = (long long)B * HW * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -371,10 +376,10 @@ int launch_gn_generic(const float* x1, int C1, const float* x2, int C2, const fl
                       float eps, int act, int round_out, float* y, float* raw, float* mr_ws, cudaStream_t st) {
   const int C = C1 + C2;
   B200_REQUIRE(C % G == 0 && mr_ws, "gn_generic: C=%d G=%d", C, G);
-  gn_generic_stats_kernel<<<dim3(G, B), 256, 0, st>>>(x1, C1, x2, C2, HW, G, eps, reinterpret_cast<float2*>(mr_ws));
+  launch_kernel(gn_generic_stats_kernel, dim3(dim3(G, B)), dim3(256), 0, st, x1, C1, x2, C2, HW, G, eps, reinterpret_cast<float2*>(mr_ws));
   const long long total = (long long)B * HW * C;
   const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-  gn_generic_apply_kernel<<<grid, 256, 0, st>>>(x1, C1, x2, C2, reinterpret_cast<const float2*>(mr_ws), gamma, beta, B, HW, G, act, round_out, y, raw);
+  launch_kernel(gn_generic_apply_kernel, dim3(grid), dim3(256), 0, st, x1, C1, x2, C2, reinterpret_cast<const float2*>(mr_ws), gamma, beta, B, HW, G, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -386,6 +391,7 @@ int launch_gn_generic(const float* x1, int C1, const float* x2, int C2, const fl
 __global__ void __launch_bounds__(128) gn_coeff_kernel(const double* __restrict__ q1, int C1, const double* __restrict__ q2, int C2,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, int G,
                                                        float eps, double inv_n, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int C = C1 + C2, Q = C >> 2, cpg = C / G, b = blockIdx.y;
   const int qd = blockIdx.x * blockDim.x + threadIdx.x;
   if (qd >= Q) return;
@@ -414,7 +420,7 @@ int launch_gn_coeff(int C1, int C2, const double* q1, const double* q2, const fl
   B200_REQUIRE(q1 && (C2 == 0 || q2) && scale && shift, "gn_coeff: null pointer");
   const double inv_n = 1.0 / ((double)HW * (C / G));
   dim3 grid((C / 4 + 127) / 128, B);
-  gn_coeff_kernel<<<grid, 128, 0, st>>>(q1, C1, q2, C2, gamma, beta, G, eps, inv_n, scale, shift);
+  launch_kernel(gn_coeff_kernel, dim3(grid), dim3(128), 0, st, q1, C1, q2, C2, gamma, beta, G, eps, inv_n, scale, shift);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -440,6 +446,7 @@ struct FirParams {
 template <int VEC>
 __global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                        const FirParams p) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int mv = p.minor / VEC;
   const long long total = (long long)p.major * p.out_h * p.out_w * mv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -484,6 +491,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict_
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                        const FirParams p) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   // grid = (x chunks over out_w * minor/4, out_h, images): no 64-bit div/mod chain per thread (the flat-index
   // version spent more instructions decoding its index than filtering)
   const int mv = p.minor >> 2;
@@ -518,6 +526,7 @@ __global__ void __launch_bounds__(256) fir4_nhwc_kernel(const float* __restrict_
 //   out[2i+ay][2j+ax] = sum over the two live taps per axis:  ay=0: (a=0, iy=i-1), (a=2, iy=i);  ay=1: (a=1, iy=i), (a=3, iy=i+1)
 __global__ void __launch_bounds__(256) fir4_up2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            const FirParams p) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int mv = p.minor >> 2;
   const unsigned xi = blockIdx.x * blockDim.x + threadIdx.x;   // grid = (x chunks over in_w * minor/4, in_h, images)
   if (xi >= (unsigned)(p.in_w * mv)) return;
@@ -560,6 +569,7 @@ __global__ void __launch_bounds__(256) fir4_up2_nhwc_kernel(const float* __restr
 // out[oy, ox] = sum_{a,b} kf[a][b] * u[oy*D + a, ox*D + b], kf = flipped FIR, u = x zero-inserted by U and padded by p0.
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(128) fir4_planar_kernel(const float* __restrict__ x, float* __restrict__ y, const FirParams p) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int qw = (p.out_w + 3) >> 2;                      // four-output groups per row
   const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= (long long)p.major * p.out_h * qw) return;
@@ -642,13 +652,13 @@ int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int maj
     const dim3 grid((unsigned)((p.out_w * mv + threads - 1) / threads), (unsigned)p.out_h, (unsigned)major);
     if (up_x == 2 && down_x == 1 && pad_x0 == 2 && p.out_h == 2 * in_h && p.out_w == 2 * in_w) {
       const int tin = (in_w * mv >= 256) ? 256 : 128;
-      fir4_up2_nhwc_kernel<<<dim3((unsigned)((in_w * mv + tin - 1) / tin), (unsigned)in_h, (unsigned)major), tin, 0, st>>>(x, y, p);
+      launch_kernel(fir4_up2_nhwc_kernel, dim3(dim3((unsigned)((in_w * mv + tin - 1) / tin), (unsigned)in_h, (unsigned)major)), dim3(tin), 0, st, x, y, p);
       B200_CHECK_LAUNCH();
       return 0;
     }
-    if (up_x == 2 && down_x == 1) { fir4_nhwc_kernel<2, 1><<<grid, threads, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
-    if (up_x == 1 && down_x == 2) { fir4_nhwc_kernel<1, 2><<<grid, threads, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
-    if (up_x == 1 && down_x == 1) { fir4_nhwc_kernel<1, 1><<<grid, threads, 0, st>>>(x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 2 && down_x == 1) { launch_kernel(fir4_nhwc_kernel<2, 1>, dim3(grid), dim3(threads), 0, st, x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 1 && down_x == 2) { launch_kernel(fir4_nhwc_kernel<1, 2>, dim3(grid), dim3(threads), 0, st, x, y, p); B200_CHECK_LAUNCH(); return 0; }
+    if (up_x == 1 && down_x == 1) { launch_kernel(fir4_nhwc_kernel<1, 1>, dim3(grid), dim3(threads), 0, st, x, y, p); B200_CHECK_LAUNCH(); return 0; }
   }
   if (minor == 1 && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && round_out != 2 &&
       ((up_x == 1 && (down_x == 1 || down_x == 2)) || (up_x == 2 && down_x == 1)) &&
@@ -657,15 +667,15 @@ int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int maj
     const int tx = 128;
     const long long quads = (long long)major * p.out_h * ((p.out_w + 3) / 4);
     const unsigned pg = (unsigned)((quads + tx - 1) / tx);
-    if (up_x == 2) fir4_planar_kernel<2, 1><<<pg, tx, 0, st>>>(x, y, p);
-    else if (down_x == 2) fir4_planar_kernel<1, 2><<<pg, tx, 0, st>>>(x, y, p);
-    else fir4_planar_kernel<1, 1><<<pg, tx, 0, st>>>(x, y, p);
+    if (up_x == 2) launch_kernel(fir4_planar_kernel<2, 1>, dim3(pg), dim3(tx), 0, st, x, y, p);
+    else if (down_x == 2) launch_kernel(fir4_planar_kernel<1, 2>, dim3(pg), dim3(tx), 0, st, x, y, p);
+    else launch_kernel(fir4_planar_kernel<1, 1>, dim3(pg), dim3(tx), 0, st, x, y, p);
     B200_CHECK_LAUNCH();
     return 0;
   }
   const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
-  if (vec) upfirdn2d_kernel<4><<<grid, 256, 0, st>>>(x, y, p);
-  else upfirdn2d_kernel<1><<<grid, 256, 0, st>>>(x, y, p);
+  if (vec) launch_kernel(upfirdn2d_kernel<4>, dim3(grid), dim3(256), 0, st, x, y, p);
+  else launch_kernel(upfirdn2d_kernel<1>, dim3(grid), dim3(256), 0, st, x, y, p);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -678,6 +688,7 @@ int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int maj
 __global__ void __launch_bounds__(256) fused_bias_act_kernel(
     const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ ref,
     float* __restrict__ y, long long n, int step_b, int size_b, int act, int grad, float alpha, float scale) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -698,7 +709,7 @@ int launch_fused_bias_act(const float* x, const float* b, const float* ref, floa
   B200_REQUIRE(act == 1 || act == 3, "fused_bias_act: act=%d unsupported (1 linear, 3 lrelu)", act);
   B200_REQUIRE(!b || (step_b > 0 && size_b > 0), "fused_bias_act: bad bias geometry");
   const int grid = (int)std::min<long long>((n + 255) / 256, 148LL * 64);
-  fused_bias_act_kernel<<<grid, 256, 0, st>>>(x, b, ref, y, n, step_b, size_b, act, grad, alpha, scale);
+  launch_kernel(fused_bias_act_kernel, dim3(grid), dim3(256), 0, st, x, b, ref, y, n, step_b, size_b, act, grad, alpha, scale);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -710,6 +721,7 @@ int launch_fused_bias_act(const float* x, const float* b, const float* ref, floa
 // ============================================================================
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, float* __restrict__ p,
                                                           long long rows, int T, float scale, int round_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -746,6 +758,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 // two rows per warp iteration in flight.
 __global__ void __launch_bounds__(256) softmax_rows256_kernel(const float* __restrict__ s, float* __restrict__ p,
                                                              long long rows, float scale, int round_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int lane = threadIdx.x & 31;
   const long long warp_id = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -784,11 +797,11 @@ int launch_softmax_rows(const float* s, float* p, long long rows, int T, float s
   const int wpb = 8;
   if (T == 256 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(p)) & 15) == 0) {
     const long long blocks = std::min<long long>((rows / 2 + wpb - 1) / wpb + 1, 148LL * 16);
-    softmax_rows256_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(s, p, rows, scale, round_out);
+    launch_kernel(softmax_rows256_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, st, s, p, rows, scale, round_out);
     B200_CHECK_LAUNCH();
     return 0;
   }
-  softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(s, p, rows, T, scale, round_out);
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, s, p, rows, T, scale, round_out);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -803,6 +816,7 @@ int launch_softmax_rows(const float* s, float* p, long long rows, int T, float s
 // frequencies and a row of emb has 2 * nf entries.
 __global__ void fourier_embed_kernel(const float* __restrict__ sigma, long long sigma_stride,
                                      const float* __restrict__ W, int nf, float* __restrict__ emb, int positional) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int r = blockIdx.x;
   const float t = sigma[r * sigma_stride];
   const float lv = positional ? t : logf(t);
@@ -815,7 +829,7 @@ __global__ void fourier_embed_kernel(const float* __restrict__ sigma, long long 
 
 int launch_fourier_embed(const float* sigma, long long sigma_stride, const float* W, int nf, int rows,
                          float* emb, cudaStream_t st, int positional) {
-  fourier_embed_kernel<<<rows, 128, 0, st>>>(sigma, sigma_stride, W, nf, emb, positional);
+  launch_kernel(fourier_embed_kernel, dim3(rows), dim3(128), 0, st, sigma, sigma_stride, W, nf, emb, positional);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -827,6 +841,7 @@ constexpr int LIN_RB = 8;
 __global__ void __launch_bounds__(256) linear_rows_kernel(
     const float* __restrict__ x, long long ldx, const float* __restrict__ W, const float* __restrict__ bias,
     int rows, int N, int K, int act_in, float* __restrict__ y, long long ldy) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   extern __shared__ float sx[];   // [LIN_RB][K]
   const int r0 = blockIdx.y * LIN_RB;
   const int nr = min(LIN_RB, rows - r0);
@@ -863,7 +878,7 @@ int launch_linear_rows(const float* x, long long ldx, const float* W, const floa
   if (smem > 48 * 1024)
     B200_CHECK_CUDA(cudaFuncSetAttribute(linear_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(std::min(ceil_div(N, 8), 148 * 4), ceil_div(rows, LIN_RB));
-  linear_rows_kernel<<<grid, 256, smem, st>>>(x, ldx, W, bias, rows, N, K, act_in, y, ldy);
+  launch_kernel(linear_rows_kernel, dim3(grid), dim3(256), smem, st, x, ldx, W, bias, rows, N, K, act_in, y, ldy);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -873,16 +888,18 @@ int launch_linear_rows(const float* x, long long ldx, const float* W, const floa
 // ============================================================================
 __global__ void fill_from_table_kernel(const float* __restrict__ table, const int* __restrict__ step,
                                        float* __restrict__ dst, int n) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const float v = table[*step];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = v;
 }
 int launch_fill_from_table(const float* table, const int* step, float* dst, int n, cudaStream_t st) {
-  fill_from_table_kernel<<<ceil_div(n, 256), 256, 0, st>>>(table, step, dst, n);
+  launch_kernel(fill_from_table_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, table, step, dst, n);
   B200_CHECK_LAUNCH();
   return 0;
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int HW, int C) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)B * HW * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -895,7 +912,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
 }
 int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cudaStream_t st) {
   const long long total = (long long)B * HW * C;
-  nhwc_to_nchw_kernel<<<(int)std::min<long long>((total + 255) / 256, 148LL * 64), 256, 0, st>>>(src, dst, B, HW, C);
+  launch_kernel(nhwc_to_nchw_kernel, dim3((int)std::min<long long>((total + 255) / 256, 148LL * 64)), dim3(256), 0, st, src, dst, B, HW, C);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -905,6 +922,7 @@ int launch_nhwc_to_nchw(const float* src, float* dst, int B, int HW, int C, cuda
 // flat-K packing of the input convolution uses dt=I, dO=row pitch.  Optional TF32 rounding.
 __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int O, int I,
                                    long long so, long long si, long long stp, int round_out, long long dt, long long dO) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)taps * O * I;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -920,7 +938,7 @@ int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, lon
                        long long stp, int round_out, cudaStream_t st, long long dt, long long dO) {
   const long long total = (long long)taps * O * I;
   if (dt == 0) { dt = (long long)O * I; dO = I; }
-  pack_weight_kernel<<<(int)std::min<long long>((total + 255) / 256, 148LL * 16), 256, 0, st>>>(
+  launch_kernel(pack_weight_kernel, dim3((int)std::min<long long>((total + 255) / 256, 148LL * 16)), dim3(256), 0, st, 
       src, dst, taps, O, I, so, si, stp, round_out, dt, dO);
   B200_CHECK_LAUNCH();
   return 0;
@@ -936,6 +954,7 @@ template <int C>   // image channels (9*C <= 32); compile-time so the patch live
 __global__ void __launch_bounds__(256) im2col3x3_nchw_kernel(const float* __restrict__ x, float* __restrict__ patches,
                                                             int B, int Hin, int Win, int H, int W, int stride, int pad,
                                                             int mode /* 1: 32 TF32 floats per row, 2: 64 halves per row */) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   // One thread per output pixel: consecutive lanes read consecutive pixels of one channel plane (coalesced; the first
   // version gave each lane a different (tap, channel) and paid ~64 L1 wavefronts per pixel), then the thread writes
   // its whole 128-byte row.
@@ -977,9 +996,9 @@ int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin,
   const long long total = (long long)B * H * W;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   switch (C) {
-    case 1: im2col3x3_nchw_kernel<1><<<blocks, 256, 0, st>>>(x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
-    case 2: im2col3x3_nchw_kernel<2><<<blocks, 256, 0, st>>>(x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
-    default: im2col3x3_nchw_kernel<3><<<blocks, 256, 0, st>>>(x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
+    case 1: launch_kernel(im2col3x3_nchw_kernel<1>, dim3(blocks), dim3(256), 0, st, x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
+    case 2: launch_kernel(im2col3x3_nchw_kernel<2>, dim3(blocks), dim3(256), 0, st, x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
+    default: launch_kernel(im2col3x3_nchw_kernel<3>, dim3(blocks), dim3(256), 0, st, x, patches, B, Hin, Win, H, W, stride, pad, mode); break;
   }
   B200_CHECK_LAUNCH();
   return 0;
@@ -997,6 +1016,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
                                                              long long div_stride, float* __restrict__ out_nchw,
                                                              int B, int H, int W, int C, int x_f16,
                                                              const float* __restrict__ add_nchw) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   // Eight lanes share one output pixel: lane `part` takes the float4s part, part+8, ... of the pixel's channel
   // vector, so a warp-wide 128-bit load covers 4 pixels x 128 contiguous bytes (4 cache lines per instruction
   // instead of 32 with one pixel per lane, which was L1-wavefront bound); the partial dot products are folded with
@@ -1109,7 +1129,7 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
       B200_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_n_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3x3_small_n_kernel<NN><<<blocks, 256, smem, st>>>(x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16, add_nchw); \
+    launch_kernel(conv3x3_small_n_kernel<NN>, dim3(blocks), dim3(256), smem, st, x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16, add_nchw); \
   } while (0)
   switch (N) {
     case 1: B200_LAUNCH_SMALLN(1); break;
@@ -1129,6 +1149,7 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
 // ============================================================================
 __global__ void __launch_bounds__(256) attn_small_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                         int T, int C, float scale, int round_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   extern __shared__ float sm[];            // q[T][C] k[T][C] v[T][C] p[T][T]
   float* sq = sm; float* sk = sq + T * C; float* sv = sk + T * C; float* sp = sv + T * C;
   const int b = blockIdx.x;
@@ -1181,7 +1202,7 @@ int launch_attn_small_configure(int T, int C) {
 
 int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st) {
   const size_t smem = ((size_t)3 * T * C + (size_t)T * T) * sizeof(float);
-  attn_small_kernel<<<B, 256, smem, st>>>(qkv, out, T, C, scale, round_out);
+  launch_kernel(attn_small_kernel, dim3(B), dim3(256), smem, st, qkv, out, T, C, scale, round_out);
   B200_CHECK_LAUNCH();
   return 0;
 }

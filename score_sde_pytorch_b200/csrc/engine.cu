@@ -90,6 +90,7 @@ class Arena {
 };
 
 __global__ void affine_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float shift, float scale) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = (x[i] + shift) * scale;
 }
@@ -834,7 +835,7 @@ struct Builder {
       const int centered = c.centered;
       op(1, [=](cudaStream_t st) {
         if (centered) return cudaMemcpyAsync(xc, eng->in_x_l[ln], n * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : (set_error("memcpy failed"), 1);
-        affine_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, st>>>(eng->in_x_l[ln], xc, n, -0.5f, 2.0f);
+        launch_kernel(affine_kernel, dim3((int)std::min<long long>((n + 255) / 256, 4096)), dim3(256), 0, st, eng->in_x_l[ln], xc, n, -0.5f, 2.0f);
         return cudaGetLastError() == cudaSuccess ? 0 : (set_error("affine launch failed"), 1);
       });
     }
@@ -1199,6 +1200,7 @@ void set_call_args(b200_ncsnpp* h, const float* x, const float* labels, int unif
 int b200_ncsnpp_forward(b200_ncsnpp_t* h, const float* x, const float* labels, int uniform, float* out, void* stream) {
   B200_REQUIRE(h && x && labels && out, "forward: null argument");
   B200_REQUIRE(!h->ops.empty(), "forward: no plan bound (call b200_ncsnpp_bind_workspace)");
+  PdlScope pdl(h->cfg.pdl != 0);            // launches of this call carry the programmatic-dependent-launch attribute
   set_call_args(h, x, labels, uniform, out);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h->ops2.empty()) {
@@ -1429,6 +1431,7 @@ int b200_pc_bind_workspace(b200_pc_t* pc, void* ws, long long bytes, void* strea
 int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_steps, unsigned long long seed,
                 unsigned long long offset, unsigned long long* offset_out, int use_graph, void* stream) {
   B200_REQUIRE(pc && pc->ws && x, "pc_run: not bound");
+  PdlScope pdl(pc->model->cfg.pdl != 0);
   B200_REQUIRE(first_step >= 0 && num_steps >= 0 && first_step + num_steps <= pc->cfg.n_steps,
                "pc_run: steps [%d,%d) outside the %d-step schedule", first_step, first_step + num_steps, pc->cfg.n_steps);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1464,6 +1467,7 @@ int b200_pc_run(b200_pc_t* pc, float* x, float* x_mean, int first_step, int num_
 int b200_pc_step_external(b200_pc_t* pc, float* x, float* x_mean, int step, const float* noise_c,
                           const float* noise_p, void* stream) {
   B200_REQUIRE(pc && pc->ws && x, "pc_step_external: not bound");
+  PdlScope pdl(pc->model->cfg.pdl != 0);
   B200_REQUIRE(step >= 0 && step < pc->cfg.n_steps, "pc_step_external: step %d out of range", step);
   B200_REQUIRE(!pc->cfg.corrector || noise_c, "pc_step_external: corrector noise missing");
   B200_REQUIRE(!pc->cfg.predictor || noise_p, "pc_step_external: predictor noise missing");

@@ -432,6 +432,7 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait(); pdl_trigger();   // barriers and TMEM are set up; nothing above touched global memory (common.cuh)
 
   const int kiters = (p.kchunks1 + p.kchunks2) * p.taps + p.kchunks3 + p.kchunks4;
   const int HW = p.H * p.W;
@@ -908,8 +909,8 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 int tc_attn_launch(const TcAttnPlan* pl, cudaStream_t st) {
   const long long tiles = 2LL * pl->prm.nimg;
   const int grid = (int)std::min<long long>(tiles, num_sms());
-  if (pl->f16) attn_tc_kernel<true><<<grid, 384, AttnSmem<true>::TOTAL, st>>>(pl->prm);
-  else attn_tc_kernel<false><<<grid, 384, AttnSmem<false>::TOTAL, st>>>(pl->prm);
+  if (pl->f16) launch_kernel(attn_tc_kernel<true>, dim3(grid), dim3(384), AttnSmem<true>::TOTAL, st, pl->prm);
+  else launch_kernel(attn_tc_kernel<false>, dim3(grid), dim3(384), AttnSmem<false>::TOTAL, st, pl->prm);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -979,8 +980,8 @@ int tcg_launch(const TcgPlan* pl, cudaStream_t st) {
   const long long pairs = ((q.tiles_m + 1) / 2) * q.tiles_n;
   if (pairs == 0) return 0;
   const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
-  if (q.W == 32) conv_gn2_kernel<true><<<grid, TG_THREADS, SmemG::TOTAL, st>>>(q);
-  else conv_gn2_kernel<false><<<grid, TG_THREADS, SmemG::TOTAL, st>>>(q);
+  if (q.W == 32) launch_kernel(conv_gn2_kernel<true>, dim3(grid), dim3(TG_THREADS), SmemG::TOTAL, st, q);
+  else launch_kernel(conv_gn2_kernel<false>, dim3(grid), dim3(TG_THREADS), SmemG::TOTAL, st, q);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -1004,7 +1005,7 @@ template <int BN, int STAGES>
 static int launch_impl(const TcGemmPlan* pl, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   const int grid = (int)std::min<long long>(pl->prm.total_tiles, num_sms());
-  gemm_tc_kernel<BN, STAGES><<<grid, 384, L::TOTAL, st>>>(pl->prm);
+  launch_kernel(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(384), L::TOTAL, st, pl->prm);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -1015,7 +1016,7 @@ int tc_gemm_launch(const TcGemmPlan* pl, cudaStream_t st) {
     const TcParams& q = pl->prm;
     const long long pairs = (((long long)q.nbatch * q.tiles_m_per_batch + 1) / 2) * q.tiles_n;
     const int grid = (int)std::min<long long>(2 * pairs, (long long)(num_sms() & ~1));
-    gemm_tc2_kernel<256, 6><<<grid, 384, Smem2<256, 6>::TOTAL, st>>>(pl->prm);
+    launch_kernel(gemm_tc2_kernel<256, 6>, dim3(grid), dim3(384), Smem2<256, 6>::TOTAL, st, pl->prm);
     B200_CHECK_LAUNCH();
     return 0;
   }

@@ -99,6 +99,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   cluster_sync_all();                               // both CTAs' barriers and TMEM exist before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait(); pdl_trigger();   // prologue done; nothing above touched global memory (common.cuh)
 
   const int kiters = (p.kchunks1 + p.kchunks2) * p.taps + p.kchunks3 + p.kchunks4;
   const int HW = p.H * p.W;

@@ -203,6 +203,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1) conv_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait(); pdl_trigger();   // prologue done; nothing above touched global memory (common.cuh)
 
   const int HW = p.H * p.W;
   const long long pairs_m = (p.tiles_m + 1) / 2;

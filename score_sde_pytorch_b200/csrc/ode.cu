@@ -25,6 +25,7 @@ struct OdeCoef { double c[8]; };
 __global__ void __launch_bounds__(ODE_THREADS) ode_stage_kernel(const double* __restrict__ y, const double* __restrict__ K,
                                                                 long long n, OdeCoef coef, int nk, double h,
                                                                 double* __restrict__ y_out, float* __restrict__ x32) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double acc = 0.0;
     for (int j = 0; j < nk; ++j) acc += K[(long long)j * n + i] * coef.c[j];       // np.dot(K[:s].T, a[:s])
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(ODE_THREADS) ode_stage_kernel(const double* __
 __global__ void __launch_bounds__(ODE_THREADS) ode_drift_kernel(const float* __restrict__ x32, const float* __restrict__ out,
                                                                 long long n, const float* __restrict__ scal,
                                                                 double* __restrict__ k_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const float c_f = scal[0], g2 = scal[1], sd = scal[2];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float score = out[i];
@@ -64,6 +66,7 @@ __device__ __forceinline__ void block_sum_to(double v, double* dst) {
 __global__ void __launch_bounds__(ODE_THREADS) ode_error_kernel(const double* __restrict__ y, const double* __restrict__ y_new,
                                                                 const double* __restrict__ K, long long n, OdeCoef e, int nk,
                                                                 double h, double rtol, double atol, double* __restrict__ partial) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   double s = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double acc = 0.0;
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(ODE_THREADS) ode_error_kernel(const double* __
 __global__ void __launch_bounds__(ODE_THREADS) ode_scaled_sq_kernel(const double* __restrict__ v, const double* __restrict__ v2,
                                                                     const double* __restrict__ y0, long long n, double rtol,
                                                                     double atol, double* __restrict__ partial) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   double s = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double d = v2 ? v[i] - v2[i] : v[i];
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(ODE_THREADS) ode_scaled_sq_kernel(const double
 }
 
 __global__ void __launch_bounds__(ODE_THREADS) ode_final_sum_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   double s = 0.0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
   block_sum_to(s, out);
@@ -107,14 +112,14 @@ int b200_ode_stage_f64(const double* y, const double* k, long long n, const doub
                        double* y_out, float* x32, void* stream) {
   B200_REQUIRE(y && n > 0 && nk >= 0 && nk <= 8 && (nk == 0 || (k && coef_host)), "ode_stage: bad argument");
   OdeCoef c; for (int j = 0; j < 8; ++j) c.c[j] = j < nk ? coef_host[j] : 0.0;
-  ode_stage_kernel<<<ode_grid(n), ODE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(y, k, n, c, nk, h, y_out, x32);
+  launch_kernel(ode_stage_kernel, dim3(ode_grid(n)), dim3(ODE_THREADS), 0, static_cast<cudaStream_t>(stream), y, k, n, c, nk, h, y_out, x32);
   B200_CHECK_LAUNCH();
   return 0;
 }
 
 int b200_ode_drift_f64(const float* x32, const float* net_out, long long n, const float* scalars_dev, double* k_out, void* stream) {
   B200_REQUIRE(x32 && net_out && scalars_dev && k_out && n > 0, "ode_drift: null argument");
-  ode_drift_kernel<<<ode_grid(n), ODE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x32, net_out, n, scalars_dev, k_out);
+  launch_kernel(ode_drift_kernel, dim3(ode_grid(n)), dim3(ODE_THREADS), 0, static_cast<cudaStream_t>(stream), x32, net_out, n, scalars_dev, k_out);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -127,8 +132,8 @@ int b200_ode_error_sumsq_f64(const double* y, const double* y_new, const double*
   OdeCoef c; for (int j = 0; j < 8; ++j) c.c[j] = j < nk ? e_host[j] : 0.0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int g = ode_grid(n);
-  ode_error_kernel<<<g, ODE_THREADS, 0, st>>>(y, y_new, k, n, c, nk, h, rtol, atol, ws + 8);
-  ode_final_sum_kernel<<<1, ODE_THREADS, 0, st>>>(ws + 8, g, ws);
+  launch_kernel(ode_error_kernel, dim3(g), dim3(ODE_THREADS), 0, st, y, y_new, k, n, c, nk, h, rtol, atol, ws + 8);
+  launch_kernel(ode_final_sum_kernel, dim3(1), dim3(ODE_THREADS), 0, st, ws + 8, g, ws);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -138,8 +143,8 @@ int b200_ode_scaled_sumsq_f64(const double* v, const double* v2, const double* y
   B200_REQUIRE(v && y0 && ws && n > 0, "ode_scaled_sumsq: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int g = ode_grid(n);
-  ode_scaled_sq_kernel<<<g, ODE_THREADS, 0, st>>>(v, v2, y0, n, rtol, atol, ws + 8);
-  ode_final_sum_kernel<<<1, ODE_THREADS, 0, st>>>(ws + 8, g, ws);
+  launch_kernel(ode_scaled_sq_kernel, dim3(g), dim3(ODE_THREADS), 0, st, v, v2, y0, n, rtol, atol, ws + 8);
+  launch_kernel(ode_final_sum_kernel, dim3(1), dim3(ODE_THREADS), 0, st, ws + 8, g, ws);
   B200_CHECK_LAUNCH();
   return 0;
 }

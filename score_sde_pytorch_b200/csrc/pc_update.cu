@@ -59,6 +59,7 @@ __device__ __forceinline__ float noise_at(const PhiloxMap& m, unsigned long long
 
 __global__ void __launch_bounds__(256) randn_torch_kernel(PhiloxMap m, const unsigned long long* offset_dev,
                                                           unsigned long long offset_add, float* out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const long long T = (long long)m.grid * m.block;
   const long long L = (m.numel + 4 * T - 1) / (4 * T);
   const unsigned long long off = *offset_dev + offset_add;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) pc_norms_kernel(const float* __restrict__
                                                        PhiloxMap m, const unsigned long long* offset_dev,
                                                        const int* step, unsigned long long cps,
                                                        unsigned long long cidx, int per_img, float* __restrict__ norms) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   __shared__ double red[2][8];
   const int b = blockIdx.x;
   const unsigned long long off = noise ? 0ull : step_offset(offset_dev, step, cps, cidx, m.inc);
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) pc_norms_kernel(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) pc_means_kernel(const float* __restrict__ norms, int B, float* __restrict__ means) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   __shared__ double red[2][8];
   double a = 0.0, c = 0.0;
   for (int i = threadIdx.x; i < B; i += blockDim.x) { a += norms[i]; c += norms[B + i]; }
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) pc_apply_kernel(float* __restrict__ x, fl
                                                        unsigned long long cps, unsigned long long cidx,
                                                        const float* __restrict__ means, float snr, PcStepScalars sc,
                                                        int mode, int add_noise) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   const long long T = (long long)m.grid * m.block;
   const long long L = (m.numel + 4 * T - 1) / (4 * T);
   const int s = step ? *step : 0;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(256) pc_apply_kernel(float* __restrict__ x, fl
   }
 }
 
-__global__ void step_increment_kernel(int* step) { *step += 1; }
+__global__ void step_increment_kernel(int* step) { pdl_wait(); pdl_trigger(); *step += 1; }
 
 int apply_grid(const PhiloxMap& m) {
   const long long T = (long long)m.grid * m.block;
@@ -173,7 +177,7 @@ int apply_grid(const PhiloxMap& m) {
 int launch_randn_torch(const PhiloxMap& m, const unsigned long long* offset_dev, unsigned long long offset_add,
                        float* out, cudaStream_t st) {
   if (m.numel == 0) return 0;
-  randn_torch_kernel<<<apply_grid(m), 256, 0, st>>>(m, offset_dev, offset_add, out);
+  launch_kernel(randn_torch_kernel, dim3(apply_grid(m)), dim3(256), 0, st, m, offset_dev, offset_add, out);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -181,9 +185,9 @@ int launch_randn_torch(const PhiloxMap& m, const unsigned long long* offset_dev,
 int launch_pc_norms(const float* out, const float* noise, const PhiloxMap& m, const unsigned long long* offset_dev,
                     const int* step, unsigned long long calls_per_step, unsigned long long call_idx,
                     int B, int per_img, float* norms, float* means, cudaStream_t st) {
-  pc_norms_kernel<<<B, 256, 0, st>>>(out, noise, m, offset_dev, step, calls_per_step, call_idx, per_img, norms);
+  launch_kernel(pc_norms_kernel, dim3(B), dim3(256), 0, st, out, noise, m, offset_dev, step, calls_per_step, call_idx, per_img, norms);
   B200_CHECK_LAUNCH();
-  pc_means_kernel<<<1, 256, 0, st>>>(norms, B, means);
+  launch_kernel(pc_means_kernel, dim3(1), dim3(256), 0, st, norms, B, means);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -192,7 +196,7 @@ int launch_langevin_apply(float* x, float* x_mean, const float* out, const float
                           const unsigned long long* offset_dev, const int* step,
                           unsigned long long calls_per_step, unsigned long long call_idx,
                           const float* means, float snr, PcStepScalars sc, cudaStream_t st) {
-  pc_apply_kernel<<<apply_grid(m), 256, 0, st>>>(x, x_mean, out, noise, m, offset_dev, step, calls_per_step,
+  launch_kernel(pc_apply_kernel, dim3(apply_grid(m)), dim3(256), 0, st, x, x_mean, out, noise, m, offset_dev, step, calls_per_step,
                                                  call_idx, means, snr, sc, 0, 1);
   B200_CHECK_LAUNCH();
   return 0;
@@ -203,14 +207,14 @@ int launch_predictor_apply(float* x, float* x_mean, const float* out, const floa
                            unsigned long long calls_per_step, unsigned long long call_idx,
                            PcStepScalars sc, int add_noise, cudaStream_t st) {
   B200_REQUIRE(sc.pb != nullptr, "predictor_apply: pb table missing");
-  pc_apply_kernel<<<apply_grid(m), 256, 0, st>>>(x, x_mean, out, noise, m, offset_dev, step, calls_per_step,
+  launch_kernel(pc_apply_kernel, dim3(apply_grid(m)), dim3(256), 0, st, x, x_mean, out, noise, m, offset_dev, step, calls_per_step,
                                                  call_idx, nullptr, 0.f, sc, 1, add_noise);
   B200_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_step_increment(int* step, cudaStream_t st) {
-  step_increment_kernel<<<1, 1, 0, st>>>(step);
+  launch_kernel(step_increment_kernel, dim3(1), dim3(1), 0, st, step);
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -23,6 +23,8 @@ import torch.nn as nn
 from . import utils
 from .. import _lib
 
+PDL_DEFAULT = False
+
 _SUPPORTED = ("engine supports embedding_type in {'fourier','positional'}, conditional=True, resblock_type='biggan', "
               "fir in {True, False} (progressive_input='residual' needs fir=True), progressive in {'none','output_skip'}, "
               "progressive_input in {'none','residual','input_skip'} with progressive_combine='sum'; "
@@ -117,7 +119,7 @@ class NCSNpp(nn.Module):
   MMA rate) or ``'fp32'`` (strict fp32 on CUDA cores; validation mode)."""
 
   def __init__(self, config, precision=None, keep_activations=False, lanes=1, cuda_core_head=None,
-               separate_groupnorm=None):
+               separate_groupnorm=None, pdl=None):
     super().__init__()
     self.config = config
     m = config.model
@@ -144,6 +146,8 @@ class NCSNpp(nn.Module):
     # batch 1024 (profiles/r02_g6_bench.json) - at the board's power cap the transform's arithmetic costs more than
     # the 4.5 GB/evaluation of HBM traffic it removes, so the separate pass stays the default.
     self.separate_groupnorm = bool(getattr(m, 'separate_groupnorm', True) if separate_groupnorm is None else separate_groupnorm)
+    # programmatic dependent launch between the kernels of a forward / PC iteration (common.cuh)
+    self.pdl = bool(getattr(m, 'pdl', PDL_DEFAULT) if pdl is None else pdl)
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
     L = len(ch_mult)
     all_res = [config.data.image_size // (2 ** i) for i in range(L)]
@@ -224,6 +228,7 @@ class NCSNpp(nn.Module):
     c.skip_rescale, c.conditional = int(bool(m.skip_rescale)), int(bool(m.conditional))
     c.progressive_input = {'none': 0, 'residual': 1, 'input_skip': 2}[m.progressive_input.lower()]
     c.progressive = 1 if m.progressive.lower() == 'output_skip' else 0
+    c.pdl = int(self.pdl)
     c.fir_taps = len(m.fir_kernel)
     for i, v in enumerate(m.fir_kernel):
       c.fir_kernel[i] = float(v)

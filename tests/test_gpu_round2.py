@@ -303,3 +303,36 @@ def test_groupnorm_on_load_convolution_matches_the_separate_pass(dev, batch):
     assert e_f < 1.25 * e_s + 1e-4, f'all_modules[{idx}]: fused plan {e_f:.3e} vs oracle, separate plan {e_s:.3e}'
   assert rel_l2(y1, y0) < 2e-3
   assert rel_l2(y1, ref) < 1.25 * rel_l2(y0, ref) + 1e-4
+
+
+def test_programmatic_dependent_launch_plan_matches_the_serialized_plan(dev):
+  """`pdl=True`: every launch of a PC iteration carries the programmatic-dependent-launch attribute and the captured
+  graph gets programmatic edges; each kernel still waits for its predecessor's completion (griddepcontrol.wait) before it
+  touches memory, so the samples must equal the serialized plan's up to the order of the fp64 GroupNorm atomics - for the
+  graph replay and for eager launches - and stay within the parity bound of the oracle."""
+  from score_sde_pytorch_b200 import native, sampling, sde_lib
+  cfg = golden_config('cifar10_ve')
+  shape = (8, 3, 32, 32)
+  sde, osde = sde_lib.VESDE(0.01, 50, 1000), SO.VE(0.01, 50, 1000)
+  torch.manual_seed(5)
+  x0 = osde.prior_sampling(shape).to(dev)
+  outs = {}
+  for pdl in (False, True):
+    model = seeded_model(cfg, precision='f16', pdl=pdl).to(dev)
+    plan = native.match_pc_plan(sde=sde, model=model, predictor=sampling.ReverseDiffusionPredictor, corrector=sampling.LangevinCorrector,
+                                shape=shape, snr=0.16, n_steps=1, probability_flow=False, continuous=True, eps=1e-5, device=dev)
+    for graph in (True, False):
+      plan.use_graph = graph
+      torch.cuda.manual_seed(77)
+      _, xm = plan.run(x0, first_step=0, num_steps=6)
+      outs[(pdl, graph)] = xm.clone()
+    sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+    del plan, model
+  base = outs[(False, True)]
+  for key, v in outs.items():
+    assert torch.isfinite(v).all()
+    assert rel_l2(v, base) < 2e-5, f'pdl={key[0]} graph={key[1]} differs from the serialized graph plan'
+  torch.cuda.manual_seed(77)
+  with torch.no_grad():
+    ref, _ = SO.pc_sample(osde, lambda a, l: NO.ncsnpp_forward(sd, cfg, a, l), shape, eps=1e-5, device=dev, x_init=x0, num_iters=6)
+  assert rel_l2(outs[(True, True)], ref) < TOL_PARITY
