@@ -183,11 +183,15 @@ B200_API int b200_ncsnpp_profile_ops(b200_ncsnpp_t* h, const float* x, const flo
 typedef struct b200_pc b200_pc_t;
 typedef struct {
   int n_steps;                 /* sde.N */
-  int corrector;               /* 0 none, 1 langevin */
-  int predictor;               /* 0 none, 1 affine (reverse_diffusion / euler_maruyama) */
+  int corrector;               /* 0 none, 1 langevin (norm-based step size, sampling.py:262-282), 2 affine corrector: annealed
+                                * Langevin dynamics (:286-319), whose step size depends on the step only: x_mean = ca x + cb out,
+                                * x = x_mean + cc z */
+  int predictor;               /* 0 none, 1 affine (reverse_diffusion / euler_maruyama / ancestral_sampling: x_mean = pa x + pb out,
+                                * x = x_mean + pc z) */
   int n_corrector_steps;       /* config.sampling.n_steps_each */
   float snr;
   const float *label, *score_scale, *alpha, *pa, *pb, *pc;   /* HOST tables [n_steps] */
+  const float *ca, *cb, *cc;   /* HOST tables [n_steps] of the affine corrector (corrector == 2), else NULL */
 } b200_pc_config;
 
 B200_API int b200_pc_create(b200_ncsnpp_t* model, const b200_pc_config* cfg, int batch, b200_pc_t** out);

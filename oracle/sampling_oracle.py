@@ -154,6 +154,41 @@ def euler_maruyama_step(sde, model, x, t, continuous=True, probability_flow=Fals
   return x_mean + diffusion[:, None, None, None] * np.sqrt(-dt) * z, x_mean
 
 
+def ancestral_step(sde, model, x, t, continuous=True):
+  """AncestralSamplingPredictor, sampling.py:204-239 (VE :213-223, VP :225-232; no sub-VP branch in the reference)."""
+  idx = (t * (sde.N - 1) / sde.T).long()
+  score = sde.score(model, x, t, continuous)
+  if sde.kind == 've':
+    tab = sde.discrete_sigmas.to(t.device)
+    sigma = tab[idx]
+    adj = torch.where(idx == 0, torch.zeros_like(t), tab[idx - 1])
+    x_mean = x + score * (sigma ** 2 - adj ** 2)[:, None, None, None]
+    std = torch.sqrt((adj ** 2 * (sigma ** 2 - adj ** 2)) / (sigma ** 2))
+    return x_mean + std[:, None, None, None] * torch.randn_like(x), x_mean
+  beta = sde.discrete_betas.to(t.device)[idx]
+  x_mean = (x + beta[:, None, None, None] * score) / torch.sqrt(1. - beta)[:, None, None, None]
+  return x_mean + torch.sqrt(beta)[:, None, None, None] * torch.randn_like(x), x_mean
+
+
+def ald_step(sde, model, x, t, snr, n_steps, continuous=True):
+  """AnnealedLangevinDynamics, sampling.py:286-319: the step size comes from the marginal std, not from norms.
+  (sub-VP reaches `sde.alphas`, which subVPSDE does not have: the reference raises there, so does this.)"""
+  if sde.kind == 've':
+    alpha = torch.ones_like(t)
+    std = sde.sigma(t)
+  else:
+    alpha = sde.alphas.to(t.device)[(t * (sde.N - 1) / sde.T).long()]
+    std = sde.std(t)
+  x_mean = x
+  for _ in range(n_steps):
+    grad = sde.score(model, x, t, continuous)
+    noise = torch.randn_like(x)
+    step_size = (snr * std) ** 2 * 2 * alpha
+    x_mean = x + step_size[:, None, None, None] * grad
+    x = x_mean + noise * torch.sqrt(step_size * 2)[:, None, None, None]
+  return x, x_mean
+
+
 def pc_sample(sde, model, shape, predictor='reverse_diffusion', corrector='langevin', snr=0.16,
               n_steps=1, eps=1e-5, continuous=True, denoise=True, device='cpu', num_iters=None,
               x_init=None, trace=None):
@@ -168,7 +203,11 @@ def pc_sample(sde, model, shape, predictor='reverse_diffusion', corrector='lange
       vec_t = torch.ones(shape[0], device=device) * timesteps[i]
       if corrector == 'langevin':
         x, x_mean = langevin_step(sde, model, x, vec_t, snr, n_steps, continuous)
-      if predictor == 'reverse_diffusion':
+      elif corrector == 'ald':
+        x, x_mean = ald_step(sde, model, x, vec_t, snr, n_steps, continuous)
+      if predictor == 'ancestral_sampling':
+        x, x_mean = ancestral_step(sde, model, x, vec_t, continuous)
+      elif predictor == 'reverse_diffusion':
         x, x_mean = reverse_diffusion_step(sde, model, x, vec_t, continuous)
       elif predictor == 'euler_maruyama':
         x, x_mean = euler_maruyama_step(sde, model, x, vec_t, continuous)

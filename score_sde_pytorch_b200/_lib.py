@@ -39,7 +39,8 @@ class PcConfig(ctypes.Structure):
   _fields_ = [('n_steps', c_int), ('corrector', c_int), ('predictor', c_int), ('n_corrector_steps', c_int),
               ('snr', c_float),
               ('label', P(c_float)), ('score_scale', P(c_float)), ('alpha', P(c_float)),
-              ('pa', P(c_float)), ('pb', P(c_float)), ('pc', P(c_float))]
+              ('pa', P(c_float)), ('pb', P(c_float)), ('pc', P(c_float)),
+              ('ca', P(c_float)), ('cb', P(c_float)), ('cc', P(c_float))]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/scoresde_b200.h

@@ -1318,9 +1318,9 @@ long long b200_ncsnpp_launches_per_forward(const b200_ncsnpp_t* h) { return h ? 
 // ===========================================================================
 struct b200_pc {
   b200_ncsnpp* model; b200_pc_config cfg; int B; long long numel, per_img;
-  std::vector<float> h_label, h_ss, h_alpha, h_pa, h_pb, h_pc;
+  std::vector<float> h_label, h_ss, h_alpha, h_pa, h_pb, h_pc, h_ca, h_cb, h_cc;
   // workspace carve-up
-  char* ws = nullptr; float *d_label, *d_ss, *d_alpha, *d_pa, *d_pb, *d_pc, *labels, *net_out, *norms, *means;
+  char* ws = nullptr; float *d_label, *d_ss, *d_alpha, *d_pa, *d_pb, *d_pc, *d_ca, *d_cb, *d_cc, *labels, *net_out, *norms, *means;
   int* d_step; unsigned long long* d_offset;
   PhiloxMap map;
   cudaGraphExec_t gexec = nullptr; float* graph_x = nullptr; float* graph_xm = nullptr; cudaStream_t graph_stream = nullptr;
@@ -1338,6 +1338,7 @@ long long pc_ws_layout(b200_pc* pc, char* base) {
   const int N = pc->cfg.n_steps;
   pc->d_label = (float*)take(N * 4LL); pc->d_ss = (float*)take(N * 4LL); pc->d_alpha = (float*)take(N * 4LL);
   pc->d_pa = (float*)take(N * 4LL); pc->d_pb = (float*)take(N * 4LL); pc->d_pc = (float*)take(N * 4LL);
+  pc->d_ca = (float*)take(N * 4LL); pc->d_cb = (float*)take(N * 4LL); pc->d_cc = (float*)take(N * 4LL);
   pc->labels = (float*)take(pc->B * 4LL); pc->net_out = (float*)take(pc->numel * 4LL);
   pc->norms = (float*)take(2LL * pc->B * 4); pc->means = (float*)take(256);
   pc->d_step = (int*)take(256); pc->d_offset = (unsigned long long*)take(256);
@@ -1352,7 +1353,16 @@ int pc_iteration(b200_pc* pc, float* x, float* x_mean, const float* noise_c, con
   const unsigned long long cps = (unsigned long long)((c.corrector ? c.n_corrector_steps : 0) + (c.predictor ? 1 : 0));
   if (int r = launch_fill_from_table(pc->d_label, pc->d_step, pc->labels, pc->B, st)) return r;
   unsigned long long call = 0;
-  if (c.corrector) {
+  if (c.corrector == 2) {
+    // affine corrector (annealed Langevin dynamics, sampling.py:286-319): the step size is a per-step scalar, so the update is
+    // the predictor's kernel with the corrector's own tables; every inner step draws fresh noise like the reference's loop
+    PcStepScalars cs{pc->d_ss, pc->d_alpha, pc->d_ca, pc->d_cb, pc->d_cc};
+    for (int k = 0; k < c.n_corrector_steps; ++k) {
+      if (int r = b200_ncsnpp_forward(m, x, pc->labels, 1, pc->net_out, st)) return r;
+      if (int r = launch_predictor_apply(x, x_mean, pc->net_out, noise_c, pc->map, pc->d_offset, pc->d_step, cps, call, cs, 1, st)) return r;
+      ++call;
+    }
+  } else if (c.corrector) {
     for (int k = 0; k < c.n_corrector_steps; ++k) {
       if (int r = b200_ncsnpp_forward(m, x, pc->labels, 1, pc->net_out, st)) return r;
       if (int r = launch_pc_norms(pc->net_out, noise_c, pc->map, pc->d_offset, pc->d_step, cps, call, pc->B,
@@ -1383,7 +1393,8 @@ int b200_pc_create(b200_ncsnpp_t* model, const b200_pc_config* cfg, int batch, b
   B200_REQUIRE(model && cfg && out && batch > 0, "pc_create: bad argument");
   B200_REQUIRE(model->B == batch && !model->ops.empty(), "pc_create: model is not planned for batch %d", batch);
   B200_REQUIRE(cfg->n_steps > 0 && cfg->label && cfg->pb, "pc_create: missing schedule tables");
-  B200_REQUIRE(cfg->corrector == 0 || cfg->corrector == 1, "pc_create: corrector %d unsupported", cfg->corrector);
+  B200_REQUIRE(cfg->corrector >= 0 && cfg->corrector <= 2, "pc_create: corrector %d unsupported", cfg->corrector);
+  B200_REQUIRE(cfg->corrector != 2 || (cfg->ca && cfg->cb && cfg->cc), "pc_create: affine corrector without its tables");
   B200_REQUIRE(cfg->predictor == 0 || cfg->predictor == 1, "pc_create: predictor %d unsupported", cfg->predictor);
   b200_pc* pc = new b200_pc();
   pc->model = model; pc->cfg = *cfg; pc->B = batch;
@@ -1394,9 +1405,12 @@ int b200_pc_create(b200_ncsnpp_t* model, const b200_pc_config* cfg, int batch, b
   auto cp = [&](std::vector<float>& dst, const float* src, float dflt) { dst.assign(N, dflt); if (src) memcpy(dst.data(), src, N * 4); };
   cp(pc->h_label, cfg->label, 0.f); cp(pc->h_ss, cfg->score_scale, 1.f); cp(pc->h_alpha, cfg->alpha, 1.f);
   cp(pc->h_pa, cfg->pa, 1.f); cp(pc->h_pb, cfg->pb, 0.f); cp(pc->h_pc, cfg->pc, 0.f);
+  cp(pc->h_ca, cfg->ca, 1.f); cp(pc->h_cb, cfg->cb, 0.f); cp(pc->h_cc, cfg->cc, 0.f);
   pc->cfg.label = pc->cfg.score_scale = pc->cfg.alpha = pc->cfg.pa = pc->cfg.pb = pc->cfg.pc = nullptr;
+  pc->cfg.ca = pc->cfg.cb = pc->cfg.cc = nullptr;
   const long long cps = (cfg->corrector ? cfg->n_corrector_steps : 0) + (cfg->predictor ? 1 : 0);
-  pc->launches_per_step = cps * model->launches + (cfg->corrector ? cfg->n_corrector_steps * 3 : 0) + 1 /* predictor apply, or the x -> x_mean copy */ + 2;
+  pc->launches_per_step = cps * model->launches + (cfg->corrector == 1 ? cfg->n_corrector_steps * 3 : cfg->corrector == 2 ? cfg->n_corrector_steps : 0) +
+                          1 /* predictor apply, or the x -> x_mean copy */ + 2;
   *out = pc;
   return 0;
 }
@@ -1423,6 +1437,9 @@ int b200_pc_bind_workspace(b200_pc_t* pc, void* ws, long long bytes, void* strea
   B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_pa, pc->h_pa.data(), N * 4, cudaMemcpyHostToDevice, st));
   B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_pb, pc->h_pb.data(), N * 4, cudaMemcpyHostToDevice, st));
   B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_pc, pc->h_pc.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_ca, pc->h_ca.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_cb, pc->h_cb.data(), N * 4, cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(pc->d_cc, pc->h_cc.data(), N * 4, cudaMemcpyHostToDevice, st));
   B200_CHECK_CUDA(cudaStreamSynchronize(st));
   if (pc->gexec) { cudaGraphExecDestroy(pc->gexec); pc->gexec = nullptr; }
   return philox_map_init(&pc->map, pc->numel, 0);

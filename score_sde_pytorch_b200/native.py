@@ -38,9 +38,11 @@ def _unwrap(model):
   return model.module if isinstance(model, torch.nn.DataParallel) else model
 
 
-def build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps):
+def build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps, snr=0.16):
   """Per-step scalars (float32 numpy arrays of length N).  ``predictor_kind`` in
-  {'none','reverse_diffusion','euler_maruyama'}, ``corrector_kind`` in {'none','langevin'}."""
+  {'none','reverse_diffusion','euler_maruyama','ancestral_sampling'}, ``corrector_kind`` in {'none','langevin','ald'}.
+  Every update the native loop runs is affine in (x, network output, noise): x_mean = a x + b out, x = x_mean + c z;
+  the tables are evaluated with the SDE's own torch ops, in the reference's operation order."""
   N, T = sde.N, sde.T
   t = torch.linspace(T, eps, N)
   half = 0.5 if probability_flow else 1.0
@@ -55,6 +57,12 @@ def build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps):
     elif predictor_kind == 'euler_maruyama':
       _, g = sde.sde(torch.zeros(N, 1, 1, 1), t)                       # sde_lib.py:224-231
       pa, pb, pc = ones.clone(), g ** 2 * half * (1. / N), g * float(np.sqrt(1. / N))
+    elif predictor_kind == 'ancestral_sampling':                       # sampling.py:213-223
+      idx = (t * (N - 1) / T).long()
+      sigma = sde.discrete_sigmas[idx]
+      adj = torch.where(idx == 0, torch.zeros_like(t), sde.discrete_sigmas[idx - 1])
+      pa, pb = ones.clone(), sigma ** 2 - adj ** 2
+      pc = torch.sqrt((adj ** 2 * (sigma ** 2 - adj ** 2)) / (sigma ** 2))
     else:
       pa, pb, pc = ones.clone(), torch.zeros(N), torch.zeros(N)
   else:
@@ -68,7 +76,10 @@ def build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps):
       alpha = ones.clone()
     beta_t = sde.beta_0 + t * (sde.beta_1 - sde.beta_0)
     _, g = sde.sde(torch.zeros(N, 1, 1, 1), t)
-    if predictor_kind == 'reverse_diffusion' and isinstance(sde, sde_lib.VPSDE):
+    if predictor_kind == 'ancestral_sampling':                         # sampling.py:225-232 (VP only, like the reference)
+      b_i = sde.discrete_betas[(t * (N - 1) / T).long()]
+      pa, pb, pc = 1. / torch.sqrt(1. - b_i), b_i * ss / torch.sqrt(1. - b_i), torch.sqrt(b_i)
+    elif predictor_kind == 'reverse_diffusion' and isinstance(sde, sde_lib.VPSDE):
       idx = (t * (N - 1) / T).long()
       a_i, b_i = sde.alphas[idx], sde.discrete_betas[idx]              # sde_lib.py:155-164
       pa, pb, pc = 2. - torch.sqrt(a_i), b_i * half * ss, torch.sqrt(b_i)
@@ -82,7 +93,14 @@ def build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps):
   if probability_flow:
     pc = torch.zeros(N)
   f32 = lambda v: np.ascontiguousarray(v.to(torch.float32).numpy())
-  return dict(label=f32(label), score_scale=f32(ss), alpha=f32(alpha), pa=f32(pa), pb=f32(pb), pc=f32(pc))
+  out = dict(label=f32(label), score_scale=f32(ss), alpha=f32(alpha), pa=f32(pa), pb=f32(pb), pc=f32(pc))
+  if corrector_kind == 'ald':
+    # AnnealedLangevinDynamics (sampling.py:299-317): step_size = (snr * std)^2 * 2 * alpha with the marginal std of the
+    # step - no norms - so x_mean = x + step_size * score, x = x_mean + sqrt(2 step_size) * z is affine as well
+    std = sde.marginal_prob(torch.zeros(N, 1, 1, 1), t)[1]
+    step = (snr * std) ** 2 * 2 * alpha
+    out.update(ca=f32(ones.clone()), cb=f32(step * ss), cc=f32(torch.sqrt(step * 2)))
+  return out
 
 
 class PcPlan:
@@ -92,7 +110,7 @@ class PcPlan:
     self.model, self.sde, self.shape, self.device = model, sde, tuple(shape), model._explicit_device(device)
     self.predictor_kind, self.corrector_kind = predictor_kind, corrector_kind
     self.snr, self.n_steps, self.probability_flow, self.eps = float(snr), int(n_steps), bool(probability_flow), float(eps)
-    self.tables = build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps)
+    self.tables = build_tables(sde, predictor_kind, corrector_kind, probability_flow, eps, snr=float(snr))
     self._pc = None
     self._ws = None
     self._engine_id = None
@@ -118,13 +136,14 @@ class PcPlan:
     self._release()
     cfg = _lib.PcConfig()
     cfg.n_steps = self.sde.N
-    cfg.corrector = 1 if self.corrector_kind == 'langevin' else 0
+    cfg.corrector = {'langevin': 1, 'ald': 2}.get(self.corrector_kind, 0)
     cfg.predictor = 0 if self.predictor_kind == 'none' else 1
     cfg.n_corrector_steps = self.n_steps
     cfg.snr = self.snr
     fp = ctypes.POINTER(ctypes.c_float)
-    for k in ('label', 'score_scale', 'alpha', 'pa', 'pb', 'pc'):
-      setattr(cfg, k, self.tables[k].ctypes.data_as(fp))
+    for k in ('label', 'score_scale', 'alpha', 'pa', 'pb', 'pc', 'ca', 'cb', 'cc'):
+      if k in self.tables:
+        setattr(cfg, k, self.tables[k].ctypes.data_as(fp))
     h = ctypes.c_void_p()
     _lib.call('b200_pc_create', eng['h'], ctypes.byref(cfg), self.shape[0], ctypes.byref(h))
     self._pc = h
@@ -184,7 +203,9 @@ def _kind_of_predictor(predictor):
     return 'reverse_diffusion'
   if predictor is sampling.EulerMaruyamaPredictor:
     return 'euler_maruyama'
-  return None   # user classes and ancestral sampling run on the generic host loop
+  if predictor is sampling.AncestralSamplingPredictor:
+    return 'ancestral_sampling'
+  return None   # user classes run on the generic host loop
 
 
 def _kind_of_corrector(corrector):
@@ -193,6 +214,8 @@ def _kind_of_corrector(corrector):
     return 'none'
   if corrector is sampling.LangevinCorrector:
     return 'langevin'
+  if corrector is sampling.AnnealedLangevinDynamics:
+    return 'ald'
   return None
 
 
@@ -207,9 +230,11 @@ def match_pc_plan(sde, model, predictor, corrector, shape, snr, n_steps, probabi
   pk, ck = _kind_of_predictor(predictor), _kind_of_corrector(corrector)
   if pk is None or ck is None or (pk == 'none' and ck == 'none'):
     return None
-  if ck == 'langevin' and isinstance(sde, sde_lib.subVPSDE):
-    return None   # the reference itself fails here (subVPSDE has no .alphas, sampling.py:267-269)
-  if ck == 'langevin' and n_steps < 1:
+  if ck in ('langevin', 'ald') and isinstance(sde, sde_lib.subVPSDE):
+    return None   # the reference itself fails here (subVPSDE has no .alphas, sampling.py:267-269, :303-305)
+  if pk == 'ancestral_sampling' and (isinstance(sde, sde_lib.subVPSDE) or probability_flow):
+    return None   # the reference raises for these (sampling.py:208-211): let its host-side class do so
+  if ck in ('langevin', 'ald') and n_steps < 1:
     return None
   # keyed on the SDE's parameters (not id(sde): a freed-and-reallocated SDE object must not hit a stale plan)
   sde_key = (type(sde).__name__, int(sde.N)) + tuple(

@@ -336,3 +336,42 @@ def test_programmatic_dependent_launch_plan_matches_the_serialized_plan(dev):
   with torch.no_grad():
     ref, _ = SO.pc_sample(osde, lambda a, l: NO.ncsnpp_forward(sd, cfg, a, l), shape, eps=1e-5, device=dev, x_init=x0, num_iters=6)
   assert rel_l2(outs[(True, True)], ref) < TOL_PARITY
+
+
+@pytest.mark.parametrize('combo', ['ve_ancestral_langevin', 've_rd_ald', 've_ancestral_ald', 'vp_ancestral_ald', 'vp_ancestral_none'])
+def test_native_loop_ancestral_sampling_and_annealed_langevin(dev, combo):
+  """AncestralSamplingPredictor (sampling.py:204-239) and AnnealedLangevinDynamics (:286-319) through the native loop
+  (affine tables, the same kernels, in-kernel Philox) against the oracle loop on the same CUDA noise stream - and through
+  get_pc_sampler, which must pick the native plan for them."""
+  from score_sde_pytorch_b200 import native, sampling, sde_lib
+  is_ve = combo.startswith('ve')
+  cfg = golden_config('tiny' if is_ve else 'tiny_vp')
+  model = seeded_model(cfg, precision='fp32').to(dev)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  shape = (4, 3, 16, 16)
+  if is_ve:
+    sde, osde, eps, snr = sde_lib.VESDE(0.01, 50, 12), SO.VE(0.01, 50, 12), 1e-5, 0.16
+  else:
+    sde, osde, eps, snr = sde_lib.VPSDE(0.1, 20., 100), SO.VP(0.1, 20., 100), 1e-3, 0.05
+  pred_name = 'ancestral_sampling' if 'ancestral' in combo else 'reverse_diffusion'
+  corr_name = 'ald' if combo.endswith('ald') else 'langevin' if combo.endswith('langevin') else 'none'
+  pred = sampling.AncestralSamplingPredictor if pred_name == 'ancestral_sampling' else sampling.ReverseDiffusionPredictor
+  corr = {'ald': sampling.AnnealedLangevinDynamics, 'langevin': sampling.LangevinCorrector, 'none': sampling.NoneCorrector}[corr_name]
+  torch.manual_seed(5)
+  x0 = osde.prior_sampling(shape).to(dev)
+  torch.cuda.manual_seed(77)
+  ref, _ = SO.pc_sample(osde, _oracle_net(cfg, sd), shape, pred_name, corr_name, snr=snr, n_steps=1, eps=eps, denoise=True, device=dev, x_init=x0)
+  assert torch.isfinite(ref).all(), 'oracle trajectory diverged: pick a tamer test configuration'
+  off_ref = torch.cuda.default_generators[0].get_offset()
+  plan = _plan(model, sde, pred, corr, shape, dev, eps, snr)
+  torch.cuda.manual_seed(77)
+  x, x_mean = plan.run(x0)
+  assert torch.cuda.default_generators[0].get_offset() == off_ref
+  e = rel_l2(x_mean, ref)
+  print(f'native {combo}: rel-L2 vs oracle loop {e:.2e}')
+  assert e < 2e-4
+  fn = sampling.get_pc_sampler(sde, shape, pred, corr, lambda v: v, snr=snr, n_steps=1, continuous=True, denoise=True, eps=eps, device=dev)
+  torch.manual_seed(5); torch.cuda.manual_seed(77)
+  s, _ = fn(model)
+  assert getattr(model, '_pc_plans', None), 'native plan was not engaged'
+  assert rel_l2(s, ref) < 2e-4

@@ -167,6 +167,44 @@ def test_affine_predictor_tables_reproduce_host_predictors():
           assert torch.allclose(xn, xn2, rtol=2e-5, atol=2e-5), (type(sde).__name__, kind, pf, i)
 
 
+def test_affine_tables_reproduce_ancestral_sampling_and_annealed_langevin():
+  """Round 2: AncestralSamplingPredictor (sampling.py:204-239) and AnnealedLangevinDynamics (:286-319) are affine in
+  (x, network output, noise) too, so the native loop runs them from tables; the tables must reproduce the classes."""
+  class Fixed(torch.nn.Module):
+    def __init__(self, out):
+      super().__init__()
+      self.out = out
+
+    def forward(self, x, labels):
+      return self.out
+
+  torch.manual_seed(0)
+  x, out = torch.randn(3, 2, 4, 4), torch.randn(3, 2, 4, 4)
+  for sde, eps in ((sde_lib.VESDE(0.01, 50, 50), 1e-5), (sde_lib.VPSDE(0.1, 20., 50), 1e-3)):
+    score_fn = mutils.get_score_fn(sde, Fixed(out), train=False, continuous=True)
+    tb = native.build_tables(sde, 'ancestral_sampling', 'ald', False, eps, snr=0.17)
+    ts = torch.linspace(sde.T, eps, sde.N)
+    for i in (0, 7, sde.N - 1):
+      t = torch.ones(3) * ts[i]
+      torch.manual_seed(5)
+      xn, xm = sampling.AncestralSamplingPredictor(sde, score_fn, False).update_fn(x, t)
+      torch.manual_seed(5)
+      zz = torch.randn_like(x)
+      xm2 = float(tb['pa'][i]) * x + float(tb['pb'][i]) * out
+      assert torch.allclose(xm, xm2, rtol=2e-5, atol=2e-5) and torch.allclose(xn, xm2 + float(tb['pc'][i]) * zz, rtol=2e-5, atol=2e-5)
+      torch.manual_seed(6)
+      xn, xm = sampling.AnnealedLangevinDynamics(sde, score_fn, 0.17, 1).update_fn(x, t)
+      torch.manual_seed(6)
+      zz = torch.randn_like(x)
+      xm2 = float(tb['ca'][i]) * x + float(tb['cb'][i]) * out
+      assert torch.allclose(xm, xm2, rtol=2e-5, atol=2e-5) and torch.allclose(xn, xm2 + float(tb['cc'][i]) * zz, rtol=2e-5, atol=2e-5)
+  # combinations the reference itself rejects stay on the host loop (which raises like the reference)
+  m = seeded_model(golden_config('tiny'))
+  kw = dict(shape=(2, 3, 16, 16), snr=0.16, n_steps=1, continuous=True, eps=1e-3, device='cuda')
+  assert native.match_pc_plan(sde=sde_lib.subVPSDE(0.1, 20., 10), model=m, predictor=sampling.AncestralSamplingPredictor,
+                              corrector=sampling.NoneCorrector, probability_flow=False, **kw) is None
+
+
 def test_library_loads_and_exports_every_declared_symbol():
   lib = _lib.load()
   assert lib.b200_version() >= 100

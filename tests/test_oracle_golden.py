@@ -110,6 +110,28 @@ def test_pc_sampler_oracle_matches_reference_none_predictor_and_subvp():
   assert rel_l2(s, torch.from_numpy(g['subvp_rd_none'])) < 1e-5
 
 
+def test_pc_sampler_oracle_matches_reference_ancestral_and_ald():
+  """AncestralSamplingPredictor (sampling.py:204-239) and AnnealedLangevinDynamics (:286-319) under VE and VP
+  (tools/make_golden_r2.py, pc_ancestral_ald_tiny.npz)."""
+  g = golden('pc_ancestral_ald_tiny.npz')
+  model = _OracleModel(golden_config('tiny'))
+  shape = tuple(golden('ncsnpp_tiny.npz')['x'].shape)
+  torch.manual_seed(34)
+  s, _ = SO.pc_sample(SO.VE(0.01, 50, 12), model, shape, 'ancestral_sampling', 'langevin', snr=0.16, n_steps=1, eps=1e-5)
+  assert rel_l2(s, torch.from_numpy(g['ve_ancestral_langevin'])) < 1e-5
+  torch.manual_seed(35)
+  s, _ = SO.pc_sample(SO.VE(0.01, 50, 12), model, shape, 'reverse_diffusion', 'ald', snr=0.16, n_steps=1, eps=1e-5)
+  assert rel_l2(s, torch.from_numpy(g['ve_rd_ald'])) < 1e-5
+  model = _OracleModel(golden_config('tiny_vp'))
+  shape = tuple(golden('ncsnpp_tiny_vp.npz')['x'].shape)
+  torch.manual_seed(36)
+  s, _ = SO.pc_sample(SO.VP(0.1, 20., 100), model, shape, 'ancestral_sampling', 'ald', snr=0.05, n_steps=1, eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['vp_ancestral_ald'])) < 1e-5
+  torch.manual_seed(37)
+  s, _ = SO.pc_sample(SO.VP(0.1, 20., 100), model, shape, 'ancestral_sampling', 'none', snr=0.16, n_steps=1, eps=1e-3)
+  assert rel_l2(s, torch.from_numpy(g['vp_ancestral_none'])) < 1e-5
+
+
 def test_pc_sampler_oracle_matches_reference_ddpmpp():
   """DDPM++ (tools/make_golden_ddpmpp.py): the config's own sampler - Euler-Maruyama, no corrector -
   under the VP and sub-VP SDEs, through the reference's get_pc_sampler on the reference's NCSNpp(fir=False,

@@ -54,6 +54,33 @@ def main():
     s, nfe = fn(m)
     out[tag] = s.numpy(); out[tag + '_nfe'] = nfe
   np.savez_compressed(os.path.join(MG.OUT, 'pc_extra_tiny.npz'), **out)
+
+  # ---- pc_ancestral_ald_tiny.npz: AncestralSamplingPredictor (sampling.py:204-239) and AnnealedLangevinDynamics (:286-319)
+  out2 = {}
+  cfg, B, m = ref_model_for('tiny')
+  shape = (B, cfg.data.num_channels, cfg.data.image_size, cfg.data.image_size)
+  sde = sde_lib.VESDE(sigma_min=0.01, sigma_max=50, N=12)
+  for tag, pred, corr, seed in (('ve_ancestral_langevin', sampling.AncestralSamplingPredictor, sampling.LangevinCorrector, 34),
+                                ('ve_rd_ald', sampling.ReverseDiffusionPredictor, sampling.AnnealedLangevinDynamics, 35)):
+    fn = sampling.get_pc_sampler(sde, shape, pred, corr, lambda v: v, snr=0.16, n_steps=1, probability_flow=False,
+                                 continuous=True, denoise=True, eps=1e-5, device='cpu')
+    torch.manual_seed(seed)
+    s, nfe = fn(m)
+    out2[tag] = s.numpy()
+  cfg, B, m = ref_model_for('tiny_vp')
+  shape = (B, cfg.data.num_channels, cfg.data.image_size, cfg.data.image_size)
+  # N = 100: with N = 20 the last discrete beta is 20/20 = 1 and the ancestral update divides by sqrt(1 - beta) = 0
+  sde = sde_lib.VPSDE(beta_min=0.1, beta_max=20., N=100)
+  for tag, pred, corr, snr, seed in (('vp_ancestral_ald', sampling.AncestralSamplingPredictor, sampling.AnnealedLangevinDynamics, 0.05, 36),
+                                     ('vp_ancestral_none', sampling.AncestralSamplingPredictor, sampling.NoneCorrector, 0.16, 37)):
+    fn = sampling.get_pc_sampler(sde, shape, pred, corr, lambda v: v, snr=snr, n_steps=1, probability_flow=False,
+                                 continuous=True, denoise=True, eps=1e-3, device='cpu')
+    torch.manual_seed(seed)
+    s, nfe = fn(m)
+    assert torch.isfinite(s).all(), tag
+    out2[tag] = s.numpy()
+  np.savez_compressed(os.path.join(MG.OUT, 'pc_ancestral_ald_tiny.npz'), **out2)
+  print('written', {k: v.shape for k, v in out2.items()})
   print('written', {k: (v.shape if hasattr(v, 'shape') else v) for k, v in out.items()})
 
 
