@@ -368,6 +368,26 @@ class NCSNpp(nn.Module):
                 _lib.ptr(out), _lib.stream_ptr(x.device))
     return out
 
+  def activation_range_report(self, x, time_cond, limit=65504.0):
+    """Largest magnitude of every module output of one evaluation, measured with an fp32-range (`'tf32'`) copy of this
+    network.  `precision='f16'` stores the operands of every contraction - normalised activations, but also the raw block
+    inputs of the skip projections - as IEEE fp16, which assumes |value| < 65504 (and loses precision below 6e-5);
+    random-init and normalised activations are far inside, a trained checkpoint can be checked with this before it is
+    sampled in fp16 mode.  Returns ``{'max_abs': {module_index: float}, 'worst': (index, value), 'fits_f16': bool}``."""
+    probe = NCSNpp(self.config, precision='tf32', keep_activations=True, separate_groupnorm=True, pdl=False).to(x.device)
+    probe.load_state_dict(self.state_dict())
+    with torch.no_grad():
+      probe(x, time_cond)
+    out = {}
+    for i in range(len(self.all_modules)):
+      try:
+        out[i] = float(probe.tap(i).abs().max())
+      except RuntimeError:
+        continue
+    probe._release()
+    worst = max(out.items(), key=lambda kv: kv[1])
+    return dict(max_abs=out, worst=worst, fits_f16=bool(worst[1] < limit))
+
   def tap(self, module_index):
     """Debug (``keep_activations=True``): output of ``all_modules[module_index]`` as NCHW."""
     eng = self._engine

@@ -47,6 +47,26 @@ def test_upfirdn2d_nhwc_matches_oracle(dev, mode, shape):
   assert (y2 - ref).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize('up,down', [(1, 1), (1, 2), (2, 1)])
+def test_upfirdn2d_planar_kernel_asymmetric_taps_and_ragged_shapes(dev, up, down):
+  """The planar 4x4 path (the reference's [N*C, H, W, 1] layout, four outputs along W per thread) with a NON-symmetric FIR
+  (a flipped or transposed tap order would show), every pad0 in 0..3, odd sizes, output widths that are not multiples of
+  four and a 1-pixel-wide plane."""
+  from score_sde_pytorch_b200.op import upfirdn2d
+  g = torch.Generator().manual_seed(5)
+  kk = torch.rand(4, 4, generator=g) - 0.3
+  for shape in ((2, 3, 9, 13), (1, 5, 16, 6), (3, 1, 7, 1), (1, 2, 32, 34)):
+    x = torch.randn(*shape, generator=g)
+    for p0 in range(4):
+      for p1 in (0, 1, 3):
+        if (shape[2] * up + p0 + p1 - 4) // down + 1 <= 0 or (shape[3] * up + p0 + p1 - 4) // down + 1 <= 0:
+          continue
+        ref = NO.upfirdn2d_native(x, kk, up=up, down=down, pad=(p0, p1)).to(dev)
+        y = upfirdn2d(x.to(dev), kk, up=up, down=down, pad=(p0, p1))
+        assert y.shape == ref.shape, (shape, p0, p1)
+        assert (y - ref).abs().max().item() < 1e-5, (shape, up, down, p0, p1)
+
+
 def test_upfirdn2d_rejects_cpu_and_bad_kernel(dev):
   from score_sde_pytorch_b200.op import upfirdn2d
   with pytest.raises(RuntimeError):

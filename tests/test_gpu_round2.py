@@ -375,3 +375,20 @@ def test_native_loop_ancestral_sampling_and_annealed_langevin(dev, combo):
   s, _ = fn(model)
   assert getattr(model, '_pc_plans', None), 'native plan was not engaged'
   assert rel_l2(s, ref) < 2e-4
+
+
+def test_activation_range_report_guards_the_fp16_operand_mode(dev):
+  """`precision='f16'` assumes every contraction operand fits IEEE fp16; `activation_range_report` measures the module
+  outputs of one evaluation in an fp32-range copy of the network so a checkpoint can be checked first."""
+  cfg = golden_config('cifar10_ve')
+  model = seeded_model(cfg, precision='f16').to(dev)
+  torch.manual_seed(1)
+  x = torch.randn(2, 3, 32, 32, device=dev) * 50          # the prior's scale: the largest inputs the sampler sees
+  rep = model.activation_range_report(x, torch.tensor([50.0, 0.01], device=dev))
+  print(f'activation range: worst module {rep["worst"][0]} max |a| = {rep["worst"][1]:.3g}; {len(rep["max_abs"])} modules')
+  assert rep['fits_f16'] and rep['worst'][1] < 6.5e4 and len(rep['max_abs']) > 40
+  # a network whose residual stream leaves the fp16 range is reported as such
+  with torch.no_grad():
+    model.all_modules[3].weight.mul_(1e5)
+  model.invalidate_weights()
+  assert not model.activation_range_report(x, torch.tensor([50.0, 0.01], device=dev))['fits_f16']
