@@ -79,3 +79,19 @@ def test_high_resolution_reference_configs_full_size(dev, name, precision):
   print(f'{name} [{precision}] 1x3x{R}x{R}: rel-L2 vs oracle {e:.3e}, {model.launches_per_forward()} launches')
   assert torch.isfinite(y).all()
   assert e < 2.5e-3
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'f16'])
+def test_deep_cifar10_variant_matches_oracle(dev, precision):
+  """configs/ve/cifar10_ncsnpp_deep_continuous.py: eight residual blocks per level ("deep")."""
+  cfg = golden_config('cifar10_deep')
+  model = seeded_model(cfg, precision=precision).to(dev)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  torch.manual_seed(6)
+  x = torch.randn(2, 3, 32, 32, device=dev) * 4
+  sigma = torch.tensor([12.0, 0.4], device=dev)
+  with torch.no_grad():
+    e = rel_l2(model(x, sigma), NO.ncsnpp_forward(sd, cfg, x, sigma))
+  print(f'cifar10 deep [{precision}]: rel-L2 vs oracle {e:.3e}, {model.launches_per_forward()} launches, '
+        f'{sum(p.numel() for p in model.parameters())} parameters')
+  assert e < 2.5e-3
