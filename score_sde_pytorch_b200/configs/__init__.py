@@ -191,3 +191,18 @@ def tiny_progressive(nf=32, image_size=32, num_res_blocks=1, ch_mult=(1, 1, 2), 
   c.model.progressive_combine = 'sum'
   c.model.fir = fir
   return c
+
+
+def subvp_celebahq_256_ddpmpp_continuous():
+  """BASELINE.json configs[3]: "DDPM++ cont. CelebA-HQ 256 sub-VP".  The reference ships no such config file; as SURVEY
+  section 8(f) notes it is composed from ``configs/subvp/cifar10_ddpmpp_continuous.py`` (DDPM++: ``fir=False``, positional
+  embedding, no pyramids, sub-VP SDE, Euler-Maruyama predictor) with the 256-pixel data / ``ch_mult`` fields of
+  ``configs/ve/celebahq_256_ncsnpp_continuous.py``."""
+  c = subvp_cifar10_ddpmpp_continuous()
+  c.data.dataset = 'CelebAHQ'
+  c.data.image_size = 256
+  c.eval.batch_size = 64
+  c.model.ch_mult = (1, 1, 2, 2, 2, 2, 2)
+  c.model.num_res_blocks = 2
+  c.model.attn_resolutions = (16,)
+  return c

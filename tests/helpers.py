@@ -37,6 +37,10 @@ def golden_config(name):
     c = configs.vp_cifar10_ddpmpp_continuous()
     c.model.init_scale = 1.0
     return c
+  if name == 'celebahq_256_ddpmpp_subvp':
+    c = configs.subvp_celebahq_256_ddpmpp_continuous()
+    c.model.init_scale = 1.0
+    return c
   if name == 'cifar10_deep':
     c = configs.ve_cifar10_ncsnpp_deep_continuous()
     c.model.init_scale = 1.0

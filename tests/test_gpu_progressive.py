@@ -7,6 +7,7 @@ import torch
 
 from helpers import golden, golden_config, seeded_model, rel_l2
 from oracle import ncsnpp_oracle as NO
+from oracle import sampling_oracle as SO
 
 pytestmark = pytest.mark.gpu
 
@@ -95,3 +96,52 @@ def test_deep_cifar10_variant_matches_oracle(dev, precision):
   print(f'cifar10 deep [{precision}]: rel-L2 vs oracle {e:.3e}, {model.launches_per_forward()} launches, '
         f'{sum(p.numel() for p in model.parameters())} parameters')
   assert e < 2.5e-3
+
+
+def test_baseline_config3_ddpmpp_celebahq256_subvp_ode_sampler(dev):
+  """BASELINE.json configs[3] at batch 1: DDPM++ cont. (fir=False, positional embedding) at 256x256 under the sub-VP SDE,
+  probability-flow ODE sampler with the state on the device.  One evaluation against the strict-fp32 oracle, then the
+  device RK45 solve against this package's scipy host loop on the same network (looser tolerances than the default
+  1e-5 keep the oracle-free comparison to a few dozen evaluations)."""
+  from score_sde_pytorch_b200 import sampling, sde_lib
+  cfg = golden_config('celebahq_256_ddpmpp_subvp')
+  model = seeded_model(cfg, precision='f16').to(dev)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  shape = (1, 3, 256, 256)
+  torch.manual_seed(8)
+  x = torch.randn(*shape, device=dev)
+  lab = torch.tensor([500.3], device=dev)
+  with torch.no_grad():
+    e = rel_l2(model(x, lab), NO.ncsnpp_forward(sd, cfg, x, lab))
+  sde = sde_lib.subVPSDE(0.1, 20., 1000)
+  z = sde.prior_sampling(shape).to(dev)
+  kw = dict(denoise=False, rtol=1e-2, atol=1e-2, eps=1e-3, device=dev)
+  s_dev, nfe_dev = sampling.get_ode_sampler(sde, shape, lambda v: v, **kw)(model, z=z.clone())
+  s_host, nfe_host = sampling.get_ode_sampler(sde, shape, lambda v: v, device_solver=False, **kw)(model, z=z.clone())
+  print(f'configs[3] (DDPM++ 256 sub-VP, f16): forward rel-L2 {e:.3e}; ODE nfe device {nfe_dev} / scipy {nfe_host}, rel-L2 {rel_l2(s_dev, s_host):.2e}')
+  assert e < 2.5e-3
+  assert nfe_dev == nfe_host and rel_l2(s_dev, s_host) < 1e-5
+
+
+def test_baseline_config4_ffhq1024_pc_sampler_steps(dev):
+  """BASELINE.json configs[4] at batch 1: NCSN++ FFHQ 1024x1024 VE-SDE PC sampler (reverse diffusion + Langevin) through
+  the native loop in tf32 mode, two iterations (four 1024x1024 evaluations) against the oracle loop on the same noise."""
+  from score_sde_pytorch_b200 import native, sampling, sde_lib
+  cfg = golden_config('ffhq_1024')
+  model = seeded_model(cfg, precision='tf32').to(dev)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  shape = (1, 3, 1024, 1024)
+  sde, osde = sde_lib.VESDE(0.01, 1348, 2000), SO.VE(0.01, 1348, 2000)
+  torch.manual_seed(9)
+  x0 = osde.prior_sampling(shape).to(dev)
+  plan = native.match_pc_plan(sde=sde, model=model, predictor=sampling.ReverseDiffusionPredictor, corrector=sampling.LangevinCorrector,
+                              shape=shape, snr=0.15, n_steps=1, probability_flow=False, continuous=True, eps=1e-5, device=dev)
+  assert plan is not None
+  torch.cuda.manual_seed(77)
+  _, xm = plan.run(x0, first_step=0, num_steps=2)
+  torch.cuda.manual_seed(77)
+  with torch.no_grad():
+    ref, _ = SO.pc_sample(osde, lambda a, l: NO.ncsnpp_forward(sd, cfg, a, l), shape, snr=0.15, eps=1e-5, device=dev, x_init=x0, num_iters=2)
+  e = rel_l2(xm, ref)
+  print(f'configs[4] (FFHQ-1024 PC, tf32): 2 iterations rel-L2 {e:.3e}')
+  assert e < 1e-3
