@@ -635,6 +635,77 @@ def run_gpu_arm(args):
     dist.destroy_process_group()
 
 
+# ---- secondary workloads (the other reference configurations the engine runs) ---------------------------
+# `python bench.py --workload NAME` prints ONE JSON line for a non-headline configuration on one GPU: same timing rules
+# (device-resident state, CUDA events, >= 3 warm-up steps), no CPU / reference / scaling legs.  Parity for these
+# configurations is held by tests/test_gpu_{ddpmpp,progressive,ode}.py; the headline line is unaffected.
+def run_secondary_workload(args):
+  from score_sde_pytorch_b200 import configs, native, sampling, sde_lib
+  from score_sde_pytorch_b200.models.ncsnpp import NCSNpp
+  dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+  torch.cuda.set_device(dev)
+  W = {
+    'cifar10_ddpmpp_vp': dict(cfg=configs.vp_cifar10_ddpmpp_continuous, sde=lambda: sde_lib.VPSDE(0.1, 20., 1000), batch=1024, precision='f16',
+                              pred=sampling.EulerMaruyamaPredictor, corr=sampling.NoneCorrector, eps=1e-3, snr=0.16, evals=1,
+                              desc='DDPM++ cont. CIFAR-10 32x32 VP-SDE, Euler-Maruyama predictor only (configs/vp/cifar10_ddpmpp_continuous.py), 1000 steps'),
+    'celebahq_256_ve': dict(cfg=configs.ve_celebahq_256_ncsnpp_continuous, sde=lambda: sde_lib.VESDE(0.01, 348, 2000), batch=16, precision='f16',
+                            pred=sampling.ReverseDiffusionPredictor, corr=sampling.LangevinCorrector, eps=1e-5, snr=0.17, evals=2,
+                            desc='NCSN++ cont. CelebA-HQ 256x256 VE-SDE PC sampler (configs/ve/celebahq_256_ncsnpp_continuous.py), 2000 steps'),
+    'ffhq_1024_ve': dict(cfg=configs.ve_ffhq_1024_ncsnpp_continuous, sde=lambda: sde_lib.VESDE(0.01, 1348, 2000), batch=2, precision='tf32',
+                         pred=sampling.ReverseDiffusionPredictor, corr=sampling.LangevinCorrector, eps=1e-5, snr=0.15, evals=2,
+                         desc='NCSN++ FFHQ 1024x1024 VE-SDE PC sampler (configs/ve/ffhq_ncsnpp_continuous.py; BASELINE configs[4] per-GPU share), 2000 steps'),
+    'celebahq_256_ddpmpp_subvp_ode': dict(cfg=configs.subvp_celebahq_256_ddpmpp_continuous, sde=lambda: sde_lib.subVPSDE(0.1, 20., 1000), batch=8, precision='f16',
+                                          ode=True, eps=1e-3,
+                                          desc='DDPM++ cont. CelebA-HQ 256 sub-VP probability-flow ODE sampler, RK45 rtol=atol=1e-5, state on the device '
+                                               '(BASELINE configs[3] per-GPU share)'),
+  }[args.workload]
+  cfg = W['cfg']()
+  cfg.model.init_scale = 1.0
+  cfg.device = dev
+  B = W['batch'] if args.batch == 1024 and W['batch'] != 1024 else args.batch
+  R = cfg.data.image_size
+  shape = (B, 3, R, R)
+  torch.manual_seed(0)
+  model = NCSNpp(cfg, precision=W['precision']).to(dev)
+  sde = W['sde']()
+  torch.manual_seed(1); torch.cuda.manual_seed(1)
+  clk = ClockSampler(dev.index or 0)
+  if W.get('ode'):
+    z = sde.prior_sampling(shape).to(dev)
+    fn = sampling.get_ode_sampler(sde, shape, lambda v: v, denoise=False, rtol=1e-5, atol=1e-5, eps=W['eps'], device=dev)
+    fn(model, z=z.clone())                                     # warm-up solve (plans, allocator)
+    torch.cuda.synchronize()
+    clk.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s, nfe = fn(model, z=z.clone())
+    e1.record(); torch.cuda.synchronize()
+    clocks = clk.stop()
+    ms = e0.elapsed_time(e1)
+    line = dict(metric='probability-flow ODE sampler images/sec', value=round(B / (ms * 1e-3), 4), unit='images/s', n_gpus=1, steps=int(nfe),
+                warmup=1, ms_per_step=round(ms / nfe, 4), higher_is_better=True, scaling='weak', vs_baseline=None, dtype=W['precision'], data='synthetic',
+                config=dict(workload=W['desc'], batch_per_gpu=B, nfe=int(nfe), host_scalar_reads=fn.last_stats.get('host_scalar_reads'),
+                            step='one right-hand side = one network evaluation + Dormand-Prince stage arithmetic in float64 on the device',
+                            weights='random init, init_scale=1, torch.manual_seed(0)'),
+                clocks=clocks, finite=bool(torch.isfinite(s).all()), gpu_launches=int(model.launches_per_forward()) * int(nfe))
+  else:
+    plan = native.match_pc_plan(sde=sde, model=model, predictor=W['pred'], corrector=W['corr'], shape=shape, snr=W['snr'], n_steps=1,
+                                probability_flow=False, continuous=True, eps=W['eps'], device=dev)
+    assert plan is not None
+    x0 = sde.prior_sampling(shape).to(dev)
+    timed_steps(plan, x0, args.warmup, 1)
+    clk.start()
+    ms = timed_steps(plan, x0, args.warmup, args.steps)
+    clocks = clk.stop()
+    N = sde.N
+    line = dict(metric='PC-sampler images/sec', value=round(B / (N * ms * 1e-3), 4), unit='images/s', n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round(ms, 4), higher_is_better=True, scaling='weak', vs_baseline=None, dtype=W['precision'], data='synthetic',
+                config=dict(workload=W['desc'], batch_per_gpu=B, sampler_steps=N, score_evaluations_per_step=W['evals'],
+                            parameters=sum(p.numel() for p in model.parameters()), weights='random init, init_scale=1, torch.manual_seed(0)'),
+                clocks=clocks, finite=bool(torch.isfinite(plan._xm).all()), gpu_launches=int(plan.launches_per_step()) * args.steps)
+  print(json.dumps(line), flush=True)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -657,11 +728,16 @@ def main():
                   help='PC iterations of the in-run parity check against the strict-fp32 GPU oracle at the full batch (0 = skip)')
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help="'weak' (default, headline): --batch images per GPU; 'strong': --batch images in total, cut over the ranks")
+  ap.add_argument('--workload', default='cifar10_ve',
+                  choices=['cifar10_ve', 'cifar10_ddpmpp_vp', 'celebahq_256_ve', 'ffhq_1024_ve', 'celebahq_256_ddpmpp_subvp_ode'],
+                  help="'cifar10_ve' (default) is the headline line; the others print one line for a secondary configuration (1 GPU)")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'ours':
     args.warmup = 3
   if args.impl == 'reference':
     run_reference_arm(args)
+  elif args.workload != 'cifar10_ve':
+    run_secondary_workload(args)
   else:
     run_gpu_arm(args)
 
