@@ -723,7 +723,7 @@ bool tc_gemm_supported(const TcGemmDesc& d, const char** why) {
     if (d.C3 % bke || d.C3 <= 0 || (d.a4 && d.C4 % bke)) return fail("extra-phase channel counts must be multiples of 32 (tf32) / 64 (f16)");
   }
   if (d.epi.out_nchw) {   // network head: zero-padded 128-row weight tile, swapped form, NCHW store of the real channels
-    if (!(d.conv && d.N_total == 128 && d.epi.n_valid > 0 && d.epi.n_valid <= 32 && (d.H * d.W) % 256 == 0 && d.W <= BM && d.stride != 2 &&
+    if (!(d.conv && d.N_total == 128 && d.epi.n_valid > 0 && d.epi.n_valid <= 32 && (d.H * d.W) % 256 == 0 && (d.W <= BM || d.W % BM == 0) && d.stride != 2 &&
           !d.qstats && !d.epi.residual && !d.epi.rowvec && d.epi.round_tf32 == 0))
       return fail("NCHW head needs a 128-row padded weight tile, HW % 256 == 0 and a plain epilogue");
   } else if (d.epi.per_img_div) return fail("per-image divisor only with the NCHW head epilogue");
@@ -760,8 +760,10 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     //    slot (small launches fill the SMs better with single-CTA tiles); `no_pair` in the descriptor opts out;
     //  * launches too small to give every SM a 256-column tile are cut into 128-column tiles: twice the CTAs at work.
     const long long Mtot = (long long)d.nimg * d.H * d.W;
+    // (image rows wider than 128 pixels - the 256..1024-pixel families - are cut into 128-pixel boxes like any other: the
+    // two boxes of a 256-pixel tile are then two halves of one row or of consecutive rows)
     const bool can_swap = d.conv && p.stride == 1 && (d.N_total % 256 != 0 || d.taps == 1) && (d.H * d.W) % 256 == 0 &&
-                          d.W <= BM && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
+                          (d.W <= BM || d.W % BM == 0) && Mtot % 256 == 0 && d.epi.rows_per_img % 256 == 0;
     p.swap = can_swap ? 1 : 0;
     if (d.epi.out_nchw && !p.swap) { delete pl; B200_REQUIRE(false, "gemm_tc: the NCHW head needs the swapped-operand form"); }
     if (p.swap) pl->bn = 256;
