@@ -18,15 +18,22 @@ ap.add_argument('--batch', type=int, default=1024)
 ap.add_argument('--precision', default='f16')
 ap.add_argument('--reps', type=int, default=5)
 ap.add_argument('--md', default=None)
+ap.add_argument('--config', default='headline', choices=['headline', 'celebahq_256', 'ddpmpp_256', 'ffhq_1024', 'cifar10_ddpmpp'])
 args = ap.parse_args()
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
-model = NCSNpp(headline_config(), precision=args.precision).to(dev)
+from score_sde_pytorch_b200 import configs                          # noqa: E402
+cfg = {'headline': headline_config, 'celebahq_256': configs.ve_celebahq_256_ncsnpp_continuous,
+       'ddpmpp_256': configs.subvp_celebahq_256_ddpmpp_continuous, 'ffhq_1024': configs.ve_ffhq_1024_ncsnpp_continuous,
+       'cifar10_ddpmpp': configs.vp_cifar10_ddpmpp_continuous}[args.config]()
+cfg.model.init_scale = 1.0
+model = NCSNpp(cfg, precision=args.precision).to(dev)
 B = args.batch
 eng = model.engine(B, dev)
 h = eng['h']
 n = int(_lib.load().b200_ncsnpp_num_ops(h))
-x = torch.randn(B, 3, 32, 32, device=dev) * 10
+R = cfg.data.image_size
+x = torch.randn(B, 3, R, R, device=dev) * 10
 lab = torch.full((B,), 1.0, device=dev)
 out = torch.empty_like(x)
 ms = (ctypes.c_float * n)()
@@ -43,7 +50,7 @@ for i in range(n):
   g = groups.setdefault(name.value.decode(), [0, 0.0, 0.0])
   g[0] += 1; g[1] += acc[i]; g[2] += fl.value
 total = sum(acc)
-lines = [f'# per-op profile, one network evaluation, batch {B}, {args.precision}: {n} ops, {total:.3f} ms (serial, event-timed)',
+lines = [f'# per-op profile ({args.config}), one network evaluation, batch {B}, {args.precision}: {n} ops, {total:.3f} ms (serial, event-timed)',
          '| op | launches | total ms | share | us/launch | TFLOP/s |', '|---|---:|---:|---:|---:|---:|']
 for k, (c, t, f) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
   tf = f / (t * 1e-3) / 1e12 if t > 0 and f > 0 else 0.0
