@@ -26,11 +26,16 @@ namespace b200 {
 constexpr int GN_THREADS = 384;   // divisible by C/4 for every channel count of the network (32, 64, 96, 128)
 
 __global__ void __launch_bounds__(GN_THREADS) gn_quad_stats_kernel(
-    const float* __restrict__ x, int C, int HW, double* __restrict__ qsums /* [B][C/4][2] */) {
+    const float* __restrict__ x, int C, int HW_img, double* __restrict__ qsums /* [B][C/4][2] */) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   extern __shared__ double sred[];   // [lanes][Q][2]
   const int Q = C >> 2, b = blockIdx.x;
-  const float* px = x + (long long)b * HW * C;
+  // gridDim.y > 1 (few large images: one CTA per image would leave the GPU idle): each CTA sums a slice of the pixels and
+  // ADDS its fp64 partials to qsums, which the caller has zeroed (the engine zeroes its whole statistics region per forward)
+  const int per = (HW_img + gridDim.y - 1) / gridDim.y, pix0 = blockIdx.y * per;
+  const int HW = max(0, min(HW_img, pix0 + per) - pix0);
+  const bool accumulate = gridDim.y > 1;
+  const float* px = x + ((long long)b * HW_img + pix0) * C;
   if (GN_THREADS % Q == 0) {
     // deterministic: thread owns quad q for pixels lane, lane+L, ...; fixed-order fold over lanes
     const int L = GN_THREADS / Q, q = threadIdx.x % Q, lane = threadIdx.x / Q;
@@ -56,8 +61,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_quad_stats_kernel(
     if (threadIdx.x < Q) {
       double a = 0.0, c = 0.0;
       for (int l = 0; l < L; ++l) { a += sred[(l * Q + threadIdx.x) * 2]; c += sred[(l * Q + threadIdx.x) * 2 + 1]; }
-      qsums[((long long)b * Q + threadIdx.x) * 2] = a;
-      qsums[((long long)b * Q + threadIdx.x) * 2 + 1] = c;
+      double* dst = qsums + ((long long)b * Q + threadIdx.x) * 2;
+      if (accumulate) { atomicAdd(dst, a); atomicAdd(dst + 1, c); }
+      else { dst[0] = a; dst[1] = c; }
     }
   } else {
     // generic channel counts: shared-memory fp64 atomics
@@ -70,16 +76,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_quad_stats_kernel(
       atomicAdd(&sred[2 * q + 1], ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * Q; i += blockDim.x) qsums[(long long)b * 2 * Q + i] = sred[i];
+    for (int i = threadIdx.x; i < 2 * Q; i += blockDim.x) {
+      if (accumulate) atomicAdd(&qsums[(long long)b * 2 * Q + i], sred[i]);
+      else qsums[(long long)b * 2 * Q + i] = sred[i];
+    }
   }
 }
 
-int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st) {
+int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st, bool qsums_zeroed) {
   B200_REQUIRE(C % 4 == 0, "gn_quad_stats: C=%d must be a multiple of 4", C);
   const int Q = C / 4;
   const size_t smem = (GN_THREADS % Q == 0) ? (size_t)GN_THREADS * 2 * sizeof(double) : (size_t)2 * Q * sizeof(double);
   B200_REQUIRE(smem <= 48 * 1024, "gn_quad_stats: C=%d too large", C);
-  launch_kernel(gn_quad_stats_kernel, dim3(B), dim3(GN_THREADS), smem, st, x, C, HW, qsums);
+  // few, large images (high-resolution networks at small batch): several CTAs per image, accumulating into zeroed sums
+  int splits = 1;
+  if (qsums_zeroed && B < 296 && HW >= 4096) splits = (int)std::min<long long>(std::min<long long>(64, HW / 1024), (296 + B - 1) / B);
+  launch_kernel(gn_quad_stats_kernel, dim3(B, splits), dim3(GN_THREADS), smem, st, x, C, HW, qsums);
   B200_CHECK_LAUNCH();
   return 0;
 }

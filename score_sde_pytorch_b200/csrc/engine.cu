@@ -425,7 +425,7 @@ struct Builder {
     t.qs = qalloc(t.C);
     const Tensor tt = t; const int Bc = B;
     name("gn_quad_stats %d @%d", t.C, t.H);
-    op(1, [=](cudaStream_t st) { return launch_gn_quad_stats(tt.p, tt.C, Bc, tt.H * tt.W, tt.qs, st); }, 2);
+    op(1, [=](cudaStream_t st) { return launch_gn_quad_stats(tt.p, tt.C, Bc, tt.H * tt.W, tt.qs, st, /*qsums_zeroed=*/true); }, 2);
   }
   void gn(Tensor& x1, Tensor& x2, int pgw, int pgb, int act, int round, Tensor y, float* raw) {
     const int C = x1.C + x2.C, G = std::min(C / 4, 32), HW = x1.H * x1.W;

@@ -10,7 +10,7 @@
 namespace b200 {
 
 // ---- elementwise.cu --------------------------------------------------------
-int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st);
+int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cudaStream_t st, bool qsums_zeroed = false);
 int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const double* q1, const double* q2,
                     const float* gamma, const float* beta, int B, int HW, int G, float eps, int act,
                     int round_out, float* y, float* raw, cudaStream_t st, int x1_f16 = 0);
