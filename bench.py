@@ -517,9 +517,9 @@ def run_gpu_arm(args):
       if kind_c.value == 0:
         _lib.call('b200_ncsnpp_op_bytes', eng['h'], i, ctypes.byref(bytes_c))
         tc_alg_bytes += bytes_c.value
-    kinds = ['tcgen05_contraction', 'cuda_core_contraction', 'groupnorm', 'fir', 'softmax', 'time_embedding', 'misc']
+    kinds = ['tcgen05_contraction', 'cuda_core_contraction', 'groupnorm', 'fir', 'softmax', 'time_embedding', 'misc', 'mma_sync_contraction']
     by_kind = {k: dict(ms=round(ms_k[i], 4), gflop=round(fl_k[i] / 1e9, 2), launches=int(n_k[i])) for i, k in enumerate(kinds)}
-    fwd_ms = sum(ms_k[i] for i in range(7))
+    fwd_ms = sum(ms_k[i] for i in range(8))
     tc_ms, tc_flops, tc_n = ms_k[0], fl_k[0], max(int(n_k[0]), 1)
     f16 = args.precision == 'f16'
     tf32_peak = measure_tf32_peak(dev, f16)

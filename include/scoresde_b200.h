@@ -65,7 +65,10 @@ B200_API int b200_randn_like_torch_f32(float* out, long long numel, unsigned lon
  * w_packed is [taps][c_out][c_in] (see b200_pack_conv_weight_f32). impl: 0 = fp32 CUDA cores,
  * 1 = tcgen05 TF32 (inputs must already be TF32-representable for exactness claims),
  * 2 = tcgen05 fp16: x1, x2 and w_packed hold IEEE fp16 elements (same layouts; round_tf32 = 2 packs / stores fp16);
- *     out is fp32 unless round_tf32 == 2. */
+ *     out is fp32 unless round_tf32 == 2;
+ * 3 = warp-level TF32 MMAs for few-channel layers (c1, c2 multiples of 16, c_out 16 / 32 / 64, h % 8 == 0, w % 32 == 0):
+ *     fp32 in and out, operands rounded to the TF32 grid while staged (the 16..64-channel levels of the nf = 16
+ *     high-resolution networks, configs/ve/ffhq_ncsnpp_continuous.py:71-94). */
 B200_API int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int batch, int h, int w,
                                 const float* w_packed, const float* bias, int c_out, int ksize,
                                 const float* rowvec, long long rowvec_ld, const float* residual, float scale,

@@ -118,6 +118,8 @@ int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int bat
   SimtConv s; memset(&s, 0, sizeof(s));
   s.x1 = x1; s.C1 = c1; s.x2 = x2; s.C2 = c2; s.in_scale = 1.f; s.H = h; s.W = w; s.R = s.S = ksize; s.stride = 1;
   s.pad = ksize / 2; s.OH = h; s.OW = w; s.nbatch = batch; s.a_batched = 1; s.w = w_packed; s.N = c_out; s.epi = ep;
+  if (impl == 3) return launch_conv_lowc(s, st);
+  B200_REQUIRE(impl == 0, "conv_nhwc: impl %d unknown", impl);
   return launch_conv_simt(s, st);
 }
 

@@ -1,0 +1,176 @@
+// Few-channel 3x3 / 1x1 stride-1 convolutions (Cin a multiple of 16, Cout 16 / 32 / 64) on NHWC fp32 tensors.
+//
+// These are the 1024..128-pixel levels of the high-resolution family (nf = 16: 16, 32, 64 channels;
+// /root/reference/configs/ve/ffhq_ncsnpp_continuous.py:71-94).  Their output tiles are far too narrow for the
+// tcgen05 tiling (N = 128 / 256 columns, K steps of 32 TF32 elements) and they are memory-bound by construction:
+// 16 -> 16 channels is 36 FLOP per byte.  What they need is enough contraction rate to stay at the HBM roofline,
+// which the strict-fp32 CUDA-core kernel (conv_simt.cu: 6 - 28 TFLOP/s on these shapes, 73 % of an FFHQ-1024
+// evaluation) does not have and warp-level TF32 MMAs do:
+//   * a CTA owns an 8 x 32 pixel output tile of one image; it stages the (8+2) x (32+2) pixel halo of one
+//     16-channel slab, rounded to the TF32 grid on the way in (one RN rounding per operand, like every TF32 layer of
+//     the engine), and the [tap][Cout][16] slab of the packed weights;
+//   * warp w computes row w of the tile: two m16 pixel blocks x Cout/8 n8 blocks, K walked as (tap, slab, k8);
+//   * all fragment loads are 128-bit: a lane reads channels 4t..4t+3 of its pixel / output row and the MMA's k slots
+//     are *defined* as (t -> 4t+2s, t+4 -> 4t+2s+1) for k8 step s.  The sum over k does not care about the order as
+//     long as A and B agree, so one LDS.128 feeds two MMAs and no shared-memory padding is needed (a quarter warp
+//     reads 32 consecutive words);
+//   * two CTAs per SM (<= 58 KB shared, <= 128 registers) overlap one tile's staging with the other's MMAs.
+// The epilogue is conv_simt's: + bias + per-image row vector + residual, * scale, optional TF32-grid store.
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int LC_TH = 8, LC_TW = 32, LC_KC = 16, LC_THREADS = 256;
+
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&d)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+__device__ __forceinline__ float4 round4_tf32(float4 v) {
+  v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+  return v;
+}
+
+template <int TAPS, int NB>
+__global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv p) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
+  constexpr int HALO = TAPS == 9 ? 1 : 0;
+  constexpr int PH = LC_TH + 2 * HALO, PW = LC_TW + 2 * HALO;
+  constexpr int N = NB * 8;
+  extern __shared__ __align__(16) float lc_smem[];
+  float* sA = lc_smem;                        // [PH][PW][16]   input slab with halo, TF32 grid
+  float* sB = lc_smem + PH * PW * LC_KC;      // [TAPS][N][16]  weight slab, TF32 grid
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tiles_x = p.W / LC_TW, tiles_y = p.H / LC_TH;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, img = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = tx * LC_TW, y0 = ty * LC_TH;
+  const int Cin = p.C1 + p.C2;
+  const long long ld1 = p.ld1 ? p.ld1 : p.C1, ld2 = p.ld2 ? p.ld2 : p.C2, wld = p.w_ld ? p.w_ld : Cin;
+  const float* a1 = p.x1 + (long long)img * p.H * p.W * ld1;
+  const float* a2 = p.x2 ? p.x2 + (long long)img * p.H * p.W * ld2 : nullptr;
+
+  float acc[2][NB][4];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mb][nb][i] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += LC_KC) {
+    const float* src = c0 < p.C1 ? a1 + c0 : a2 + (c0 - p.C1);
+    const long long ld = c0 < p.C1 ? ld1 : ld2;
+    __syncthreads();                          // the previous slab's fragment loads are done
+    for (int e = tid; e < PH * PW * 4; e += LC_THREADS) {
+      const int q = e & 3, pix = e >> 2, py = pix / PW, px = pix - py * PW;
+      const int iy = y0 + py - HALO, ix = x0 + px - HALO;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        v = round4_tf32(__ldg(reinterpret_cast<const float4*>(src + ((long long)iy * p.W + ix) * ld + 4 * q)));
+      *reinterpret_cast<float4*>(sA + pix * LC_KC + 4 * q) = v;
+    }
+    for (int e = tid; e < TAPS * N * 4; e += LC_THREADS) {
+      const int q = e & 3, row = e >> 2;      // row = tap * N + n of the packed [tap][N][Cin] weights
+      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (long long)row * wld + c0 + 4 * q)));
+      *reinterpret_cast<float4*>(sB + row * LC_KC + 4 * q) = v;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
+      float4 av[2][2];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          av[mb][h] = *reinterpret_cast<const float4*>(sA + ((warp + dy) * PW + mb * 16 + g + 8 * h + dx) * LC_KC + 4 * t);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const float4 bv = *reinterpret_cast<const float4*>(sB + (tap * N + nb * 8 + g) * LC_KC + 4 * t);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].x, av[mb][1].x, av[mb][0].y, av[mb][1].y, bv.x, bv.y);
+          mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].z, av[mb][1].z, av[mb][0].w, av[mb][1].w, bv.z, bv.w);
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: lane (g, t) holds pixels g / g+8 of each m16 block and output channels 2t, 2t+1 of each n8 block ----
+  const Epilogue& e = p.epi;
+  const int oy = y0 + warp;
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ox = x0 + mb * 16 + g + 8 * h;
+      const long long gm = ((long long)img * p.H + oy) * p.W + ox;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int n = nb * 8 + 2 * t;
+        float v0 = acc[mb][nb][2 * h], v1 = acc[mb][nb][2 * h + 1];
+        if (e.bias) { const float2 b = __ldg(reinterpret_cast<const float2*>(e.bias + n)); v0 += b.x; v1 += b.y; }
+        if (e.rowvec) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.rowvec + img * e.rowvec_ld + n)); v0 += r.x; v1 += r.y; }
+        if (e.residual) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.residual + gm * e.ld_res + n)); v0 += r.x; v1 += r.y; }
+        v0 *= e.scale; v1 *= e.scale;
+        if (e.round_tf32) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
+        *reinterpret_cast<float2*>(e.out + gm * e.ld_out + n) = make_float2(v0, v1);
+      }
+    }
+}
+
+template <int TAPS, int NB>
+int launch_lowc(const SimtConv& p, cudaStream_t st) {
+  constexpr int HALO = TAPS == 9 ? 1 : 0;
+  constexpr int smem = ((LC_TH + 2 * HALO) * (LC_TW + 2 * HALO) + TAPS * NB * 8) * LC_KC * (int)sizeof(float);
+  static bool configured = false;   // one attribute call per instantiation (same value every time: benign if raced)
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_lowc_kernel<TAPS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const long long tiles = (long long)p.nbatch * (p.H / LC_TH) * (p.W / LC_TW);
+  B200_REQUIRE(tiles > 0 && tiles < (1LL << 31), "conv_lowc: %lld tiles", tiles);
+  launch_kernel(conv_lowc_kernel<TAPS, NB>, dim3((unsigned)tiles), dim3(LC_THREADS), smem, st, p);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+bool aligned(const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; }
+
+}  // namespace
+
+bool conv_lowc_supported(const SimtConv& p) {
+  const bool geom = (p.R == 3 && p.S == 3 && p.pad == 1) || (p.R == 1 && p.S == 1 && p.pad == 0);
+  const long long ld1 = p.ld1 ? p.ld1 : p.C1, ld2 = p.ld2 ? p.ld2 : p.C2, wld = p.w_ld ? p.w_ld : p.C1 + p.C2;
+  return geom && p.stride == 1 && !p.in_nchw && p.in_scale == 1.f && p.in_shift == 0.f && p.OH == p.H && p.OW == p.W &&
+         p.H % LC_TH == 0 && p.W % LC_TW == 0 && p.C1 > 0 && p.C1 % LC_KC == 0 && p.C2 >= 0 && p.C2 % LC_KC == 0 &&
+         (p.N == 16 || p.N == 32 || p.N == 64) && p.a_batched && p.w_batch_stride == 0 && ld1 % 4 == 0 && ld2 % 4 == 0 &&
+         wld % 4 == 0 && !p.epi.out_nchw && !p.epi.per_img_div && (p.epi.round_tf32 == 0 || p.epi.round_tf32 == 1) &&
+         p.epi.ld_out % 2 == 0 && p.epi.ld_res % 2 == 0 && p.epi.rowvec_ld % 2 == 0;
+}
+
+int launch_conv_lowc(const SimtConv& p, cudaStream_t st) {
+  B200_REQUIRE(p.x1 && p.w && p.epi.out, "conv_lowc: null operand");
+  B200_REQUIRE(conv_lowc_supported(p), "conv_lowc: unsupported shape (C %d+%d -> %d, %dx%d, %dx%d filter)", p.C1, p.C2, p.N, p.H,
+               p.W, p.R, p.S);
+  B200_REQUIRE((p.x2 != nullptr) == (p.C2 > 0), "conv_lowc: second source / channel count mismatch");
+  B200_REQUIRE(aligned(p.x1, 16) && aligned(p.x2, 16) && aligned(p.w, 16) && aligned(p.epi.out, 8) && aligned(p.epi.residual, 8) &&
+               aligned(p.epi.bias, 8) && aligned(p.epi.rowvec, 8), "conv_lowc: operands must be 16-byte, epilogue terms 8-byte aligned");
+  if (p.R == 3) {
+    if (p.N == 16) return launch_lowc<9, 2>(p, st);
+    if (p.N == 32) return launch_lowc<9, 4>(p, st);
+    return launch_lowc<9, 8>(p, st);
+  }
+  if (p.N == 16) return launch_lowc<1, 2>(p, st);
+  if (p.N == 32) return launch_lowc<1, 4>(p, st);
+  return launch_lowc<1, 8>(p, st);
+}
+
+}  // namespace b200

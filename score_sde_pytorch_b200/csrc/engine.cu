@@ -414,7 +414,7 @@ struct Builder {
   void op(int launches, std::function<int(cudaStream_t)> f, int kind = 6, double flops = 0.0) {
     if (dry) return;
     e->launches += launches;
-    static const char* kind_names[] = {"tcgen05", "cuda-core contraction", "groupnorm", "fir", "softmax", "time embedding", "misc", "?"};
+    static const char* kind_names[] = {"tcgen05", "cuda-core contraction", "groupnorm", "fir", "softmax", "time embedding", "misc", "mma.sync contraction"};
     (lane ? e->ops2 : e->ops).push_back({kind, flops, std::move(f), next_name.empty() ? std::string(kind_names[kind & 7]) : next_name, next_bytes});
     next_name.clear(); next_bytes = 0.0;
   }
@@ -594,12 +594,17 @@ struct Builder {
       s.OH = a1.H; s.OW = a1.W; s.nbatch = B; s.a_batched = 1; s.w = e->W(pw); s.N = Cout;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
       s.epi = ep;
-      name("conv%s %d+%d->%d @%d [cuda-core]", taps == 9 ? "3x3" : "1x1", a1.C, a2.C, Cout, out.H);
+      // few-channel levels of the nf = 16 networks: warp-level TF32 MMAs keep them at the HBM roofline (conv_lowc.cu);
+      // strict-fp32 mode and every other shape stay on the CUDA-core kernel
+      const bool lowc = e->cfg.precision != 1 && !a1.f16 && !a2.f16 && sumC % 2 == 0 && conv_lowc_supported(s);
+      name("conv%s %d+%d->%d @%d [%s]", taps == 9 ? "3x3" : "1x1", a1.C, a2.C, Cout, out.H, lowc ? "mma.sync tf32" : "cuda-core");
+      next_bytes = (double)B * out.H * out.W * ((a1.C + a2.C) * 4.0 + Cout * 4.0 + (residual ? Cout * 4.0 : 0.0)) +
+                   (double)taps * (a1.C + a2.C) * Cout * 4.0;
       op(1, [=](cudaStream_t st) {
         SimtConv c = s;
         if (dense_row >= 0) c.epi.rowvec_ld = eng->uniform ? 0 : sumC;
-        return launch_conv_simt(c, st);
-      }, 1, cflops);
+        return lowc ? launch_conv_lowc(c, st) : launch_conv_simt(c, st);
+      }, lowc ? 7 : 1, cflops);
     }
   }
 

@@ -63,6 +63,12 @@ struct SimtConv {
 };
 int launch_conv_simt(const SimtConv& p, cudaStream_t st);
 
+// ---- conv_lowc.cu : few-channel stride-1 3x3 / 1x1 convolutions on warp-level TF32 MMAs (same descriptor) ----
+// Cin % 16 == 0, Cout in {16, 32, 64}, H % 8 == 0, W % 32 == 0, NHWC fp32 in and out; operands are rounded to the
+// TF32 grid while they are staged.  `conv_lowc_supported` looks at shapes and flags only (usable while planning).
+bool conv_lowc_supported(const SimtConv& p);
+int launch_conv_lowc(const SimtConv& p, cudaStream_t st);
+
 // ---- gemm_tc.cu : tcgen05 / TMEM / TMA implicit GEMM (TF32 operands) -------
 struct TcGemmPlan;   // opaque, owns the encoded tensor maps
 struct TcGemmDesc {

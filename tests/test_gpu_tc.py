@@ -66,6 +66,67 @@ def test_tcgen05_conv_matches_cuda_core_conv(dev, case):
   assert torch.equal(y2, rt(y))
 
 
+LOWC_CASES = [
+    dict(B=2, H=64, W=64, C1=16, C2=0, Cout=16, k=3),      # FFHQ level 0 shape (16 -> 16), 2 x 8 x 2 tiles
+    dict(B=1, H=32, W=96, C1=32, C2=0, Cout=32, k=3),
+    dict(B=2, H=16, W=32, C1=64, C2=0, Cout=64, k=3),      # four 16-channel slabs
+    dict(B=1, H=24, W=64, C1=48, C2=0, Cout=16, k=3),      # concat already materialised (48 channels)
+    dict(B=1, H=16, W=64, C1=128, C2=64, Cout=64, k=3),    # 192 channels from two sources
+    dict(B=2, H=32, W=32, C1=32, C2=16, Cout=16, k=1),     # two-source 1x1 skip projection
+    dict(B=1, H=8, W=32, C1=16, C2=16, Cout=32, k=1),      # a single tile
+    dict(B=1, H=40, W=160, C1=16, C2=0, Cout=64, k=3),
+]
+
+
+@pytest.mark.parametrize('case', LOWC_CASES, ids=lambda c: 'B{B}_{H}x{W}_{C1}+{C2}->{Cout}_k{k}'.format(**c))
+def test_few_channel_mma_conv_matches_cuda_core_conv(dev, case):
+  """conv_lowc.cu (impl 3: warp-level TF32 MMAs, the 16..64-channel levels of the nf=16 networks) against the strict-fp32
+  CUDA-core kernel.  On TF32-representable operands the products are exact, so only the summation order differs; on
+  arbitrary fp32 operands the kernel rounds them to the TF32 grid itself, i.e. equals impl 0 on pre-rounded operands."""
+  import gpu_util
+  B, H, W, C1, C2, Cout, k = (case[x] for x in ('B', 'H', 'W', 'C1', 'C2', 'Cout', 'k'))
+  torch.manual_seed(11)
+  rt = gpu_util.round_tf32
+  x1f = torch.randn(B, H, W, C1, device=dev)
+  x2f = torch.randn(B, H, W, C2, device=dev) if C2 else None
+  wf = torch.randn(Cout, C1 + C2, k, k, device=dev) / np.sqrt((C1 + C2) * k * k)
+  x1, x2, w = rt(x1f), (rt(x2f) if C2 else None), rt(wf)
+  bias = torch.randn(Cout, device=dev)
+  rowvec = torch.randn(B, Cout, device=dev)
+  res = torch.randn(B, H, W, Cout, device=dev)
+  wp = gpu_util.pack_conv_weight(w)
+  kw = dict(rowvec=rowvec, rowvec_ld=Cout, residual=res, scale=0.7071067690849304)
+  ref = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=0, **kw)
+  y = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=3, **kw)
+  torch.cuda.synchronize()
+  err = (y - ref).abs().max().item()
+  assert err < 2e-5 * max(1.0, ref.abs().max().item()), f'max abs err {err}'
+  xc = x1 if x2 is None else torch.cat([x1, x2], 3)
+  tref = (F.conv2d(xc.permute(0, 3, 1, 2), w, bias, padding=k // 2).permute(0, 2, 3, 1) + rowvec[:, None, None, :] + res) * 0.7071067690849304
+  assert torch.allclose(y, tref, rtol=2e-5, atol=2e-5)
+  # unrounded operands: the kernel's own rounding is cvt.rna, the same as round_tf32 -> same result as above, bit for bit
+  y_raw = gpu_util.conv_nhwc(x1f, x2f, gpu_util.pack_conv_weight(wf), bias, Cout, k, impl=3, **kw)
+  assert torch.equal(y_raw, y)
+  # plain epilogue (no bias / row vector / residual) and the TF32-grid store
+  y_plain = gpu_util.conv_nhwc(x1, x2, wp, None, Cout, k, impl=3)
+  ref_plain = gpu_util.conv_nhwc(x1, x2, wp, None, Cout, k, impl=0)
+  assert (y_plain - ref_plain).abs().max().item() < 2e-5 * max(1.0, ref_plain.abs().max().item())
+  y2 = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=3, round_out=True, **kw)
+  assert torch.equal(y2, rt(y))
+
+
+def test_few_channel_mma_conv_rejects_other_shapes(dev):
+  import gpu_util
+  x = torch.randn(1, 8, 32, 24, device=dev)      # 24 channels: not a multiple of 16
+  w = gpu_util.pack_conv_weight(torch.randn(16, 24, 3, 3, device=dev))
+  with pytest.raises(RuntimeError, match='conv_lowc'):
+    gpu_util.conv_nhwc(x, None, w, None, 16, 3, impl=3)
+  x = torch.randn(1, 8, 16, 16, device=dev)      # 16 pixels wide: no 32-pixel tile
+  w = gpu_util.pack_conv_weight(torch.randn(16, 16, 3, 3, device=dev))
+  with pytest.raises(RuntimeError, match='conv_lowc'):
+    gpu_util.conv_nhwc(x, None, w, None, 16, 3, impl=3)
+
+
 F16_CASES = [c for c in CASES if c['C1'] % 64 == 0 and c['C2'] % 64 == 0]
 
 
