@@ -14,7 +14,8 @@
 //     are *defined* as (t -> 4t+2s, t+4 -> 4t+2s+1) for k8 step s.  The sum over k does not care about the order as
 //     long as A and B agree, so one LDS.128 feeds two MMAs and no shared-memory padding is needed (a quarter warp
 //     reads 32 consecutive words);
-//   * two CTAs per SM (<= 58 KB shared, <= 128 registers) overlap one tile's staging with the other's MMAs.
+//   * two persistent CTAs per SM (<= 81 KB shared, <= 128 registers); the next 16-channel input slab arrives by
+//     cp.async while the current one is multiplied.
 // The epilogue is conv_simt's: + bias + per-image row vector + residual, * scale, optional TF32-grid store.
 #include "kernels.h"
 
@@ -36,24 +37,64 @@ __device__ __forceinline__ float4 round4_tf32(float4 v) {
   return v;
 }
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;           // src-size 0: the 16 destination bytes are zero-filled (the padding ring)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Persistent CTAs: a CTA walks (tile, 16-channel slab) work items.  The input slab of item i+1 is in flight (cp.async into
+// the other buffer) while item i's MMAs run; a thread rounds the 16-byte pieces it copied itself to the TF32 grid in place
+// before the barrier that publishes the buffer.  Single-slab layers (Cin = 16) load their weights once per CTA; the
+// others re-stage the [tap][Cout][16] weight slab of each item from L2.
 template <int TAPS, int NB>
-__global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv p) {
+__global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv p, int num_tiles) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PH = LC_TH + 2 * HALO, PW = LC_TW + 2 * HALO;
   constexpr int N = NB * 8;
+  constexpr int A_PIECES = PH * PW * 4;                                   // 16-byte pieces of one input slab
+  constexpr int A_ITERS = (A_PIECES + LC_THREADS - 1) / LC_THREADS;
+  constexpr int B_PIECES = TAPS * N * 4;
   extern __shared__ __align__(16) float lc_smem[];
-  float* sA = lc_smem;                        // [PH][PW][16]   input slab with halo, TF32 grid
-  float* sB = lc_smem + PH * PW * LC_KC;      // [TAPS][N][16]  weight slab, TF32 grid
+  float* sA0 = lc_smem;                         // 2 x [PH][PW][16]  input slab with halo
+  float* sB = lc_smem + 2 * PH * PW * LC_KC;    // [TAPS][N][16]     weight slab, TF32 grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int tiles_x = p.W / LC_TW, tiles_y = p.H / LC_TH;
-  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, img = blockIdx.x / (tiles_x * tiles_y);
-  const int x0 = tx * LC_TW, y0 = ty * LC_TH;
-  const int Cin = p.C1 + p.C2;
+  const int Cin = p.C1 + p.C2, slabs = Cin / LC_KC;
   const long long ld1 = p.ld1 ? p.ld1 : p.C1, ld2 = p.ld2 ? p.ld2 : p.C2, wld = p.w_ld ? p.w_ld : Cin;
-  const float* a1 = p.x1 + (long long)img * p.H * p.W * ld1;
-  const float* a2 = p.x2 ? p.x2 + (long long)img * p.H * p.W * ld2 : nullptr;
+  const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long items = my_tiles * slabs;
+
+  auto stage_weights = [&](int c0) {
+    for (int e = tid; e < B_PIECES; e += LC_THREADS) {
+      const int q = e & 3, row = e >> 2;      // row = tap * N + n of the packed [tap][N][Cin] weights
+      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (long long)row * wld + c0 + 4 * q)));
+      *reinterpret_cast<float4*>(sB + row * LC_KC + 4 * q) = v;
+    }
+  };
+  // issue the copies of work item `it` into buffer it & 1
+  auto issue = [&](long long it) {
+    const int tile = blockIdx.x + (int)(it / slabs) * gridDim.x, c0 = (int)(it % slabs) * LC_KC;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
+    const float* src = c0 < p.C1 ? p.x1 + (long long)img * p.H * p.W * ld1 + c0 : p.x2 + (long long)img * p.H * p.W * ld2 + (c0 - p.C1);
+    const long long ld = c0 < p.C1 ? ld1 : ld2;
+    float* dst = sA0 + (it & 1) * (PH * PW * LC_KC);
+#pragma unroll
+    for (int k = 0; k < A_ITERS; ++k) {
+      const int e = tid + k * LC_THREADS;
+      if (e < A_PIECES) {
+        const int q = e & 3, pix = e >> 2, py = pix / PW, px = pix - py * PW;
+        const int iy = ty * LC_TH + py - HALO, ix = tx * LC_TW + px - HALO;
+        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        cp_async16(dst + pix * LC_KC + 4 * q, ok ? src + ((long long)iy * p.W + ix) * ld + 4 * q : src, ok);
+      }
+    }
+    cp_async_commit();
+  };
 
   float acc[2][NB][4];
 #pragma unroll
@@ -63,23 +104,21 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mb][nb][i] = 0.f;
 
-  for (int c0 = 0; c0 < Cin; c0 += LC_KC) {
-    const float* src = c0 < p.C1 ? a1 + c0 : a2 + (c0 - p.C1);
-    const long long ld = c0 < p.C1 ? ld1 : ld2;
-    __syncthreads();                          // the previous slab's fragment loads are done
-    for (int e = tid; e < PH * PW * 4; e += LC_THREADS) {
-      const int q = e & 3, pix = e >> 2, py = pix / PW, px = pix - py * PW;
-      const int iy = y0 + py - HALO, ix = x0 + px - HALO;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-        v = round4_tf32(__ldg(reinterpret_cast<const float4*>(src + ((long long)iy * p.W + ix) * ld + 4 * q)));
-      *reinterpret_cast<float4*>(sA + pix * LC_KC + 4 * q) = v;
+  if (items > 0) issue(0);
+  if (slabs == 1) stage_weights(0);
+  for (long long it = 0; it < items; ++it) {
+    if (it + 1 < items) { issue(it + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    float* sA = sA0 + (it & 1) * (PH * PW * LC_KC);
+#pragma unroll
+    for (int k = 0; k < A_ITERS; ++k) {          // round this thread's own pieces of item `it`
+      const int e = tid + k * LC_THREADS;
+      if (e < A_PIECES) {
+        float4* q4 = reinterpret_cast<float4*>(sA + (e >> 2) * LC_KC + 4 * (e & 3));
+        *q4 = round4_tf32(*q4);
+      }
     }
-    for (int e = tid; e < TAPS * N * 4; e += LC_THREADS) {
-      const int q = e & 3, row = e >> 2;      // row = tap * N + n of the packed [tap][N][Cin] weights
-      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (long long)row * wld + c0 + 4 * q)));
-      *reinterpret_cast<float4*>(sB + row * LC_KC + 4 * q) = v;
-    }
+    const int slab = (int)(it % slabs);
+    if (slabs > 1) stage_weights(slab * LC_KC);   // (the barrier that closed the previous item freed sB)
     __syncthreads();
 
 #pragma unroll
@@ -101,43 +140,56 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
         }
       }
     }
-  }
+    __syncthreads();                              // buffer it & 1 and sB may be overwritten from here on
 
-  // ---- epilogue: lane (g, t) holds pixels g / g+8 of each m16 block and output channels 2t, 2t+1 of each n8 block ----
-  const Epilogue& e = p.epi;
-  const int oy = y0 + warp;
+    if (slab == slabs - 1) {
+      // ---- epilogue: lane (g, t) holds pixels g / g+8 of each m16 block and output channels 2t, 2t+1 of each n8 block ----
+      const int tile = blockIdx.x + (int)(it / slabs) * gridDim.x;
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
+      const Epilogue& e = p.epi;
+      const int oy = ty * LC_TH + warp;
 #pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
+      for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ox = x0 + mb * 16 + g + 8 * h;
-      const long long gm = ((long long)img * p.H + oy) * p.W + ox;
+        for (int h = 0; h < 2; ++h) {
+          const int ox = tx * LC_TW + mb * 16 + g + 8 * h;
+          const long long gm = ((long long)img * p.H + oy) * p.W + ox;
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const int n = nb * 8 + 2 * t;
-        float v0 = acc[mb][nb][2 * h], v1 = acc[mb][nb][2 * h + 1];
-        if (e.bias) { const float2 b = __ldg(reinterpret_cast<const float2*>(e.bias + n)); v0 += b.x; v1 += b.y; }
-        if (e.rowvec) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.rowvec + img * e.rowvec_ld + n)); v0 += r.x; v1 += r.y; }
-        if (e.residual) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.residual + gm * e.ld_res + n)); v0 += r.x; v1 += r.y; }
-        v0 *= e.scale; v1 *= e.scale;
-        if (e.round_tf32) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
-        *reinterpret_cast<float2*>(e.out + gm * e.ld_out + n) = make_float2(v0, v1);
-      }
+          for (int nb = 0; nb < NB; ++nb) {
+            const int n = nb * 8 + 2 * t;
+            float v0 = acc[mb][nb][2 * h], v1 = acc[mb][nb][2 * h + 1];
+            acc[mb][nb][2 * h] = 0.f; acc[mb][nb][2 * h + 1] = 0.f;
+            if (e.bias) { const float2 b = __ldg(reinterpret_cast<const float2*>(e.bias + n)); v0 += b.x; v1 += b.y; }
+            if (e.rowvec) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.rowvec + img * e.rowvec_ld + n)); v0 += r.x; v1 += r.y; }
+            if (e.residual) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.residual + gm * e.ld_res + n)); v0 += r.x; v1 += r.y; }
+            v0 *= e.scale; v1 *= e.scale;
+            if (e.round_tf32) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
+            *reinterpret_cast<float2*>(e.out + gm * e.ld_out + n) = make_float2(v0, v1);
+          }
+        }
     }
+  }
+}
+
+int lc_num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
 }
 
 template <int TAPS, int NB>
 int launch_lowc(const SimtConv& p, cudaStream_t st) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
-  constexpr int smem = ((LC_TH + 2 * HALO) * (LC_TW + 2 * HALO) + TAPS * NB * 8) * LC_KC * (int)sizeof(float);
+  constexpr int smem = (2 * (LC_TH + 2 * HALO) * (LC_TW + 2 * HALO) + TAPS * NB * 8) * LC_KC * (int)sizeof(float);
   static bool configured = false;   // one attribute call per instantiation (same value every time: benign if raced)
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(conv_lowc_kernel<TAPS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const long long tiles = (long long)p.nbatch * (p.H / LC_TH) * (p.W / LC_TW);
-  B200_REQUIRE(tiles > 0 && tiles < (1LL << 31), "conv_lowc: %lld tiles", tiles);
-  launch_kernel(conv_lowc_kernel<TAPS, NB>, dim3((unsigned)tiles), dim3(LC_THREADS), smem, st, p);
+  B200_REQUIRE(tiles > 0 && tiles < (1LL << 30), "conv_lowc: %lld tiles", tiles);
+  const int grid = (int)std::min<long long>(tiles, 2LL * lc_num_sms());
+  launch_kernel(conv_lowc_kernel<TAPS, NB>, dim3(grid), dim3(LC_THREADS), smem, st, p, (int)tiles);
   B200_CHECK_LAUNCH();
   return 0;
 }

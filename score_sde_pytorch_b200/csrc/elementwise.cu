@@ -90,7 +90,7 @@ int launch_gn_quad_stats(const float* x, int C, int B, int HW, double* qsums, cu
   B200_REQUIRE(smem <= 48 * 1024, "gn_quad_stats: C=%d too large", C);
   // few, large images (high-resolution networks at small batch): several CTAs per image, accumulating into zeroed sums
   int splits = 1;
-  if (qsums_zeroed && B < 296 && HW >= 4096) splits = (int)std::min<long long>(std::min<long long>(64, HW / 1024), (296 + B - 1) / B);
+  if (qsums_zeroed && B < 296 && HW >= 4096) splits = (int)std::min<long long>(std::min<long long>(512, HW / 1024), (592 + B - 1) / B);
   launch_kernel(gn_quad_stats_kernel, dim3(B, splits), dim3(GN_THREADS), smem, st, x, C, HW, qsums);
   B200_CHECK_LAUNCH();
   return 0;
@@ -320,7 +320,9 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
   // aim for ~16 float4 per thread (four 4-deep batches), at least one block per image
   const long long per_img_units = (long long)HW * Q;
   const int work = 16;
-  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / ((long long)threads * work), 64));
+  // (few, very large images - the 1024-pixel family at batch 2 - need more than 64 CTAs per image to fill the chip)
+  const long long max_splits = std::max<long long>(64, (148LL * 16 + B - 1) / B);
+  int splits = (int)std::max<long long>(1, std::min<long long>(per_img_units / ((long long)threads * work), max_splits));
   splits = std::min(splits, HW);
   dim3 grid(splits, B);
   B200_REQUIRE(!x1_f16 || C2 == 0, "gn_apply: fp16 input is single-source");
@@ -344,14 +346,20 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
 // path): such groups straddle the aligned channel quads the fused statistics are kept in.  These rare layers take a plain
 // two-kernel path: per-(image, group) mean / rstd in fp64, then an elementwise apply over the (two-source) tensor.
 __global__ void __launch_bounds__(256) gn_generic_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-                                                               int HW, int G, float eps, float2* __restrict__ mr) {
+                                                               int HW, int G, double* __restrict__ part) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
-  const int C = C1 + C2, cpg = C / G, g = blockIdx.x, b = blockIdx.y;
+  // grid (group, image, pixel split): each CTA reduces its pixel range of one group to one (sum, sum of squares) pair
+  const int C = C1 + C2, cpg = C / G, g = blockIdx.x, b = blockIdx.y, S = gridDim.z;
+  const int per = (HW + S - 1) / S, p0 = blockIdx.z * per, p1 = min(HW, p0 + per);
   double s = 0.0, ss = 0.0;
-  for (long long i = threadIdx.x; i < (long long)HW * cpg; i += blockDim.x) {
-    const int pix = (int)(i / cpg), c = g * cpg + (int)(i % cpg);
-    const float v = c < C1 ? x1[((long long)b * HW + pix) * C1 + c] : x2[((long long)b * HW + pix) * C2 + (c - C1)];
-    s += v; ss += (double)v * v;
+  for (int pix = p0 + threadIdx.x; pix < p1; pix += blockDim.x) {
+    float fs = 0.f, fq = 0.f;                  // <= a few dozen channels per pixel: fp32 inside the pixel, fp64 across pixels
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const float v = c < C1 ? __ldg(x1 + ((long long)b * HW + pix) * C1 + c) : __ldg(x2 + ((long long)b * HW + pix) * C2 + (c - C1));
+      fs += v; fq = fmaf(v, v, fq);
+    }
+    s += fs; ss += fq;
   }
   __shared__ double sh[2][8];
   s = warp_sum_d(s); ss = warp_sum_d(ss);
@@ -360,10 +368,20 @@ __global__ void __launch_bounds__(256) gn_generic_stats_kernel(const float* __re
   if (threadIdx.x == 0) {
     double a = 0.0, q = 0.0;
     for (int w = 0; w < 8; ++w) { a += sh[0][w]; q += sh[1][w]; }
-    const double n = (double)HW * cpg, mean = a / n;
-    const float var = fmaxf((float)(q / n - mean * mean), 0.f);
-    mr[(long long)b * G + g] = make_float2((float)mean, rsqrtf(var + eps));
+    double* dst = part + (((long long)b * G + g) * S + blockIdx.z) * 2;
+    dst[0] = a; dst[1] = q;
   }
+}
+// one thread per (image, group): fold the pixel-split partials (fixed order: deterministic) into mean / rstd
+__global__ void gn_generic_finish_kernel(const double* __restrict__ part, int BG, int S, double n, float eps, float2* __restrict__ mr) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BG) return;
+  double a = 0.0, q = 0.0;
+  for (int k = 0; k < S; ++k) { a += part[((long long)i * S + k) * 2]; q += part[((long long)i * S + k) * 2 + 1]; }
+  const double mean = a / n;
+  const float var = fmaxf((float)(q / n - mean * mean), 0.f);
+  mr[i] = make_float2((float)mean, rsqrtf(var + eps));
 }
 __global__ void __launch_bounds__(256) gn_generic_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                                                const float2* __restrict__ mr, const float* __restrict__ gamma,
@@ -384,14 +402,24 @@ __global__ void __launch_bounds__(256) gn_generic_apply_kernel(const float* __re
     if (raw) store_operand1(raw, i, v, round_out);
   }
 }
+// pixel splits of the statistics pass, and the workspace (in floats) the two-kernel path needs:
+// [B*G] float2 mean/rstd, then [B*G][splits] (sum, sum of squares) fp64 partials
+static int gn_generic_splits(int HW) { return (int)std::max(1, std::min(64, HW / 1024)); }
+long long gn_generic_workspace_floats(int B, int HW, int G) { return 2LL * B * G + 4LL * B * G * gn_generic_splits(HW); }
+
 int launch_gn_generic(const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, int B, int HW, int G,
                       float eps, int act, int round_out, float* y, float* raw, float* mr_ws, cudaStream_t st) {
   const int C = C1 + C2;
   B200_REQUIRE(C % G == 0 && mr_ws, "gn_generic: C=%d G=%d", C, G);
-  launch_kernel(gn_generic_stats_kernel, dim3(dim3(G, B)), dim3(256), 0, st, x1, C1, x2, C2, HW, G, eps, reinterpret_cast<float2*>(mr_ws));
+  const int S = gn_generic_splits(HW);
+  float2* mr = reinterpret_cast<float2*>(mr_ws);
+  double* part = reinterpret_cast<double*>(mr_ws + 2LL * B * G);
+  launch_kernel(gn_generic_stats_kernel, dim3(G, B, S), dim3(256), 0, st, x1, C1, x2, C2, HW, G, part);
+  launch_kernel(gn_generic_finish_kernel, dim3((B * G + 127) / 128), dim3(128), 0, st, (const double*)part, B * G, S,
+                (double)HW * (C / G), eps, mr);
   const long long total = (long long)B * HW * C;
   const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-  launch_kernel(gn_generic_apply_kernel, dim3(grid), dim3(256), 0, st, x1, C1, x2, C2, reinterpret_cast<const float2*>(mr_ws), gamma, beta, B, HW, G, act, round_out, y, raw);
+  launch_kernel(gn_generic_apply_kernel, dim3(grid), dim3(256), 0, st, x1, C1, x2, C2, (const float2*)mr, gamma, beta, B, HW, G, act, round_out, y, raw);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -1022,19 +1050,20 @@ int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin,
 // (reads the activation once through L1, 9x tap reuse between neighbouring threads); the 9*N*C
 // weights sit in shared memory and are read as broadcast float4s.
 // ============================================================================
-template <int N>
+template <int N, int LPP>
 __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w /* [9][N][C] */,
                                                              const float* __restrict__ bias, const float* __restrict__ div,
                                                              long long div_stride, float* __restrict__ out_nchw,
                                                              int B, int H, int W, int C, int x_f16,
                                                              const float* __restrict__ add_nchw) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
-  // Eight lanes share one output pixel: lane `part` takes the float4s part, part+8, ... of the pixel's channel
+  // LPP (eight; two for <= 32 channels, whose pixel vector is only 4 - 8 float4s) lanes share one output pixel: lane
+  // `part` takes the float4s part, part+LPP, ... of the pixel's channel
   // vector, so a warp-wide 128-bit load covers 4 pixels x 128 contiguous bytes (4 cache lines per instruction
   // instead of 32 with one pixel per lane, which was L1-wavefront bound); the partial dot products are folded with
   // three shuffles per output channel.
   extern __shared__ float sw[];   // [9][N][C]
-  if (x_f16) {
+  if (x_f16 && LPP == 8) {
     // fp16 input: lane `part` owns 8 consecutive channels per 64-channel block.  Its two weight float4s are stored
     // so that the eight lanes of a pixel read 128 contiguous bytes per LDS.128 (conflict-free), i.e. within a block
     // channel c = 8*part + 4*k + e sits at float ((2*blk + k)*8 + part)*4 + e.
@@ -1047,8 +1076,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
   }
   __syncthreads();
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long pg = gt >> 3;
-  const int part = (int)(gt & 7);
+  const long long pg = gt / LPP;
+  const int part = (int)(gt & (LPP - 1));
   const bool live = pg < (long long)B * H * W;
   const long long pgc = live ? pg : 0;
   const int px = (int)(pgc % W), py = (int)((pgc / W) % H), b = (int)(pgc / ((long long)W * H));
@@ -1057,7 +1086,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
   for (int n = 0; n < N; ++n) acc[n] = 0.f;
   const float* xb = x + (long long)b * H * W * C;
   const int nq = C >> 2;                                  // float4s per pixel
-  if (x_f16) {
+  if (x_f16 && LPP == 8) {
     // fp16 activations (operand mode 2): a lane's 128-bit load carries 8 channels, half the L1/L2 bytes of the
     // nine-fold tap re-reads that bound this kernel
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(x) + (long long)b * H * W * C;
@@ -1096,16 +1125,16 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
     if (!live || iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
     const float4* src = reinterpret_cast<const float4*>(xb + ((long long)iy * W + ix) * C);
     const float4* wt = reinterpret_cast<const float4*>(sw + tap * N * C);
-    for (int c4 = part; c4 < nq; c4 += 32) {               // up to four 128-bit loads in flight
+    for (int c4 = part; c4 < nq; c4 += 4 * LPP) {          // up to four 128-bit loads in flight
       float4 a[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = (c4 + 8 * u < nq) ? __ldg(src + c4 + 8 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) a[u] = (c4 + LPP * u < nq) ? __ldg(src + c4 + LPP * u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (c4 + 8 * u >= nq) break;
+        if (c4 + LPP * u >= nq) break;
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-          const float4 ww = wt[n * nq + c4 + 8 * u];
+          const float4 ww = wt[n * nq + c4 + LPP * u];
           acc[n] = fmaf(a[u].x, ww.x, fmaf(a[u].y, ww.y, fmaf(a[u].z, ww.z, fmaf(a[u].w, ww.w, acc[n]))));
         }
       }
@@ -1113,9 +1142,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const float* __res
   }
 #pragma unroll
   for (int n = 0; n < N; ++n) {
-    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
-    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
-    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+#pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
   }
   if (live && part == 0) {
     const float dv = div ? __ldg(div + b * div_stride) : 1.f;
@@ -1135,13 +1163,15 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
   B200_REQUIRE(N >= 1 && N <= 4 && C % (x_f16 ? 64 : 4) == 0, "conv3x3_small_n: N=%d C=%d unsupported", N, C);
   const size_t smem = (size_t)9 * N * C * sizeof(float);
   B200_REQUIRE(smem <= 96 * 1024, "conv3x3_small_n: weights (%zu B) exceed shared memory", smem);
-  const long long total = (long long)B * H * W * 8;      // eight lanes per output pixel
+  const bool two = !x_f16 && C <= 32;                     // lanes per output pixel: 2 for short channel vectors, else 8
+  const long long total = (long long)B * H * W * (two ? 2 : 8);
   const unsigned blocks = (unsigned)((total + 255) / 256);
 #define B200_LAUNCH_SMALLN(NN)                                                                                      \
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
-      B200_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_n_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    launch_kernel(conv3x3_small_n_kernel<NN>, dim3(blocks), dim3(256), smem, st, x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16, add_nchw); \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_n_kernel<NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    if (two) launch_kernel(conv3x3_small_n_kernel<NN, 2>, dim3(blocks), dim3(256), smem, st, x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16, add_nchw); \
+    else launch_kernel(conv3x3_small_n_kernel<NN, 8>, dim3(blocks), dim3(256), smem, st, x, w, bias, div, div_stride, out_nchw, B, H, W, C, x_f16, add_nchw); \
   } while (0)
   switch (N) {
     case 1: B200_LAUNCH_SMALLN(1); break;
@@ -1155,34 +1185,44 @@ int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, co
 }
 
 // ============================================================================
-// Attention core for small token counts (T = H*W <= 64, e.g. the 4x4 bottleneck block): one CTA per image keeps
-// q, k, v [T, C] in shared memory, forms logits = q k^T * C^-1/2 (layerspp.py:82), softmax over keys (:83-85),
-// and h = P v (:86).  qkv is the [B*T, 3C] output of the fused projection (bias included).
+// Attention core for small token counts (T = H*W <= 64, e.g. the 4x4 bottleneck block, or the 8x8, 512-channel one of
+// FFHQ-1024): one CTA per image forms logits = q k^T * C^-1/2 (layerspp.py:82), softmax over keys (:83-85) and
+// h = P v (:86).  qkv is the [B*T, 3C] output of the fused projection (bias included).  q and k are staged in shared
+// memory one slab of Cc channels at a time (Cc = C when everything fits: one slab, the original single-pass order);
+// the logits accumulate across slabs; v is read through L2 in the last phase (each element once per CTA).
 // ============================================================================
 __global__ void __launch_bounds__(256) attn_small_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                        int T, int C, float scale, int round_out) {
+                                                        int T, int C, int Cc, float scale, int round_out) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
-  extern __shared__ float sm[];            // q[T][C] k[T][C] v[T][C] p[T][T]
-  float* sq = sm; float* sk = sq + T * C; float* sv = sk + T * C; float* sp = sv + T * C;
-  const int b = blockIdx.x;
+  extern __shared__ float sm[];            // q[TQ][Cc] (room for T rows) k[T][Cc] p[TQ][T]
+  float* sq = sm; float* sk = sq + T * Cc; float* sp = sk + T * Cc;
+  // grid (image, query-row block): few images (the batch-2 1024-pixel network) are split over row blocks so that more
+  // than `images` SMs work; every output element is computed by the same instruction sequence whatever the split
+  const int b = blockIdx.x, TQ = T / gridDim.y, r0 = blockIdx.y * TQ;
   const float* src = qkv + (long long)b * T * 3 * C;
-  for (int i = threadIdx.x; i < T * C / 4; i += blockDim.x) {
-    const int t = i / (C / 4), c = (i % (C / 4)) * 4;
-    *reinterpret_cast<float4*>(sq + t * C + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + c));
-    *reinterpret_cast<float4*>(sk + t * C + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + C + c));
-    *reinterpret_cast<float4*>(sv + t * C + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + 2 * C + c));
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int e = warp; e < T * T; e += nw) {          // one warp per logit
-    const int i = e / T, j = e % T;
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(sq[i * C + c], sk[j * C + c], a);
-    a = warp_sum(a);
-    if (lane == 0) sp[e] = a * scale;
+  for (int c0 = 0; c0 < C; c0 += Cc) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * Cc / 4; i += blockDim.x) {
+      const int t = i / (Cc / 4), c = (i % (Cc / 4)) * 4;
+      if (t < TQ) *reinterpret_cast<float4*>(sq + t * Cc + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)(r0 + t) * 3 * C + c0 + c));
+      *reinterpret_cast<float4*>(sk + t * Cc + c) = __ldg(reinterpret_cast<const float4*>(src + (long long)t * 3 * C + C + c0 + c));
+    }
+    __syncthreads();
+    const bool first = c0 == 0, last = c0 + Cc >= C;
+    for (int e = warp; e < TQ * T; e += nw) {         // one warp per logit
+      const int i = e / T, j = e % T;
+      float a = 0.f;
+      for (int c = lane; c < Cc; c += 32) a = fmaf(sq[i * Cc + c], sk[j * Cc + c], a);
+      a = warp_sum(a);
+      if (lane == 0) {
+        const float acc = first ? a : sp[e] + a;
+        sp[e] = last ? acc * scale : acc;
+      }
+    }
   }
   __syncthreads();
-  for (int i = warp; i < T; i += nw) {              // softmax of row i
+  for (int i = warp; i < TQ; i += nw) {             // softmax of row i
     float mx = -INFINITY;
     for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sp[i * T + j]);
     mx = warp_max(mx);
@@ -1192,18 +1232,31 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const float* __restrict
     for (int j = lane; j < T; j += 32) sp[i * T + j] = sp[i * T + j] / sum;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+  const float* sv = src + 2 * C;                    // v[j][c] at sv[j * 3C + c]
+  for (int i = threadIdx.x; i < TQ * C; i += blockDim.x) {
     const int t = i / C, c = i % C;
     float a = 0.f;
-    for (int j = 0; j < T; ++j) a = fmaf(sp[t * T + j], sv[j * C + c], a);
-    store_operand1(out, ((long long)b * T + t) * C + c, a, round_out);
+    for (int j = 0; j < T; ++j) a = fmaf(sp[t * T + j], __ldg(sv + (long long)j * 3 * C + c), a);
+    store_operand1(out, ((long long)b * T + r0 + t) * C + c, a, round_out);
   }
+}
+
+// channels per staged slab: the largest C / 2^k (a multiple of 4) whose q, k slabs and the logits fit 160 KB
+static int attn_small_slab(int T, int C) {
+  int Cc = C;
+  while (Cc % 8 == 0 && ((size_t)2 * T * Cc + (size_t)T * T) * sizeof(float) > 160 * 1024) Cc /= 2;
+  return Cc;
+}
+bool attn_small_supported(int T, int C) {
+  if (T < 1 || T > 64 || C < 4 || C % 4 != 0) return false;
+  const int Cc = attn_small_slab(T, C);
+  return C % Cc == 0 && ((size_t)2 * T * Cc + (size_t)T * T) * sizeof(float) <= 160 * 1024;
 }
 
 // called at plan time (outside any stream capture): opt in to > 48 KB of dynamic shared memory
 int launch_attn_small_configure(int T, int C) {
-  const size_t smem = ((size_t)3 * T * C + (size_t)T * T) * sizeof(float);
-  B200_REQUIRE(T <= 64 && C % 4 == 0 && smem <= 200 * 1024, "attn_small: T=%d C=%d unsupported", T, C);
+  B200_REQUIRE(attn_small_supported(T, C), "attn_small: T=%d C=%d unsupported", T, C);
+  const size_t smem = ((size_t)2 * T * attn_small_slab(T, C) + (size_t)T * T) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1213,8 +1266,12 @@ int launch_attn_small_configure(int T, int C) {
 }
 
 int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st) {
-  const size_t smem = ((size_t)3 * T * C + (size_t)T * T) * sizeof(float);
-  launch_kernel(attn_small_kernel, dim3(B), dim3(256), smem, st, qkv, out, T, C, scale, round_out);
+  B200_REQUIRE(attn_small_supported(T, C), "attn_small: T=%d C=%d unsupported", T, C);
+  const int Cc = attn_small_slab(T, C);
+  const size_t smem = ((size_t)2 * T * Cc + (size_t)T * T) * sizeof(float);
+  int TQ = T;                                       // query rows per CTA
+  if (B < 32 && T % 4 == 0) TQ = 4; else if (B < 128 && T % 8 == 0) TQ = 8;
+  launch_kernel(attn_small_kernel, dim3(B, T / TQ), dim3(256), smem, st, qkv, out, T, C, Cc, scale, round_out);
   B200_CHECK_LAUNCH();
   return 0;
 }

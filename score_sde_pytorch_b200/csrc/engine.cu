@@ -256,9 +256,9 @@ int build_graph(b200_ncsnpp* e) {
     m.tcattn = tcmode && (C % 128 == 0) && (T % 128 == 0) && (T <= 1024);
     // fp16 operands: the logits/probabilities never leave the chip, so only the fused core is implemented
     if (om == 2 && !tc_attn_supported(T, C)) m.tcattn = false;
-    // few tokens: q, k, v and the logits of one image fit one CTA's shared memory (attn_small_kernel); otherwise (e.g. the
-    // 8x8, 512-channel bottleneck of FFHQ-1024) the block runs as separate contractions on CUDA cores
-    const bool small_ok = T <= 64 && ((size_t)3 * T * C + (size_t)T * T) * sizeof(float) <= 200 * 1024;
+    // few tokens (T <= 64: the 4x4 block of CIFAR-10, the 8x8, 512-channel bottleneck of FFHQ-1024): one CTA per image
+    // (attn_small_kernel); otherwise the block runs as separate contractions
+    const bool small_ok = attn_small_supported(T, C);
     m.tc0 = tcmode && (C % 128 == 0) && (m.tcattn || small_ok);   // q/k/v projections on tensor cores
     m.gn0w = add_param(e, nm("GroupNorm_0.weight"), {C}, PK_COPY, 0, 0, 0, 0);
     m.gn0b = add_param(e, nm("GroupNorm_0.bias"), {C}, PK_COPY, 0, 0, 0, 0);
@@ -281,7 +281,9 @@ int build_graph(b200_ncsnpp* e) {
   { Mod m; m.kind = M_CONV_IN; m.index = cur(); m.cin1 = ch; m.cout = nf; m.res = c.image_size;
     // on tensor cores the 3x3 input conv is one K=32 contraction over im2col patches: weights packed [nf][32]
     m.tc0 = tcmode && (9 * ch <= 32) && (nf % 128 == 0);
-    m.w = m.tc0 ? add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV_FLAT32, 9, nf, ch, om, -1, (long long)nf * 32)
+    // nf = 16 / 32 / 64 (the high-resolution family) in TF32 mode: the same patches, contracted by the few-channel kernel
+    m.tc1 = !m.tc0 && c.precision == 0 && (9 * ch <= 32) && (nf == 16 || nf == 32 || nf == 64) && c.image_size % 32 == 0;
+    m.w = (m.tc0 || m.tc1) ? add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV_FLAT32, 9, nf, ch, om, -1, (long long)nf * 32)
                 : add_param(e, nm("weight"), {nf, ch, 3, 3}, PK_CONV, 9, nf, ch, 0);
     m.b = add_param(e, nm("bias"), {nf}, PK_COPY, 0, 0, 0, 0); e->mods.push_back(m); }
   std::vector<int> hs_c = {nf};
@@ -432,11 +434,11 @@ struct Builder {
     if ((C / G) % 4 != 0) {
       // groups that are not whole channel quads (C = 192 -> 6 channels per group): the generic two-kernel path
       if (x1.f16 || x2.f16) { set_error("ncsnpp: GroupNorm with %d-channel groups on an fp16 tensor", C / G); rc = 2; return; }
-      long long mb; float* mr = falloc(2LL * B * G, &mb);
+      long long mb; float* mr = falloc(gn_generic_workspace_floats(B, HW, G), &mb);
       const float *g = e->W(pgw), *bt = e->W(pgb);
       const Tensor a = x1, b = x2; const int Bc = B;
       name("gn_generic %d+%d @%d (%d-channel groups)", x1.C, x2.C, x1.H, C / G);
-      op(2, [=](cudaStream_t st) { return launch_gn_generic(a.p, a.C, b.p, b.C, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, mr, st); }, 2);
+      op(3, [=](cudaStream_t st) { return launch_gn_generic(a.p, a.C, b.p, b.C, g, bt, Bc, HW, G, 1e-6f, act, round, y.p, raw, mr, st); }, 2);
       ffree(mr, mb);
       return;
     }
@@ -849,14 +851,15 @@ struct Builder {
     {
       const Mod& m = e->mods[mi++];
       Tensor h0 = talloc(nf, R, R);
-      if (m.tc0) {
-        // im2col patches [B*R*R][32] (TF32 grid) then one K=32 tcgen05 contraction with the flat-packed weights
+      if (m.tc0 || m.tc1) {
+        // im2col patches [B*R*R][32] (TF32 grid) then one K=32 contraction with the flat-packed weights (tcgen05, or the
+        // few-channel kernel for nf <= 64)
         long long pb; float* patches = falloc((long long)B * R * R * 32, &pb);   // 128 B per pixel: 32 fp32 or 64 fp16
         const int Bc = B, omc = om;
         name("im2col 3x3 %d @%d", ch, R);
         op(1, [=](cudaStream_t st) { return launch_im2col3x3_nchw(xc, patches, Bc, ch, R, R, R, R, 1, 1, omc, st); }, 6);
         Tensor pt; pt.p = patches; pt.C = om == 2 ? 64 : 32; pt.H = R; pt.W = R;   // patches as a one-K-step NHWC image: a 1x1 conv
-        conv(true, pt, Tensor(), 1, m.w, m.b, nf, -1, nullptr, 1.f, 0, h0, /*want_stats=*/true);
+        conv(m.tc0, pt, Tensor(), 1, m.w, m.b, nf, -1, nullptr, 1.f, 0, h0, /*want_stats=*/true);
         ffree(patches, pb);
       } else {
         SimtConv s; memset(&s, 0, sizeof(s));

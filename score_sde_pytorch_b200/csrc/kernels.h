@@ -16,6 +16,7 @@ int launch_gn_apply(const float* x1, int C1, const float* x2, int C2, const doub
                     int round_out, float* y, float* raw, cudaStream_t st, int x1_f16 = 0);
 int launch_gn_generic(const float* x1, int C1, const float* x2, int C2, const float* gamma, const float* beta, int B, int HW, int G,
                       float eps, int act, int round_out, float* y, float* raw, float* mr_ws, cudaStream_t st);
+long long gn_generic_workspace_floats(int B, int HW, int G);   // size of mr_ws
 int launch_gn_coeff(int C1, int C2, const double* q1, const double* q2, const float* gamma, const float* beta, int B, int HW,
                     int G, float eps, float* scale, float* shift, cudaStream_t st);
 int launch_upfirdn2d(const float* x, const float* kernel_host, float* y, int major, int in_h, int in_w,
@@ -36,6 +37,7 @@ int launch_pack_weight(const float* src, float* dst, int taps, int O, int I, lon
                        long long stp, int round_out, cudaStream_t st, long long dt = 0, long long dO = 0);
 int launch_im2col3x3_nchw(const float* x, float* patches, int B, int C, int Hin, int Win, int H, int W, int stride,
                           int pad, int mode, cudaStream_t st);
+bool attn_small_supported(int T, int C);   // T <= 64 tokens; q / k staged in channel slabs when 2*T*C floats exceed shared memory
 int launch_attn_small_configure(int T, int C);
 int launch_attn_small(const float* qkv, float* out, int B, int T, int C, float scale, int round_out, cudaStream_t st);
 int launch_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* div, long long div_stride,
