@@ -55,45 +55,62 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PH = LC_TH + 2 * HALO, PW = LC_TW + 2 * HALO;
   constexpr int N = NB * 8;
+  constexpr int A_FLOATS = PH * PW * LC_KC;
   constexpr int A_PIECES = PH * PW * 4;                                   // 16-byte pieces of one input slab
   constexpr int A_ITERS = (A_PIECES + LC_THREADS - 1) / LC_THREADS;
   constexpr int B_PIECES = TAPS * N * 4;
   extern __shared__ __align__(16) float lc_smem[];
   float* sA0 = lc_smem;                         // 2 x [PH][PW][16]  input slab with halo
-  float* sB = lc_smem + 2 * PH * PW * LC_KC;    // [TAPS][N][16]     weight slab, TF32 grid
+  float* sB = lc_smem + 2 * A_FLOATS;           // [TAPS][N][16]     weight slab, TF32 grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int tiles_x = p.W / LC_TW, tiles_y = p.H / LC_TH;
+  const int tiles_x = p.W / LC_TW, tiles_y = p.H / LC_TH, tiles_img = tiles_x * tiles_y;
   const int Cin = p.C1 + p.C2, slabs = Cin / LC_KC;
-  const long long ld1 = p.ld1 ? p.ld1 : p.C1, ld2 = p.ld2 ? p.ld2 : p.C2, wld = p.w_ld ? p.w_ld : Cin;
-  const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const long long items = my_tiles * slabs;
+  const int ld1 = (int)(p.ld1 ? p.ld1 : p.C1), ld2 = (int)(p.ld2 ? p.ld2 : p.C2), wld = (int)(p.w_ld ? p.w_ld : Cin);
+  const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long img_pix = (long long)p.H * p.W;
 
   auto stage_weights = [&](int c0) {
-    for (int e = tid; e < B_PIECES; e += LC_THREADS) {
-      const int q = e & 3, row = e >> 2;      // row = tap * N + n of the packed [tap][N][Cin] weights
-      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (long long)row * wld + c0 + 4 * q)));
-      *reinterpret_cast<float4*>(sB + row * LC_KC + 4 * q) = v;
+    for (int e = tid; e < B_PIECES; e += LC_THREADS) {   // piece e = 4 floats of row e/4 (= tap * N + n) of the [tap][N][Cin] weights
+      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (e >> 2) * wld + c0 + 4 * (e & 3))));
+      *reinterpret_cast<float4*>(sB + 4 * e) = v;
     }
   };
-  // issue the copies of work item `it` into buffer it & 1
-  auto issue = [&](long long it) {
-    const int tile = blockIdx.x + (int)(it / slabs) * gridDim.x, c0 = (int)(it % slabs) * LC_KC;
-    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
-    const float* src = c0 < p.C1 ? p.x1 + (long long)img * p.H * p.W * ld1 + c0 : p.x2 + (long long)img * p.H * p.W * ld2 + (c0 - p.C1);
-    const long long ld = c0 < p.C1 ? ld1 : ld2;
-    float* dst = sA0 + (it & 1) * (PH * PW * LC_KC);
+  // copies of one (tile, slab) work item into `dst`: piece e = floats 4e..4e+3 of the [PH][PW][16] slab.  A thread's
+  // pieces are e = tid + 256 k: channel quad q = tid & 3 for all of them, slab pixel (tid >> 2) + 64 k.
+  const int q4 = 4 * (tid & 3), pix0 = tid >> 2;
+  auto issue = [&](int img, int ty, int tx, int slab, float* dst) {
+    const int c0 = slab * LC_KC;
+    const bool one = c0 < p.C1;
+    const int ld = one ? ld1 : ld2;
+    const int y0 = ty * LC_TH - HALO, x0 = tx * LC_TW - HALO;
+    // (tile origin may lie one pixel outside the image: only dereferenced for in-bounds pixels)
+    const float* src = (one ? p.x1 + c0 : p.x2 + (c0 - p.C1)) + (img * img_pix + (long long)y0 * p.W + x0) * ld + q4;
+    float* d = dst + 4 * tid;
+    if (HALO == 0 || (ty > 0 && ty < tiles_y - 1 && tx > 0 && tx < tiles_x - 1)) {
 #pragma unroll
-    for (int k = 0; k < A_ITERS; ++k) {
-      const int e = tid + k * LC_THREADS;
-      if (e < A_PIECES) {
-        const int q = e & 3, pix = e >> 2, py = pix / PW, px = pix - py * PW;
-        const int iy = ty * LC_TH + py - HALO, ix = tx * LC_TW + px - HALO;
-        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        cp_async16(dst + pix * LC_KC + 4 * q, ok ? src + ((long long)iy * p.W + ix) * ld + 4 * q : src, ok);
+      for (int k = 0; k < A_ITERS; ++k) {
+        const int pix = pix0 + 64 * k;
+        if (k < A_ITERS - 1 || pix < PH * PW) {
+          const int py = pix / PW, px = pix - py * PW;
+          cp_async16(d + 4 * LC_THREADS * k, src + (py * p.W + px) * ld, true);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < A_ITERS; ++k) {
+        const int pix = pix0 + 64 * k;
+        if (k < A_ITERS - 1 || pix < PH * PW) {
+          const int py = pix / PW, px = pix - py * PW, iy = y0 + py, ix = x0 + px;
+          const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          cp_async16(d + 4 * LC_THREADS * k, ok ? src + (py * p.W + px) * ld : p.x1, ok);
+        }
       }
     }
     cp_async_commit();
+  };
+  auto decompose = [&](int tile, int& img, int& ty, int& tx) {
+    img = tile / tiles_img; const int r = tile - img * tiles_img; ty = r / tiles_x; tx = r - ty * tiles_x;
   };
 
   float acc[2][NB][4];
@@ -104,70 +121,85 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mb][nb][i] = 0.f;
 
-  if (items > 0) issue(0);
+  int img = 0, ty = 0, tx = 0, nimg = 0, nty = 0, ntx = 0;     // current / next tile of this CTA
+  if (my_tiles > 0) { decompose(blockIdx.x, img, ty, tx); issue(img, ty, tx, 0, sA0); }
   if (slabs == 1) stage_weights(0);
-  for (long long it = 0; it < items; ++it) {
-    if (it + 1 < items) { issue(it + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-    float* sA = sA0 + (it & 1) * (PH * PW * LC_KC);
-#pragma unroll
-    for (int k = 0; k < A_ITERS; ++k) {          // round this thread's own pieces of item `it`
-      const int e = tid + k * LC_THREADS;
-      if (e < A_PIECES) {
-        float4* q4 = reinterpret_cast<float4*>(sA + (e >> 2) * LC_KC + 4 * (e & 3));
-        *q4 = round4_tf32(*q4);
-      }
-    }
-    const int slab = (int)(it % slabs);
-    if (slabs > 1) stage_weights(slab * LC_KC);   // (the barrier that closed the previous item freed sB)
-    __syncthreads();
-
-#pragma unroll
-    for (int tap = 0; tap < TAPS; ++tap) {
-      const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
-      float4 av[2][2];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          av[mb][h] = *reinterpret_cast<const float4*>(sA + ((warp + dy) * PW + mb * 16 + g + 8 * h + dx) * LC_KC + 4 * t);
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const float4 bv = *reinterpret_cast<const float4*>(sB + (tap * N + nb * 8 + g) * LC_KC + 4 * t);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].x, av[mb][1].x, av[mb][0].y, av[mb][1].y, bv.x, bv.y);
-          mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].z, av[mb][1].z, av[mb][0].w, av[mb][1].w, bv.z, bv.w);
+  int buf = 0;
+  for (int k = 0, tile = blockIdx.x; k < my_tiles; ++k, tile += gridDim.x, img = nimg, ty = nty, tx = ntx) {
+    if (k + 1 < my_tiles) decompose(tile + gridDim.x, nimg, nty, ntx);
+    for (int slab = 0; slab < slabs; ++slab, buf ^= 1) {
+      float* sA = sA0 + buf * A_FLOATS;
+      {                                            // next work item: the next slab of this tile, else the next tile's first
+        const bool same = slab + 1 < slabs;
+        if (same || k + 1 < my_tiles) {
+          issue(same ? img : nimg, same ? ty : nty, same ? tx : ntx, same ? slab + 1 : 0, sA0 + (buf ^ 1) * A_FLOATS);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
         }
       }
-    }
-    __syncthreads();                              // buffer it & 1 and sB may be overwritten from here on
+#pragma unroll
+      for (int kk = 0; kk < A_ITERS; ++kk) {       // round this thread's own pieces of the current item
+        const int e = tid + kk * LC_THREADS;
+        if (e < A_PIECES) {
+          float4* q4 = reinterpret_cast<float4*>(sA + 4 * e);
+          *q4 = round4_tf32(*q4);
+        }
+      }
+      if (slabs > 1) stage_weights(slab * LC_KC);  // (the barrier that closed the previous item freed sB)
+      __syncthreads();
 
-    if (slab == slabs - 1) {
-      // ---- epilogue: lane (g, t) holds pixels g / g+8 of each m16 block and output channels 2t, 2t+1 of each n8 block ----
-      const int tile = blockIdx.x + (int)(it / slabs) * gridDim.x;
-      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
-      const Epilogue& e = p.epi;
-      const int oy = ty * LC_TH + warp;
 #pragma unroll
-      for (int mb = 0; mb < 2; ++mb)
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
+        float4 av[2][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int ox = tx * LC_TW + mb * 16 + g + 8 * h;
-          const long long gm = ((long long)img * p.H + oy) * p.W + ox;
+        for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            const int n = nb * 8 + 2 * t;
-            float v0 = acc[mb][nb][2 * h], v1 = acc[mb][nb][2 * h + 1];
-            acc[mb][nb][2 * h] = 0.f; acc[mb][nb][2 * h + 1] = 0.f;
-            if (e.bias) { const float2 b = __ldg(reinterpret_cast<const float2*>(e.bias + n)); v0 += b.x; v1 += b.y; }
-            if (e.rowvec) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.rowvec + img * e.rowvec_ld + n)); v0 += r.x; v1 += r.y; }
-            if (e.residual) { const float2 r = __ldg(reinterpret_cast<const float2*>(e.residual + gm * e.ld_res + n)); v0 += r.x; v1 += r.y; }
-            v0 *= e.scale; v1 *= e.scale;
-            if (e.round_tf32) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
-            *reinterpret_cast<float2*>(e.out + gm * e.ld_out + n) = make_float2(v0, v1);
+          for (int h = 0; h < 2; ++h)
+            av[mb][h] = *reinterpret_cast<const float4*>(sA + ((warp + dy) * PW + mb * 16 + g + 8 * h + dx) * LC_KC + 4 * t);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const float4 bv = *reinterpret_cast<const float4*>(sB + (tap * N + nb * 8 + g) * LC_KC + 4 * t);
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].x, av[mb][1].x, av[mb][0].y, av[mb][1].y, bv.x, bv.y);
+            mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].z, av[mb][1].z, av[mb][0].w, av[mb][1].w, bv.z, bv.w);
           }
         }
+      }
+      __syncthreads();                             // this buffer and sB may be overwritten from here on
     }
+
+    // ---- epilogue: lane (g, t) holds pixels g / g+8 of each m16 block and output channels 2t, 2t+1 of each n8 block ----
+    const Epilogue& e = p.epi;
+    const int oy = ty * LC_TH + warp;
+    float2 add[NB];                                // bias + per-image row vector of this lane's channels
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int n = nb * 8 + 2 * t;
+      add[nb] = make_float2(0.f, 0.f);
+      if (e.bias) { const float2 b = __ldg(reinterpret_cast<const float2*>(e.bias + n)); add[nb].x += b.x; add[nb].y += b.y; }
+      if (e.rowvec) { const float2 rv = __ldg(reinterpret_cast<const float2*>(e.rowvec + img * e.rowvec_ld + n)); add[nb].x += rv.x; add[nb].y += rv.y; }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ox = tx * LC_TW + mb * 16 + g + 8 * h;
+        const long long gm = (img * img_pix + (long long)oy * p.W + ox);
+        float* orow = e.out + gm * e.ld_out + 2 * t;
+        const float* rrow = e.residual ? e.residual + gm * e.ld_res + 2 * t : nullptr;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          float v0 = acc[mb][nb][2 * h] + add[nb].x, v1 = acc[mb][nb][2 * h + 1] + add[nb].y;
+          acc[mb][nb][2 * h] = 0.f; acc[mb][nb][2 * h + 1] = 0.f;
+          if (rrow) { const float2 rr = __ldg(reinterpret_cast<const float2*>(rrow + nb * 8)); v0 += rr.x; v1 += rr.y; }
+          v0 *= e.scale; v1 *= e.scale;
+          if (e.round_tf32) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
+          *reinterpret_cast<float2*>(orow + nb * 8) = make_float2(v0, v1);
+        }
+      }
   }
 }
 
