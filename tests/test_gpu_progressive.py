@@ -64,8 +64,8 @@ def test_progressive_nofir_matches_oracle(dev):
 @pytest.mark.parametrize('name,precision', [('celebahq_256', 'tf32'), ('celebahq_256', 'f16'), ('ffhq_1024', 'tf32')])
 def test_high_resolution_reference_configs_full_size(dev, name, precision):
   """configs/ve/celebahq_256_ncsnpp_continuous.py (65.6 M parameters, 256x256, seven levels) and
-  configs/ve/ffhq_ncsnpp_continuous.py (105.8 M parameters, 1024x1024, eight levels, nf=16: the 16/32-channel levels run on
-  the CUDA-core convolution, the rest on tcgen05), one evaluation at batch 1 against the strict-fp32 oracle."""
+  configs/ve/ffhq_ncsnpp_continuous.py (105.8 M parameters, 1024x1024, eight levels, nf=16: the 16/32/64-channel levels run on
+  the few-channel TF32 MMA kernel, the rest on tcgen05), one evaluation at batch 1 against the strict-fp32 oracle."""
   cfg = golden_config(name)
   model = seeded_model(cfg, precision=precision).to(dev)
   sd = {k: v.to(dev) for k, v in model.state_dict().items()}
