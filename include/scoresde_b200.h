@@ -121,7 +121,9 @@ typedef struct {
   int separate_groupnorm;       /* 1: every GroupNorm+SiLU as its own streaming pass (the round-1 plan, kept for A/B and
                                  * as the checked alternative); 0: in fp16 operand mode GroupNorm+SiLU is applied ON LOAD by
                                  * the consuming 3x3 convolution (csrc/gemm_tcg.cuh) wherever the shape allows
-                                 * (256-channel outputs at 16x16 / 32x32), so the normalised tensor never reaches HBM */
+                                 * (256-channel outputs at 16x16 / 32x32), so the normalised tensor never reaches HBM.
+                                 * The few-channel convolutions of the nf = 16 networks (csrc/conv_lowc.cu, TF32 mode) are
+                                 * memory-bound and apply their GroupNorm+SiLU on load under 0 and 1; 2: separate passes there too */
   int embedding_type;           /* 0: Gaussian Fourier features of log(sigma) (layerspp.py:32-41, all_modules[0].W); 1: sinusoidal
                                  * positional embedding of the time label (layers.py:515-529, ncsnpp.py:242-247): no module,
                                  * the frequency table is the pseudo-parameter "pos_freqs" [nf/2] */

@@ -80,6 +80,17 @@ __device__ __forceinline__ void store_operand1(float* base, long long idx, float
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// SiLU for outputs that are rounded to an 11-bit significand right after (operand modes 1, 2): ex2.approx +
+// rcp.approx (relative error ~1e-6, two orders below the rounding) instead of the IEEE exp/divide sequences,
+// which made this HBM-streaming kernel instruction-bound (~25 -> ~8 instructions per element).
+// (Written out as the two MUFU ops: __fdividef / __expf wrap them in range-scaling code, 9-10 instructions per element
+// instead of 5; the convolution that applies GroupNorm on load, gemm_tcg.cuh, uses the same function so both plans round alike.)
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -138,12 +138,39 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
           cp_async_wait<0>();
         }
       }
+      if (!p.gn_scale) {
 #pragma unroll
-      for (int kk = 0; kk < A_ITERS; ++kk) {       // round this thread's own pieces of the current item
-        const int e = tid + kk * LC_THREADS;
-        if (e < A_PIECES) {
-          float4* q4 = reinterpret_cast<float4*>(sA + 4 * e);
-          *q4 = round4_tf32(*q4);
+        for (int kk = 0; kk < A_ITERS; ++kk) {     // round this thread's own pieces of the current item
+          const int e = tid + kk * LC_THREADS;
+          if (e < A_PIECES) {
+            float4* q4p = reinterpret_cast<float4*>(sA + 4 * e);
+            *q4p = round4_tf32(*q4p);
+          }
+        }
+      } else {
+        // GroupNorm + SiLU on load: y = fma(x, scale, shift) of this thread's channel quad (the same four channels for
+        // all of its pieces), SiLU, TF32 rounding - the arithmetic of gn_apply_stream_kernel's TF32-grid mode.  The
+        // padding ring must stay zero AFTER the transform (the reference pads the normalised tensor), so border tiles
+        // re-derive which pieces lie outside the image.
+        const int cidx = img * Cin + slab * LC_KC + q4;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.gn_scale + cidx));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.gn_shift + cidx));
+        const bool interior = HALO == 0 || (ty > 0 && ty < tiles_y - 1 && tx > 0 && tx < tiles_x - 1);
+        const int y0 = ty * LC_TH - HALO, x0 = tx * LC_TW - HALO;
+#pragma unroll
+        for (int kk = 0; kk < A_ITERS; ++kk) {
+          const int pix = pix0 + 64 * kk;
+          if (kk < A_ITERS - 1 || pix < PH * PW) {
+            float4* q4p = reinterpret_cast<float4*>(sA + 4 * (tid + kk * LC_THREADS));
+            float4 v = *q4p;
+            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            if (p.gn_act) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
+            if (!interior) {
+              const int py = pix / PW, px = pix - py * PW, iy = y0 + py, ix = x0 + px;
+              if (!(iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *q4p = round4_tf32(v);
+          }
         }
       }
       if (slabs > 1) stage_weights(slab * LC_KC);  // (the barrier that closed the previous item freed sB)
@@ -245,6 +272,8 @@ int launch_conv_lowc(const SimtConv& p, cudaStream_t st) {
   B200_REQUIRE(conv_lowc_supported(p), "conv_lowc: unsupported shape (C %d+%d -> %d, %dx%d, %dx%d filter)", p.C1, p.C2, p.N, p.H,
                p.W, p.R, p.S);
   B200_REQUIRE((p.x2 != nullptr) == (p.C2 > 0), "conv_lowc: second source / channel count mismatch");
+  B200_REQUIRE((p.gn_scale == nullptr) == (p.gn_shift == nullptr) && aligned(p.gn_scale, 16) && aligned(p.gn_shift, 16),
+               "conv_lowc: GroupNorm scale and shift come together, 16-byte aligned");
   B200_REQUIRE(aligned(p.x1, 16) && aligned(p.x2, 16) && aligned(p.w, 16) && aligned(p.epi.out, 8) && aligned(p.epi.residual, 8) &&
                aligned(p.epi.bias, 8) && aligned(p.epi.rowvec, 8), "conv_lowc: operands must be 16-byte, epilogue terms 8-byte aligned");
   if (p.R == 3) {

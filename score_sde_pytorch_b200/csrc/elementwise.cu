@@ -112,17 +112,6 @@ __device__ __forceinline__ float2 group_mean_rstd(const double* __restrict__ q1,
   return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
-// SiLU for outputs that are rounded to an 11-bit significand right after (operand modes 1, 2): ex2.approx +
-// rcp.approx (relative error ~1e-6, two orders below the rounding) instead of the IEEE exp/divide sequences,
-// which made this HBM-streaming kernel instruction-bound (~25 -> ~8 instructions per element).
-// (Written out as the two MUFU ops: __fdividef / __expf wrap them in range-scaling code, 9-10 instructions per element
-// instead of 5; the convolution that applies GroupNorm on load, gemm_tcg.cuh, uses the same function so both plans round alike.)
-__device__ __forceinline__ float silu_fast(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return x * r;
-}
 // y = v * sc + sh with sc = rstd * gamma, sh = beta - mean * sc folded per channel by the caller
 __device__ __forceinline__ float4 gn_affine4(float4 v, float4 sc, float4 sh, int act) {
   float4 o;

@@ -378,6 +378,7 @@ struct Builder {
   char* stats_base = nullptr; long long stats_top = 0;   // bump region for GroupNorm quad sums, zeroed once per forward
   bool fused_stats = false;
   bool gn_on_load = false;                     // GroupNorm+SiLU applied by the consuming convolution (gemm_tcg.cuh) where shapes allow
+  bool lowc_gn = false;                        // the few-channel convolutions (conv_lowc.cu, TF32 mode) apply GroupNorm+SiLU while staging their input
   int lane = 0;                                // which half-batch plan this builder fills (ops or ops2)
   int om = 1;                                  // operand store mode of tensor-core inputs: 1 TF32-grid fp32, 2 fp16
   std::string next_name;                       // label of the next op (shape summary for the per-op profile)
@@ -388,7 +389,8 @@ struct Builder {
   Builder(b200_ncsnpp* e_, int B_, char* base_, bool dry_, int lane_ = 0) : e(e_), B(B_), base(base_), dry(dry_), arena(e_->cfg.keep_activations != 0), lane(lane_) {
     fused_stats = e_->cfg.precision != 1;
     om = e_->cfg.precision == 2 ? 2 : 1;
-    gn_on_load = om == 2 && !e_->cfg.separate_groupnorm;
+    gn_on_load = om == 2 && e_->cfg.separate_groupnorm == 0;
+    lowc_gn = e_->cfg.precision == 0 && e_->cfg.separate_groupnorm != 2;
     if (dry_) stats_base = reinterpret_cast<char*>(uintptr_t(1) << 40);   // any non-null base: only offsets matter in a dry run
   }
   double* qalloc(int C) {
@@ -547,7 +549,7 @@ struct Builder {
   // 3x3 / 1x1 'same' convolution on NHWC tensors, stride 1.
   void conv(bool use_tc, Tensor a1, Tensor a2, int taps, int pw, int pb, int Cout, int dense_row /* -1 = none */,
             const float* residual, float scale, int round, Tensor& out, bool want_stats = false, int stride = 1,
-            int Hin = 0, Tensor x3 = Tensor(), Tensor x4 = Tensor(), int pw2 = -1, int pb2 = -1) {
+            int Hin = 0, Tensor x3 = Tensor(), Tensor x4 = Tensor(), int pw2 = -1, int pb2 = -1, const Coef* gnc = nullptr) {
     Epilogue ep; memset(&ep, 0, sizeof(ep));
     ep.bias = e->W(pb);
     ep.rowvec = nullptr;   // patched at launch (depends on the per-call buffers)
@@ -558,6 +560,7 @@ struct Builder {
     const int sumC = e->sumC;
     const double cflops = 2.0 * B * out.H * out.W * (double)Cout * ((a1.C + a2.C) * taps + x3.C + x4.C);
     if (x3.p && !use_tc) { set_error("ncsnpp: fused skip projection needs the tensor-core path"); rc = 2; return; }
+    if (gnc && use_tc) { set_error("ncsnpp: conv(): GroupNorm coefficients go with the few-channel kernel (convg() is the tcgen05 form)"); rc = 2; return; }
     if (use_tc) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = out.H; d.W = out.W; d.nimg = B; d.taps = taps;
@@ -599,7 +602,11 @@ struct Builder {
       // few-channel levels of the nf = 16 networks: warp-level TF32 MMAs keep them at the HBM roofline (conv_lowc.cu);
       // strict-fp32 mode and every other shape stay on the CUDA-core kernel
       const bool lowc = e->cfg.precision != 1 && !a1.f16 && !a2.f16 && sumC % 2 == 0 && conv_lowc_supported(s);
-      name("conv%s %d+%d->%d @%d [%s]", taps == 9 ? "3x3" : "1x1", a1.C, a2.C, Cout, out.H, lowc ? "mma.sync tf32" : "cuda-core");
+      if (gnc) {
+        if (!lowc) { set_error("ncsnpp: GroupNorm on load planned for a convolution the few-channel kernel does not take"); rc = 2; return; }
+        s.gn_scale = gnc->scale; s.gn_shift = gnc->shift; s.gn_act = 1;
+      }
+      name("conv%s %s%d+%d->%d @%d [%s]", taps == 9 ? "3x3" : "1x1", gnc ? "gn+silu " : "", a1.C, a2.C, Cout, out.H, lowc ? "mma.sync tf32" : "cuda-core");
       next_bytes = (double)B * out.H * out.W * ((a1.C + a2.C) * 4.0 + Cout * 4.0 + (residual ? Cout * 4.0 : 0.0)) +
                    (double)taps * (a1.C + a2.C) * Cout * 4.0;
       op(1, [=](cudaStream_t st) {
@@ -648,6 +655,15 @@ struct Builder {
   const float* dense_all_ = nullptr;
   void tap(int idx, const Tensor& t) { if (!dry) e->taps[idx] = t; }
 
+  // would conv() run this stride-1 convolution on the few-channel kernel (conv_lowc.cu: TF32 mode, fp32 tensors)?
+  bool lowc_ok(int C1, int C2, int Cout, int H, int taps) const {
+    if (e->cfg.precision != 0 || e->sumC % 2 != 0) return false;
+    SimtConv s; memset(&s, 0, sizeof(s));
+    s.C1 = C1; s.C2 = C2; s.in_scale = 1.f; s.H = H; s.W = H; s.R = s.S = (taps == 9 ? 3 : 1); s.stride = 1; s.pad = (taps == 9 ? 1 : 0);
+    s.OH = H; s.OW = H; s.nbatch = B; s.a_batched = 1; s.N = Cout; s.epi.ld_out = Cout; s.epi.ld_res = Cout;
+    return conv_lowc_supported(s);
+  }
+
   Tensor resblock(const Mod& m, Tensor& x1, Tensor& x2) {
     Tensor none;
     const int Cin = x1.C + x2.C, H = x1.H, Ho = m.up ? 2 * H : m.down ? H / 2 : H;
@@ -660,8 +676,14 @@ struct Builder {
     const bool skip_ok = !m.has_conv2 || (m.tc2 && (resample ? Cin % 64 == 0 : (x1.C % 64 == 0 && x2.C % 64 == 0)));
     const bool g1 = m.tc0 && m.tc1 && h1_f16 && skip_ok && tcg_shape_ok(m.cout, 0, m.cout, Ho, Ho);
     const bool g0 = g1 && !resample && tcg_shape_ok(x1.C, x2.C, m.cout, Ho, Ho);
+    // few-channel levels (TF32 mode): both 3x3 convolutions normalise their input while they stage it, so neither
+    // GroupNorm writes a tensor (quad-aligned groups only: the coefficient kernel works on channel quads)
+    const int G0 = std::min(Cin / 4, 32);
+    const bool lc0 = lowc_gn && !m.tc0 && !resample && !x1.f16 && !x2.f16 && Cin % G0 == 0 && (Cin / G0) % 4 == 0 && x1.C % 4 == 0 &&
+                     lowc_ok(x1.C, x2.C, m.cout, H, 9);
+    const bool lc1 = lowc_gn && !m.tc1 && lowc_ok(m.cout, 0, m.cout, Ho, 9);
     Tensor a0, raw;   // raw: operand-format copy of the (concatenated) block input for the tensor-core skip conv
-    if (!g0) {
+    if (!g0 && !lc0) {
       a0 = talloc(Cin, H, H);
       if (m.has_conv2 && m.tc2 && !resample && !g1) raw = talloc(Cin, H, H);
       gn(x1, x2, m.gn0w, m.gn0b, 1, (m.tc0 && !resample) ? om : 0, a0, raw.p);
@@ -684,6 +706,10 @@ struct Builder {
       Coef c0 = gncoef(x1, x2, m.gn0w, m.gn0b);
       convg(x1, x2, c0, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 2, h1);
       ffree(c0.scale, c0.bytes);
+    } else if (lc0) {
+      Coef c0 = gncoef(x1, x2, m.gn0w, m.gn0b);
+      conv(false, x1, x2, 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, 0, h1, /*want_stats=*/true, 1, 0, Tensor(), Tensor(), -1, -1, &c0);
+      ffree(c0.scale, c0.bytes);
     } else {
       conv(m.tc0, a0, Tensor(), 9, m.c0w, m.c0b, m.cout, m.dense_row, nullptr, 1.f, h1_f16 ? 2 : 0, h1, /*want_stats=*/true);
       tfree(a0);
@@ -702,9 +728,14 @@ struct Builder {
       tfree(h1); tfree(xr);
       return out;
     }
-    Tensor a1 = talloc(m.cout, Ho, Ho);
-    gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? om : 0, a1, nullptr);
-    tfree(h1);
+    Tensor a1; Coef c1;
+    if (lc1) {
+      c1 = gncoef(h1, none, m.gn1w, m.gn1b);
+    } else {
+      a1 = talloc(m.cout, Ho, Ho);
+      gn(h1, none, m.gn1w, m.gn1b, 1, m.tc1 ? om : 0, a1, nullptr);
+      tfree(h1);
+    }
     Tensor s;
     const float* residual = x1.p;
     // Fused skip projection (default): Conv_2(x) (layerspp.py:270) is accumulated inside the second 3x3 convolution
@@ -727,8 +758,14 @@ struct Builder {
       tfree(raw); tfree(xr);
     } else if (x2.p) { set_error("ncsnpp: concat input without a skip convolution"); rc = 2; return Tensor(); }
     Tensor out = talloc(m.cout, Ho, Ho);
-    conv(m.tc1, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, residual, inv_s2, 0, out, /*want_stats=*/true);
-    tfree(a1); tfree(s);
+    if (lc1) {
+      conv(false, h1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, residual, inv_s2, 0, out, /*want_stats=*/true, 1, 0, Tensor(), Tensor(), -1, -1, &c1);
+      ffree(c1.scale, c1.bytes); tfree(h1);
+    } else {
+      conv(m.tc1, a1, Tensor(), 9, m.c1w, m.c1b, m.cout, -1, residual, inv_s2, 0, out, /*want_stats=*/true);
+      tfree(a1);
+    }
+    tfree(s);
     return out;
   }
 

@@ -61,6 +61,9 @@ struct SimtConv {
   // W operand: [tap][N][Cin] (Cin contiguous), optionally one per batch item
   const float* w; int N; long long w_batch_stride;
   long long w_ld;                   // row pitch of W in elements (0 = Cin)
+  // GroupNorm (+ SiLU) applied to the input while it is staged (conv_lowc.cu only): per-(image, concatenated channel)
+  // y = fma(x, gn_scale, gn_shift) as written by launch_gn_coeff, then SiLU when gn_act; null = plain input
+  const float* gn_scale; const float* gn_shift; int gn_act;
   Epilogue epi;
 };
 int launch_conv_simt(const SimtConv& p, cudaStream_t st);

@@ -145,7 +145,10 @@ class NCSNpp(nn.Module):
     # supported (False; csrc/gemm_tcg.cuh).  Measured in the same run on the same B200: 62.41 vs 63.39 ms per PC step at
     # batch 1024 (profiles/r02_g6_bench.json) - at the board's power cap the transform's arithmetic costs more than
     # the 4.5 GB/evaluation of HBM traffic it removes, so the separate pass stays the default.
-    self.separate_groupnorm = bool(getattr(m, 'separate_groupnorm', True) if separate_groupnorm is None else separate_groupnorm)
+    # (2: separate passes also in front of the memory-bound few-channel convolutions of the nf = 16 networks, which
+    # otherwise always normalise on load in tf32 mode - csrc/conv_lowc.cu; kept for A/B tests)
+    sg = getattr(m, 'separate_groupnorm', True) if separate_groupnorm is None else separate_groupnorm
+    self.separate_groupnorm = 2 if (not isinstance(sg, bool) and sg == 2) else bool(sg)
     # programmatic dependent launch between the kernels of a forward / PC iteration (common.cuh)
     self.pdl = bool(getattr(m, 'pdl', PDL_DEFAULT) if pdl is None else pdl)
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
@@ -404,3 +407,17 @@ class NCSNpp(nn.Module):
 
   def launches_per_forward(self):
     return int(_lib.load().b200_ncsnpp_launches_per_forward(self._engine['h'])) if self._engine else 0
+
+  def op_names(self):
+    """Shape labels of the ops of the bound plan, in execution order (b200_ncsnpp_op_info); empty before the first call."""
+    if not self._engine:
+      return []
+    import ctypes
+    h = self._engine['h']
+    n = int(_lib.load().b200_ncsnpp_num_ops(h))
+    buf, kind, fl = ctypes.create_string_buffer(200), ctypes.c_int(), ctypes.c_double()
+    names = []
+    for i in range(n):
+      _lib.call('b200_ncsnpp_op_info', h, i, buf, 200, ctypes.byref(kind), ctypes.byref(fl))
+      names.append(buf.value.decode())
+    return names
