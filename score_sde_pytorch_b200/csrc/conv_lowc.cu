@@ -121,6 +121,20 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mb][nb][i] = 0.f;
 
+  // GroupNorm quad sums of the output (p.qstats): per-CTA fp64 accumulators [N/4][2] for the image the CTA is working
+  // on, flushed to global memory when the image changes and at the end (a CTA's tiles come in image order)
+  __shared__ double sQ[2 * NB * 2];
+  int q_img = -1;
+  auto flush_stats = [&](int next_img) {         // CTA-uniform call sites only
+    __syncthreads();
+    if (tid < 2 * NB * 2) {
+      if (q_img >= 0 && sQ[tid] != 0.0) atomicAdd(p.qstats + ((long long)q_img * (2 * NB) * 2 + tid), sQ[tid]);
+      sQ[tid] = 0.0;
+    }
+    __syncthreads();
+    q_img = next_img;
+  };
+
   int img = 0, ty = 0, tx = 0, nimg = 0, nty = 0, ntx = 0;     // current / next tile of this CTA
   if (my_tiles > 0) { decompose(blockIdx.x, img, ty, tx); issue(img, ty, tx, 0, sA0); }
   if (slabs == 1) stage_weights(0);
@@ -200,6 +214,10 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
 
     // ---- epilogue: lane (g, t) holds pixels g / g+8 of each m16 block and output channels 2t, 2t+1 of each n8 block ----
     const Epilogue& e = p.epi;
+    if (p.qstats && img != q_img) flush_stats(img);
+    float qs[NB], qq[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) { qs[nb] = 0.f; qq[nb] = 0.f; }
     const int oy = ty * LC_TH + warp;
     float2 add[NB];                                // bias + per-image row vector of this lane's channels
 #pragma unroll
@@ -225,9 +243,27 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
           v0 *= e.scale; v1 *= e.scale;
           if (e.round_tf32) { v0 = round_tf32(v0); v1 = round_tf32(v1); }
           *reinterpret_cast<float2*>(orow + nb * 8) = make_float2(v0, v1);
+          qs[nb] += v0 + v1; qq[nb] = fmaf(v0, v0, fmaf(v1, v1, qq[nb]));
         }
       }
+    if (p.qstats) {
+      // lane (g, t): channels 2t, 2t+1 of each n8 block -> lanes t = 0,1 share quad 2nb, t = 2,3 quad 2nb+1; fold the
+      // lane pair, then the eight pixel lanes g; lanes 0 and 2 add the warp's 32-pixel totals to the CTA accumulators
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        float a = qs[nb], b = qq[nb];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);  b += __shfl_xor_sync(0xffffffffu, b, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);  b += __shfl_xor_sync(0xffffffffu, b, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+        if (lane == 0 || lane == 2) {
+          const int quad = 2 * nb + (lane >> 1);
+          atomicAdd(&sQ[2 * quad], (double)a); atomicAdd(&sQ[2 * quad + 1], (double)b);
+        }
+      }
+    }
   }
+  if (p.qstats) flush_stats(-1);
 }
 
 int lc_num_sms() {
@@ -272,6 +308,7 @@ int launch_conv_lowc(const SimtConv& p, cudaStream_t st) {
   B200_REQUIRE(conv_lowc_supported(p), "conv_lowc: unsupported shape (C %d+%d -> %d, %dx%d, %dx%d filter)", p.C1, p.C2, p.N, p.H,
                p.W, p.R, p.S);
   B200_REQUIRE((p.x2 != nullptr) == (p.C2 > 0), "conv_lowc: second source / channel count mismatch");
+  B200_REQUIRE(aligned(p.qstats, 8), "conv_lowc: quad sums must be 8-byte aligned");
   B200_REQUIRE((p.gn_scale == nullptr) == (p.gn_shift == nullptr) && aligned(p.gn_scale, 16) && aligned(p.gn_shift, 16),
                "conv_lowc: GroupNorm scale and shift come together, 16-byte aligned");
   B200_REQUIRE(aligned(p.x1, 16) && aligned(p.x2, 16) && aligned(p.w, 16) && aligned(p.epi.out, 8) && aligned(p.epi.residual, 8) &&

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConv p) {
 int launch_conv_simt(const SimtConv& p, cudaStream_t st) {
   B200_REQUIRE(p.x1 && p.w && p.epi.out, "conv_simt: null operand");
   B200_REQUIRE(!(p.in_nchw && p.x2), "conv_simt: NCHW input cannot be two-source");
-  B200_REQUIRE(!p.gn_scale, "conv_simt: GroupNorm on load is implemented by the few-channel kernel only");
+  B200_REQUIRE(!p.gn_scale && !p.qstats, "conv_simt: GroupNorm on load / fused quad sums are implemented by the few-channel kernel only");
   B200_REQUIRE(p.in_nchw || (p.in_scale == 1.f && p.in_shift == 0.f) || (p.C1 % 4 != 0),
                "conv_simt: input affine is only wired for the scalar-load path");
   const int rows_per_img = p.OH * p.OW;

@@ -602,6 +602,7 @@ struct Builder {
       // few-channel levels of the nf = 16 networks: warp-level TF32 MMAs keep them at the HBM roofline (conv_lowc.cu);
       // strict-fp32 mode and every other shape stay on the CUDA-core kernel
       const bool lowc = e->cfg.precision != 1 && !a1.f16 && !a2.f16 && sumC % 2 == 0 && conv_lowc_supported(s);
+      if (want_stats && lowc && fused_stats) { out.qs = qalloc(Cout); s.qstats = out.qs; }   // the epilogue sums what the next GroupNorm needs
       if (gnc) {
         if (!lowc) { set_error("ncsnpp: GroupNorm on load planned for a convolution the few-channel kernel does not take"); rc = 2; return; }
         s.gn_scale = gnc->scale; s.gn_shift = gnc->shift; s.gn_act = 1;

@@ -64,6 +64,9 @@ struct SimtConv {
   // GroupNorm (+ SiLU) applied to the input while it is staged (conv_lowc.cu only): per-(image, concatenated channel)
   // y = fma(x, gn_scale, gn_shift) as written by launch_gn_coeff, then SiLU when gn_act; null = plain input
   const float* gn_scale; const float* gn_shift; int gn_act;
+  // GroupNorm quad sums of the stored output, accumulated by the epilogue (conv_lowc.cu only): [image][N/4][2] fp64
+  // (sum, sum of squares), zeroed by the caller; null = none
+  double* qstats;
   Epilogue epi;
 };
 int launch_conv_simt(const SimtConv& p, cudaStream_t st);
