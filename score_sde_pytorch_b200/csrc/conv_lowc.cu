@@ -50,7 +50,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // before the barrier that publishes the buffer.  Single-slab layers (Cin = 16) load their weights once per CTA; the
 // others re-stage the [tap][Cout][16] weight slab of each item from L2.
 template <int TAPS, int NB>
-__global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv p, int num_tiles) {
+__global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv p, int num_tiles, int w_slabs) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see common.cuh
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PH = LC_TH + 2 * HALO, PW = LC_TW + 2 * HALO;
@@ -70,12 +70,16 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
   const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const long long img_pix = (long long)p.H * p.W;
 
-  auto stage_weights = [&](int c0) {
-    for (int e = tid; e < B_PIECES; e += LC_THREADS) {   // piece e = 4 floats of row e/4 (= tap * N + n) of the [tap][N][Cin] weights
-      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (e >> 2) * wld + c0 + 4 * (e & 3))));
-      *reinterpret_cast<float4*>(sB + 4 * e) = v;
+  // weight slab `slab` ([tap][N][16 channels]) into dst; piece e = 4 floats of row e/4 (= tap * N + n) of the [tap][N][Cin] weights
+  auto stage_weights = [&](int slab, float* dst) {
+    for (int e = tid; e < B_PIECES; e += LC_THREADS) {
+      const float4 v = round4_tf32(__ldg(reinterpret_cast<const float4*>(p.w + (e >> 2) * wld + slab * LC_KC + 4 * (e & 3))));
+      *reinterpret_cast<float4*>(dst + 4 * e) = v;
     }
   };
+  // all slabs stay resident when they fit the launch's shared memory (w_slabs == slabs: staged once per CTA, e.g. 32 -> 32
+  // channels = 36 KB); otherwise one slab at a time, re-staged from L2 for every work item
+  const bool resident = w_slabs == slabs;
   // copies of one (tile, slab) work item into `dst`: piece e = floats 4e..4e+3 of the [PH][PW][16] slab.  A thread's
   // pieces are e = tid + 256 k: channel quad q = tid & 3 for all of them, slab pixel (tid >> 2) + 64 k.
   const int q4 = 4 * (tid & 3), pix0 = tid >> 2;
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
 
   int img = 0, ty = 0, tx = 0, nimg = 0, nty = 0, ntx = 0;     // current / next tile of this CTA
   if (my_tiles > 0) { decompose(blockIdx.x, img, ty, tx); issue(img, ty, tx, 0, sA0); }
-  if (slabs == 1) stage_weights(0);
+  if (resident) for (int sl = 0; sl < slabs; ++sl) stage_weights(sl, sB + sl * (B_PIECES * 4));
   int buf = 0;
   for (int k = 0, tile = blockIdx.x; k < my_tiles; ++k, tile += gridDim.x, img = nimg, ty = nty, tx = ntx) {
     if (k + 1 < my_tiles) decompose(tile + gridDim.x, nimg, nty, ntx);
@@ -187,7 +191,8 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
           }
         }
       }
-      if (slabs > 1) stage_weights(slab * LC_KC);  // (the barrier that closed the previous item freed sB)
+      if (!resident) stage_weights(slab, sB);      // (the barrier that closed the previous item freed sB)
+      const float* sBs = resident ? sB + slab * (B_PIECES * 4) : sB;
       __syncthreads();
 
 #pragma unroll
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(LC_THREADS, 2) conv_lowc_kernel(const SimtConv
             av[mb][h] = *reinterpret_cast<const float4*>(sA + ((warp + dy) * PW + mb * 16 + g + 8 * h + dx) * LC_KC + 4 * t);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-          const float4 bv = *reinterpret_cast<const float4*>(sB + (tap * N + nb * 8 + g) * LC_KC + 4 * t);
+          const float4 bv = *reinterpret_cast<const float4*>(sBs + (tap * N + nb * 8 + g) * LC_KC + 4 * t);
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb) {
             mma_tf32_m16n8k8(acc[mb][nb], av[mb][0].x, av[mb][1].x, av[mb][0].y, av[mb][1].y, bv.x, bv.y);
@@ -275,16 +280,21 @@ int lc_num_sms() {
 template <int TAPS, int NB>
 int launch_lowc(const SimtConv& p, cudaStream_t st) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
-  constexpr int smem = (2 * (LC_TH + 2 * HALO) * (LC_TW + 2 * HALO) + TAPS * NB * 8) * LC_KC * (int)sizeof(float);
+  constexpr int a_bytes = 2 * (LC_TH + 2 * HALO) * (LC_TW + 2 * HALO) * LC_KC * (int)sizeof(float);
+  constexpr int slab_bytes = TAPS * NB * 8 * LC_KC * (int)sizeof(float);
+  constexpr int max_smem = a_bytes + 36 * 1024;   // two CTAs per SM: <= 43.5 + 36 KB each (one 64-channel 3x3 slab is 36 KB)
+  const int slabs = (p.C1 + p.C2) / LC_KC;
+  const int w_slabs = (a_bytes + slabs * slab_bytes <= max_smem) ? slabs : 1;
+  const int smem = a_bytes + w_slabs * slab_bytes;
   static bool configured = false;   // one attribute call per instantiation (same value every time: benign if raced)
   if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_lowc_kernel<TAPS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_lowc_kernel<TAPS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   const long long tiles = (long long)p.nbatch * (p.H / LC_TH) * (p.W / LC_TW);
   B200_REQUIRE(tiles > 0 && tiles < (1LL << 30), "conv_lowc: %lld tiles", tiles);
   const int grid = (int)std::min<long long>(tiles, 2LL * lc_num_sms());
-  launch_kernel(conv_lowc_kernel<TAPS, NB>, dim3(grid), dim3(LC_THREADS), smem, st, p, (int)tiles);
+  launch_kernel(conv_lowc_kernel<TAPS, NB>, dim3(grid), dim3(LC_THREADS), smem, st, p, (int)tiles, w_slabs);
   B200_CHECK_LAUNCH();
   return 0;
 }
