@@ -566,7 +566,7 @@ struct Builder {
       d.a1 = a1.p; d.C1 = a1.C; d.a2 = a2.p; d.C2 = a2.C; d.conv = 1; d.H = out.H; d.W = out.W; d.nimg = B; d.taps = taps;
       d.stride = stride; d.valid_pad = stride == 2 ? 1 : 0; d.Hin = Hin ? Hin : out.H; d.Win = Hin ? Hin : out.W;
       d.w = e->W(pw); d.N_total = Cout; d.K_total = a1.C + a2.C; d.w_rows = (long long)taps * Cout; d.nbatch = 1;
-      d.f16 = om == 2;
+      d.f16 = om == 2; d.no_halo = e->cfg.no_halo;
       if (dense_row >= 0) ep.rowvec = dense_all + dense_row;
       if (x3.p) {   // fused skip projection: its bias rides in the (image-independent) row-vector slot
         if (dense_row >= 0) { set_error("ncsnpp: fused skip projection on a conv with a time-embedding bias"); rc = 2; return; }

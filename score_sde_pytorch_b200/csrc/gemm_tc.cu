@@ -40,9 +40,23 @@ constexpr int BM = 128;          // rows (pixels) per tile == UMMA M
 constexpr int BKE = 32;          // fp32 elements per K step == one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BKE * 4;   // 16 KiB
 
+// Halo form of the 3x3 mainloop.  The nine filter taps of one channel chunk read three W-shifted
+// copies of the tile *with its one-row halo* (TMA box [chunk, W, rows + 2], origin w = -1 / 0 / +1, zero fill outside the
+// image); the operand of tap (dh, dw) is copy[dw] starting (dh + 1) * W pixels in - a multiple of 1024 bytes, so a plain
+// swizzled descriptor.  L2 -> shared-memory traffic per chunk: 3 x (rows + 2) / rows tiles instead of 9.
+constexpr int HALO_XS = 4;                  // halo copies in flight (both kernels)
+constexpr int HALO_X_BYTES = 40 * 1024;     // single-CTA swapped form: (8 + 2) rows x 32 pixels x 128 B
+constexpr int HALO_WS = 4;                  //   its weight-slice ring: 4 x 16 KB   (4 x 40 + 4 x 16 = 224 KB = the plain form's footprint)
+constexpr int HALO2_X_BYTES = 24 * 1024;    // CTA pair: (4 + 2) rows x 32 pixels x 128 B per CTA
+constexpr int HALO2_WS = 6;                 //   its weight-half ring: 6 x 16 KB   (4 x 24 + 6 x 16 = 192 KB = the plain form's stages)
+
 struct TcParams {
   CUtensorMap tmA1, tmA2, tmW;
   CUtensorMap tmA3, tmA4, tmW2;            // optional extra 1x1 K phase (fused skip projection): out += [A3|A4] W2^T
+  CUtensorMap tmH1, tmH2;                  // halo form: box = [bke channels, W, tile rows + 2, 1] of the two filter sources
+  int halo;                                // 1: 3x3 taps read W-shifted halo copies of the tile (3 loads per channel chunk instead of 9)
+  int halo_dh_bytes;                       // W * 128: bytes between the operand windows of consecutive filter rows inside a copy
+  int halo_copy_bytes;                     // (tile rows + 2) * W * 128: bytes of one halo copy
   int conv, H, W, taps, pad, S, stride;   // H, W: OUTPUT spatial size; S = filter width (3 or 1)
   int kchunks1, kchunks2, C1;
   int kchunks3, kchunks4, C3;              // extra phase: channel chunks of its (two-source) input
@@ -414,11 +428,14 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* wfull_bar = tmem_empty + 3;          // halo form: the weight-slice ring has its own barriers
+  uint64_t* wempty_bar = wfull_bar + HALO_WS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < HALO_WS; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
     // one arrival per epilogue warp (384 threads: two warps per TMEM lane quarter)
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], (blockDim.x >> 5) - 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -441,6 +458,53 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
   if (warp == 0 && lane == 0) {
     // ======================= TMA producer =======================
     uint32_t stage = 0, phase = 0;
+    if (BN == 256 && p.halo) {
+      // halo form (swapped operands, one image per 256-pixel tile, W <= 32): per channel chunk three halo copies, each
+      // followed by the three 16 KB weight slices of its filter column
+      uint32_t ws = 0, wphase = 0;
+      uint8_t* const wring = smem + HALO_XS * HALO_X_BYTES;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % p.tiles_n);
+        const long long p0 = (tile / p.tiles_n) * 256;
+        const int img0 = (int)(p0 / HW), h0 = (int)(p0 % HW) / p.W;
+        const int wrow0 = nt * 128;
+        for (int src = 0; src < 4; ++src) {
+          const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
+          if (nch == 0) continue;
+          const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
+          for (int kc = 0; kc < nch; ++kc) {
+            if (src < 2) {
+              const CUtensorMap* tmH = src == 0 ? &p.tmH1 : &p.tmH2;
+              for (int dwi = 0; dwi < 3; ++dwi) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], (uint32_t)p.halo_copy_bytes);
+                tma_load_4d(tmH, smem + stage * HALO_X_BYTES, &full_bar[stage], kc * bke, dwi - 1, h0 - 1, img0);
+                if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
+                for (int dhi = 0; dhi < 3; ++dhi) {
+                  mbar_wait(&wempty_bar[ws], wphase ^ 1);
+                  mbar_expect_tx(&wfull_bar[ws], A_STAGE_BYTES);
+                  tma_load_2d(&p.tmW, wring + ws * A_STAGE_BYTES, &wfull_bar[ws], wcol0 + kc * bke, wrow0 + (dhi * 3 + dwi) * p.N_total);
+                  if (++ws == HALO_WS) { ws = 0; wphase ^= 1; }
+                }
+              }
+            } else {
+              // extra 1x1 phase (fused skip projection): the plain 256-pixel tile as two 128-pixel boxes, its own weights
+              const CUtensorMap* tmA = src == 2 ? &p.tmA3 : &p.tmA4;
+              const int h1 = h0 + 128 / p.W;
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
+              tma_load_4d(tmA, smem + stage * HALO_X_BYTES, &full_bar[stage], kc * bke, 0, h0, img0);
+              tma_load_4d(tmA, smem + stage * HALO_X_BYTES + A_STAGE_BYTES, &full_bar[stage], kc * bke, 0, h1, img0);
+              if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
+              mbar_wait(&wempty_bar[ws], wphase ^ 1);
+              mbar_expect_tx(&wfull_bar[ws], A_STAGE_BYTES);
+              tma_load_2d(&p.tmW2, wring + ws * A_STAGE_BYTES, &wfull_bar[ws], wcol0 + kc * bke, wrow0);
+              if (++ws == HALO_WS) { ws = 0; wphase ^= 1; }
+            }
+          }
+        }
+      }
+    } else
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % p.tiles_n);
       const long long mg = tile / p.tiles_n;
@@ -497,6 +561,41 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
     const bool f16 = p.f16 != 0;
     const uint32_t idesc = f16 ? make_idesc_f16<BN>() : make_idesc<BN>();
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    if (BN == 256 && p.halo) {
+      // halo form: A = the 16 KB weight slice (128 output channels), B = 256 pixel rows of a halo copy starting one filter
+      // row (W pixels) further in per dh; the slice's slot is released per tap, the copy's after its three taps
+      uint32_t ws = 0, wphase = 0;
+      const uint32_t wring = smem_u32(smem + HALO_XS * HALO_X_BYTES);
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        int it = 0;
+        for (int src = 0; src < 4; ++src) {
+          const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
+          const int ncopies = src < 2 ? 3 * nch : nch, ntap = src < 2 ? 3 : 1;
+          for (int c = 0; c < ncopies; ++c) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sx = smem_u32(smem + stage * HALO_X_BYTES);
+            for (int dhi = 0; dhi < ntap; ++dhi, ++it) {
+              mbar_wait(&wfull_bar[ws], wphase);
+              tc_fence_after();
+              const uint64_t adesc = make_smem_desc(wring + ws * A_STAGE_BYTES);
+              const uint64_t bdesc = make_smem_desc(sx + (src < 2 ? dhi * p.halo_dh_bytes : 0));
+              if (f16) umma_kstep<true>(d_tmem, adesc, bdesc, idesc, it);
+              else umma_kstep<false>(d_tmem, adesc, bdesc, idesc, it);
+              umma_commit(&wempty_bar[ws]);
+              if (++ws == HALO_WS) { ws = 0; wphase ^= 1; }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    } else
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -816,6 +915,30 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
   }
   if (!d.a2) p.tmA2 = p.tmA1;
   p.tmA3 = p.tmA1; p.tmA4 = p.tmA1;
+  p.tmH1 = p.tmA1; p.tmH2 = p.tmA1;
+  {
+    // Halo form: 'same'-padded stride-1 3x3 filters on 16- or 32-pixel-wide images, where the CTA's tile
+    // (256 pixels swapped, 128 pixels per CTA of a pair) is whole rows of ONE image: 3 loads of (rows + 2) x W pixels per
+    // channel chunk instead of 9 loads of rows x W - the plain form is bound by the L2 -> SM fill rate, not the tensor pipe.
+    const int tile_px = p.swap ? 256 : BM;
+    const bool halo = !d.no_halo && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (p.swap || pl->two_cta) &&
+                      (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 && (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W);
+    if (halo) {
+      const int rows = tile_px / d.W;
+      p.halo = 1; p.halo_dh_bytes = d.W * 128; p.halo_copy_bytes = (rows + 2) * d.W * 128;
+      B200_REQUIRE(p.halo_copy_bytes <= (p.swap ? HALO_X_BYTES : HALO2_X_BYTES), "gemm_tc: halo copy of %d bytes does not fit its slot", p.halo_copy_bytes);
+      uint32_t box[4] = {(uint32_t)bke, (uint32_t)d.W, (uint32_t)(rows + 2), 1};
+      for (int s = 0; s < 2; ++s) {
+        const float* base = s ? d.a2 : d.a1;
+        const int C = s ? d.C2 : d.C1;
+        if (!base) continue;
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.nimg};
+        uint64_t str[3] = {(uint64_t)C * es, (uint64_t)d.W * C * es, (uint64_t)d.H * d.W * C * es};
+        rc = encode_map(s ? &p.tmH2 : &p.tmH1, base, 4, dims, str, box, nullptr, f16);
+        if (rc) { delete pl; return rc; }
+      }
+    }
+  }
   if (d.a3) {
     // extra 1x1 phase: same pixel box as the main input (stride 1, same spatial size), its own channel counts
     const int HW = d.H * d.W;
@@ -856,8 +979,8 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 const char* tc_gemm_form(const TcGemmPlan* p) {
-  if (p->two_cta) return "pair256";
-  if (p->prm.swap) return "swap";
+  if (p->two_cta) return p->prm.halo ? "pair256-halo" : "pair256";
+  if (p->prm.swap) return p->prm.halo ? "swap-halo" : "swap";
   return p->bn == 256 ? "single256" : "single128";
 }
 void tc_gemm_set_rowvec_ld(TcGemmPlan* p, long long ld) { p->prm.epi.rowvec_ld = ld; }

@@ -79,6 +79,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;                                     // used in the leader only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* wfull_bar = tmem_empty + 3;                                     // halo form: barriers of the weight-half ring
+  uint64_t* wempty_bar = wfull_bar + HALO2_WS;
+  static_assert((2 * STAGES + 4 + 1 + 2 * HALO2_WS) * 8 <= 256 && STAGES >= HALO_XS, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -86,6 +89,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // full: one arrive per CTA
+    for (int s = 0; s < HALO2_WS; ++s) { mbar_init(&wfull_bar[s], 2); mbar_init(&wempty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }     // empty: 8 warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -111,6 +115,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   if (warp == 0 && lane == 0) {
     // ======================= TMA producer (both CTAs) =======================
     uint32_t stage = 0, phase = 0;
+    if (p.halo) {
+      // halo form (see gemm_tc_kernel): per channel chunk three halo copies of this CTA's 128 pixels (whole rows of one
+      // image), each followed by this CTA's half of the three weight slices of that filter column
+      uint32_t ws = 0, wphase = 0;
+      uint8_t* const wring = smem + HALO_XS * HALO2_X_BYTES;
+      for (long long pair = cid; pair < total_pairs; pair += nclusters) {
+        const int nt = (int)(pair % p.tiles_n);
+        const long long mg = (pair / p.tiles_n) * 2 + rank;
+        const long long p0 = mg * BM;
+        const int img0 = mg >= tiles_m_total ? (1 << 28) : (int)(p0 / HW);      // past the end -> TMA zero fill
+        const int h0 = (int)(p0 % HW) / p.W;
+        const int wrow0 = nt * BN + (int)rank * (BN / 2);
+        for (int src = 0; src < 4; ++src) {
+          const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
+          if (nch == 0) continue;
+          const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
+          for (int kc = 0; kc < nch; ++kc) {
+            const int ncopy = src < 2 ? 3 : 1;
+            for (int dwi = 0; dwi < ncopy; ++dwi) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint32_t lead = map_to_cta(smem_u32(&full_bar[stage]), 0);
+              if (src < 2) {
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * (uint32_t)p.halo_copy_bytes);
+                tma2_load_4d(src == 0 ? &p.tmH1 : &p.tmH2, smem + stage * HALO2_X_BYTES, lead, kc * p.bke, dwi - 1, h0 - 1, img0);
+              } else {
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
+                tma2_load_4d(src == 2 ? &p.tmA3 : &p.tmA4, smem + stage * HALO2_X_BYTES, lead, kc * p.bke, 0, h0, img0);
+              }
+              if (!leader) mbar_arrive_cluster(lead);
+              if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
+              const int ntap = src < 2 ? 3 : 1;
+              for (int dhi = 0; dhi < ntap; ++dhi) {
+                mbar_wait(&wempty_bar[ws], wphase ^ 1);
+                lead = map_to_cta(smem_u32(&wfull_bar[ws]), 0);
+                if (leader) mbar_expect_tx(&wfull_bar[ws], 2 * A_STAGE_BYTES);
+                if (src < 2) tma2_load_2d(&p.tmW, wring + ws * A_STAGE_BYTES, lead, wcol0 + kc * p.bke, wrow0 + (dhi * 3 + dwi) * p.N_total);
+                else tma2_load_2d(&p.tmW2, wring + ws * A_STAGE_BYTES, lead, wcol0 + kc * p.bke, wrow0);
+                if (!leader) mbar_arrive_cluster(lead);
+                if (++ws == HALO2_WS) { ws = 0; wphase ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    } else
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
       const int nt = (int)(pair % p.tiles_n);
       const long long mg = (pair / p.tiles_n) * 2 + rank;      // this CTA's 128-row tile (may be one past the end)
@@ -157,6 +206,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
     const bool f16 = p.f16 != 0;
     const uint32_t idesc = (1u << 4) | (f16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    if (p.halo) {
+      // halo form: A = 128 pixel rows of the halo copy starting one filter row further in per dh (same offset in both
+      // CTAs), B = the pair's two weight halves; slices are released per tap, a copy after its three taps
+      uint32_t ws = 0, wphase = 0;
+      const uint32_t wring = smem_u32(smem + HALO_XS * HALO2_X_BYTES);
+      for (long long pair = cid; pair < total_pairs; pair += nclusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        int it = 0;
+        for (int src = 0; src < 4; ++src) {
+          const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
+          const int ncopies = src < 2 ? 3 * nch : nch, ntap = src < 2 ? 3 : 1;
+          for (int c = 0; c < ncopies; ++c) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sx = smem_u32(smem + stage * HALO2_X_BYTES);
+            for (int dhi = 0; dhi < ntap; ++dhi, ++it) {
+              mbar_wait(&wfull_bar[ws], wphase);
+              tc_fence_after();
+              const uint64_t adesc = make_smem_desc(sx + (src < 2 ? dhi * p.halo_dh_bytes : 0));
+              const uint64_t bdesc = make_smem_desc(wring + ws * A_STAGE_BYTES);
+              if (f16) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+              }
+              umma2_commit_mc(&wempty_bar[ws]);
+              if (++ws == HALO2_WS) { ws = 0; wphase ^= 1; }
+            }
+            umma2_commit_mc(&empty_bar[stage]);
+            if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma2_commit_mc(&tmem_full[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    } else
     for (long long pair = cid; pair < total_pairs; pair += nclusters) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();

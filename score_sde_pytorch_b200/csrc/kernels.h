@@ -101,6 +101,7 @@ struct TcGemmDesc {
   const float* a3; int C3; const float* a4; int C4; const float* w2;
   int f16;                  // 1: a1..a4, w, w2 hold fp16 elements (tcgen05 kind::f16, 64-channel K steps); pitches stay in elements
   int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
+  int no_halo;              // 1 = never use the halo form of the 3x3 mainloop (nine shifted tile loads per channel chunk instead)
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
   Epilogue epi;
 };
@@ -146,7 +147,7 @@ int tcg_plan_create(const TcgDesc& d, TcgPlan** out);
 void tcg_plan_destroy(TcgPlan* p);
 int tcg_launch(const TcgPlan* p, cudaStream_t st);
 void tc_gemm_set_head(TcGemmPlan* p, float* out_nchw, const float* per_img_div, long long div_stride);   // per-call pointers of the NCHW head
-const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256" | "single256" | "single128" | "swap"
+const char* tc_gemm_form(const TcGemmPlan* p);   // "pair256[-halo]" | "single256" | "single128" | "swap[-halo]"
 
 // ---- pc_update.cu -----------------------------------------------------------
 struct PhiloxMap {          // torch.randn_like's launch geometry for `numel` elements

@@ -24,6 +24,7 @@ from . import utils
 from .. import _lib
 
 PDL_DEFAULT = False
+HALO_DEFAULT = True
 
 _SUPPORTED = ("engine supports embedding_type in {'fourier','positional'}, conditional=True, resblock_type='biggan', "
               "fir in {True, False} (progressive_input='residual' needs fir=True), progressive in {'none','output_skip'}, "
@@ -119,7 +120,7 @@ class NCSNpp(nn.Module):
   MMA rate) or ``'fp32'`` (strict fp32 on CUDA cores; validation mode)."""
 
   def __init__(self, config, precision=None, keep_activations=False, lanes=1, cuda_core_head=None,
-               separate_groupnorm=None, pdl=None):
+               separate_groupnorm=None, pdl=None, halo=None):
     super().__init__()
     self.config = config
     m = config.model
@@ -151,6 +152,9 @@ class NCSNpp(nn.Module):
     self.separate_groupnorm = 2 if (not isinstance(sg, bool) and sg == 2) else bool(sg)
     # programmatic dependent launch between the kernels of a forward / PC iteration (common.cuh)
     self.pdl = bool(getattr(m, 'pdl', PDL_DEFAULT) if pdl is None else pdl)
+    # halo form of the 3x3 tensor-core mainloop (csrc/gemm_tc.cu); False = nine shifted tile loads per
+    # channel chunk (the round-1 mainloop, kept for A/B)
+    self.halo = bool(getattr(m, 'halo', HALO_DEFAULT) if halo is None else halo)
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
     L = len(ch_mult)
     all_res = [config.data.image_size // (2 ** i) for i in range(L)]
@@ -232,6 +236,7 @@ class NCSNpp(nn.Module):
     c.progressive_input = {'none': 0, 'residual': 1, 'input_skip': 2}[m.progressive_input.lower()]
     c.progressive = 1 if m.progressive.lower() == 'output_skip' else 0
     c.pdl = int(self.pdl)
+    c.no_halo = int(not self.halo)
     c.fir_taps = len(m.fir_kernel)
     for i, v in enumerate(m.fir_kernel):
       c.fir_kernel[i] = float(v)

@@ -35,6 +35,11 @@ CASES = [
     dict(B=1, H=8, W=256, C1=32, C2=0, Cout=128, k=3),     # width > 128: column tiles
     dict(B=40, H=16, W=16, C1=128, C2=0, Cout=256, k=3),   # > 148 tiles? (80 tiles) multi-wave accum ping-pong
     dict(B=160, H=16, W=16, C1=32, C2=0, Cout=128, k=3),   # 320 tiles on 148 CTAs: persistent loop, both TMEM stages reused
+    # halo form of the 3x3 mainloop (three W-shifted halo copies per channel chunk): swapped, and CTA pairs at both widths
+    dict(B=2, H=32, W=32, C1=256, C2=128, Cout=128, k=3),  # swapped, two sources, 6 (f16) / 12 (tf32) chunks
+    dict(B=4, H=16, W=16, C1=128, C2=0, Cout=128, k=3),    # swapped, 16-pixel rows: one whole image per tile
+    dict(B=160, H=16, W=16, C1=256, C2=0, Cout=256, k=3),  # 160 CTA pairs on 74 clusters: each CTA half an image
+    dict(B=20, H=32, W=32, C1=256, C2=128, Cout=256, k=3), # pairs at 32-pixel rows (4 rows per CTA), two sources
 ]
 
 
@@ -152,6 +157,40 @@ def test_tcgen05_f16_conv_matches_torch(dev, case):
   xc = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], 3)
   tref = (F.conv2d(xc.permute(0, 3, 1, 2), w, bias, padding=k // 2).permute(0, 2, 3, 1) + rowvec[:, None, None, :] + res) * 0.7071067690849304
   assert torch.allclose(y, tref, rtol=2e-4, atol=2e-4), (y - tref).abs().max().item()
+
+
+HALO_CASES = [c for c in CASES if c['k'] == 3 and c['W'] in (16, 32) and (c['Cout'] == 128 or c['B'] * c['H'] * c['W'] >= 148 * 128)]
+
+
+@pytest.mark.parametrize('f16', [False, True], ids=['tf32', 'f16'])
+@pytest.mark.parametrize('case', HALO_CASES, ids=lambda c: 'B{B}_{H}x{W}_{C1}+{C2}->{Cout}_k{k}'.format(**c))
+def test_halo_mainloop_equals_nine_load_mainloop(dev, case, f16):
+  """impl 1 / 2 take the halo form where the shape allows (these shapes do), impl 4 / 5 force one shifted tile load per
+  filter tap.  Same operands, same products; only the order of the K loop differs (chunk-major vs tap-major), i.e. fp32
+  summation order."""
+  import gpu_util
+  B, H, W, C1, C2, Cout, k = (case[x] for x in ('B', 'H', 'W', 'C1', 'C2', 'Cout', 'k'))
+  if f16 and (C1 % 64 or C2 % 64):
+    pytest.skip('fp16 operands need 64-channel chunks')
+  torch.manual_seed(26)
+  cvt = (lambda t: t.half()) if f16 else gpu_util.round_tf32
+  x1 = cvt(torch.randn(B, H, W, C1, device=dev))
+  x2 = cvt(torch.randn(B, H, W, C2, device=dev)) if C2 else None
+  w = torch.randn(Cout, C1 + C2, k, k, device=dev) / np.sqrt((C1 + C2) * k * k)
+  w = w.half().float() if f16 else gpu_util.round_tf32(w)
+  wp = gpu_util.pack_conv_weight(w, f16=True) if f16 else gpu_util.pack_conv_weight(w)
+  bias = torch.randn(Cout, device=dev)
+  res = torch.randn(B, H, W, Cout, device=dev)
+  kw = dict(residual=res, scale=0.7071067690849304)
+  y_halo = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=2 if f16 else 1, **kw)
+  y_nine = gpu_util.conv_nhwc(x1, x2, wp, bias, Cout, k, impl=5 if f16 else 4, **kw)
+  torch.cuda.synchronize()
+  err = (y_halo - y_nine).abs().max().item()
+  print(f'halo vs nine-load mainloop {"f16" if f16 else "tf32"} B{B} {H}x{W} {C1}+{C2}->{Cout}: max abs diff {err:.2e}')
+  assert torch.allclose(y_halo, y_nine, rtol=1e-5, atol=2e-5), err
+  # borders are where the two forms differ in mechanism (zero fill of a shifted tile vs of a halo copy): check them alone
+  for sl in (y_halo[:, 0] - y_nine[:, 0], y_halo[:, -1] - y_nine[:, -1], y_halo[:, :, 0] - y_nine[:, :, 0], y_halo[:, :, -1] - y_nine[:, :, -1]):
+    assert sl.abs().max().item() <= 2e-5 + 1e-5 * y_nine.abs().max().item()
 
 
 SKIP_CASES = [
