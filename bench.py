@@ -577,16 +577,17 @@ def run_gpu_arm(args):
         variants['f16_pdl_' + ('off' if model.pdl else 'on')] = dict(value=round(B / (N_SAMPLER_STEPS * ms4 * 1e-3), 4), unit='images/s',
                                                                    ms_per_step=round(ms4, 4))
         del plan4, model4
-        # A/B of the halo form of the 3x3 mainloop (headline: package default) against one shifted tile load per filter tap
-        torch.manual_seed(0)
-        model5 = NCSNpp(cfg, precision='f16', separate_groupnorm=args.separate_groupnorm, halo=not model.halo).to(dev)
-        plan5 = native.match_pc_plan(sde=sde, model=model5, predictor=sampling.ReverseDiffusionPredictor,
-                                     corrector=sampling.LangevinCorrector, shape=shape, snr=cfg.sampling.snr, n_steps=1,
-                                     probability_flow=False, continuous=True, eps=1e-5, device=dev)
-        ms5 = timed_steps(plan5, x_host.to(dev), args.warmup, args.steps)
-        variants['f16_halo_' + ('off' if model.halo else 'on')] = dict(value=round(B / (N_SAMPLER_STEPS * ms5 * 1e-3), 4), unit='images/s',
-                                                                     ms_per_step=round(ms5, 4))
-        del plan5, model5
+        # A/B of the halo form of the 3x3 mainloop (headline: package default = swapped-form convolutions only) against one
+        # shifted tile load per filter tap, and against the halo form in the CTA-pair kernel as well
+        for hv, key in ((False, 'f16_halo_off'), ('pairs', 'f16_halo_pairs_too')):
+          torch.manual_seed(0)
+          model5 = NCSNpp(cfg, precision='f16', separate_groupnorm=args.separate_groupnorm, halo=hv).to(dev)
+          plan5 = native.match_pc_plan(sde=sde, model=model5, predictor=sampling.ReverseDiffusionPredictor,
+                                       corrector=sampling.LangevinCorrector, shape=shape, snr=cfg.sampling.snr, n_steps=1,
+                                       probability_flow=False, continuous=True, eps=1e-5, device=dev)
+          ms5 = timed_steps(plan5, x_host.to(dev), args.warmup, args.steps)
+          variants[key] = dict(value=round(B / (N_SAMPLER_STEPS * ms5 * 1e-3), 4), unit='images/s', ms_per_step=round(ms5, 4))
+          del plan5, model5
     # ---- strong-scaling probe: the same 1024-image job cut over 8 GPUs is 128 images per GPU; time that
     # per-GPU share here and name the launches that under-fill the 148 SMs ----
     strong = None
@@ -627,7 +628,7 @@ def run_gpu_arm(args):
                             weights='random init, init_scale=1, torch.manual_seed(0)', precision=args.precision,
                             groupnorm='separate streaming pass' if args.separate_groupnorm else
                             'applied on load by the consuming convolution where supported (256-channel outputs at 16x16 / 32x32), separate pass elsewhere',
-                            conv3x3_mainloop='halo form (three W-shifted halo copies per channel chunk)' if model.halo else 'one shifted tile load per filter tap'),
+                            conv3x3_mainloop={True: 'halo form (three W-shifted halo copies per channel chunk) in the swapped kernel, one shifted tile per tap in CTA pairs', False: 'one shifted tile load per filter tap', 'pairs': 'halo form in swapped and CTA-pair kernels'}[model.halo]),
                 clocks=clk,
                 e2e=dict(value=round(e2e_value, 4), unit='images/s', h2d_bytes_per_step=int(np.prod(shape)) * 4,
                          d2h_bytes_per_step=int(np.prod(shape)) * 4, ms_per_step=round(ms_e2e / e2e_steps, 4)),

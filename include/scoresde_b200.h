@@ -69,7 +69,8 @@ B200_API int b200_randn_like_torch_f32(float* out, long long numel, unsigned lon
  * 3 = warp-level TF32 MMAs for few-channel layers (c1, c2 multiples of 16, c_out 16 / 32 / 64, h % 8 == 0, w % 32 == 0):
  *     fp32 in and out, operands rounded to the TF32 grid while staged (the 16..64-channel levels of the nf = 16
  *     high-resolution networks, configs/ve/ffhq_ncsnpp_continuous.py:71-94);
- * 4 / 5 = as 1 / 2 with the halo form of the 3x3 mainloop disabled (nine shifted tile loads per channel chunk): A/B checks. */
+ * 4 / 5 = as 1 / 2 with the halo form of the 3x3 mainloop disabled (nine shifted tile loads per channel chunk), 6 / 7 = as 1 / 2
+ *     with the halo form in the CTA-pair kernel as well (b200_ncsnpp_config.no_halo = 1 / 2): A/B checks, bit-identical results. */
 B200_API int b200_conv_nhwc_f32(const float* x1, int c1, const float* x2, int c2, int batch, int h, int w,
                                 const float* w_packed, const float* bias, int c_out, int ksize,
                                 const float* rowvec, long long rowvec_ld, const float* residual, float scale,
@@ -136,9 +137,12 @@ typedef struct {
   int pdl;                      /* 1: every launch of a forward / PC iteration carries the programmatic-dependent-launch attribute
                                  * (each kernel waits for its predecessor with griddepcontrol.wait after its own prologue, so launch
                                  * latency, barrier init and TMEM allocation of kernel k+1 overlap the tail of kernel k) */
-  int no_halo;                  /* 0 (default): 3x3 convolutions on 16- / 32-pixel-wide images read three W-shifted halo copies of
-                                 * their tile per channel chunk (csrc/gemm_tc.cu "halo form": 2.4x fewer L2 -> shared-memory bytes
-                                 * than one shifted tile per filter tap); 1: the nine-loads-per-chunk mainloop of round 1, kept for A/B */
+  int no_halo;                  /* 0 (default): swapped-form 3x3 convolutions (128 output channels) on 16- / 32-pixel-wide images read
+                                 * three W-shifted halo copies of their tile per channel chunk (csrc/gemm_tc.cu "halo form": 2.4x fewer
+                                 * L2 -> shared-memory bytes than one shifted tile per filter tap; measured +5..10 % on those launches);
+                                 * 1: one shifted tile per tap everywhere (the round-1 mainloop, kept for A/B); 2: halo form in the
+                                 * CTA-pair kernel as well (measured 5..13 % SLOWER there - DESIGN.md section 4.13).  All three add the
+                                 * same products in the same order: results are bit-identical. */
 } b200_ncsnpp_config;
 
 B200_API int b200_ncsnpp_create(const b200_ncsnpp_config* cfg, b200_ncsnpp_t** out);

@@ -534,9 +534,12 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
         const CUtensorMap* tmW = src < 2 ? &p.tmW : &p.tmW2;
         const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
         const int ntaps = src < 2 ? p.taps : 1;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
-          for (int kc = 0; kc < nch; ++kc) {
+        // K order: channel chunk, then filter column, then filter row - the order of the halo form, so that every form of
+        // a convolution adds the same products in the same order (plans for different batch sizes agree bit for bit)
+        for (int kc = 0; kc < nch; ++kc) {
+          for (int t = 0; t < ntaps; ++t) {
+            const int tap = ntaps == 1 ? 0 : (t % p.S) * p.S + t / p.S;
+            const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
@@ -921,7 +924,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // (256 pixels swapped, 128 pixels per CTA of a pair) is whole rows of ONE image: 3 loads of (rows + 2) x W pixels per
     // channel chunk instead of 9 loads of rows x W - the plain form is bound by the L2 -> SM fill rate, not the tensor pipe.
     const int tile_px = p.swap ? 256 : BM;
-    const bool halo = !d.no_halo && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (p.swap || pl->two_cta) &&
+    const bool halo = d.no_halo != 1 && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (p.swap || (pl->two_cta && d.no_halo == 2)) &&
                       (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 && (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W);
     if (halo) {
       const int rows = tile_px / d.W;

@@ -183,9 +183,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         const CUtensorMap* tmW = src < 2 ? &p.tmW : &p.tmW2;
         const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
         const int ntaps = src < 2 ? p.taps : 1;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
-          for (int kc = 0; kc < nch; ++kc) {
+        for (int kc = 0; kc < nch; ++kc) {                       // K order: chunk, filter column, filter row (see gemm_tc_kernel)
+          for (int t = 0; t < ntaps; ++t) {
+            const int tap = ntaps == 1 ? 0 : (t % p.S) * p.S + t / p.S;
+            const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);            // own smem slot released by the pair's MMA commit
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
