@@ -247,6 +247,21 @@ B200_API int b200_ode_error_sumsq_f64(const double* y, const double* y_new, cons
 B200_API int b200_ode_scaled_sumsq_f64(const double* v, const double* v2, const double* y0, long long n, double rtol, double atol,
                                        double* ws, void* stream);
 
+/* ---- denoising score matching losses: the evaluation step ---------------------------------------
+ * Device pieces of losses.py:55-150 (get_sde_loss_fn / get_smld_loss_fn / get_ddpm_loss_fn) around the engine's network
+ * evaluation, used by score_sde_pytorch_b200/losses.py.  Per-image scalars are device arrays [nimg] computed with the SDE's own
+ * torch ops (sde.marginal_prob, sde.sde), as the reference does. */
+/* out = mean_coef[img] * x + noise_coef[img] * z (mean_coef NULL: 1): losses.py:86-87, :111-112, :133-134; separate fp32
+ * roundings like the reference's unfused torch ops, i.e. bit-equal to it */
+B200_API int b200_dsm_perturb_f32(const float* x, const float* z, const float* mean_coef, const float* noise_coef, float* out,
+                                  int nimg, long long n_per_img, void* stream);
+/* losses[img] = reduce(residual^2) over the image, reduce = mean (reduce_mean != 0) or 0.5 * sum (losses.py:71); residual by
+ * mode: 0 score * w + z (:90), 1 score + z / w (:94), 2 score + (z * w) / w2 (SMLD, w = sigma, w2 = sigma^2, :110-115),
+ * 3 score - z (DDPM, :136).  ws: b200_dsm_workspace_doubles(nimg, n_per_img) doubles; deterministic fixed-order fp64 sums. */
+B200_API long long b200_dsm_workspace_doubles(int nimg, long long n_per_img);
+B200_API int b200_dsm_loss_f32(const float* score, const float* z, const float* w, const float* w2, float* losses, int nimg,
+                               long long n_per_img, int mode, int reduce_mean, double* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

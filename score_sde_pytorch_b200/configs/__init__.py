@@ -45,6 +45,8 @@ def cifar10_defaults():
                       random_flip=True, uniform_dequantization=False)
   c.model = ConfigDict(sigma_min=0.01, sigma_max=50, num_scales=1000, beta_min=0.1,
                        beta_max=20., dropout=0.1, embedding_type='fourier')
+  # configs/default_cifar10_configs.py:59-67 - read by losses.get_optimizer / optimization_manager
+  c.optim = ConfigDict(weight_decay=0, optimizer='Adam', lr=2e-4, beta1=0.9, eps=1e-8, warmup=5000, grad_clip=1.)
   c.seed = 42
   c.device = _default_device()
   return c

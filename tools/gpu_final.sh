@@ -13,6 +13,10 @@ timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc -s 3 -c 8 -f -o gpurun_out/ncu_gemm_${TAG} \
   python tools/ncu_step.py --batch 1024 > gpurun_out/ncu_gemm_${TAG}.log 2>&1; echo "ncu --set full exit $?" >> $S
 timeout 300 python tools/profile_ops.py --batch 1024 --md gpurun_out/ops_${TAG}.md > /dev/null 2> gpurun_out/ops_${TAG}.err; echo "profile_ops exit $?" >> $S
+# memcheck over the halo-form convolutions (new shared-memory layout, halo TMA boxes) and the loss / op-gradient kernels
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_tc.py tests/test_gpu_f4.py -q -m gpu -x --tb=line \
+  -p no:cacheprovider -k "(halo_mainloop and not B160 and not B20) or upfirdn2d_first or fused_leaky or ddpm_evaluation" > gpurun_out/memcheck_${TAG}.log 2>&1
+echo "memcheck exit $?; $(grep -h 'passed\|failed' gpurun_out/memcheck_${TAG}.log | tail -1); $(grep -h 'ERROR SUMMARY' gpurun_out/memcheck_${TAG}.log | tail -1)" >> $S
 cat $S; grep -h "passed\|failed\|error" gpurun_out/pytest_${TAG}.log | tail -3; grep -h "smoke ok" gpurun_out/smoke_$TAG.log
 python - <<PY
 import json
