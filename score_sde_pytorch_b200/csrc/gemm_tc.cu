@@ -57,6 +57,8 @@ struct TcParams {
   int halo;                                // 1: 3x3 taps read W-shifted halo copies of the tile (3 loads per channel chunk instead of 9)
   int halo_dh_bytes;                       // W * 128: bytes between the operand windows of consecutive filter rows inside a copy
   int halo_copy_bytes;                     // (tile rows + 2) * W * 128: bytes of one halo copy
+  int halo_prefetch;                       // 1: the halo producers prefetch the next tile's halo boxes (all channel chunks) into L2
+  int chunk_major;                         // nine-load loop of the single-CTA kernel walks K as (chunk, filter column, filter row): shapes with a halo form
   int conv, H, W, taps, pad, S, stride;   // H, W: OUTPUT spatial size; S = filter width (3 or 1)
   int kchunks1, kchunks2, C1;
   int kchunks3, kchunks4, C3;              // extra phase: channel chunks of its (two-source) input
@@ -115,6 +117,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, ui
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// fire-and-forget: pull a 4-D box towards L2 (UTMAPF); the halo producers use it for the NEXT tile's whole channel vector so
+// that DRAM sees each pixel row once, contiguously, instead of one 128-byte chunk per K phase
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -468,6 +476,12 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
         const long long p0 = (tile / p.tiles_n) * 256;
         const int img0 = (int)(p0 / HW), h0 = (int)(p0 % HW) / p.W;
         const int wrow0 = nt * 128;
+        if (p.halo_prefetch && tile + gridDim.x < p.total_tiles && (tile + gridDim.x) / p.tiles_n != tile / p.tiles_n) {
+          const long long q0 = ((tile + gridDim.x) / p.tiles_n) * 256;                 // next tile of this CTA: its pixels, every chunk
+          const int qi = (int)(q0 / HW), qh = (int)(q0 % HW) / p.W;
+          for (int kc = 0; kc < p.kchunks1; ++kc) tma_prefetch_4d(&p.tmH1, kc * bke, 0, qh - 1, qi);
+          for (int kc = 0; kc < p.kchunks2; ++kc) tma_prefetch_4d(&p.tmH2, kc * bke, 0, qh - 1, qi);
+        }
         for (int src = 0; src < 4; ++src) {
           const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
           if (nch == 0) continue;
@@ -534,11 +548,16 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
         const CUtensorMap* tmW = src < 2 ? &p.tmW : &p.tmW2;
         const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
         const int ntaps = src < 2 ? p.taps : 1;
-        // K order: channel chunk, then filter column, then filter row - the order of the halo form, so that every form of
-        // a convolution adds the same products in the same order (plans for different batch sizes agree bit for bit)
-        for (int kc = 0; kc < nch; ++kc) {
-          for (int t = 0; t < ntaps; ++t) {
-            const int tap = ntaps == 1 ? 0 : (t % p.S) * p.S + t / p.S;
+        // K order.  Default: filter tap, then channel chunk - consecutive loads sweep the channel vector of the same shifted
+        // pixels (contiguous 128-byte segments of every pixel row; measured ~30 % faster than the other order in the
+        // CTA-pair kernel, profiles/r02_f3_*).  Shapes that have a halo form (p.chunk_major) walk K the way that form must -
+        // channel chunk, filter column, filter row - so that halo on / off add the same products in the same order and
+        // are bit-identical (the nine-load loop of such a shape only runs in A/B checks).
+        const int nouter = p.chunk_major ? nch : ntaps, ninner = p.chunk_major ? ntaps : nch;
+        for (int o = 0; o < nouter; ++o) {
+          for (int i = 0; i < ninner; ++i) {
+            const int kc = p.chunk_major ? o : i, t = p.chunk_major ? i : o;
+            const int tap = (ntaps == 1 || !p.chunk_major) ? t : (t % p.S) * p.S + t / p.S;
             const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -924,11 +943,15 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     // (256 pixels swapped, 128 pixels per CTA of a pair) is whole rows of ONE image: 3 loads of (rows + 2) x W pixels per
     // channel chunk instead of 9 loads of rows x W - the plain form is bound by the L2 -> SM fill rate, not the tensor pipe.
     const int tile_px = p.swap ? 256 : BM;
-    const bool halo = d.no_halo != 1 && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (p.swap || (pl->two_cta && d.no_halo == 2)) &&
+    const bool halo = (d.no_halo & 3) != 1 && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (p.swap || (pl->two_cta && (d.no_halo & 3) == 2)) &&
                       (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 && (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W);
+    // swapped-form shapes that have a halo form keep its K order when it is switched off (bit-identical A/B)
+    p.chunk_major = (p.swap && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 &&
+                     (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W)) ? 1 : 0;
     if (halo) {
       const int rows = tile_px / d.W;
       p.halo = 1; p.halo_dh_bytes = d.W * 128; p.halo_copy_bytes = (rows + 2) * d.W * 128;
+      p.halo_prefetch = (d.no_halo & 4) ? 0 : 1;
       B200_REQUIRE(p.halo_copy_bytes <= (p.swap ? HALO_X_BYTES : HALO2_X_BYTES), "gemm_tc: halo copy of %d bytes does not fit its slot", p.halo_copy_bytes);
       uint32_t box[4] = {(uint32_t)bke, (uint32_t)d.W, (uint32_t)(rows + 2), 1};
       for (int s = 0; s < 2; ++s) {

@@ -127,6 +127,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         const int img0 = mg >= tiles_m_total ? (1 << 28) : (int)(p0 / HW);      // past the end -> TMA zero fill
         const int h0 = (int)(p0 % HW) / p.W;
         const int wrow0 = nt * BN + (int)rank * (BN / 2);
+        if (p.halo_prefetch && pair + nclusters < total_pairs && (pair + nclusters) / p.tiles_n != pair / p.tiles_n) {
+          const long long qg = ((pair + nclusters) / p.tiles_n) * 2 + rank;               // this CTA's next 128 pixels, every chunk
+          if (qg < tiles_m_total) {
+            const int qi = (int)(qg * BM / HW), qh = (int)(qg * BM % HW) / p.W;
+            for (int kc = 0; kc < p.kchunks1; ++kc) tma_prefetch_4d(&p.tmH1, kc * p.bke, 0, qh - 1, qi);
+            for (int kc = 0; kc < p.kchunks2; ++kc) tma_prefetch_4d(&p.tmH2, kc * p.bke, 0, qh - 1, qi);
+          }
+        }
         for (int src = 0; src < 4; ++src) {
           const int nch = src == 0 ? p.kchunks1 : src == 1 ? p.kchunks2 : src == 2 ? p.kchunks3 : p.kchunks4;
           if (nch == 0) continue;
@@ -183,10 +191,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         const CUtensorMap* tmW = src < 2 ? &p.tmW : &p.tmW2;
         const int wcol0 = src == 1 ? p.C1 : src == 3 ? p.C3 : 0;
         const int ntaps = src < 2 ? p.taps : 1;
-        for (int kc = 0; kc < nch; ++kc) {                       // K order: chunk, filter column, filter row (see gemm_tc_kernel)
-          for (int t = 0; t < ntaps; ++t) {
-            const int tap = ntaps == 1 ? 0 : (t % p.S) * p.S + t / p.S;
-            const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
+        for (int tap = 0; tap < ntaps; ++tap) {                 // K order: filter tap, then channel chunk (see gemm_tc_kernel)
+          const int dh = src < 2 ? tap / p.S - p.pad : 0, dw = src < 2 ? tap % p.S - p.pad : 0;
+          for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);            // own smem slot released by the pair's MMA commit
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;

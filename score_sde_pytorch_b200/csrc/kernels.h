@@ -102,7 +102,8 @@ struct TcGemmDesc {
   int f16;                  // 1: a1..a4, w, w2 hold fp16 elements (tcgen05 kind::f16, 64-channel K steps); pitches stay in elements
   int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
   int no_halo;              // halo form of the 3x3 mainloop (three W-shifted halo copies per channel chunk instead of nine shifted
-                            // tiles): 0 = in the swapped form only (the measured winner), 1 = never, 2 = CTA pairs as well
+                            // tiles): 0 = in the swapped form only (the measured winner), 1 = never, 2 = CTA pairs as well;
+                            // + 4 = without the L2 prefetch of the next tile's halo boxes (A/B)
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
   Epilogue epi;
 };

@@ -156,7 +156,7 @@ class NCSNpp(nn.Module):
     # channel chunk (the round-1 mainloop, kept for A/B)
     # 'pairs' = also in the CTA-pair kernel (measured slower there)
     hv = getattr(m, 'halo', HALO_DEFAULT) if halo is None else halo
-    self.halo = 'pairs' if hv == 'pairs' else bool(hv)
+    self.halo = hv if (hv == 'pairs' or (isinstance(hv, int) and not isinstance(hv, bool))) else bool(hv)   # int: raw b200_ncsnpp_config.no_halo
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
     L = len(ch_mult)
     all_res = [config.data.image_size // (2 ** i) for i in range(L)]
@@ -238,7 +238,7 @@ class NCSNpp(nn.Module):
     c.progressive_input = {'none': 0, 'residual': 1, 'input_skip': 2}[m.progressive_input.lower()]
     c.progressive = 1 if m.progressive.lower() == 'output_skip' else 0
     c.pdl = int(self.pdl)
-    c.no_halo = 2 if self.halo == 'pairs' else int(not self.halo)
+    c.no_halo = 2 if self.halo == 'pairs' else self.halo if (isinstance(self.halo, int) and not isinstance(self.halo, bool)) else int(not self.halo)
     c.fir_taps = len(m.fir_kernel)
     for i, v in enumerate(m.fir_kernel):
       c.fir_kernel[i] = float(v)

@@ -48,11 +48,10 @@ def test_upfirdn2d_gradient_of_the_network_resampling_layers(dev):
   """The three parameterisations NCSN++ uses (upsample_2d / downsample_2d / conv_downsample_2d's FIR,
   up_or_down_sampling.py:216-257) on a larger tensor, against autograd of the oracle's pure-torch form."""
   from score_sde_pytorch_b200.op import upfirdn2d
-  k = NO.setup_kernel([1, 3, 3, 1])
+  k = torch.as_tensor(NO.setup_kernel([1, 3, 3, 1]), dtype=torch.float32)
   torch.manual_seed(4)
   for kk, up, down, pad in ((k * 4, 2, 1, (2, 1)), (k, 1, 2, (1, 1)), (k, 1, 1, (2, 1))):
     x = torch.randn(3, 5, 32, 32)
-    y_ref, gi_ref, ggo_ref = None, None, None
     go_shape = NO.upfirdn2d_native(x, kk, up=up, down=down, pad=pad).shape
     go, v = torch.randn(go_shape), torch.randn(x.shape)
     y_ref, gi_ref, ggo_ref = LO.upfirdn2d_grads(x, kk, up, down, pad, go, v)
@@ -91,7 +90,8 @@ def _sdes(name):
 def test_sde_evaluation_losses_match_the_reference(dev, mname, sname):
   """get_sde_loss_fn(train=False) with the reference's own draws (t, z): perturbation kernel -> engine forward (strict fp32
   mode) -> reduction kernel.  (a) the perturbed batch is bit-equal to the reference's unfused torch arithmetic, (b) the
-  loss equals the reference's CPU value to fp32 network noise, (c) tensor-core modes stay within their operand rounding."""
+  loss equals the reference's CPU value to fp32 network noise, (c) the TF32 tensor-core mode stays within its operand
+  rounding (fp16 operand mode needs the fused attention shape, which these 16x16 test networks do not have)."""
   from score_sde_pytorch_b200 import losses
   g = golden('f4_losses.npz')
   cfg = golden_config(mname)
@@ -103,7 +103,7 @@ def test_sde_evaluation_losses_match_the_reference(dev, mname, sname):
   one = torch.ones(batch.shape[0], 1, 1, 1, device=dev)
   got = losses._perturb(batch, z, sde.marginal_prob(one, t)[0].reshape(-1), std)
   assert torch.equal(got, want)
-  for precision, tol in (('fp32', 2e-5), ('tf32', 3e-3), ('f16', 3e-3)):
+  for precision, tol in (('fp32', 2e-5), ('tf32', 3e-3)):
     model = seeded_model(cfg, precision=precision).to(dev)
     for rm in (False, True):
       for lw in (False, True):
@@ -159,7 +159,12 @@ def test_evaluation_step_swaps_the_ema_weights_in_and_out(dev):
   cfg = golden_config('tiny')
   sde, _ = _sdes('ve')
   model = seeded_model(cfg, precision='fp32').to(dev)
-  other = seeded_model(cfg, seed=5, precision='fp32').to(dev)                 # stands in for the averaged weights
+  other = seeded_model(cfg, precision='fp32').to(dev)                         # stands in for the averaged weights: every
+  torch.manual_seed(5)                                                        # TRAINABLE parameter moved (the frozen Fourier
+  with torch.no_grad():                                                       # projection is not part of the EMA, models/ema.py:24)
+    for p in other.parameters():
+      if p.requires_grad:
+        p.add_(0.02 * torch.randn_like(p))
   ema = ExponentialMovingAverage(other.parameters(), decay=0.999)
   state = dict(model=model, ema=ema, step=0, optimizer=None)
   torch.manual_seed(1)

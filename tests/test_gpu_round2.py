@@ -309,8 +309,11 @@ def test_groupnorm_on_load_convolution_matches_the_separate_pass(dev, batch):
 def test_halo_form_network_equals_nine_load_network_batch256(dev, precision):
   """`halo=True` (default): the swapped-form 3x3 convolutions (128 output channels, 32x32 / 16x16) read three halo copies
   per channel chunk; `halo='pairs'`: the CTA-pair convolutions too; `halo=False`: one shifted tile per filter tap (the
-  round-1 mainloop).  All forms add the same products in the same order, so the three networks differ only by the
-  order of the fp64 GroupNorm atomics (the level of two runs of one plan); the plan names say which form a launch took."""
+  round-1 mainloop).  The swapped forms add the same products in the same order, so halo=True and halo=False differ only
+  by the order of the fp64 GroupNorm atomics (the level of two runs of one plan).  The pair kernel's halo form walks K
+  chunk-major, its nine-load form tap-major: 'pairs' re-rolls the 11-bit operand roundings downstream of ~1e-6 summation
+  differences, so it is held to the oracle like any plan (the bounds of the batch-256 test above), not to the other plan.
+  The plan names say which form a launch took."""
   cfg = golden_config('cifar10_ve')
   B = 256
   torch.manual_seed(19)
@@ -326,10 +329,17 @@ def test_halo_form_network_equals_nine_load_network_batch256(dev, precision):
   assert any('[swap-halo]' in n for n in names[True]) and not any('[pair256-halo]' in n for n in names[True])
   assert any('[swap-halo]' in n for n in names['pairs']) and any('[pair256-halo]' in n for n in names['pairs'])
   assert not any('halo' in n for n in names[False])
+  d = ((ys[True] - ys[False]).flatten(1).double().norm(dim=1) / ys[False].flatten(1).double().norm(dim=1))
+  print(f'halo=True vs nine-load network [{precision}] batch {B}: max rel-L2 {d.max():.3e}, {sum("halo" in n for n in names[True])} halo launches')
+  assert d.max().item() < 2e-5
+  model = seeded_model(cfg, precision=precision)
+  sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+  with torch.no_grad():
+    ref = _oracle_net(cfg, sd)(x, sigma)
   for halo in (True, 'pairs'):
-    d = ((ys[halo] - ys[False]).flatten(1).double().norm(dim=1) / ys[False].flatten(1).double().norm(dim=1))
-    print(f'halo={halo} vs nine-load network [{precision}] batch {B}: max rel-L2 {d.max():.3e}, {sum("halo" in n for n in names[halo])} halo launches')
-    assert d.max().item() < 2e-5
+    e = ((ys[halo] - ref).flatten(1).double().norm(dim=1) / ref.flatten(1).double().norm(dim=1))
+    print(f'halo={halo} vs oracle [{precision}] batch {B}: max {e.max():.3e} median {e.median():.3e}, {sum("halo" in n for n in names[halo])} halo launches')
+    assert e.max().item() < 3e-3 and e.median().item() < 1.5e-3
 
 
 def test_programmatic_dependent_launch_plan_matches_the_serialized_plan(dev):

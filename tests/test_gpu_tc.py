@@ -166,9 +166,11 @@ HALO_CASES = [c for c in CASES if c['k'] == 3 and c['W'] in (16, 32) and (c['Cou
 @pytest.mark.parametrize('case', HALO_CASES, ids=lambda c: 'B{B}_{H}x{W}_{C1}+{C2}->{Cout}_k{k}'.format(**c))
 def test_halo_mainloop_equals_nine_load_mainloop(dev, case, f16):
   """impl 1 / 2: halo form in the swapped kernel (the default plan), 6 / 7: in the CTA-pair kernel as well, 4 / 5: one
-  shifted tile load per filter tap everywhere.  Same operands, same products, and - since every form walks K as
-  (channel chunk, filter column, filter row) - the same fp32 summation order: the results must be bit-identical.  What
-  differs is the mechanism at the borders (zero fill of a shifted tile vs of a halo copy) and the operand addressing."""
+  shifted tile load per filter tap everywhere.  Same operands, same products.  Swapped form: the nine-load loop of a
+  shape that has a halo form walks K in the halo form's order (channel chunk, filter column, filter row), so on / off
+  are bit-identical.  CTA pairs: the nine-load loop walks K tap-major (measured faster), the halo form chunk-major,
+  i.e. only the fp32 summation order differs.  What differs in mechanism: zero fill of a shifted tile vs of a halo
+  copy at the borders, and the operand addressing."""
   import gpu_util
   B, H, W, C1, C2, Cout, k = (case[x] for x in ('B', 'H', 'W', 'C1', 'C2', 'Cout', 'k'))
   if f16 and (C1 % 64 or C2 % 64):
@@ -189,7 +191,10 @@ def test_halo_mainloop_equals_nine_load_mainloop(dev, case, f16):
   torch.cuda.synchronize()
   e1, e2 = (y_default - y_nine).abs().max().item(), (y_all - y_nine).abs().max().item()
   print(f'halo vs nine-load mainloop {"f16" if f16 else "tf32"} B{B} {H}x{W} {C1}+{C2}->{Cout}: max abs diff {e1:.2e} (default plan), {e2:.2e} (pairs too)')
-  assert torch.equal(y_default, y_nine) and torch.equal(y_all, y_nine)
+  assert torch.equal(y_default, y_nine)
+  assert torch.allclose(y_all, y_nine, rtol=1e-5, atol=3e-5), e2
+  if Cout == 128:
+    assert torch.equal(y_all, y_nine)            # swapped form in every mode
 
 
 SKIP_CASES = [
