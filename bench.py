@@ -578,8 +578,10 @@ def run_gpu_arm(args):
                                                                    ms_per_step=round(ms4, 4))
         del plan4, model4
         # A/B of the halo form of the 3x3 mainloop (headline: package default = swapped-form convolutions only) against one
-        # shifted tile load per filter tap, and against the halo form in the CTA-pair kernel as well
-        for hv, key in ((False, 'f16_halo_off'), ('pairs', 'f16_halo_pairs_too')):
+        # shifted tile load per filter tap IN THE HALO FORM'S K ORDER (chunk-major, bit-identical results; round 1's tap-major
+        # nine-load loop was ~5 % faster than this on those launches, profiles/r02_h1_*), and against the halo form in the
+        # CTA-pair kernel as well
+        for hv, key in ((False, 'f16_halo_off_same_k_order'), ('pairs', 'f16_halo_pairs_too')):
           torch.manual_seed(0)
           model5 = NCSNpp(cfg, precision='f16', separate_groupnorm=args.separate_groupnorm, halo=hv).to(dev)
           plan5 = native.match_pc_plan(sde=sde, model=model5, predictor=sampling.ReverseDiffusionPredictor,

@@ -141,8 +141,8 @@ typedef struct {
                                  * three W-shifted halo copies of their tile per channel chunk (csrc/gemm_tc.cu "halo form": 2.4x fewer
                                  * L2 -> shared-memory bytes than one shifted tile per filter tap; measured +5..10 % on those launches);
                                  * 1: one shifted tile per tap everywhere (the round-1 mainloop, kept for A/B); 2: halo form in the
-                                 * CTA-pair kernel as well; + 4: without the L2 prefetch of the next tile's halo
-                                 * boxes.  Swapped-form results are bit-identical in every mode (same products, same order); the
+                                 * CTA-pair kernel as well; + 4: with an L2 prefetch of the next tile's halo
+                                 * boxes (measured 2 % slower).  Swapped-form results are bit-identical in every mode (same products, same order); the
                                  * pair kernel's halo form walks K chunk-major, its nine-load form tap-major: fp32 summation order differs. */
 } b200_ncsnpp_config;
 

@@ -57,7 +57,7 @@ struct TcParams {
   int halo;                                // 1: 3x3 taps read W-shifted halo copies of the tile (3 loads per channel chunk instead of 9)
   int halo_dh_bytes;                       // W * 128: bytes between the operand windows of consecutive filter rows inside a copy
   int halo_copy_bytes;                     // (tile rows + 2) * W * 128: bytes of one halo copy
-  int halo_prefetch;                       // 1: the halo producers prefetch the next tile's halo boxes (all channel chunks) into L2
+  int halo_prefetch;                       // 1: the halo producers prefetch the next tile's halo boxes (all channel chunks) into L2 (opt-in: measured -2 %)
   int chunk_major;                         // nine-load loop of the single-CTA kernel walks K as (chunk, filter column, filter row): shapes with a halo form
   int conv, H, W, taps, pad, S, stride;   // H, W: OUTPUT spatial size; S = filter width (3 or 1)
   int kchunks1, kchunks2, C1;
@@ -951,7 +951,7 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     if (halo) {
       const int rows = tile_px / d.W;
       p.halo = 1; p.halo_dh_bytes = d.W * 128; p.halo_copy_bytes = (rows + 2) * d.W * 128;
-      p.halo_prefetch = (d.no_halo & 4) ? 0 : 1;
+      p.halo_prefetch = (d.no_halo & 4) ? 1 : 0;
       B200_REQUIRE(p.halo_copy_bytes <= (p.swap ? HALO_X_BYTES : HALO2_X_BYTES), "gemm_tc: halo copy of %d bytes does not fit its slot", p.halo_copy_bytes);
       uint32_t box[4] = {(uint32_t)bke, (uint32_t)d.W, (uint32_t)(rows + 2), 1};
       for (int s = 0; s < 2; ++s) {

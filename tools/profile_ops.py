@@ -20,7 +20,7 @@ ap.add_argument('--reps', type=int, default=5)
 ap.add_argument('--md', default=None)
 ap.add_argument('--config', default='headline', choices=['headline', 'celebahq_256', 'ddpmpp_256', 'ffhq_1024', 'cifar10_ddpmpp'])
 ap.add_argument('--no-halo', action='store_true', help='round-1 3x3 mainloop: one shifted tile load per filter tap')
-ap.add_argument('--halo-mode', type=int, default=None, help='raw b200_ncsnpp_config.no_halo (0 swap only, 1 off, 2 pairs too, +4 no L2 prefetch)')
+ap.add_argument('--halo-mode', type=int, default=None, help='raw b200_ncsnpp_config.no_halo (0 swap only, 1 off, 2 pairs too, +4 with L2 prefetch of the next tile)')
 args = ap.parse_args()
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
