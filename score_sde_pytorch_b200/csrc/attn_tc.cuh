@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
   uint64_t* y_full = o_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index provably warp-uniform
   if (threadIdx.x == 0) {
     for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(y_full, 1);
@@ -120,8 +120,9 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
   constexpr int KB = L::KB;        // K blocks in every phase (C = T = 256 elements)
   constexpr int BKA = L::BKA;
 
-  if (warp == 0 && lane == 0) {
-    // ======================= TMA producer =======================
+  if (warp == 0) {
+    // ======================= TMA producer (whole warp; one elected lane issues - see elect_one in gemm_tc.cu) =======================
+    const bool issue = elect_one();
     uint32_t stage = 0, phase = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = (int)(tile >> 1), qh = (int)(tile & 1);
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (ph == 0) {
+          if (!issue) {
+          } else if (ph == 0) {
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             tma_load_2d(&p.tmQ, sa, &full_bar[stage], kc * BKA, b * AT_T + qh * BM);
             tma_load_2d(&p.tmK, sb, &full_bar[stage], AT_C + kc * BKA, b * AT_T);
@@ -145,8 +147,9 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ======================= MMA issuer =======================
+  } else if (warp == 1) {
+    // ======================= MMA issuer (whole warp; one elected lane issues) =======================
+    const bool issue = elect_one();
     constexpr uint32_t idesc = F16 ? make_idesc_f16<256>() : make_idesc<256>();
     uint32_t stage = 0, phase = 0, tpar = 0;
     const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 256;
@@ -161,11 +164,13 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           const uint32_t sa = smem_u32(ring + stage * L::STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(ph == 0 ? sa : smem_u32(pbuf + kc * 16384));
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
-          umma_kstep<F16>(d_tmem, adesc, bdesc, idesc, kc);
-          umma_commit(&empty_bar[stage]);
+          if (issue) {
+            umma_kstep<F16>(d_tmem, adesc, bdesc, idesc, kc);
+            umma_commit(&empty_bar[stage]);
+          }
           if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(ph == 0 ? s_full : ph == 1 ? o_full : y_full);
+        if (issue) umma_commit(ph == 0 ? s_full : ph == 1 ? o_full : y_full);
       }
     }
   } else if (warp >= 4) {

@@ -173,6 +173,16 @@ __device__ __forceinline__ void umma_kstep(uint32_t d_tmem, uint64_t adesc, uint
     else umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
   }
 }
+// One lane of a converged warp (elect.sync).  The MMA issuer runs as a whole warp with its loop counters, barrier
+// addresses and descriptors warp-uniform, and only the tcgen05 instructions predicated on this: under a `lane == 0`
+// branch the compiler cannot prove a single active lane and wraps every UTCHMMA / UTCBAR in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop (~8 extra instructions per MMA), which made the issue loop - not data, not the tensor pipe - the
+// bound of every convolution (profiles/r02_h1_ncu_swap_halo.md: the issuer's samples sit on ALU latencies).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -439,7 +449,7 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
   uint64_t* wfull_bar = tmem_empty + 3;          // halo form: the weight-slice ring has its own barriers
   uint64_t* wempty_bar = wfull_bar + HALO_WS;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index provably warp-uniform
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -463,8 +473,9 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
   const int HW = p.H * p.W;
   const int bke = p.bke;
 
-  if (warp == 0 && lane == 0) {
-    // ======================= TMA producer =======================
+  if (warp == 0) {
+    // ======================= TMA producer (whole warp; one elected lane issues, see elect_one) =======================
+    const bool issue = elect_one();
     uint32_t stage = 0, phase = 0;
     if (BN == 256 && p.halo) {
       // halo form (swapped operands, one image per 256-pixel tile, W <= 32): per channel chunk three halo copies, each
@@ -476,7 +487,7 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
         const long long p0 = (tile / p.tiles_n) * 256;
         const int img0 = (int)(p0 / HW), h0 = (int)(p0 % HW) / p.W;
         const int wrow0 = nt * 128;
-        if (p.halo_prefetch && tile + gridDim.x < p.total_tiles && (tile + gridDim.x) / p.tiles_n != tile / p.tiles_n) {
+        if (issue && p.halo_prefetch && tile + gridDim.x < p.total_tiles && (tile + gridDim.x) / p.tiles_n != tile / p.tiles_n) {
           const long long q0 = ((tile + gridDim.x) / p.tiles_n) * 256;                 // next tile of this CTA: its pixels, every chunk
           const int qi = (int)(q0 / HW), qh = (int)(q0 % HW) / p.W;
           for (int kc = 0; kc < p.kchunks1; ++kc) tma_prefetch_4d(&p.tmH1, kc * bke, 0, qh - 1, qi);
@@ -491,13 +502,17 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
               const CUtensorMap* tmH = src == 0 ? &p.tmH1 : &p.tmH2;
               for (int dwi = 0; dwi < 3; ++dwi) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], (uint32_t)p.halo_copy_bytes);
-                tma_load_4d(tmH, smem + stage * HALO_X_BYTES, &full_bar[stage], kc * bke, dwi - 1, h0 - 1, img0);
+                if (issue) {
+                  mbar_expect_tx(&full_bar[stage], (uint32_t)p.halo_copy_bytes);
+                  tma_load_4d(tmH, smem + stage * HALO_X_BYTES, &full_bar[stage], kc * bke, dwi - 1, h0 - 1, img0);
+                }
                 if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
                 for (int dhi = 0; dhi < 3; ++dhi) {
                   mbar_wait(&wempty_bar[ws], wphase ^ 1);
-                  mbar_expect_tx(&wfull_bar[ws], A_STAGE_BYTES);
-                  tma_load_2d(&p.tmW, wring + ws * A_STAGE_BYTES, &wfull_bar[ws], wcol0 + kc * bke, wrow0 + (dhi * 3 + dwi) * p.N_total);
+                  if (issue) {
+                    mbar_expect_tx(&wfull_bar[ws], A_STAGE_BYTES);
+                    tma_load_2d(&p.tmW, wring + ws * A_STAGE_BYTES, &wfull_bar[ws], wcol0 + kc * bke, wrow0 + (dhi * 3 + dwi) * p.N_total);
+                  }
                   if (++ws == HALO_WS) { ws = 0; wphase ^= 1; }
                 }
               }
@@ -506,13 +521,17 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
               const CUtensorMap* tmA = src == 2 ? &p.tmA3 : &p.tmA4;
               const int h1 = h0 + 128 / p.W;
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
-              tma_load_4d(tmA, smem + stage * HALO_X_BYTES, &full_bar[stage], kc * bke, 0, h0, img0);
-              tma_load_4d(tmA, smem + stage * HALO_X_BYTES + A_STAGE_BYTES, &full_bar[stage], kc * bke, 0, h1, img0);
+              if (issue) {
+                mbar_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
+                tma_load_4d(tmA, smem + stage * HALO_X_BYTES, &full_bar[stage], kc * bke, 0, h0, img0);
+                tma_load_4d(tmA, smem + stage * HALO_X_BYTES + A_STAGE_BYTES, &full_bar[stage], kc * bke, 0, h1, img0);
+              }
               if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
               mbar_wait(&wempty_bar[ws], wphase ^ 1);
-              mbar_expect_tx(&wfull_bar[ws], A_STAGE_BYTES);
-              tma_load_2d(&p.tmW2, wring + ws * A_STAGE_BYTES, &wfull_bar[ws], wcol0 + kc * bke, wrow0);
+              if (issue) {
+                mbar_expect_tx(&wfull_bar[ws], A_STAGE_BYTES);
+                tma_load_2d(&p.tmW2, wring + ws * A_STAGE_BYTES, &wfull_bar[ws], wcol0 + kc * bke, wrow0);
+              }
               if (++ws == HALO_WS) { ws = 0; wphase ^= 1; }
             }
           }
@@ -562,24 +581,27 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-            if (p.swap) {
-              // first 16 KiB: 128 output channels x 32 k of W (UMMA A); next 32 KiB: 256 pixels x 32 k (UMMA B)
-              tma_load_2d(tmW, sa, &full_bar[stage], wcol0 + kc * bke, wrow0 + tap * p.N_total);
-              tma_load_4d(tmA, sb, &full_bar[stage], kc * bke, w0 + dw, h0 + dh, img0);
-              tma_load_4d(tmA, sb + A_STAGE_BYTES, &full_bar[stage], kc * bke, w1 + dw, h1 + dh, img1);
-            } else {
-              if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * bke, w0 * p.stride + dw, h0 * p.stride + dh, img0);
-              else tma_load_4d(tmA, sa, &full_bar[stage], kc * bke, arow0, 0, 0);
-              tma_load_2d(tmW, sb, &full_bar[stage], wcol0 + kc * bke, wrow0 + tap * p.N_total);
+            if (issue) {
+              mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+              if (p.swap) {
+                // first 16 KiB: 128 output channels x 32 k of W (UMMA A); next 32 KiB: 256 pixels x 32 k (UMMA B)
+                tma_load_2d(tmW, sa, &full_bar[stage], wcol0 + kc * bke, wrow0 + tap * p.N_total);
+                tma_load_4d(tmA, sb, &full_bar[stage], kc * bke, w0 + dw, h0 + dh, img0);
+                tma_load_4d(tmA, sb + A_STAGE_BYTES, &full_bar[stage], kc * bke, w1 + dw, h1 + dh, img1);
+              } else {
+                if (p.conv) tma_load_4d(tmA, sa, &full_bar[stage], kc * bke, w0 * p.stride + dw, h0 * p.stride + dh, img0);
+                else tma_load_4d(tmA, sa, &full_bar[stage], kc * bke, arow0, 0, 0);
+                tma_load_2d(tmW, sb, &full_bar[stage], wcol0 + kc * bke, wrow0 + tap * p.N_total);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ======================= MMA issuer =======================
+  } else if (warp == 1) {
+    // ======================= MMA issuer (whole warp; one elected lane issues) =======================
+    const bool issue = elect_one();
     const bool f16 = p.f16 != 0;
     const uint32_t idesc = f16 ? make_idesc_f16<BN>() : make_idesc<BN>();
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -605,16 +627,18 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
               tc_fence_after();
               const uint64_t adesc = make_smem_desc(wring + ws * A_STAGE_BYTES);
               const uint64_t bdesc = make_smem_desc(sx + (src < 2 ? dhi * p.halo_dh_bytes : 0));
-              if (f16) umma_kstep<true>(d_tmem, adesc, bdesc, idesc, it);
-              else umma_kstep<false>(d_tmem, adesc, bdesc, idesc, it);
-              umma_commit(&wempty_bar[ws]);
+              if (issue) {
+                if (f16) umma_kstep<true>(d_tmem, adesc, bdesc, idesc, it);
+                else umma_kstep<false>(d_tmem, adesc, bdesc, idesc, it);
+                umma_commit(&wempty_bar[ws]);
+              }
               if (++ws == HALO_WS) { ws = 0; wphase ^= 1; }
             }
-            umma_commit(&empty_bar[stage]);
+            if (issue) umma_commit(&empty_bar[stage]);
             if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (issue) umma_commit(&tmem_full[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     } else
@@ -628,12 +652,14 @@ __global__ void __maxnreg__(160) gemm_tc_kernel(const __grid_constant__ TcParams
         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(sa);
         const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
-        if (f16) umma_kstep<true>(d_tmem, adesc, bdesc, idesc, it);
-        else umma_kstep<false>(d_tmem, adesc, bdesc, idesc, it);
-        umma_commit(&empty_bar[stage]);
+        if (issue) {
+          if (f16) umma_kstep<true>(d_tmem, adesc, bdesc, idesc, it);
+          else umma_kstep<false>(d_tmem, adesc, bdesc, idesc, it);
+          umma_commit(&empty_bar[stage]);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tmem_full[acc]);
+      if (issue) umma_commit(&tmem_full[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {

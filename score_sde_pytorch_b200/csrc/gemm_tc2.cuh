@@ -83,7 +83,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   uint64_t* wempty_bar = wfull_bar + HALO2_WS;
   static_assert((2 * STAGES + 4 + 1 + 2 * HALO2_WS) * 8 <= 256 && STAGES >= HALO_XS, "barrier block");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index provably warp-uniform
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
@@ -112,8 +112,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
   const long long total_pairs = pairs_m * p.tiles_n;
   const long long cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
-    // ======================= TMA producer (both CTAs) =======================
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs; whole warp, one elected lane issues - see elect_one) =======================
+    const bool issue = elect_one();
     uint32_t stage = 0, phase = 0;
     if (p.halo) {
       // halo form (see gemm_tc_kernel): per channel chunk three halo copies of this CTA's 128 pixels (whole rows of one
@@ -127,7 +128,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         const int img0 = mg >= tiles_m_total ? (1 << 28) : (int)(p0 / HW);      // past the end -> TMA zero fill
         const int h0 = (int)(p0 % HW) / p.W;
         const int wrow0 = nt * BN + (int)rank * (BN / 2);
-        if (p.halo_prefetch && pair + nclusters < total_pairs && (pair + nclusters) / p.tiles_n != pair / p.tiles_n) {
+        if (issue && p.halo_prefetch && pair + nclusters < total_pairs && (pair + nclusters) / p.tiles_n != pair / p.tiles_n) {
           const long long qg = ((pair + nclusters) / p.tiles_n) * 2 + rank;               // this CTA's next 128 pixels, every chunk
           if (qg < tiles_m_total) {
             const int qi = (int)(qg * BM / HW), qh = (int)(qg * BM % HW) / p.W;
@@ -144,23 +145,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             for (int dwi = 0; dwi < ncopy; ++dwi) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint32_t lead = map_to_cta(smem_u32(&full_bar[stage]), 0);
-              if (src < 2) {
-                if (leader) mbar_expect_tx(&full_bar[stage], 2 * (uint32_t)p.halo_copy_bytes);
-                tma2_load_4d(src == 0 ? &p.tmH1 : &p.tmH2, smem + stage * HALO2_X_BYTES, lead, kc * p.bke, dwi - 1, h0 - 1, img0);
-              } else {
-                if (leader) mbar_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
-                tma2_load_4d(src == 2 ? &p.tmA3 : &p.tmA4, smem + stage * HALO2_X_BYTES, lead, kc * p.bke, 0, h0, img0);
+              if (issue) {
+                if (src < 2) {
+                  if (leader) mbar_expect_tx(&full_bar[stage], 2 * (uint32_t)p.halo_copy_bytes);
+                  tma2_load_4d(src == 0 ? &p.tmH1 : &p.tmH2, smem + stage * HALO2_X_BYTES, lead, kc * p.bke, dwi - 1, h0 - 1, img0);
+                } else {
+                  if (leader) mbar_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
+                  tma2_load_4d(src == 2 ? &p.tmA3 : &p.tmA4, smem + stage * HALO2_X_BYTES, lead, kc * p.bke, 0, h0, img0);
+                }
+                if (!leader) mbar_arrive_cluster(lead);
               }
-              if (!leader) mbar_arrive_cluster(lead);
               if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
               const int ntap = src < 2 ? 3 : 1;
               for (int dhi = 0; dhi < ntap; ++dhi) {
                 mbar_wait(&wempty_bar[ws], wphase ^ 1);
                 lead = map_to_cta(smem_u32(&wfull_bar[ws]), 0);
-                if (leader) mbar_expect_tx(&wfull_bar[ws], 2 * A_STAGE_BYTES);
-                if (src < 2) tma2_load_2d(&p.tmW, wring + ws * A_STAGE_BYTES, lead, wcol0 + kc * p.bke, wrow0 + (dhi * 3 + dwi) * p.N_total);
-                else tma2_load_2d(&p.tmW2, wring + ws * A_STAGE_BYTES, lead, wcol0 + kc * p.bke, wrow0);
-                if (!leader) mbar_arrive_cluster(lead);
+                if (issue) {
+                  if (leader) mbar_expect_tx(&wfull_bar[ws], 2 * A_STAGE_BYTES);
+                  if (src < 2) tma2_load_2d(&p.tmW, wring + ws * A_STAGE_BYTES, lead, wcol0 + kc * p.bke, wrow0 + (dhi * 3 + dwi) * p.N_total);
+                  else tma2_load_2d(&p.tmW2, wring + ws * A_STAGE_BYTES, lead, wcol0 + kc * p.bke, wrow0);
+                  if (!leader) mbar_arrive_cluster(lead);
+                }
                 if (++ws == HALO2_WS) { ws = 0; wphase ^= 1; }
               }
             }
@@ -198,18 +203,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
             const uint32_t lead_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);     // bytes of BOTH CTAs land on this barrier
-            if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * p.bke, w0 * p.stride + dw, h0 * p.stride + dh, img0);
-            else tma2_load_4d(tmA, sa, lead_full, kc * p.bke, arow0, 0, 0);
-            tma2_load_2d(tmW, sb, lead_full, wcol0 + kc * p.bke, wrow0 + tap * p.N_total);
-            if (!leader) mbar_arrive_cluster(lead_full);                          // second of the barrier's two arrivals
+            if (issue) {
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);     // bytes of BOTH CTAs land on this barrier
+              if (p.conv) tma2_load_4d(tmA, sa, lead_full, kc * p.bke, w0 * p.stride + dw, h0 * p.stride + dh, img0);
+              else tma2_load_4d(tmA, sa, lead_full, kc * p.bke, arow0, 0, 0);
+              tma2_load_2d(tmW, sb, lead_full, wcol0 + kc * p.bke, wrow0 + tap * p.N_total);
+              if (!leader) mbar_arrive_cluster(lead_full);                          // second of the barrier's two arrivals
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
-    // ======================= MMA issuer (leader CTA, for the pair) =======================
+  } else if (warp == 1 && leader) {
+    // ======================= MMA issuer (leader CTA, for the pair; whole warp, one elected lane issues) =======================
+    const bool issue = elect_one();
     // instruction: M = 256 (128 rows per CTA), N = BN, K = 8 tf32; D fp32 in each CTA's own TMEM
     const bool f16 = p.f16 != 0;
     const uint32_t idesc = (1u << 4) | (f16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -236,21 +244,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
               tc_fence_after();
               const uint64_t adesc = make_smem_desc(sx + (src < 2 ? dhi * p.halo_dh_bytes : 0));
               const uint64_t bdesc = make_smem_desc(wring + ws * A_STAGE_BYTES);
-              if (f16) {
+              if (issue) {
+                if (f16) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-              } else {
+                  for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                  for (int k = 0; k < 4; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                }
+                umma2_commit_mc(&wempty_bar[ws]);
               }
-              umma2_commit_mc(&wempty_bar[ws]);
               if (++ws == HALO2_WS) { ws = 0; wphase ^= 1; }
             }
-            umma2_commit_mc(&empty_bar[stage]);
+            if (issue) umma2_commit_mc(&empty_bar[stage]);
             if (++stage == HALO_XS) { stage = 0; phase ^= 1; }
           }
         }
-        umma2_commit_mc(&tmem_full[acc]);
+        if (issue) umma2_commit_mc(&tmem_full[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     } else
@@ -264,17 +274,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) gemm_tc2_ker
         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(sa);
         const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
-        if (f16) {
+        if (issue) {
+          if (f16) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-        } else {
+            for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            for (int k = 0; k < 4; ++k) umma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          }
+          umma2_commit_mc(&empty_bar[stage]);                   // frees the slot in both CTAs
         }
-        umma2_commit_mc(&empty_bar[stage]);                     // frees the slot in both CTAs
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma2_commit_mc(&tmem_full[acc]);                         // accumulator ready in both CTAs
+      if (issue) umma2_commit_mc(&tmem_full[acc]);              // accumulator ready in both CTAs
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
