@@ -577,11 +577,11 @@ def run_gpu_arm(args):
         variants['f16_pdl_' + ('off' if model.pdl else 'on')] = dict(value=round(B / (N_SAMPLER_STEPS * ms4 * 1e-3), 4), unit='images/s',
                                                                    ms_per_step=round(ms4, 4))
         del plan4, model4
-        # A/B of the halo form of the 3x3 mainloop (headline: package default = swapped-form convolutions only) against one
-        # shifted tile load per filter tap IN THE HALO FORM'S K ORDER (chunk-major, bit-identical results; round 1's tap-major
-        # nine-load loop was ~5 % faster than this on those launches, profiles/r02_h1_*), and against the halo form in the
-        # CTA-pair kernel as well
-        for hv, key in ((False, 'f16_halo_off_same_k_order'), ('pairs', 'f16_halo_pairs_too')):
+        # A/B of the halo form of the 3x3 mainloop (headline: package default = swapped AND CTA-pair kernels) against one shifted
+        # tile load per filter tap (swapped kernel: in the halo form's chunk-major K order, bit-identical results - round 1's
+        # tap-major loop was ~5 % faster than this on those launches, profiles/r02_h1_*; pair kernel: round 1's tap-major
+        # loop), and against the halo form in the swapped kernel only
+        for hv, key in ((False, 'f16_halo_off_same_k_order'), (True, 'f16_halo_swapped_kernel_only')):
           torch.manual_seed(0)
           model5 = NCSNpp(cfg, precision='f16', separate_groupnorm=args.separate_groupnorm, halo=hv).to(dev)
           plan5 = native.match_pc_plan(sde=sde, model=model5, predictor=sampling.ReverseDiffusionPredictor,

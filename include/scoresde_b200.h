@@ -142,7 +142,8 @@ typedef struct {
                                  * L2 -> shared-memory bytes than one shifted tile per filter tap; measured +5..10 % on those launches);
                                  * 1: one shifted tile per tap everywhere (the round-1 mainloop, kept for A/B); 2: halo form in the
                                  * CTA-pair kernel as well; + 4: with an L2 prefetch of the next tile's halo
-                                 * boxes (measured 2 % slower).  Swapped-form results are bit-identical in every mode (same products, same order); the
+                                 * boxes (measured 2 % slower); + 8: small launches that fall back to the single-CTA kernel walk K in the halo form's
+                                 * order, so a small-batch plan agrees bit for bit with the pair plan of a large batch (tests).  Swapped-form results are bit-identical in every mode (same products, same order); the
                                  * pair kernel's halo form walks K chunk-major, its nine-load form tap-major: fp32 summation order differs. */
 } b200_ncsnpp_config;
 

@@ -971,9 +971,13 @@ int tc_gemm_plan_create(const TcGemmDesc& d, TcGemmPlan** out) {
     const int tile_px = p.swap ? 256 : BM;
     const bool halo = (d.no_halo & 3) != 1 && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (p.swap || (pl->two_cta && (d.no_halo & 3) == 2)) &&
                       (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 && (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W);
-    // swapped-form shapes that have a halo form keep its K order when it is switched off (bit-identical A/B)
-    p.chunk_major = (p.swap && d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 &&
-                     (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W)) ? 1 : 0;
+    // swapped-form shapes that have a halo form keep its K order when it is switched off (bit-identical A/B).  `no_halo & 8`
+    // asks the same of the single-CTA row-major kernel for shapes the CTA-pair kernel would run in halo form: a small-batch
+    // plan then adds the same products in the same order as the pair plan of a large batch (plan-agreement tests; the
+    // chunk-major nine-load loop is ~30 % slower, so nothing else sets it)
+    const bool halo_shape = d.conv && d.taps == 9 && p.pad == 1 && p.stride == 1 && (d.W == 16 || d.W == 32) && (d.H * d.W) % tile_px == 0 &&
+                            (d.Hin == 0 || d.Hin == d.H) && (d.Win == 0 || d.Win == d.W);
+    p.chunk_major = (halo_shape && (p.swap || ((d.no_halo & 8) && !pl->two_cta))) ? 1 : 0;
     if (halo) {
       const int rows = tile_px / d.W;
       p.halo = 1; p.halo_dh_bytes = d.W * 128; p.halo_copy_bytes = (rows + 2) * d.W * 128;

@@ -103,7 +103,8 @@ struct TcGemmDesc {
   int no_pair;              // 1 = never use the two-CTA (cta_group::2) kernel for this launch
   int no_halo;              // halo form of the 3x3 mainloop (three W-shifted halo copies per channel chunk instead of nine shifted
                             // tiles): 0 = in the swapped form only (the measured winner), 1 = never, 2 = CTA pairs as well;
-                            // + 4 = with an L2 prefetch (UTMAPF) of the next tile's halo boxes (A/B: measured 2 % slower)
+                            // + 4 = with an L2 prefetch (UTMAPF) of the next tile's halo boxes (A/B: measured 2 % slower);
+                            // + 8 = single-CTA row-major launches of shapes the pair kernel runs in halo form walk K in that form's order
   double* qstats;           // optional GroupNorm quad sums [img][N_total/4][2] accumulated by the epilogue (mode 1)
   Epilogue epi;
 };

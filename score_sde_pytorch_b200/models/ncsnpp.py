@@ -24,7 +24,7 @@ from . import utils
 from .. import _lib
 
 PDL_DEFAULT = False
-HALO_DEFAULT = True
+HALO_DEFAULT = 'pairs'   # halo form of the 3x3 mainloop in the swapped AND the CTA-pair kernel
 
 _SUPPORTED = ("engine supports embedding_type in {'fourier','positional'}, conditional=True, resblock_type='biggan', "
               "fir in {True, False} (progressive_input='residual' needs fir=True), progressive in {'none','output_skip'}, "
@@ -152,9 +152,9 @@ class NCSNpp(nn.Module):
     self.separate_groupnorm = 2 if (not isinstance(sg, bool) and sg == 2) else bool(sg)
     # programmatic dependent launch between the kernels of a forward / PC iteration (common.cuh)
     self.pdl = bool(getattr(m, 'pdl', PDL_DEFAULT) if pdl is None else pdl)
-    # halo form of the 3x3 tensor-core mainloop (csrc/gemm_tc.cu); False = nine shifted tile loads per
-    # channel chunk (the round-1 mainloop, kept for A/B)
-    # 'pairs' = also in the CTA-pair kernel (measured slower there)
+    # halo form of the 3x3 tensor-core mainloop (csrc/gemm_tc.cu): 'pairs' (default) = in the swapped and
+    # the CTA-pair kernel, True = swapped kernel only, False = nine shifted tile loads per channel chunk (the round-1
+    # mainloop, kept for A/B); an int is the raw b200_ncsnpp_config.no_halo (tests: 2 | 8)
     hv = getattr(m, 'halo', HALO_DEFAULT) if halo is None else halo
     self.halo = hv if (hv == 'pairs' or (isinstance(hv, int) and not isinstance(hv, bool))) else bool(hv)   # int: raw b200_ncsnpp_config.no_halo
     nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks

@@ -146,7 +146,10 @@ def test_forward_batch256_pair_kernels_match_small_batch_plan_and_oracle(dev, pr
   SAMPLER output and is held by test_pc_sampler_cifar10_full_1000_steps_within_parity_bound and by bench.py's in-run
   check at batch 1024, so (b) only guards against gross errors."""
   cfg = golden_config('cifar10_ve')
-  model = seeded_model(cfg, precision=precision).to(dev)
+  # no_halo = 2 | 8: the default plan (halo form in the swapped and the pair kernel) plus "small launches that fall back to the
+  # single-CTA kernel walk K in the halo form's order" - at batch 256 that is exactly the default plan, at batch 8 it makes
+  # the single-CTA tiles add the products in the pair plan's order, which is what lets (a) demand bit equality
+  model = seeded_model(cfg, precision=precision, halo=2 | 8).to(dev)
   sd = {k: v.to(dev) for k, v in model.state_dict().items()}
   B = 256
   torch.manual_seed(9)
@@ -169,6 +172,12 @@ def test_forward_batch256_pair_kernels_match_small_batch_plan_and_oracle(dev, pr
   s1 = torch.full((B,), 3.3, device=dev)
   with torch.no_grad():
     assert rel_l2(model(x, s1, labels_uniform=True), model(x, s1)) < 2e-5
+  # and the package default is that plan: same launches, same result up to the order of the GroupNorm atomics
+  dflt = seeded_model(cfg, precision=precision).to(dev)
+  with torch.no_grad():
+    yd = dflt(x, sigma)
+  assert dflt.op_names() == model.op_names() and any('[pair256-halo]' in n for n in dflt.op_names())
+  assert rel_l2(yd, y) < 2e-5
 
 
 @pytest.mark.parametrize('case', ['tiny_fp32', 'cifar10_f16'])

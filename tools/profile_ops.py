@@ -29,7 +29,7 @@ cfg = {'headline': headline_config, 'celebahq_256': configs.ve_celebahq_256_ncsn
        'ddpmpp_256': configs.subvp_celebahq_256_ddpmpp_continuous, 'ffhq_1024': configs.ve_ffhq_1024_ncsnpp_continuous,
        'cifar10_ddpmpp': configs.vp_cifar10_ddpmpp_continuous}[args.config]()
 cfg.model.init_scale = 1.0
-model = NCSNpp(cfg, precision=args.precision, halo=(args.halo_mode if args.halo_mode is not None else not args.no_halo)).to(dev)
+model = NCSNpp(cfg, precision=args.precision, halo=(args.halo_mode if args.halo_mode is not None else False if args.no_halo else None)).to(dev)
 B = args.batch
 eng = model.engine(B, dev)
 h = eng['h']
