@@ -137,7 +137,7 @@ typedef struct {
   int pdl;                      /* 1: every launch of a forward / PC iteration carries the programmatic-dependent-launch attribute
                                  * (each kernel waits for its predecessor with griddepcontrol.wait after its own prologue, so launch
                                  * latency, barrier init and TMEM allocation of kernel k+1 overlap the tail of kernel k) */
-  int no_halo;                  /* 0 (default): swapped-form 3x3 convolutions (128 output channels) on 16- / 32-pixel-wide images read
+  int no_halo;                  /* (the Python host sets 2 unless told otherwise.)  0: swapped-form 3x3 convolutions (128 output channels) on 16- / 32-pixel-wide images read
                                  * three W-shifted halo copies of their tile per channel chunk (csrc/gemm_tc.cu "halo form": 2.4x fewer
                                  * L2 -> shared-memory bytes than one shifted tile per filter tap; measured +5..10 % on those launches);
                                  * 1: one shifted tile per tap everywhere (the round-1 mainloop, kept for A/B); 2: halo form in the
