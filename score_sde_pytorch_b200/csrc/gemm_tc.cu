@@ -16,10 +16,13 @@
 //                                      stages its own A rows and half of the W tile;
 //   attn_tc_kernel<F16>                attn_tc.cuh: QK^T, softmax, PV, NIN_3 + residual in one kernel;
 //   gemm_tc_kernel<BN, STAGES, true>   256 threads: the smem-staged TMA-store epilogue kept for A/B runs.
-// Roles: warp 0 lane 0 TMA producer (4-D box of the NHWC tensor shifted by the filter tap, zero halo and
-// tail rows from out-of-bounds fill, SWIZZLE_128B, STAGES-deep ring with full/empty mbarriers); warp 1
-// lane 0 MMA issuer (four MMAs per K step into one of two TMEM accumulator stages, tcgen05.commit frees
-// the slot / publishes the accumulator); warp 2 TMEM allocation; warps 4..11 epilogue, two per TMEM lane
+// Roles: warp 0 TMA producer (4-D box of the NHWC tensor shifted by the filter tap - or, in the halo form, three
+// W-shifted copies of the tile with its halo per channel chunk - zero halo and tail rows from out-of-bounds fill,
+// SWIZZLE_128B, ring with full/empty mbarriers); warp 1 MMA issuer (four MMAs per K step into one of two TMEM
+// accumulator stages, tcgen05.commit frees the slot / publishes the accumulator); both run as WHOLE warps whose
+// loop state is warp-uniform, with the TMA / tcgen05 instructions predicated on one elect.sync lane (see elect_one:
+// under a `lane == 0` branch every such instruction was wrapped in a lane-serialising loop and the issue loop became
+// the bound of the kernel); warp 2 TMEM allocation; warps 4..11 epilogue, two per TMEM lane
 // quarter: tcgen05.ld, then a block routine compiled per (residual, store format, stats) combination -
 // `row_chunk_t` (row-major outputs: 32x32 blocks transposed through warp-private shared memory so global
 // accesses are coalesced) or `swap_chunk` (lane = channel, already coalesced) - with bias, time-embedding

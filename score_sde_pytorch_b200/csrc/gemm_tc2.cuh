@@ -8,8 +8,8 @@
 // and only HALF of the W tile (128 of the 256 output channels); the pair's tensor cores share the two W halves,
 // so a CTA writes 32 KB and reads 32 KB per K step = 128 B/clk.
 //
-// Roles per CTA (256 threads): warp 0 lane 0 TMA producer (both CTAs; transaction bytes are accounted on the
-// leader's `full` barrier), warp 1 lane 0 of the LEADER issues tcgen05.mma.cta_group::2 for the pair and
+// Roles per CTA (384 threads): warp 0 TMA producer (both CTAs, one elect.sync lane issuing; transaction bytes are
+// accounted on the leader's `full` barrier), warp 1 of the LEADER (one elected lane) issues tcgen05.mma.cta_group::2 for the pair and
 // multicasts its commits to both CTAs' `empty` / `tmem_full` barriers, warp 2 allocates TMEM (cta_group::2),
 // warps 4..11 of each CTA drain their own 128 TMEM lanes (direct 128-bit stores, fused bias / time-embedding /
 // residual / scale / TF32 rounding / GroupNorm quad sums) and release the accumulator stage on the leader's

@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU session: halo forms with the L2 prefetch of the next tile (A/B per op, same box), the f4 tests, short bench.
+# GPU session: halo modes A/B per op on one box (profile_ops --halo-mode = raw no_halo: 0 swapped kernel only, 1 off, 2 pairs too,
+# +4 with the L2 prefetch of the next tile - at the commit of profiles/r02_h2_* the prefetch bit was inverted), f4 tests, short bench.
 #   tools/gpu_halo2.sh TAG
 TAG=${1:-h2}
 mkdir -p gpurun_out; S=gpurun_out/summary_$TAG.txt; rm -f $S
