@@ -400,3 +400,17 @@ def test_profile_tooling_reads_the_committed_artifacts():
   out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'summarize_launches.py'), csvs[-1]],
                        capture_output=True, text=True, timeout=120)
   assert out.returncode == 0 and 'gemm_tc' in out.stdout and 'gn_apply' in out.stdout
+
+
+def test_execution_options_reach_the_native_config():
+  """Per-engine options are fields of b200_ncsnpp_config (nothing is read from the environment).  `halo`: the package
+  default is the halo form in the swapped AND the CTA-pair kernel (no_halo = 2); True / False / raw ints map as documented
+  in include/scoresde_b200.h."""
+  from score_sde_pytorch_b200.models.ncsnpp import NCSNpp
+  cfg = golden_config('tiny')
+  want = {None: 2, 'pairs': 2, True: 0, False: 1, 2 | 8: 10, 6: 6}
+  for halo, no_halo in want.items():
+    m = NCSNpp(cfg) if halo is None else NCSNpp(cfg, halo=halo)
+    assert m._native_config().no_halo == no_halo, (halo, m._native_config().no_halo)
+  c = NCSNpp(cfg, precision='f16', separate_groupnorm=False, pdl=True, cuda_core_head=True)._native_config()
+  assert (c.precision, c.separate_groupnorm, c.pdl, c.cuda_core_head) == (2, 0, 1, 1)
