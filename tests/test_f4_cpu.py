@@ -8,7 +8,7 @@ from helpers import golden, golden_config, seeded_model
 from oracle import losses_oracle as LO
 from oracle import ncsnpp_oracle as NO
 from oracle import sampling_oracle as SO
-from tools_f4_cases import FIR_CASES
+from tools_f4_cases import FIR_CASES, StandIn
 
 SDES = {'ve': lambda: SO.VE(0.01, 50, 1000), 'vp': lambda: SO.VP(0.1, 20, 1000), 'subvp': lambda: SO.SubVP(0.1, 20, 1000)}
 
@@ -45,6 +45,20 @@ def test_oracle_ddpm_loss_matches_the_reference():
       loss, _ = LO.ddpm_loss(sa, sde.sqrt_1m_alphas_cumprod, net, batch, labels, z, reduce_mean=rm)
       ref = float(g[f'tiny_ddpmpp_ddpm_loss_rm{int(rm)}'])
       assert abs(loss.item() - ref) <= 2e-6 * abs(ref)
+
+
+def test_oracle_smld_loss_matches_the_reference():
+  """get_smld_loss_fn (losses.py:105-126) on a deterministic stand-in model: the loss arithmetic (descending sigma table,
+  perturbation, target -noise / sigma^2, reduction, sigma^2 weighting) is what is pinned."""
+  g = golden('f4_losses.npz')
+  sde = SO.VE(0.01, 50, 1000)
+  batch = torch.from_numpy(g['smld_batch'])
+  labels, z = torch.from_numpy(g['smld_labels']), torch.from_numpy(g['smld_z'])
+  with torch.no_grad():
+    for rm in (False, True):
+      loss, _ = LO.smld_loss(torch.flip(sde.discrete_sigmas, dims=(0,)), StandIn(), batch, labels, z, reduce_mean=rm)
+      ref = float(g[f'smld_loss_rm{int(rm)}'])
+      assert abs(loss.item() - ref) <= 2e-6 * abs(ref), (rm, loss.item(), ref)
 
 
 @pytest.mark.parametrize('case', FIR_CASES, ids=lambda c: c[0])

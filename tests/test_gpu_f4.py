@@ -8,7 +8,7 @@ from helpers import golden, golden_config, seeded_model
 from oracle import losses_oracle as LO
 from oracle import ncsnpp_oracle as NO
 from oracle import sampling_oracle as SO
-from tools_f4_cases import FIR_CASES
+from tools_f4_cases import FIR_CASES, StandIn
 
 pytestmark = pytest.mark.gpu
 
@@ -149,6 +149,31 @@ def test_ddpm_evaluation_loss_and_internal_draws(dev):
   lab = torch.randint(0, sde.N, (batch.shape[0],), device=dev)
   zz = torch.randn_like(batch)
   assert dfn(model, batch, labels=lab, z=zz).item() == b
+
+
+def test_smld_evaluation_loss_matches_the_reference(dev):
+  """get_smld_loss_fn(train=False) (losses.py:105-126) through the device kernels (perturbation with mean coefficient 1,
+  residual mode 2: score + (z sigma) / sigma^2) on the goldens' stand-in model, with the reference's own draws."""
+  from score_sde_pytorch_b200 import losses
+  g = golden('f4_losses.npz')
+  sde, _ = _sdes('ve')
+  model = StandIn().to(dev)
+  batch = torch.from_numpy(g['smld_batch']).to(dev)
+  labels, z = torch.from_numpy(g['smld_labels']).to(dev), torch.from_numpy(g['smld_z']).to(dev)
+  sig = torch.flip(sde.discrete_sigmas, dims=(0,)).to(dev)[labels]
+  assert torch.equal(losses._perturb(batch, z, None, sig), z * sig[:, None, None, None] + batch)   # noise + batch (:111-112)
+  for rm in (False, True):
+    loss = losses.get_smld_loss_fn(sde, train=False, reduce_mean=rm)(model, batch, labels=labels, z=z).item()
+    ref = float(g[f'smld_loss_rm{int(rm)}'])
+    assert abs(loss - ref) <= 2e-5 * abs(ref), (rm, loss, ref)
+  # the discrete step function picks this loss for a VE SDE (losses.py:176-183) and evaluates the EMA weights
+  from score_sde_pytorch_b200.models.ema import ExponentialMovingAverage
+  state = dict(model=model, ema=ExponentialMovingAverage(model.parameters(), decay=0.999), step=0, optimizer=None)
+  step_fn = losses.get_step_fn(sde, train=False, reduce_mean=False, continuous=False)
+  torch.manual_seed(8)
+  a = step_fn(state, batch).item()
+  torch.manual_seed(8)
+  assert losses.get_smld_loss_fn(sde, train=False, reduce_mean=False)(model, batch).item() == a
 
 
 def test_evaluation_step_swaps_the_ema_weights_in_and_out(dev):

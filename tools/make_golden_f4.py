@@ -3,8 +3,9 @@
   f4_op_grads.npz   first and second derivatives of the reference's two native ops through its own CPU forms under autograd
                     (op/upfirdn2d.py:159-200 `upfirdn2d_native`; op/fused_act.py:85-93) - what its CUDA autograd Functions
                     (op/upfirdn2d.py:19-141, op/fused_act.py:20-72) compute with the kernels
-  f4_losses.npz     losses.get_sde_loss_fn / get_ddpm_loss_fn / get_smld_loss_fn (train=False) of the reference's NCSNpp
-                    holding this repository's deterministic weights, with the draws (t / labels, z) the loss made
+  f4_losses.npz     losses.get_sde_loss_fn / get_ddpm_loss_fn (train=False) of the reference's NCSNpp holding this repository's
+                    deterministic weights, with the draws (t / labels, z) the loss made; get_smld_loss_fn on a deterministic
+                    stand-in model (the reference's positional-embedding VE network does not run on current PyTorch)
 
     python tools/make_golden_f4.py
 """
@@ -116,6 +117,34 @@ def loss_goldens(sde_lib, mutils):
   return out
 
 
+class StandIn(torch.nn.Module):
+  """A deterministic stand-in score model for the SMLD loss: the reference's own positional-embedding VE network raises a
+  dtype error on current PyTorch, and the loss arithmetic does not care what the model is."""
+
+  def forward(self, x, labels):
+    return 0.3 * torch.flip(x, dims=(3,)) + (0.001 * labels.float())[:, None, None, None] * x
+
+
+def smld_goldens(sde_lib):
+  import losses as ref_losses
+  out = {}
+  sde = sde_lib.VESDE(sigma_min=0.01, sigma_max=50, N=1000)
+  g = torch.Generator().manual_seed(33)
+  batch = torch.rand(5, 3, 8, 8, generator=g)
+  out['smld_batch'] = batch.numpy()
+  seed = 555
+  torch.manual_seed(seed)
+  labels = torch.randint(0, sde.N, (batch.shape[0],))
+  z = torch.randn_like(batch)
+  out['smld_labels'], out['smld_z'] = labels.numpy(), z.numpy()
+  for rm in (False, True):
+    fn = ref_losses.get_smld_loss_fn(sde, train=False, reduce_mean=rm)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+      out[f'smld_loss_rm{int(rm)}'] = np.float64(fn(StandIn(), batch).item())
+  return out
+
+
 def main():
   torch.set_num_threads(8)
   sde_lib, sampling, ncsnpp, mutils, _ = MG.import_reference()
@@ -124,6 +153,7 @@ def main():
   np.savez_compressed(os.path.join(MG.OUT, 'f4_op_grads.npz'), **og)
   print('op grads', len(og), 'arrays')
   lg = loss_goldens(sde_lib, mutils)
+  lg.update(smld_goldens(sde_lib))
   np.savez_compressed(os.path.join(MG.OUT, 'f4_losses.npz'), **lg)
   print({k: float(v) for k, v in lg.items() if 'loss' in k})
 
